@@ -1,0 +1,1047 @@
+/*
+ * suhmo_oracle.c -- CPU restatement of SUHMO's hydraulic-head solve hot path.  See suhmo_oracle.h.
+ * TEST INFRASTRUCTURE ONLY (checker + CPU baseline); "parity unpinned" at the Chombo boundary.
+ *
+ * Build: see oracle/Makefile (-O2 -ffp-contract=off: the reference's gfortran/x86-64 build has no
+ * FMA contraction, so neither does this file).  All citations are relative to /root/reference/.
+ */
+#include "suhmo_oracle.h"
+
+#include <math.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#ifdef _OPENMP
+#include <omp.h>
+#endif
+
+/* ------------------------------------------------------------------------------------------- */
+/* boxes                                                                                        */
+/* ------------------------------------------------------------------------------------------- */
+typedef struct { int lo[2], hi[2]; } obox;
+
+static inline int imax(int a, int b) { return a > b ? a : b; }
+static inline int imin(int a, int b) { return a < b ? a : b; }
+static inline int box_empty(const obox* b) { return b->hi[0] < b->lo[0] || b->hi[1] < b->lo[1]; }
+static inline obox box_and(obox a, obox b) {
+  obox r;
+  for (int d = 0; d < 2; d++) { r.lo[d] = imax(a.lo[d], b.lo[d]); r.hi[d] = imin(a.hi[d], b.hi[d]); }
+  return r;
+}
+static inline obox box_grow(obox a, int g) {
+  for (int d = 0; d < 2; d++) { a.lo[d] -= g; a.hi[d] += g; }
+  return a;
+}
+static inline obox box_shift(obox a, int sx, int sy) {
+  a.lo[0] += sx; a.hi[0] += sx; a.lo[1] += sy; a.hi[1] += sy;
+  return a;
+}
+/* Chombo adjCellBox(b, dir, side, 1): the 1-cell strip just outside b on that side (no corners) */
+static inline obox box_adj(obox a, int dir, int hiside) {
+  obox r = a;
+  if (hiside) { r.lo[dir] = a.hi[dir] + 1; r.hi[dir] = a.hi[dir] + 1; }
+  else        { r.lo[dir] = a.lo[dir] - 1; r.hi[dir] = a.lo[dir] - 1; }
+  return r;
+}
+static inline int box_contains(const obox* a, const obox* b) {
+  return b->lo[0] >= a->lo[0] && b->hi[0] <= a->hi[0] && b->lo[1] >= a->lo[1] && b->hi[1] <= a->hi[1];
+}
+/* floor division (Chombo coarsen semantics for negative indices) */
+static inline int fdiv(int a, int r) { return (a >= 0) ? a / r : -((-a + r - 1) / r); }
+
+/* ------------------------------------------------------------------------------------------- */
+/* layouts and copy plans                                                                       */
+/* ------------------------------------------------------------------------------------------- */
+typedef struct { int src, dst; obox reg; int sh[2]; } ocopy; /* dst(i,j) = src(i-sh0, j-sh1) on reg */
+typedef struct { int n, cap; ocopy* c; int built; } oplan;
+
+struct orc_layout {
+  int nbox;
+  obox* box;
+  obox domain;
+  int periodic[2];
+  oplan faces1;   /* 1 ghost, face strips only */
+  oplan full[4];  /* all ghosts incl. corners, index = ng (1..3) */
+};
+
+static void plan_push(oplan* p, ocopy c) {
+  if (p->n == p->cap) { p->cap = p->cap ? 2 * p->cap : 64; p->c = (ocopy*)realloc(p->c, sizeof(ocopy) * p->cap); }
+  p->c[p->n++] = c;
+}
+
+orc_layout* orc_layout_create(int nbox, const int* boxes, const int domain[4], const int periodic[2]) {
+  orc_layout* L = (orc_layout*)calloc(1, sizeof(orc_layout));
+  L->nbox = nbox;
+  L->box = (obox*)malloc(sizeof(obox) * (nbox > 0 ? nbox : 1));
+  for (int b = 0; b < nbox; b++) {
+    L->box[b].lo[0] = boxes[4 * b + 0]; L->box[b].lo[1] = boxes[4 * b + 1];
+    L->box[b].hi[0] = boxes[4 * b + 2]; L->box[b].hi[1] = boxes[4 * b + 3];
+  }
+  L->domain.lo[0] = domain[0]; L->domain.lo[1] = domain[1];
+  L->domain.hi[0] = domain[2]; L->domain.hi[1] = domain[3];
+  L->periodic[0] = periodic[0]; L->periodic[1] = periodic[1];
+  return L;
+}
+
+/* coarsen_dbl(): every box coarsened by r (src/VCAMRNonLinearPoissonOp.cpp:1060) */
+orc_layout* orc_layout_coarsen(const orc_layout* lay, int r) {
+  orc_layout* L = (orc_layout*)calloc(1, sizeof(orc_layout));
+  L->nbox = lay->nbox;
+  L->box = (obox*)malloc(sizeof(obox) * (lay->nbox > 0 ? lay->nbox : 1));
+  for (int b = 0; b < lay->nbox; b++)
+    for (int d = 0; d < 2; d++) { L->box[b].lo[d] = fdiv(lay->box[b].lo[d], r); L->box[b].hi[d] = fdiv(lay->box[b].hi[d], r); }
+  for (int d = 0; d < 2; d++) { L->domain.lo[d] = fdiv(lay->domain.lo[d], r); L->domain.hi[d] = fdiv(lay->domain.hi[d], r); }
+  L->periodic[0] = lay->periodic[0]; L->periodic[1] = lay->periodic[1];
+  return L;
+}
+
+/* DisjointBoxLayout::coarsenable(r): refine(coarsen(b,r),r)==b for every box */
+int orc_layout_coarsenable(const orc_layout* lay, int r) {
+  for (int b = 0; b < lay->nbox; b++)
+    for (int d = 0; d < 2; d++) {
+      int lo = lay->box[b].lo[d], hi = lay->box[b].hi[d];
+      if (fdiv(lo, r) * r != lo) return 0;
+      if (fdiv(hi, r) * r + r - 1 != hi) return 0;
+    }
+  return 1;
+}
+int orc_layout_nbox(const orc_layout* lay) { return lay->nbox; }
+void orc_layout_box(const orc_layout* lay, int b, int out[4]) {
+  out[0] = lay->box[b].lo[0]; out[1] = lay->box[b].lo[1]; out[2] = lay->box[b].hi[0]; out[3] = lay->box[b].hi[1];
+}
+void orc_layout_free(orc_layout* L) {
+  if (!L) return;
+  free(L->faces1.c);
+  for (int i = 0; i < 4; i++) free(L->full[i].c);
+  free(L->box);
+  free(L);
+}
+
+/* spatial bins so plan construction is ~O(nbox) instead of O(nbox^2) */
+typedef struct { int S, nbx, nby, ox, oy; int* start; int* items; } obins;
+static void bins_build(obins* B, const orc_layout* L) {
+  int S = 1;
+  for (int b = 0; b < L->nbox; b++) {
+    S = imax(S, L->box[b].hi[0] - L->box[b].lo[0] + 1);
+    S = imax(S, L->box[b].hi[1] - L->box[b].lo[1] + 1);
+  }
+  B->S = S; B->ox = L->domain.lo[0]; B->oy = L->domain.lo[1];
+  B->nbx = (L->domain.hi[0] - L->domain.lo[0]) / S + 1;
+  B->nby = (L->domain.hi[1] - L->domain.lo[1]) / S + 1;
+  int nb = B->nbx * B->nby;
+  int* cnt = (int*)calloc(nb + 1, sizeof(int));
+  for (int pass = 0; pass < 2; pass++) {
+    if (pass == 1) {
+      B->start = (int*)malloc(sizeof(int) * (nb + 1));
+      B->start[0] = 0;
+      for (int k = 0; k < nb; k++) B->start[k + 1] = B->start[k] + cnt[k];
+      B->items = (int*)malloc(sizeof(int) * (B->start[nb] > 0 ? B->start[nb] : 1));
+      memset(cnt, 0, sizeof(int) * (nb + 1));
+    }
+    for (int b = 0; b < L->nbox; b++) {
+      int bx0 = (L->box[b].lo[0] - B->ox) / S, bx1 = (L->box[b].hi[0] - B->ox) / S;
+      int by0 = (L->box[b].lo[1] - B->oy) / S, by1 = (L->box[b].hi[1] - B->oy) / S;
+      for (int by = by0; by <= by1; by++)
+        for (int bx = bx0; bx <= bx1; bx++) {
+          int k = by * B->nbx + bx;
+          if (pass == 1) B->items[B->start[k] + cnt[k]] = b;
+          cnt[k]++;
+        }
+    }
+  }
+  free(cnt);
+}
+static void bins_free(obins* B) { free(B->start); free(B->items); }
+
+/* add to plan every piece of `want` (a region of ghost cells of box d) covered by a valid box, including
+   periodic images (ProblemDomain shifts).  Restates what a Chombo Copier holds. */
+static void plan_cover(oplan* P, const orc_layout* L, const obins* B, int d, obox want) {
+  int nxd = L->domain.hi[0] - L->domain.lo[0] + 1, nyd = L->domain.hi[1] - L->domain.lo[1] + 1;
+  for (int py = -1; py <= 1; py++) {
+    if (py != 0 && !L->periodic[1]) continue;
+    for (int px = -1; px <= 1; px++) {
+      if (px != 0 && !L->periodic[0]) continue;
+      /* a source box s shifted by (px*nxd, py*nyd) covers part of want <=> s covers want shifted back */
+      obox w = box_shift(want, -px * nxd, -py * nyd);
+      obox wd = box_and(w, L->domain);
+      if (box_empty(&wd)) continue;
+      int bx0 = (wd.lo[0] - B->ox) / B->S, bx1 = (wd.hi[0] - B->ox) / B->S;
+      int by0 = (wd.lo[1] - B->oy) / B->S, by1 = (wd.hi[1] - B->oy) / B->S;
+      for (int by = by0; by <= by1; by++)
+        for (int bx = bx0; bx <= bx1; bx++) {
+          int k = by * B->nbx + bx;
+          for (int it = B->start[k]; it < B->start[k + 1]; it++) {
+            int s = B->items[it];
+            if (s == d && px == 0 && py == 0) continue;
+            obox ov = box_and(w, L->box[s]);
+            if (box_empty(&ov)) continue;
+            /* a box spanning several bins is visited more than once: keep only the visit from the
+               bin that holds the overlap's low corner */
+            int kbx = (ov.lo[0] - B->ox) / B->S, kby = (ov.lo[1] - B->oy) / B->S;
+            if (kbx < bx0) kbx = bx0;
+            if (kby < by0) kby = by0;
+            if (kbx != bx || kby != by) continue;
+            ocopy c;
+            c.src = s; c.dst = d;
+            c.reg = box_shift(ov, px * nxd, py * nyd);
+            c.sh[0] = px * nxd; c.sh[1] = py * nyd;
+            plan_push(P, c);
+          }
+        }
+    }
+  }
+}
+
+static void plan_build(orc_layout* L, oplan* P, int ng, int corners) {
+  obins B;
+  bins_build(&B, L);
+  for (int d = 0; d < L->nbox; d++) {
+    if (corners) {
+      /* grown box minus valid box, split into 4 disjoint slabs */
+      obox v = L->box[d], g = box_grow(v, ng), s;
+      s = g; s.hi[1] = v.lo[1] - 1; plan_cover(P, L, &B, d, s);               /* bottom rows (with corners) */
+      s = g; s.lo[1] = v.hi[1] + 1; plan_cover(P, L, &B, d, s);               /* top rows */
+      s = g; s.lo[1] = v.lo[1]; s.hi[1] = v.hi[1]; s.hi[0] = v.lo[0] - 1; plan_cover(P, L, &B, d, s);
+      s = g; s.lo[1] = v.lo[1]; s.hi[1] = v.hi[1]; s.lo[0] = v.hi[0] + 1; plan_cover(P, L, &B, d, s);
+    } else {
+      for (int dir = 0; dir < 2; dir++)
+        for (int side = 0; side < 2; side++) plan_cover(P, L, &B, d, box_adj(L->box[d], dir, side));
+    }
+  }
+  bins_free(&B);
+  P->built = 1;
+}
+
+/* ------------------------------------------------------------------------------------------- */
+/* fields                                                                                       */
+/* ------------------------------------------------------------------------------------------- */
+struct orc_field {
+  const orc_layout* lay;
+  int ncomp, ng, cent;
+  double** d;   /* per box */
+  obox* ab;     /* per box: index box of the array (ghosts and face extension included) */
+};
+
+static inline obox array_box(obox valid, int ng, int cent) {
+  obox a = box_grow(valid, ng);
+  if (cent == ORC_XFACE) a.hi[0] += 1;
+  if (cent == ORC_YFACE) a.hi[1] += 1;
+  return a;
+}
+#define NXOF(a) ((a).hi[0] - (a).lo[0] + 1)
+#define NYOF(a) ((a).hi[1] - (a).lo[1] + 1)
+/* element (i,j,c) of box b of field f */
+#define AT(f, b, i, j, c) \
+  ((f)->d[b][((size_t)(c) * NYOF((f)->ab[b]) + (size_t)((j) - (f)->ab[b].lo[1])) * NXOF((f)->ab[b]) + (size_t)((i) - (f)->ab[b].lo[0])])
+
+orc_field* orc_field_create(const orc_layout* lay, int ncomp, int ng, int centering) {
+  orc_field* f = (orc_field*)calloc(1, sizeof(orc_field));
+  f->lay = lay; f->ncomp = ncomp; f->ng = ng; f->cent = centering;
+  f->d = (double**)calloc(lay->nbox > 0 ? lay->nbox : 1, sizeof(double*));
+  f->ab = (obox*)calloc(lay->nbox > 0 ? lay->nbox : 1, sizeof(obox));
+  for (int b = 0; b < lay->nbox; b++) {
+    f->ab[b] = array_box(lay->box[b], ng, centering);
+    size_t n = (size_t)NXOF(f->ab[b]) * NYOF(f->ab[b]) * ncomp;
+    f->d[b] = (double*)calloc(n, sizeof(double));
+  }
+  return f;
+}
+void orc_field_free(orc_field* f) {
+  if (!f) return;
+  for (int b = 0; b < f->lay->nbox; b++) free(f->d[b]);
+  free(f->d); free(f->ab); free(f);
+}
+double* orc_field_fab(orc_field* f, int b, int dims[3], int lo[2]) {
+  if (dims) { dims[0] = NXOF(f->ab[b]); dims[1] = NYOF(f->ab[b]); dims[2] = f->ncomp; }
+  if (lo) { lo[0] = f->ab[b].lo[0]; lo[1] = f->ab[b].lo[1]; }
+  return f->d[b];
+}
+void orc_field_setval(orc_field* f, double v) {
+  for (int b = 0; b < f->lay->nbox; b++) {
+    size_t n = (size_t)NXOF(f->ab[b]) * NYOF(f->ab[b]) * f->ncomp;
+    for (size_t k = 0; k < n; k++) f->d[b][k] = v;
+  }
+}
+void orc_field_copy(orc_field* dst, const orc_field* src) {
+#pragma omp parallel for schedule(static)
+  for (int b = 0; b < dst->lay->nbox; b++) {
+    size_t n = (size_t)NXOF(dst->ab[b]) * NYOF(dst->ab[b]) * dst->ncomp;
+    memcpy(dst->d[b], src->d[b], n * sizeof(double));
+  }
+}
+
+/* valid region of box b in the field's own centering (faces of the valid cells for face data) */
+static inline obox valid_box(const orc_field* f, int b) { return array_box(f->lay->box[b], 0, f->cent); }
+
+/* ------------------------------------------------------------------------------------------- */
+/* exchange (absent Chombo: LevelData::exchange + Copier)               */
+/* ------------------------------------------------------------------------------------------- */
+static void run_plan(orc_field* f, const oplan* P) {
+  /* every ghost cell has exactly one writer, so copies can run concurrently */
+#pragma omp parallel for schedule(static)
+  for (int k = 0; k < P->n; k++) {
+    const ocopy* c = &P->c[k];
+    for (int comp = 0; comp < f->ncomp; comp++)
+      for (int j = c->reg.lo[1]; j <= c->reg.hi[1]; j++)
+        for (int i = c->reg.lo[0]; i <= c->reg.hi[0]; i++)
+          AT(f, c->dst, i, j, comp) = AT(f, c->src, i - c->sh[0], j - c->sh[1], comp);
+  }
+}
+/* phi.exchange(interval, m_exchangeCopier) with exchangeDefine(grids, Unit) + trimEdges
+   (src/VCAMRNonLinearPoissonOp.cpp:911-913): 1-cell face strips, no corners. */
+void orc_exchange_faces(orc_field* f) {
+  orc_layout* L = (orc_layout*)f->lay;
+  if (f->cent != ORC_CELL || f->ng < 1) return;
+  if (!L->faces1.built) plan_build(L, &L->faces1, 1, 0);
+  run_plan(f, &L->faces1);
+}
+/* plain ld.exchange(): every ghost cell (corners too) covered by another box or a periodic image */
+void orc_exchange_full(orc_field* f) {
+  orc_layout* L = (orc_layout*)f->lay;
+  if (f->cent != ORC_CELL || f->ng < 1) return; /* 0-ghost FluxBox exchange is a no-op (bcoefCoar.exchange()) */
+  if (f->ng > 3) { fprintf(stderr, "orc_exchange_full: ng>3 unsupported\n"); abort(); }
+  if (!L->full[f->ng].built) plan_build(L, &L->full[f->ng], f->ng, 1);
+  run_plan(f, &L->full[f->ng]);
+}
+
+/* ------------------------------------------------------------------------------------------- */
+/* physical BCs: mixBCValues (src/AmrHydro.cpp:248-309) over Chombo DiriBC(order 1)/NeumBC      */
+/* ------------------------------------------------------------------------------------------- */
+void orc_apply_bc(orc_field* f, const orc_bc* bc, const double dx[2], int homogeneous) {
+  const orc_layout* L = f->lay;
+#pragma omp parallel for schedule(static)
+  for (int b = 0; b < L->nbox; b++) {
+    /* if(!a_domain.domainBox().contains(a_state.box())) */
+    if (box_contains(&L->domain, &f->ab[b])) continue;
+    obox valid = L->box[b];
+    for (int dir = 0; dir < 2; dir++) {
+      if (L->periodic[dir]) continue;
+      for (int side = 0; side < 2; side++) {
+        obox gb = box_adj(valid, dir, side);
+        if (box_contains(&L->domain, &gb)) continue;
+        int type = side ? bc->hi_type[dir] : bc->lo_type[dir];
+        double val = side ? bc->hi_val[dir] : bc->lo_val[dir];
+        int isign = side ? 1 : -1;
+        obox to = box_and(gb, f->ab[b]);
+        for (int c = 0; c < f->ncomp; c++)
+          for (int j = to.lo[1]; j <= to.hi[1]; j++)
+            for (int i = to.lo[0]; i <= to.hi[0]; i++) {
+              int in = i - (dir == 0 ? isign : 0), jn = j - (dir == 1 ? isign : 0);
+              double nearVal = AT(f, b, in, jn, c);
+              double inhomogVal = homogeneous ? 0.0 : val;
+              if (type == 0) {
+                /* DiriBC order 1: linearInterp = 2*inhomogVal - nearVal */
+                AT(f, b, i, j, c) = 2 * inhomogVal - nearVal;
+              } else if (type == 1) {
+                /* NeumBC: nearVal + sign(side)*dx*inhomogVal */
+                AT(f, b, i, j, c) = nearVal + isign * dx[dir] * inhomogVal;
+              }
+              /* other types (Robin = 2): mixBCValues does nothing */
+            }
+      }
+    }
+  }
+}
+
+/* util/ExtrapGhostCells.cpp:94-179 + util/ExtrapBCF.ChF:7-33 (SIMPLEEXTRAPBC), cell-centred data */
+static void ghost_fill_domain(orc_field* f, int copy_only) {
+  const orc_layout* L = f->lay;
+  int rad = f->ng;
+#pragma omp parallel for schedule(static)
+  for (int b = 0; b < L->nbox; b++) {
+    for (int dir = 0; dir < 2; dir++) {
+      if (L->periodic[dir]) continue;
+      int odir = 1 - dir;
+      /* lo side, one strip at a time moving outwards */
+      obox strip = box_adj(L->domain, dir, 0);
+      strip.lo[odir] -= rad; strip.hi[odir] += rad; /* grow(rad); grow(dir,-rad) */
+      for (int s = 0; s < rad; s++) {
+        obox g = box_and(strip, f->ab[b]);
+        if (!box_empty(&g))
+          for (int c = 0; c < f->ncomp; c++)
+            for (int j = g.lo[1]; j <= g.hi[1]; j++)
+              for (int i = g.lo[0]; i <= g.hi[0]; i++) {
+                int i1 = i + (dir == 0), j1 = j + (dir == 1), i2 = i + 2 * (dir == 0), j2 = j + 2 * (dir == 1);
+                AT(f, b, i, j, c) = copy_only ? AT(f, b, i1, j1, c) : 2.0 * AT(f, b, i1, j1, c) - AT(f, b, i2, j2, c);
+              }
+        strip.lo[dir] -= 1; strip.hi[dir] -= 1;
+      }
+      /* hi side: adjCellHi(domain, dir, rad), grown by 1 tangentially, done in one sweep */
+      obox gh = L->domain;
+      gh.lo[dir] = L->domain.hi[dir] + 1; gh.hi[dir] = L->domain.hi[dir] + rad;
+      gh.lo[odir] -= 1; gh.hi[odir] += 1;
+      gh = box_and(gh, f->ab[b]);
+      if (!box_empty(&gh))
+        for (int c = 0; c < f->ncomp; c++)
+          for (int j = gh.lo[1]; j <= gh.hi[1]; j++)
+            for (int i = gh.lo[0]; i <= gh.hi[0]; i++) {
+              int i1 = i - (dir == 0), j1 = j - (dir == 1), i2 = i - 2 * (dir == 0), j2 = j - 2 * (dir == 1);
+              AT(f, b, i, j, c) = copy_only ? AT(f, b, i1, j1, c) : 2.0 * AT(f, b, i1, j1, c) - AT(f, b, i2, j2, c);
+            }
+    }
+  }
+}
+void orc_extrap_ghost(orc_field* f) { ghost_fill_domain(f, 0); }
+void orc_copy_ghost(orc_field* f) { ghost_fill_domain(f, 1); }
+
+/* ------------------------------------------------------------------------------------------- */
+/* centering changes (absent Chombo CellToEdge / EdgeToCell)            */
+/* ------------------------------------------------------------------------------------------- */
+void orc_cell_to_edge(const orc_field* cell, orc_field* ex, orc_field* ey) {
+  const orc_layout* L = cell->lay;
+#pragma omp parallel for schedule(static)
+  for (int b = 0; b < L->nbox; b++) {
+    obox v = L->box[b];
+    for (int j = v.lo[1]; j <= v.hi[1]; j++)
+      for (int i = v.lo[0]; i <= v.hi[0] + 1; i++) AT(ex, b, i, j, 0) = 0.5 * (AT(cell, b, i, j, 0) + AT(cell, b, i - 1, j, 0));
+    for (int j = v.lo[1]; j <= v.hi[1] + 1; j++)
+      for (int i = v.lo[0]; i <= v.hi[0]; i++) AT(ey, b, i, j, 0) = 0.5 * (AT(cell, b, i, j, 0) + AT(cell, b, i, j - 1, 0));
+  }
+}
+/* cell(comp = dir) = half*(edge_dir(i) + edge_dir(i+e_dir)) on valid cells */
+void orc_edge_to_cell(const orc_field* ex, const orc_field* ey, orc_field* cell2) {
+  const orc_layout* L = cell2->lay;
+#pragma omp parallel for schedule(static)
+  for (int b = 0; b < L->nbox; b++) {
+    obox v = L->box[b];
+    for (int j = v.lo[1]; j <= v.hi[1]; j++)
+      for (int i = v.lo[0]; i <= v.hi[0]; i++) {
+        AT(cell2, b, i, j, 0) = 0.5 * (AT(ex, b, i, j, 0) + AT(ex, b, i + 1, j, 0));
+        AT(cell2, b, i, j, 1) = 0.5 * (AT(ey, b, i, j, 0) + AT(ey, b, i, j + 1, 0));
+      }
+  }
+}
+
+/* NEWMACGRAD, normal derivative branch (util/GradientF.ChF:55-70), on the faces of each valid box
+   (util/Gradient.cpp:110-121: "only do this in interior of grid") */
+void orc_mac_gradient(orc_field* phi, const orc_field* mask, const double dx[2], orc_field* gx, orc_field* gy) {
+  const orc_layout* L = phi->lay;
+  int hasMask = (mask != NULL);
+#pragma omp parallel for schedule(static)
+  for (int b = 0; b < L->nbox; b++) {
+    obox v = L->box[b];
+    double fx = 1.0 / dx[0], fy = 1.0 / dx[1];
+    for (int j = v.lo[1]; j <= v.hi[1]; j++)
+      for (int i = v.lo[0]; i <= v.hi[0] + 1; i++) {
+        if (hasMask && (AT(mask, b, i, j, 0) < 1E-6 || AT(mask, b, i - 1, j, 0) < 1E-6)) AT(gx, b, i, j, 0) = 0.0;
+        else AT(gx, b, i, j, 0) = fx * (AT(phi, b, i, j, 0) - AT(phi, b, i - 1, j, 0));
+      }
+    for (int j = v.lo[1]; j <= v.hi[1] + 1; j++)
+      for (int i = v.lo[0]; i <= v.hi[0]; i++) {
+        if (hasMask && (AT(mask, b, i, j, 0) < 1E-6 || AT(mask, b, i, j - 1, 0) < 1E-6)) AT(gy, b, i, j, 0) = 0.0;
+        else AT(gy, b, i, j, 0) = fy * (AT(phi, b, i, j, 0) - AT(phi, b, i, j - 1, 0));
+      }
+  }
+}
+
+/* DIVERGENCE (util/DivergenceF.ChF:23-57): div += (u_hi - u_lo)/dx per direction.  Dead code in the
+   reference (no call site), restated because the north-star names it. */
+void orc_divergence(const orc_field* ux, const orc_field* uy, const double dx[2], orc_field* div) {
+  const orc_layout* L = div->lay;
+#pragma omp parallel for schedule(static)
+  for (int b = 0; b < L->nbox; b++) {
+    obox v = L->box[b];
+    double ox = 1.0 / dx[0], oy = 1.0 / dx[1];
+    for (int j = v.lo[1]; j <= v.hi[1]; j++)
+      for (int i = v.lo[0]; i <= v.hi[0]; i++) {
+        AT(div, b, i, j, 0) = AT(div, b, i, j, 0) + ox * (AT(ux, b, i + 1, j, 0) - AT(ux, b, i, j, 0));
+        AT(div, b, i, j, 0) = AT(div, b, i, j, 0) + oy * (AT(uy, b, i, j + 1, 0) - AT(uy, b, i, j, 0));
+      }
+  }
+}
+
+/* HydroIBC::setup_iceMask_EC (src/HydroIBC.cpp:138-184) */
+void orc_icemask_ec(const orc_field* mask, orc_field* mx, orc_field* my) {
+  const orc_layout* L = mask->lay;
+#pragma omp parallel for schedule(static)
+  for (int b = 0; b < L->nbox; b++) {
+    obox v = L->box[b];
+    for (int dir = 0; dir < 2; dir++) {
+      orc_field* m = dir == 0 ? mx : my;
+      int flo = L->domain.lo[dir], fhi = L->domain.hi[dir] + 1; /* face_box small/big end */
+      for (int j = v.lo[1]; j <= v.hi[1] + (dir == 1); j++)
+        for (int i = v.lo[0]; i <= v.hi[0] + (dir == 0); i++) {
+          double a = AT(mask, b, i, j, 0), am1 = AT(mask, b, i - (dir == 0), j - (dir == 1), 0), r;
+          if (fabs(a - am1) < 1e-10) r = (a > 0.0) ? 1.0 : -1.0;
+          else r = 0.0;
+          int idx = dir == 0 ? i : j;
+          if (idx == flo) r = 0.0;
+          if (idx == fhi) r = 0.0;
+          AT(m, b, i, j, 0) = r;
+        }
+    }
+  }
+}
+
+/* CoarseAverage::averageToCoarse, arithmetic (absent Chombo FORT_AVERAGE; appendix C.6): sum of the r*r fine
+   cells, i fastest, divided by r^2.  Same-box layouts (coarse = coarsen(fine layout, r)). */
+void orc_coarse_average(const orc_field* fine, orc_field* coarse, int r) {
+  const orc_layout* Lc = coarse->lay;
+#pragma omp parallel for schedule(static)
+  for (int b = 0; b < Lc->nbox; b++) {
+    obox v = Lc->box[b];
+    double refScale = (double)(r * r);
+    for (int c = 0; c < coarse->ncomp; c++)
+      for (int jc = v.lo[1]; jc <= v.hi[1]; jc++)
+        for (int ic = v.lo[0]; ic <= v.hi[0]; ic++) {
+          double s = 0.0;
+          for (int jj = 0; jj < r; jj++)
+            for (int ii = 0; ii < r; ii++) s = s + AT(fine, b, ic * r + ii, jc * r + jj, c);
+          AT(coarse, b, ic, jc, c) = s / refScale;
+        }
+  }
+}
+/* CoarseAverageFace::averageToCoarse, arithmetic: mean of the r fine faces lying on each coarse face */
+void orc_coarse_average_face(const orc_field* fine, orc_field* coarse, int r) {
+  const orc_layout* Lc = coarse->lay;
+  int dir = coarse->cent == ORC_XFACE ? 0 : 1;
+#pragma omp parallel for schedule(static)
+  for (int b = 0; b < Lc->nbox; b++) {
+    obox v = valid_box(coarse, b);
+    double refScale = (double)r;
+    for (int jc = v.lo[1]; jc <= v.hi[1]; jc++)
+      for (int ic = v.lo[0]; ic <= v.hi[0]; ic++) {
+        double s = 0.0;
+        for (int k = 0; k < r; k++) {
+          int fi = dir == 0 ? ic * r : ic * r + k;
+          int fj = dir == 0 ? jc * r + k : jc * r;
+          s = s + AT(fine, b, fi, fj, 0);
+        }
+        AT(coarse, b, ic, jc, 0) = s / refScale;
+      }
+  }
+}
+
+/* ------------------------------------------------------------------------------------------- */
+/* pointwise physics (src/AmrHydroF.ChF)                                                        */
+/* ------------------------------------------------------------------------------------------- */
+/* COMPUTENONLINEARTERMS (src/AmrHydroF.ChF:23-68); literals 1000.0*9.8 as in the source.
+   NonLinear_level (src/AmrHydro.cpp:1542-1574): skipped when !use_NL -> we define NL=dNL=0. */
+static inline void nl_terms(const orc_params* p, double phi, double B, double IM, double Pi, double zb, double* nl, double* dnl) {
+  if (!p->use_NL) { *nl = 0.0; *dnl = 0.0; return; }
+  if (IM < 0.0) { *nl = 0.0; *dnl = 0.0; return; }
+  double P = Pi - 1000.0 * 9.8 * (phi - zb);
+  double n = -p->A * B * P * P * P;
+  double d = 3.0 * p->A * B * 1000.0 * 9.8 * P * P;
+  if (p->cutOffbr > B) {
+    n = n * (1.0 - (p->cutOffbr - B) / p->cutOffbr);
+    d = d * B / p->cutOffbr;
+  }
+  if (p->maxOffbr < B) {
+    n = n * (1.0 - (p->maxOffbr - B) / p->maxOffbr);
+    d = d * B / p->maxOffbr;
+  }
+  *nl = n; *dnl = d;
+}
+void orc_compute_nl(const orc_params* p, const orc_field* phi, const orc_field* B, const orc_field* mask,
+                    const orc_field* Pi, const orc_field* zb, orc_field* nl, orc_field* dnl) {
+  const orc_layout* L = phi->lay;
+#pragma omp parallel for schedule(static)
+  for (int b = 0; b < L->nbox; b++) {
+    obox v = L->box[b];
+    for (int j = v.lo[1]; j <= v.hi[1]; j++)
+      for (int i = v.lo[0]; i <= v.hi[0]; i++)
+        nl_terms(p, AT(phi, b, i, j, 0), AT(B, b, i, j, 0), AT(mask, b, i, j, 0), AT(Pi, b, i, j, 0), AT(zb, b, i, j, 0),
+                 &AT(nl, b, i, j, 0), &AT(dnl, b, i, j, 0));
+  }
+}
+/* COMPUTERE (src/AmrHydroF.ChF:81-112), over the ghosted box (src/AmrHydro.cpp:1497) */
+void orc_compute_re(const orc_params* p, const orc_field* B, const orc_field* gradH, orc_field* Re) {
+  const orc_layout* L = B->lay;
+#pragma omp parallel for schedule(static)
+  for (int b = 0; b < L->nbox; b++) {
+    obox a = Re->ab[b];
+    for (int j = a.lo[1]; j <= a.hi[1]; j++)
+      for (int i = a.lo[0]; i <= a.hi[0]; i++) {
+        double gx = AT(gradH, b, i, j, 0), gy = AT(gradH, b, i, j, 1), Bc = AT(B, b, i, j, 0);
+        double sq = sqrt(gx * gx + gy * gy);
+        double discr = 1.0 + 4.0 * p->omega * (Bc * Bc * Bc * 9.8 * sq) / (12.0 * p->nu * p->nu);
+        AT(Re, b, i, j, 0) = (-1.0 + sqrt(discr)) / (2.0 * p->omega);
+      }
+  }
+}
+/* COMPUTEBCOEFF (src/AmrHydroF.ChF:199-231) */
+static inline double bcoeff(const orc_params* p, double Bec, double Reec, double IMec) {
+  double num_q = -(Bec * Bec * Bec * 9.8);
+  double denom_q = 12.0 * p->nu * (1.0 + p->omega * Reec);
+  if ((IMec < 0.0) && (p->cutOffBcoef > 0)) return 0.0;
+  return num_q / denom_q;
+}
+
+/* ------------------------------------------------------------------------------------------- */
+/* vector ops over valid cells (LevelDataOps; src/AMRNonLinearPoissonOp.cpp:519-688)            */
+/* ------------------------------------------------------------------------------------------- */
+#define FOR_VALID(f, b, i, j, c)                       \
+  for (int c = 0; c < (f)->ncomp; c++)                 \
+    for (int j = (f)->lay->box[b].lo[1]; j <= (f)->lay->box[b].hi[1]; j++) \
+      for (int i = (f)->lay->box[b].lo[0]; i <= (f)->lay->box[b].hi[0]; i++)
+
+void orc_set_to_zero(orc_field* f) { orc_field_setval(f, 0.0); } /* LevelDataOps::setToZero: whole FAB */
+void orc_assign(orc_field* dst, const orc_field* src) {
+  /* LevelDataOps::assign = a_rhs.copyTo(a_lhs): valid cells */
+#pragma omp parallel for schedule(static)
+  for (int b = 0; b < dst->lay->nbox; b++) FOR_VALID(dst, b, i, j, c) AT(dst, b, i, j, c) = AT(src, b, i, j, c);
+}
+void orc_incr(orc_field* lhs, const orc_field* x, double scale) {
+#pragma omp parallel for schedule(static)
+  for (int b = 0; b < lhs->lay->nbox; b++) FOR_VALID(lhs, b, i, j, c) AT(lhs, b, i, j, c) = AT(lhs, b, i, j, c) + scale * AT(x, b, i, j, c);
+}
+void orc_axby(orc_field* lhs, const orc_field* x, const orc_field* y, double a, double b_) {
+#pragma omp parallel for schedule(static)
+  for (int b = 0; b < lhs->lay->nbox; b++) FOR_VALID(lhs, b, i, j, c) AT(lhs, b, i, j, c) = a * AT(x, b, i, j, c) + b_ * AT(y, b, i, j, c);
+}
+void orc_scale(orc_field* f, double s) {
+#pragma omp parallel for schedule(static)
+  for (int b = 0; b < f->lay->nbox; b++) FOR_VALID(f, b, i, j, c) AT(f, b, i, j, c) = AT(f, b, i, j, c) * s;
+}
+double orc_dot(const orc_field* a, const orc_field* b_) {
+  double s = 0.0;
+  for (int b = 0; b < a->lay->nbox; b++) FOR_VALID(a, b, i, j, c) s += AT(a, b, i, j, c) * AT(b_, b, i, j, c);
+  return s;
+}
+/* Chombo norm(): p=0 max|x|, p=1 sum|x|, p=2 sqrt(sum x^2); unweighted (src/AMRNonLinearPoissonOp.cpp:660-666) */
+double orc_norm(const orc_field* f, int p) {
+  double r = 0.0;
+  if (p == 0) {
+#pragma omp parallel for schedule(static) reduction(max : r)
+    for (int b = 0; b < f->lay->nbox; b++) FOR_VALID(f, b, i, j, c) { double v = fabs(AT(f, b, i, j, c)); if (v > r) r = v; }
+    return r;
+  }
+  for (int b = 0; b < f->lay->nbox; b++) FOR_VALID(f, b, i, j, c) {
+    double v = fabs(AT(f, b, i, j, c));
+    r += (p == 1) ? v : v * v;
+  }
+  return p == 1 ? r : sqrt(r);
+}
+
+/* ------------------------------------------------------------------------------------------- */
+/* the operator                                                                                 */
+/* ------------------------------------------------------------------------------------------- */
+struct orc_op {
+  const orc_layout* lay;
+  double dx[2], alpha, beta;
+  orc_bc bc;
+  orc_params prm;
+  orc_field *aCoef, *bX, *bY, *B, *Pi, *zb, *mask; /* shared (RefCountedPtr in the reference) */
+  orc_field* lambda;
+  orc_field *nl, *dnl; /* reference allocates these per call (VCAMRNonLinearPoissonOp.cpp:126-127); kept here */
+  int lambda_dirty;
+};
+
+orc_op* orc_op_create(const orc_layout* lay, const double dx[2], double alpha, double beta,
+                      const orc_bc* bc, const orc_params* prm,
+                      orc_field* aCoef, orc_field* bX, orc_field* bY,
+                      orc_field* B, orc_field* Pi, orc_field* zb, orc_field* mask) {
+  orc_op* op = (orc_op*)calloc(1, sizeof(orc_op));
+  op->lay = lay; op->dx[0] = dx[0]; op->dx[1] = dx[1]; op->alpha = alpha; op->beta = beta;
+  op->bc = *bc; op->prm = *prm;
+  op->aCoef = aCoef; op->bX = bX; op->bY = bY; op->B = B; op->Pi = Pi; op->zb = zb; op->mask = mask;
+  op->lambda = orc_field_create(lay, 1, 0, ORC_CELL);
+  op->nl = orc_field_create(lay, 1, 0, ORC_CELL);
+  op->dnl = orc_field_create(lay, 1, 0, ORC_CELL);
+  op->lambda_dirty = 1;
+  orc_op_reset_lambda(op); /* computeLambda() in MGnewOp/AMRnewOp */
+  return op;
+}
+void orc_op_free(orc_op* op) {
+  if (!op) return;
+  orc_field_free(op->lambda); orc_field_free(op->nl); orc_field_free(op->dnl);
+  free(op);
+}
+orc_field* orc_op_lambda(orc_op* op) { return op->lambda; }
+
+/* resetLambda (src/VCAMRNonLinearPoissonOp.cpp:505-534) + SUMFACESNL (VCAMRNonLinearPoissonOpF.ChF:574-601):
+   lambda = alpha*a; for dir: lambda += scale*beta*(b(i+e)+b(i)), scale = 1/(dx*dx).  The diagonal itself. */
+void orc_op_reset_lambda(orc_op* op) {
+  if (!op->lambda_dirty) return;
+  const orc_layout* L = op->lay;
+#pragma omp parallel for schedule(static)
+  for (int b = 0; b < L->nbox; b++) {
+    obox v = L->box[b];
+    double s0 = 1.0 / (op->dx[0] * op->dx[0]), s1 = 1.0 / (op->dx[1] * op->dx[1]);
+    for (int j = v.lo[1]; j <= v.hi[1]; j++)
+      for (int i = v.lo[0]; i <= v.hi[0]; i++) {
+        double lam = AT(op->aCoef, b, i, j, 0) * op->alpha;
+        double sumVal = AT(op->bX, b, i + 1, j, 0) + AT(op->bX, b, i, j, 0);
+        lam = lam + s0 * op->beta * sumVal;
+        sumVal = AT(op->bY, b, i, j + 1, 0) + AT(op->bY, b, i, j, 0);
+        lam = lam + s1 * op->beta * sumVal;
+        AT(op->lambda, b, i, j, 0) = lam;
+      }
+  }
+  op->lambda_dirty = 0;
+}
+
+/* L(phi) at one cell, Fortran evaluation order of VCNLCOMPUTEOP2D / GSRBHELMHOLTZVCNL2D */
+#define LOFPHI(op, phi, b, i, j, dxi0, dxi1, nlv)                                                          \
+  ((op)->alpha * AT((op)->aCoef, b, i, j, 0) * AT(phi, b, i, j, 0) -                                       \
+   (op)->beta * (AT((op)->bX, b, (i) + 1, j, 0) * (AT(phi, b, (i) + 1, j, 0) - AT(phi, b, i, j, 0)) * (dxi0) - \
+                 AT((op)->bX, b, i, j, 0) * (AT(phi, b, i, j, 0) - AT(phi, b, (i)-1, j, 0)) * (dxi0) +      \
+                 AT((op)->bY, b, i, (j) + 1, 0) * (AT(phi, b, i, (j) + 1, 0) - AT(phi, b, i, j, 0)) * (dxi1) - \
+                 AT((op)->bY, b, i, j, 0) * (AT(phi, b, i, j, 0) - AT(phi, b, i, (j)-1, 0)) * (dxi1)) +      \
+   (nlv))
+
+static void op_nl(orc_op* op, const orc_field* phi) {
+  orc_compute_nl(&op->prm, phi, op->B, op->mask, op->Pi, op->zb, op->nl, op->dnl);
+}
+
+/* levelGSRB (src/VCAMRNonLinearPoissonOp.cpp:654-760) + GSRBHELMHOLTZVCNL2D (VCAMRNonLinearPoissonOpF.ChF:46-168) */
+static void level_gsrb(orc_op* op, orc_field* phi, const orc_field* rhs) {
+  const orc_layout* L = op->lay;
+  orc_op_reset_lambda(op);
+  for (int whichPass = 0; whichPass <= 1; whichPass++) {
+    orc_exchange_faces(phi);
+    orc_apply_bc(phi, &op->bc, op->dx, 0);
+    op_nl(op, phi);
+#pragma omp parallel for schedule(static)
+    for (int b = 0; b < L->nbox; b++) {
+      obox v = L->box[b];
+      double dxinv0 = 1.0 / (op->dx[0] * op->dx[0]), dxinv1 = 1.0 / (op->dx[1] * op->dx[1]);
+      for (int j = v.lo[1]; j <= v.hi[1]; j++) {
+        int imin_ = v.lo[0];
+        int indtot = imin_ + j;
+        imin_ = imin_ + abs((indtot + whichPass) % 2);
+        for (int i = imin_; i <= v.hi[0]; i += 2) {
+          double lofphi = LOFPHI(op, phi, b, i, j, dxinv0, dxinv1, AT(op->nl, b, i, j, 0));
+          double denom = 1.0e-16 + AT(op->lambda, b, i, j, 0) + AT(op->dnl, b, i, j, 0);
+          AT(phi, b, i, j, 0) = AT(phi, b, i, j, 0) + (AT(rhs, b, i, j, 0) - lofphi) / denom;
+        }
+      }
+    }
+  }
+  orc_exchange_faces(phi);
+  orc_apply_bc(phi, &op->bc, op->dx, 1); /* homogeneous fill, src/VCAMRNonLinearPoissonOp.cpp:757-759 */
+}
+/* relax (src/AMRNonLinearPoissonOp.cpp:707-750), s_relaxMode = 1 */
+void orc_op_relax(orc_op* op, orc_field* phi, const orc_field* rhs, int iterations) {
+  for (int it = 0; it < iterations; it++) level_gsrb(op, phi, rhs);
+}
+
+/* residualI (src/VCAMRNonLinearPoissonOp.cpp:98-167) + VCNLCOMPUTERES2D (VCAMRNonLinearPoissonOpF.ChF:319-406) */
+void orc_op_residual(orc_op* op, orc_field* res, orc_field* phi, const orc_field* rhs) {
+  const orc_layout* L = op->lay;
+  orc_apply_bc(phi, &op->bc, op->dx, 0);
+  orc_exchange_faces(phi);
+  op_nl(op, phi);
+#pragma omp parallel for schedule(static)
+  for (int b = 0; b < L->nbox; b++) {
+    obox v = L->box[b];
+    double dxinv0 = 1.0 / (op->dx[0] * op->dx[0]), dxinv1 = 1.0 / (op->dx[1] * op->dx[1]);
+    for (int j = v.lo[1]; j <= v.hi[1]; j++)
+      for (int i = v.lo[0]; i <= v.hi[0]; i++)
+        AT(res, b, i, j, 0) = AT(rhs, b, i, j, 0) - (LOFPHI(op, phi, b, i, j, dxinv0, dxinv1, AT(op->nl, b, i, j, 0)));
+  }
+}
+/* applyOpI + applyOpNoBoundary (src/VCAMRNonLinearPoissonOp.cpp:273-345) + VCNLCOMPUTEOP2D (ChF:201-284) */
+void orc_op_apply(orc_op* op, orc_field* lhs, orc_field* phi, int homogeneous) {
+  const orc_layout* L = op->lay;
+  orc_apply_bc(phi, &op->bc, op->dx, homogeneous);
+  orc_exchange_faces(phi);
+  op_nl(op, phi);
+#pragma omp parallel for schedule(static)
+  for (int b = 0; b < L->nbox; b++) {
+    obox v = L->box[b];
+    double dxinv0 = 1.0 / (op->dx[0] * op->dx[0]), dxinv1 = 1.0 / (op->dx[1] * op->dx[1]);
+    for (int j = v.lo[1]; j <= v.hi[1]; j++)
+      for (int i = v.lo[0]; i <= v.hi[0]; i++)
+        AT(lhs, b, i, j, 0) = LOFPHI(op, phi, b, i, j, dxinv0, dxinv1, AT(op->nl, b, i, j, 0));
+  }
+}
+/* restrictResidual, 5-arg FAS form with phiCoarse == NULL (src/VCAMRNonLinearPoissonOp.cpp:384-460)
+   + RESTRICTRESVCNL2D (ChF:480-561): res_c = 0; res_c(i/2,j/2) += (rhs - L phi)/4, fine cells in i-fastest order */
+void orc_op_restrict_residual(orc_op* op, orc_field* resCoarse, orc_field* phiFine, const orc_field* rhsFine) {
+  const orc_layout* L = op->lay;
+  orc_apply_bc(phiFine, &op->bc, op->dx, 0);
+  orc_exchange_faces(phiFine);
+  op_nl(op, phiFine);
+#pragma omp parallel for schedule(static)
+  for (int b = 0; b < L->nbox; b++) {
+    obox v = L->box[b];
+    double dxinv0 = 1.0 / (op->dx[0] * op->dx[0]), dxinv1 = 1.0 / (op->dx[1] * op->dx[1]);
+    double denom = 2 * 2;
+    { /* res.setVal(0.0): whole coarse FAB */
+      size_t n = (size_t)NXOF(resCoarse->ab[b]) * NYOF(resCoarse->ab[b]);
+      for (size_t k = 0; k < n; k++) resCoarse->d[b][k] = 0.0;
+    }
+    for (int j = v.lo[1]; j <= v.hi[1]; j++)
+      for (int i = v.lo[0]; i <= v.hi[0]; i++) {
+        int ii = fdiv(i, 2), jj = fdiv(j, 2);
+        double lofphi = LOFPHI(op, phiFine, b, i, j, dxinv0, dxinv1, AT(op->nl, b, i, j, 0));
+        AT(resCoarse, b, ii, jj, 0) = AT(resCoarse, b, ii, jj, 0) + (AT(rhsFine, b, i, j, 0) - lofphi) / denom;
+      }
+  }
+}
+/* restrictR (src/VCAMRNonLinearPoissonOp.cpp:347-372) + RESTRICTVCNL (ChF:419-449) */
+void orc_op_restrict_r(orc_op* op, orc_field* phiCoarse, const orc_field* phiFine) {
+  const orc_layout* L = op->lay;
+#pragma omp parallel for schedule(static)
+  for (int b = 0; b < L->nbox; b++) {
+    obox v = L->box[b];
+    double denom = 2 * 2;
+    { /* phiCoarse.setVal(0.0): ghosts too */
+      size_t n = (size_t)NXOF(phiCoarse->ab[b]) * NYOF(phiCoarse->ab[b]);
+      for (size_t k = 0; k < n; k++) phiCoarse->d[b][k] = 0.0;
+    }
+    for (int j = v.lo[1]; j <= v.hi[1]; j++)
+      for (int i = v.lo[0]; i <= v.hi[0]; i++) {
+        int ii = fdiv(i, 2), jj = fdiv(j, 2);
+        AT(phiCoarse, b, ii, jj, 0) = AT(phiCoarse, b, ii, jj, 0) + (AT(phiFine, b, i, j, 0)) / denom;
+      }
+  }
+}
+/* prolongIncrement (src/AMRNonLinearPoissonOp.cpp:856-886) + PROLONGNL (AMRNonLinearPoissonOpF.ChF:607-632), m = 2 */
+void orc_op_prolong_increment(orc_op* op, orc_field* phiFine, const orc_field* corrCoarse) {
+  const orc_layout* L = op->lay;
+#pragma omp parallel for schedule(static)
+  for (int b = 0; b < L->nbox; b++) {
+    obox v = L->box[b];
+    for (int j = v.lo[1]; j <= v.hi[1]; j++)
+      for (int i = v.lo[0]; i <= v.hi[0]; i++)
+        AT(phiFine, b, i, j, 0) = AT(phiFine, b, i, j, 0) + AT(corrCoarse, b, fdiv(i, 2), fdiv(j, 2), 0);
+  }
+}
+
+/* UpdateOperator (src/VCAMRNonLinearPoissonOp.cpp:34-64) with WFlx_level (src/AmrHydro.cpp:1415-1539),
+   no coarser level (a_phicoarsePtr == NULL). */
+void orc_op_update_operator(orc_op* op, orc_field* phi) {
+  const orc_layout* L = op->lay;
+  orc_exchange_faces(phi);
+  orc_apply_bc(phi, &op->bc, op->dx, 0);
+
+  /* compGradientCC (util/Gradient.cpp:478-624): MAC gradient on valid-box faces, then EdgeToCell */
+  orc_field* gx = orc_field_create(L, 1, 1, ORC_XFACE);
+  orc_field* gy = orc_field_create(L, 1, 1, ORC_YFACE);
+  orc_field* gradH = orc_field_create(L, 2, phi->ng, ORC_CELL);
+  orc_mac_gradient(phi, op->prm.use_mask_grad ? op->mask : NULL, op->dx, gx, gy);
+  orc_edge_to_cell(gx, gy, gradH);
+  orc_exchange_full(gradH);
+  orc_extrap_ghost(gradH);
+
+  orc_field* Re = orc_field_create(L, 1, phi->ng, ORC_CELL);
+  orc_compute_re(&op->prm, op->B, gradH, Re);
+
+  orc_field* Bx = orc_field_create(L, 1, 0, ORC_XFACE);
+  orc_field* By = orc_field_create(L, 1, 0, ORC_YFACE);
+  orc_field* Rx = orc_field_create(L, 1, 0, ORC_XFACE);
+  orc_field* Ry = orc_field_create(L, 1, 0, ORC_YFACE);
+  orc_field* Mx = orc_field_create(L, 1, 0, ORC_XFACE);
+  orc_field* My = orc_field_create(L, 1, 0, ORC_YFACE);
+  orc_cell_to_edge(Re, Rx, Ry);
+  orc_cell_to_edge(op->B, Bx, By);
+  orc_icemask_ec(op->mask, Mx, My);
+#pragma omp parallel for schedule(static)
+  for (int b = 0; b < L->nbox; b++) {
+    obox v = L->box[b];
+    for (int j = v.lo[1]; j <= v.hi[1]; j++)
+      for (int i = v.lo[0]; i <= v.hi[0] + 1; i++)
+        AT(op->bX, b, i, j, 0) = bcoeff(&op->prm, AT(Bx, b, i, j, 0), AT(Rx, b, i, j, 0), AT(Mx, b, i, j, 0));
+    for (int j = v.lo[1]; j <= v.hi[1] + 1; j++)
+      for (int i = v.lo[0]; i <= v.hi[0]; i++)
+        AT(op->bY, b, i, j, 0) = bcoeff(&op->prm, AT(By, b, i, j, 0), AT(Ry, b, i, j, 0), AT(My, b, i, j, 0));
+  }
+  orc_field_free(gx); orc_field_free(gy); orc_field_free(gradH); orc_field_free(Re);
+  orc_field_free(Bx); orc_field_free(By); orc_field_free(Rx); orc_field_free(Ry); orc_field_free(Mx); orc_field_free(My);
+  op->lambda_dirty = 1;
+  orc_op_reset_lambda(op);
+}
+
+/* AverageOperator (src/VCAMRNonLinearPoissonOp.cpp:66-95): bCoef = CoarseAverageFace(finest bCoef, 2^depth) */
+void orc_op_average_operator(orc_op* op, const orc_op* finest, int depth) {
+  int coarsening = 1;
+  for (int i = 0; i < depth; i++) coarsening *= 2;
+  if (coarsening != 1) {
+    orc_coarse_average_face(finest->bX, op->bX, coarsening);
+    orc_coarse_average_face(finest->bY, op->bY, coarsening);
+  }
+  /* bcoefCoar.exchange(): 0-ghost FluxBox -> nothing to do */
+  op->lambda_dirty = 1;
+  orc_op_reset_lambda(op);
+}
+
+/* ------------------------------------------------------------------------------------------- */
+/* factory (MGnewOp) + FAS multigrid driver, single AMR level                                   */
+/* ------------------------------------------------------------------------------------------- */
+#define ORC_MAXDEPTH 32
+struct orc_solver {
+  int ndepth;
+  orc_layout* lay[ORC_MAXDEPTH]; /* [0] borrowed */
+  orc_op* op[ORC_MAXDEPTH];
+  /* owned coefficient sets for depth >= 1 */
+  orc_field *aCoef[ORC_MAXDEPTH], *bX[ORC_MAXDEPTH], *bY[ORC_MAXDEPTH], *B[ORC_MAXDEPTH], *Pi[ORC_MAXDEPTH], *zb[ORC_MAXDEPTH], *mask[ORC_MAXDEPTH];
+  /* MG work vectors for depth >= 1 */
+  orc_field *phi[ORC_MAXDEPTH], *rhs[ORC_MAXDEPTH], *save[ORC_MAXDEPTH], *tmp[ORC_MAXDEPTH];
+  orc_field* resid; /* depth 0 residual */
+  int update_operator;
+};
+
+/* NeumBCForB (src/VCAMRNonLinearPoissonOp.cpp:1309-1341) */
+static void neum_bc_for_b(orc_field* f) {
+  const orc_layout* L = f->lay;
+  for (int b = 0; b < L->nbox; b++) {
+    if (box_contains(&L->domain, &f->ab[b])) continue;
+    for (int dir = 0; dir < 2; dir++) {
+      if (L->periodic[dir]) continue;
+      for (int side = 0; side < 2; side++) {
+        obox gb = box_adj(L->box[b], dir, side);
+        if (box_contains(&L->domain, &gb) || !box_contains(&f->ab[b], &gb)) continue;
+        int isign = side ? 1 : -1;
+        for (int j = gb.lo[1]; j <= gb.hi[1]; j++)
+          for (int i = gb.lo[0]; i <= gb.hi[0]; i++)
+            AT(f, b, i, j, 0) = AT(f, b, i - (dir == 0 ? isign : 0), j - (dir == 1 ? isign : 0), 0);
+      }
+    }
+  }
+}
+
+/* VCAMRNonLinearPoissonOpFactory::define + MGnewOp for depth = 0,1,... until NULL
+   (src/VCAMRNonLinearPoissonOp.cpp:877-953,1016-1181) as MultiGrid::define drives it. */
+orc_solver* orc_solver_create(const orc_layout* lay, const double dx[2], double alpha, double beta,
+                              const orc_bc* bc, const orc_params* prm,
+                              orc_field* aCoef, orc_field* bX, orc_field* bY,
+                              orc_field* B, orc_field* Pi, orc_field* zb, orc_field* mask) {
+  orc_solver* s = (orc_solver*)calloc(1, sizeof(orc_solver));
+  s->update_operator = prm->bcoeff_otf;
+  s->lay[0] = (orc_layout*)lay;
+  s->op[0] = orc_op_create(lay, dx, alpha, beta, bc, prm, aCoef, bX, bY, B, Pi, zb, mask);
+  s->ndepth = 1;
+  s->resid = orc_field_create(lay, 1, 0, ORC_CELL);
+  const int s_maxCoarse = 2; /* src/AMRNonLinearPoissonOp.cpp:32 */
+  for (int depth = 1; depth < ORC_MAXDEPTH; depth++) {
+    int coarsening = 1 << depth;
+    if (!orc_layout_coarsenable(lay, coarsening * s_maxCoarse)) break; /* MGnewOp returns NULL */
+    orc_layout* Lc = orc_layout_coarsen(lay, coarsening);
+    double dxc[2] = {dx[0] * coarsening, dx[1] * coarsening};
+    s->lay[depth] = Lc;
+    s->aCoef[depth] = orc_field_create(Lc, 1, aCoef->ng, ORC_CELL);
+    s->bX[depth] = orc_field_create(Lc, 1, bX->ng, ORC_XFACE);
+    s->bY[depth] = orc_field_create(Lc, 1, bY->ng, ORC_YFACE);
+    s->B[depth] = orc_field_create(Lc, 1, B->ng, ORC_CELL);
+    s->Pi[depth] = orc_field_create(Lc, 1, Pi->ng, ORC_CELL);
+    s->zb[depth] = orc_field_create(Lc, 1, zb->ng, ORC_CELL);
+    s->mask[depth] = orc_field_create(Lc, 1, mask->ng, ORC_CELL);
+    /* arithmetic averages of the FINEST data by 2^depth (:1130-1139) */
+    orc_coarse_average(aCoef, s->aCoef[depth], coarsening);
+    orc_coarse_average_face(bX, s->bX[depth], coarsening);
+    orc_coarse_average_face(bY, s->bY[depth], coarsening);
+    orc_coarse_average(B, s->B[depth], coarsening);
+    orc_coarse_average(Pi, s->Pi[depth], coarsening);
+    orc_coarse_average(zb, s->zb[depth], coarsening);
+    orc_coarse_average(mask, s->mask[depth], coarsening);
+    /* fork's CoarseAverage(ghost) fills coarse ghosts from neighbours ("seems to do the perio fine"), then NeumBCForB */
+    orc_exchange_full(s->B[depth]); orc_exchange_full(s->Pi[depth]); orc_exchange_full(s->zb[depth]); orc_exchange_full(s->mask[depth]);
+    neum_bc_for_b(s->B[depth]);
+    s->op[depth] = orc_op_create(Lc, dxc, alpha, beta, bc, prm, s->aCoef[depth], s->bX[depth], s->bY[depth],
+                                 s->B[depth], s->Pi[depth], s->zb[depth], s->mask[depth]);
+    s->phi[depth] = orc_field_create(Lc, 1, 1, ORC_CELL);
+    s->rhs[depth] = orc_field_create(Lc, 1, 0, ORC_CELL);
+    s->save[depth] = orc_field_create(Lc, 1, 1, ORC_CELL);
+    s->tmp[depth] = orc_field_create(Lc, 1, 0, ORC_CELL);
+    s->ndepth = depth + 1;
+  }
+  return s;
+}
+void orc_solver_free(orc_solver* s) {
+  if (!s) return;
+  orc_op_free(s->op[0]);
+  orc_field_free(s->resid);
+  for (int d = 1; d < s->ndepth; d++) {
+    orc_op_free(s->op[d]);
+    orc_field_free(s->aCoef[d]); orc_field_free(s->bX[d]); orc_field_free(s->bY[d]); orc_field_free(s->B[d]);
+    orc_field_free(s->Pi[d]); orc_field_free(s->zb[d]); orc_field_free(s->mask[d]);
+    orc_field_free(s->phi[d]); orc_field_free(s->rhs[d]); orc_field_free(s->save[d]); orc_field_free(s->tmp[d]);
+    orc_layout_free(s->lay[d]);
+  }
+  free(s);
+}
+int orc_solver_depth(const orc_solver* s) { return s->ndepth; }
+orc_op* orc_solver_op(orc_solver* s, int depth) { return s->op[depth]; }
+
+/* MultiGrid::cycle in FAS form (absent fork; SURVEY.md 3.3 pseudo-code; INFERRED pieces flagged):
+   - [inferred] AverageOperator(op[0], depth+1) is applied before anything at depth+1 is evaluated, so the FAS
+     coarse right-hand side and the coarse relaxation see the same operator;
+   - [inferred] the bottom "solve" under FAS is relax(numBottom) (VCAMRNonLinearPoissonOp.cpp:173). */
+static void mg_cycle(orc_solver* s, int depth, orc_field* phi, const orc_field* rhs, const orc_solver_params* sp) {
+  orc_op* op = s->op[depth];
+  if (depth == s->ndepth - 1) {
+    orc_op_relax(op, phi, rhs, sp->bottom);
+    return;
+  }
+  orc_op_relax(op, phi, rhs, sp->pre);
+  int dc = depth + 1;
+  if (s->update_operator) orc_op_average_operator(s->op[dc], s->op[0], dc);
+  orc_op_restrict_r(op, s->phi[dc], phi);
+  orc_field_copy(s->save[dc], s->phi[dc]); /* assignLocal */
+  orc_op_restrict_residual(op, s->rhs[dc], phi, rhs);
+  orc_op_apply(s->op[dc], s->tmp[dc], s->phi[dc], 0); /* applyOpMg(lhs, phiC, NULL, false) */
+  orc_incr(s->rhs[dc], s->tmp[dc], 1.0);
+  mg_cycle(s, dc, s->phi[dc], s->rhs[dc], sp);
+  orc_axby(s->save[dc], s->phi[dc], s->save[dc], 1.0, -1.0); /* corr = phiC_new - phiC_saved */
+  orc_op_prolong_increment(op, phi, s->save[dc]);
+  orc_op_relax(op, phi, rhs, sp->post);
+}
+
+/* AMRFASMultiGrid::VCycle at ilev == lbase == 0: UpdateOperator then the MG cycle */
+void orc_solver_vcycle(orc_solver* s, orc_field* phi, const orc_field* rhs, const orc_solver_params* sp, int iter) {
+  (void)iter;
+  if (s->update_operator) orc_op_update_operator(s->op[0], phi);
+  mg_cycle(s, 0, phi, rhs, sp);
+}
+
+/* computeAMRResidual: max-norm of rhs - L(phi) */
+static double amr_residual_norm(orc_solver* s, orc_field* phi, const orc_field* rhs) {
+  orc_op_residual(s->op[0], s->resid, phi, rhs);
+  return orc_norm(s->resid, 0);
+}
+
+/* AMRMultiGrid::solveNoInitResid stop logic (stock Chombo 3.2) with the fork's m_imin / m_iterMin */
+int orc_solver_solve(orc_solver* s, orc_field* phi, const orc_field* rhs, const orc_solver_params* sp, double* resnorm) {
+  double initial_rnorm = amr_residual_norm(s, phi, rhs);
+  double rnorm = initial_rnorm, norm_last = 2 * initial_rnorm;
+  int iter = 0;
+  if (resnorm) resnorm[0] = initial_rnorm;
+  if (sp->fixed_cycles > 0) {
+    for (iter = 0; iter < sp->fixed_cycles; iter++) {
+      orc_solver_vcycle(s, phi, rhs, sp, iter);
+      rnorm = amr_residual_norm(s, phi, rhs);
+      if (resnorm) resnorm[iter + 1] = rnorm;
+    }
+    return iter;
+  }
+  int goNorm = rnorm > sp->norm_thresh;
+  int goRedu = rnorm > sp->eps * initial_rnorm;
+  int goIter = iter < sp->max_iter;
+  int goHang = iter < sp->imin || rnorm < (1 - sp->hang) * norm_last;
+  int goMin = iter < sp->iter_min;
+  while (goMin || (goIter && goRedu && goHang && goNorm)) {
+    norm_last = rnorm;
+    orc_solver_vcycle(s, phi, rhs, sp, iter);
+    iter++;
+    rnorm = amr_residual_norm(s, phi, rhs);
+    if (resnorm) resnorm[iter] = rnorm;
+    goNorm = rnorm > sp->norm_thresh;
+    goRedu = rnorm > sp->eps * initial_rnorm;
+    goIter = iter < sp->max_iter;
+    goHang = iter < sp->imin || rnorm < (1 - sp->hang) * norm_last;
+    goMin = iter < sp->iter_min;
+  }
+  return iter;
+}
+
+static double layout_cells(const orc_layout* L) {
+  double n = 0;
+  for (int b = 0; b < L->nbox; b++) n += (double)(L->box[b].hi[0] - L->box[b].lo[0] + 1) * (L->box[b].hi[1] - L->box[b].lo[1] + 1);
+  return n;
+}
+double orc_solver_cell_updates(const orc_solver* s, const orc_solver_params* sp) {
+  double n = 0;
+  for (int d = 0; d < s->ndepth; d++) n += layout_cells(s->lay[d]) * (d == s->ndepth - 1 ? sp->bottom : sp->pre + sp->post);
+  return n;
+}
+
+void orc_set_threads(int n) {
+#ifdef _OPENMP
+  omp_set_num_threads(n);
+#else
+  (void)n;
+#endif
+}

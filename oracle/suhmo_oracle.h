@@ -1,0 +1,141 @@
+/*
+ * suhmo_oracle.h -- CPU restatement (plain C) of SUHMO's hydraulic-head solve hot path.
+ *
+ * TEST INFRASTRUCTURE ONLY.  Nothing under suhmo_b200/ may include, link or call this.
+ * Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs use it,
+ * and only as the checker / CPU baseline -- never as the product path.
+ *
+ * PARITY UNPINNED at the Chombo boundary: the reference ships no golden vectors, known-answer
+ * tests or fixtures for this path and cannot be built here (no gfortran,
+ * MPI, HDF5 or Chombo).  This file restates, operation by operation and in the Fortran
+ * evaluation order, the in-tree kernels
+ *     src/VCAMRNonLinearPoissonOpF.ChF, src/AMRNonLinearPoissonOpF.ChF:607-741,
+ *     src/AmrHydroF.ChF, util/GradientF.ChF, util/ExtrapBCF.ChF, util/DivergenceF.ChF
+ * and the C++ orchestration in src/VCAMRNonLinearPoissonOp.cpp, src/AMRNonLinearPoissonOp.cpp,
+ * src/AmrHydro.cpp:248-309,666-769,1415-1574, util/Gradient.cpp, util/ExtrapGhostCells.cpp,
+ * src/HydroIBC.cpp:138-184.  Pieces that live in the absent Chombo fork
+ * (EnnaDelfen/Chombo_3.2, branch feature_SUHMO, unpinned: mk/CloneChombo.sh:7) -- exchange,
+ * DiriBC/NeumBC, CellToEdge/EdgeToCell, CoarseAverage[Face], the FAS V-cycle driver -- are
+ * restated from the published Chombo 3.2 design; each such function says so.
+ *
+ * Data model mirrors Chombo: a level is a DisjointBoxLayout (list of boxes) over a ProblemDomain;
+ * a field is one Fortran-ordered (i fastest) array per box, grown by `ng` ghost cells.
+ */
+#ifndef SUHMO_ORACLE_H
+#define SUHMO_ORACLE_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct orc_layout orc_layout;
+typedef struct orc_field orc_field;
+typedef struct orc_op orc_op;
+typedef struct orc_solver orc_solver;
+
+/* suhmo.* / solver.* keys used inside the hot path (src/suhmo_params.cpp:56-71, src/AmrHydro.cpp:864-884) */
+typedef struct orc_params {
+  double A;          /* suhmo.A */
+  double cutOffbr;   /* suhmo.cutOffbr */
+  double maxOffbr;   /* suhmo.maxOffbr */
+  double omega;      /* suhmo.turbulentParam */
+  double nu;         /* suhmo.WaterViscosity */
+  int cutOffBcoef;   /* solver.cut_solve_outside_domain */
+  int use_NL;        /* solver.use_NL */
+  int use_mask_grad; /* solver.use_mask_for_gradients */
+  int bcoeff_otf;    /* solver.bcoeff_otf -> m_update_operator */
+} orc_params;
+
+/* bc.lo_bc / bc.hi_bc (0 Dirichlet, 1 Neumann) and the per-side constants (src/AmrHydro.cpp:99-155) */
+typedef struct orc_bc {
+  int lo_type[2], hi_type[2];
+  double lo_val[2], hi_val[2];
+} orc_bc;
+
+enum { ORC_CELL = 0, ORC_XFACE = 1, ORC_YFACE = 2 };
+
+/* ---- layouts: boxes = [nbox][4] = lo0 lo1 hi0 hi1 (inclusive cell indices) ---- */
+orc_layout* orc_layout_create(int nbox, const int* boxes, const int domain[4], const int periodic[2]);
+orc_layout* orc_layout_coarsen(const orc_layout* lay, int r);
+int orc_layout_coarsenable(const orc_layout* lay, int r);
+int orc_layout_nbox(const orc_layout* lay);
+void orc_layout_box(const orc_layout* lay, int b, int out[4]);
+void orc_layout_free(orc_layout* lay);
+
+/* ---- fields ---- */
+orc_field* orc_field_create(const orc_layout* lay, int ncomp, int ng, int centering);
+void orc_field_free(orc_field* f);
+/* pointer to box b's array; dims = {nx, ny, ncomp} incl. ghosts; lo = index of element (0,0) */
+double* orc_field_fab(orc_field* f, int b, int dims[3], int lo[2]);
+void orc_field_setval(orc_field* f, double v);
+void orc_field_copy(orc_field* dst, const orc_field* src); /* whole arrays, same shape */
+
+/* ghost utilities */
+void orc_exchange_faces(orc_field* f);  /* Copier::exchangeDefine(grids,1)+trimEdges: face strips only */
+void orc_exchange_full(orc_field* f);   /* plain LevelData::exchange(): all ghost cells incl. corners */
+void orc_apply_bc(orc_field* f, const orc_bc* bc, const double dx[2], int homogeneous); /* mixBCValues */
+void orc_extrap_ghost(orc_field* f);    /* util/ExtrapGhostCells.cpp:47-55,94-179 (cell data) */
+void orc_copy_ghost(orc_field* f);      /* util/ExtrapGhostCells.cpp CopyGhostCells (cell data) */
+void orc_cell_to_edge(const orc_field* cell, orc_field* ex, orc_field* ey);
+void orc_edge_to_cell(const orc_field* ex, const orc_field* ey, orc_field* cell2);
+void orc_mac_gradient(orc_field* phi, const orc_field* mask, const double dx[2], orc_field* gx, orc_field* gy);
+void orc_divergence(const orc_field* ux, const orc_field* uy, const double dx[2], orc_field* div);
+void orc_icemask_ec(const orc_field* mask, orc_field* mx, orc_field* my);
+void orc_coarse_average(const orc_field* fine, orc_field* coarse, int r);          /* cells */
+void orc_coarse_average_face(const orc_field* fine, orc_field* coarse, int r);     /* faces */
+void orc_compute_nl(const orc_params* p, const orc_field* phi, const orc_field* B, const orc_field* mask,
+                    const orc_field* Pi, const orc_field* zb, orc_field* nl, orc_field* dnl);
+void orc_compute_re(const orc_params* p, const orc_field* B, const orc_field* gradH, orc_field* Re);
+
+/* vector ops (src/AMRNonLinearPoissonOp.cpp:519-688), valid cells only */
+void orc_set_to_zero(orc_field* f);
+void orc_assign(orc_field* dst, const orc_field* src);
+void orc_incr(orc_field* lhs, const orc_field* x, double scale);
+void orc_axby(orc_field* lhs, const orc_field* x, const orc_field* y, double a, double b);
+void orc_scale(orc_field* f, double s);
+double orc_dot(const orc_field* a, const orc_field* b);
+double orc_norm(const orc_field* f, int p);
+
+/* ---- operator = VCAMRNonLinearPoissonOp on one level / MG depth (fields are shared, not copied) ---- */
+orc_op* orc_op_create(const orc_layout* lay, const double dx[2], double alpha, double beta,
+                      const orc_bc* bc, const orc_params* prm,
+                      orc_field* aCoef, orc_field* bX, orc_field* bY,
+                      orc_field* B, orc_field* Pi, orc_field* zb, orc_field* mask);
+void orc_op_free(orc_op* op);
+void orc_op_reset_lambda(orc_op* op);
+orc_field* orc_op_lambda(orc_op* op);
+void orc_op_relax(orc_op* op, orc_field* phi, const orc_field* rhs, int iterations);
+void orc_op_residual(orc_op* op, orc_field* res, orc_field* phi, const orc_field* rhs);
+void orc_op_apply(orc_op* op, orc_field* lhs, orc_field* phi, int homogeneous);
+void orc_op_restrict_residual(orc_op* op, orc_field* resCoarse, orc_field* phiFine, const orc_field* rhsFine);
+void orc_op_restrict_r(orc_op* op, orc_field* phiCoarse, const orc_field* phiFine);
+void orc_op_prolong_increment(orc_op* op, orc_field* phiFine, const orc_field* corrCoarse);
+void orc_op_update_operator(orc_op* op, orc_field* phi);
+void orc_op_average_operator(orc_op* op, const orc_op* finest, int depth);
+
+/* ---- factory + FAS multigrid on a single AMR level (lbase = lmax = 0) ---- */
+typedef struct orc_solver_params {
+  int pre, post, bottom, max_iter, imin, iter_min;
+  double eps, hang, norm_thresh;
+  int fixed_cycles; /* >0: run exactly this many V-cycles (parity protocol), ignoring the stop test */
+} orc_solver_params;
+
+orc_solver* orc_solver_create(const orc_layout* lay, const double dx[2], double alpha, double beta,
+                              const orc_bc* bc, const orc_params* prm,
+                              orc_field* aCoef, orc_field* bX, orc_field* bY,
+                              orc_field* B, orc_field* Pi, orc_field* zb, orc_field* mask);
+void orc_solver_free(orc_solver* s);
+int orc_solver_depth(const orc_solver* s);            /* number of MG ops (depths 0..n-1) */
+orc_op* orc_solver_op(orc_solver* s, int depth);
+/* returns number of V-cycles done; resnorm[0] = initial, resnorm[k] after cycle k (needs max_iter+1 slots) */
+int orc_solver_solve(orc_solver* s, orc_field* phi, const orc_field* rhs, const orc_solver_params* sp, double* resnorm);
+void orc_solver_vcycle(orc_solver* s, orc_field* phi, const orc_field* rhs, const orc_solver_params* sp, int iter);
+/* cell-updates performed by one V-cycle (SURVEY.md 8d metric) */
+double orc_solver_cell_updates(const orc_solver* s, const orc_solver_params* sp);
+
+void orc_set_threads(int n);
+
+#ifdef __cplusplus
+}
+#endif
+#endif
