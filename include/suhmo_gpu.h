@@ -1,0 +1,246 @@
+/*
+ * suhmo_gpu.h -- C ABI of libsuhmo_gpu.so: the B200-native hydraulic-head solve behind SUHMO's
+ * VCAMRNonLinearPoissonOp / AMRNonLinearPoissonOp operator surface.
+ *
+ * The reference has no C ABI for this path: its boundary is the C++ virtual interface that the
+ * (Chombo-fork) AMRFASMultiGrid/MultiGrid drivers call.  Each entry point below names the reference
+ * member it replaces (paths relative to the SUHMO tree).  A Chombo-side subclass forwards each
+ * virtual to the matching function here.
+ *
+ * Conventions
+ *  - plain C: opaque handles, int / double / pointers only, no C++ or torch types;
+ *  - every function returns an int status (SG_OK == 0); sg_last_error() gives the message.  The
+ *    reference aborts (MayDay::Abort / CH_assert); the C++ mirror in suhmo_b200/host turns a non-zero
+ *    status into abort() to keep that behaviour;
+ *  - all reals are FP64 (Chombo Real, PRECISION=DOUBLE); boxes are {lo0, lo1, hi0, hi1} inclusive cell
+ *    indices; host arrays are Fortran-ordered FArrayBox data (i fastest, then j, then component),
+ *    i.e. exactly FArrayBox::dataPtr();
+ *  - all device work is enqueued on the context's CUDA stream; functions that return a scalar
+ *    (norm, dot, solve) synchronise that stream;
+ *  - there is NO CPU fallback: with no usable CUDA device sg_ctx_create fails.
+ */
+#ifndef SUHMO_GPU_H
+#define SUHMO_GPU_H
+
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct sg_ctx sg_ctx;         /* device + stream (+ NCCL communicator)                   */
+typedef struct sg_layout sg_layout;   /* DisjointBoxLayout + ProblemDomain (+ box ownership)     */
+typedef struct sg_field sg_field;     /* LevelData<FArrayBox>, or one direction of a FluxBox      */
+typedef struct sg_op sg_op;           /* VCAMRNonLinearPoissonOp (one AMR level or one MG depth)  */
+typedef struct sg_factory sg_factory; /* VCAMRNonLinearPoissonOpFactory                           */
+typedef struct sg_solver sg_solver;   /* AMRFASMultiGrid<LevelData<FArrayBox>> for this operator  */
+
+enum {
+  SG_OK = 0,
+  SG_ERR_INVALID = 1,     /* bad argument (CH_assert in the reference)                            */
+  SG_ERR_CUDA = 2,        /* CUDA runtime error                                                    */
+  SG_ERR_UNSUPPORTED = 3, /* legal in the reference, not built here yet                            */
+  SG_ERR_ABORT = 4,       /* the reference would MayDay::Abort here (e.g. homogeneous residualI)   */
+  SG_ERR_NCCL = 5
+};
+
+enum { SG_CELL = 0, SG_XFACE = 1, SG_YFACE = 2 };
+
+/* suhmo.* / solver.* values the kernels need (src/suhmo_params.cpp:56-71, src/AmrHydro.cpp:864-884).
+   rho_w*g (1000.0*9.8) and g (9.8) are literals inside the reference kernels (src/AmrHydroF.ChF:45-52,
+   103,142,217) and therefore not parameters here either. */
+typedef struct sg_params {
+  double A, cutOffbr, maxOffbr, omega, nu;
+  int cutOffBcoef;   /* solver.cut_solve_outside_domain */
+  int use_NL;        /* solver.use_NL (0 => NL = dNL = 0) */
+  int use_mask_grad; /* solver.use_mask_for_gradients */
+  int bcoeff_otf;    /* solver.bcoeff_otf => m_update_operator */
+} sg_params;
+
+/* mixBCValues' inputs (src/AmrHydro.cpp:99-155,248-309): per direction/side type 0 Dirichlet, 1 Neumann,
+   and the constant boundary value. */
+typedef struct sg_bc {
+  int lo_type[2], hi_type[2];
+  double lo_val[2], hi_val[2];
+} sg_bc;
+
+/* AMRMultiGrid::setSolverParameters + m_imin / m_iterMin (src/AmrHydro.cpp:737-762) */
+typedef struct sg_solver_params {
+  int pre, post, bottom, num_mg, max_iter, imin, iter_min;
+  double eps, hang, norm_thresh;
+  int fixed_cycles; /* >0: run exactly this many V-cycles (parity / benchmark protocol) */
+} sg_solver_params;
+
+typedef struct sg_solve_stats {
+  int iterations;
+  int exit_status;            /* AMRMultiGrid::m_exitStatus bit mask */
+  double initial_resnorm, final_resnorm;
+  double cell_updates;        /* GSRB point updates performed, summed over levels/depths and V-cycles */
+  double device_ms;           /* CUDA-event time of the V-cycles (excludes set-up) */
+  long long kernel_launches;  /* kernels of this library launched by the call */
+} sg_solve_stats;
+
+const char* sg_last_error(void);
+int sg_version(void);
+
+/* ------------------------------------------------------------------ context ------------------------------ */
+/* One per process/GPU.  rank/nranks and nccl_unique_id (128 bytes, from sg_nccl_unique_id on rank 0, broadcast
+   by the caller) describe the box-wise partition over the GPUs of one node; nranks == 1 needs no NCCL.
+   Replaces Chombo's MPI communicator set-up (Chombo_MPI::comm). */
+int sg_ctx_create(sg_ctx** out, int device, int rank, int nranks, const void* nccl_unique_id);
+int sg_ctx_destroy(sg_ctx* ctx);
+int sg_ctx_sync(sg_ctx* ctx);
+int sg_ctx_set_stream(sg_ctx* ctx, void* cuda_stream);
+int sg_ctx_kernel_launches(sg_ctx* ctx, long long* out);
+int sg_nccl_unique_id(void* out128);
+
+/* ------------------------------------------------------------------ layouts ------------------------------ */
+/* DisjointBoxLayout(boxes, procIDs, ProblemDomain) as built at src/AmrHydro.cpp:4844-4930.  owner[b] is the
+   rank holding box b (LoadBalance); NULL => all on rank 0. */
+int sg_layout_create(sg_ctx* ctx, sg_layout** out, int nbox, const int* boxes, const int* owner,
+                     const int domain[4], const int periodic[2]);
+int sg_layout_coarsen(sg_layout* lay, int ratio, sg_layout** out); /* coarsen_dbl, VCAMRNonLinearPoissonOp.cpp:1060 */
+int sg_layout_coarsenable(const sg_layout* lay, int ratio, int* out);
+int sg_layout_nbox(const sg_layout* lay, int* nbox);
+int sg_layout_destroy(sg_layout* lay);
+
+/* ------------------------------------------------------------------ fields ------------------------------- */
+/* LevelData<FArrayBox>(grids, ncomp, nghost*IntVect::Unit) / LevelData<FluxBox> direction. */
+int sg_field_create(sg_layout* lay, sg_field** out, int ncomp, int nghost, int centering);
+int sg_field_destroy(sg_field* f);
+/* copy box `box`'s whole FArrayBox (ghosts included) host<->device; only boxes owned by this rank. */
+int sg_field_upload_box(sg_field* f, int box, const double* host_fab);
+int sg_field_download_box(const sg_field* f, int box, double* host_fab);
+/* batched variants: fabs[b] for every box of the layout (entries of boxes owned elsewhere are ignored) */
+int sg_field_upload(sg_field* f, const double* const* fabs);
+int sg_field_download(const sg_field* f, double* const* fabs);
+/* raw device view for zero-copy callers (torch): base pointer of the rank-local patch array, element strides */
+int sg_field_device_view(sg_field* f, void** base, long long* pitch, long long* comp_stride,
+                         int patch_lo[2], int patch_hi[2], long long* offset_of_patch_lo);
+
+/* ghost utilities used around the solve */
+int sg_exchange(sg_field* f, int corners);                      /* LevelData::exchange / exchange(copier) */
+int sg_extrap_ghost_cells(sg_field* f);                         /* util/ExtrapGhostCells.cpp:47-55,94-179 */
+int sg_copy_ghost_cells(sg_field* f);                           /* util/ExtrapGhostCells.cpp CopyGhostCells */
+int sg_apply_bc(sg_field* f, const sg_bc* bc, const double dx[2], int homogeneous); /* mixBCValues */
+
+/* ------------------------------------------------------------------ field kernels ------------------------ */
+/* FORT_COMPUTENONLINEARTERMS via AmrHydro::NonLinear_level (src/AmrHydro.cpp:1542-1574) */
+int sg_nonlinear_level(const sg_params* p, sg_field* nl, sg_field* dnl, const sg_field* u, const sg_field* B,
+                       const sg_field* mask, const sg_field* Pi, const sg_field* zb);
+/* Gradient::compGradientCC without coarser/finer levels (util/Gradient.cpp:478-624): MAC gradient + EdgeToCell */
+int sg_gradient_cc(sg_field* grad2, sg_field* phi, const sg_field* mask_or_null, const double dx[2]);
+/* FORT_COMPUTERE over the ghosted box (src/AmrHydro.cpp:1493-1505) */
+int sg_compute_re(const sg_params* p, sg_field* Re, const sg_field* B, const sg_field* gradH);
+/* FORT_DIVERGENCE (util/DivergenceF.ChF:23-57): div += d(ux)/dx + d(uy)/dy */
+int sg_divergence(sg_field* div, const sg_field* ux, const sg_field* uy, const double dx[2]);
+/* AmrHydro::WFlx_level (src/AmrHydro.cpp:1415-1539): bcoef <- B(h); u_coarse may be NULL */
+int sg_wflx_level(sg_ctx* ctx, const sg_params* p, sg_field* bcoefX, sg_field* bcoefY, sg_field* u,
+                  const sg_field* u_coarse, const sg_field* B, const sg_field* mask, const double dx[2]);
+
+/* ------------------------------------------------------------------ factory ------------------------------ */
+/* VCAMRNonLinearPoissonOpFactory::define (src/VCAMRNonLinearPoissonOp.cpp:877-953).  Arrays have nlevels
+   entries.  Fields are shared with the caller (RefCountedPtr semantics): UpdateOperator/AverageOperator
+   write bCoef in place. */
+int sg_factory_define(sg_ctx* ctx, sg_factory** out, int nlevels, sg_layout* const* grids, const int* ref_ratios,
+                      const double coarse_dx[2], const sg_bc* bc, double alpha, sg_field* const* aCoef, double beta,
+                      sg_field* const* bCoefX, sg_field* const* bCoefY, const sg_params* params,
+                      sg_field* const* B, sg_field* const* Pi, sg_field* const* zb, sg_field* const* iceMask);
+int sg_factory_destroy(sg_factory* f);
+/* MGnewOp (src/VCAMRNonLinearPoissonOp.cpp:1016-1181): *out = NULL when the boxes cannot coarsen by 2^depth * 2 */
+int sg_factory_MGnewOp(sg_factory* f, int level, int depth, int homo_only, sg_op** out);
+/* AMRnewOp (src/VCAMRNonLinearPoissonOp.cpp:1183-1286) */
+int sg_factory_AMRnewOp(sg_factory* f, int level, sg_op** out);
+/* refToFiner (src/VCAMRNonLinearPoissonOp.cpp:1288-1306) */
+int sg_factory_refToFiner(const sg_factory* f, int level, int* out);
+int sg_op_destroy(sg_op* op);
+
+/* ------------------------------------------------------------------ MGLevelOp surface -------------------- */
+/* relax (src/AMRNonLinearPoissonOp.cpp:707-750) -> levelGSRB (src/VCAMRNonLinearPoissonOp.cpp:654-760) */
+int sg_op_relax(sg_op* op, sg_field* phi, const sg_field* rhs, int iterations, int amr_fasmg_iter, int depth);
+/* relaxNF (src/AMRNonLinearPoissonOp.cpp:690-704) */
+int sg_op_relaxNF(sg_op* op, sg_field* phi, const sg_field* phi_coarse, const sg_field* rhs, int iterations,
+                  int amr_fasmg_iter, int depth, int print);
+/* residual / residualNF / residualI (src/AMRNonLinearPoissonOp.cpp:241-273, VCAMRNonLinearPoissonOp.cpp:98-167).
+   homogeneous != 0 is an abort in the reference's VC residualI: returns SG_ERR_ABORT. */
+int sg_op_residual(sg_op* op, sg_field* lhs, sg_field* phi, const sg_field* rhs, int homogeneous);
+int sg_op_residualNF(sg_op* op, sg_field* lhs, sg_field* phi, const sg_field* phi_coarse, const sg_field* rhs,
+                     int homogeneous);
+/* applyOp / applyOpI / applyOpNoBoundary / applyOpMg (AMRNonLinearPoissonOp.cpp:431-443,
+   VCAMRNonLinearPoissonOp.cpp:211-231,273-345) */
+int sg_op_applyOp(sg_op* op, sg_field* lhs, sg_field* phi, int homogeneous);
+int sg_op_applyOpNoBoundary(sg_op* op, sg_field* lhs, sg_field* phi);
+int sg_op_applyOpMg(sg_op* op, sg_field* lhs, sg_field* phi, sg_field* phi_coarse, int homogeneous);
+/* restrictResidual, 5-argument FAS form (VCAMRNonLinearPoissonOp.cpp:384-460); homogeneous != 0 -> SG_ERR_ABORT */
+int sg_op_restrictResidual(sg_op* op, sg_field* res_coarse, sg_field* phi_fine, const sg_field* phi_coarse,
+                           const sg_field* rhs_fine, int homogeneous);
+/* restrictR (VCAMRNonLinearPoissonOp.cpp:347-372) */
+int sg_op_restrictR(sg_op* op, sg_field* phi_coarse, const sg_field* phi_fine);
+/* prolongIncrement (src/AMRNonLinearPoissonOp.cpp:856-886) */
+int sg_op_prolongIncrement(sg_op* op, sg_field* phi_this_level, const sg_field* correct_coarse);
+/* UpdateOperator (VCAMRNonLinearPoissonOp.cpp:34-64); homogeneous != 0 -> SG_ERR_ABORT */
+int sg_op_UpdateOperator(sg_op* op, sg_field* phi, const sg_field* phi_coarse, int depth, int amr_fasmg_iter,
+                         int homogeneous);
+/* AverageOperator (VCAMRNonLinearPoissonOp.cpp:66-95) */
+int sg_op_AverageOperator(sg_op* op, const sg_op* finest, int depth);
+/* resetLambda / computeLambda (VCAMRNonLinearPoissonOp.cpp:505-547): lambda is recomputed inside the kernels;
+   this materialises it for inspection. */
+int sg_op_lambda(sg_op* op, sg_field* lambda_out);
+/* createCoarser / create (src/AMRNonLinearPoissonOp.cpp:519-526,753-766) */
+int sg_op_createCoarser(sg_op* op, sg_field** coarse, const sg_field* fine, int ghosted);
+int sg_op_create(sg_op* op, sg_field** lhs, const sg_field* rhs);
+
+/* LinearOp vector surface (src/AMRNonLinearPoissonOp.cpp:556-688) */
+int sg_op_assign(sg_op* op, sg_field* lhs, const sg_field* rhs);
+int sg_op_assignLocal(sg_op* op, sg_field* lhs, const sg_field* rhs);
+int sg_op_incr(sg_op* op, sg_field* lhs, const sg_field* x, double scale);
+int sg_op_axby(sg_op* op, sg_field* lhs, const sg_field* x, const sg_field* y, double a, double b);
+int sg_op_scale(sg_op* op, sg_field* lhs, double scale);
+int sg_op_setToZero(sg_op* op, sg_field* lhs);
+int sg_op_dotProduct(sg_op* op, const sg_field* a, const sg_field* b, double* out);
+int sg_op_norm(sg_op* op, const sg_field* x, int ord, double* out);       /* global (all ranks) */
+int sg_op_localMaxNorm(sg_op* op, const sg_field* x, double* out);       /* this rank only      */
+
+/* ------------------------------------------------------------------ AMRLevelOp surface ------------------- */
+/* src/AMRNonLinearPoissonOp.cpp:889-1264 and VCAMRNonLinearPoissonOp.cpp:555-652 (reflux/getFlux) */
+int sg_op_AMRResidual(sg_op* op, sg_field* residual, const sg_field* phi_fine, sg_field* phi, const sg_field* phi_coarse,
+                      const sg_field* rhs, int homogeneous_phys_bc, sg_op* finer_op);
+int sg_op_AMRResidualNC(sg_op* op, sg_field* residual, const sg_field* phi_fine, sg_field* phi, const sg_field* rhs,
+                        int homogeneous_phys_bc, sg_op* finer_op);
+int sg_op_AMRResidualNF(sg_op* op, sg_field* residual, sg_field* phi, const sg_field* phi_coarse, const sg_field* rhs,
+                        int homogeneous_phys_bc);
+int sg_op_AMROperator(sg_op* op, sg_field* lofphi, const sg_field* phi_fine, sg_field* phi, const sg_field* phi_coarse,
+                      int homogeneous_phys_bc, sg_op* finer_op);
+int sg_op_AMROperatorNC(sg_op* op, sg_field* lofphi, const sg_field* phi_fine, sg_field* phi, int homogeneous_phys_bc,
+                        sg_op* finer_op);
+int sg_op_AMROperatorNF(sg_op* op, sg_field* lofphi, sg_field* phi, const sg_field* phi_coarse, int homogeneous_phys_bc);
+int sg_op_AMRRestrictS(sg_op* op, sg_field* res_coarse, const sg_field* residual, sg_field* correction,
+                       const sg_field* coarse_correction, sg_field* scratch, int skip_res);
+int sg_op_AMRProlongS(sg_op* op, sg_field* correction, const sg_field* coarse_correction);
+int sg_op_AMRProlongS_2(sg_op* op, sg_field* correction, const sg_field* coarse_correction, sg_op* coarse_op);
+int sg_op_AMRUpdateResidual(sg_op* op, sg_field* residual, sg_field* correction, const sg_field* coarse_correction);
+int sg_op_AMRNorm(sg_op* op, const sg_field* coar_resid, const sg_field* fine_resid_or_null, int ref_rat, int ord,
+                  double* out);
+int sg_op_reflux(sg_op* op, const sg_field* phi_fine, const sg_field* phi, sg_field* residual, sg_op* finer_op);
+/* QuadCFInterp::coarseFineInterp as used by the op (m_interpWithCoarser) */
+int sg_op_cfInterp(sg_op* op, sg_field* phi, const sg_field* phi_coarse);
+
+/* ------------------------------------------------------------------ whole solve -------------------------- */
+/* AMRFASMultiGrid::define + setSolverParameters + solve as driven by AmrHydro::SolveForHead_nl
+   (src/AmrHydro.cpp:719-768), kept on the device: one call = all V-cycles, residual norms on device. */
+int sg_solver_define(sg_factory* f, sg_solver** out, int num_levels);
+int sg_solver_destroy(sg_solver* s);
+int sg_solver_depth(const sg_solver* s, int level, int* ndepth);
+int sg_solver_solve(sg_solver* s, sg_field* const* phi, sg_field* const* rhs, int l_max, int l_base,
+                    const sg_solver_params* sp, double* resnorm_history /* max_iter+2 or NULL */,
+                    sg_solve_stats* stats);
+/* cell-updates one V-cycle performs with these parameters (metric of SURVEY.md 8d) */
+int sg_solver_cell_updates_per_cycle(const sg_solver* s, const sg_solver_params* sp, double* out);
+/* relax implementation switch for experiments/tests: 0 = separate colour passes (generic), 1 = fused red+black
+   streaming kernel (default where the level is a single rectangular patch) */
+int sg_set_relax_mode(sg_ctx* ctx, int mode);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SUHMO_GPU_H */

@@ -1,0 +1,386 @@
+"""Python mirror of the reference's operator surface over the C ABI (include/suhmo_gpu.h).
+
+Class and method names follow the reference (src/VCAMRNonLinearPoissonOp.H, src/AMRNonLinearPoissonOp.H and
+the Chombo types they use) so that tests read like calls into the reference.  Everything executes in
+libsuhmo_gpu.so on the GPU; there is no CPU path here.
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import capi
+from .capi import CELL, XFACE, YFACE, check, lib
+
+
+def _ip(a):
+    return a.ctypes.data_as(C.POINTER(C.c_int))
+
+
+def _dp(a):
+    return a.ctypes.data_as(C.POINTER(C.c_double))
+
+
+class Context:
+    """One GPU (+ its rank in the box-wise partition of a node)."""
+
+    def __init__(self, device=0, rank=0, nranks=1, nccl_unique_id=None):
+        self.h = C.c_void_p()
+        uid = None
+        if nccl_unique_id is not None:
+            self._uid = (C.c_char * 128).from_buffer_copy(bytes(nccl_unique_id))
+            uid = C.cast(self._uid, C.c_void_p)
+        check(lib().sg_ctx_create(C.byref(self.h), device, rank, nranks, uid))
+        self.rank, self.nranks, self.device = rank, nranks, device
+
+    @staticmethod
+    def nccl_unique_id():
+        buf = (C.c_char * 128)()
+        check(lib().sg_nccl_unique_id(C.cast(buf, C.c_void_p)))
+        return bytes(buf)
+
+    def sync(self):
+        check(lib().sg_ctx_sync(self.h))
+
+    def set_stream(self, cuda_stream):
+        check(lib().sg_ctx_set_stream(self.h, C.c_void_p(cuda_stream)))
+
+    def kernel_launches(self):
+        n = C.c_longlong()
+        check(lib().sg_ctx_kernel_launches(self.h, C.byref(n)))
+        return n.value
+
+    def set_relax_mode(self, mode):
+        check(lib().sg_set_relax_mode(self.h, mode))
+
+    def destroy(self):
+        if self.h:
+            lib().sg_ctx_destroy(self.h)
+            self.h = None
+
+
+class DisjointBoxLayout:
+    """boxes [nbox,4] = lo0 lo1 hi0 hi1; domain = ProblemDomain box; periodic flags; owner = procIDs."""
+
+    def __init__(self, ctx, boxes, domain, periodic, owner=None, _h=None):
+        self.ctx = ctx
+        self.boxes = np.ascontiguousarray(boxes, dtype=np.int32).reshape(-1, 4)
+        self.domain = np.ascontiguousarray(domain, dtype=np.int32)
+        self.periodic = np.ascontiguousarray(periodic, dtype=np.int32)
+        self.owner = None if owner is None else np.ascontiguousarray(owner, dtype=np.int32)
+        if _h is None:
+            _h = C.c_void_p()
+            check(lib().sg_layout_create(ctx.h, C.byref(_h), len(self.boxes), _ip(self.boxes),
+                                         None if self.owner is None else _ip(self.owner), _ip(self.domain), _ip(self.periodic)))
+        self.h = _h
+
+    def owned(self, b):
+        return (0 if self.owner is None else int(self.owner[b])) == self.ctx.rank
+
+    def coarsenable(self, r):
+        out = C.c_int()
+        check(lib().sg_layout_coarsenable(self.h, r, C.byref(out)))
+        return bool(out.value)
+
+    def coarsen(self, r):
+        h = C.c_void_p()
+        check(lib().sg_layout_coarsen(self.h, r, C.byref(h)))
+        return DisjointBoxLayout(self.ctx, self.boxes // r, self.domain // r, self.periodic, self.owner, _h=h)
+
+
+class LevelData:
+    """LevelData<FArrayBox> (centering CELL) or one direction of LevelData<FluxBox> (XFACE / YFACE), on the device."""
+
+    def __init__(self, layout, ncomp=1, nghost=0, centering=CELL, _h=None):
+        self.layout, self.ncomp, self.ng, self.cent = layout, ncomp, nghost, centering
+        if _h is None:
+            _h = C.c_void_p()
+            check(lib().sg_field_create(layout.h, C.byref(_h), ncomp, nghost, centering))
+        self.h = _h
+
+    def fab_shape(self, b):
+        bx = self.layout.boxes[b]
+        nx = bx[2] - bx[0] + 1 + 2 * self.ng + (self.cent == XFACE)
+        ny = bx[3] - bx[1] + 1 + 2 * self.ng + (self.cent == YFACE)
+        return (self.ncomp, ny, nx)
+
+    def upload_box(self, b, fab):
+        fab = np.ascontiguousarray(fab, dtype=np.float64)
+        assert fab.size == int(np.prod(self.fab_shape(b))), (fab.shape, self.fab_shape(b))
+        check(lib().sg_field_upload_box(self.h, b, _dp(fab)))
+
+    def download_box(self, b):
+        out = np.empty(self.fab_shape(b), dtype=np.float64)
+        check(lib().sg_field_download_box(self.h, b, _dp(out)))
+        return out
+
+    def upload(self, fabs):
+        """batched: fabs[b] is box b's FArrayBox data (entries for boxes owned elsewhere may be None)."""
+        keep = [None if f is None else np.ascontiguousarray(f, dtype=np.float64) for f in fabs]
+        ptrs = (C.c_void_p * len(keep))(*[None if f is None else f.ctypes.data for f in keep])
+        check(lib().sg_field_upload(self.h, ptrs))
+
+    def download(self):
+        outs = [np.empty(self.fab_shape(b), dtype=np.float64) if self.layout.owned(b) else None
+                for b in range(len(self.layout.boxes))]
+        ptrs = (C.c_void_p * len(outs))(*[None if f is None else f.ctypes.data for f in outs])
+        check(lib().sg_field_download(self.h, ptrs))
+        return outs
+
+    # -- helpers for tests: move whole-level arrays -------------------------------------------------
+    def set_global(self, g, glo):
+        """upload every owned box from global array g[(comp,) j, i] whose element (0,0) is index glo."""
+        g = np.asarray(g, dtype=np.float64)
+        if g.ndim == 2:
+            g = g[None]
+        fabs = []
+        for b, bx in enumerate(self.layout.boxes):
+            if not self.layout.owned(b):
+                fabs.append(None)
+                continue
+            _, ny, nx = self.fab_shape(b)
+            j0, i0 = bx[1] - self.ng - glo[1], bx[0] - self.ng - glo[0]
+            fabs.append(np.ascontiguousarray(g[:, j0:j0 + ny, i0:i0 + nx]))
+        self.upload(fabs)
+
+    def get_global(self, fill=np.nan):
+        d = self.layout.domain
+        nx, ny = d[2] - d[0] + 1 + (self.cent == XFACE), d[3] - d[1] + 1 + (self.cent == YFACE)
+        out = np.full((self.ncomp, ny, nx), fill)
+        fabs = self.download()
+        for b, bx in enumerate(self.layout.boxes):
+            if fabs[b] is None:
+                continue
+            vx, vy = bx[2] - bx[0] + 1 + (self.cent == XFACE), bx[3] - bx[1] + 1 + (self.cent == YFACE)
+            out[:, bx[1] - d[1]:bx[1] - d[1] + vy, bx[0] - d[0]:bx[0] - d[0] + vx] = \
+                fabs[b][:, self.ng:self.ng + vy, self.ng:self.ng + vx]
+        return out[0] if self.ncomp == 1 else out
+
+    def exchange(self, corners=True):
+        check(lib().sg_exchange(self.h, int(corners)))
+
+    def destroy(self):
+        if self.h:
+            lib().sg_field_destroy(self.h)
+            self.h = None
+
+
+def ExtrapGhostCells(ld):
+    """util/ExtrapGhostCells.cpp:47-55"""
+    check(lib().sg_extrap_ghost_cells(ld.h))
+
+
+def CopyGhostCells(ld):
+    check(lib().sg_copy_ghost_cells(ld.h))
+
+
+def make_bc(lo_type, hi_type, lo_val=(0.0, 0.0), hi_val=(0.0, 0.0)):
+    bc = capi.BC()
+    for d in range(2):
+        bc.lo_type[d], bc.hi_type[d] = lo_type[d], hi_type[d]
+        bc.lo_val[d], bc.hi_val[d] = lo_val[d], hi_val[d]
+    return bc
+
+
+def make_params(A=2.5e-25, cutOffbr=0.0, maxOffbr=10000.0, omega=1e-3, nu=1.787e-6, cutOffBcoef=0, use_NL=1,
+                use_mask_grad=0, bcoeff_otf=1):
+    return capi.Params(A, cutOffbr, maxOffbr, omega, nu, cutOffBcoef, use_NL, use_mask_grad, bcoeff_otf)
+
+
+def make_solver_params(pre=4, post=4, bottom=16, num_mg=1, max_iter=100, imin=0, iter_min=2, eps=1e-7, hang=0.01,
+                       norm_thresh=1e-7, fixed_cycles=0):
+    return capi.SolverParams(pre, post, bottom, num_mg, max_iter, imin, iter_min, eps, hang, norm_thresh, fixed_cycles)
+
+
+def _h(x):
+    return None if x is None else x.h
+
+
+class VCAMRNonLinearPoissonOp:
+    """src/VCAMRNonLinearPoissonOp.H:24-285 + the inherited AMRNonLinearPoissonOp surface."""
+
+    def __init__(self, h, layout):
+        self.h, self.layout = h, layout
+
+    def relax(self, e, residual, iterations, AMRFASMGiter=0, depth=0):
+        check(lib().sg_op_relax(self.h, e.h, residual.h, iterations, AMRFASMGiter, depth))
+
+    def relaxNF(self, e, eCoarse, residual, iterations, AMRFASMGiter=0, depth=0, print_=False):
+        check(lib().sg_op_relaxNF(self.h, e.h, _h(eCoarse), residual.h, iterations, AMRFASMGiter, depth, int(print_)))
+
+    def residual(self, lhs, phi, rhs, homogeneous=False):
+        check(lib().sg_op_residual(self.h, lhs.h, phi.h, rhs.h, int(homogeneous)))
+
+    def residualNF(self, lhs, phi, phiCoarse, rhs, homogeneous=False):
+        check(lib().sg_op_residualNF(self.h, lhs.h, phi.h, _h(phiCoarse), rhs.h, int(homogeneous)))
+
+    def applyOp(self, lhs, phi, homogeneous=False):
+        check(lib().sg_op_applyOp(self.h, lhs.h, phi.h, int(homogeneous)))
+
+    def applyOpNoBoundary(self, lhs, phi):
+        check(lib().sg_op_applyOpNoBoundary(self.h, lhs.h, phi.h))
+
+    def applyOpMg(self, lhs, phi, phiCoarse, homogeneous):
+        check(lib().sg_op_applyOpMg(self.h, lhs.h, phi.h, _h(phiCoarse), int(homogeneous)))
+
+    def restrictResidual(self, resCoarse, phiFine, phiCoarse, rhsFine, homogeneous):
+        check(lib().sg_op_restrictResidual(self.h, resCoarse.h, phiFine.h, _h(phiCoarse), rhsFine.h, int(homogeneous)))
+
+    def restrictR(self, phiCoarse, phiFine):
+        check(lib().sg_op_restrictR(self.h, phiCoarse.h, phiFine.h))
+
+    def prolongIncrement(self, phiThisLevel, correctCoarse):
+        check(lib().sg_op_prolongIncrement(self.h, phiThisLevel.h, correctCoarse.h))
+
+    def UpdateOperator(self, phi, phicoarse, depth, AMRFASMGiter, homogeneous):
+        check(lib().sg_op_UpdateOperator(self.h, phi.h, _h(phicoarse), depth, AMRFASMGiter, int(homogeneous)))
+
+    def AverageOperator(self, finest, depth):
+        check(lib().sg_op_AverageOperator(self.h, finest.h, depth))
+
+    def lambda_(self, out):
+        check(lib().sg_op_lambda(self.h, out.h))
+
+    def createCoarser(self, fine, ghosted=True):
+        h = C.c_void_p()
+        check(lib().sg_op_createCoarser(self.h, C.byref(h), fine.h, int(ghosted)))
+        return LevelData(fine.layout.coarsen(2), fine.ncomp, fine.ng, fine.cent, _h=h)
+
+    def create(self, rhs):
+        h = C.c_void_p()
+        check(lib().sg_op_create(self.h, C.byref(h), rhs.h))
+        return LevelData(rhs.layout, rhs.ncomp, rhs.ng, rhs.cent, _h=h)
+
+    def assign(self, lhs, rhs):
+        check(lib().sg_op_assign(self.h, lhs.h, rhs.h))
+
+    def assignLocal(self, lhs, rhs):
+        check(lib().sg_op_assignLocal(self.h, lhs.h, rhs.h))
+
+    def incr(self, lhs, x, scale):
+        check(lib().sg_op_incr(self.h, lhs.h, x.h, scale))
+
+    def axby(self, lhs, x, y, a, b):
+        check(lib().sg_op_axby(self.h, lhs.h, x.h, y.h, a, b))
+
+    def scale(self, lhs, s):
+        check(lib().sg_op_scale(self.h, lhs.h, s))
+
+    def setToZero(self, lhs):
+        check(lib().sg_op_setToZero(self.h, lhs.h))
+
+    def dotProduct(self, a, b):
+        out = C.c_double()
+        check(lib().sg_op_dotProduct(self.h, a.h, b.h, C.byref(out)))
+        return out.value
+
+    def norm(self, x, ord_):
+        out = C.c_double()
+        check(lib().sg_op_norm(self.h, x.h, ord_, C.byref(out)))
+        return out.value
+
+    def localMaxNorm(self, x):
+        out = C.c_double()
+        check(lib().sg_op_localMaxNorm(self.h, x.h, C.byref(out)))
+        return out.value
+
+    def AMRResidualNC(self, residual, phiFine, phi, rhs, homogeneousPhysBC, finerOp):
+        check(lib().sg_op_AMRResidualNC(self.h, residual.h, _h(phiFine), phi.h, rhs.h, int(homogeneousPhysBC), _h(finerOp)))
+
+    def AMROperatorNC(self, LofPhi, phiFine, phi, homogeneousPhysBC, finerOp):
+        check(lib().sg_op_AMROperatorNC(self.h, LofPhi.h, _h(phiFine), phi.h, int(homogeneousPhysBC), _h(finerOp)))
+
+    def AMRNorm(self, coarResid, fineResid, refRat, ord_):
+        out = C.c_double()
+        check(lib().sg_op_AMRNorm(self.h, coarResid.h, _h(fineResid), refRat, ord_, C.byref(out)))
+        return out.value
+
+    def destroy(self):
+        if self.h:
+            lib().sg_op_destroy(self.h)
+            self.h = None
+
+
+class VCAMRNonLinearPoissonOpFactory:
+    """src/VCAMRNonLinearPoissonOp.H:291-403"""
+
+    def define(self, ctx, grids, refRatios, coarsedx, bc, alpha, aCoef, beta, bCoefX, bCoefY, params, B, Pi, zb, iceMask):
+        n = len(grids)
+        self.ctx, self.grids = ctx, grids
+        self._keep = (bc, params, aCoef, bCoefX, bCoefY, B, Pi, zb, iceMask)
+
+        def arr(fs):
+            return (C.c_void_p * n)(*[f.h.value if isinstance(f.h, C.c_void_p) else f.h for f in fs])
+
+        rr = np.ascontiguousarray(list(refRatios) + [2], dtype=np.int32)
+        dxa = np.ascontiguousarray(coarsedx, dtype=np.float64)
+        self.h = C.c_void_p()
+        check(lib().sg_factory_define(ctx.h, C.byref(self.h), n, arr(grids), _ip(rr), _dp(dxa), C.byref(bc), alpha, arr(aCoef),
+                                      beta, arr(bCoefX), arr(bCoefY), C.byref(params), arr(B), arr(Pi), arr(zb), arr(iceMask)))
+        return self
+
+    def MGnewOp(self, level, depth, homoOnly=True):
+        """returns None when the boxes cannot coarsen by 2^depth * 2 (reference: NULL)"""
+        h = C.c_void_p()
+        check(lib().sg_factory_MGnewOp(self.h, level, depth, int(homoOnly), C.byref(h)))
+        if not h:
+            return None
+        lay = self.grids[level] if depth == 0 else self.grids[level].coarsen(2 ** depth)
+        return VCAMRNonLinearPoissonOp(h, lay)
+
+    def AMRnewOp(self, level):
+        h = C.c_void_p()
+        check(lib().sg_factory_AMRnewOp(self.h, level, C.byref(h)))
+        return VCAMRNonLinearPoissonOp(h, self.grids[level])
+
+    def refToFiner(self, level):
+        out = C.c_int()
+        check(lib().sg_factory_refToFiner(self.h, level, C.byref(out)))
+        return out.value
+
+    def destroy(self):
+        if self.h:
+            lib().sg_factory_destroy(self.h)
+            self.h = None
+
+
+class AMRFASMultiGrid:
+    """AMRFASMultiGrid<LevelData<FArrayBox>> as AmrHydro::SolveForHead_nl uses it (src/AmrHydro.cpp:719-768),
+    with all V-cycles kept on the device."""
+
+    def define(self, factory, numLevels=1):
+        self.factory = factory
+        self.h = C.c_void_p()
+        check(lib().sg_solver_define(factory.h, C.byref(self.h), numLevels))
+        self.params = make_solver_params()
+        return self
+
+    def setSolverParameters(self, pre, post, bottom, numMG, maxIter, eps, hang, normThresh):
+        p = self.params
+        p.pre, p.post, p.bottom, p.num_mg, p.max_iter, p.eps, p.hang, p.norm_thresh = pre, post, bottom, numMG, maxIter, eps, hang, normThresh
+
+    @property
+    def depth(self):
+        out = C.c_int()
+        check(lib().sg_solver_depth(self.h, 0, C.byref(out)))
+        return out.value
+
+    def cell_updates_per_cycle(self):
+        out = C.c_double()
+        check(lib().sg_solver_cell_updates_per_cycle(self.h, C.byref(self.params), C.byref(out)))
+        return out.value
+
+    def solve(self, phi, rhs, l_max=0, l_base=0, fixed_cycles=0):
+        """phi, rhs: lists of LevelData per level.  Returns (iterations, residual-norm history, stats)."""
+        self.params.fixed_cycles = fixed_cycles
+        n = max(self.params.max_iter, fixed_cycles) + 2
+        hist = np.zeros(n)
+        stats = capi.SolveStats()
+        pa = (C.c_void_p * len(phi))(*[f.h.value for f in phi])
+        ra = (C.c_void_p * len(rhs))(*[f.h.value for f in rhs])
+        check(lib().sg_solver_solve(self.h, pa, ra, l_max, l_base, C.byref(self.params), _dp(hist), C.byref(stats)))
+        return stats.iterations, hist[:stats.iterations + 1], stats
+
+    def destroy(self):
+        if self.h:
+            lib().sg_solver_destroy(self.h)
+            self.h = None

@@ -1,0 +1,1339 @@
+// sg_api.cu -- C-ABI implementation (include/suhmo_gpu.h): layouts, device-resident fields, the
+// VCAMRNonLinearPoissonOp surface, the factory and the device-resident FAS multigrid driver.
+// Host logic only; all arithmetic is in sg_kernels.cuh.  There is no CPU fallback anywhere in this file.
+#include "../../include/suhmo_gpu.h"
+#include "sg_kernels.cuh"
+#include "sg_nccl.h"
+
+#include <algorithm>
+#include <array>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+// ------------------------------------------------------------------------------------------------
+// errors
+// ------------------------------------------------------------------------------------------------
+static thread_local std::string g_err;
+static int fail(int code, const char* fmt, ...) {
+  char buf[1024];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof(buf), fmt, ap);
+  va_end(ap);
+  g_err = buf;
+  return code;
+}
+extern "C" const char* sg_last_error(void) { return g_err.c_str(); }
+extern "C" int sg_version(void) { return 100; }
+
+#define CK(call)                                                                                         \
+  do {                                                                                                   \
+    cudaError_t e_ = (call);                                                                             \
+    if (e_ != cudaSuccess) return fail(SG_ERR_CUDA, "%s:%d %s: %s", __FILE__, __LINE__, #call, cudaGetErrorString(e_)); \
+  } while (0)
+#define SGCALL(call)            \
+  do {                          \
+    int r_ = (call);            \
+    if (r_ != SG_OK) return r_; \
+  } while (0)
+#define REQUIRE(cond, ...)                                  \
+  do {                                                      \
+    if (!(cond)) return fail(SG_ERR_INVALID, __VA_ARGS__);  \
+  } while (0)
+
+// ------------------------------------------------------------------------------------------------
+// objects
+// ------------------------------------------------------------------------------------------------
+struct Box {
+  int lo[2], hi[2];
+  int nx() const { return hi[0] - lo[0] + 1; }
+  int ny() const { return hi[1] - lo[1] + 1; }
+  long long npts() const { return (long long)nx() * ny(); }
+};
+static inline int fdiv(int a, int r) { return a >= 0 ? a / r : -((-a + r - 1) / r); }
+
+struct sg_ctx {
+  int device = 0, rank = 0, nranks = 1;
+  cudaStream_t stream = nullptr;
+  bool own_stream = true;
+  long long launches = 0;
+  int relax_mode = 1;
+  SgNccl nccl;
+  // reduction scratch
+  double* d_partial = nullptr;
+  size_t partial_cap = 0;
+  double* d_scalar = nullptr;            // [0..63] device scalars (as doubles / bit patterns)
+  double* h_scalar = nullptr;            // pinned mirror
+  double* h_stage = nullptr; size_t h_stage_cap = 0; // pinned staging for batched upload/download
+  double* d_stage = nullptr; size_t d_stage_cap = 0;
+  CopySeg* d_segs = nullptr; size_t segs_cap = 0;
+};
+
+struct sg_field;
+struct sg_layout {
+  sg_ctx* ctx;
+  int nbox;
+  std::vector<Box> boxes;
+  std::vector<int> owner;
+  Box domain;
+  int periodic[2];
+  bool has_local = false;
+  Box patch;             // rank-local valid rectangle
+  int nx = 0, ny = 0, pitch = 0, rows = 0;
+  bool side_ghost[4] = {false, false, false, false}; // ghost data from a periodic image / neighbour rank
+  bool side_domain[4] = {false, false, false, false}; // side lies on the problem-domain boundary
+  int nbr[4] = {-1, -1, -1, -1};                      // neighbour rank for y sides (-1: none / self wrap)
+  bool wrap_local[2] = {false, false};
+  std::vector<sg_field*> ws; // lazily allocated work fields
+  int refs = 1;
+};
+
+struct sg_field {
+  sg_layout* lay;
+  int ncomp, ng, cent;
+  double* base = nullptr;
+  size_t comp_stride = 0;
+  double* p(int c = 0) const { return base + (size_t)c * comp_stride + (size_t)SG_YOFF * lay->pitch + SG_XOFF; }
+};
+
+struct sg_factory {
+  sg_ctx* ctx;
+  int nlevels;
+  std::vector<sg_layout*> grids;
+  std::vector<int> ref_ratios;
+  std::vector<std::array<double, 2>> dx;
+  sg_bc bc;
+  double alpha, beta;
+  sg_params prm;
+  std::vector<sg_field*> aCoef, bX, bY, B, Pi, zb, mask;
+};
+
+struct sg_op {
+  sg_ctx* ctx;
+  sg_layout* lay;
+  double dx[2];
+  double alpha, beta;
+  sg_bc bc;
+  sg_params prm;
+  sg_field *aCoef, *bX, *bY, *B, *Pi, *zb, *mask;
+  bool owns_coefs = false;
+  bool owns_layout = false;
+  int level = 0, depth = 0;
+  bool update_operator = false;
+};
+
+struct sg_solver {
+  sg_ctx* ctx;
+  sg_factory* fac;
+  int num_levels;
+  std::vector<sg_op*> ops;                          // MG depths of level 0
+  std::vector<sg_field*> phi, rhs, save, tmp;       // per depth (depth 0 entries unused except tmp/resid)
+  sg_field* resid = nullptr;
+};
+
+// ------------------------------------------------------------------------------------------------
+// launch helpers
+// ------------------------------------------------------------------------------------------------
+#define LAUNCH(ctx, kernel, grid, block, ...)                    \
+  do {                                                           \
+    kernel<<<(grid), (block), 0, (ctx)->stream>>>(__VA_ARGS__);  \
+    (ctx)->launches++;                                           \
+  } while (0)
+static inline dim3 grid2(int nx, int ny, dim3 b) { return dim3((nx + b.x - 1) / b.x, (ny + b.y - 1) / b.y); }
+static const dim3 B2D(32, 8);
+
+static PhysP phys(const sg_params& p) {
+  PhysP q;
+  q.A = p.A; q.cutOffbr = p.cutOffbr; q.maxOffbr = p.maxOffbr; q.omega = p.omega; q.nu = p.nu;
+  q.cutOffBcoef = p.cutOffBcoef; q.use_NL = p.use_NL; q.use_mask_grad = p.use_mask_grad;
+  return q;
+}
+
+static Geom make_geom(const sg_layout* L, const sg_bc* bc) {
+  Geom g;
+  g.nx = L->nx; g.ny = L->ny; g.pitch = L->pitch;
+  g.glo0 = L->patch.lo[0]; g.glo1 = L->patch.lo[1];
+  g.dlo0 = L->domain.lo[0]; g.dlo1 = L->domain.lo[1]; g.dhi0 = L->domain.hi[0]; g.dhi1 = L->domain.hi[1];
+  for (int s = 0; s < 4; s++) {
+    int dir = s >> 1, side = s & 1;
+    g.bcval[s] = 0.0;
+    if (L->side_ghost[s]) g.kind[s] = SK_GHOST;
+    else if (L->side_domain[s]) {
+      int type = bc ? (side ? bc->hi_type[dir] : bc->lo_type[dir]) : -1;
+      g.kind[s] = type == 0 ? SK_PHYS_DIRI : type == 1 ? SK_PHYS_NEUM : SK_PHYS_NONE;
+      if (bc) g.bcval[s] = side ? bc->hi_val[dir] : bc->lo_val[dir];
+    } else g.kind[s] = SK_FROZEN;
+  }
+  return g;
+}
+
+static OpArgs make_args(const sg_op* op) {
+  OpArgs a;
+  a.g = make_geom(op->lay, &op->bc);
+  a.prm = phys(op->prm);
+  a.alpha = op->alpha; a.beta = op->beta;
+  a.dx0 = op->dx[0]; a.dx1 = op->dx[1];
+  a.dxi0 = 1.0 / (op->dx[0] * op->dx[0]);
+  a.dxi1 = 1.0 / (op->dx[1] * op->dx[1]);
+  a.has_a = op->alpha != 0.0;
+  a.aC = op->aCoef ? op->aCoef->p() : nullptr;
+  a.bX = op->bX->p(); a.bY = op->bY->p();
+  a.B = op->B->p(); a.Pi = op->Pi->p(); a.zb = op->zb->p(); a.mask = op->mask->p();
+  return a;
+}
+
+// ------------------------------------------------------------------------------------------------
+// context
+// ------------------------------------------------------------------------------------------------
+extern "C" int sg_nccl_unique_id(void* out128) {
+  REQUIRE(out128, "sg_nccl_unique_id: null");
+  return sgnccl_unique_id(out128, g_err);
+}
+
+extern "C" int sg_ctx_create(sg_ctx** out, int device, int rank, int nranks, const void* nccl_unique_id) {
+  REQUIRE(out, "sg_ctx_create: null out");
+  REQUIRE(nranks >= 1 && rank >= 0 && rank < nranks, "sg_ctx_create: bad rank %d/%d", rank, nranks);
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0)
+    return fail(SG_ERR_CUDA, "sg_ctx_create: no CUDA device (%s); this library has no CPU fallback", cudaGetErrorString(e));
+  REQUIRE(device >= 0 && device < ndev, "sg_ctx_create: device %d of %d", device, ndev);
+  CK(cudaSetDevice(device));
+  sg_ctx* c = new sg_ctx();
+  c->device = device; c->rank = rank; c->nranks = nranks;
+  CK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+  CK(cudaMalloc(&c->d_scalar, 64 * sizeof(double)));
+  CK(cudaMemsetAsync(c->d_scalar, 0, 64 * sizeof(double), c->stream));
+  CK(cudaMallocHost(&c->h_scalar, 64 * sizeof(double)));
+  if (nranks > 1) {
+    REQUIRE(nccl_unique_id, "sg_ctx_create: nranks > 1 needs an NCCL unique id");
+    int r = c->nccl.init(nccl_unique_id, rank, nranks, g_err);
+    if (r != SG_OK) return r;
+  }
+  *out = c;
+  return SG_OK;
+}
+extern "C" int sg_ctx_destroy(sg_ctx* c) {
+  if (!c) return SG_OK;
+  cudaSetDevice(c->device);
+  cudaStreamSynchronize(c->stream);
+  c->nccl.destroy();
+  cudaFree(c->d_partial); cudaFree(c->d_scalar); cudaFreeHost(c->h_scalar);
+  cudaFreeHost(c->h_stage); cudaFree(c->d_stage); cudaFree(c->d_segs);
+  if (c->own_stream) cudaStreamDestroy(c->stream);
+  delete c;
+  return SG_OK;
+}
+extern "C" int sg_ctx_sync(sg_ctx* c) {
+  REQUIRE(c, "null ctx");
+  CK(cudaStreamSynchronize(c->stream));
+  CK(cudaGetLastError());
+  return SG_OK;
+}
+extern "C" int sg_ctx_set_stream(sg_ctx* c, void* s) {
+  REQUIRE(c, "null ctx");
+  CK(cudaStreamSynchronize(c->stream));
+  if (c->own_stream) cudaStreamDestroy(c->stream);
+  c->stream = (cudaStream_t)s;
+  c->own_stream = false;
+  return SG_OK;
+}
+extern "C" int sg_ctx_kernel_launches(sg_ctx* c, long long* out) {
+  REQUIRE(c && out, "null");
+  *out = c->launches;
+  return SG_OK;
+}
+extern "C" int sg_set_relax_mode(sg_ctx* c, int mode) {
+  REQUIRE(c && (mode == 0 || mode == 1), "sg_set_relax_mode");
+  c->relax_mode = mode;
+  return SG_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// layouts
+// ------------------------------------------------------------------------------------------------
+static int layout_finish(sg_layout* L) {
+  sg_ctx* c = L->ctx;
+  // per-rank bounding rectangles, each required to be tiled exactly by that rank's boxes
+  std::vector<Box> rp(c->nranks);
+  std::vector<long long> area(c->nranks, 0);
+  std::vector<bool> has(c->nranks, false);
+  for (int b = 0; b < L->nbox; b++) {
+    int r = L->owner[b];
+    REQUIRE(r >= 0 && r < c->nranks, "layout: box %d owned by rank %d of %d", b, r, c->nranks);
+    const Box& bx = L->boxes[b];
+    REQUIRE(bx.nx() > 0 && bx.ny() > 0, "layout: empty box %d", b);
+    if (!has[r]) { rp[r] = bx; has[r] = true; }
+    else
+      for (int d = 0; d < 2; d++) { rp[r].lo[d] = std::min(rp[r].lo[d], bx.lo[d]); rp[r].hi[d] = std::max(rp[r].hi[d], bx.hi[d]); }
+    area[r] += bx.npts();
+  }
+  for (int r = 0; r < c->nranks; r++)
+    if (has[r] && area[r] != rp[r].npts())
+      return fail(SG_ERR_UNSUPPORTED, "layout: boxes of rank %d do not tile a rectangle (%lld of %lld cells); "
+                  "multi-patch levels are not built yet", r, area[r], rp[r].npts());
+  L->has_local = has[c->rank];
+  if (!L->has_local) return SG_OK;
+  L->patch = rp[c->rank];
+  L->nx = L->patch.nx(); L->ny = L->patch.ny();
+  L->pitch = ((L->nx + 2 * SG_XOFF + 15) / 16) * 16;
+  L->rows = L->ny + SG_YOFF + SG_YTOP;
+  for (int s = 0; s < 4; s++) {
+    int dir = s >> 1, side = s & 1;
+    bool ondom = side ? L->patch.hi[dir] == L->domain.hi[dir] : L->patch.lo[dir] == L->domain.lo[dir];
+    L->side_domain[s] = ondom;
+    L->side_ghost[s] = false;
+    L->nbr[s] = -1;
+    bool spans = L->patch.lo[dir] == L->domain.lo[dir] && L->patch.hi[dir] == L->domain.hi[dir];
+    if (ondom && L->periodic[dir]) {
+      L->side_ghost[s] = true;
+      if (spans) L->wrap_local[dir] = true;
+    }
+    if (!(ondom && L->periodic[dir] && spans) && (!ondom || L->periodic[dir])) {
+      // need a neighbouring rank's patch across this side (only full-width strips in y are supported)
+      if (dir == 0) {
+        if (!ondom) {
+          // level does not reach the domain side and nobody is next to it: coarse-fine boundary
+          bool found = false;
+          for (int r = 0; r < c->nranks; r++)
+            if (r != c->rank && has[r]) {
+              bool adj = side ? rp[r].lo[0] == L->patch.hi[0] + 1 : rp[r].hi[0] == L->patch.lo[0] - 1;
+              if (adj && rp[r].lo[1] <= L->patch.hi[1] && rp[r].hi[1] >= L->patch.lo[1]) found = true;
+            }
+          if (found) return fail(SG_ERR_UNSUPPORTED, "layout: box partition splits the x direction across ranks");
+          L->side_ghost[s] = false;
+        } else return fail(SG_ERR_UNSUPPORTED, "layout: periodic x across ranks");
+      } else {
+        int want = side ? L->patch.hi[1] + 1 : L->patch.lo[1] - 1;
+        int ny_dom = L->domain.hi[1] - L->domain.lo[1] + 1;
+        if (ondom) want = side ? want - ny_dom : want + ny_dom;
+        int found = -1;
+        for (int r = 0; r < c->nranks; r++)
+          if (has[r] && r != c->rank) {
+            bool adj = side ? rp[r].lo[1] == want : rp[r].hi[1] == want;
+            if (adj && rp[r].lo[0] == L->patch.lo[0] && rp[r].hi[0] == L->patch.hi[0]) found = r;
+            else if (adj && rp[r].lo[0] <= L->patch.hi[0] && rp[r].hi[0] >= L->patch.lo[0])
+              return fail(SG_ERR_UNSUPPORTED, "layout: neighbouring rank patches must share the x extent");
+          }
+        if (found >= 0) { L->nbr[s] = found; L->side_ghost[s] = true; }
+        else REQUIRE(!ondom, "layout: periodic y side without an owner");
+      }
+    }
+  }
+  return SG_OK;
+}
+
+extern "C" int sg_layout_create(sg_ctx* ctx, sg_layout** out, int nbox, const int* boxes, const int* owner,
+                                const int domain[4], const int periodic[2]) {
+  REQUIRE(ctx && out && boxes && domain && periodic && nbox > 0, "sg_layout_create: bad arguments");
+  sg_layout* L = new sg_layout();
+  L->ctx = ctx; L->nbox = nbox;
+  L->boxes.resize(nbox); L->owner.resize(nbox);
+  for (int b = 0; b < nbox; b++) {
+    L->boxes[b].lo[0] = boxes[4 * b]; L->boxes[b].lo[1] = boxes[4 * b + 1];
+    L->boxes[b].hi[0] = boxes[4 * b + 2]; L->boxes[b].hi[1] = boxes[4 * b + 3];
+    L->owner[b] = owner ? owner[b] : 0;
+  }
+  L->domain.lo[0] = domain[0]; L->domain.lo[1] = domain[1]; L->domain.hi[0] = domain[2]; L->domain.hi[1] = domain[3];
+  L->periodic[0] = periodic[0]; L->periodic[1] = periodic[1];
+  int r = layout_finish(L);
+  if (r != SG_OK) { delete L; return r; }
+  *out = L;
+  return SG_OK;
+}
+extern "C" int sg_layout_coarsenable(const sg_layout* L, int ratio, int* out) {
+  REQUIRE(L && out && ratio >= 1, "sg_layout_coarsenable");
+  *out = 1;
+  for (const Box& b : L->boxes)
+    for (int d = 0; d < 2; d++)
+      if (fdiv(b.lo[d], ratio) * ratio != b.lo[d] || fdiv(b.hi[d], ratio) * ratio + ratio - 1 != b.hi[d]) { *out = 0; return SG_OK; }
+  return SG_OK;
+}
+extern "C" int sg_layout_coarsen(sg_layout* L, int ratio, sg_layout** out) {
+  REQUIRE(L && out && ratio >= 1, "sg_layout_coarsen");
+  sg_layout* C = new sg_layout();
+  C->ctx = L->ctx; C->nbox = L->nbox;
+  C->boxes.resize(L->nbox); C->owner = L->owner;
+  for (int b = 0; b < L->nbox; b++)
+    for (int d = 0; d < 2; d++) { C->boxes[b].lo[d] = fdiv(L->boxes[b].lo[d], ratio); C->boxes[b].hi[d] = fdiv(L->boxes[b].hi[d], ratio); }
+  for (int d = 0; d < 2; d++) { C->domain.lo[d] = fdiv(L->domain.lo[d], ratio); C->domain.hi[d] = fdiv(L->domain.hi[d], ratio); }
+  C->periodic[0] = L->periodic[0]; C->periodic[1] = L->periodic[1];
+  int r = layout_finish(C);
+  if (r != SG_OK) { delete C; return r; }
+  *out = C;
+  return SG_OK;
+}
+extern "C" int sg_layout_nbox(const sg_layout* L, int* nbox) {
+  REQUIRE(L && nbox, "sg_layout_nbox");
+  *nbox = L->nbox;
+  return SG_OK;
+}
+extern "C" int sg_field_destroy(sg_field* f);
+extern "C" int sg_layout_destroy(sg_layout* L) {
+  if (!L) return SG_OK;
+  for (sg_field* w : L->ws) sg_field_destroy(w);
+  delete L;
+  return SG_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// fields
+// ------------------------------------------------------------------------------------------------
+extern "C" int sg_field_create(sg_layout* L, sg_field** out, int ncomp, int nghost, int centering) {
+  REQUIRE(L && out && ncomp >= 1 && nghost >= 0 && nghost <= 2 && centering >= 0 && centering <= 2, "sg_field_create: bad arguments");
+  sg_field* f = new sg_field();
+  f->lay = L; f->ncomp = ncomp; f->ng = nghost; f->cent = centering;
+  if (L->has_local) {
+    f->comp_stride = (size_t)L->rows * L->pitch;
+    CK(cudaMalloc(&f->base, f->comp_stride * ncomp * sizeof(double)));
+    CK(cudaMemsetAsync(f->base, 0, f->comp_stride * ncomp * sizeof(double), L->ctx->stream));
+  }
+  *out = f;
+  return SG_OK;
+}
+extern "C" int sg_field_destroy(sg_field* f) {
+  if (!f) return SG_OK;
+  if (f->base) {
+    cudaStreamSynchronize(f->lay->ctx->stream);
+    cudaFree(f->base);
+  }
+  delete f;
+  return SG_OK;
+}
+// work field k of a layout (same shape as every other field of the layout)
+static int ws_field(sg_layout* L, int k, int ncomp, sg_field** out) {
+  if ((int)L->ws.size() <= k) L->ws.resize(k + 1, nullptr);
+  if (!L->ws[k] || L->ws[k]->ncomp < ncomp) {
+    if (L->ws[k]) sg_field_destroy(L->ws[k]);
+    SGCALL(sg_field_create(L, &L->ws[k], ncomp, 2, SG_CELL));
+  }
+  *out = L->ws[k];
+  return SG_OK;
+}
+
+// rectangle of box b's FArrayBox in the field's centering, ghosts included
+static Box fab_rect(const sg_field* f, int b, int ng) {
+  Box r = f->lay->boxes[b];
+  for (int d = 0; d < 2; d++) { r.lo[d] -= ng; r.hi[d] += ng; }
+  if (f->cent == SG_XFACE) r.hi[0] += 1;
+  if (f->cent == SG_YFACE) r.hi[1] += 1;
+  return r;
+}
+static Box patch_rect(const sg_field* f) {
+  Box r = f->lay->patch;
+  if (f->cent == SG_XFACE) r.hi[0] += 1;
+  if (f->cent == SG_YFACE) r.hi[1] += 1;
+  return r;
+}
+// pieces of box b's FAB that are copied on upload: the valid region plus the ghost cells lying outside the patch
+static int upload_rects(const sg_field* f, int b, Box out[5]) {
+  int n = 0;
+  Box F = fab_rect(f, b, f->ng), V = fab_rect(f, b, 0), Pv = patch_rect(f);
+  out[n++] = V;
+  if (f->ng == 0) return n;
+  Box r;
+  if (F.lo[1] < Pv.lo[1]) { r = F; r.hi[1] = Pv.lo[1] - 1; out[n++] = r; }
+  if (F.hi[1] > Pv.hi[1]) { r = F; r.lo[1] = Pv.hi[1] + 1; out[n++] = r; }
+  int m0 = std::max(F.lo[1], Pv.lo[1]), m1 = std::min(F.hi[1], Pv.hi[1]);
+  if (m0 <= m1) {
+    if (F.lo[0] < Pv.lo[0]) { r = F; r.lo[1] = m0; r.hi[1] = m1; r.hi[0] = Pv.lo[0] - 1; out[n++] = r; }
+    if (F.hi[0] > Pv.hi[0]) { r = F; r.lo[1] = m0; r.hi[1] = m1; r.lo[0] = Pv.hi[0] + 1; out[n++] = r; }
+  }
+  return n;
+}
+static inline ptrdiff_t dev_off(const sg_field* f, int gi, int gj) {
+  return (ptrdiff_t)(gj - f->lay->patch.lo[1]) * f->lay->pitch + (gi - f->lay->patch.lo[0]);
+}
+
+extern "C" int sg_field_upload_box(sg_field* f, int box, const double* host) {
+  REQUIRE(f && host && box >= 0 && box < f->lay->nbox, "sg_field_upload_box: bad arguments");
+  sg_layout* L = f->lay;
+  REQUIRE(L->owner[box] == L->ctx->rank, "sg_field_upload_box: box %d is owned by rank %d", box, L->owner[box]);
+  Box F = fab_rect(f, box, f->ng);
+  Box rs[5];
+  int n = upload_rects(f, box, rs);
+  size_t fabn = (size_t)F.nx() * F.ny();
+  for (int c = 0; c < f->ncomp; c++)
+    for (int k = 0; k < n; k++) {
+      const Box& r = rs[k];
+      const double* src = host + c * fabn + (size_t)(r.lo[1] - F.lo[1]) * F.nx() + (r.lo[0] - F.lo[0]);
+      double* dst = f->p(c) + dev_off(f, r.lo[0], r.lo[1]);
+      CK(cudaMemcpy2DAsync(dst, (size_t)L->pitch * 8, src, (size_t)F.nx() * 8, (size_t)r.nx() * 8, r.ny(), cudaMemcpyHostToDevice, L->ctx->stream));
+    }
+  CK(cudaStreamSynchronize(L->ctx->stream)); // host buffer may be reused by the caller
+  return SG_OK;
+}
+extern "C" int sg_field_download_box(const sg_field* f, int box, double* host) {
+  REQUIRE(f && host && box >= 0 && box < f->lay->nbox, "sg_field_download_box: bad arguments");
+  sg_layout* L = f->lay;
+  REQUIRE(L->owner[box] == L->ctx->rank, "sg_field_download_box: box %d is owned by rank %d", box, L->owner[box]);
+  Box F = fab_rect(f, box, f->ng);
+  size_t fabn = (size_t)F.nx() * F.ny();
+  for (int c = 0; c < f->ncomp; c++) {
+    const double* src = f->p(c) + dev_off(f, F.lo[0], F.lo[1]);
+    CK(cudaMemcpy2DAsync(host + c * fabn, (size_t)F.nx() * 8, src, (size_t)L->pitch * 8, (size_t)F.nx() * 8, F.ny(), cudaMemcpyDeviceToHost, L->ctx->stream));
+  }
+  CK(cudaStreamSynchronize(L->ctx->stream));
+  return SG_OK;
+}
+
+static int ensure_stage(sg_ctx* c, size_t ndoubles, size_t nsegs) {
+  if (c->h_stage_cap < ndoubles) {
+    CK(cudaStreamSynchronize(c->stream));
+    cudaFreeHost(c->h_stage); cudaFree(c->d_stage);
+    c->h_stage = nullptr; c->d_stage = nullptr;
+    CK(cudaMallocHost(&c->h_stage, ndoubles * sizeof(double)));
+    CK(cudaMalloc(&c->d_stage, ndoubles * sizeof(double)));
+    c->h_stage_cap = c->d_stage_cap = ndoubles;
+  }
+  if (c->segs_cap < nsegs) {
+    CK(cudaStreamSynchronize(c->stream));
+    cudaFree(c->d_segs);
+    CK(cudaMalloc(&c->d_segs, nsegs * sizeof(CopySeg)));
+    c->segs_cap = nsegs;
+  }
+  return SG_OK;
+}
+
+// batched upload: pack every owned FAB into pinned memory, one H2D copy, one scatter kernel
+extern "C" int sg_field_upload(sg_field* f, const double* const* fabs) {
+  REQUIRE(f && fabs, "sg_field_upload: bad arguments");
+  sg_layout* L = f->lay;
+  sg_ctx* c = L->ctx;
+  if (!L->has_local) return SG_OK;
+  size_t total = 0;
+  std::vector<CopySeg> segs;
+  std::vector<size_t> offs(L->nbox, 0);
+  for (int b = 0; b < L->nbox; b++) {
+    if (L->owner[b] != c->rank) continue;
+    Box F = fab_rect(f, b, f->ng);
+    offs[b] = total;
+    Box rs[5];
+    int n = upload_rects(f, b, rs);
+    for (int cc = 0; cc < f->ncomp; cc++)
+      for (int k = 0; k < n; k++) {
+        CopySeg s;
+        s.so = (long long)(total + (size_t)cc * F.nx() * F.ny() + (size_t)(rs[k].lo[1] - F.lo[1]) * F.nx() + (rs[k].lo[0] - F.lo[0]));
+        s.dofs = (long long)((f->p(cc) - f->base) + dev_off(f, rs[k].lo[0], rs[k].lo[1]));
+        s.nx = rs[k].nx(); s.ny = rs[k].ny(); s.sp = F.nx(); s.dp = L->pitch;
+        segs.push_back(s);
+      }
+    total += (size_t)F.nx() * F.ny() * f->ncomp;
+  }
+  SGCALL(ensure_stage(c, total, segs.size()));
+  CK(cudaStreamSynchronize(c->stream)); // staging buffers may still be in use by a previous transfer
+  for (int b = 0; b < L->nbox; b++) {
+    if (L->owner[b] != c->rank) continue;
+    Box F = fab_rect(f, b, f->ng);
+    REQUIRE(fabs[b], "sg_field_upload: null FAB pointer for owned box %d", b);
+    memcpy(c->h_stage + offs[b], fabs[b], (size_t)F.nx() * F.ny() * f->ncomp * sizeof(double));
+  }
+  CK(cudaMemcpyAsync(c->d_stage, c->h_stage, total * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+  CK(cudaMemcpyAsync(c->d_segs, segs.data(), segs.size() * sizeof(CopySeg), cudaMemcpyHostToDevice, c->stream));
+  // valid regions first, then ghost pieces: launch in two passes so a ghost piece never races a valid copy
+  LAUNCH(c, k_copy_segs, dim3(4, (unsigned)segs.size()), 256, f->base, c->d_stage, c->d_segs, (int)segs.size());
+  CK(cudaStreamSynchronize(c->stream)); // segs vector goes out of scope
+  return SG_OK;
+}
+extern "C" int sg_field_download(const sg_field* f, double* const* fabs) {
+  REQUIRE(f && fabs, "sg_field_download: bad arguments");
+  sg_layout* L = f->lay;
+  sg_ctx* c = L->ctx;
+  if (!L->has_local) return SG_OK;
+  size_t total = 0;
+  std::vector<CopySeg> segs;
+  std::vector<size_t> offs(L->nbox, 0);
+  for (int b = 0; b < L->nbox; b++) {
+    if (L->owner[b] != c->rank) continue;
+    Box F = fab_rect(f, b, f->ng);
+    offs[b] = total;
+    for (int cc = 0; cc < f->ncomp; cc++) {
+      CopySeg s;
+      s.dofs = (long long)(total + (size_t)cc * F.nx() * F.ny());
+      s.so = (long long)((f->p(cc) - f->base) + dev_off(f, F.lo[0], F.lo[1]));
+      s.nx = F.nx(); s.ny = F.ny(); s.sp = L->pitch; s.dp = F.nx();
+      segs.push_back(s);
+    }
+    total += (size_t)F.nx() * F.ny() * f->ncomp;
+  }
+  SGCALL(ensure_stage(c, total, segs.size()));
+  CK(cudaMemcpyAsync(c->d_segs, segs.data(), segs.size() * sizeof(CopySeg), cudaMemcpyHostToDevice, c->stream));
+  LAUNCH(c, k_copy_segs, dim3(4, (unsigned)segs.size()), 256, c->d_stage, f->base, c->d_segs, (int)segs.size());
+  CK(cudaMemcpyAsync(c->h_stage, c->d_stage, total * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+  CK(cudaStreamSynchronize(c->stream));
+  for (int b = 0; b < L->nbox; b++) {
+    if (L->owner[b] != c->rank) continue;
+    Box F = fab_rect(f, b, f->ng);
+    REQUIRE(fabs[b], "sg_field_download: null FAB pointer for owned box %d", b);
+    memcpy(fabs[b], c->h_stage + offs[b], (size_t)F.nx() * F.ny() * f->ncomp * sizeof(double));
+  }
+  return SG_OK;
+}
+extern "C" int sg_field_device_view(sg_field* f, void** base, long long* pitch, long long* comp_stride, int patch_lo[2],
+                                    int patch_hi[2], long long* offset_of_patch_lo) {
+  REQUIRE(f && base, "sg_field_device_view");
+  *base = f->base;
+  if (pitch) *pitch = f->lay->pitch;
+  if (comp_stride) *comp_stride = (long long)f->comp_stride;
+  if (patch_lo) { patch_lo[0] = f->lay->patch.lo[0]; patch_lo[1] = f->lay->patch.lo[1]; }
+  if (patch_hi) { patch_hi[0] = f->lay->patch.hi[0]; patch_hi[1] = f->lay->patch.hi[1]; }
+  if (offset_of_patch_lo) *offset_of_patch_lo = (long long)SG_YOFF * f->lay->pitch + SG_XOFF;
+  return SG_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// ghost filling
+// ------------------------------------------------------------------------------------------------
+// ghosts that come from other valid cells of the level: periodic images inside the patch, neighbouring ranks.
+// depth <= 2.  Replaces LevelData::exchange (the in-patch box-to-box part needs no copy at all: boxes of one
+// rank are merged into one array).
+static int fill_ghosts(sg_field* f, int depth) {
+  sg_layout* L = f->lay;
+  sg_ctx* c = L->ctx;
+  if (!L->has_local) return SG_OK;
+  Geom g = make_geom(L, nullptr);
+  int ex = f->cent == SG_XFACE, ey = f->cent == SG_YFACE;
+  for (int comp = 0; comp < f->ncomp; comp++) {
+    double* p = f->p(comp);
+    if (L->wrap_local[0]) {
+      int n = (g.ny + ey) * depth;
+      LAUNCH(c, k_wrap_ghost, (n + 127) / 128, 128, p, g, 0, depth, ex, ey);
+    }
+    if (L->wrap_local[1]) {
+      int n = (g.nx + 2 * depth + ex) * depth;
+      LAUNCH(c, k_wrap_ghost, (n + 127) / 128, 128, p, g, 1, depth, ex, ey);
+    }
+  }
+  if (L->nbr[2] >= 0 || L->nbr[3] >= 0) {
+    // rows are contiguous (x fastest, full pitch incl. ghost columns): send/recv straight from the field
+    size_t cnt = (size_t)depth * L->pitch;
+    for (int comp = 0; comp < f->ncomp; comp++) {
+      double* p = f->p(comp) - SG_XOFF;
+      SGCALL(c->nccl.group_start(g_err));
+      // receives are posted high-side first so that, when both neighbours are the same rank (2 ranks, periodic),
+      // the peer's [low send, high send] order pairs with [high recv, low recv] here
+      if (L->nbr[3] >= 0) SGCALL(c->nccl.recv(p + (ptrdiff_t)(g.ny + ey) * L->pitch, cnt, L->nbr[3], c->stream, g_err));
+      if (L->nbr[2] >= 0) SGCALL(c->nccl.recv(p + (ptrdiff_t)(-depth) * L->pitch, cnt, L->nbr[2], c->stream, g_err));
+      if (L->nbr[2] >= 0) SGCALL(c->nccl.send(p + (ptrdiff_t)ey * L->pitch, cnt, L->nbr[2], c->stream, g_err));
+      if (L->nbr[3] >= 0) SGCALL(c->nccl.send(p + (ptrdiff_t)(g.ny - depth) * L->pitch, cnt, L->nbr[3], c->stream, g_err));
+      SGCALL(c->nccl.group_end(g_err));
+    }
+  }
+  return SG_OK;
+}
+static bool has_ghost_sides(const sg_layout* L) { return L->side_ghost[0] || L->side_ghost[1] || L->side_ghost[2] || L->side_ghost[3]; }
+
+static int phys_bc(sg_field* f, const sg_bc* bc, const double dx[2], int homogeneous) {
+  sg_layout* L = f->lay;
+  if (!L->has_local) return SG_OK;
+  Geom g = make_geom(L, bc);
+  bool any = false;
+  for (int s = 0; s < 4; s++) any |= (g.kind[s] == SK_PHYS_DIRI || g.kind[s] == SK_PHYS_NEUM);
+  if (!any) return SG_OK;
+  int n = std::max(g.nx, g.ny);
+  LAUNCH(L->ctx, k_bc_ghost, dim3((n + 127) / 128, 4), 128, f->p(), g, dx[0], dx[1], homogeneous);
+  return SG_OK;
+}
+
+extern "C" int sg_exchange(sg_field* f, int corners) {
+  REQUIRE(f, "sg_exchange: null");
+  (void)corners; // rows/columns are moved at full width, so corner ghosts are always consistent
+  return fill_ghosts(f, std::max(1, std::min(f->ng, 2)));
+}
+extern "C" int sg_apply_bc(sg_field* f, const sg_bc* bc, const double dx[2], int homogeneous) {
+  REQUIRE(f && bc && dx, "sg_apply_bc: null");
+  return phys_bc(f, bc, dx, homogeneous);
+}
+static int extrap_ghost(sg_field* f, int copy_only) {
+  sg_layout* L = f->lay;
+  if (!L->has_local) return SG_OK;
+  REQUIRE(f->cent == SG_CELL, "ExtrapGhostCells: cell data only");
+  Geom g = make_geom(L, nullptr);
+  for (int dir = 0; dir < 2; dir++) {
+    int n = (dir == 0 ? g.ny : g.nx) + 2;
+    LAUNCH(L->ctx, k_extrap_ghost, dim3((n + 127) / 128, f->ncomp), 128, f->p(), g, dir, copy_only, f->comp_stride, f->ncomp);
+  }
+  return SG_OK;
+}
+extern "C" int sg_extrap_ghost_cells(sg_field* f) { REQUIRE(f, "null"); return extrap_ghost(f, 0); }
+extern "C" int sg_copy_ghost_cells(sg_field* f) { REQUIRE(f, "null"); return extrap_ghost(f, 1); }
+
+// ------------------------------------------------------------------------------------------------
+// stand-alone field kernels
+// ------------------------------------------------------------------------------------------------
+extern "C" int sg_nonlinear_level(const sg_params* p, sg_field* nl, sg_field* dnl, const sg_field* u, const sg_field* B,
+                                  const sg_field* mask, const sg_field* Pi, const sg_field* zb) {
+  REQUIRE(p && nl && dnl && u && B && mask && Pi && zb, "sg_nonlinear_level: null");
+  sg_layout* L = u->lay;
+  if (!L->has_local) return SG_OK;
+  Geom g = make_geom(L, nullptr);
+  LAUNCH(L->ctx, k_nl, grid2(g.nx, g.ny, B2D), B2D, nl->p(), dnl->p(), u->p(), B->p(), mask->p(), Pi->p(), zb->p(), g, phys(*p));
+  return SG_OK;
+}
+extern "C" int sg_gradient_cc(sg_field* grad2, sg_field* phi, const sg_field* mask, const double dx[2]) {
+  REQUIRE(grad2 && phi && dx && grad2->ncomp >= 2, "sg_gradient_cc: bad arguments");
+  sg_layout* L = phi->lay;
+  if (!L->has_local) return SG_OK;
+  Geom g = make_geom(L, nullptr);
+  LAUNCH(L->ctx, k_gradient_cc, grid2(g.nx, g.ny, B2D), B2D, grad2->p(0), grad2->p(1), phi->p(), mask ? mask->p() : nullptr, g, dx[0], dx[1]);
+  return SG_OK;
+}
+extern "C" int sg_compute_re(const sg_params* p, sg_field* Re, const sg_field* B, const sg_field* gradH) {
+  REQUIRE(p && Re && B && gradH && gradH->ncomp >= 2, "sg_compute_re: bad arguments");
+  sg_layout* L = Re->lay;
+  if (!L->has_local) return SG_OK;
+  Geom g = make_geom(L, nullptr);
+  LAUNCH(L->ctx, k_compute_re, grid2(g.nx + 2, g.ny + 2, B2D), B2D, Re->p(), B->p(), gradH->p(0), gradH->p(1), g, phys(*p));
+  return SG_OK;
+}
+extern "C" int sg_divergence(sg_field* div, const sg_field* ux, const sg_field* uy, const double dx[2]) {
+  REQUIRE(div && ux && uy && dx, "sg_divergence: null");
+  sg_layout* L = div->lay;
+  if (!L->has_local) return SG_OK;
+  Geom g = make_geom(L, nullptr);
+  LAUNCH(L->ctx, k_divergence, grid2(g.nx, g.ny, B2D), B2D, div->p(), ux->p(), uy->p(), g, dx[0], dx[1]);
+  return SG_OK;
+}
+
+// AmrHydro::WFlx_level (src/AmrHydro.cpp:1415-1539), no coarser level
+extern "C" int sg_wflx_level(sg_ctx* ctx, const sg_params* p, sg_field* bX, sg_field* bY, sg_field* u, const sg_field* u_coarse,
+                             const sg_field* B, const sg_field* mask, const double dx[2]) {
+  REQUIRE(ctx && p && bX && bY && u && B && mask && dx, "sg_wflx_level: null");
+  if (u_coarse) return fail(SG_ERR_UNSUPPORTED, "sg_wflx_level: coarse-fine gradient interpolation not built yet");
+  sg_layout* L = u->lay;
+  if (!L->has_local) return SG_OK;
+  Geom g = make_geom(L, nullptr);
+  sg_field *grad, *Re;
+  SGCALL(ws_field(L, 1, 2, &grad));
+  SGCALL(ws_field(L, 2, 1, &Re));
+  LAUNCH(ctx, k_gradient_cc, grid2(g.nx, g.ny, B2D), B2D, grad->p(0), grad->p(1), u->p(), p->use_mask_grad ? mask->p() : nullptr, g, dx[0], dx[1]);
+  int ngsave = grad->ng;
+  grad->ng = 1;
+  SGCALL(fill_ghosts(grad, 1)); // lvlgradH.exchange()
+  SGCALL(extrap_ghost(grad, 0)); // ExtrapGhostCells(lvlgradH, levelDomain)
+  grad->ng = ngsave;
+  LAUNCH(ctx, k_compute_re, grid2(g.nx + 2, g.ny + 2, B2D), B2D, Re->p(), B->p(), grad->p(0), grad->p(1), g, phys(*p));
+  LAUNCH(ctx, k_bcoef_faces, grid2(g.nx + 1, g.ny + 1, B2D), B2D, bX->p(), bY->p(), Re->p(), B->p(), mask->p(), g, phys(*p));
+  return SG_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// factory
+// ------------------------------------------------------------------------------------------------
+extern "C" int sg_factory_define(sg_ctx* ctx, sg_factory** out, int nlevels, sg_layout* const* grids, const int* ref_ratios,
+                                 const double coarse_dx[2], const sg_bc* bc, double alpha, sg_field* const* aCoef, double beta,
+                                 sg_field* const* bCoefX, sg_field* const* bCoefY, const sg_params* params,
+                                 sg_field* const* B, sg_field* const* Pi, sg_field* const* zb, sg_field* const* iceMask) {
+  REQUIRE(ctx && out && nlevels >= 1 && grids && coarse_dx && bc && aCoef && bCoefX && bCoefY && params && B && Pi && zb && iceMask,
+          "sg_factory_define: null argument");
+  REQUIRE(nlevels == 1 || ref_ratios, "sg_factory_define: ref_ratios needed");
+  sg_factory* f = new sg_factory();
+  f->ctx = ctx; f->nlevels = nlevels;
+  f->bc = *bc; f->alpha = alpha; f->beta = beta; f->prm = *params;
+  f->dx.resize(nlevels);
+  f->dx[0] = {coarse_dx[0], coarse_dx[1]};
+  for (int l = 0; l < nlevels; l++) {
+    f->grids.push_back(grids[l]);
+    f->aCoef.push_back(aCoef[l]); f->bX.push_back(bCoefX[l]); f->bY.push_back(bCoefY[l]);
+    f->B.push_back(B[l]); f->Pi.push_back(Pi[l]); f->zb.push_back(zb[l]); f->mask.push_back(iceMask[l]);
+    f->ref_ratios.push_back(l < nlevels - 1 ? ref_ratios[l] : (ref_ratios ? ref_ratios[std::max(0, nlevels - 2)] : 2));
+    if (l > 0) f->dx[l] = {f->dx[l - 1][0] / f->ref_ratios[l - 1], f->dx[l - 1][1] / f->ref_ratios[l - 1]};
+  }
+  *out = f;
+  return SG_OK;
+}
+extern "C" int sg_factory_destroy(sg_factory* f) { delete f; return SG_OK; }
+extern "C" int sg_factory_refToFiner(const sg_factory* f, int level, int* out) {
+  REQUIRE(f && out, "null");
+  if (level < 0 || level >= f->nlevels) return fail(SG_ERR_ABORT, "Domain not found in AMR hierarchy");
+  *out = f->ref_ratios[level];
+  return SG_OK;
+}
+
+// coefficient ghosts on SK_GHOST sides (periodic images / neighbouring ranks): depth 1, needed by the fused sweep
+static int coef_ghosts(sg_op* op, bool only_b) {
+  if (!has_ghost_sides(op->lay)) return SG_OK;
+  SGCALL(fill_ghosts(op->bX, 1));
+  SGCALL(fill_ghosts(op->bY, 1));
+  if (only_b) return SG_OK;
+  SGCALL(fill_ghosts(op->B, 1));
+  SGCALL(fill_ghosts(op->Pi, 1));
+  SGCALL(fill_ghosts(op->zb, 1));
+  SGCALL(fill_ghosts(op->mask, 1));
+  if (op->alpha != 0.0) SGCALL(fill_ghosts(op->aCoef, 1));
+  return SG_OK;
+}
+
+static sg_op* new_op(sg_factory* f, int level) {
+  sg_op* op = new sg_op();
+  op->ctx = f->ctx;
+  op->alpha = f->alpha; op->beta = f->beta; op->bc = f->bc; op->prm = f->prm;
+  op->level = level;
+  op->update_operator = f->prm.bcoeff_otf != 0;
+  return op;
+}
+
+extern "C" int sg_op_destroy(sg_op* op) {
+  if (!op) return SG_OK;
+  if (op->owns_coefs) {
+    sg_field_destroy(op->aCoef); sg_field_destroy(op->bX); sg_field_destroy(op->bY);
+    sg_field_destroy(op->B); sg_field_destroy(op->Pi); sg_field_destroy(op->zb); sg_field_destroy(op->mask);
+  }
+  if (op->owns_layout) sg_layout_destroy(op->lay);
+  delete op;
+  return SG_OK;
+}
+
+static int avg_cell(sg_field* c, const sg_field* f, int r) {
+  sg_layout* Lc = c->lay;
+  if (!Lc->has_local) return SG_OK;
+  LAUNCH(Lc->ctx, k_avg_cell, grid2(Lc->nx, Lc->ny, B2D), B2D, c->p(), Lc->pitch, Lc->nx, Lc->ny, f->p(), f->lay->pitch, r);
+  return SG_OK;
+}
+static int avg_face(sg_field* c, const sg_field* f, int r) {
+  sg_layout* Lc = c->lay;
+  if (!Lc->has_local) return SG_OK;
+  int dir = c->cent == SG_XFACE ? 0 : 1;
+  LAUNCH(Lc->ctx, k_avg_face, grid2(Lc->nx + 1, Lc->ny + 1, B2D), B2D, c->p(), Lc->pitch, Lc->nx, Lc->ny, f->p(), f->lay->pitch, r, dir);
+  return SG_OK;
+}
+
+extern "C" int sg_factory_MGnewOp(sg_factory* f, int level, int depth, int homo_only, sg_op** out) {
+  (void)homo_only;
+  REQUIRE(f && out && level >= 0 && level < f->nlevels && depth >= 0, "sg_factory_MGnewOp: bad arguments");
+  *out = nullptr;
+  int coarsening = 1;
+  for (int i = 0; i < depth; i++) coarsening *= 2;
+  const int s_maxCoarse = 2; // src/AMRNonLinearPoissonOp.cpp:32
+  if (coarsening > 1) {
+    int ok = 0;
+    SGCALL(sg_layout_coarsenable(f->grids[level], coarsening * s_maxCoarse, &ok));
+    if (!ok) return SG_OK; // NULL: cannot coarsen further
+  }
+  sg_op* op = new_op(f, level);
+  op->depth = depth;
+  op->dx[0] = f->dx[level][0] * coarsening; op->dx[1] = f->dx[level][1] * coarsening;
+  if (depth == 0) {
+    op->lay = f->grids[level];
+    op->aCoef = f->aCoef[level]; op->bX = f->bX[level]; op->bY = f->bY[level];
+    op->B = f->B[level]; op->Pi = f->Pi[level]; op->zb = f->zb[level]; op->mask = f->mask[level];
+  } else {
+    sg_layout* Lc;
+    int r = sg_layout_coarsen(f->grids[level], coarsening, &Lc);
+    if (r != SG_OK) { delete op; return r; }
+    op->lay = Lc; op->owns_layout = true; op->owns_coefs = true;
+    SGCALL(sg_field_create(Lc, &op->aCoef, 1, 0, SG_CELL));
+    SGCALL(sg_field_create(Lc, &op->bX, 1, 0, SG_XFACE));
+    SGCALL(sg_field_create(Lc, &op->bY, 1, 0, SG_YFACE));
+    SGCALL(sg_field_create(Lc, &op->B, 1, 1, SG_CELL));
+    SGCALL(sg_field_create(Lc, &op->Pi, 1, 1, SG_CELL));
+    SGCALL(sg_field_create(Lc, &op->zb, 1, 1, SG_CELL));
+    SGCALL(sg_field_create(Lc, &op->mask, 1, 1, SG_CELL));
+    // arithmetic averages of the FINEST data by 2^depth (src/VCAMRNonLinearPoissonOp.cpp:1130-1139)
+    if (f->alpha != 0.0) SGCALL(avg_cell(op->aCoef, f->aCoef[level], coarsening));
+    SGCALL(avg_face(op->bX, f->bX[level], coarsening));
+    SGCALL(avg_face(op->bY, f->bY[level], coarsening));
+    SGCALL(avg_cell(op->B, f->B[level], coarsening));
+    SGCALL(avg_cell(op->Pi, f->Pi[level], coarsening));
+    SGCALL(avg_cell(op->zb, f->zb[level], coarsening));
+    SGCALL(avg_cell(op->mask, f->mask[level], coarsening));
+    if (Lc->has_local) { // NeumBCForB on the coarse gap height (:1142-1148)
+      Geom g = make_geom(Lc, nullptr);
+      int n = std::max(g.nx, g.ny);
+      LAUNCH(f->ctx, k_neum_copy_ghost, dim3((n + 127) / 128, 4), 128, op->B->p(), g);
+    }
+  }
+  SGCALL(coef_ghosts(op, false));
+  *out = op;
+  return SG_OK;
+}
+extern "C" int sg_factory_AMRnewOp(sg_factory* f, int level, sg_op** out) {
+  REQUIRE(f && out && level >= 0 && level < f->nlevels, "sg_factory_AMRnewOp: bad arguments");
+  if (f->nlevels > 1) return fail(SG_ERR_UNSUPPORTED, "AMRnewOp: multi-level hierarchies are not built yet");
+  return sg_factory_MGnewOp(f, level, 0, 0, out);
+}
+
+// ------------------------------------------------------------------------------------------------
+// operator
+// ------------------------------------------------------------------------------------------------
+static int check_same(const sg_op* op, const sg_field* f, const char* what) {
+  if (!f) return fail(SG_ERR_INVALID, "%s: null field", what);
+  if (f->lay != op->lay && (f->lay->nx != op->lay->nx || f->lay->ny != op->lay->ny || f->lay->patch.lo[0] != op->lay->patch.lo[0] ||
+                            f->lay->patch.lo[1] != op->lay->patch.lo[1]))
+    return fail(SG_ERR_INVALID, "%s: field layout differs from the operator's", what);
+  return SG_OK;
+}
+
+// one levelGSRB iteration set
+static int relax_impl(sg_op* op, sg_field* phi, const sg_field* rhs, int iterations) {
+  sg_layout* L = op->lay;
+  sg_ctx* c = op->ctx;
+  if (!L->has_local || iterations <= 0) return SG_OK;
+  OpArgs a = make_args(op);
+  bool ghosts = has_ghost_sides(L);
+  if (c->relax_mode == 1) {
+    sg_field* scratch;
+    SGCALL(ws_field(L, 0, 1, &scratch));
+    if (ghosts) SGCALL(fill_ghosts(const_cast<sg_field*>(rhs), 1));
+    FusedArgs f;
+    f.a = a;
+    f.rhs = rhs->p();
+    f.sdx[0] = -op->dx[0]; f.sdx[1] = op->dx[0]; f.sdx[2] = -op->dx[1]; f.sdx[3] = op->dx[1];
+    f.nstrips = (L->nx + FUSED_COLS - 1) / FUSED_COLS;
+    // rows per warp: enough warps to fill 148 SMs x 16 warps, but segments of at least 32 rows when possible
+    int target_warps = 148 * 16;
+    int nsegs = std::max(1, std::min((L->ny + 31) / 32, (target_warps + f.nstrips - 1) / f.nstrips));
+    f.rows_per_warp = (L->ny + nsegs - 1) / nsegs;
+    f.nsegs = (L->ny + f.rows_per_warp - 1) / f.rows_per_warp;
+    int nwarps = f.nstrips * f.nsegs;
+    int blocks = (nwarps * 32 + 127) / 128;
+    for (int it = 0; it < iterations; it++) {
+      if (ghosts) SGCALL(fill_ghosts(phi, 2));
+      f.phi_in = phi->p();
+      f.phi_out = scratch->p();
+      if (a.has_a) LAUNCH(c, k_gsrb_fused<1>, blocks, 128, f);
+      else LAUNCH(c, k_gsrb_fused<0>, blocks, 128, f);
+      std::swap(phi->base, scratch->base); // out-of-place sweep: the field now owns the new buffer
+    }
+  } else {
+    for (int it = 0; it < iterations; it++) {
+      for (int pass = 0; pass < 2; pass++) {
+        if (ghosts) SGCALL(fill_ghosts(phi, 1));
+        SGCALL(phys_bc(phi, &op->bc, op->dx, 0));
+        int half = (L->nx + 1) / 2;
+        LAUNCH(c, k_gsrb_color, grid2(half, L->ny, B2D), B2D, phi->p(), rhs->p(), a, pass);
+      }
+    }
+  }
+  // trailing exchange + homogeneous BC fill (src/VCAMRNonLinearPoissonOp.cpp:751-759)
+  if (ghosts) SGCALL(fill_ghosts(phi, 1));
+  SGCALL(phys_bc(phi, &op->bc, op->dx, 1));
+  return SG_OK;
+}
+
+extern "C" int sg_op_relax(sg_op* op, sg_field* phi, const sg_field* rhs, int iterations, int amr_fasmg_iter, int depth) {
+  (void)amr_fasmg_iter; (void)depth;
+  REQUIRE(op, "sg_op_relax: null op");
+  SGCALL(check_same(op, phi, "relax(phi)"));
+  SGCALL(check_same(op, rhs, "relax(rhs)"));
+  REQUIRE(phi->ng >= 1, "relax: phi needs one ghost cell (CH_assert)");
+  return relax_impl(op, phi, rhs, iterations);
+}
+extern "C" int sg_op_relaxNF(sg_op* op, sg_field* phi, const sg_field* phi_coarse, const sg_field* rhs, int iterations,
+                             int amr_fasmg_iter, int depth, int print) {
+  (void)print;
+  if (phi_coarse) return fail(SG_ERR_UNSUPPORTED, "relaxNF: coarse-fine interpolation not built yet");
+  return sg_op_relax(op, phi, rhs, iterations, amr_fasmg_iter, depth);
+}
+
+// BC -> exchange -> (NL fused) kernel; mode 0 apply, 1 residual, 2 residual + max-norm into d_scalar[slot]
+static int apply_impl(sg_op* op, sg_field* out, sg_field* phi, const sg_field* rhs, int homogeneous, int mode, int slot) {
+  sg_layout* L = op->lay;
+  sg_ctx* c = op->ctx;
+  if (!L->has_local) return SG_OK;
+  OpArgs a = make_args(op);
+  SGCALL(phys_bc(phi, &op->bc, op->dx, homogeneous));
+  if (has_ghost_sides(L)) SGCALL(fill_ghosts(phi, 1));
+  unsigned long long* nb = reinterpret_cast<unsigned long long*>(c->d_scalar) + slot;
+  dim3 g = grid2(L->nx, L->ny, B2D);
+  if (mode == 0) LAUNCH(c, k_apply<0>, g, B2D, out->p(), phi->p(), nullptr, a, nb);
+  else if (mode == 1) LAUNCH(c, k_apply<1>, g, B2D, out->p(), phi->p(), rhs->p(), a, nb);
+  else {
+    CK(cudaMemsetAsync(nb, 0, sizeof(double), c->stream));
+    LAUNCH(c, k_apply<2>, g, B2D, out->p(), phi->p(), rhs->p(), a, nb);
+  }
+  return SG_OK;
+}
+
+extern "C" int sg_op_residual(sg_op* op, sg_field* lhs, sg_field* phi, const sg_field* rhs, int homogeneous) {
+  REQUIRE(op, "sg_op_residual: null op");
+  SGCALL(check_same(op, lhs, "residual(lhs)")); SGCALL(check_same(op, phi, "residual(phi)")); SGCALL(check_same(op, rhs, "residual(rhs)"));
+  // AMRNonLinearPoissonOp::residual under FAS always calls residualI(..., false) (src/AMRNonLinearPoissonOp.cpp:247-253)
+  (void)homogeneous;
+  return apply_impl(op, lhs, phi, rhs, 0, 1, 0);
+}
+extern "C" int sg_op_residualNF(sg_op* op, sg_field* lhs, sg_field* phi, const sg_field* phi_coarse, const sg_field* rhs, int homogeneous) {
+  REQUIRE(op, "sg_op_residualNF: null op");
+  if (phi_coarse) return fail(SG_ERR_UNSUPPORTED, "residualNF: coarse-fine interpolation not built yet");
+  if (homogeneous) return fail(SG_ERR_ABORT, "VCAMRNonLinearPoissonOp::residualI homogeneous");
+  SGCALL(check_same(op, lhs, "residualNF(lhs)")); SGCALL(check_same(op, phi, "residualNF(phi)")); SGCALL(check_same(op, rhs, "residualNF(rhs)"));
+  return apply_impl(op, lhs, phi, rhs, 0, 1, 0);
+}
+extern "C" int sg_op_applyOp(sg_op* op, sg_field* lhs, sg_field* phi, int homogeneous) {
+  REQUIRE(op, "sg_op_applyOp: null op");
+  SGCALL(check_same(op, lhs, "applyOp(lhs)")); SGCALL(check_same(op, phi, "applyOp(phi)"));
+  (void)homogeneous; // applyOp under FAS calls applyOpI(..., false) (src/AMRNonLinearPoissonOp.cpp:437-442)
+  return apply_impl(op, lhs, phi, nullptr, 0, 0, 0);
+}
+extern "C" int sg_op_applyOpMg(sg_op* op, sg_field* lhs, sg_field* phi, sg_field* phi_coarse, int homogeneous) {
+  REQUIRE(op, "sg_op_applyOpMg: null op");
+  if (phi_coarse) return fail(SG_ERR_UNSUPPORTED, "applyOpMg: coarse-fine interpolation not built yet");
+  SGCALL(check_same(op, lhs, "applyOpMg(lhs)")); SGCALL(check_same(op, phi, "applyOpMg(phi)"));
+  return apply_impl(op, lhs, phi, nullptr, homogeneous, 0, 0); // applyOpI(lhs, phi, homogeneous)
+}
+extern "C" int sg_op_applyOpNoBoundary(sg_op* op, sg_field* lhs, sg_field* phi) {
+  REQUIRE(op, "sg_op_applyOpNoBoundary: null op");
+  SGCALL(check_same(op, lhs, "applyOpNoBoundary(lhs)")); SGCALL(check_same(op, phi, "applyOpNoBoundary(phi)"));
+  sg_layout* L = op->lay;
+  if (!L->has_local) return SG_OK;
+  OpArgs a = make_args(op);
+  if (has_ghost_sides(L)) SGCALL(fill_ghosts(phi, 1));
+  LAUNCH(op->ctx, k_apply<0>, grid2(L->nx, L->ny, B2D), B2D, lhs->p(), phi->p(), nullptr, a, nullptr);
+  return SG_OK;
+}
+
+static int restrict_impl(sg_op* op, sg_field* resC, sg_field* phiC, sg_field* phiF, const sg_field* rhsF) {
+  sg_layout* L = op->lay;
+  sg_ctx* c = op->ctx;
+  if (!L->has_local) return SG_OK;
+  sg_layout* Lc = resC ? resC->lay : phiC->lay;
+  REQUIRE(Lc->nx * 2 == L->nx && Lc->ny * 2 == L->ny, "restrict: coarse layout is not the fine layout coarsened by 2");
+  OpArgs a = make_args(op);
+  if (resC) {
+    SGCALL(phys_bc(phiF, &op->bc, op->dx, 0));
+    if (has_ghost_sides(L)) SGCALL(fill_ghosts(phiF, 1));
+    CK(cudaMemsetAsync(resC->base, 0, resC->comp_stride * sizeof(double), c->stream)); // res.setVal(0.0)
+  }
+  if (phiC) CK(cudaMemsetAsync(phiC->base, 0, phiC->comp_stride * sizeof(double), c->stream)); // phiCoarse.setVal(0.0)
+  dim3 g = grid2(Lc->nx, Lc->ny, B2D);
+  if (phiC) LAUNCH(c, k_restrict<1>, g, B2D, resC ? resC->p() : nullptr, phiC->p(), Lc->pitch, phiF->p(), rhsF ? rhsF->p() : nullptr, a);
+  else LAUNCH(c, k_restrict<0>, g, B2D, resC->p(), nullptr, Lc->pitch, phiF->p(), rhsF->p(), a);
+  return SG_OK;
+}
+extern "C" int sg_op_restrictResidual(sg_op* op, sg_field* res_coarse, sg_field* phi_fine, const sg_field* phi_coarse,
+                                      const sg_field* rhs_fine, int homogeneous) {
+  REQUIRE(op && res_coarse, "sg_op_restrictResidual: null");
+  if (homogeneous) return fail(SG_ERR_ABORT, "VCAMRNonLinearPoissonOp::restrictResidual homogeneous");
+  if (phi_coarse) return fail(SG_ERR_UNSUPPORTED, "restrictResidual: coarse-fine interpolation not built yet");
+  SGCALL(check_same(op, phi_fine, "restrictResidual(phiFine)")); SGCALL(check_same(op, rhs_fine, "restrictResidual(rhsFine)"));
+  return restrict_impl(op, res_coarse, nullptr, phi_fine, rhs_fine);
+}
+extern "C" int sg_op_restrictR(sg_op* op, sg_field* phi_coarse, const sg_field* phi_fine) {
+  REQUIRE(op && phi_coarse, "sg_op_restrictR: null");
+  SGCALL(check_same(op, phi_fine, "restrictR(phiFine)"));
+  return restrict_impl(op, nullptr, phi_coarse, const_cast<sg_field*>(phi_fine), nullptr);
+}
+extern "C" int sg_op_prolongIncrement(sg_op* op, sg_field* phi, const sg_field* corr) {
+  REQUIRE(op && corr, "sg_op_prolongIncrement: null");
+  SGCALL(check_same(op, phi, "prolongIncrement(phi)"));
+  sg_layout* L = op->lay;
+  if (!L->has_local) return SG_OK;
+  REQUIRE(corr->lay->nx * 2 == L->nx && corr->lay->ny * 2 == L->ny, "prolongIncrement: coarse layout mismatch");
+  LAUNCH(op->ctx, k_prolong, grid2(L->nx, L->ny, B2D), B2D, phi->p(), L->pitch, L->nx, L->ny, corr->p(), nullptr, corr->lay->pitch);
+  return SG_OK;
+}
+
+extern "C" int sg_op_UpdateOperator(sg_op* op, sg_field* phi, const sg_field* phi_coarse, int depth, int amr_fasmg_iter, int homogeneous) {
+  (void)depth; (void)amr_fasmg_iter;
+  REQUIRE(op, "sg_op_UpdateOperator: null op");
+  if (homogeneous) return fail(SG_ERR_ABORT, "VCAMRNonLinearPoissonOp::UpdateOperator homogeneous");
+  SGCALL(check_same(op, phi, "UpdateOperator(phi)"));
+  sg_layout* L = op->lay;
+  if (!L->has_local) return SG_OK;
+  if (has_ghost_sides(L)) SGCALL(fill_ghosts(phi, 1));
+  SGCALL(phys_bc(phi, &op->bc, op->dx, 0));
+  SGCALL(sg_wflx_level(op->ctx, &op->prm, op->bX, op->bY, phi, phi_coarse, op->B, op->mask, op->dx));
+  SGCALL(coef_ghosts(op, true));
+  return SG_OK; // lambda is recomputed inside the kernels
+}
+extern "C" int sg_op_AverageOperator(sg_op* op, const sg_op* finest, int depth) {
+  REQUIRE(op && finest && depth >= 0, "sg_op_AverageOperator: bad arguments");
+  int coarsening = 1;
+  for (int i = 0; i < depth; i++) coarsening *= 2;
+  if (coarsening != 1) {
+    SGCALL(avg_face(op->bX, finest->bX, coarsening));
+    SGCALL(avg_face(op->bY, finest->bY, coarsening));
+  }
+  SGCALL(coef_ghosts(op, true));
+  return SG_OK;
+}
+extern "C" int sg_op_lambda(sg_op* op, sg_field* lam) {
+  REQUIRE(op, "null");
+  SGCALL(check_same(op, lam, "lambda"));
+  sg_layout* L = op->lay;
+  if (!L->has_local) return SG_OK;
+  LAUNCH(op->ctx, k_lambda, grid2(L->nx, L->ny, B2D), B2D, lam->p(), make_args(op));
+  return SG_OK;
+}
+extern "C" int sg_op_createCoarser(sg_op* op, sg_field** coarse, const sg_field* fine, int ghosted) {
+  (void)ghosted;
+  REQUIRE(op && coarse && fine, "sg_op_createCoarser: null");
+  int ok = 0;
+  SGCALL(sg_layout_coarsenable(fine->lay, 2, &ok));
+  REQUIRE(ok, "createCoarser: layout not coarsenable by 2 (CH_assert)");
+  sg_layout* Lc;
+  SGCALL(sg_layout_coarsen(fine->lay, 2, &Lc));
+  return sg_field_create(Lc, coarse, fine->ncomp, fine->ng, fine->cent); // note: layout is leaked to the field's lifetime
+}
+extern "C" int sg_op_create(sg_op* op, sg_field** lhs, const sg_field* rhs) {
+  REQUIRE(op && lhs && rhs, "sg_op_create: null");
+  return sg_field_create(rhs->lay, lhs, rhs->ncomp, rhs->ng, rhs->cent);
+}
+
+// ---- vector surface -----------------------------------------------------------------------------
+template <int OP>
+static int vec_launch(sg_field* y, const sg_field* x, const sg_field* z, double a, double b, bool whole) {
+  sg_layout* L = y->lay;
+  if (!L->has_local) return SG_OK;
+  int ex = y->cent == SG_XFACE, ey = y->cent == SG_YFACE;
+  int i0 = whole ? -y->ng : 0, i1 = L->nx + ex + (whole ? y->ng : 0), j0 = whole ? -y->ng : 0, j1 = L->ny + ey + (whole ? y->ng : 0);
+  for (int c = 0; c < y->ncomp; c++)
+    LAUNCH(L->ctx, k_vec<OP>, grid2(i1 - i0, j1 - j0, B2D), B2D, y->p(c), x ? x->p(c) : nullptr, z ? z->p(c) : nullptr, a, b, L->pitch, i0, i1, j0, j1);
+  return SG_OK;
+}
+extern "C" int sg_op_assign(sg_op*, sg_field* lhs, const sg_field* rhs) { REQUIRE(lhs && rhs, "null"); return vec_launch<3>(lhs, rhs, nullptr, 0, 0, false); }
+extern "C" int sg_op_assignLocal(sg_op*, sg_field* lhs, const sg_field* rhs) { REQUIRE(lhs && rhs, "null"); return vec_launch<3>(lhs, rhs, nullptr, 0, 0, true); }
+extern "C" int sg_op_incr(sg_op*, sg_field* lhs, const sg_field* x, double scale) { REQUIRE(lhs && x, "null"); return vec_launch<1>(lhs, x, nullptr, scale, 0, false); }
+extern "C" int sg_op_axby(sg_op*, sg_field* lhs, const sg_field* x, const sg_field* y, double a, double b) { REQUIRE(lhs && x && y, "null"); return vec_launch<0>(lhs, x, y, a, b, false); }
+extern "C" int sg_op_scale(sg_op*, sg_field* lhs, double s) { REQUIRE(lhs, "null"); return vec_launch<2>(lhs, nullptr, nullptr, s, 0, false); }
+extern "C" int sg_op_setToZero(sg_op*, sg_field* lhs) {
+  REQUIRE(lhs, "null");
+  if (!lhs->lay->has_local) return SG_OK;
+  CK(cudaMemsetAsync(lhs->base, 0, lhs->comp_stride * lhs->ncomp * sizeof(double), lhs->lay->ctx->stream));
+  return SG_OK;
+}
+
+// mode 0 max|x|, 1 sum|x|, 2 sum x^2, 3 sum x*y ; result (this rank) left in d_scalar[slot]
+static int reduce_local(const sg_field* x, const sg_field* y, int mode, int slot) {
+  sg_layout* L = x->lay;
+  sg_ctx* c = L->ctx;
+  CK(cudaMemsetAsync(c->d_scalar + slot, 0, sizeof(double), c->stream));
+  if (!L->has_local) return SG_OK;
+  dim3 g = grid2(L->nx, L->ny, B2D);
+  size_t nb = (size_t)g.x * g.y;
+  if (mode != 0 && c->partial_cap < nb) {
+    CK(cudaStreamSynchronize(c->stream));
+    cudaFree(c->d_partial);
+    CK(cudaMalloc(&c->d_partial, nb * sizeof(double)));
+    c->partial_cap = nb;
+  }
+  LAUNCH(c, k_reduce, g, B2D, x->p(), y ? y->p() : nullptr, L->pitch, L->nx, L->ny, mode, c->d_partial,
+         reinterpret_cast<unsigned long long*>(c->d_scalar) + slot);
+  if (mode != 0) LAUNCH(c, k_reduce_final, 1, 256, c->d_partial, (int)nb, c->d_scalar + slot);
+  return SG_OK;
+}
+static int fetch_scalar(sg_ctx* c, int slot, double* out) {
+  CK(cudaMemcpyAsync(c->h_scalar + slot, c->d_scalar + slot, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+  CK(cudaStreamSynchronize(c->stream));
+  *out = c->h_scalar[slot];
+  return SG_OK;
+}
+static int global_reduce(sg_ctx* c, int slot, bool is_max) {
+  if (c->nranks > 1) SGCALL(c->nccl.allreduce(c->d_scalar + slot, 1, is_max, c->stream, g_err));
+  return SG_OK;
+}
+extern "C" int sg_op_norm(sg_op* op, const sg_field* x, int ord, double* out) {
+  REQUIRE(op && x && out && ord >= 0 && ord <= 2, "sg_op_norm: bad arguments");
+  REQUIRE(x->ncomp == 1, "norm: single-component fields only");
+  SGCALL(reduce_local(x, nullptr, ord, 1));
+  SGCALL(global_reduce(op->ctx, 1, ord == 0));
+  SGCALL(fetch_scalar(op->ctx, 1, out));
+  if (ord == 2) *out = std::sqrt(*out);
+  return SG_OK;
+}
+extern "C" int sg_op_localMaxNorm(sg_op* op, const sg_field* x, double* out) {
+  REQUIRE(op && x && out, "sg_op_localMaxNorm: null");
+  SGCALL(reduce_local(x, nullptr, 0, 1));
+  return fetch_scalar(op->ctx, 1, out);
+}
+extern "C" int sg_op_dotProduct(sg_op* op, const sg_field* a, const sg_field* b, double* out) {
+  REQUIRE(op && a && b && out, "sg_op_dotProduct: null");
+  SGCALL(reduce_local(a, b, 3, 1));
+  SGCALL(global_reduce(op->ctx, 1, false));
+  return fetch_scalar(op->ctx, 1, out);
+}
+
+// ---- AMR surface: declared, multi-level hierarchies come next ---------------------------------------
+#define AMR_UNSUPPORTED(name) return fail(SG_ERR_UNSUPPORTED, name ": multi-level (AMR) operators are not built yet")
+extern "C" int sg_op_AMRResidual(sg_op*, sg_field*, const sg_field*, sg_field*, const sg_field*, const sg_field*, int, sg_op*) { AMR_UNSUPPORTED("AMRResidual"); }
+extern "C" int sg_op_AMRResidualNC(sg_op* op, sg_field* residual, const sg_field* phi_fine, sg_field* phi, const sg_field* rhs, int hom, sg_op*) {
+  if (phi_fine) AMR_UNSUPPORTED("AMRResidualNC");
+  // no finer level: AMROperatorNC = applyOpI; residual = rhs - L(phi) (src/AMRNonLinearPoissonOp.cpp:906-920,977-993)
+  REQUIRE(op, "null op");
+  SGCALL(apply_impl(op, residual, phi, nullptr, hom, 0, 0));
+  return sg_op_axby(op, residual, residual, rhs, -1.0, 1.0);
+}
+extern "C" int sg_op_AMRResidualNF(sg_op* op, sg_field* residual, sg_field* phi, const sg_field* phi_coarse, const sg_field* rhs, int hom) {
+  if (phi_coarse) AMR_UNSUPPORTED("AMRResidualNF");
+  return sg_op_residualNF(op, residual, phi, nullptr, rhs, hom);
+}
+extern "C" int sg_op_AMROperator(sg_op*, sg_field*, const sg_field*, sg_field*, const sg_field*, int, sg_op*) { AMR_UNSUPPORTED("AMROperator"); }
+extern "C" int sg_op_AMROperatorNC(sg_op* op, sg_field* lofphi, const sg_field* phi_fine, sg_field* phi, int hom, sg_op*) {
+  if (phi_fine) AMR_UNSUPPORTED("AMROperatorNC");
+  REQUIRE(op, "null op");
+  return apply_impl(op, lofphi, phi, nullptr, hom, 0, 0);
+}
+extern "C" int sg_op_AMROperatorNF(sg_op* op, sg_field* lofphi, sg_field* phi, const sg_field* phi_coarse, int hom) {
+  if (phi_coarse) AMR_UNSUPPORTED("AMROperatorNF");
+  REQUIRE(op, "null op");
+  return apply_impl(op, lofphi, phi, nullptr, hom, 0, 0);
+}
+extern "C" int sg_op_AMRRestrictS(sg_op*, sg_field*, const sg_field*, sg_field*, const sg_field*, sg_field*, int) { AMR_UNSUPPORTED("AMRRestrictS"); }
+extern "C" int sg_op_AMRProlongS(sg_op*, sg_field*, const sg_field*) { AMR_UNSUPPORTED("AMRProlongS"); }
+extern "C" int sg_op_AMRProlongS_2(sg_op*, sg_field*, const sg_field*, sg_op*) { AMR_UNSUPPORTED("AMRProlongS_2"); }
+extern "C" int sg_op_AMRUpdateResidual(sg_op* op, sg_field* residual, sg_field* correction, const sg_field* coarse_correction) {
+  if (coarse_correction) AMR_UNSUPPORTED("AMRUpdateResidual");
+  return sg_op_residualNF(op, residual, correction, nullptr, residual, 0);
+}
+extern "C" int sg_op_AMRNorm(sg_op* op, const sg_field* coar, const sg_field* fine, int, int ord, double* out) {
+  if (fine) AMR_UNSUPPORTED("AMRNorm");
+  return sg_op_norm(op, coar, ord, out);
+}
+extern "C" int sg_op_reflux(sg_op*, const sg_field*, const sg_field*, sg_field*, sg_op*) { AMR_UNSUPPORTED("reflux"); }
+extern "C" int sg_op_cfInterp(sg_op*, sg_field*, const sg_field*) { AMR_UNSUPPORTED("coarseFineInterp"); }
+
+// ------------------------------------------------------------------------------------------------
+// FAS multigrid driver, device resident (absent fork's AMRFASMultiGrid / MultiGrid; see DESIGN.md for the
+// inferred pieces, identical to oracle/suhmo_oracle.c)
+// ------------------------------------------------------------------------------------------------
+extern "C" int sg_solver_define(sg_factory* f, sg_solver** out, int num_levels) {
+  REQUIRE(f && out, "sg_solver_define: null");
+  if (num_levels != 1 || f->nlevels != 1) return fail(SG_ERR_UNSUPPORTED, "AMRFASMultiGrid: only single-level hierarchies are built so far");
+  sg_solver* s = new sg_solver();
+  s->ctx = f->ctx; s->fac = f; s->num_levels = num_levels;
+  for (int depth = 0;; depth++) {
+    sg_op* op = nullptr;
+    int r = depth == 0 ? sg_factory_AMRnewOp(f, 0, &op) : sg_factory_MGnewOp(f, 0, depth, 1, &op);
+    if (r != SG_OK) { return r; }
+    if (!op) break;
+    s->ops.push_back(op);
+    sg_field *phi = nullptr, *rhs = nullptr, *save = nullptr, *tmp = nullptr;
+    if (depth > 0) {
+      SGCALL(sg_field_create(op->lay, &phi, 1, 1, SG_CELL));
+      SGCALL(sg_field_create(op->lay, &rhs, 1, 0, SG_CELL));
+      SGCALL(sg_field_create(op->lay, &save, 1, 1, SG_CELL));
+      SGCALL(sg_field_create(op->lay, &tmp, 1, 0, SG_CELL));
+    }
+    s->phi.push_back(phi); s->rhs.push_back(rhs); s->save.push_back(save); s->tmp.push_back(tmp);
+  }
+  SGCALL(sg_field_create(s->ops[0]->lay, &s->resid, 1, 0, SG_CELL));
+  *out = s;
+  return SG_OK;
+}
+extern "C" int sg_solver_destroy(sg_solver* s) {
+  if (!s) return SG_OK;
+  for (size_t d = 0; d < s->ops.size(); d++) {
+    sg_field_destroy(s->phi[d]); sg_field_destroy(s->rhs[d]); sg_field_destroy(s->save[d]); sg_field_destroy(s->tmp[d]);
+  }
+  sg_field_destroy(s->resid);
+  for (sg_op* op : s->ops) sg_op_destroy(op);
+  delete s;
+  return SG_OK;
+}
+extern "C" int sg_solver_depth(const sg_solver* s, int level, int* ndepth) {
+  REQUIRE(s && ndepth && level == 0, "sg_solver_depth");
+  *ndepth = (int)s->ops.size();
+  return SG_OK;
+}
+
+static long long layout_cells_global(const sg_layout* L) {
+  long long n = 0;
+  for (const Box& b : L->boxes) n += b.npts();
+  return n;
+}
+extern "C" int sg_solver_cell_updates_per_cycle(const sg_solver* s, const sg_solver_params* sp, double* out) {
+  REQUIRE(s && sp && out, "null");
+  double n = 0;
+  int nd = (int)s->ops.size();
+  for (int d = 0; d < nd; d++) n += (double)layout_cells_global(s->ops[d]->lay) * (d == nd - 1 ? sp->bottom : sp->pre + sp->post);
+  *out = n;
+  return SG_OK;
+}
+
+static int mg_cycle(sg_solver* s, int depth, sg_field* phi, sg_field* rhs, const sg_solver_params* sp) {
+  sg_op* op = s->ops[depth];
+  int nd = (int)s->ops.size();
+  if (depth == nd - 1) return relax_impl(op, phi, rhs, sp->bottom);
+  SGCALL(relax_impl(op, phi, rhs, sp->pre));
+  int dc = depth + 1;
+  sg_op* opc = s->ops[dc];
+  if (op->update_operator) SGCALL(sg_op_AverageOperator(opc, s->ops[0], dc));
+  // restrictR + restrictResidual in one sweep over the fine level
+  SGCALL(restrict_impl(op, s->rhs[dc], s->phi[dc], phi, rhs));
+  SGCALL(vec_launch<3>(s->save[dc], s->phi[dc], nullptr, 0, 0, true));                    // assignLocal
+  SGCALL(apply_impl(opc, s->tmp[dc], s->phi[dc], nullptr, 0, 0, 0));                     // applyOpMg(tmp, phiC, NULL, false)
+  SGCALL(vec_launch<1>(s->rhs[dc], s->tmp[dc], nullptr, 1.0, 0, false));                 // rhsC += L(phiC)
+  SGCALL(mg_cycle(s, dc, s->phi[dc], s->rhs[dc], sp));
+  if (op->lay->has_local) {                                                             // phi += I(phiC_new - phiC_saved)
+    sg_layout* L = op->lay;
+    LAUNCH(s->ctx, k_prolong, grid2(L->nx, L->ny, B2D), B2D, phi->p(), L->pitch, L->nx, L->ny, s->phi[dc]->p(), s->save[dc]->p(), opc->lay->pitch);
+  }
+  return relax_impl(op, phi, rhs, sp->post);
+}
+static int vcycle(sg_solver* s, sg_field* phi, sg_field* rhs, const sg_solver_params* sp, int iter) {
+  sg_op* op0 = s->ops[0];
+  if (op0->update_operator) SGCALL(sg_op_UpdateOperator(op0, phi, nullptr, 0, iter, 0));
+  return mg_cycle(s, 0, phi, rhs, sp);
+}
+// computeAMRResidual: max-norm of rhs - L(phi), left in d_scalar[slot] (all ranks)
+static int residual_norm(sg_solver* s, sg_field* phi, sg_field* rhs, int slot) {
+  SGCALL(apply_impl(s->ops[0], s->resid, phi, rhs, 0, 2, slot));
+  return global_reduce(s->ctx, slot, true);
+}
+
+extern "C" int sg_solver_solve(sg_solver* s, sg_field* const* phi, sg_field* const* rhs, int l_max, int l_base,
+                               const sg_solver_params* sp, double* hist, sg_solve_stats* stats) {
+  REQUIRE(s && phi && rhs && sp && phi[0] && rhs[0], "sg_solver_solve: null");
+  REQUIRE(l_max == 0 && l_base == 0, "sg_solver_solve: single-level hierarchies only so far");
+  sg_ctx* c = s->ctx;
+  SGCALL(check_same(s->ops[0], phi[0], "solve(phi)")); SGCALL(check_same(s->ops[0], rhs[0], "solve(rhs)"));
+  long long l0 = c->launches;
+  cudaEvent_t e0, e1;
+  CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
+  double initial = 0, rnorm = 0;
+  SGCALL(residual_norm(s, phi[0], rhs[0], 2));
+  SGCALL(fetch_scalar(c, 2, &initial));
+  rnorm = initial;
+  if (hist) hist[0] = initial;
+  int iter = 0, exit_status = 0;
+  CK(cudaEventRecord(e0, c->stream));
+  if (sp->fixed_cycles > 0) {
+    REQUIRE(sp->fixed_cycles <= 60, "fixed_cycles <= 60");
+    for (iter = 0; iter < sp->fixed_cycles; iter++) {
+      SGCALL(vcycle(s, phi[0], rhs[0], sp, iter));
+      SGCALL(residual_norm(s, phi[0], rhs[0], 3 + iter)); // norms stay on the device until the end
+    }
+    CK(cudaEventRecord(e1, c->stream));
+    CK(cudaMemcpyAsync(c->h_scalar + 3, c->d_scalar + 3, sizeof(double) * sp->fixed_cycles, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    for (int k = 0; k < sp->fixed_cycles; k++) {
+      if (hist) hist[k + 1] = c->h_scalar[3 + k];
+      rnorm = c->h_scalar[3 + k];
+    }
+  } else {
+    double norm_last = 2 * initial;
+    bool goNorm = rnorm > sp->norm_thresh, goRedu = rnorm > sp->eps * initial, goIter = iter < sp->max_iter;
+    bool goHang = iter < sp->imin || rnorm < (1 - sp->hang) * norm_last, goMin = iter < sp->iter_min;
+    while (goMin || (goIter && goRedu && goHang && goNorm)) {
+      norm_last = rnorm;
+      SGCALL(vcycle(s, phi[0], rhs[0], sp, iter));
+      iter++;
+      SGCALL(residual_norm(s, phi[0], rhs[0], 2));
+      SGCALL(fetch_scalar(c, 2, &rnorm)); // the stop test needs the norm on the host: one sync per V-cycle
+      if (hist) hist[iter] = rnorm;
+      goNorm = rnorm > sp->norm_thresh; goRedu = rnorm > sp->eps * initial; goIter = iter < sp->max_iter;
+      goHang = iter < sp->imin || rnorm < (1 - sp->hang) * norm_last; goMin = iter < sp->iter_min;
+    }
+    exit_status = int(!goRedu) + int(!goIter) * 2 + int(!goHang) * 4 + int(!goNorm) * 8;
+    CK(cudaEventRecord(e1, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+  }
+  CK(cudaGetLastError());
+  if (stats) {
+    float ms = 0;
+    CK(cudaEventElapsedTime(&ms, e0, e1));
+    double per = 0;
+    SGCALL(sg_solver_cell_updates_per_cycle(s, sp, &per));
+    stats->iterations = iter; stats->exit_status = exit_status;
+    stats->initial_resnorm = initial; stats->final_resnorm = rnorm;
+    stats->cell_updates = per * iter; stats->device_ms = ms;
+    stats->kernel_launches = c->launches - l0;
+  }
+  cudaEventDestroy(e0); cudaEventDestroy(e1);
+  return SG_OK;
+}

@@ -1,0 +1,670 @@
+// sg_kernels.cuh -- hand-written sm_100a FP64 kernels of the hydraulic-head solve.
+//
+// Compiled with -fmad=false: the reference's gfortran/x86-64 build has no FMA contraction, and every
+// kernel here keeps the Fortran evaluation order of the .ChF source it replaces, so results are
+// bit-identical to the CPU oracle (IEEE add/mul/div/sqrt), not merely within 1e-10.
+//
+// Data layout: a level on one GPU is one rectangular patch.  Every field is a pitched 2-D FP64 array,
+// x fastest, with SG_XOFF pad/ghost columns on both sides and SG_YOFF ghost rows below (and >= 3 above),
+// so that cell/face (0,0) of the patch sits on a 128-byte boundary and double2 accesses of even columns
+// are aligned.  Kernel pointers are pre-offset to local (0,0): element (i,j) is p[j*pitch + i].
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#define SG_XOFF 16
+#define SG_YOFF 2
+#define SG_YTOP 4
+
+// side kinds of the rank-local patch
+enum { SK_PHYS_DIRI = 0, SK_PHYS_NEUM = 1, SK_GHOST = 2, SK_FROZEN = 3, SK_PHYS_NONE = 4 };
+// side index: 0 x-lo, 1 x-hi, 2 y-lo, 3 y-hi
+
+struct PhysP {
+  double A, cutOffbr, maxOffbr, omega, nu;
+  int cutOffBcoef, use_NL, use_mask_grad;
+};
+
+struct Geom {
+  int nx, ny, pitch;
+  int glo0, glo1;             // global index of local cell (0,0)
+  int dlo0, dlo1, dhi0, dhi1; // problem domain (cells)
+  int kind[4];                // side kinds
+  double bcval[4];            // inhomogeneous boundary value per side
+};
+
+// ------------------------------------------------------------------------------------------------
+// pointwise physics, same operation order as src/AmrHydroF.ChF
+// ------------------------------------------------------------------------------------------------
+// COMPUTENONLINEARTERMS (src/AmrHydroF.ChF:23-68)
+__device__ __forceinline__ void nl_terms(const PhysP& p, double phi, double B, double IM, double Pi, double zb,
+                                         double& nl, double& dnl) {
+  if (!p.use_NL || IM < 0.0) { nl = 0.0; dnl = 0.0; return; }
+  double P = Pi - 1000.0 * 9.8 * (phi - zb);
+  double n = -p.A * B * P * P * P;
+  double d = 3.0 * p.A * B * 1000.0 * 9.8 * P * P;
+  if (p.cutOffbr > B) {
+    n = n * (1.0 - (p.cutOffbr - B) / p.cutOffbr);
+    d = d * B / p.cutOffbr;
+  }
+  if (p.maxOffbr < B) {
+    n = n * (1.0 - (p.maxOffbr - B) / p.maxOffbr);
+    d = d * B / p.maxOffbr;
+  }
+  nl = n; dnl = d;
+}
+// COMPUTEBCOEFF (src/AmrHydroF.ChF:199-231)
+__device__ __forceinline__ double bcoeff_face(const PhysP& p, double Bec, double Reec, double IMec) {
+  double num_q = -(Bec * Bec * Bec * 9.8);
+  double denom_q = 12.0 * p.nu * (1.0 + p.omega * Reec);
+  if ((IMec < 0.0) && (p.cutOffBcoef > 0)) return 0.0;
+  return num_q / denom_q;
+}
+// COMPUTERE (src/AmrHydroF.ChF:81-112)
+__device__ __forceinline__ double reynolds(const PhysP& p, double Bc, double gx, double gy) {
+  double sq = sqrt(gx * gx + gy * gy);
+  double discr = 1.0 + 4.0 * p.omega * (Bc * Bc * Bc * 9.8 * sq) / (12.0 * p.nu * p.nu);
+  return (-1.0 + sqrt(discr)) / (2.0 * p.omega);
+}
+// L(phi) at one cell: VCNLCOMPUTEOP2D / GSRBHELMHOLTZVCNL2D (src/VCAMRNonLinearPoissonOpF.ChF:130-152,257-279)
+__device__ __forceinline__ double lofphi_cell(double alpha, double a, double beta, double pc, double pw, double pe,
+                                              double ps, double pn, double bw, double be, double bs, double bn,
+                                              double dxi0, double dxi1, double nl) {
+  return alpha * a * pc - beta * (be * (pe - pc) * dxi0 - bw * (pc - pw) * dxi0 + bn * (pn - pc) * dxi1 - bs * (pc - ps) * dxi1) + nl;
+}
+// resetLambda + SUMFACESNL (src/VCAMRNonLinearPoissonOp.cpp:505-534, VCAMRNonLinearPoissonOpF.ChF:574-601)
+__device__ __forceinline__ double lambda_cell(double alpha, double a, double beta, double bw, double be, double bs,
+                                              double bn, double s0, double s1) {
+  double lam = a * alpha;
+  lam = lam + s0 * beta * (be + bw);
+  lam = lam + s1 * beta * (bn + bs);
+  return lam;
+}
+// DiriBC order 1 / NeumBC ghost value from the first interior cell (absent Chombo BCFunc)
+__device__ __forceinline__ double bc_ghost_value(int kind, double nearv, double val, double sdx) {
+  return kind == SK_PHYS_DIRI ? 2 * val - nearv : nearv + sdx * val;
+}
+
+struct OpArgs {
+  Geom g;
+  PhysP prm;
+  double alpha, beta, dxi0, dxi1, dx0, dx1;
+  int has_a; // alpha != 0: read aCoef
+  const double* aC;
+  const double* bX;
+  const double* bY;
+  const double* B;
+  const double* Pi;
+  const double* zb;
+  const double* mask;
+};
+
+// ------------------------------------------------------------------------------------------------
+// ghost cells
+// ------------------------------------------------------------------------------------------------
+// mixBCValues (src/AmrHydro.cpp:248-309): 1-cell face strips on physical sides, no corners.
+__global__ void k_bc_ghost(double* __restrict__ p, Geom g, double dx0, double dx1, int homogeneous) {
+  int t = blockIdx.x * blockDim.x + threadIdx.x;
+  int side = blockIdx.y;
+  int kind = g.kind[side];
+  if (kind != SK_PHYS_DIRI && kind != SK_PHYS_NEUM) return;
+  double val = homogeneous ? 0.0 : g.bcval[side];
+  if (side < 2) {
+    if (t >= g.ny) return;
+    int ig = side == 0 ? -1 : g.nx, in = side == 0 ? 0 : g.nx - 1;
+    double sdx = side == 0 ? -dx0 : dx0;
+    p[(ptrdiff_t)t * g.pitch + ig] = bc_ghost_value(kind, p[(ptrdiff_t)t * g.pitch + in], val, sdx);
+  } else {
+    if (t >= g.nx) return;
+    int jg = side == 2 ? -1 : g.ny, jn = side == 2 ? 0 : g.ny - 1;
+    double sdx = side == 2 ? -dx1 : dx1;
+    p[(ptrdiff_t)jg * g.pitch + t] = bc_ghost_value(kind, p[(ptrdiff_t)jn * g.pitch + t], val, sdx);
+  }
+}
+
+// periodic wrap inside one patch (the patch spans the domain in that direction): ghost columns/rows of
+// depth `depth` from the opposite side.  dir 0 copies columns for rows [0,ny+ey); dir 1 copies full-width rows
+// (ghost columns included, so corners get the doubly-wrapped image).  ex/ey = 1 for x/y-face fields: the
+// face on the high boundary is the image of face 0, and high ghosts start one later.
+__global__ void k_wrap_ghost(double* __restrict__ p, Geom g, int dir, int depth, int ex, int ey) {
+  int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (dir == 0) {
+    int rows = g.ny + ey;
+    if (t >= rows * depth) return;
+    int j = t / depth, d = t % depth + 1;
+    double* r = p + (ptrdiff_t)j * g.pitch;
+    r[-d] = r[g.nx - d];
+    r[g.nx - 1 + ex + d] = r[ex + d - 1];
+    if (ex) r[g.nx] = r[0];
+  } else {
+    int w = g.nx + 2 * depth + ex;
+    if (t >= w * depth) return;
+    int i = t % w - depth, d = t / w + 1;
+    p[(ptrdiff_t)(-d) * g.pitch + i] = p[(ptrdiff_t)(g.ny - d) * g.pitch + i];
+    p[(ptrdiff_t)(g.ny - 1 + ey + d) * g.pitch + i] = p[(ptrdiff_t)(ey + d - 1) * g.pitch + i];
+    if (ey && d == 1) p[(ptrdiff_t)g.ny * g.pitch + i] = p[i];
+  }
+}
+
+// ExtrapGhostCells / CopyGhostCells on cell data, one direction per launch (util/ExtrapGhostCells.cpp:94-179,
+// util/ExtrapBCF.ChF:7-63): domain-side strips grown by 1 tangentially; ng = 1.
+__global__ void k_extrap_ghost(double* __restrict__ p, Geom g, int dir, int copy_only, size_t comp_stride, int ncomp) {
+  int t = blockIdx.x * blockDim.x + threadIdx.x;
+  int c = blockIdx.y;
+  if (c >= ncomp) return;
+  double* q = p + (size_t)c * comp_stride;
+  int n = (dir == 0 ? g.ny : g.nx) + 2;
+  if (t >= n) return;
+  int k = t - 1; // tangential index -1..n
+  for (int side = 0; side < 2; side++) {
+    int s = 2 * dir + side;
+    bool touches = (dir == 0) ? (side == 0 ? g.glo0 == g.dlo0 : g.glo0 + g.nx - 1 == g.dhi0)
+                              : (side == 0 ? g.glo1 == g.dlo1 : g.glo1 + g.ny - 1 == g.dhi1);
+    if (!touches || g.kind[s] == SK_GHOST) continue; // periodic: skipped for cell data
+    int step = side == 0 ? 1 : -1;
+    int gidx = side == 0 ? -1 : (dir == 0 ? g.nx : g.ny);
+    ptrdiff_t b0 = (dir == 0) ? (ptrdiff_t)k * g.pitch + gidx : (ptrdiff_t)gidx * g.pitch + k;
+    ptrdiff_t st = (dir == 0) ? step : (ptrdiff_t)step * g.pitch;
+    q[b0] = copy_only ? q[b0 + st] : 2.0 * q[b0 + st] - q[b0 + 2 * st];
+  }
+}
+
+// NeumBCForB (src/VCAMRNonLinearPoissonOp.cpp:1309-1341): copy first interior cell into the domain ghost strip
+__global__ void k_neum_copy_ghost(double* __restrict__ p, Geom g) {
+  int t = blockIdx.x * blockDim.x + threadIdx.x;
+  int side = blockIdx.y;
+  int kind = g.kind[side];
+  if (kind == SK_GHOST || kind == SK_FROZEN) return;
+  if (side < 2) {
+    if (t >= g.ny) return;
+    int ig = side == 0 ? -1 : g.nx, in = side == 0 ? 0 : g.nx - 1;
+    p[(ptrdiff_t)t * g.pitch + ig] = p[(ptrdiff_t)t * g.pitch + in];
+  } else {
+    if (t >= g.nx) return;
+    ptrdiff_t jg = side == 2 ? -1 : g.ny, jn = side == 2 ? 0 : g.ny - 1;
+    p[jg * g.pitch + t] = p[jn * g.pitch + t];
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// generic GSRB colour pass (reference flow: ghosts in memory, one colour per launch, in place)
+// GSRBHELMHOLTZVCNL2D (src/VCAMRNonLinearPoissonOpF.ChF:46-168) with COMPUTENONLINEARTERMS and lambda fused in.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_gsrb_color(double* __restrict__ phi, const double* __restrict__ rhs, OpArgs a, int pass) {
+  int half = (a.g.nx + 1) >> 1;
+  int t = blockIdx.x * blockDim.x + threadIdx.x;
+  int j = blockIdx.y * blockDim.y + threadIdx.y;
+  if (j >= a.g.ny || t >= half) return;
+  // imin = lo + |(lo + j + pass) mod 2| in global indices
+  int off = (a.g.glo0 + a.g.glo1 + j + pass) & 1;
+  int i = 2 * t + off;
+  if (i >= a.g.nx) return;
+  size_t o = (size_t)j * a.g.pitch + i;
+  ptrdiff_t P = a.g.pitch;
+  double pc = phi[o], pw = phi[o - 1], pe = phi[o + 1], ps = phi[(ptrdiff_t)o - P], pn = phi[o + P];
+  double bw = a.bX[o], be = a.bX[o + 1], bs = a.bY[o], bn = a.bY[o + P];
+  double ac = a.has_a ? a.aC[o] : 0.0;
+  double nl, dnl;
+  nl_terms(a.prm, pc, a.B[o], a.mask[o], a.Pi[o], a.zb[o], nl, dnl);
+  double lof = lofphi_cell(a.alpha, ac, a.beta, pc, pw, pe, ps, pn, bw, be, bs, bn, a.dxi0, a.dxi1, nl);
+  double lam = lambda_cell(a.alpha, ac, a.beta, bw, be, bs, bn, a.dxi0, a.dxi1);
+  double denom = 1.0e-16 + lam + dnl;
+  phi[o] = pc + (rhs[o] - lof) / denom;
+}
+
+// ------------------------------------------------------------------------------------------------
+// fused red+black GSRB sweep: one kernel = one levelGSRB iteration, out of place (phi_in -> phi_out).
+//
+// Each WARP streams a strip of 64 columns upwards over a segment of rows, entirely in registers:
+// lane t owns columns (c0+2t, c0+2t+1); horizontal neighbours come from warp shuffles, vertical neighbours
+// from the rows kept in registers.  Step r does the RED update of row r+1 and then the BLACK update of row
+// r, so every black cell sees post-red neighbours exactly as in the two-pass reference.  The red update of
+// the one-cell ring around the strip is recomputed redundantly (60 of 64 columns are stored), which removes
+// any dependence between warps: no shared memory, no __syncthreads, no inter-CTA ordering.
+// Every array is read once (72 B per cell update incl. the store) instead of once per colour.
+//
+// Physical-boundary ghosts are never read: the reference refills them before each colour from the first
+// interior cell, i.e. from the cell being updated itself, so they are evaluated on the fly.  Sides of kind
+// SK_GHOST (periodic image / neighbouring GPU) need depth-2 ghosts of phi and depth-1 ghosts of the
+// coefficients in memory; the ring there is recomputed, which replaces the exchange between colours.
+// ------------------------------------------------------------------------------------------------
+#define FUSED_COLS 60
+struct FusedArgs {
+  OpArgs a;
+  const double* phi_in;
+  double* phi_out;
+  const double* rhs;
+  int rows_per_warp;
+  int nstrips, nsegs;
+  double sdx[4]; // isign*dx per side for Neumann
+};
+
+__device__ __forceinline__ double2 ld2(const double* p) { return *reinterpret_cast<const double2*>(p); }
+
+template <int HAS_A>
+__global__ void __launch_bounds__(128, 4) k_gsrb_fused(FusedArgs f) {
+  const OpArgs& a = f.a;
+  const int lane = threadIdx.x & 31;
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (warp >= f.nstrips * f.nsegs) return;
+  const int strip = warp % f.nstrips, seg = warp / f.nstrips;
+  const int nx = a.g.nx, ny = a.g.ny;
+  const ptrdiff_t P = a.g.pitch;
+  const int x0 = strip * FUSED_COLS - 2 + 2 * lane; // columns x0, x0+1 (x0 even)
+  const int r0 = seg * f.rows_per_warp;
+  const int r1 = min(ny, r0 + f.rows_per_warp);
+  const bool colok = x0 < nx + 2; // pair lies inside the allocated row
+  const int kxlo = a.g.kind[0], kxhi = a.g.kind[1], kylo = a.g.kind[2], kyhi = a.g.kind[3];
+  // which columns of this lane may be updated at all (valid cells, or ring cells on SK_GHOST sides)
+  const bool upd0 = (x0 >= 0 && x0 < nx) || (x0 == -1 && kxlo == SK_GHOST) || (x0 == nx && kxhi == SK_GHOST);
+  const bool upd1 = (x0 + 1 >= 0 && x0 + 1 < nx) || (x0 + 1 == -1 && kxlo == SK_GHOST) || (x0 + 1 == nx && kxhi == SK_GHOST);
+  const bool st0 = lane >= 1 && lane <= 30 && x0 >= 0 && x0 < nx;         // stored output columns
+  const bool st1 = lane >= 1 && lane <= 30 && x0 + 1 >= 0 && x0 + 1 < nx;
+  const int gpar = (a.g.glo0 + a.g.glo1 + x0) & 1; // parity of column x0 at local row 0 (x0 even, +ve modulo)
+
+  // rows of phi in registers: pm (r-1), p0 (r), p1 (r+1), p2 (r+2)
+  double2 pm, p0, p1, p2;
+  auto ldphi = [&](int j) -> double2 {
+    double2 z = make_double2(0.0, 0.0);
+    if (colok && j >= -2 && j <= ny + 1) z = ld2(f.phi_in + (ptrdiff_t)j * P + x0);
+    return z;
+  };
+  struct RowC { double2 rhs, B, Pi, zb, mk, ac; double bx0, bx1, bx2; };
+  auto ldrow = [&](int j) -> RowC {
+    RowC c;
+    c.rhs = c.B = c.Pi = c.zb = c.mk = c.ac = make_double2(0.0, 0.0);
+    double2 bx = make_double2(0.0, 0.0);
+    bool rowok = (j >= 0 && j < ny) || (j == -1 && kylo == SK_GHOST) || (j == ny && kyhi == SK_GHOST);
+    if (colok && rowok) {
+      ptrdiff_t o = (ptrdiff_t)j * P + x0;
+      c.rhs = ld2(f.rhs + o); c.B = ld2(a.B + o); c.Pi = ld2(a.Pi + o); c.zb = ld2(a.zb + o); c.mk = ld2(a.mask + o);
+      if (HAS_A) c.ac = ld2(a.aC + o);
+      bx = ld2(a.bX + o);
+    }
+    c.bx0 = bx.x; c.bx1 = bx.y;
+    c.bx2 = __shfl_down_sync(0xffffffffu, bx.x, 1);
+    return c;
+  };
+  auto ldby = [&](int j) -> double2 {
+    double2 z = make_double2(0.0, 0.0);
+    bool rowok = (j >= 0 && j <= ny) || (j == -1 && kylo == SK_GHOST) || (j == ny + 1 && kyhi == SK_GHOST);
+    if (colok && rowok) z = ld2(a.bY + (ptrdiff_t)j * P + x0);
+    return z;
+  };
+  // point update of the cell in column k (0/1) of row j
+  auto update = [&](int k, int j, const RowC& c, double2 pc2, double pwest, double peast, double psouth, double pnorth,
+                    double bys, double byn) -> double {
+    const int x = x0 + k;
+    double pc = k ? pc2.y : pc2.x;
+    double bw = k ? c.bx1 : c.bx0, be = k ? c.bx2 : c.bx1;
+    // physical-boundary neighbours: ghost = BC(first interior cell) = BC(this cell)
+    if (x == 0 && kxlo <= SK_PHYS_NEUM) pwest = bc_ghost_value(kxlo, pc, a.g.bcval[0], f.sdx[0]);
+    if (x == nx - 1 && kxhi <= SK_PHYS_NEUM) peast = bc_ghost_value(kxhi, pc, a.g.bcval[1], f.sdx[1]);
+    if (j == 0 && kylo <= SK_PHYS_NEUM) psouth = bc_ghost_value(kylo, pc, a.g.bcval[2], f.sdx[2]);
+    if (j == ny - 1 && kyhi <= SK_PHYS_NEUM) pnorth = bc_ghost_value(kyhi, pc, a.g.bcval[3], f.sdx[3]);
+    double ac = HAS_A ? (k ? c.ac.y : c.ac.x) : 0.0;
+    double nl, dnl;
+    nl_terms(a.prm, pc, k ? c.B.y : c.B.x, k ? c.mk.y : c.mk.x, k ? c.Pi.y : c.Pi.x, k ? c.zb.y : c.zb.x, nl, dnl);
+    double lof = lofphi_cell(a.alpha, ac, a.beta, pc, pwest, peast, psouth, pnorth, bw, be, bys, byn, a.dxi0, a.dxi1, nl);
+    double lam = lambda_cell(a.alpha, ac, a.beta, bw, be, bys, byn, a.dxi0, a.dxi1);
+    double denom = 1.0e-16 + lam + dnl;
+    return pc + ((k ? c.rhs.y : c.rhs.x) - lof) / denom;
+  };
+  auto rowupd = [&](int j) -> bool { // may cells of row j be updated (valid row, or ring row on a SK_GHOST side)
+    return (j >= 0 && j < ny) || (j == -1 && kylo == SK_GHOST) || (j == ny && kyhi == SK_GHOST);
+  };
+
+  // prologue: rows r0-2 .. r0+1
+  pm = ldphi(r0 - 2);
+  p0 = ldphi(r0 - 1);
+  p1 = ldphi(r0);
+  RowC c0 = ldrow(r0 - 1), c1 = ldrow(r0);
+  double2 by0 = ldby(r0 - 1), by1 = ldby(r0), by2 = ldby(r0 + 1);
+  // red update of ring row r0-1 (needed by the black cells of row r0)
+  {
+    int j = r0 - 1;
+    int k = (gpar + j) & 1; // red cell: (gi+gj) even -> column x0 if (gpar + j) even
+    k = k & 1;
+    double w = __shfl_up_sync(0xffffffffu, p0.y, 1), e = __shfl_down_sync(0xffffffffu, p0.x, 1);
+    if (rowupd(j)) {
+      bool u = k ? upd1 : upd0;
+      // interior lanes only: lane 0 column 0 and lane 31 column 1 have no neighbour in the warp
+      if (u && !(lane == 0 && k == 0) && !(lane == 31 && k == 1)) {
+        double nv = update(k, j, c0, p0, k ? p0.x : w, k ? e : p0.y, k ? pm.y : pm.x, k ? p1.y : p1.x,
+                           k ? by0.y : by0.x, k ? by1.y : by1.x);
+        if (k) p0.y = nv; else p0.x = nv;
+      }
+    }
+  }
+  // main loop: step r = red on row r+1, black on row r, store row r.
+  // entering step r: pm = row r-1 (final), p0 = row r (red done), p1 = row r+1 (old); c0/c1 = coefs of rows r/r+1;
+  // by0/by1/by2 = y-faces r, r+1, r+2.  The step r0-1 (red on row r0 only) is peeled: shift first.
+  // Shift state so that "row r" = r0-1.
+  // (pm,p0,p1) currently = rows (r0-2, r0-1, r0); c0,c1 = rows r0-1, r0; by0..2 = r0-1, r0, r0+1.
+  for (int r = r0 - 1; r < r1; r++) {
+    // prefetch what the next step needs
+    p2 = ldphi(r + 2);
+    RowC c2 = ldrow(r + 2);
+    double2 by3 = ldby(r + 3);
+    // ---- red update on row r+1
+    {
+      int j = r + 1;
+      int k = (gpar + j) & 1;
+      double w = __shfl_up_sync(0xffffffffu, p1.y, 1), e = __shfl_down_sync(0xffffffffu, p1.x, 1);
+      if (rowupd(j)) {
+        bool u = k ? upd1 : upd0;
+        if (u && !(lane == 0 && k == 0) && !(lane == 31 && k == 1)) {
+          double nv = update(k, j, c1, p1, k ? p1.x : w, k ? e : p1.y, k ? p0.y : p0.x, k ? p2.y : p2.x,
+                             k ? by1.y : by1.x, k ? by2.y : by2.x);
+          if (k) p1.y = nv; else p1.x = nv;
+        }
+      }
+    }
+    // ---- black update on row r (valid rows only), then store
+    if (r >= r0) {
+      int j = r;
+      int k = ((gpar + j) & 1) ^ 1; // black cell
+      double w = __shfl_up_sync(0xffffffffu, p0.y, 1), e = __shfl_down_sync(0xffffffffu, p0.x, 1);
+      bool s = k ? st1 : st0;
+      if (s) {
+        double nv = update(k, j, c0, p0, k ? p0.x : w, k ? e : p0.y, k ? pm.y : pm.x, k ? p1.y : p1.x,
+                           k ? by0.y : by0.x, k ? by1.y : by1.x);
+        if (k) p0.y = nv; else p0.x = nv;
+      }
+      if (st0 && st1) *reinterpret_cast<double2*>(f.phi_out + (ptrdiff_t)j * P + x0) = p0;
+      else if (st0) f.phi_out[(ptrdiff_t)j * P + x0] = p0.x;
+      else if (st1) f.phi_out[(ptrdiff_t)j * P + x0 + 1] = p0.y;
+    }
+    pm = p0; p0 = p1; p1 = p2;
+    c0 = c1; c1 = c2;
+    by0 = by1; by1 = by2; by2 = by3;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// applyOp / residual (+ max-norm) : VCNLCOMPUTEOP2D / VCNLCOMPUTERES2D (src/VCAMRNonLinearPoissonOpF.ChF:201-406)
+// MODE 0: out = L(phi);  1: out = rhs - L(phi);  2: as 1 plus max|out| accumulated into *norm_bits
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void block_max_to_global(double v, unsigned long long* dst) {
+  // non-negative doubles order like their bit patterns
+  for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
+  __shared__ double wmax[32];
+  int lane = threadIdx.x & 31, w = (threadIdx.y * blockDim.x + threadIdx.x) >> 5;
+  int nw = (blockDim.x * blockDim.y + 31) >> 5;
+  if (((threadIdx.y * blockDim.x + threadIdx.x) & 31) == 0) wmax[w] = v;
+  __syncthreads();
+  if (w == 0) {
+    v = lane < nw ? wmax[lane] : 0.0;
+    for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
+    if (lane == 0) atomicMax(dst, (unsigned long long)__double_as_longlong(v));
+  }
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(256) k_apply(double* __restrict__ out, const double* __restrict__ phi,
+                                               const double* __restrict__ rhs, OpArgs a, unsigned long long* norm_bits) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  int j = blockIdx.y * blockDim.y + threadIdx.y;
+  double r = 0.0;
+  if (i < a.g.nx && j < a.g.ny) {
+    size_t o = (size_t)j * a.g.pitch + i;
+    ptrdiff_t P = a.g.pitch;
+    double pc = phi[o], pw = phi[o - 1], pe = phi[o + 1], ps = phi[(ptrdiff_t)o - P], pn = phi[o + P];
+    double bw = a.bX[o], be = a.bX[o + 1], bs = a.bY[o], bn = a.bY[o + P];
+    double ac = a.has_a ? a.aC[o] : 0.0;
+    double nl, dnl;
+    nl_terms(a.prm, pc, a.B[o], a.mask[o], a.Pi[o], a.zb[o], nl, dnl);
+    double lof = lofphi_cell(a.alpha, ac, a.beta, pc, pw, pe, ps, pn, bw, be, bs, bn, a.dxi0, a.dxi1, nl);
+    r = MODE == 0 ? lof : rhs[o] - (lof);
+    out[o] = r;
+  }
+  if (MODE == 2) block_max_to_global(fabs(r), norm_bits);
+}
+
+// restrictResidual + restrictR fused (src/VCAMRNonLinearPoissonOp.cpp:347-460; RESTRICTRESVCNL2D / RESTRICTVCNL,
+// VCAMRNonLinearPoissonOpF.ChF:419-561): one thread per coarse cell, the four fine cells accumulated in the
+// Fortran loop order (i fastest):  acc = 0; acc += v/4 ...
+template <int WITH_PHI>
+__global__ void __launch_bounds__(256) k_restrict(double* __restrict__ resC, double* __restrict__ phiC, int pitchC,
+                                                  const double* __restrict__ phi, const double* __restrict__ rhs, OpArgs a) {
+  int ic = blockIdx.x * blockDim.x + threadIdx.x;
+  int jc = blockIdx.y * blockDim.y + threadIdx.y;
+  if (ic >= (a.g.nx >> 1) || jc >= (a.g.ny >> 1)) return;
+  const double denom = 4.0;
+  double acc = 0.0, accp = 0.0;
+  ptrdiff_t P = a.g.pitch;
+#pragma unroll
+  for (int jj = 0; jj < 2; jj++)
+#pragma unroll
+    for (int ii = 0; ii < 2; ii++) {
+      size_t o = (size_t)(2 * jc + jj) * a.g.pitch + (2 * ic + ii);
+      double pc = phi[o];
+      if (resC) {
+        double pw = phi[o - 1], pe = phi[o + 1], ps = phi[(ptrdiff_t)o - P], pn = phi[o + P];
+        double bw = a.bX[o], be = a.bX[o + 1], bs = a.bY[o], bn = a.bY[o + P];
+        double ac = a.has_a ? a.aC[o] : 0.0;
+        double nl, dnl;
+        nl_terms(a.prm, pc, a.B[o], a.mask[o], a.Pi[o], a.zb[o], nl, dnl);
+        double lof = lofphi_cell(a.alpha, ac, a.beta, pc, pw, pe, ps, pn, bw, be, bs, bn, a.dxi0, a.dxi1, nl);
+        acc = acc + (rhs[o] - lof) / denom;
+      }
+      if (WITH_PHI) accp = accp + pc / denom;
+    }
+  size_t oc = (size_t)jc * pitchC + ic;
+  if (resC) resC[oc] = acc;
+  if (WITH_PHI) phiC[oc] = accp;
+}
+
+// prolongIncrement (src/AMRNonLinearPoissonOp.cpp:856-886; PROLONGNL AMRNonLinearPoissonOpF.ChF:607-632), m = 2.
+// corr = phiC_new - phiC_saved is fused in (the driver's axby) when saved != nullptr.
+__global__ void __launch_bounds__(256) k_prolong(double* __restrict__ phi, int pitch, int nx, int ny,
+                                                 const double* __restrict__ cnew, const double* __restrict__ csaved, int pitchC) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  int j = blockIdx.y * blockDim.y + threadIdx.y;
+  if (i >= nx || j >= ny) return;
+  size_t oc = (size_t)(j >> 1) * pitchC + (i >> 1);
+  double corr = csaved ? 1.0 * cnew[oc] + (-1.0) * csaved[oc] : cnew[oc];
+  size_t o = (size_t)j * pitch + i;
+  phi[o] = phi[o] + corr;
+}
+
+// ------------------------------------------------------------------------------------------------
+// UpdateOperator pieces (src/AmrHydro.cpp:1415-1539)
+// ------------------------------------------------------------------------------------------------
+// compGradientCC: NEWMACGRAD normal derivative on the faces of the valid box then EdgeToCell
+// (util/GradientF.ChF:55-70, util/Gradient.cpp:478-624)
+__global__ void __launch_bounds__(256) k_gradient_cc(double* __restrict__ gx, double* __restrict__ gy,
+                                                     const double* __restrict__ phi, const double* __restrict__ mask,
+                                                     Geom g, double dx0, double dx1) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  int j = blockIdx.y * blockDim.y + threadIdx.y;
+  if (i >= g.nx || j >= g.ny) return;
+  size_t o = (size_t)j * g.pitch + i;
+  ptrdiff_t P = g.pitch;
+  double fx = 1.0 / dx0, fy = 1.0 / dx1;
+  double pc = phi[o], pw = phi[o - 1], pe = phi[o + 1], ps = phi[(ptrdiff_t)o - P], pn = phi[o + P];
+  double gxl, gxh, gyl, gyh;
+  if (mask) {
+    double mc = mask[o], mw = mask[o - 1], me = mask[o + 1], ms = mask[(ptrdiff_t)o - P], mn = mask[o + P];
+    gxl = (mc < 1E-6 || mw < 1E-6) ? 0.0 : fx * (pc - pw);
+    gxh = (me < 1E-6 || mc < 1E-6) ? 0.0 : fx * (pe - pc);
+    gyl = (mc < 1E-6 || ms < 1E-6) ? 0.0 : fy * (pc - ps);
+    gyh = (mn < 1E-6 || mc < 1E-6) ? 0.0 : fy * (pn - pc);
+  } else {
+    gxl = fx * (pc - pw); gxh = fx * (pe - pc); gyl = fy * (pc - ps); gyh = fy * (pn - pc);
+  }
+  gx[o] = 0.5 * (gxl + gxh);
+  gy[o] = 0.5 * (gyl + gyh);
+}
+
+// COMPUTERE over the ghosted box (ring of width 1 included)
+__global__ void __launch_bounds__(256) k_compute_re(double* __restrict__ Re, const double* __restrict__ B,
+                                                    const double* __restrict__ gx, const double* __restrict__ gy,
+                                                    Geom g, PhysP prm) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x - 1;
+  int j = blockIdx.y * blockDim.y + threadIdx.y - 1;
+  if (i > g.nx || j > g.ny) return;
+  ptrdiff_t o = (ptrdiff_t)j * g.pitch + i;
+  Re[o] = reynolds(prm, B[o], gx[o], gy[o]);
+}
+
+// CellToEdge(Re), CellToEdge(B), setup_iceMask_EC (src/HydroIBC.cpp:138-184), COMPUTEBCOEFF -> bX, bY
+__global__ void __launch_bounds__(256) k_bcoef_faces(double* __restrict__ bX, double* __restrict__ bY,
+                                                     const double* __restrict__ Re, const double* __restrict__ B,
+                                                     const double* __restrict__ mask, Geom g, PhysP prm) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  int j = blockIdx.y * blockDim.y + threadIdx.y;
+  if (i > g.nx || j > g.ny) return;
+  ptrdiff_t o = (ptrdiff_t)j * g.pitch + i;
+  ptrdiff_t P = g.pitch;
+  double rc = Re[o], bc = B[o], mc = mask[o];
+  if (j < g.ny) { // x-face (i,j), i in [0,nx]
+    double r = 0.5 * (rc + Re[o - 1]), b = 0.5 * (bc + B[o - 1]);
+    double mm = mask[o - 1];
+    double im = fabs(mc - mm) < 1e-10 ? (mc > 0.0 ? 1.0 : -1.0) : 0.0;
+    int gi = g.glo0 + i;
+    if (gi == g.dlo0) im = 0.0;
+    if (gi == g.dhi0 + 1) im = 0.0;
+    bX[o] = bcoeff_face(prm, b, r, im);
+  }
+  if (i < g.nx) { // y-face (i,j), j in [0,ny]
+    double r = 0.5 * (rc + Re[o - P]), b = 0.5 * (bc + B[o - P]);
+    double mm = mask[o - P];
+    double im = fabs(mc - mm) < 1e-10 ? (mc > 0.0 ? 1.0 : -1.0) : 0.0;
+    int gj = g.glo1 + j;
+    if (gj == g.dlo1) im = 0.0;
+    if (gj == g.dhi1 + 1) im = 0.0;
+    bY[o] = bcoeff_face(prm, b, r, im);
+  }
+}
+
+// lambda materialised (inspection only; the solver recomputes it inside the kernels)
+__global__ void __launch_bounds__(256) k_lambda(double* __restrict__ lam, OpArgs a) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  int j = blockIdx.y * blockDim.y + threadIdx.y;
+  if (i >= a.g.nx || j >= a.g.ny) return;
+  size_t o = (size_t)j * a.g.pitch + i;
+  double ac = a.has_a ? a.aC[o] : 0.0;
+  lam[o] = lambda_cell(a.alpha, ac, a.beta, a.bX[o], a.bX[o + 1], a.bY[o], a.bY[o + a.g.pitch], a.dxi0, a.dxi1);
+}
+
+// NonLinear_level as a stand-alone kernel (src/AmrHydro.cpp:1542-1574)
+__global__ void __launch_bounds__(256) k_nl(double* __restrict__ nl, double* __restrict__ dnl, const double* __restrict__ phi,
+                                            const double* __restrict__ B, const double* __restrict__ mask,
+                                            const double* __restrict__ Pi, const double* __restrict__ zb, Geom g, PhysP prm) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  int j = blockIdx.y * blockDim.y + threadIdx.y;
+  if (i >= g.nx || j >= g.ny) return;
+  size_t o = (size_t)j * g.pitch + i;
+  double n, d;
+  nl_terms(prm, phi[o], B[o], mask[o], Pi[o], zb[o], n, d);
+  nl[o] = n; dnl[o] = d;
+}
+
+// DIVERGENCE (util/DivergenceF.ChF:23-57)
+__global__ void __launch_bounds__(256) k_divergence(double* __restrict__ div, const double* __restrict__ ux,
+                                                    const double* __restrict__ uy, Geom g, double dx0, double dx1) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  int j = blockIdx.y * blockDim.y + threadIdx.y;
+  if (i >= g.nx || j >= g.ny) return;
+  size_t o = (size_t)j * g.pitch + i;
+  double ox = 1.0 / dx0, oy = 1.0 / dx1;
+  double d = div[o];
+  d = d + ox * (ux[o + 1] - ux[o]);
+  d = d + oy * (uy[o + g.pitch] - uy[o]);
+  div[o] = d;
+}
+
+// ------------------------------------------------------------------------------------------------
+// coefficient averaging (absent Chombo CoarseAverage / CoarseAverageFace, arithmetic; sequential sums in the
+// Fortran loop order so results are bit-identical to the oracle)
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_avg_cell(double* __restrict__ c, int pitchC, int nxc, int nyc,
+                                                  const double* __restrict__ f, int pitchF, int r) {
+  int ic = blockIdx.x * blockDim.x + threadIdx.x;
+  int jc = blockIdx.y * blockDim.y + threadIdx.y;
+  if (ic >= nxc || jc >= nyc) return;
+  double s = 0.0;
+  for (int jj = 0; jj < r; jj++)
+    for (int ii = 0; ii < r; ii++) s = s + f[(size_t)(jc * r + jj) * pitchF + ic * r + ii];
+  c[(size_t)jc * pitchC + ic] = s / (double)(r * r);
+}
+// dir 0: x-faces (nxc+1 x nyc), fine faces (ic*r, jc*r + k); dir 1: y-faces
+__global__ void __launch_bounds__(256) k_avg_face(double* __restrict__ c, int pitchC, int nxc, int nyc,
+                                                  const double* __restrict__ f, int pitchF, int r, int dir) {
+  int ic = blockIdx.x * blockDim.x + threadIdx.x;
+  int jc = blockIdx.y * blockDim.y + threadIdx.y;
+  if (ic >= nxc + (dir == 0) || jc >= nyc + (dir == 1)) return;
+  double s = 0.0;
+  for (int k = 0; k < r; k++) {
+    size_t o = dir == 0 ? (size_t)(jc * r + k) * pitchF + ic * r : (size_t)(jc * r) * pitchF + ic * r + k;
+    s = s + f[o];
+  }
+  c[(size_t)jc * pitchC + ic] = s / (double)r;
+}
+
+// ------------------------------------------------------------------------------------------------
+// vector ops over the valid region (LevelDataOps)
+// ------------------------------------------------------------------------------------------------
+// op 0: y = a*x + b*z ; 1: y = y + a*x ; 2: y = y*a ; 3: y = x (copy) ; 4: y = a (set)
+template <int OP>
+__global__ void __launch_bounds__(256) k_vec(double* __restrict__ y, const double* __restrict__ x, const double* __restrict__ z,
+                                             double a, double b, int pitch, int i0, int i1, int j0, int j1) {
+  int i = i0 + blockIdx.x * blockDim.x + threadIdx.x;
+  int j = j0 + blockIdx.y * blockDim.y + threadIdx.y;
+  if (i >= i1 || j >= j1) return;
+  ptrdiff_t o = (ptrdiff_t)j * pitch + i;
+  if (OP == 0) y[o] = a * x[o] + b * z[o];
+  if (OP == 1) y[o] = y[o] + a * x[o];
+  if (OP == 2) y[o] = y[o] * a;
+  if (OP == 3) y[o] = x[o];
+  if (OP == 4) y[o] = a;
+}
+
+// reductions: mode 0 max|x| (exact, order independent), 1 sum|x|, 2 sum x^2, 3 sum x*y.
+// Sums use one fixed-shape pass (per-block partials, then a single-block tree), so they are deterministic.
+__global__ void __launch_bounds__(256) k_reduce(const double* __restrict__ x, const double* __restrict__ y, int pitch, int nx, int ny,
+                                                int mode, double* __restrict__ partial, unsigned long long* maxbits) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  int j = blockIdx.y * blockDim.y + threadIdx.y;
+  double v = 0.0;
+  if (i < nx && j < ny) {
+    size_t o = (size_t)j * pitch + i;
+    double xv = x[o];
+    v = mode == 0 ? fabs(xv) : mode == 1 ? fabs(xv) : mode == 2 ? xv * xv : xv * y[o];
+  }
+  if (mode == 0) { block_max_to_global(v, maxbits); return; }
+  __shared__ double sh[256];
+  int t = threadIdx.y * blockDim.x + threadIdx.x;
+  sh[t] = v;
+  __syncthreads();
+  for (int s = 128; s > 0; s >>= 1) {
+    if (t < s) sh[t] = sh[t] + sh[t + s];
+    __syncthreads();
+  }
+  if (t == 0) partial[blockIdx.y * gridDim.x + blockIdx.x] = sh[0];
+}
+__global__ void __launch_bounds__(256) k_reduce_final(const double* __restrict__ partial, int n, double* __restrict__ out) {
+  __shared__ double sh[256];
+  double v = 0.0;
+  for (int k = threadIdx.x; k < n; k += 256) v = v + partial[k];
+  sh[threadIdx.x] = v;
+  __syncthreads();
+  for (int s = 128; s > 0; s >>= 1) {
+    if (threadIdx.x < s) sh[threadIdx.x] = sh[threadIdx.x] + sh[threadIdx.x + s];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) *out = sh[0];
+}
+
+// box <-> patch staging for batched upload/download: segment table {src offset, dst offset, nx, ny, src pitch, dst pitch}
+struct CopySeg { long long so, dofs; int nx, ny, sp, dp; };
+__global__ void k_copy_segs(double* __restrict__ dst, const double* __restrict__ src, const CopySeg* __restrict__ segs, int nseg) {
+  int s = blockIdx.y;
+  if (s >= nseg) return;
+  CopySeg c = segs[s];
+  for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < c.nx * c.ny; t += gridDim.x * blockDim.x) {
+    int i = t % c.nx, j = t / c.nx;
+    dst[c.dofs + (long long)j * c.dp + i] = src[c.so + (long long)j * c.sp + i];
+  }
+}

@@ -1,0 +1,105 @@
+"""Builds the same head-solve problem for the CPU oracle and (optionally) the GPU library from one set of
+seeded synthetic fields, so parity tests feed both sides identical bits."""
+import numpy as np
+
+from oracle import binding as ob
+from suhmo_b200 import synthetic as syn
+
+CELL, XFACE, YFACE = 0, 1, 2
+NAMES = ("head", "B", "Pi", "zb", "mask", "rhs", "a", "bX", "bY")
+
+
+class OracleSide:
+    def __init__(self, cfg, boxes, seed=12345, perturb=True, bc_vals=None, prm_over=None):
+        self.cfg = cfg
+        self.boxes = np.asarray(boxes, dtype=np.int32)
+        self.domain = (0, 0, cfg.nx - 1, cfg.ny - 1)
+        self.layout = ob.Layout(self.boxes, self.domain, cfg.periodic)
+        g = syn.fields(cfg, ng=1, seed=seed, perturb=perturb)
+        F = {}
+        for k in ("head", "B", "Pi", "zb", "mask"):
+            F[k] = ob.Field(self.layout, 1, 1)
+            F[k].set_global(g[k], (-1, -1))
+            # what AmrHydro does before the solve: exchange, and copy into domain ghosts (src/AmrHydro.cpp:2360-2445)
+            ob.lib().orc_exchange_full(F[k].h)
+            if k != "head":
+                ob.lib().orc_copy_ghost(F[k].h)
+        F["rhs"] = ob.Field(self.layout, 1, 0)
+        F["rhs"].set_global(g["rhs"], (0, 0))
+        F["a"] = ob.Field(self.layout, 1, 0)
+        F["bX"] = ob.Field(self.layout, 1, 0, XFACE)
+        F["bY"] = ob.Field(self.layout, 1, 0, YFACE)
+        self.F = F
+        lo_val, hi_val = bc_vals if bc_vals else ((0.0, 0.0), (0.0, 0.0))
+        self.bc_vals = (lo_val, hi_val)
+        self.bc = ob.make_bc(cfg.bc_lo, cfg.bc_hi, lo_val, hi_val)
+        self.prm_kw = dict(A=cfg.A, omega=cfg.omega, nu=cfg.nu, cutOffbr=cfg.cutOffbr, maxOffbr=cfg.maxOffbr,
+                           cutOffBcoef=cfg.cutOffBcoef, use_mask_grad=cfg.use_mask_grad)
+        if prm_over:
+            self.prm_kw.update(prm_over)
+        self.prm = ob.make_params(**self.prm_kw)
+        self.alpha, self.beta = 0.0, -1.0
+
+    def op(self):
+        F = self.F
+        return ob.Op(self.layout, self.cfg.dx, self.alpha, self.beta, self.bc, self.prm,
+                     F["a"], F["bX"], F["bY"], F["B"], F["Pi"], F["zb"], F["mask"])
+
+    def solver(self):
+        F = self.F
+        return ob.Solver(self.layout, self.cfg.dx, self.alpha, self.beta, self.bc, self.prm,
+                         F["a"], F["bX"], F["bY"], F["B"], F["Pi"], F["zb"], F["mask"])
+
+    def init_bcoef(self):
+        """bCoef as the Picard body would hand it over: B(h) of the current head (aCoeff_bCoeff)."""
+        o = self.op()
+        o.update_operator(self.F["head"])
+        return o
+
+
+class GpuSide:
+    """Device twin of an OracleSide: every box's FArrayBox is uploaded from the oracle's arrays."""
+
+    def __init__(self, ctx, orc, owner=None):
+        from suhmo_b200 import amr
+        self.amr, self.ctx, self.orc = amr, ctx, orc
+        cfg = orc.cfg
+        self.layout = amr.DisjointBoxLayout(ctx, orc.boxes, orc.domain, cfg.periodic, owner)
+        spec = dict(head=(1, CELL), B=(1, CELL), Pi=(1, CELL), zb=(1, CELL), mask=(1, CELL), rhs=(0, CELL),
+                    a=(0, CELL), bX=(0, XFACE), bY=(0, YFACE))
+        self.F = {}
+        for k, (ng, cent) in spec.items():
+            self.F[k] = amr.LevelData(self.layout, 1, ng, cent)
+            self.push(k)
+        self.bc = amr.make_bc(cfg.bc_lo, cfg.bc_hi, *orc.bc_vals)
+        self.prm = amr.make_params(**orc.prm_kw)
+        self.factory = amr.VCAMRNonLinearPoissonOpFactory().define(
+            ctx, [self.layout], [], cfg.dx, self.bc, orc.alpha, [self.F["a"]], orc.beta, [self.F["bX"]], [self.F["bY"]],
+            self.prm, [self.F["B"]], [self.F["Pi"]], [self.F["zb"]], [self.F["mask"]])
+
+    def push(self, name, src=None):
+        """upload oracle field `name` (or the given oracle field) into the device field `name`"""
+        of = src if src is not None else self.orc.F[name]
+        fabs = []
+        for b in range(len(self.layout.boxes)):
+            fabs.append(of.fab(b)[0].copy() if self.layout.owned(b) else None)
+        self.F[name].upload(fabs)
+
+    def new_like(self, name):
+        f = self.F[name]
+        return self.amr.LevelData(self.layout, f.ncomp, f.ng, f.cent)
+
+
+def fields_equal(gpu_ld, orc_field, valid_only=True):
+    """max abs difference and exact-equality flag between a device field and an oracle field (valid cells)."""
+    g = gpu_ld.get_global()
+    o = orc_field.get_global()
+    m = ~np.isnan(o) & ~np.isnan(g)
+    diff = np.abs(g[m] - o[m])
+    return (float(diff.max()) if diff.size else 0.0), bool(np.array_equal(g[m], o[m]))
+
+
+def rel_l2(a, b):
+    m = ~np.isnan(a) & ~np.isnan(b)
+    den = np.sqrt(np.sum(b[m] ** 2))
+    return float(np.sqrt(np.sum((a[m] - b[m]) ** 2)) / (den if den > 0 else 1.0))
