@@ -1,0 +1,327 @@
+#!/usr/bin/env python
+"""bench.py -- head-solve cell-updates/s per FAS V-cycle (BASELINE.json metric) on N B200s.
+
+  python bench.py --gpus N --steps K --warmup W            (N > 1: launched by torch.distributed.run)
+  python bench.py --impl reference ...                     (the CPU path, timed on the box's host cores)
+
+A "step" is one complete FAS V-cycle of the head solve (everything between two residual-norm evaluations:
+UpdateOperator, AverageOperator, 4+4 GSRB smooths per depth, 10/16 bottom smooths, restriction, FAS right-hand
+side, prolongation, residual + max-norm) on the synthetic AMR_multiMoulins base grid scaled to 8192 x 8192 cells
+per GPU (weak scaling: the domain grows in y with N; box-wise strip partition, 64^2 boxes).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+from suhmo_b200 import synthetic as syn  # noqa: E402
+
+METRIC = "head-solve cell-updates/sec (V-cycle)"
+UNIT = "cell-updates/s"
+BYTES_PER_UPDATE_SMOOTHER = 72.0   # phi, rhs, bX, bY, B, Pi, zb, mask read + phi written
+BYTES_PER_UPDATE_VCYCLE = 97.0     # whole V-cycle amortised
+
+
+def bench_config(size, nranks):
+    cfg = syn.config("C5", 1)
+    cfg.nx, cfg.ny = size, size * nranks
+    cfg.domain_size = (100000.0, 100000.0 * nranks)
+    return cfg
+
+
+def strip_boxes(cfg, nranks):
+    boxes = syn.domain_split(cfg.nx, cfg.ny, cfg.max_box_size, cfg.block_factor)
+    rows = cfg.ny // nranks
+    owner = (boxes[:, 1] // rows).astype(np.int32)
+    return boxes, owner
+
+
+def pack_boxes(garr, nbx, nby, bs, ng, ex=0, ey=0, pinned=None):
+    """[j,i] strip array with ng ghosts -> all boxes' FArrayBoxes consecutively (box order: x fastest)."""
+    from numpy.lib.stride_tricks import as_strided
+    s0, s1 = garr.strides
+    w, h = bs + 2 * ng + ex, bs + 2 * ng + ey
+    v = as_strided(garr, shape=(nby, nbx, h, w), strides=(bs * s0, bs * s1, s0, s1))
+    out = pinned if pinned is not None else np.empty((nby * nbx, h, w))
+    out.reshape(nby, nbx, h, w)[...] = v
+    return out
+
+
+class Clocks(threading.Thread):
+    """samples nvidia-smi SM clocks and throttle reasons while the timed region runs"""
+    Q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, device):
+        super().__init__(daemon=True)
+        self.device, self.samples, self.stop_flag, self.proc = device, [], False, None
+
+    def run(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.device), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE, text=True)
+            for line in self.proc.stdout:
+                if self.stop_flag:
+                    break
+                self.samples.append([x.strip() for x in line.split(",")])
+        except Exception:
+            pass
+
+    def finish(self):
+        self.stop_flag = True
+        if self.proc:
+            self.proc.terminate()
+        sm = [float(s[0]) for s in self.samples if s and s[0].replace(".", "").isdigit()]
+        mx = [float(s[1]) for s in self.samples if len(s) > 1 and s[1].replace(".", "").isdigit()]
+        reasons = set()
+        for s in self.samples:
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), s[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def measured_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def cpu_vcycles(size, cycles, threads, bottom):
+    """the CPU restatement of the reference path (oracle, OpenMP over boxes) on a bounded sample of the workload"""
+    from oracle import binding as ob
+    from tests.problem import OracleSide
+    ob.lib().orc_set_threads(threads)
+    cfg = bench_config(size, 1)
+    boxes = syn.domain_split(cfg.nx, cfg.ny, cfg.max_box_size, cfg.block_factor)
+    orc = OracleSide(cfg, boxes)
+    orc.init_bcoef()
+    sol = orc.solver()
+    sp1 = ob.make_solver_params(bottom=bottom, fixed_cycles=1)
+    sol.solve(orc.F["head"], orc.F["rhs"], sp1)  # warm-up cycle (page faults, plans)
+    sp = ob.make_solver_params(bottom=bottom, fixed_cycles=cycles)
+    t0 = time.perf_counter()
+    sol.solve(orc.F["head"], orc.F["rhs"], sp)
+    dt = time.perf_counter() - t0
+    # solve() also evaluates the residual norm after each cycle, as the GPU arm does
+    return sol.cell_updates(sp) * cycles / dt, dt, sol.depth
+
+
+def run_reference(args, rank):
+    if rank != 0:
+        return
+    threads = os.cpu_count() or 1
+    size = args.cpu_size
+    total = args.steps + args.warmup
+    # one "step" = one V-cycle on the bounded sample
+    _ = cpu_vcycles(size, max(1, args.warmup), threads, args.bottom) if args.warmup > 0 else None
+    v, dt, depth = cpu_vcycles(size, args.steps, threads, args.bottom)
+    cfgname = f"AMR_multiMoulins base grid, synthetic, bounded sample {size}x{size} (64^2 boxes, MG depth {depth})"
+    line = {
+        "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": cfgname, "pre": 4, "post": 4, "bottom": args.bottom, "threads": threads, "total_cycles": total},
+        "cpu_baseline": {"value": v, "unit": UNIT, "cores": threads, "kind": "port",
+                         "sample": f"{args.steps} FAS V-cycles on a {size}x{size} sample of the workload, oracle (C restatement, "
+                                   f"OpenMP over boxes); the reference's Chombo/Fortran/MPI build cannot be produced here"},
+        "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--size", type=int, default=8192, help="cells per GPU in x and y")
+    ap.add_argument("--bottom", type=int, default=16)
+    ap.add_argument("--cpu-size", type=int, default=2048, help="bounded CPU sample (cells in x and y)")
+    ap.add_argument("--cpu-cycles", type=int, default=3)
+    ap.add_argument("--e2e-cycles", type=int, default=5, help="V-cycles per head solve in the end-to-end leg")
+    ap.add_argument("--e2e-steps", type=int, default=2)
+    ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--relax-mode", type=int, default=1)
+    args = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+
+    if args.impl == "reference":
+        run_reference(args, rank)
+        return
+
+    import torch
+    import torch.distributed as dist
+    from suhmo_b200 import amr
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; this framework has no CPU fallback (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local_rank)
+    uid = None
+    if world > 1:
+        dist.init_process_group(backend="gloo")
+        obj = [amr.Context.nccl_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(obj, src=0)
+        uid = obj[0]
+    ctx = amr.Context(device=local_rank, rank=rank, nranks=world, nccl_unique_id=uid)
+    ctx.set_relax_mode(args.relax_mode)
+
+    def barrier():
+        ctx.sync()
+        if world > 1:
+            dist.barrier()
+
+    def max_over_ranks(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t[0])
+
+    # ---------------- synthetic inputs: this rank's strip of the global grid, as per-box FArrayBoxes in pinned memory
+    size, bs = args.size, 64
+    cfg = bench_config(size, world)
+    boxes, owner = strip_boxes(cfg, world)
+    nbx, nby = size // bs, size // bs
+    g = syn.fields(cfg, ng=1, lo=(0, rank * size), shape=(size, size))
+    layout = amr.DisjointBoxLayout(ctx, boxes, (0, 0, cfg.nx - 1, cfg.ny - 1), cfg.periodic, owner)
+    F, host = {}, {}
+    spec = dict(head=(1, 0), rhs=(0, 0), B=(1, 0), Pi=(1, 0), zb=(1, 0), mask=(1, 0), a=(0, 0), bX=(0, 1), bY=(0, 2))
+    for k, (ng, cent) in spec.items():
+        F[k] = amr.LevelData(layout, 1, ng, cent)
+    for k in ("head", "rhs", "B", "Pi", "zb", "mask"):
+        ng = spec[k][0]
+        n = F[k].packed_size()
+        host[k] = torch.empty(n, dtype=torch.float64, pin_memory=True)
+        src = g[k] if ng == 1 else g[k]
+        pack_boxes(np.ascontiguousarray(src), nbx, nby, bs, ng, pinned=host[k].numpy().reshape(nbx * nby, bs + 2 * ng, bs + 2 * ng))
+        F[k].upload_packed(host[k])
+    del g
+    for k in ("B", "Pi", "zb", "mask"):
+        amr.CopyGhostCells(F[k])  # AmrHydro fills domain ghosts by copy before the solve
+    bc = amr.make_bc(cfg.bc_lo, cfg.bc_hi)
+    prm = amr.make_params(A=cfg.A, omega=cfg.omega, nu=cfg.nu, cutOffbr=cfg.cutOffbr, maxOffbr=cfg.maxOffbr)
+    fac = amr.VCAMRNonLinearPoissonOpFactory().define(ctx, [layout], [], cfg.dx, bc, 0.0, [F["a"]], -1.0, [F["bX"]], [F["bY"]],
+                                                      prm, [F["B"]], [F["Pi"]], [F["zb"]], [F["mask"]])
+    op0 = fac.AMRnewOp(0)
+    op0.UpdateOperator(F["head"], None, 0, 0, False)  # bCoef = B(h) as the Picard body hands it over
+    mg = amr.AMRFASMultiGrid().define(fac, 1)
+    mg.setSolverParameters(4, 4, args.bottom, 1, 100, 1e-10, 1e-4, 1e-7)
+    head_out = torch.empty(F["head"].packed_size(), dtype=torch.float64, pin_memory=True)
+    host["bX"] = torch.empty(F["bX"].packed_size(), dtype=torch.float64, pin_memory=True)
+    host["bY"] = torch.empty(F["bY"].packed_size(), dtype=torch.float64, pin_memory=True)
+    F["bX"].download_packed(host["bX"])
+    F["bY"].download_packed(host["bY"])
+    ndepth = mg.depth
+    updates_per_cycle = mg.cell_updates_per_cycle()  # global (all ranks)
+
+    # ---------------- device-resident V-cycles: W warm-up, K timed (CUDA events inside the library, max over ranks)
+    if args.warmup > 0:
+        mg.solve([F["head"]], [F["rhs"]], fixed_cycles=args.warmup)
+    clocks = Clocks(local_rank)
+    if rank == 0:
+        clocks.start()
+        time.sleep(0.3)
+    barrier()
+    l0 = ctx.kernel_launches()
+    t0 = time.perf_counter()
+    it, hist, stats = mg.solve([F["head"]], [F["rhs"]], fixed_cycles=args.steps)
+    barrier()
+    wall = time.perf_counter() - t0
+    launches = ctx.kernel_launches() - l0
+    dev_ms = max_over_ranks(stats.device_ms)
+    value = updates_per_cycle * args.steps / (dev_ms * 1e-3)
+
+    # ---------------- dominant kernel alone: fused red+black GSRB sweep of the finest level, CUDA events on its stream
+    nrel = 16
+    op0.relax(F["head"], F["rhs"], 4)
+    ctx.event_record(0)
+    op0.relax(F["head"], F["rhs"], nrel)
+    ctx.event_record(1)
+    k_ms = ctx.event_elapsed_ms(0, 1) / nrel
+    clk = clocks.finish() if rank == 0 else None
+    cells_local = size * size
+    peak, peak_src = measured_peak()
+    achieved = BYTES_PER_UPDATE_SMOOTHER * cells_local / (k_ms * 1e-3) / 1e9
+
+    # ---------------- end to end through the public API with HOST buffers: one head solve = upload of all inputs from
+    # pinned FArrayBox memory, per-solve operator set-up, E2E_CYCLES V-cycles, download of the head
+    e2e_bytes_in = sum(host[k].numel() * 8 for k in ("head", "rhs", "B", "Pi", "zb", "mask", "bX", "bY"))
+    e2e_bytes_out = head_out.numel() * 8
+    e2e_times = []
+    for s in range(args.e2e_steps + 1):
+        barrier()
+        t0 = time.perf_counter()
+        for k in ("head", "rhs", "B", "Pi", "zb", "mask", "bX", "bY"):
+            F[k].upload_packed(host[k])
+        for k in ("B", "Pi", "zb", "mask"):
+            amr.CopyGhostCells(F[k])
+        mg.refresh()
+        mg.solve([F["head"]], [F["rhs"]], fixed_cycles=args.e2e_cycles)
+        F["head"].download_packed(head_out)
+        barrier()
+        if s > 0:
+            e2e_times.append(time.perf_counter() - t0)
+    e2e_t = max_over_ranks(float(np.mean(e2e_times)))
+    e2e_value = updates_per_cycle * args.e2e_cycles / e2e_t
+
+    # ---------------- CPU baseline beside it (rank 0, N = 1 only): bounded sample, all host threads
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        threads = os.cpu_count() or 1
+        v, dt, d = cpu_vcycles(args.cpu_size, args.cpu_cycles, threads, args.bottom)
+        cpu = {"value": v, "unit": UNIT, "cores": threads, "kind": "port",
+               "sample": f"{args.cpu_cycles} FAS V-cycles on a {args.cpu_size}x{args.cpu_size} sample of the workload "
+                         f"({dt:.1f} s), oracle C restatement with OpenMP over boxes"}
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic",
+            "config": {"workload": f"AMR_multiMoulins base grid scaled to {size}x{size} cells per GPU (global {cfg.nx}x{cfg.ny}), "
+                                   f"single level, {len(boxes)} boxes of 64^2, MG depths 0-{ndepth - 1}",
+                       "step": "one FAS V-cycle incl. UpdateOperator/AverageOperator and residual max-norm",
+                       "pre": 4, "post": 4, "bottom": args.bottom, "partition": f"box-wise y-strips over {world} GPU(s)",
+                       "l2_policy": "inputs larger than L2 (finest-level fields 512 MiB each)",
+                       "relax_mode": "fused red+black streaming sweep" if args.relax_mode == 1 else "separate colour passes",
+                       "e2e_step": f"one head solve = H2D of 8 fields + set-up + {args.e2e_cycles} V-cycles + D2H of head"},
+            "roofline": {"bound": "hbm", "kernel": "k_gsrb_fused (finest level)", "achieved": achieved, "peak": peak,
+                         "unit": "GB/s", "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                         "kernel_ms": k_ms, "bytes_per_cell_update": BYTES_PER_UPDATE_SMOOTHER,
+                         "vcycle_gbs_at_97B": value / world * BYTES_PER_UPDATE_VCYCLE / 1e9},
+            "cpu_baseline": cpu,
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": e2e_bytes_in, "d2h_bytes_per_step": e2e_bytes_out,
+                    "ms_per_step": 1e3 * e2e_t, "vcycles_per_step": args.e2e_cycles},
+            "gpu_launches": int(launches),
+            "clocks": clk,
+            "resnorm": [float(hist[0]), float(hist[-1])],
+            "wall_ms_per_step": 1e3 * wall / args.steps,
+        }
+        print(json.dumps(line), flush=True)
+    ctx.sync()
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -93,6 +93,9 @@ int sg_ctx_sync(sg_ctx* ctx);
 int sg_ctx_set_stream(sg_ctx* ctx, void* cuda_stream);
 int sg_ctx_kernel_launches(sg_ctx* ctx, long long* out);
 int sg_nccl_unique_id(void* out128);
+/* CUDA events on the context's stream (slots 0..7): device-side timing of any sequence of calls */
+int sg_ctx_event_record(sg_ctx* ctx, int slot);
+int sg_ctx_event_elapsed_ms(sg_ctx* ctx, int slot0, int slot1, double* ms);
 
 /* ------------------------------------------------------------------ layouts ------------------------------ */
 /* DisjointBoxLayout(boxes, procIDs, ProblemDomain) as built at src/AmrHydro.cpp:4844-4930.  owner[b] is the
@@ -114,6 +117,10 @@ int sg_field_download_box(const sg_field* f, int box, double* host_fab);
 /* batched variants: fabs[b] for every box of the layout (entries of boxes owned elsewhere are ignored) */
 int sg_field_upload(sg_field* f, const double* const* fabs);
 int sg_field_download(const sg_field* f, double* const* fabs);
+/* same, when the caller keeps all owned FArrayBoxes consecutively (box order) in one buffer, ideally pinned:
+   one DMA straight from/to that buffer, no staging copy on the host */
+int sg_field_upload_packed(sg_field* f, const double* packed, size_t ndoubles);
+int sg_field_download_packed(const sg_field* f, double* packed, size_t ndoubles);
 /* raw device view for zero-copy callers (torch): base pointer of the rank-local patch array, element strides */
 int sg_field_device_view(sg_field* f, void** base, long long* pitch, long long* comp_stride,
                          int patch_lo[2], int patch_hi[2], long long* offset_of_patch_lo);
@@ -230,6 +237,9 @@ int sg_op_cfInterp(sg_op* op, sg_field* phi, const sg_field* phi_coarse);
    (src/AmrHydro.cpp:719-768), kept on the device: one call = all V-cycles, residual norms on device. */
 int sg_solver_define(sg_factory* f, sg_solver** out, int num_levels);
 int sg_solver_destroy(sg_solver* s);
+/* re-derive the MG-depth coefficient sets from the (updated) finest fields: what rebuilding factory + solver per
+   Picard iteration does in the reference (src/AmrHydro.cpp:704-735), without reallocating */
+int sg_solver_refresh(sg_solver* s);
 int sg_solver_depth(const sg_solver* s, int level, int* ndepth);
 int sg_solver_solve(sg_solver* s, sg_field* const* phi, sg_field* const* rhs, int l_max, int l_base,
                     const sg_solver_params* sp, double* resnorm_history /* max_iter+2 or NULL */,

@@ -49,6 +49,14 @@ class Context:
         check(lib().sg_ctx_kernel_launches(self.h, C.byref(n)))
         return n.value
 
+    def event_record(self, slot):
+        check(lib().sg_ctx_event_record(self.h, slot))
+
+    def event_elapsed_ms(self, slot0, slot1):
+        ms = C.c_double()
+        check(lib().sg_ctx_event_elapsed_ms(self.h, slot0, slot1, C.byref(ms)))
+        return ms.value
+
     def set_relax_mode(self, mode):
         check(lib().sg_set_relax_mode(self.h, mode))
 
@@ -125,6 +133,18 @@ class LevelData:
         ptrs = (C.c_void_p * len(outs))(*[None if f is None else f.ctypes.data for f in outs])
         check(lib().sg_field_download(self.h, ptrs))
         return outs
+
+    def packed_size(self):
+        return int(sum(np.prod(self.fab_shape(b)) for b in range(len(self.layout.boxes)) if self.layout.owned(b)))
+
+    def upload_packed(self, buf):
+        """buf: all owned FArrayBoxes consecutively in box order (numpy array or anything with a data pointer)"""
+        ptr, n = (buf.ctypes.data, buf.size) if isinstance(buf, np.ndarray) else (buf.data_ptr(), buf.numel())
+        check(lib().sg_field_upload_packed(self.h, C.c_void_p(ptr), n))
+
+    def download_packed(self, buf):
+        ptr, n = (buf.ctypes.data, buf.size) if isinstance(buf, np.ndarray) else (buf.data_ptr(), buf.numel())
+        check(lib().sg_field_download_packed(self.h, C.c_void_p(ptr), n))
 
     # -- helpers for tests: move whole-level arrays -------------------------------------------------
     def set_global(self, g, glo):
@@ -363,6 +383,9 @@ class AMRFASMultiGrid:
         out = C.c_int()
         check(lib().sg_solver_depth(self.h, 0, C.byref(out)))
         return out.value
+
+    def refresh(self):
+        check(lib().sg_solver_refresh(self.h))
 
     def cell_updates_per_cycle(self):
         out = C.c_double()

@@ -45,12 +45,14 @@ pvp, ip, dp = C.POINTER(C.c_void_p), C.POINTER(C.c_int), C.POINTER(C.c_double)
 # name -> argtypes; every function returns int status except sg_last_error / sg_version
 SIGNATURES = {
     "sg_ctx_create": [pvp, ci, ci, ci, vp], "sg_ctx_destroy": [vp], "sg_ctx_sync": [vp], "sg_ctx_set_stream": [vp, vp],
-    "sg_ctx_kernel_launches": [vp, C.POINTER(C.c_longlong)], "sg_nccl_unique_id": [vp], "sg_set_relax_mode": [vp, ci],
+    "sg_ctx_kernel_launches": [vp, C.POINTER(C.c_longlong)], "sg_nccl_unique_id": [vp],
+    "sg_ctx_event_record": [vp, ci], "sg_ctx_event_elapsed_ms": [vp, ci, ci, dp], "sg_solver_refresh": [vp], "sg_set_relax_mode": [vp, ci],
     "sg_layout_create": [vp, pvp, ci, ip, ip, ip, ip], "sg_layout_coarsen": [vp, ci, pvp],
     "sg_layout_coarsenable": [vp, ci, ip], "sg_layout_nbox": [vp, ip], "sg_layout_destroy": [vp],
     "sg_field_create": [vp, pvp, ci, ci, ci], "sg_field_destroy": [vp],
     "sg_field_upload_box": [vp, ci, dp], "sg_field_download_box": [vp, ci, dp],
     "sg_field_upload": [vp, pvp], "sg_field_download": [vp, pvp],
+    "sg_field_upload_packed": [vp, vp, C.c_size_t], "sg_field_download_packed": [vp, vp, C.c_size_t],
     "sg_field_device_view": [vp, pvp, C.POINTER(C.c_longlong), C.POINTER(C.c_longlong), ip, ip, C.POINTER(C.c_longlong)],
     "sg_exchange": [vp, ci], "sg_extrap_ghost_cells": [vp], "sg_copy_ghost_cells": [vp],
     "sg_apply_bc": [vp, C.POINTER(BC), dp, ci],

@@ -72,6 +72,7 @@ struct sg_ctx {
   double* h_stage = nullptr; size_t h_stage_cap = 0; // pinned staging for batched upload/download
   double* d_stage = nullptr; size_t d_stage_cap = 0;
   CopySeg* d_segs = nullptr; size_t segs_cap = 0;
+  cudaEvent_t ev[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
 };
 
 struct sg_field;
@@ -246,6 +247,20 @@ extern "C" int sg_ctx_set_stream(sg_ctx* c, void* s) {
 extern "C" int sg_ctx_kernel_launches(sg_ctx* c, long long* out) {
   REQUIRE(c && out, "null");
   *out = c->launches;
+  return SG_OK;
+}
+extern "C" int sg_ctx_event_record(sg_ctx* c, int slot) {
+  REQUIRE(c && slot >= 0 && slot < 8, "sg_ctx_event_record: slot 0..7");
+  if (!c->ev[slot]) CK(cudaEventCreate(&c->ev[slot]));
+  CK(cudaEventRecord(c->ev[slot], c->stream));
+  return SG_OK;
+}
+extern "C" int sg_ctx_event_elapsed_ms(sg_ctx* c, int slot0, int slot1, double* ms) {
+  REQUIRE(c && ms && slot0 >= 0 && slot0 < 8 && slot1 >= 0 && slot1 < 8 && c->ev[slot0] && c->ev[slot1], "sg_ctx_event_elapsed_ms: bad slots");
+  CK(cudaEventSynchronize(c->ev[slot1]));
+  float f = 0;
+  CK(cudaEventElapsedTime(&f, c->ev[slot0], c->ev[slot1]));
+  *ms = f;
   return SG_OK;
 }
 extern "C" int sg_set_relax_mode(sg_ctx* c, int mode) {
@@ -482,14 +497,53 @@ extern "C" int sg_field_download_box(const sg_field* f, int box, double* host) {
   return SG_OK;
 }
 
-static int ensure_stage(sg_ctx* c, size_t ndoubles, size_t nsegs) {
-  if (c->h_stage_cap < ndoubles) {
+// segment tables for moving all owned FABs (packed consecutively in box order) to/from the patch array
+static size_t build_segs(const sg_field* f, bool upload, std::vector<CopySeg>& segs, std::vector<size_t>& offs) {
+  sg_layout* L = f->lay;
+  sg_ctx* c = L->ctx;
+  size_t total = 0;
+  offs.assign(L->nbox, 0);
+  for (int b = 0; b < L->nbox; b++) {
+    if (L->owner[b] != c->rank) continue;
+    Box F = fab_rect(f, b, f->ng);
+    offs[b] = total;
+    Box rs[5];
+    int n = 1;
+    if (upload) n = upload_rects(f, b, rs); else rs[0] = F;
+    for (int cc = 0; cc < f->ncomp; cc++)
+      for (int k = 0; k < n; k++) {
+        CopySeg s;
+        long long packed = (long long)(total + (size_t)cc * F.nx() * F.ny() + (size_t)(rs[k].lo[1] - F.lo[1]) * F.nx() + (rs[k].lo[0] - F.lo[0]));
+        long long dev = (long long)((f->p(cc) - f->base) + dev_off(f, rs[k].lo[0], rs[k].lo[1]));
+        s.so = upload ? packed : dev; s.dofs = upload ? dev : packed;
+        s.nx = rs[k].nx(); s.ny = rs[k].ny();
+        s.sp = upload ? F.nx() : L->pitch; s.dp = upload ? L->pitch : F.nx();
+        segs.push_back(s);
+      }
+    total += (size_t)F.nx() * F.ny() * f->ncomp;
+  }
+  return total;
+}
+static int scatter_from_stage(sg_field* f, const std::vector<CopySeg>& segs, const double* host_packed, size_t total) {
+  sg_ctx* c = f->lay->ctx;
+  CK(cudaMemcpyAsync(c->d_stage, host_packed, total * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+  CK(cudaMemcpyAsync(c->d_segs, segs.data(), segs.size() * sizeof(CopySeg), cudaMemcpyHostToDevice, c->stream));
+  LAUNCH(c, k_copy_segs, dim3((unsigned)segs.size(), 4), 256, f->base, c->d_stage, c->d_segs, (int)segs.size());
+  CK(cudaStreamSynchronize(c->stream)); // segs / caller's buffer may go away
+  return SG_OK;
+}
+static int ensure_dev_stage(sg_ctx* c, size_t ndoubles, size_t nsegs, bool host_too) {
+  if (c->d_stage_cap < ndoubles) {
     CK(cudaStreamSynchronize(c->stream));
-    cudaFreeHost(c->h_stage); cudaFree(c->d_stage);
-    c->h_stage = nullptr; c->d_stage = nullptr;
-    CK(cudaMallocHost(&c->h_stage, ndoubles * sizeof(double)));
+    cudaFree(c->d_stage); c->d_stage = nullptr;
     CK(cudaMalloc(&c->d_stage, ndoubles * sizeof(double)));
-    c->h_stage_cap = c->d_stage_cap = ndoubles;
+    c->d_stage_cap = ndoubles;
+  }
+  if (host_too && c->h_stage_cap < ndoubles) {
+    CK(cudaStreamSynchronize(c->stream));
+    cudaFreeHost(c->h_stage); c->h_stage = nullptr;
+    CK(cudaMallocHost(&c->h_stage, ndoubles * sizeof(double)));
+    c->h_stage_cap = ndoubles;
   }
   if (c->segs_cap < nsegs) {
     CK(cudaStreamSynchronize(c->stream));
@@ -506,26 +560,10 @@ extern "C" int sg_field_upload(sg_field* f, const double* const* fabs) {
   sg_layout* L = f->lay;
   sg_ctx* c = L->ctx;
   if (!L->has_local) return SG_OK;
-  size_t total = 0;
   std::vector<CopySeg> segs;
-  std::vector<size_t> offs(L->nbox, 0);
-  for (int b = 0; b < L->nbox; b++) {
-    if (L->owner[b] != c->rank) continue;
-    Box F = fab_rect(f, b, f->ng);
-    offs[b] = total;
-    Box rs[5];
-    int n = upload_rects(f, b, rs);
-    for (int cc = 0; cc < f->ncomp; cc++)
-      for (int k = 0; k < n; k++) {
-        CopySeg s;
-        s.so = (long long)(total + (size_t)cc * F.nx() * F.ny() + (size_t)(rs[k].lo[1] - F.lo[1]) * F.nx() + (rs[k].lo[0] - F.lo[0]));
-        s.dofs = (long long)((f->p(cc) - f->base) + dev_off(f, rs[k].lo[0], rs[k].lo[1]));
-        s.nx = rs[k].nx(); s.ny = rs[k].ny(); s.sp = F.nx(); s.dp = L->pitch;
-        segs.push_back(s);
-      }
-    total += (size_t)F.nx() * F.ny() * f->ncomp;
-  }
-  SGCALL(ensure_stage(c, total, segs.size()));
+  std::vector<size_t> offs;
+  size_t total = build_segs(f, true, segs, offs);
+  SGCALL(ensure_dev_stage(c, total, segs.size(), true));
   CK(cudaStreamSynchronize(c->stream)); // staging buffers may still be in use by a previous transfer
   for (int b = 0; b < L->nbox; b++) {
     if (L->owner[b] != c->rank) continue;
@@ -533,11 +571,26 @@ extern "C" int sg_field_upload(sg_field* f, const double* const* fabs) {
     REQUIRE(fabs[b], "sg_field_upload: null FAB pointer for owned box %d", b);
     memcpy(c->h_stage + offs[b], fabs[b], (size_t)F.nx() * F.ny() * f->ncomp * sizeof(double));
   }
-  CK(cudaMemcpyAsync(c->d_stage, c->h_stage, total * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+  return scatter_from_stage(f, segs, c->h_stage, total);
+}
+// same, but the caller already holds all owned FABs consecutively (box order) in one (ideally pinned) buffer
+extern "C" int sg_field_upload_packed(sg_field* f, const double* packed, size_t ndoubles) {
+  REQUIRE(f && packed, "sg_field_upload_packed: bad arguments");
+  sg_layout* L = f->lay;
+  if (!L->has_local) return SG_OK;
+  std::vector<CopySeg> segs;
+  std::vector<size_t> offs;
+  size_t total = build_segs(f, true, segs, offs);
+  REQUIRE(total == ndoubles, "sg_field_upload_packed: buffer holds %zu doubles, the owned boxes need %zu", ndoubles, total);
+  SGCALL(ensure_dev_stage(L->ctx, total, segs.size(), false));
+  return scatter_from_stage(f, segs, packed, total);
+}
+static int gather_to_stage(const sg_field* f, std::vector<CopySeg>& segs, double* host_packed, size_t total) {
+  sg_ctx* c = f->lay->ctx;
   CK(cudaMemcpyAsync(c->d_segs, segs.data(), segs.size() * sizeof(CopySeg), cudaMemcpyHostToDevice, c->stream));
-  // valid regions first, then ghost pieces: launch in two passes so a ghost piece never races a valid copy
-  LAUNCH(c, k_copy_segs, dim3(4, (unsigned)segs.size()), 256, f->base, c->d_stage, c->d_segs, (int)segs.size());
-  CK(cudaStreamSynchronize(c->stream)); // segs vector goes out of scope
+  LAUNCH(c, k_copy_segs, dim3((unsigned)segs.size(), 4), 256, c->d_stage, f->base, c->d_segs, (int)segs.size());
+  CK(cudaMemcpyAsync(host_packed, c->d_stage, total * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+  CK(cudaStreamSynchronize(c->stream));
   return SG_OK;
 }
 extern "C" int sg_field_download(const sg_field* f, double* const* fabs) {
@@ -545,27 +598,11 @@ extern "C" int sg_field_download(const sg_field* f, double* const* fabs) {
   sg_layout* L = f->lay;
   sg_ctx* c = L->ctx;
   if (!L->has_local) return SG_OK;
-  size_t total = 0;
   std::vector<CopySeg> segs;
-  std::vector<size_t> offs(L->nbox, 0);
-  for (int b = 0; b < L->nbox; b++) {
-    if (L->owner[b] != c->rank) continue;
-    Box F = fab_rect(f, b, f->ng);
-    offs[b] = total;
-    for (int cc = 0; cc < f->ncomp; cc++) {
-      CopySeg s;
-      s.dofs = (long long)(total + (size_t)cc * F.nx() * F.ny());
-      s.so = (long long)((f->p(cc) - f->base) + dev_off(f, F.lo[0], F.lo[1]));
-      s.nx = F.nx(); s.ny = F.ny(); s.sp = L->pitch; s.dp = F.nx();
-      segs.push_back(s);
-    }
-    total += (size_t)F.nx() * F.ny() * f->ncomp;
-  }
-  SGCALL(ensure_stage(c, total, segs.size()));
-  CK(cudaMemcpyAsync(c->d_segs, segs.data(), segs.size() * sizeof(CopySeg), cudaMemcpyHostToDevice, c->stream));
-  LAUNCH(c, k_copy_segs, dim3(4, (unsigned)segs.size()), 256, c->d_stage, f->base, c->d_segs, (int)segs.size());
-  CK(cudaMemcpyAsync(c->h_stage, c->d_stage, total * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
-  CK(cudaStreamSynchronize(c->stream));
+  std::vector<size_t> offs;
+  size_t total = build_segs(f, false, segs, offs);
+  SGCALL(ensure_dev_stage(c, total, segs.size(), true));
+  SGCALL(gather_to_stage(f, segs, c->h_stage, total));
   for (int b = 0; b < L->nbox; b++) {
     if (L->owner[b] != c->rank) continue;
     Box F = fab_rect(f, b, f->ng);
@@ -573,6 +610,17 @@ extern "C" int sg_field_download(const sg_field* f, double* const* fabs) {
     memcpy(fabs[b], c->h_stage + offs[b], (size_t)F.nx() * F.ny() * f->ncomp * sizeof(double));
   }
   return SG_OK;
+}
+extern "C" int sg_field_download_packed(const sg_field* f, double* packed, size_t ndoubles) {
+  REQUIRE(f && packed, "sg_field_download_packed: bad arguments");
+  sg_layout* L = f->lay;
+  if (!L->has_local) return SG_OK;
+  std::vector<CopySeg> segs;
+  std::vector<size_t> offs;
+  size_t total = build_segs(f, false, segs, offs);
+  REQUIRE(total == ndoubles, "sg_field_download_packed: buffer holds %zu doubles, the owned boxes need %zu", ndoubles, total);
+  SGCALL(ensure_dev_stage(L->ctx, total, segs.size(), false));
+  return gather_to_stage(f, segs, packed, total);
 }
 extern "C" int sg_field_device_view(sg_field* f, void** base, long long* pitch, long long* comp_stride, int patch_lo[2],
                                     int patch_hi[2], long long* offset_of_patch_lo) {
@@ -803,6 +851,24 @@ static int avg_face(sg_field* c, const sg_field* f, int r) {
   return SG_OK;
 }
 
+// arithmetic averages of the FINEST data by 2^depth (src/VCAMRNonLinearPoissonOp.cpp:1130-1139) + NeumBCForB (:1142-1148)
+static int average_coefficients(sg_factory* f, sg_op* op, int level, int coarsening) {
+  sg_layout* Lc = op->lay;
+  if (f->alpha != 0.0) SGCALL(avg_cell(op->aCoef, f->aCoef[level], coarsening));
+  SGCALL(avg_face(op->bX, f->bX[level], coarsening));
+  SGCALL(avg_face(op->bY, f->bY[level], coarsening));
+  SGCALL(avg_cell(op->B, f->B[level], coarsening));
+  SGCALL(avg_cell(op->Pi, f->Pi[level], coarsening));
+  SGCALL(avg_cell(op->zb, f->zb[level], coarsening));
+  SGCALL(avg_cell(op->mask, f->mask[level], coarsening));
+  if (Lc->has_local) {
+    Geom g = make_geom(Lc, nullptr);
+    int n = std::max(g.nx, g.ny);
+    LAUNCH(f->ctx, k_neum_copy_ghost, dim3((n + 127) / 128, 4), 128, op->B->p(), g);
+  }
+  return SG_OK;
+}
+
 extern "C" int sg_factory_MGnewOp(sg_factory* f, int level, int depth, int homo_only, sg_op** out) {
   (void)homo_only;
   REQUIRE(f && out && level >= 0 && level < f->nlevels && depth >= 0, "sg_factory_MGnewOp: bad arguments");
@@ -834,19 +900,7 @@ extern "C" int sg_factory_MGnewOp(sg_factory* f, int level, int depth, int homo_
     SGCALL(sg_field_create(Lc, &op->Pi, 1, 1, SG_CELL));
     SGCALL(sg_field_create(Lc, &op->zb, 1, 1, SG_CELL));
     SGCALL(sg_field_create(Lc, &op->mask, 1, 1, SG_CELL));
-    // arithmetic averages of the FINEST data by 2^depth (src/VCAMRNonLinearPoissonOp.cpp:1130-1139)
-    if (f->alpha != 0.0) SGCALL(avg_cell(op->aCoef, f->aCoef[level], coarsening));
-    SGCALL(avg_face(op->bX, f->bX[level], coarsening));
-    SGCALL(avg_face(op->bY, f->bY[level], coarsening));
-    SGCALL(avg_cell(op->B, f->B[level], coarsening));
-    SGCALL(avg_cell(op->Pi, f->Pi[level], coarsening));
-    SGCALL(avg_cell(op->zb, f->zb[level], coarsening));
-    SGCALL(avg_cell(op->mask, f->mask[level], coarsening));
-    if (Lc->has_local) { // NeumBCForB on the coarse gap height (:1142-1148)
-      Geom g = make_geom(Lc, nullptr);
-      int n = std::max(g.nx, g.ny);
-      LAUNCH(f->ctx, k_neum_copy_ghost, dim3((n + 127) / 128, 4), 128, op->B->p(), g);
-    }
+    SGCALL(average_coefficients(f, op, level, coarsening));
   }
   SGCALL(coef_ghosts(op, false));
   *out = op;
@@ -1213,6 +1267,16 @@ extern "C" int sg_solver_define(sg_factory* f, sg_solver** out, int num_levels) 
   }
   SGCALL(sg_field_create(s->ops[0]->lay, &s->resid, 1, 0, SG_CELL));
   *out = s;
+  return SG_OK;
+}
+// The reference builds a new factory + operator hierarchy for every Picard iteration (src/AmrHydro.cpp:704-735).
+// Same effect without reallocating: re-average the (changed) finest coefficients into the existing MG operators.
+extern "C" int sg_solver_refresh(sg_solver* s) {
+  REQUIRE(s, "sg_solver_refresh: null");
+  for (size_t d = 0; d < s->ops.size(); d++) {
+    if (d > 0) SGCALL(average_coefficients(s->fac, s->ops[d], 0, 1 << d));
+    SGCALL(coef_ghosts(s->ops[d], false));
+  }
   return SG_OK;
 }
 extern "C" int sg_solver_destroy(sg_solver* s) {

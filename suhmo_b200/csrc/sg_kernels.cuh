@@ -660,10 +660,10 @@ __global__ void __launch_bounds__(256) k_reduce_final(const double* __restrict__
 // box <-> patch staging for batched upload/download: segment table {src offset, dst offset, nx, ny, src pitch, dst pitch}
 struct CopySeg { long long so, dofs; int nx, ny, sp, dp; };
 __global__ void k_copy_segs(double* __restrict__ dst, const double* __restrict__ src, const CopySeg* __restrict__ segs, int nseg) {
-  int s = blockIdx.y;
+  int s = blockIdx.x;
   if (s >= nseg) return;
   CopySeg c = segs[s];
-  for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < c.nx * c.ny; t += gridDim.x * blockDim.x) {
+  for (int t = blockIdx.y * blockDim.x + threadIdx.x; t < c.nx * c.ny; t += gridDim.y * blockDim.x) {
     int i = t % c.nx, j = t / c.nx;
     dst[c.dofs + (long long)j * c.dp + i] = src[c.so + (long long)j * c.sp + i];
   }
