@@ -267,7 +267,7 @@ def main():
     e2e_bytes_in = sum(host[k].numel() * 8 for k in ("head", "rhs", "B", "Pi", "zb", "mask", "bX", "bY"))
     e2e_bytes_out = head_out.numel() * 8
     e2e_times = []
-    for s in range(args.e2e_steps + 1):
+    for s in range(args.e2e_steps + 1 if args.e2e_steps > 0 else 0):  # --e2e-steps 0: profiling runs skip this leg
         barrier()
         t0 = time.perf_counter()
         for k in ("head", "rhs", "B", "Pi", "zb", "mask", "bX", "bY"):
@@ -280,7 +280,7 @@ def main():
         barrier()
         if s > 0:
             e2e_times.append(time.perf_counter() - t0)
-    e2e_t = max_over_ranks(float(np.mean(e2e_times)))
+    e2e_t = max_over_ranks(float(np.mean(e2e_times))) if e2e_times else float("nan")
     e2e_value = updates_per_cycle * args.e2e_cycles / e2e_t
 
     # ---------------- CPU baseline beside it (rank 0, N = 1 only): bounded sample, all host threads

@@ -60,6 +60,9 @@ class Context:
     def set_relax_mode(self, mode):
         check(lib().sg_set_relax_mode(self.h, mode))
 
+    def set_tuning(self, key, value):
+        check(lib().sg_set_tuning(self.h, key, value))
+
     def destroy(self):
         if self.h:
             lib().sg_ctx_destroy(self.h)

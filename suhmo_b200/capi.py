@@ -46,7 +46,7 @@ pvp, ip, dp = C.POINTER(C.c_void_p), C.POINTER(C.c_int), C.POINTER(C.c_double)
 SIGNATURES = {
     "sg_ctx_create": [pvp, ci, ci, ci, vp], "sg_ctx_destroy": [vp], "sg_ctx_sync": [vp], "sg_ctx_set_stream": [vp, vp],
     "sg_ctx_kernel_launches": [vp, C.POINTER(C.c_longlong)], "sg_nccl_unique_id": [vp],
-    "sg_ctx_event_record": [vp, ci], "sg_ctx_event_elapsed_ms": [vp, ci, ci, dp], "sg_solver_refresh": [vp], "sg_set_relax_mode": [vp, ci],
+    "sg_ctx_event_record": [vp, ci], "sg_ctx_event_elapsed_ms": [vp, ci, ci, dp], "sg_solver_refresh": [vp], "sg_set_relax_mode": [vp, ci], "sg_set_tuning": [vp, ci, ci],
     "sg_layout_create": [vp, pvp, ci, ip, ip, ip, ip], "sg_layout_coarsen": [vp, ci, pvp],
     "sg_layout_coarsenable": [vp, ci, ip], "sg_layout_nbox": [vp, ip], "sg_layout_destroy": [vp],
     "sg_field_create": [vp, pvp, ci, ci, ci], "sg_field_destroy": [vp],

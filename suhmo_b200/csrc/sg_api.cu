@@ -58,11 +58,12 @@ struct Box {
 static inline int fdiv(int a, int r) { return a >= 0 ? a / r : -((-a + r - 1) / r); }
 
 struct sg_ctx {
-  int device = 0, rank = 0, nranks = 1;
+  int device = 0, rank = 0, nranks = 1, num_sms = 148;
   cudaStream_t stream = nullptr;
   bool own_stream = true;
   long long launches = 0;
   int relax_mode = 1;
+  int tune[8] = {0, 0, 0, 0, 0, 0, 0, 0}; // experiment knobs (sg_set_tuning): 0 rows per warp, 1 CTAs per SM of the fused sweep
   SgNccl nccl;
   // reduction scratch
   double* d_partial = nullptr;
@@ -207,6 +208,7 @@ extern "C" int sg_ctx_create(sg_ctx** out, int device, int rank, int nranks, con
   CK(cudaSetDevice(device));
   sg_ctx* c = new sg_ctx();
   c->device = device; c->rank = rank; c->nranks = nranks;
+  CK(cudaDeviceGetAttribute(&c->num_sms, cudaDevAttrMultiProcessorCount, device));
   CK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
   CK(cudaMalloc(&c->d_scalar, 64 * sizeof(double)));
   CK(cudaMemsetAsync(c->d_scalar, 0, 64 * sizeof(double), c->stream));
@@ -261,6 +263,11 @@ extern "C" int sg_ctx_event_elapsed_ms(sg_ctx* c, int slot0, int slot1, double* 
   float f = 0;
   CK(cudaEventElapsedTime(&f, c->ev[slot0], c->ev[slot1]));
   *ms = f;
+  return SG_OK;
+}
+extern "C" int sg_set_tuning(sg_ctx* c, int key, int value) {
+  REQUIRE(c && key >= 0 && key < 8, "sg_set_tuning: key 0..7");
+  c->tune[key] = value;
   return SG_OK;
 }
 extern "C" int sg_set_relax_mode(sg_ctx* c, int mode) {
@@ -939,9 +946,18 @@ static int relax_impl(sg_op* op, sg_field* phi, const sg_field* rhs, int iterati
     f.rhs = rhs->p();
     f.sdx[0] = -op->dx[0]; f.sdx[1] = op->dx[0]; f.sdx[2] = -op->dx[1]; f.sdx[3] = op->dx[1];
     f.nstrips = (L->nx + FUSED_COLS - 1) / FUSED_COLS;
-    // rows per warp: enough warps to fill 148 SMs x 16 warps, but segments of at least 32 rows when possible
-    int target_warps = 148 * 16;
-    int nsegs = std::max(1, std::min((L->ny + 31) / 32, (target_warps + f.nstrips - 1) / f.nstrips));
+    // Segments of rows per warp.  Every warp does the same amount of work, so a partly filled last wave costs
+    // as much as a full one: either fit the whole sweep into ONE resident wave (large levels: warps <= SMs x
+    // resident warps), or cut it into many short segments so that the tail is a small fraction (never between).
+    int minb = c->tune[1] == 3 ? 3 : 4;
+    int capacity = c->num_sms * minb * 4; // resident warps (128-thread CTAs)
+    int nsegs;
+    if (c->tune[0] > 0) nsegs = (L->ny + c->tune[0] - 1) / c->tune[0];
+    else if (f.nstrips * ((L->ny + 63) / 64) <= capacity) nsegs = std::max(1, std::min((L->ny + 31) / 32, capacity / f.nstrips));
+    else {
+      nsegs = capacity / f.nstrips;               // one full wave ...
+      if (nsegs < 1 || L->ny / nsegs > 1024) nsegs = (L->ny + 63) / 64; // ... unless segments get too long: many waves
+    }
     f.rows_per_warp = (L->ny + nsegs - 1) / nsegs;
     f.nsegs = (L->ny + f.rows_per_warp - 1) / f.rows_per_warp;
     int nwarps = f.nstrips * f.nsegs;
@@ -950,8 +966,9 @@ static int relax_impl(sg_op* op, sg_field* phi, const sg_field* rhs, int iterati
       if (ghosts) SGCALL(fill_ghosts(phi, 2));
       f.phi_in = phi->p();
       f.phi_out = scratch->p();
-      if (a.has_a) LAUNCH(c, k_gsrb_fused<1>, blocks, 128, f);
-      else LAUNCH(c, k_gsrb_fused<0>, blocks, 128, f);
+      if (a.has_a) LAUNCH(c, (k_gsrb_fused<1, 4>), blocks, 128, f);
+      else if (minb == 3) LAUNCH(c, (k_gsrb_fused<0, 3>), blocks, 128, f);
+      else LAUNCH(c, (k_gsrb_fused<0, 4>), blocks, 128, f);
       std::swap(phi->base, scratch->base); // out-of-place sweep: the field now owns the new buffer
     }
   } else {

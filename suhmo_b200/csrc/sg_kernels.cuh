@@ -241,8 +241,8 @@ struct FusedArgs {
 
 __device__ __forceinline__ double2 ld2(const double* p) { return *reinterpret_cast<const double2*>(p); }
 
-template <int HAS_A>
-__global__ void __launch_bounds__(128, 4) k_gsrb_fused(FusedArgs f) {
+template <int HAS_A, int MINB>
+__global__ void __launch_bounds__(128, MINB) k_gsrb_fused(FusedArgs f) {
   const OpArgs& a = f.a;
   const int lane = threadIdx.x & 31;
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
