@@ -62,6 +62,7 @@ struct orc_layout {
   int periodic[2];
   oplan faces1;   /* 1 ghost, face strips only */
   oplan full[4];  /* all ghosts incl. corners, index = ng (1..3) */
+  int* cover;     /* lazily built: box index holding each domain cell, -1 where the level has no box */
 };
 
 static void plan_push(oplan* p, ocopy c) {
@@ -112,6 +113,7 @@ void orc_layout_box(const orc_layout* lay, int b, int out[4]) {
 void orc_layout_free(orc_layout* L) {
   if (!L) return;
   free(L->faces1.c);
+  free(L->cover);
   for (int i = 0; i < 4; i++) free(L->full[i].c);
   free(L->box);
   free(L);
@@ -626,6 +628,7 @@ struct orc_op {
   orc_field* lambda;
   orc_field *nl, *dnl; /* reference allocates these per call (VCAMRNonLinearPoissonOp.cpp:126-127); kept here */
   int lambda_dirty;
+  int ref_to_coarser;  /* m_refToCoarser (2 in every SUHMO input) */
 };
 
 orc_op* orc_op_create(const orc_layout* lay, const double dx[2], double alpha, double beta,
@@ -640,6 +643,7 @@ orc_op* orc_op_create(const orc_layout* lay, const double dx[2], double alpha, d
   op->nl = orc_field_create(lay, 1, 0, ORC_CELL);
   op->dnl = orc_field_create(lay, 1, 0, ORC_CELL);
   op->lambda_dirty = 1;
+  op->ref_to_coarser = 2;
   orc_op_reset_lambda(op); /* computeLambda() in MGnewOp/AMRnewOp */
   return op;
 }
@@ -1044,4 +1048,533 @@ void orc_set_threads(int n) {
 #else
   (void)n;
 #endif
+}
+
+/* =========================================================================================== */
+/* AMR: two-level machinery and the multi-level FAS V-cycle                                     */
+/*                                                                                             */
+/* Everything in this section that is not in the SUHMO tree (QuadCFInterp, LevelFluxRegister,   */
+/* copyTo between layouts, the AMRFASMultiGrid cycle) restates public Chombo 3.2 from the       */
+/* design documents / recollection; each function says which part is INFERRED.  r = 2 only      */
+/* (every SUHMO input uses ref_ratios = 2; WFlx_level hard-codes it, src/AmrHydro.cpp:1467).    */
+/* =========================================================================================== */
+
+/* box index that holds domain cell (i,j) of the level, periodic images included; -1 if none.  On return
+   (*wi,*wj) is the index inside the domain where the data lives. */
+static void cover_build(orc_layout* L) {
+  if (L->cover) return;
+  int nx = L->domain.hi[0] - L->domain.lo[0] + 1, ny = L->domain.hi[1] - L->domain.lo[1] + 1;
+  L->cover = (int*)malloc(sizeof(int) * (size_t)nx * ny);
+  for (size_t k = 0; k < (size_t)nx * ny; k++) L->cover[k] = -1;
+  for (int b = 0; b < L->nbox; b++)
+    for (int j = L->box[b].lo[1]; j <= L->box[b].hi[1]; j++)
+      for (int i = L->box[b].lo[0]; i <= L->box[b].hi[0]; i++)
+        L->cover[(size_t)(j - L->domain.lo[1]) * nx + (i - L->domain.lo[0])] = b;
+}
+static inline int cover_at(const orc_layout* L, int i, int j, int* wi, int* wj) {
+  int nx = L->domain.hi[0] - L->domain.lo[0] + 1, ny = L->domain.hi[1] - L->domain.lo[1] + 1;
+  if (i < L->domain.lo[0] || i > L->domain.hi[0]) {
+    if (!L->periodic[0]) return -1;
+    i = L->domain.lo[0] + (((i - L->domain.lo[0]) % nx) + nx) % nx;
+  }
+  if (j < L->domain.lo[1] || j > L->domain.hi[1]) {
+    if (!L->periodic[1]) return -1;
+    j = L->domain.lo[1] + (((j - L->domain.lo[1]) % ny) + ny) % ny;
+  }
+  if (wi) *wi = i;
+  if (wj) *wj = j;
+  return L->cover[(size_t)(j - L->domain.lo[1]) * nx + (i - L->domain.lo[0])];
+}
+/* is cell (i,j) inside the problem domain, counting periodic directions as unbounded */
+static inline int in_domain_p(const orc_layout* L, int i, int j) {
+  if (!L->periodic[0] && (i < L->domain.lo[0] || i > L->domain.hi[0])) return 0;
+  if (!L->periodic[1] && (j < L->domain.lo[1] || j > L->domain.hi[1])) return 0;
+  return 1;
+}
+
+/* LevelData::copyTo between two layouts of the same index space (absent Chombo): every cell of dst's
+   valid region (or of its whole array when with_ghosts, as a Copier built with a ghost vector does) that
+   some src box holds in its VALID region (periodic images included) is overwritten; others are left alone. */
+void orc_copy_to(orc_field* dst, const orc_field* src, int with_ghosts) {
+  orc_layout* Ls = (orc_layout*)src->lay;
+  cover_build(Ls);
+#pragma omp parallel for schedule(static)
+  for (int b = 0; b < dst->lay->nbox; b++) {
+    obox r = with_ghosts ? dst->ab[b] : dst->lay->box[b];
+    for (int c = 0; c < dst->ncomp; c++)
+      for (int j = r.lo[1]; j <= r.hi[1]; j++)
+        for (int i = r.lo[0]; i <= r.hi[0]; i++) {
+          int wi, wj, sb = cover_at(Ls, i, j, &wi, &wj);
+          if (sb >= 0) AT(dst, b, i, j, c) = AT(src, sb, wi, wj, c);
+        }
+  }
+}
+
+/* value of a coarse-level cell wherever it lives; returns 0 when no coarse box holds it */
+static inline int crse_val(const orc_field* c, int i, int j, int comp, double* v) {
+  int wi, wj, sb = cover_at(c->lay, i, j, &wi, &wj);
+  if (sb < 0) return 0;
+  *v = AT(c, sb, wi, wj, comp);
+  return 1;
+}
+
+/* QuadCFInterp::coarseFineInterp (absent Chombo; INFERRED from public Chombo 3.2).
+   For every ghost cell of a fine box across a coarse-fine face (inside the domain, not covered by another
+   fine box):  (1) phistar = coarse value at the ghost cell's tangential position from the coarse cell under it:
+   phic + dist*D1 + half*dist^2*D2, with centred differences when both tangential coarse neighbours are usable
+   (inside the domain and NOT covered by the fine level), else one-sided three-point differences on the usable
+   side, else two-point / zero;  (2) quadratic in the normal direction through phistar and the two nearest
+   interior fine cells (QuadCFInterp::interpPhiOnIVS form, a*x*x + b*x + c at x = 2h).
+   SUHMO call sites: src/AMRNonLinearPoissonOp.cpp:268,699,934,956,1003; VCAMRNonLinearPoissonOp.cpp:225,396,602;
+   src/AmrHydro.cpp:1483-1487. */
+void orc_cf_interp(orc_field* phiF, const orc_field* phiC, int r, double dxFine) {
+  orc_layout* Lf = (orc_layout*)phiF->lay;
+  orc_layout* Lc = (orc_layout*)phiC->lay;
+  cover_build(Lf); cover_build(Lc);
+  const double dxf = dxFine, dxc = r * dxFine;
+#pragma omp parallel for schedule(static)
+  for (int b = 0; b < Lf->nbox; b++) {
+    for (int dir = 0; dir < 2; dir++)
+      for (int side = 0; side < 2; side++) {
+        obox strip = box_adj(Lf->box[b], dir, side);
+        int ihilo = side ? 1 : -1, t = 1 - dir;
+        for (int j = strip.lo[1]; j <= strip.hi[1]; j++)
+          for (int i = strip.lo[0]; i <= strip.hi[0]; i++) {
+            if (!in_domain_p(Lf, i, j)) continue;                 /* physical boundary: m_bc's job */
+            if (cover_at(Lf, i, j, NULL, NULL) >= 0) continue;    /* another fine box: exchange's job */
+            int ivf[2] = {i, j};
+            int ivc[2] = {fdiv(i, r), fdiv(j, r)};
+            int e[2] = {t == 0, t == 1};
+            /* usable coarse neighbours in the tangential direction */
+            int av[5]; /* offsets -2..2 */
+            for (int o = -2; o <= 2; o++) {
+              int ci = ivc[0] + o * e[0], cj = ivc[1] + o * e[1];
+              av[o + 2] = in_domain_p(Lc, ci, cj) && cover_at(Lc, ci, cj, NULL, NULL) >= 0 &&
+                          cover_at(Lf, ci * r, cj * r, NULL, NULL) < 0;
+            }
+            double dist = (ivf[t] + 0.5) * dxf - (ivc[t] + 0.5) * dxc;
+            for (int c = 0; c < phiF->ncomp; c++) {
+              double p0 = 0, pp = 0, pm = 0, pp2 = 0, pm2 = 0, d1, d2;
+              crse_val(phiC, ivc[0], ivc[1], c, &p0);
+              if (av[3]) crse_val(phiC, ivc[0] + e[0], ivc[1] + e[1], c, &pp);
+              if (av[1]) crse_val(phiC, ivc[0] - e[0], ivc[1] - e[1], c, &pm);
+              if (av[4]) crse_val(phiC, ivc[0] + 2 * e[0], ivc[1] + 2 * e[1], c, &pp2);
+              if (av[0]) crse_val(phiC, ivc[0] - 2 * e[0], ivc[1] - 2 * e[1], c, &pm2);
+              if (av[3] && av[1]) { d1 = (pp - pm) / (2.0 * dxc); d2 = (pp - 2.0 * p0 + pm) / (dxc * dxc); }
+              else if (av[3] && av[4]) { d1 = (-3.0 * p0 + 4.0 * pp - pp2) / (2.0 * dxc); d2 = (p0 - 2.0 * pp + pp2) / (dxc * dxc); }
+              else if (av[1] && av[0]) { d1 = (3.0 * p0 - 4.0 * pm + pm2) / (2.0 * dxc); d2 = (p0 - 2.0 * pm + pm2) / (dxc * dxc); }
+              else if (av[3]) { d1 = (pp - p0) / dxc; d2 = 0.0; }
+              else if (av[1]) { d1 = (p0 - pm) / dxc; d2 = 0.0; }
+              else { d1 = 0.0; d2 = 0.0; }
+              double pc = p0 + dist * d1 + 0.5 * dist * dist * d2;
+              double pa = AT(phiF, b, i - 2 * ihilo * (dir == 0), j - 2 * ihilo * (dir == 1), c);
+              double pb = AT(phiF, b, i - ihilo * (dir == 0), j - ihilo * (dir == 1), c);
+              double h = dxf;
+              double a = (2. / h / h) * (2. * pc + pa * (r + 1.0) - pb * (r + 3.0)) / (r * r + 4 * r + 3.0);
+              double bq = (pb - pa) / h - a * h;
+              double x = 2. * h;
+              AT(phiF, b, i, j, c) = a * x * x + bq * x + pa;
+            }
+          }
+      }
+  }
+}
+
+void orc_op_set_ref_to_coarser(orc_op* op, int r) { op->ref_to_coarser = r; }
+
+/* relaxNF / residualNF / AMROperatorNF: CF interpolation, then the level operator
+   (src/AMRNonLinearPoissonOp.cpp:257-273,690-704,995-1008) */
+void orc_op_relax_nf(orc_op* op, orc_field* phi, const orc_field* phiCoarse, const orc_field* rhs, int iterations) {
+  if (phiCoarse) orc_cf_interp(phi, phiCoarse, op->ref_to_coarser, op->dx[0]);
+  orc_op_relax(op, phi, rhs, iterations);
+}
+void orc_op_residual_nf(orc_op* op, orc_field* res, orc_field* phi, const orc_field* phiCoarse, const orc_field* rhs) {
+  if (phiCoarse) orc_cf_interp(phi, phiCoarse, op->ref_to_coarser, op->dx[0]);
+  orc_op_residual(op, res, phi, rhs);
+}
+
+/* VCAMRNonLinearPoissonOp::getFlux (src/VCAMRNonLinearPoissonOp.cpp:792-841) at one face:
+   scale = beta*ref/dx; gradphi = (phihi - philo)*scale; flux = -bCoef*gradphi */
+static inline double face_flux(double bface, double phihi, double philo, double scale) {
+  double gradphi = (phihi - philo) * scale;
+  return -bface * gradphi;
+}
+
+/* VCAMRNonLinearPoissonOp::reflux (src/VCAMRNonLinearPoissonOp.cpp:555-652) over Chombo's LevelFluxRegister
+   (absent; appendix C.8; accumulation order INFERRED).  For every coarse cell that is not covered by the fine
+   level and has a covered neighbour across a face:
+     register  = sum over (dir, Lo/Hi)  -sign*scale*F_coarse          (incrementCoarse; coarse cell on the Lo side of
+                                                                       the fine region sees its HIGH face, sign(Lo) = -1)
+     register += for each (dir, side):  sum over the r fine faces      (incrementFine: sign*scale/r^(D-1) * F_fine)
+     residual += -(1/(dx*dy)) * register                               (LevelFluxRegister::reflux)
+   with scale = dx of the tangential direction.  Fine ghost cells are first filled by the FINER op's QuadCFInterp. */
+void orc_op_reflux(orc_op* op, orc_field* phiFine, orc_field* phi, orc_field* residual, orc_op* finerOp) {
+  orc_layout* Lc = (orc_layout*)op->lay;
+  orc_layout* Lf = (orc_layout*)finerOp->lay;
+  const int r = finerOp->ref_to_coarser;
+  cover_build(Lc); cover_build(Lf);
+  orc_cf_interp(phiFine, phi, r, finerOp->dx[0]);
+  double scale2 = 1.0;
+  for (int d = 0; d < 2; d++) scale2 *= op->dx[d];
+  scale2 = 1.0 / scale2;
+#pragma omp parallel for schedule(static)
+  for (int b = 0; b < Lc->nbox; b++) {
+    obox v = Lc->box[b];
+    for (int j = v.lo[1]; j <= v.hi[1]; j++)
+      for (int i = v.lo[0]; i <= v.hi[0]; i++) {
+        if (cover_at(Lf, i * r, j * r, NULL, NULL) >= 0) continue; /* covered coarse cell: no register */
+        double reg = 0.0;
+        int any = 0;
+        /* incrementCoarse, dir by dir, Lo then Hi */
+        for (int dir = 0; dir < 2; dir++)
+          for (int side = 0; side < 2; side++) {
+            /* side = 0 (Lo): this cell lies just below a fine box's low side, i.e. its neighbour at +e is covered */
+            int ni = i + (dir == 0) * (side ? -1 : 1), nj = j + (dir == 1) * (side ? -1 : 1);
+            if (!in_domain_p(Lc, ni, nj) || cover_at(Lf, ni * r, nj * r, NULL, NULL) < 0) continue;
+            any = 1;
+            double scale = op->dx[1 - dir];
+            int fi = i + (dir == 0) * (side ? 0 : 1), fj = j + (dir == 1) * (side ? 0 : 1); /* the CF face */
+            double bface = dir == 0 ? AT(op->bX, b, fi, fj, 0) : AT(op->bY, b, fi, fj, 0);
+            double phihi = AT(phi, b, fi, fj, 0), philo = AT(phi, b, fi - (dir == 0), fj - (dir == 1), 0);
+            double F = face_flux(bface, phihi, philo, op->beta * 1 / op->dx[dir]);
+            double sgn = side ? 1.0 : -1.0;
+            reg = reg + (-sgn * scale) * F;
+          }
+        if (!any) continue;
+        /* incrementFine */
+        for (int dir = 0; dir < 2; dir++)
+          for (int side = 0; side < 2; side++) {
+            int ni = i + (dir == 0) * (side ? -1 : 1), nj = j + (dir == 1) * (side ? -1 : 1);
+            int wi, wj;
+            if (!in_domain_p(Lc, ni, nj) || cover_at(Lf, ni * r, nj * r, &wi, &wj) < 0) continue;
+            double scale = op->dx[1 - dir];
+            double sgn = side ? 1.0 : -1.0;
+            double sf = sgn * scale / (double)r; /* denom = nRefine^(SpaceDim-1) */
+            double piece = 0.0;
+            for (int k = 0; k < r; k++) {
+              /* interior fine cell next to the CF face (wrapped into the domain), on the fine box's `side` */
+              int ci = (dir == 0) ? (side ? wi + r - 1 : wi) : wi + k;
+              int cj = (dir == 1) ? (side ? wj + r - 1 : wj) : wj + k;
+              int fb = cover_at(Lf, ci, cj, NULL, NULL);
+              int gi = ci + (dir == 0) * (side ? 1 : -1), gj = cj + (dir == 1) * (side ? 1 : -1); /* its CF ghost cell */
+              int fi = (dir == 0) ? (side ? ci + 1 : ci) : ci, fj = (dir == 1) ? (side ? cj + 1 : cj) : cj; /* fine face */
+              double bface = dir == 0 ? AT(finerOp->bX, fb, fi, fj, 0) : AT(finerOp->bY, fb, fi, fj, 0);
+              double phihi = side ? AT(phiFine, fb, gi, gj, 0) : AT(phiFine, fb, ci, cj, 0);
+              double philo = side ? AT(phiFine, fb, ci, cj, 0) : AT(phiFine, fb, gi, gj, 0);
+              double F = face_flux(bface, phihi, philo, op->beta * r / op->dx[dir]);
+              piece = piece + sf * F;
+            }
+            reg = reg + piece;
+          }
+        AT(residual, b, i, j, 0) = AT(residual, b, i, j, 0) + (-scale2) * reg;
+      }
+  }
+}
+
+/* AMROperator / NC / NF (src/AMRNonLinearPoissonOp.cpp:942-1008): phiFine/finerOp and phiCoarse may be NULL */
+void orc_op_amr_operator(orc_op* op, orc_field* LofPhi, orc_field* phiFine, orc_field* phi, const orc_field* phiCoarse,
+                         int homogeneous, orc_op* finerOp) {
+  if (phiCoarse) orc_cf_interp(phi, phiCoarse, op->ref_to_coarser, op->dx[0]);
+  orc_op_apply(op, LofPhi, phi, homogeneous);
+  if (phiFine) orc_op_reflux(op, phiFine, phi, LofPhi, finerOp);
+}
+/* AMRResidual / NC / NF (:889-939): residual = rhs - AMROperator; NF goes through residualI */
+void orc_op_amr_residual(orc_op* op, orc_field* residual, orc_field* phiFine, orc_field* phi, const orc_field* phiCoarse,
+                         const orc_field* rhs, int homogeneous, orc_op* finerOp) {
+  if (!phiFine) {
+    if (phiCoarse) { orc_op_residual_nf(op, residual, phi, phiCoarse, rhs); return; }   /* AMRResidualNF */
+  }
+  orc_op_amr_operator(op, residual, phiFine, phi, phiCoarse, homogeneous, finerOp);
+  orc_axby(residual, residual, rhs, -1.0, 1.0);
+}
+
+/* AMRRestrictS (src/AMRNonLinearPoissonOp.cpp:1027-1069) + FORT_AVERAGE (absent Chombo AMRPoissonOpF.ChF:
+   coarse = sum of the r*r fine cells (i fastest) * (1/r^2)).  resCoarse lives on the COARSENED FINE layout. */
+void orc_op_amr_restrict_s(orc_op* op, orc_field* resCoarse, const orc_field* residual, orc_field* correction,
+                           const orc_field* coarseCorrection, orc_field* scratch, int skip_res) {
+  const int r = op->ref_to_coarser;
+  if (!skip_res) orc_op_residual_nf(op, scratch, correction, coarseCorrection, residual);
+  else {
+    /* assignLocal: whole arrays when shapes agree, else the valid region */
+    for (int b = 0; b < scratch->lay->nbox; b++) {
+      obox rr = box_and(scratch->ab[b], residual->ab[b]);
+      for (int j = rr.lo[1]; j <= rr.hi[1]; j++)
+        for (int i = rr.lo[0]; i <= rr.hi[0]; i++) AT(scratch, b, i, j, 0) = AT(residual, b, i, j, 0);
+    }
+  }
+#pragma omp parallel for schedule(static)
+  for (int b = 0; b < resCoarse->lay->nbox; b++) {
+    obox v = resCoarse->lay->box[b];
+    double refScale = 1.0 / (double)(r * r);
+    for (int jc = v.lo[1]; jc <= v.hi[1]; jc++)
+      for (int ic = v.lo[0]; ic <= v.hi[0]; ic++) {
+        double coarseSum = 0.0;
+        for (int jj = 0; jj < r; jj++)
+          for (int ii = 0; ii < r; ii++) coarseSum = coarseSum + AT(scratch, b, ic * r + ii, jc * r + jj, 0);
+        AT(resCoarse, b, ic, jc, 0) = coarseSum * refScale;
+      }
+  }
+}
+
+/* AMRProlongS (src/AMRNonLinearPoissonOp.cpp:1105-1139): temp (coarsened fine layout) <- coarse; PROLONGNL */
+void orc_op_amr_prolong_s(orc_op* op, orc_field* correction, const orc_field* coarseCorrection, orc_field* temp) {
+  const int r = op->ref_to_coarser;
+  orc_copy_to(temp, coarseCorrection, 0);
+#pragma omp parallel for schedule(static)
+  for (int b = 0; b < correction->lay->nbox; b++) {
+    obox v = correction->lay->box[b];
+    for (int j = v.lo[1]; j <= v.hi[1]; j++)
+      for (int i = v.lo[0]; i <= v.hi[0]; i++)
+        AT(correction, b, i, j, 0) = AT(correction, b, i, j, 0) + AT(temp, b, fdiv(i, r), fdiv(j, r), 0);
+  }
+}
+/* AMRProlongS_2 (src/AMRNonLinearPoissonOp.cpp:1141-1206) + PROLONG_2_NL (src/AMRNonLinearPoissonOpF.ChF:646-709):
+   temp (coarsened fine layout, 1 ghost) <- coarse (ghosts too: the copier carries temp's ghost vector); coarse-level
+   INHOMOGENEOUS BC on temp (m_use_FAS); exchange incl. corners among temp's boxes; weights 9/16, 3/16, 3/16, 1/16. */
+void orc_op_amr_prolong_s2(orc_op* op, orc_field* correction, const orc_field* coarseCorrection, orc_field* temp,
+                           const orc_op* crseOp) {
+  const int r = op->ref_to_coarser;
+  orc_copy_to(temp, coarseCorrection, 1);
+  orc_apply_bc(temp, &crseOp->bc, crseOp->dx, 0);
+  orc_exchange_full(temp);
+  const double den = 1.0 / 16.0;
+  const double fx1 = 3.0 * den, fx2 = 3.0 * 3.0 * den, f0 = 1.0 * den;
+#pragma omp parallel for schedule(static)
+  for (int b = 0; b < correction->lay->nbox; b++) {
+    obox v = correction->lay->box[b];
+    for (int j = v.lo[1]; j <= v.hi[1]; j++)
+      for (int i = v.lo[0]; i <= v.hi[0]; i++) {
+        int ic = fdiv(i, r), jc = fdiv(j, r);
+        int o1 = 2 * (((i % 2) + 2) % 2) - 1, o2 = 2 * (((j % 2) + 2) % 2) - 1;
+        double p = AT(correction, b, i, j, 0);
+        p = p + fx2 * AT(temp, b, ic, jc, 0) + f0 * AT(temp, b, ic + o1, jc + o2, 0);
+        p = p + fx1 * (AT(temp, b, ic + o1, jc, 0) + AT(temp, b, ic, jc + o2, 0));
+        AT(correction, b, i, j, 0) = p;
+      }
+  }
+}
+
+/* zeroCovered / AMRNorm (src/AMRNonLinearPoissonOp.cpp:1222-1264): coarse cells under the fine level set to 0 */
+void orc_zero_covered(orc_field* crse, const orc_layout* fineLay, int r) {
+  orc_layout* Lf = (orc_layout*)fineLay;
+  cover_build(Lf);
+#pragma omp parallel for schedule(static)
+  for (int b = 0; b < crse->lay->nbox; b++) {
+    obox a = crse->ab[b]; /* overlayBox = coarTempFAB.box() & coarsenedGrid: ghost cells included */
+    for (int c = 0; c < crse->ncomp; c++)
+      for (int j = a.lo[1]; j <= a.hi[1]; j++)
+        for (int i = a.lo[0]; i <= a.hi[0]; i++) {
+          if (i * r < Lf->domain.lo[0] || i * r > Lf->domain.hi[0] || j * r < Lf->domain.lo[1] || j * r > Lf->domain.hi[1]) continue;
+          if (cover_at(Lf, i * r, j * r, NULL, NULL) >= 0) AT(crse, b, i, j, c) = 0.0;
+        }
+  }
+}
+double orc_op_amr_norm(const orc_field* coarResid, const orc_layout* fineLay, int r, int ord) {
+  orc_field* tmp = orc_field_create(coarResid->lay, coarResid->ncomp, coarResid->ng, coarResid->cent);
+  orc_field_copy(tmp, coarResid);
+  if (fineLay) orc_zero_covered(tmp, fineLay, r);
+  double n = orc_norm(tmp, ord);
+  orc_field_free(tmp);
+  return n;
+}
+
+/* UpdateOperator with a coarser level (src/VCAMRNonLinearPoissonOp.cpp:34-64, WFlx_level src/AmrHydro.cpp:1415-1539):
+   as orc_op_update_operator, plus the coarse gradient (dx*2), its exchange + ExtrapGhostCells, and QuadCFInterp of the
+   two gradient components into the fine CF ghost cells before the fine exchange/extrapolation. */
+void orc_op_update_operator_amr(orc_op* op, orc_field* phi, orc_field* phiCoarse, const orc_field* maskCoarse) {
+  const orc_layout* L = op->lay;
+  orc_exchange_faces(phi);
+  orc_apply_bc(phi, &op->bc, op->dx, 0);
+  orc_field* gx = orc_field_create(L, 1, 1, ORC_XFACE);
+  orc_field* gy = orc_field_create(L, 1, 1, ORC_YFACE);
+  orc_field* gradH = orc_field_create(L, 2, phi->ng, ORC_CELL);
+  orc_mac_gradient(phi, op->prm.use_mask_grad ? op->mask : NULL, op->dx, gx, gy);
+  orc_edge_to_cell(gx, gy, gradH);
+  if (phiCoarse) {
+    const orc_layout* Lc = phiCoarse->lay;
+    double dxc[2] = {op->dx[0] * 2, op->dx[1] * 2};
+    orc_field* cgx = orc_field_create(Lc, 1, 1, ORC_XFACE);
+    orc_field* cgy = orc_field_create(Lc, 1, 1, ORC_YFACE);
+    orc_field* gradC = orc_field_create(Lc, 2, phiCoarse->ng, ORC_CELL);
+    orc_mac_gradient(phiCoarse, op->prm.use_mask_grad ? maskCoarse : NULL, dxc, cgx, cgy);
+    orc_edge_to_cell(cgx, cgy, gradC);
+    orc_exchange_full(gradC);
+    orc_extrap_ghost(gradC);
+    orc_cf_interp(gradH, gradC, 2, op->dx[0]);
+    orc_field_free(cgx); orc_field_free(cgy); orc_field_free(gradC);
+  }
+  orc_exchange_full(gradH);
+  orc_extrap_ghost(gradH);
+  orc_field* Re = orc_field_create(L, 1, phi->ng, ORC_CELL);
+  orc_compute_re(&op->prm, op->B, gradH, Re);
+  orc_field* Bx = orc_field_create(L, 1, 0, ORC_XFACE);
+  orc_field* By = orc_field_create(L, 1, 0, ORC_YFACE);
+  orc_field* Rx = orc_field_create(L, 1, 0, ORC_XFACE);
+  orc_field* Ry = orc_field_create(L, 1, 0, ORC_YFACE);
+  orc_field* Mx = orc_field_create(L, 1, 0, ORC_XFACE);
+  orc_field* My = orc_field_create(L, 1, 0, ORC_YFACE);
+  orc_cell_to_edge(Re, Rx, Ry);
+  orc_cell_to_edge(op->B, Bx, By);
+  orc_icemask_ec(op->mask, Mx, My);
+#pragma omp parallel for schedule(static)
+  for (int b = 0; b < L->nbox; b++) {
+    obox v = L->box[b];
+    for (int j = v.lo[1]; j <= v.hi[1]; j++)
+      for (int i = v.lo[0]; i <= v.hi[0] + 1; i++)
+        AT(op->bX, b, i, j, 0) = bcoeff(&op->prm, AT(Bx, b, i, j, 0), AT(Rx, b, i, j, 0), AT(Mx, b, i, j, 0));
+    for (int j = v.lo[1]; j <= v.hi[1] + 1; j++)
+      for (int i = v.lo[0]; i <= v.hi[0]; i++)
+        AT(op->bY, b, i, j, 0) = bcoeff(&op->prm, AT(By, b, i, j, 0), AT(Ry, b, i, j, 0), AT(My, b, i, j, 0));
+  }
+  orc_field_free(gx); orc_field_free(gy); orc_field_free(gradH); orc_field_free(Re);
+  orc_field_free(Bx); orc_field_free(By); orc_field_free(Rx); orc_field_free(Ry); orc_field_free(Mx); orc_field_free(My);
+  op->lambda_dirty = 1;
+  orc_op_reset_lambda(op);
+}
+
+/* ------------------------------------------------------------------------------------------- */
+/* AMRFASMultiGrid over several levels (absent fork; the cycle is INFERRED)      */
+/* ------------------------------------------------------------------------------------------- */
+#define ORC_MAXLEV 8
+struct orc_amr_solver {
+  int nlev;
+  orc_layout* lay[ORC_MAXLEV];      /* borrowed */
+  orc_layout* clay[ORC_MAXLEV];     /* coarsened fine layouts (levels >= 1), owned */
+  orc_op* op[ORC_MAXLEV];           /* AMR level ops; op[0] belongs to mg0 */
+  orc_solver* mg0;                  /* MG hierarchy below the base level */
+  orc_field *resid[ORC_MAXLEV], *corr[ORC_MAXLEV], *tmp[ORC_MAXLEV], *scratch[ORC_MAXLEV];
+  orc_field *resC[ORC_MAXLEV];      /* coarsened-fine, 1 ghost: m_resC, also AMRProlongS_2's temp */
+  orc_field* mask[ORC_MAXLEV];
+  int update_operator;
+};
+typedef struct orc_amr_solver orc_amr_solver;
+
+orc_amr_solver* orc_amr_solver_create(int nlev, orc_layout* const* lay, const double dx0[2], double alpha, double beta,
+                                      const orc_bc* bc, const orc_params* prm, orc_field* const* aCoef,
+                                      orc_field* const* bX, orc_field* const* bY, orc_field* const* B,
+                                      orc_field* const* Pi, orc_field* const* zb, orc_field* const* mask) {
+  orc_amr_solver* s = (orc_amr_solver*)calloc(1, sizeof(orc_amr_solver));
+  s->nlev = nlev;
+  s->update_operator = prm->bcoeff_otf;
+  double dx[2] = {dx0[0], dx0[1]};
+  for (int l = 0; l < nlev; l++) {
+    s->lay[l] = lay[l];
+    s->mask[l] = mask[l];
+    if (l == 0) {
+      s->mg0 = orc_solver_create(lay[0], dx, alpha, beta, bc, prm, aCoef[0], bX[0], bY[0], B[0], Pi[0], zb[0], mask[0]);
+      s->op[0] = s->mg0->op[0];
+    } else {
+      s->op[l] = orc_op_create(lay[l], dx, alpha, beta, bc, prm, aCoef[l], bX[l], bY[l], B[l], Pi[l], zb[l], mask[l]);
+      s->clay[l] = orc_layout_coarsen(lay[l], 2);
+      s->resC[l] = orc_field_create(s->clay[l], 1, 1, ORC_CELL);
+    }
+    s->resid[l] = orc_field_create(lay[l], 1, 0, ORC_CELL);
+    s->corr[l] = orc_field_create(lay[l], 1, 1, ORC_CELL);
+    s->tmp[l] = orc_field_create(lay[l], 1, 0, ORC_CELL);
+    s->scratch[l] = orc_field_create(lay[l], 1, 1, ORC_CELL);
+    dx[0] /= 2; dx[1] /= 2;
+  }
+  return s;
+}
+void orc_amr_solver_free(orc_amr_solver* s) {
+  if (!s) return;
+  for (int l = 0; l < s->nlev; l++) {
+    if (l > 0) { orc_op_free(s->op[l]); orc_field_free(s->resC[l]); orc_layout_free(s->clay[l]); }
+    orc_field_free(s->resid[l]); orc_field_free(s->corr[l]); orc_field_free(s->tmp[l]); orc_field_free(s->scratch[l]);
+  }
+  orc_solver_free(s->mg0);
+  free(s);
+}
+orc_op* orc_amr_solver_op(orc_amr_solver* s, int lev) { return s->op[lev]; }
+orc_solver* orc_amr_solver_mg0(orc_amr_solver* s) { return s->mg0; }
+
+/* AMRMultiGrid::computeAMRResidualLevel: residual[l] = rhs[l] - L_composite(phi) */
+static void amr_residual_level(orc_amr_solver* s, orc_field* const* phi, orc_field* const* rhs, int l, int l_max) {
+  orc_field* fine = l < l_max ? phi[l + 1] : NULL;
+  orc_field* crse = l > 0 ? phi[l - 1] : NULL;
+  orc_op_amr_residual(s->op[l], s->resid[l], fine, phi[l], crse, rhs[l], 0, fine ? s->op[l + 1] : NULL);
+}
+
+/* AMRFASMultiGrid::VCycle(ilev) -- INFERRED:
+     UpdateOperator on entry to every AMR level; base level = MultiGrid FAS cycle on residual[0];
+     finer levels: pre-relax, restrict the solution (AMRRestrictS skip_res), save it, composite residual on the coarser
+     level, overwrite its covered part with the averaged fine residual (AMRRestrictS), add L_NF(phi_coarse) (FAS
+     right-hand side: the operator WITHOUT refluxing, i.e. the one relaxNF smooths with), recurse, prolong the change
+     of the coarse solution with AMRProlongS_2, post-relax. */
+static void amr_vcycle(orc_amr_solver* s, orc_field* const* phi, orc_field* const* rhs, int ilev, int l_max,
+                       const orc_solver_params* sp) {
+  orc_op* op = s->op[ilev];
+  if (s->update_operator) {
+    if (ilev > 0) orc_op_update_operator_amr(op, phi[ilev], phi[ilev - 1], s->mask[ilev - 1]);
+    else orc_op_update_operator(op, phi[0]);
+  }
+  if (ilev == 0) {
+    mg_cycle(s->mg0, 0, phi[0], s->resid[0], sp);
+    return;
+  }
+  orc_op* opc = s->op[ilev - 1];
+  orc_op_relax_nf(op, phi[ilev], phi[ilev - 1], s->resid[ilev], sp->pre);
+  /* phi[ilev-1] <- average of phi[ilev] on the covered region */
+  orc_op_amr_restrict_s(op, s->resC[ilev], phi[ilev], phi[ilev], phi[ilev - 1], s->scratch[ilev], 1);
+  orc_copy_to(phi[ilev - 1], s->resC[ilev], 0);
+  orc_field_copy(s->corr[ilev - 1], phi[ilev - 1]); /* assignLocal */
+  amr_residual_level(s, phi, rhs, ilev - 1, l_max);
+  orc_op_amr_restrict_s(op, s->resC[ilev], s->resid[ilev], phi[ilev], phi[ilev - 1], s->scratch[ilev], 0);
+  orc_copy_to(s->resid[ilev - 1], s->resC[ilev], 0);
+  orc_op_amr_operator(opc, s->tmp[ilev - 1], NULL, phi[ilev - 1], ilev - 1 > 0 ? phi[ilev - 2] : NULL, 0, NULL);
+  orc_incr(s->resid[ilev - 1], s->tmp[ilev - 1], 1.0);
+  amr_vcycle(s, phi, rhs, ilev - 1, l_max, sp);
+  orc_axby(s->corr[ilev - 1], phi[ilev - 1], s->corr[ilev - 1], 1.0, -1.0);
+  orc_op_amr_prolong_s2(op, phi[ilev], s->corr[ilev - 1], s->resC[ilev], opc);
+  orc_op_relax_nf(op, phi[ilev], phi[ilev - 1], s->resid[ilev], sp->post);
+}
+void orc_amr_solver_vcycle(orc_amr_solver* s, orc_field* const* phi, orc_field* const* rhs, int l_max,
+                           const orc_solver_params* sp) {
+  orc_assign(s->resid[l_max], rhs[l_max]);
+  amr_vcycle(s, phi, rhs, l_max, l_max, sp);
+}
+/* AMRMultiGrid::computeAMRResidual: composite residual on every level, covered cells zeroed, max over levels */
+double orc_amr_solver_resnorm(orc_amr_solver* s, orc_field* const* phi, orc_field* const* rhs, int l_max) {
+  double n = 0.0;
+  for (int l = l_max; l >= 0; l--) {
+    amr_residual_level(s, phi, rhs, l, l_max);
+    if (l < l_max) orc_zero_covered(s->resid[l], s->lay[l + 1], 2);
+    double nl = orc_norm(s->resid[l], 0);
+    if (nl > n) n = nl;
+  }
+  return n;
+}
+orc_field* orc_amr_solver_residual(orc_amr_solver* s, int lev) { return s->resid[lev]; }
+
+int orc_amr_solver_solve(orc_amr_solver* s, orc_field* const* phi, orc_field* const* rhs, int l_max,
+                         const orc_solver_params* sp, double* resnorm) {
+  double initial_rnorm = orc_amr_solver_resnorm(s, phi, rhs, l_max);
+  double rnorm = initial_rnorm, norm_last = 2 * initial_rnorm;
+  int iter = 0;
+  if (resnorm) resnorm[0] = initial_rnorm;
+  if (sp->fixed_cycles > 0) {
+    for (iter = 0; iter < sp->fixed_cycles; iter++) {
+      orc_amr_solver_vcycle(s, phi, rhs, l_max, sp);
+      rnorm = orc_amr_solver_resnorm(s, phi, rhs, l_max);
+      if (resnorm) resnorm[iter + 1] = rnorm;
+    }
+    return iter;
+  }
+  int goNorm = rnorm > sp->norm_thresh, goRedu = rnorm > sp->eps * initial_rnorm, goIter = iter < sp->max_iter;
+  int goHang = iter < sp->imin || rnorm < (1 - sp->hang) * norm_last, goMin = iter < sp->iter_min;
+  while (goMin || (goIter && goRedu && goHang && goNorm)) {
+    norm_last = rnorm;
+    orc_amr_solver_vcycle(s, phi, rhs, l_max, sp);
+    iter++;
+    rnorm = orc_amr_solver_resnorm(s, phi, rhs, l_max);
+    if (resnorm) resnorm[iter] = rnorm;
+    goNorm = rnorm > sp->norm_thresh; goRedu = rnorm > sp->eps * initial_rnorm; goIter = iter < sp->max_iter;
+    goHang = iter < sp->imin || rnorm < (1 - sp->hang) * norm_last; goMin = iter < sp->iter_min;
+  }
+  return iter;
+}
+double orc_amr_solver_cell_updates(const orc_amr_solver* s, const orc_solver_params* sp, int l_max) {
+  double n = orc_solver_cell_updates(s->mg0, sp);
+  for (int l = 1; l <= l_max; l++) n += layout_cells(s->lay[l]) * (sp->pre + sp->post);
+  return n;
 }

@@ -133,6 +133,42 @@ void orc_solver_vcycle(orc_solver* s, orc_field* phi, const orc_field* rhs, cons
 /* cell-updates performed by one V-cycle (SURVEY.md 8d metric) */
 double orc_solver_cell_updates(const orc_solver* s, const orc_solver_params* sp);
 
+/* ---- AMR (two-level machinery + multi-level FAS V-cycle); r = 2 ---- */
+typedef struct orc_amr_solver orc_amr_solver;
+void orc_copy_to(orc_field* dst, const orc_field* src, int with_ghosts);           /* LevelData::copyTo */
+void orc_cf_interp(orc_field* phiFine, const orc_field* phiCoarse, int r, double dxFine); /* QuadCFInterp */
+void orc_op_set_ref_to_coarser(orc_op* op, int r);
+void orc_op_relax_nf(orc_op* op, orc_field* phi, const orc_field* phiCoarse, const orc_field* rhs, int iterations);
+void orc_op_residual_nf(orc_op* op, orc_field* res, orc_field* phi, const orc_field* phiCoarse, const orc_field* rhs);
+void orc_op_reflux(orc_op* op, orc_field* phiFine, orc_field* phi, orc_field* residual, orc_op* finerOp);
+void orc_op_amr_operator(orc_op* op, orc_field* LofPhi, orc_field* phiFine, orc_field* phi, const orc_field* phiCoarse,
+                         int homogeneous, orc_op* finerOp);
+void orc_op_amr_residual(orc_op* op, orc_field* residual, orc_field* phiFine, orc_field* phi, const orc_field* phiCoarse,
+                         const orc_field* rhs, int homogeneous, orc_op* finerOp);
+void orc_op_amr_restrict_s(orc_op* op, orc_field* resCoarse, const orc_field* residual, orc_field* correction,
+                           const orc_field* coarseCorrection, orc_field* scratch, int skip_res);
+void orc_op_amr_prolong_s(orc_op* op, orc_field* correction, const orc_field* coarseCorrection, orc_field* temp);
+void orc_op_amr_prolong_s2(orc_op* op, orc_field* correction, const orc_field* coarseCorrection, orc_field* temp,
+                           const orc_op* crseOp);
+void orc_zero_covered(orc_field* crse, const orc_layout* fineLay, int r);
+double orc_op_amr_norm(const orc_field* coarResid, const orc_layout* fineLay, int r, int ord);
+void orc_op_update_operator_amr(orc_op* op, orc_field* phi, orc_field* phiCoarse, const orc_field* maskCoarse);
+
+orc_amr_solver* orc_amr_solver_create(int nlev, orc_layout* const* lay, const double dx0[2], double alpha, double beta,
+                                      const orc_bc* bc, const orc_params* prm, orc_field* const* aCoef,
+                                      orc_field* const* bX, orc_field* const* bY, orc_field* const* B,
+                                      orc_field* const* Pi, orc_field* const* zb, orc_field* const* mask);
+void orc_amr_solver_free(orc_amr_solver* s);
+orc_op* orc_amr_solver_op(orc_amr_solver* s, int lev);
+orc_solver* orc_amr_solver_mg0(orc_amr_solver* s);
+orc_field* orc_amr_solver_residual(orc_amr_solver* s, int lev);
+void orc_amr_solver_vcycle(orc_amr_solver* s, orc_field* const* phi, orc_field* const* rhs, int l_max,
+                           const orc_solver_params* sp);
+double orc_amr_solver_resnorm(orc_amr_solver* s, orc_field* const* phi, orc_field* const* rhs, int l_max);
+int orc_amr_solver_solve(orc_amr_solver* s, orc_field* const* phi, orc_field* const* rhs, int l_max,
+                         const orc_solver_params* sp, double* resnorm);
+double orc_amr_solver_cell_updates(const orc_amr_solver* s, const orc_solver_params* sp, int l_max);
+
 void orc_set_threads(int n);
 
 #ifdef __cplusplus
