@@ -271,7 +271,7 @@ extern "C" int sg_set_tuning(sg_ctx* c, int key, int value) {
   return SG_OK;
 }
 extern "C" int sg_set_relax_mode(sg_ctx* c, int mode) {
-  REQUIRE(c && (mode == 0 || mode == 1), "sg_set_relax_mode");
+  REQUIRE(c && mode >= 0 && mode <= 2, "sg_set_relax_mode");
   c->relax_mode = mode;
   return SG_OK;
 }
@@ -937,7 +937,8 @@ static int relax_impl(sg_op* op, sg_field* phi, const sg_field* rhs, int iterati
   if (!L->has_local || iterations <= 0) return SG_OK;
   OpArgs a = make_args(op);
   bool ghosts = has_ghost_sides(L);
-  if (c->relax_mode == 1) {
+  if (c->relax_mode >= 1) {
+    const bool stream = c->relax_mode == 1;
     sg_field* scratch;
     SGCALL(ws_field(L, 0, 1, &scratch));
     if (ghosts) SGCALL(fill_ghosts(const_cast<sg_field*>(rhs), 1));
@@ -946,14 +947,18 @@ static int relax_impl(sg_op* op, sg_field* phi, const sg_field* rhs, int iterati
     f.rhs = rhs->p();
     f.sdx[0] = -op->dx[0]; f.sdx[1] = op->dx[0]; f.sdx[2] = -op->dx[1]; f.sdx[3] = op->dx[1];
     f.nstrips = (L->nx + FUSED_COLS - 1) / FUSED_COLS;
-    // Segments of rows per warp.  Every warp does the same amount of work, so a partly filled last wave costs
-    // as much as a full one: either fit the whole sweep into ONE resident wave (large levels: warps <= SMs x
-    // resident warps), or cut it into many short segments so that the tail is a small fraction (never between).
-    int minb = c->tune[1] == 3 ? 3 : 4;
+    // Segments of rows per warp.  Measured on B200 (tools/relax_bench.py): many short segments beat one resident wave
+    // (warps marching in lock-step), 32-64 rows per warp is the plateau on HBM-sized levels, and L2-resident levels want
+    // the shortest segments that still amortise the 4 load-only steps of a segment.
+    int minb = stream ? 3 : (c->tune[1] == 3 ? 3 : 4);
     int capacity = c->num_sms * minb * 4; // resident warps (128-thread CTAs)
     int nsegs;
     if (c->tune[0] > 0) nsegs = (L->ny + c->tune[0] - 1) / c->tune[0];
-    else if (f.nstrips * ((L->ny + 63) / 64) <= capacity) nsegs = std::max(1, std::min((L->ny + 31) / 32, capacity / f.nstrips));
+    else if (stream) {
+      long long rows = ((long long)f.nstrips * L->ny) / (4LL * capacity);
+      rows = std::max(8LL, std::min(48LL, rows));
+      nsegs = (int)((L->ny + rows - 1) / rows);
+    } else if (f.nstrips * ((L->ny + 63) / 64) <= capacity) nsegs = std::max(1, std::min((L->ny + 31) / 32, capacity / f.nstrips));
     else {
       nsegs = capacity / f.nstrips;               // one full wave ...
       if (nsegs < 1 || L->ny / nsegs > 1024) nsegs = (L->ny + 63) / 64; // ... unless segments get too long: many waves
@@ -966,7 +971,18 @@ static int relax_impl(sg_op* op, sg_field* phi, const sg_field* rhs, int iterati
       if (ghosts) SGCALL(fill_ghosts(phi, 2));
       f.phi_in = phi->p();
       f.phi_out = scratch->p();
-      if (a.has_a) LAUNCH(c, (k_gsrb_fused<1, 4>), blocks, 128, f);
+      if (stream) {
+        // 4 warps x GS_STAGES row bundles x (8|9) arrays x 32 lanes x 16 B of warp-private staging rings
+        static bool attr_set = false;
+        if (!attr_set) {
+          CK(cudaFuncSetAttribute(k_gsrb_stream<0, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 * GS_STAGES * 8 * 512));
+          CK(cudaFuncSetAttribute(k_gsrb_stream<1, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 * GS_STAGES * 9 * 512));
+          attr_set = true;
+        }
+        if (a.has_a) { k_gsrb_stream<1, 3><<<blocks, 128, 4 * GS_STAGES * 9 * 512, c->stream>>>(f); c->launches++; }
+        else { k_gsrb_stream<0, 3><<<blocks, 128, 4 * GS_STAGES * 8 * 512, c->stream>>>(f); c->launches++; }
+      }
+      else if (a.has_a) LAUNCH(c, (k_gsrb_fused<1, 4>), blocks, 128, f);
       else if (minb == 3) LAUNCH(c, (k_gsrb_fused<0, 3>), blocks, 128, f);
       else LAUNCH(c, (k_gsrb_fused<0, 4>), blocks, 128, f);
       std::swap(phi->base, scratch->base); // out-of-place sweep: the field now owns the new buffer

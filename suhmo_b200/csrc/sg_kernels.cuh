@@ -382,6 +382,161 @@ __global__ void __launch_bounds__(128, MINB) k_gsrb_fused(FusedArgs f) {
 }
 
 // ------------------------------------------------------------------------------------------------
+// streaming red+black GSRB sweep, second generation (the default smoother): same arithmetic and the same
+// warp-autonomous strip/ring scheme as k_gsrb_fused, but
+//  * every row of every array is staged into a warp-private shared-memory ring with cp.async (LDGSTS), GS_D
+//    row bundles ahead of its use, so HBM latency is hidden by bytes in flight rather than by occupancy;
+//  * bundle q carries exactly what step q uses first: phi and the y-face coefficient of row q+2, and the
+//    cell coefficients / x-face coefficient of row q+1; everything older lives in registers;
+//  * the colour of a lane's two columns is warp-uniform per row, so the two point updates of a step are
+//    compiled for a fixed column (no per-lane selects), out-of-range lanes compute and simply do not commit.
+// Step q:  RED update of row q+1, then BLACK update of row q, then row q is stored.
+// ------------------------------------------------------------------------------------------------
+#define GS_COLS 60
+#define GS_D 3
+#define GS_STAGES (GS_D + 1)
+
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
+  unsigned s = (unsigned)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(s), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory"); }
+
+struct GsRow { double2 rhs, B, Pi, zb, mk, bx, ac; };
+struct GsBC { // physical-boundary data of the patch, warp-uniform
+  int kxlo, kxhi, kylo, kyhi, nx, ny;
+  double v0, v1, v2, v3, s0, s1, s2, s3;
+  bool xany;
+};
+
+// point update of column K (0/1) of the lane's pair in row j.  pc2/ps2/pn2: phi of rows j, j-1, j+1;
+// bys2/byn2: y-face coefficients below / above row j.  All lanes must call (shuffles).
+template <int K, int HAS_A>
+__device__ __forceinline__ double gs_update(const OpArgs& a, const GsBC& bc, int j, int x, const GsRow& c, double2 pc2, double2 ps2,
+                                            double2 pn2, double2 bys2, double2 byn2) {
+  double pc, pw, pe, bw, be;
+  if (K == 0) {
+    pc = pc2.x; pe = pc2.y; pw = __shfl_up_sync(0xffffffffu, pc2.y, 1);
+    bw = c.bx.x; be = c.bx.y;
+  } else {
+    pc = pc2.y; pw = pc2.x; pe = __shfl_down_sync(0xffffffffu, pc2.x, 1);
+    bw = c.bx.y; be = __shfl_down_sync(0xffffffffu, c.bx.x, 1);
+  }
+  double ps = K ? ps2.y : ps2.x, pn = K ? pn2.y : pn2.x;
+  const double bs = K ? bys2.y : bys2.x, bn = K ? byn2.y : byn2.x;
+  // physical-boundary neighbours: ghost = BC(first interior cell) = BC(this cell), evaluated on the fly
+  if (bc.xany) {
+    if (x == 0 && bc.kxlo <= SK_PHYS_NEUM) pw = bc_ghost_value(bc.kxlo, pc, bc.v0, bc.s0);
+    if (x == bc.nx - 1 && bc.kxhi <= SK_PHYS_NEUM) pe = bc_ghost_value(bc.kxhi, pc, bc.v1, bc.s1);
+  }
+  if (j == 0 && bc.kylo <= SK_PHYS_NEUM) ps = bc_ghost_value(bc.kylo, pc, bc.v2, bc.s2);
+  if (j == bc.ny - 1 && bc.kyhi <= SK_PHYS_NEUM) pn = bc_ghost_value(bc.kyhi, pc, bc.v3, bc.s3);
+  const double ac = HAS_A ? (K ? c.ac.y : c.ac.x) : 0.0;
+  double nl, dnl;
+  nl_terms(a.prm, pc, K ? c.B.y : c.B.x, K ? c.mk.y : c.mk.x, K ? c.Pi.y : c.Pi.x, K ? c.zb.y : c.zb.x, nl, dnl);
+  const double lof = lofphi_cell(a.alpha, ac, a.beta, pc, pw, pe, ps, pn, bw, be, bs, bn, a.dxi0, a.dxi1, nl);
+  const double lam = lambda_cell(a.alpha, ac, a.beta, bw, be, bs, bn, a.dxi0, a.dxi1);
+  const double denom = 1.0e-16 + lam + dnl;
+  return pc + ((K ? c.rhs.y : c.rhs.x) - lof) / denom;
+}
+
+template <int HAS_A, int MINB>
+__global__ void __launch_bounds__(128, MINB) k_gsrb_stream(FusedArgs f) {
+  extern __shared__ double2 gs_smem[];
+  constexpr int NARR = 8 + HAS_A;
+  const OpArgs& a = f.a;
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  const int warp = blockIdx.x * 4 + wib;
+  if (warp >= f.nstrips * f.nsegs) return;
+  const int strip = warp % f.nstrips, seg = warp / f.nstrips;
+  const int nx = a.g.nx, ny = a.g.ny;
+  const ptrdiff_t P = a.g.pitch;
+  const int x0 = strip * GS_COLS - 2 + 2 * lane; // columns x0, x0+1 (x0 even)
+  const int r0 = seg * f.rows_per_warp;
+  const int r1 = min(ny, r0 + f.rows_per_warp);
+  GsBC bc;
+  bc.kxlo = a.g.kind[0]; bc.kxhi = a.g.kind[1]; bc.kylo = a.g.kind[2]; bc.kyhi = a.g.kind[3];
+  bc.nx = nx; bc.ny = ny;
+  bc.v0 = a.g.bcval[0]; bc.v1 = a.g.bcval[1]; bc.v2 = a.g.bcval[2]; bc.v3 = a.g.bcval[3];
+  bc.s0 = f.sdx[0]; bc.s1 = f.sdx[1]; bc.s2 = f.sdx[2]; bc.s3 = f.sdx[3];
+  bc.xany = (strip == 0 && bc.kxlo <= SK_PHYS_NEUM) || (strip * GS_COLS + GS_COLS + 1 >= nx - 1 && bc.kxhi <= SK_PHYS_NEUM);
+  // which cells of this lane may be updated at all (valid cells, or ring cells on SK_GHOST sides) ...
+  const bool upd0 = (x0 >= 0 && x0 < nx) || (x0 == -1 && bc.kxlo == SK_GHOST) || (x0 == nx && bc.kxhi == SK_GHOST);
+  const bool upd1 = (x0 + 1 >= 0 && x0 + 1 < nx) || (x0 + 1 == -1 && bc.kxlo == SK_GHOST) || (x0 + 1 == nx && bc.kxhi == SK_GHOST);
+  // ... the outermost column of the warp has no neighbour inside the warp and stays as loaded
+  const bool red0 = upd0 && lane != 0, red1 = upd1 && lane != 31;
+  const bool st0 = lane >= 1 && lane <= 30 && x0 >= 0 && x0 < nx; // stored output columns
+  const bool st1 = lane >= 1 && lane <= 30 && x0 + 1 >= 0 && x0 + 1 < nx;
+  const int gpar = (a.g.glo0 + a.g.glo1) & 1; // x0 is even: column x0 of local row j is red iff (gpar + j) even
+
+  double2* ring = gs_smem + (size_t)wib * (GS_STAGES * NARR * 32) + lane;
+  // row-0 addresses of this lane's pair in every array; bundle order: phi, bY (row q+2); rhs, B, Pi, zb, mask, bX[, aC] (row q+1)
+  const double* g0 = f.phi_in + x0; const double* g1 = a.bY + x0;
+  const double* g2 = f.rhs + x0; const double* g3 = a.B + x0; const double* g4 = a.Pi + x0; const double* g5 = a.zb + x0;
+  const double* g6 = a.mask + x0; const double* g7 = a.bX + x0; const double* g8 = HAS_A ? a.aC + x0 : nullptr;
+  auto issue = [&](int q, int stage) {
+    if (q < r1) { // bundles past the last step are never consumed
+      // rows q+2 / q+1 lie inside the allocated rows [-2, ny+3] for every consumed bundle; the two load-only bundles at the
+      // start may name row -3 for the coefficients: clamp (that data is not used)
+      const ptrdiff_t o2 = (ptrdiff_t)(q + 2) * P, o1 = (ptrdiff_t)max(q + 1, -2) * P;
+      double2* s = ring + (size_t)stage * (NARR * 32);
+      cp_async16(s, g0 + o2); cp_async16(s + 32, g1 + o2);
+      cp_async16(s + 64, g2 + o1); cp_async16(s + 96, g3 + o1); cp_async16(s + 128, g4 + o1); cp_async16(s + 160, g5 + o1);
+      cp_async16(s + 192, g6 + o1); cp_async16(s + 224, g7 + o1);
+      if (HAS_A) cp_async16(s + 256, g8 + o1);
+    }
+    cp_async_commit();
+  };
+  auto rowupd = [&](int j) -> bool { return (j >= 0 && j < ny) || (j == -1 && bc.kylo == SK_GHOST) || (j == ny && bc.kyhi == SK_GHOST); };
+
+  const double2 z2 = make_double2(0.0, 0.0);
+  double2 pm = z2, p0 = z2, p1 = z2, p2 = z2, by0 = z2, by1 = z2, by2 = z2;
+  GsRow c0, c1;
+  c0.rhs = c0.B = c0.Pi = c0.zb = c0.mk = c0.bx = c0.ac = z2;
+  c1 = c0;
+  const int qstart = r0 - 4;
+#pragma unroll
+  for (int d = 0; d < GS_D; d++) issue(qstart + d, d);
+  int stage = 0;
+  for (int q = qstart; q < r1; q++) {
+    cp_async_wait<GS_D - 1>(); // bundle q has landed (each lane reads back only what it copied itself)
+    pm = p0; p0 = p1; p1 = p2; by0 = by1; by1 = by2; c0 = c1;
+    {
+      const double2* s = ring + (size_t)stage * (NARR * 32);
+      p2 = s[0]; by2 = s[32];
+      c1.rhs = s[64]; c1.B = s[96]; c1.Pi = s[128]; c1.zb = s[160]; c1.mk = s[192]; c1.bx = s[224];
+      if (HAS_A) c1.ac = s[256];
+    }
+    {
+      int st = stage + GS_D; // = the slot of bundle q-1, consumed one step ago
+      if (st >= GS_STAGES) st -= GS_STAGES;
+      issue(q + GS_D, st);
+    }
+    stage = stage + 1 == GS_STAGES ? 0 : stage + 1;
+    // ---- red update of row q+1
+    if (q >= r0 - 2) {
+      const int j = q + 1;
+      if (rowupd(j)) {
+        if ((gpar + j) & 1) { double nv = gs_update<1, HAS_A>(a, bc, j, x0 + 1, c1, p1, p0, p2, by1, by2); if (red1) p1.y = nv; }
+        else { double nv = gs_update<0, HAS_A>(a, bc, j, x0, c1, p1, p0, p2, by1, by2); if (red0) p1.x = nv; }
+      }
+    }
+    // ---- black update of row q, then store
+    if (q >= r0) {
+      const int j = q;
+      if ((gpar + j) & 1) { double nv = gs_update<0, HAS_A>(a, bc, j, x0, c0, p0, pm, p1, by0, by1); if (st0) p0.x = nv; }
+      else { double nv = gs_update<1, HAS_A>(a, bc, j, x0 + 1, c0, p0, pm, p1, by0, by1); if (st1) p0.y = nv; }
+      double* o = f.phi_out + (ptrdiff_t)j * P + x0;
+      if (st0 && st1) *reinterpret_cast<double2*>(o) = p0;
+      else if (st0) o[0] = p0.x;
+      else if (st1) o[1] = p0.y;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
 // applyOp / residual (+ max-norm) : VCNLCOMPUTEOP2D / VCNLCOMPUTERES2D (src/VCAMRNonLinearPoissonOpF.ChF:201-406)
 // MODE 0: out = L(phi);  1: out = rhs - L(phi);  2: as 1 plus max|out| accumulated into *norm_bits
 // ------------------------------------------------------------------------------------------------
