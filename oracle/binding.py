@@ -102,6 +102,30 @@ def lib():
     sig("orc_solver_vcycle", None, vp, vp, vp, C.POINTER(SolverParams), ci)
     sig("orc_solver_cell_updates", cd, vp, C.POINTER(SolverParams))
     sig("orc_set_threads", None, ci)
+    pvp = C.POINTER(C.c_void_p)
+    sig("orc_copy_to", None, vp, vp, ci)
+    sig("orc_cf_interp", None, vp, vp, ci, cd)
+    sig("orc_op_set_ref_to_coarser", None, vp, ci)
+    sig("orc_op_relax_nf", None, vp, vp, vp, vp, ci)
+    sig("orc_op_residual_nf", None, vp, vp, vp, vp, vp)
+    sig("orc_op_reflux", None, vp, vp, vp, vp, vp)
+    sig("orc_op_amr_operator", None, vp, vp, vp, vp, vp, ci, vp)
+    sig("orc_op_amr_residual", None, vp, vp, vp, vp, vp, vp, ci, vp)
+    sig("orc_op_amr_restrict_s", None, vp, vp, vp, vp, vp, vp, ci)
+    sig("orc_op_amr_prolong_s", None, vp, vp, vp, vp)
+    sig("orc_op_amr_prolong_s2", None, vp, vp, vp, vp, vp)
+    sig("orc_zero_covered", None, vp, vp, ci)
+    sig("orc_op_amr_norm", cd, vp, vp, ci, ci)
+    sig("orc_op_update_operator_amr", None, vp, vp, vp, vp)
+    sig("orc_amr_solver_create", vp, ci, pvp, dp, cd, cd, C.POINTER(BC), C.POINTER(Params), pvp, pvp, pvp, pvp, pvp, pvp, pvp)
+    sig("orc_amr_solver_free", None, vp)
+    sig("orc_amr_solver_op", vp, vp, ci)
+    sig("orc_amr_solver_mg0", vp, vp)
+    sig("orc_amr_solver_residual", vp, vp, ci)
+    sig("orc_amr_solver_vcycle", None, vp, pvp, pvp, ci, C.POINTER(SolverParams))
+    sig("orc_amr_solver_resnorm", cd, vp, pvp, pvp, ci)
+    sig("orc_amr_solver_solve", ci, vp, pvp, pvp, ci, C.POINTER(SolverParams), dp)
+    sig("orc_amr_solver_cell_updates", cd, vp, C.POINTER(SolverParams), ci)
     _LIB = L
     return L
 
@@ -209,6 +233,30 @@ def make_solver_params(pre=4, post=4, bottom=16, max_iter=100, imin=0, iter_min=
     return SolverParams(pre, post, bottom, max_iter, imin, iter_min, eps, hang, norm_thresh, fixed_cycles)
 
 
+def _h(x):
+    return None if x is None else x.h
+
+
+def _harr(fs):
+    return (C.c_void_p * len(fs))(*[f.h for f in fs])
+
+
+def cf_interp(phiF, phiC, r, dxFine):
+    lib().orc_cf_interp(phiF.h, phiC.h, r, dxFine)
+
+
+def copy_to(dst, src, with_ghosts=False):
+    lib().orc_copy_to(dst.h, src.h, int(with_ghosts))
+
+
+def zero_covered(crse, fineLayout, r=2):
+    lib().orc_zero_covered(crse.h, fineLayout.h, r)
+
+
+def amr_norm(coarResid, fineLayout, r, ord_):
+    return lib().orc_op_amr_norm(coarResid.h, None if fineLayout is None else fineLayout.h, r, ord_)
+
+
 class Op:
     def __init__(self, layout, dx, alpha, beta, bc, prm, aCoef, bX, bY, B, Pi, zb, mask, _h=None):
         self.layout = layout
@@ -247,6 +295,34 @@ class Op:
     def lambda_field(self):
         return Field(self.layout, 1, 0, CELL, _h=lib().orc_op_lambda(self.h))
 
+    # ---- AMR surface (phiCoarse / phiFine / finerOp may be None) ----
+    def relax_nf(self, phi, phiC, rhs, n):
+        lib().orc_op_relax_nf(self.h, phi.h, _h(phiC), rhs.h, n)
+
+    def residual_nf(self, res, phi, phiC, rhs):
+        lib().orc_op_residual_nf(self.h, res.h, phi.h, _h(phiC), rhs.h)
+
+    def reflux(self, phiFine, phi, residual, finerOp):
+        lib().orc_op_reflux(self.h, phiFine.h, phi.h, residual.h, finerOp.h)
+
+    def amr_operator(self, lof, phiFine, phi, phiC, homogeneous=False, finerOp=None):
+        lib().orc_op_amr_operator(self.h, lof.h, _h(phiFine), phi.h, _h(phiC), int(homogeneous), _h(finerOp))
+
+    def amr_residual(self, res, phiFine, phi, phiC, rhs, homogeneous=False, finerOp=None):
+        lib().orc_op_amr_residual(self.h, res.h, _h(phiFine), phi.h, _h(phiC), rhs.h, int(homogeneous), _h(finerOp))
+
+    def amr_restrict_s(self, resC, residual, correction, coarseCorrection, scratch, skip_res):
+        lib().orc_op_amr_restrict_s(self.h, resC.h, residual.h, correction.h, _h(coarseCorrection), scratch.h, int(skip_res))
+
+    def amr_prolong_s(self, correction, coarseCorrection, temp):
+        lib().orc_op_amr_prolong_s(self.h, correction.h, coarseCorrection.h, temp.h)
+
+    def amr_prolong_s2(self, correction, coarseCorrection, temp, crseOp):
+        lib().orc_op_amr_prolong_s2(self.h, correction.h, coarseCorrection.h, temp.h, crseOp.h)
+
+    def update_operator_amr(self, phi, phiC, maskC):
+        lib().orc_op_update_operator_amr(self.h, phi.h, _h(phiC), _h(maskC))
+
 
 class Solver:
     def __init__(self, layout, dx, alpha, beta, bc, prm, aCoef, bX, bY, B, Pi, zb, mask):
@@ -271,4 +347,41 @@ class Solver:
 
     def free(self):
         lib().orc_solver_free(self.h)
+        self.h = None
+
+
+class AmrSolver:
+    """AMRFASMultiGrid over several levels (fields: lists per level)."""
+
+    def __init__(self, layouts, dx0, alpha, beta, bc, prm, aCoef, bX, bY, B, Pi, zb, mask):
+        self.layouts = layouts
+        self.keep = (bc, prm, aCoef, bX, bY, B, Pi, zb, mask)
+        _, dxp = _da(dx0)
+        self.h = lib().orc_amr_solver_create(len(layouts), _harr(layouts), dxp, alpha, beta, C.byref(bc), C.byref(prm),
+                                             _harr(aCoef), _harr(bX), _harr(bY), _harr(B), _harr(Pi), _harr(zb), _harr(mask))
+
+    def op(self, lev):
+        o = Op(self.layouts[lev], None, 0, 0, None, None, None, None, None, None, None, None, None, _h=lib().orc_amr_solver_op(self.h, lev))
+        return o
+
+    def residual_field(self, lev):
+        return Field(self.layouts[lev], 1, 0, CELL, _h=lib().orc_amr_solver_residual(self.h, lev))
+
+    def resnorm(self, phi, rhs, l_max):
+        return lib().orc_amr_solver_resnorm(self.h, _harr(phi), _harr(rhs), l_max)
+
+    def vcycle(self, phi, rhs, l_max, sp):
+        lib().orc_amr_solver_vcycle(self.h, _harr(phi), _harr(rhs), l_max, C.byref(sp))
+
+    def solve(self, phi, rhs, l_max, sp):
+        n = max(sp.max_iter, sp.fixed_cycles) + 2
+        hist = np.zeros(n)
+        it = lib().orc_amr_solver_solve(self.h, _harr(phi), _harr(rhs), l_max, C.byref(sp), hist.ctypes.data_as(C.POINTER(C.c_double)))
+        return it, hist[:it + 1]
+
+    def cell_updates(self, sp, l_max):
+        return lib().orc_amr_solver_cell_updates(self.h, C.byref(sp), l_max)
+
+    def free(self):
+        lib().orc_amr_solver_free(self.h)
         self.h = None

@@ -103,3 +103,86 @@ def rel_l2(a, b):
     m = ~np.isnan(a) & ~np.isnan(b)
     den = np.sqrt(np.sum(b[m] ** 2))
     return float(np.sqrt(np.sum((a[m] - b[m]) ** 2)) / (den if den > 0 else 1.0))
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# multi-level (AMR) problems: explicit box lists per level (what Chombo reads from AmrHydro.grids_file), ref ratio 2
+# ---------------------------------------------------------------------------------------------------------------
+def amr_hierarchy(name="C5"):
+    """A small 3-level hierarchy on a 64x64 base grid: L-shaped level 1 (concave corner, box-box exchange, a box on the
+    domain boundary), level 2 properly nested inside it.  Boxes are lo0 lo1 hi0 hi1, block-factor 8 aligned."""
+    cfg = syn.config(name, 1)
+    cfg.nx, cfg.ny = 64, 64
+    cfg.max_box_size = 32
+    base = syn.domain_split(64, 64, 32, 2)
+    lev1 = np.array([(16, 16, 47, 47), (48, 16, 79, 47), (16, 48, 47, 79), (96, 0, 127, 31)], dtype=np.int32)
+    lev2 = np.array([(48, 48, 79, 79), (80, 48, 111, 79), (48, 80, 79, 111)], dtype=np.int32)
+    return cfg, [base, lev1, lev2]
+
+
+class AmrOracleSide:
+    """Per-level oracle fields of a head-solve problem on an explicit hierarchy."""
+
+    def __init__(self, cfg, level_boxes, seed=12345, bc_vals=None, prm_over=None):
+        self.cfg, self.level_boxes = cfg, [np.asarray(b, dtype=np.int32) for b in level_boxes]
+        self.nlev = len(level_boxes)
+        self.layouts, self.F, self.dx = [], [], []
+        for l, boxes in enumerate(self.level_boxes):
+            r = 2 ** l
+            dom = (0, 0, cfg.nx * r - 1, cfg.ny * r - 1)
+            lay = ob.Layout(boxes, dom, cfg.periodic)
+            g = syn.fields(cfg, ng=1, seed=seed, level_ratio=r)
+            F = {}
+            for k in ("head", "B", "Pi", "zb", "mask"):
+                F[k] = ob.Field(lay, 1, 1)
+                F[k].set_global(g[k], (-1, -1))   # ghosts (CF ghosts included) from the analytic fields
+                if k != "head":
+                    ob.lib().orc_copy_ghost(F[k].h)
+            F["rhs"] = ob.Field(lay, 1, 0)
+            F["rhs"].set_global(g["rhs"], (0, 0))
+            F["a"] = ob.Field(lay, 1, 0)
+            F["bX"] = ob.Field(lay, 1, 0, XFACE)
+            F["bY"] = ob.Field(lay, 1, 0, YFACE)
+            self.layouts.append(lay)
+            self.F.append(F)
+            self.dx.append((cfg.dx[0] / r, cfg.dx[1] / r))
+        lo_val, hi_val = bc_vals if bc_vals else ((0.0, 0.0), (0.0, 0.0))
+        self.bc_vals = (lo_val, hi_val)
+        self.bc = ob.make_bc(cfg.bc_lo, cfg.bc_hi, lo_val, hi_val)
+        self.prm_kw = dict(A=cfg.A, omega=cfg.omega, nu=cfg.nu, cutOffbr=cfg.cutOffbr, maxOffbr=cfg.maxOffbr,
+                           cutOffBcoef=cfg.cutOffBcoef, use_mask_grad=cfg.use_mask_grad)
+        if prm_over:
+            self.prm_kw.update(prm_over)
+        self.prm = ob.make_params(**self.prm_kw)
+        self.alpha, self.beta = 0.0, -1.0
+
+    def fields(self, name):
+        return [F[name] for F in self.F]
+
+    def level_op(self, l):
+        F = self.F[l]
+        return ob.Op(self.layouts[l], self.dx[l], self.alpha, self.beta, self.bc, self.prm,
+                     F["a"], F["bX"], F["bY"], F["B"], F["Pi"], F["zb"], F["mask"])
+
+    def average_down(self, name="head"):
+        """fine -> coarse average of the covered region (AmrHydro does this before the solve, src/AmrHydro.cpp:3139)"""
+        for l in range(self.nlev - 1, 0, -1):
+            clay = self.layouts[l].coarsen(2)
+            tmp = ob.Field(clay, 1, 0)
+            ob.lib().orc_coarse_average(self.F[l][name].h, tmp.h, 2)
+            ob.copy_to(self.F[l - 1][name], tmp)
+
+    def init_bcoef(self):
+        """bCoef = B(h) of the current head on every level (what aCoeff_bCoeff hands to the solver)"""
+        for l in range(self.nlev):
+            op = self.level_op(l)
+            if l == 0:
+                op.update_operator(self.F[0]["head"])
+            else:
+                ob.cf_interp(self.F[l]["head"], self.F[l - 1]["head"], 2, self.dx[l][0])
+                op.update_operator_amr(self.F[l]["head"], self.F[l - 1]["head"], self.F[l - 1]["mask"])
+
+    def solver(self):
+        f = self.fields
+        return ob.AmrSolver(self.layouts, self.cfg.dx, self.alpha, self.beta, self.bc, self.prm,
+                            f("a"), f("bX"), f("bY"), f("B"), f("Pi"), f("zb"), f("mask"))
