@@ -29,6 +29,9 @@ METRIC = "head-solve cell-updates/sec (V-cycle)"
 UNIT = "cell-updates/s"
 BYTES_PER_UPDATE_SMOOTHER = 72.0   # phi, rhs, bX, bY, B, Pi, zb, mask read + phi written
 BYTES_PER_UPDATE_VCYCLE = 97.0     # whole V-cycle amortised
+# dram__bytes_read.sum + dram__bytes_write.sum of one finest-level smoother launch, from the `ncu --set full` capture of this
+# command committed as profiles/r01_k_gsrb_stream_ncu_full_raw.csv (4.697 GB read + 0.531 GB written; algorithmic 4.832 GB)
+NCU_TRAFFIC = {(8192, 1): 4.696833e9 + 0.531284224e9}
 
 
 def bench_config(size, nranks):
@@ -305,7 +308,7 @@ def main():
                        "relax_mode": {0: "separate colour passes", 1: "streaming red+black sweep, cp.async-staged", 2: "register-only fused sweep"}[args.relax_mode],
                        "e2e_step": f"one head solve = H2D of 8 fields + set-up + {args.e2e_cycles} V-cycles + D2H of head"},
             "roofline": {"bound": "hbm", "kernel": "k_gsrb_stream (finest level)" if args.relax_mode == 1 else "levelGSRB (finest level)", "achieved": achieved, "peak": peak,
-                         "unit": "GB/s", "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                         "unit": "GB/s", "frac": achieved / peak, "traffic": NCU_TRAFFIC.get((size, args.relax_mode)), "peak_source": peak_src,
                          "kernel_ms": k_ms, "bytes_per_cell_update": BYTES_PER_UPDATE_SMOOTHER,
                          "vcycle_gbs_at_97B": value / world * BYTES_PER_UPDATE_VCYCLE / 1e9},
             "cpu_baseline": cpu,

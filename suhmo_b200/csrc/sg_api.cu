@@ -3,6 +3,7 @@
 // Host logic only; all arithmetic is in sg_kernels.cuh.  There is no CPU fallback anywhere in this file.
 #include "../../include/suhmo_gpu.h"
 #include "sg_kernels.cuh"
+#include "sg_general.cuh"
 #include "sg_nccl.h"
 
 #include <algorithm>
@@ -12,6 +13,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <map>
 #include <string>
 #include <vector>
 
@@ -93,14 +95,30 @@ struct sg_layout {
   bool wrap_local[2] = {false, false};
   std::vector<sg_field*> ws; // lazily allocated work fields
   int refs = 1;
+  // patch table: one entry (the merged rectangle) for uniform levels, one entry per box otherwise
+  bool general = false;            // patches are the individual boxes (each with its own ghost ring)
+  bool fast = false;               // one rectangle without coarse-fine sides: the streaming kernels of sg_kernels.cuh apply
+  std::vector<PatchG> patches;
+  std::vector<int> patch_of_box;   // -1: box owned by another rank; RECT: 0
+  PatchG* d_patches = nullptr;
+  size_t total = 0;                // doubles per component
+  int max_nx = 0, max_ny = 0;
+  struct Plan { CopySeg* d = nullptr; int n = 0; bool built = false; };
+  Plan ex_faces, ex_full[3];       // exchange plans (general path): face strips depth 1; all ghosts depth 1 / 2
+  // spatial bins over the domain for "which patch holds cell (i,j)"
+  int bin_s = 0, bin_nx = 0, bin_ny = 0;
+  std::vector<std::vector<int>> bins;
 };
+#define GEN_GX 2
+#define GEN_GY 2
 
 struct sg_field {
   sg_layout* lay;
   int ncomp, ng, cent;
   double* base = nullptr;
   size_t comp_stride = 0;
-  double* p(int c = 0) const { return base + (size_t)c * comp_stride + (size_t)SG_YOFF * lay->pitch + SG_XOFF; }
+  double* p(int c = 0) const { return base + (size_t)c * comp_stride + (size_t)SG_YOFF * lay->pitch + SG_XOFF; } // fast path
+  double* cb(int c = 0) const { return base + (size_t)c * comp_stride; } // component base for patch-table kernels
 };
 
 struct sg_factory {
@@ -279,9 +297,63 @@ extern "C" int sg_set_relax_mode(sg_ctx* c, int mode) {
 // ------------------------------------------------------------------------------------------------
 // layouts
 // ------------------------------------------------------------------------------------------------
+// which local patch holds cell (i,j) in its valid region, periodic images included (-1: none); (*wi,*wj) = wrapped index
+static int patch_at(const sg_layout* L, int i, int j, int* wi, int* wj) {
+  for (int d = 0; d < 2; d++) {
+    int& x = d == 0 ? i : j;
+    int lo = L->domain.lo[d], n = L->domain.hi[d] - lo + 1;
+    if (x < lo || x > L->domain.hi[d]) {
+      if (!L->periodic[d]) return -1;
+      x = lo + (((x - lo) % n) + n) % n;
+    }
+  }
+  if (wi) *wi = i;
+  if (wj) *wj = j;
+  int bx = (i - L->domain.lo[0]) / L->bin_s, by = (j - L->domain.lo[1]) / L->bin_s;
+  for (int k : L->bins[(size_t)by * L->bin_nx + bx]) {
+    const PatchG& g = L->patches[k];
+    if (i >= g.glo0 && i < g.glo0 + g.nx && j >= g.glo1 && j < g.glo1 + g.ny) return k;
+  }
+  return -1;
+}
+static inline bool in_domain_p(const sg_layout* L, int i, int j) {
+  if (!L->periodic[0] && (i < L->domain.lo[0] || i > L->domain.hi[0])) return false;
+  if (!L->periodic[1] && (j < L->domain.lo[1] || j > L->domain.hi[1])) return false;
+  return true;
+}
+static inline Box patch_box(const PatchG& g) {
+  Box b;
+  b.lo[0] = g.glo0; b.lo[1] = g.glo1; b.hi[0] = g.glo0 + g.nx - 1; b.hi[1] = g.glo1 + g.ny - 1;
+  return b;
+}
+// element offset (from the component base) of global cell (gi,gj) inside patch g's array (ghost region included)
+static inline long long patch_off(const PatchG& g, int gi, int gj) { return g.off + (long long)(gj - g.glo1) * g.pitch + (gi - g.glo0); }
+
+static int layout_tables(sg_layout* L) {
+  sg_ctx* c = L->ctx;
+  if (!L->has_local) return SG_OK;
+  L->max_nx = L->max_ny = 0;
+  for (const PatchG& g : L->patches) { L->max_nx = std::max(L->max_nx, g.nx); L->max_ny = std::max(L->max_ny, g.ny); }
+  CK(cudaMalloc(&L->d_patches, L->patches.size() * sizeof(PatchG)));
+  CK(cudaMemcpyAsync(L->d_patches, L->patches.data(), L->patches.size() * sizeof(PatchG), cudaMemcpyHostToDevice, c->stream));
+  CK(cudaStreamSynchronize(c->stream));
+  L->bin_s = std::max(16, std::max(L->max_nx, L->max_ny));
+  L->bin_nx = (L->domain.hi[0] - L->domain.lo[0]) / L->bin_s + 1;
+  L->bin_ny = (L->domain.hi[1] - L->domain.lo[1]) / L->bin_s + 1;
+  L->bins.assign((size_t)L->bin_nx * L->bin_ny, std::vector<int>());
+  for (int k = 0; k < (int)L->patches.size(); k++) {
+    const PatchG& g = L->patches[k];
+    int bx0 = (g.glo0 - L->domain.lo[0]) / L->bin_s, bx1 = (g.glo0 + g.nx - 1 - L->domain.lo[0]) / L->bin_s;
+    int by0 = (g.glo1 - L->domain.lo[1]) / L->bin_s, by1 = (g.glo1 + g.ny - 1 - L->domain.lo[1]) / L->bin_s;
+    for (int by = by0; by <= by1; by++)
+      for (int bx = bx0; bx <= bx1; bx++) L->bins[(size_t)by * L->bin_nx + bx].push_back(k);
+  }
+  return SG_OK;
+}
+
 static int layout_finish(sg_layout* L) {
   sg_ctx* c = L->ctx;
-  // per-rank bounding rectangles, each required to be tiled exactly by that rank's boxes
+  // per-rank bounding rectangles; a rank whose boxes tile its rectangle exactly stores the level as ONE merged patch
   std::vector<Box> rp(c->nranks);
   std::vector<long long> area(c->nranks, 0);
   std::vector<bool> has(c->nranks, false);
@@ -295,11 +367,39 @@ static int layout_finish(sg_layout* L) {
       for (int d = 0; d < 2; d++) { rp[r].lo[d] = std::min(rp[r].lo[d], bx.lo[d]); rp[r].hi[d] = std::max(rp[r].hi[d], bx.hi[d]); }
     area[r] += bx.npts();
   }
+  bool tiles = true;
   for (int r = 0; r < c->nranks; r++)
-    if (has[r] && area[r] != rp[r].npts())
-      return fail(SG_ERR_UNSUPPORTED, "layout: boxes of rank %d do not tile a rectangle (%lld of %lld cells); "
-                  "multi-patch levels are not built yet", r, area[r], rp[r].npts());
+    if (has[r] && area[r] != rp[r].npts()) tiles = false;
   L->has_local = has[c->rank];
+  L->patch_of_box.assign(L->nbox, -1);
+  if (!tiles) {
+    // refined AMR level: every box is its own patch with a private ghost ring (Chombo's own data model)
+    if (c->nranks != 1)
+      return fail(SG_ERR_UNSUPPORTED, "layout: boxes do not tile one rectangle per rank; multi-patch (refined AMR) levels are "
+                  "single-GPU in this build");
+    L->general = true; L->fast = false;
+    L->patch = rp[0];
+    L->nx = L->patch.nx(); L->ny = L->patch.ny(); L->pitch = 0; L->rows = 0;
+    size_t tot = 0;
+    for (int b = 0; b < L->nbox; b++) {
+      const Box& bx = L->boxes[b];
+      PatchG g;
+      g.nx = bx.nx(); g.ny = bx.ny(); g.glo0 = bx.lo[0]; g.glo1 = bx.lo[1];
+      g.pitch = ((g.nx + 2 * GEN_GX + 2 + 1) / 2) * 2;
+      int rows = g.ny + 2 * GEN_GY + 2;
+      g.off = (long long)tot + (long long)GEN_GY * g.pitch + GEN_GX;
+      for (int s = 0; s < 4; s++) {
+        int dir = s >> 1, side = s & 1;
+        bool ondom = side ? bx.hi[dir] == L->domain.hi[dir] : bx.lo[dir] == L->domain.lo[dir];
+        g.phys[s] = ondom && !L->periodic[dir];
+      }
+      tot += (size_t)rows * g.pitch;
+      L->patch_of_box[b] = (int)L->patches.size();
+      L->patches.push_back(g);
+    }
+    L->total = tot;
+    return layout_tables(L);
+  }
   if (!L->has_local) return SG_OK;
   L->patch = rp[c->rank];
   L->nx = L->patch.nx(); L->ny = L->patch.ny();
@@ -347,7 +447,21 @@ static int layout_finish(sg_layout* L) {
       }
     }
   }
-  return SG_OK;
+  {
+    PatchG g;
+    g.off = (long long)SG_YOFF * L->pitch + SG_XOFF;
+    g.pitch = L->pitch; g.nx = L->nx; g.ny = L->ny; g.glo0 = L->patch.lo[0]; g.glo1 = L->patch.lo[1];
+    L->fast = true;
+    for (int s = 0; s < 4; s++) {
+      g.phys[s] = L->side_domain[s] && !L->periodic[s >> 1];
+      if (!L->side_domain[s] && !L->side_ghost[s]) L->fast = false; // coarse-fine side: ghost cells hold interpolated data
+    }
+    L->patches.push_back(g);
+    L->total = (size_t)L->rows * L->pitch;
+    for (int b = 0; b < L->nbox; b++)
+      if (L->owner[b] == c->rank) L->patch_of_box[b] = 0;
+  }
+  return layout_tables(L);
 }
 
 extern "C" int sg_layout_create(sg_ctx* ctx, sg_layout** out, int nbox, const int* boxes, const int* owner,
@@ -399,6 +513,9 @@ extern "C" int sg_field_destroy(sg_field* f);
 extern "C" int sg_layout_destroy(sg_layout* L) {
   if (!L) return SG_OK;
   for (sg_field* w : L->ws) sg_field_destroy(w);
+  cudaFree(L->d_patches);
+  cudaFree(L->ex_faces.d);
+  for (int k = 0; k < 3; k++) cudaFree(L->ex_full[k].d);
   delete L;
   return SG_OK;
 }
@@ -411,7 +528,7 @@ extern "C" int sg_field_create(sg_layout* L, sg_field** out, int ncomp, int ngho
   sg_field* f = new sg_field();
   f->lay = L; f->ncomp = ncomp; f->ng = nghost; f->cent = centering;
   if (L->has_local) {
-    f->comp_stride = (size_t)L->rows * L->pitch;
+    f->comp_stride = L->total;
     CK(cudaMalloc(&f->base, f->comp_stride * ncomp * sizeof(double)));
     CK(cudaMemsetAsync(f->base, 0, f->comp_stride * ncomp * sizeof(double), L->ctx->stream));
   }
@@ -455,6 +572,7 @@ static Box patch_rect(const sg_field* f) {
 // pieces of box b's FAB that are copied on upload: the valid region plus the ghost cells lying outside the patch
 static int upload_rects(const sg_field* f, int b, Box out[5]) {
   int n = 0;
+  if (f->lay->general) { out[0] = fab_rect(f, b, f->ng); return 1; } // every box owns its ghost ring
   Box F = fab_rect(f, b, f->ng), V = fab_rect(f, b, 0), Pv = patch_rect(f);
   out[n++] = V;
   if (f->ng == 0) return n;
@@ -468,9 +586,11 @@ static int upload_rects(const sg_field* f, int b, Box out[5]) {
   }
   return n;
 }
-static inline ptrdiff_t dev_off(const sg_field* f, int gi, int gj) {
-  return (ptrdiff_t)(gj - f->lay->patch.lo[1]) * f->lay->pitch + (gi - f->lay->patch.lo[0]);
+// element offset from the component base of global index (gi,gj) in the array of the patch that holds box b
+static inline ptrdiff_t dev_off(const sg_field* f, int b, int gi, int gj) {
+  return (ptrdiff_t)patch_off(f->lay->patches[f->lay->patch_of_box[b]], gi, gj);
 }
+static inline int box_pitch(const sg_field* f, int b) { return f->lay->patches[f->lay->patch_of_box[b]].pitch; }
 
 extern "C" int sg_field_upload_box(sg_field* f, int box, const double* host) {
   REQUIRE(f && host && box >= 0 && box < f->lay->nbox, "sg_field_upload_box: bad arguments");
@@ -484,8 +604,8 @@ extern "C" int sg_field_upload_box(sg_field* f, int box, const double* host) {
     for (int k = 0; k < n; k++) {
       const Box& r = rs[k];
       const double* src = host + c * fabn + (size_t)(r.lo[1] - F.lo[1]) * F.nx() + (r.lo[0] - F.lo[0]);
-      double* dst = f->p(c) + dev_off(f, r.lo[0], r.lo[1]);
-      CK(cudaMemcpy2DAsync(dst, (size_t)L->pitch * 8, src, (size_t)F.nx() * 8, (size_t)r.nx() * 8, r.ny(), cudaMemcpyHostToDevice, L->ctx->stream));
+      double* dst = f->cb(c) + dev_off(f, box, r.lo[0], r.lo[1]);
+      CK(cudaMemcpy2DAsync(dst, (size_t)box_pitch(f, box) * 8, src, (size_t)F.nx() * 8, (size_t)r.nx() * 8, r.ny(), cudaMemcpyHostToDevice, L->ctx->stream));
     }
   CK(cudaStreamSynchronize(L->ctx->stream)); // host buffer may be reused by the caller
   return SG_OK;
@@ -497,8 +617,8 @@ extern "C" int sg_field_download_box(const sg_field* f, int box, double* host) {
   Box F = fab_rect(f, box, f->ng);
   size_t fabn = (size_t)F.nx() * F.ny();
   for (int c = 0; c < f->ncomp; c++) {
-    const double* src = f->p(c) + dev_off(f, F.lo[0], F.lo[1]);
-    CK(cudaMemcpy2DAsync(host + c * fabn, (size_t)F.nx() * 8, src, (size_t)L->pitch * 8, (size_t)F.nx() * 8, F.ny(), cudaMemcpyDeviceToHost, L->ctx->stream));
+    const double* src = f->cb(c) + dev_off(f, box, F.lo[0], F.lo[1]);
+    CK(cudaMemcpy2DAsync(host + c * fabn, (size_t)F.nx() * 8, src, (size_t)box_pitch(f, box) * 8, (size_t)F.nx() * 8, F.ny(), cudaMemcpyDeviceToHost, L->ctx->stream));
   }
   CK(cudaStreamSynchronize(L->ctx->stream));
   return SG_OK;
@@ -521,10 +641,10 @@ static size_t build_segs(const sg_field* f, bool upload, std::vector<CopySeg>& s
       for (int k = 0; k < n; k++) {
         CopySeg s;
         long long packed = (long long)(total + (size_t)cc * F.nx() * F.ny() + (size_t)(rs[k].lo[1] - F.lo[1]) * F.nx() + (rs[k].lo[0] - F.lo[0]));
-        long long dev = (long long)((f->p(cc) - f->base) + dev_off(f, rs[k].lo[0], rs[k].lo[1]));
+        long long dev = (long long)((f->cb(cc) - f->base) + dev_off(f, b, rs[k].lo[0], rs[k].lo[1]));
         s.so = upload ? packed : dev; s.dofs = upload ? dev : packed;
         s.nx = rs[k].nx(); s.ny = rs[k].ny();
-        s.sp = upload ? F.nx() : L->pitch; s.dp = upload ? L->pitch : F.nx();
+        s.sp = upload ? F.nx() : box_pitch(f, b); s.dp = upload ? box_pitch(f, b) : F.nx();
         segs.push_back(s);
       }
     total += (size_t)F.nx() * F.ny() * f->ncomp;

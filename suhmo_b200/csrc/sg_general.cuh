@@ -1,0 +1,411 @@
+// sg_general.cuh -- kernels over a TABLE of patches: AMR levels whose boxes do not tile one rectangle, levels with
+// coarse-fine ("frozen") ghost cells, and every two-level operation (QuadCFInterp, flux register, AMRRestrict/Prolong).
+//
+// A level on one GPU is a list of patches (PatchG).  Uniform base levels are one patch (the merged rectangle) and run the
+// streaming kernels of sg_kernels.cuh; everything here addresses cells as base[patch.off + j*patch.pitch + i], so the same
+// kernels serve one-patch and many-patch levels and any mixture of the two across levels.
+// Arithmetic follows the same sources, in the same order, as sg_kernels.cuh (-fmad=false): bit-identical to the oracle.
+#pragma once
+#include "sg_kernels.cuh"
+
+struct PatchG {
+  long long off;   // element offset of cell (0,0) of the patch from the component base
+  int pitch, nx, ny;
+  int glo0, glo1;  // global index of local cell (0,0)
+  int phys[4];     // side lies on a non-periodic problem-domain boundary (x-lo, x-hi, y-lo, y-hi)
+};
+
+struct OpArgsG { // OpArgs without geometry: component bases of the coefficient fields
+  PhysP prm;
+  double alpha, beta, dxi0, dxi1, dx0, dx1;
+  int has_a;
+  const double* aC; const double* bX; const double* bY; const double* B; const double* Pi; const double* zb; const double* mask;
+  int bc_kind[4];   // per side: SK_PHYS_DIRI / SK_PHYS_NEUM / SK_PHYS_NONE (applies where PatchG.phys is set)
+  double bcval[4];
+};
+
+// mixBCValues on every patch side that lies on the physical boundary (face strips, no corners)
+__global__ void k_bc_ghost_g(double* __restrict__ base, const PatchG* __restrict__ tab, OpArgsG a, int homogeneous) {
+  const PatchG g = tab[blockIdx.z];
+  int t = blockIdx.x * blockDim.x + threadIdx.x;
+  int side = blockIdx.y;
+  if (!g.phys[side]) return;
+  int kind = a.bc_kind[side];
+  if (kind != SK_PHYS_DIRI && kind != SK_PHYS_NEUM) return;
+  double val = homogeneous ? 0.0 : a.bcval[side];
+  double* p = base + g.off;
+  if (side < 2) {
+    if (t >= g.ny) return;
+    int ig = side == 0 ? -1 : g.nx, in = side == 0 ? 0 : g.nx - 1;
+    double sdx = side == 0 ? -a.dx0 : a.dx0;
+    p[(ptrdiff_t)t * g.pitch + ig] = bc_ghost_value(kind, p[(ptrdiff_t)t * g.pitch + in], val, sdx);
+  } else {
+    if (t >= g.nx) return;
+    int jg = side == 2 ? -1 : g.ny, jn = side == 2 ? 0 : g.ny - 1;
+    double sdx = side == 2 ? -a.dx1 : a.dx1;
+    p[(ptrdiff_t)jg * g.pitch + t] = bc_ghost_value(kind, p[(ptrdiff_t)jn * g.pitch + t], val, sdx);
+  }
+}
+
+// ExtrapGhostCells / CopyGhostCells (cell data, 1 ghost), one direction per launch, strips grown by 1 tangentially
+__global__ void k_extrap_ghost_g(double* __restrict__ base, const PatchG* __restrict__ tab, int dir, int copy_only) {
+  const PatchG g = tab[blockIdx.z];
+  int t = blockIdx.x * blockDim.x + threadIdx.x;
+  double* q = base + g.off;
+  int n = (dir == 0 ? g.ny : g.nx) + 2;
+  if (t >= n) return;
+  int k = t - 1;
+  for (int side = 0; side < 2; side++) {
+    if (!g.phys[2 * dir + side]) continue;
+    int step = side == 0 ? 1 : -1;
+    int gidx = side == 0 ? -1 : (dir == 0 ? g.nx : g.ny);
+    ptrdiff_t b0 = (dir == 0) ? (ptrdiff_t)k * g.pitch + gidx : (ptrdiff_t)gidx * g.pitch + k;
+    ptrdiff_t st = (dir == 0) ? step : (ptrdiff_t)step * g.pitch;
+    q[b0] = copy_only ? q[b0 + st] : 2.0 * q[b0 + st] - q[b0 + 2 * st];
+  }
+}
+
+// GSRB colour pass (GSRBHELMHOLTZVCNL2D), ghosts in memory, in place
+__global__ void __launch_bounds__(256) k_gsrb_color_g(double* __restrict__ phib, const double* __restrict__ rhsb,
+                                                      const PatchG* __restrict__ tab, OpArgsG a, int pass) {
+  const PatchG g = tab[blockIdx.z];
+  int half = (g.nx + 1) >> 1;
+  int t = blockIdx.x * blockDim.x + threadIdx.x;
+  int j = blockIdx.y * blockDim.y + threadIdx.y;
+  if (j >= g.ny || t >= half) return;
+  int off = (g.glo0 + g.glo1 + j + pass) & 1;
+  int i = 2 * t + off;
+  if (i >= g.nx) return;
+  ptrdiff_t P = g.pitch;
+  ptrdiff_t o = g.off + (ptrdiff_t)j * P + i;
+  double pc = phib[o], pw = phib[o - 1], pe = phib[o + 1], ps = phib[o - P], pn = phib[o + P];
+  double bw = a.bX[o], be = a.bX[o + 1], bs = a.bY[o], bn = a.bY[o + P];
+  double ac = a.has_a ? a.aC[o] : 0.0;
+  double nl, dnl;
+  nl_terms(a.prm, pc, a.B[o], a.mask[o], a.Pi[o], a.zb[o], nl, dnl);
+  double lof = lofphi_cell(a.alpha, ac, a.beta, pc, pw, pe, ps, pn, bw, be, bs, bn, a.dxi0, a.dxi1, nl);
+  double lam = lambda_cell(a.alpha, ac, a.beta, bw, be, bs, bn, a.dxi0, a.dxi1);
+  double denom = 1.0e-16 + lam + dnl;
+  phib[o] = pc + (rhsb[o] - lof) / denom;
+}
+
+// MODE 0: out = L(phi); 1: out = rhs - L(phi); 2: as 1 plus max|out| into *norm_bits
+template <int MODE>
+__global__ void __launch_bounds__(256) k_apply_g(double* __restrict__ outb, const double* __restrict__ phib,
+                                                 const double* __restrict__ rhsb, const PatchG* __restrict__ tab, OpArgsG a,
+                                                 unsigned long long* norm_bits) {
+  const PatchG g = tab[blockIdx.z];
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  int j = blockIdx.y * blockDim.y + threadIdx.y;
+  double r = 0.0;
+  if (i < g.nx && j < g.ny) {
+    ptrdiff_t P = g.pitch;
+    ptrdiff_t o = g.off + (ptrdiff_t)j * P + i;
+    double pc = phib[o], pw = phib[o - 1], pe = phib[o + 1], ps = phib[o - P], pn = phib[o + P];
+    double bw = a.bX[o], be = a.bX[o + 1], bs = a.bY[o], bn = a.bY[o + P];
+    double ac = a.has_a ? a.aC[o] : 0.0;
+    double nl, dnl;
+    nl_terms(a.prm, pc, a.B[o], a.mask[o], a.Pi[o], a.zb[o], nl, dnl);
+    double lof = lofphi_cell(a.alpha, ac, a.beta, pc, pw, pe, ps, pn, bw, be, bs, bn, a.dxi0, a.dxi1, nl);
+    r = MODE == 0 ? lof : rhsb[o] - (lof);
+    outb[o] = r;
+  }
+  if (MODE == 2) block_max_to_global(fabs(r), norm_bits);
+}
+
+// vector ops over valid cells (whole != 0: ghost ring of width ng included). op as k_vec.
+template <int OP>
+__global__ void __launch_bounds__(256) k_vec_g(double* __restrict__ y, const double* __restrict__ x, const double* __restrict__ z,
+                                               double a, double b, const PatchG* __restrict__ tab, int ng, int ex, int ey) {
+  const PatchG g = tab[blockIdx.z];
+  int i = (int)(blockIdx.x * blockDim.x + threadIdx.x) - ng;
+  int j = (int)(blockIdx.y * blockDim.y + threadIdx.y) - ng;
+  if (i >= g.nx + ex + ng || j >= g.ny + ey + ng) return;
+  ptrdiff_t o = g.off + (ptrdiff_t)j * g.pitch + i;
+  if (OP == 0) y[o] = a * x[o] + b * z[o];
+  if (OP == 1) y[o] = y[o] + a * x[o];
+  if (OP == 2) y[o] = y[o] * a;
+  if (OP == 3) y[o] = x[o];
+  if (OP == 4) y[o] = a;
+}
+
+// reductions over valid cells of all patches: mode 0 max|x| (exact), 1 sum|x|, 2 sum x^2, 3 sum x*y (fixed-shape partials)
+__global__ void __launch_bounds__(256) k_reduce_g(const double* __restrict__ x, const double* __restrict__ y,
+                                                  const PatchG* __restrict__ tab, int mode, double* __restrict__ partial,
+                                                  unsigned long long* maxbits) {
+  const PatchG g = tab[blockIdx.z];
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  int j = blockIdx.y * blockDim.y + threadIdx.y;
+  double v = 0.0;
+  if (i < g.nx && j < g.ny) {
+    ptrdiff_t o = g.off + (ptrdiff_t)j * g.pitch + i;
+    double xv = x[o];
+    v = mode == 0 ? fabs(xv) : mode == 1 ? fabs(xv) : mode == 2 ? xv * xv : xv * y[o];
+  }
+  if (mode == 0) { block_max_to_global(v, maxbits); return; }
+  __shared__ double sh[256];
+  int t = threadIdx.y * blockDim.x + threadIdx.x;
+  sh[t] = v;
+  __syncthreads();
+  for (int s = 128; s > 0; s >>= 1) {
+    if (t < s) sh[t] = sh[t] + sh[t + s];
+    __syncthreads();
+  }
+  if (t == 0) partial[((size_t)blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x] = sh[0];
+}
+
+// compGradientCC (NEWMACGRAD normal derivative on valid-box faces + EdgeToCell) -> gx, gy component bases
+__global__ void __launch_bounds__(256) k_gradient_cc_g(double* __restrict__ gxb, double* __restrict__ gyb, const double* __restrict__ phib,
+                                                       const double* __restrict__ maskb, const PatchG* __restrict__ tab, double dx0,
+                                                       double dx1) {
+  const PatchG g = tab[blockIdx.z];
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  int j = blockIdx.y * blockDim.y + threadIdx.y;
+  if (i >= g.nx || j >= g.ny) return;
+  ptrdiff_t P = g.pitch;
+  ptrdiff_t o = g.off + (ptrdiff_t)j * P + i;
+  double fx = 1.0 / dx0, fy = 1.0 / dx1;
+  double pc = phib[o], pw = phib[o - 1], pe = phib[o + 1], ps = phib[o - P], pn = phib[o + P];
+  double gxl, gxh, gyl, gyh;
+  if (maskb) {
+    double mc = maskb[o], mw = maskb[o - 1], me = maskb[o + 1], ms = maskb[o - P], mn = maskb[o + P];
+    gxl = (mc < 1E-6 || mw < 1E-6) ? 0.0 : fx * (pc - pw);
+    gxh = (me < 1E-6 || mc < 1E-6) ? 0.0 : fx * (pe - pc);
+    gyl = (mc < 1E-6 || ms < 1E-6) ? 0.0 : fy * (pc - ps);
+    gyh = (mn < 1E-6 || mc < 1E-6) ? 0.0 : fy * (pn - pc);
+  } else {
+    gxl = fx * (pc - pw); gxh = fx * (pe - pc); gyl = fy * (pc - ps); gyh = fy * (pn - pc);
+  }
+  gxb[o] = 0.5 * (gxl + gxh);
+  gyb[o] = 0.5 * (gyl + gyh);
+}
+
+// COMPUTERE over the ghosted box
+__global__ void __launch_bounds__(256) k_compute_re_g(double* __restrict__ Reb, const double* __restrict__ Bb, const double* __restrict__ gxb,
+                                                      const double* __restrict__ gyb, const PatchG* __restrict__ tab, PhysP prm) {
+  const PatchG g = tab[blockIdx.z];
+  int i = (int)(blockIdx.x * blockDim.x + threadIdx.x) - 1;
+  int j = (int)(blockIdx.y * blockDim.y + threadIdx.y) - 1;
+  if (i > g.nx || j > g.ny) return;
+  ptrdiff_t o = g.off + (ptrdiff_t)j * g.pitch + i;
+  Reb[o] = reynolds(prm, Bb[o], gxb[o], gyb[o]);
+}
+
+// CellToEdge(Re), CellToEdge(B), setup_iceMask_EC, COMPUTEBCOEFF -> bX, bY on the faces of every patch
+__global__ void __launch_bounds__(256) k_bcoef_faces_g(double* __restrict__ bXb, double* __restrict__ bYb, const double* __restrict__ Reb,
+                                                       const double* __restrict__ Bb, const double* __restrict__ maskb,
+                                                       const PatchG* __restrict__ tab, PhysP prm, int dlo0, int dlo1, int dhi0, int dhi1) {
+  const PatchG g = tab[blockIdx.z];
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  int j = blockIdx.y * blockDim.y + threadIdx.y;
+  if (i > g.nx || j > g.ny) return;
+  ptrdiff_t P = g.pitch;
+  ptrdiff_t o = g.off + (ptrdiff_t)j * P + i;
+  double rc = Reb[o], bc = Bb[o], mc = maskb[o];
+  if (j < g.ny) {
+    double r = 0.5 * (rc + Reb[o - 1]), b = 0.5 * (bc + Bb[o - 1]);
+    double mm = maskb[o - 1];
+    double im = fabs(mc - mm) < 1e-10 ? (mc > 0.0 ? 1.0 : -1.0) : 0.0;
+    int gi = g.glo0 + i;
+    if (gi == dlo0) im = 0.0;
+    if (gi == dhi0 + 1) im = 0.0;
+    bXb[o] = bcoeff_face(prm, b, r, im);
+  }
+  if (i < g.nx) {
+    double r = 0.5 * (rc + Reb[o - P]), b = 0.5 * (bc + Bb[o - P]);
+    double mm = maskb[o - P];
+    double im = fabs(mc - mm) < 1e-10 ? (mc > 0.0 ? 1.0 : -1.0) : 0.0;
+    int gj = g.glo1 + j;
+    if (gj == dlo1) im = 0.0;
+    if (gj == dhi1 + 1) im = 0.0;
+    bYb[o] = bcoeff_face(prm, b, r, im);
+  }
+}
+
+__global__ void __launch_bounds__(256) k_lambda_g(double* __restrict__ lamb, const PatchG* __restrict__ tab, OpArgsG a) {
+  const PatchG g = tab[blockIdx.z];
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  int j = blockIdx.y * blockDim.y + threadIdx.y;
+  if (i >= g.nx || j >= g.ny) return;
+  ptrdiff_t o = g.off + (ptrdiff_t)j * g.pitch + i;
+  double ac = a.has_a ? a.aC[o] : 0.0;
+  lamb[o] = lambda_cell(a.alpha, ac, a.beta, a.bX[o], a.bX[o + 1], a.bY[o], a.bY[o + g.pitch], a.dxi0, a.dxi1);
+}
+
+__global__ void __launch_bounds__(256) k_nl_g(double* __restrict__ nl, double* __restrict__ dnl, const double* __restrict__ phi,
+                                              const double* __restrict__ B, const double* __restrict__ mask, const double* __restrict__ Pi,
+                                              const double* __restrict__ zb, const PatchG* __restrict__ tab, PhysP prm) {
+  const PatchG g = tab[blockIdx.z];
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  int j = blockIdx.y * blockDim.y + threadIdx.y;
+  if (i >= g.nx || j >= g.ny) return;
+  ptrdiff_t o = g.off + (ptrdiff_t)j * g.pitch + i;
+  double n, d;
+  nl_terms(prm, phi[o], B[o], mask[o], Pi[o], zb[o], n, d);
+  nl[o] = n; dnl[o] = d;
+}
+
+__global__ void __launch_bounds__(256) k_divergence_g(double* __restrict__ div, const double* __restrict__ ux, const double* __restrict__ uy,
+                                                      const PatchG* __restrict__ tab, double dx0, double dx1) {
+  const PatchG g = tab[blockIdx.z];
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  int j = blockIdx.y * blockDim.y + threadIdx.y;
+  if (i >= g.nx || j >= g.ny) return;
+  ptrdiff_t o = g.off + (ptrdiff_t)j * g.pitch + i;
+  double ox = 1.0 / dx0, oy = 1.0 / dx1;
+  double d = div[o];
+  d = d + ox * (ux[o + 1] - ux[o]);
+  d = d + oy * (uy[o + g.pitch] - uy[o]);
+  div[o] = d;
+}
+
+// ------------------------------------------------------------------------------------------------
+// two-level kernels
+// ------------------------------------------------------------------------------------------------
+// QuadCFInterp (absent Chombo; same formulas as oracle/suhmo_oracle.c:orc_cf_interp).  One thread per coarse-fine ghost
+// cell.  Coarse values come from a coarsened-fine scratch (2 ghost cells, filled by a copy plan), so the whole stencil
+// of an item lies in one scratch patch: c0 = offset of the coarse cell under the ghost cell, cstep = tangential stride.
+struct CFItem {
+  long long fo;   // fine ghost cell
+  long long c0;   // coarse cell in the scratch
+  int fstep;      // fine stride from the ghost cell towards the interior
+  int cstep;      // coarse tangential stride
+  int type;       // 0 centred, 1 forward 3-pt, 2 backward 3-pt, 3 forward 2-pt, 4 backward 2-pt, 5 none
+  int pad;
+  double dist;    // tangential offset of the fine cell centre from the coarse cell centre
+};
+__global__ void __launch_bounds__(128) k_cf_interp(double* __restrict__ fineb, const double* __restrict__ crseb,
+                                                   const CFItem* __restrict__ items, int n, double dxf, double dxc, int r) {
+  int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n) return;
+  const CFItem it = items[t];
+  const double p0 = crseb[it.c0];
+  double d1, d2;
+  if (it.type == 0) {
+    double pp = crseb[it.c0 + it.cstep], pm = crseb[it.c0 - it.cstep];
+    d1 = (pp - pm) / (2.0 * dxc); d2 = (pp - 2.0 * p0 + pm) / (dxc * dxc);
+  } else if (it.type == 1) {
+    double pp = crseb[it.c0 + it.cstep], pp2 = crseb[it.c0 + 2 * (ptrdiff_t)it.cstep];
+    d1 = (-3.0 * p0 + 4.0 * pp - pp2) / (2.0 * dxc); d2 = (p0 - 2.0 * pp + pp2) / (dxc * dxc);
+  } else if (it.type == 2) {
+    double pm = crseb[it.c0 - it.cstep], pm2 = crseb[it.c0 - 2 * (ptrdiff_t)it.cstep];
+    d1 = (3.0 * p0 - 4.0 * pm + pm2) / (2.0 * dxc); d2 = (p0 - 2.0 * pm + pm2) / (dxc * dxc);
+  } else if (it.type == 3) {
+    double pp = crseb[it.c0 + it.cstep];
+    d1 = (pp - p0) / dxc; d2 = 0.0;
+  } else if (it.type == 4) {
+    double pm = crseb[it.c0 - it.cstep];
+    d1 = (p0 - pm) / dxc; d2 = 0.0;
+  } else { d1 = 0.0; d2 = 0.0; }
+  const double dist = it.dist;
+  const double pc = p0 + dist * d1 + 0.5 * dist * dist * d2;
+  const double pa = fineb[it.fo + 2 * (ptrdiff_t)it.fstep];
+  const double pb = fineb[it.fo + it.fstep];
+  const double h = dxf;
+  const double a = (2. / h / h) * (2. * pc + pa * (r + 1.0) - pb * (r + 3.0)) / (r * r + 4 * r + 3.0);
+  const double bq = (pb - pa) / h - a * h;
+  const double x = 2. * h;
+  fineb[it.fo] = a * x * x + bq * x + pa;
+}
+
+// Flux register (VCAMRNonLinearPoissonOp::reflux over LevelFluxRegister; oracle: orc_op_reflux).  One thread per coarse
+// cell that borders the fine level; faces in the order dir0-Lo, dir0-Hi, dir1-Lo, dir1-Hi.
+struct RefluxFace {
+  int valid, pad;
+  long long c_hi, c_lo, c_b;            // coarse phi cells on the high/low side of the CF face, coarse face coefficient
+  long long f_in[2], f_gh[2], f_b[2];   // per fine face: interior fine cell, its CF ghost cell, fine face coefficient
+};
+struct RefluxItem {
+  long long res;
+  RefluxFace f[4];
+};
+__global__ void __launch_bounds__(128) k_reflux(double* __restrict__ resb, const double* __restrict__ phicb, const double* __restrict__ bXc,
+                                                const double* __restrict__ bYc, const double* __restrict__ phifb,
+                                                const double* __restrict__ bXf, const double* __restrict__ bYf,
+                                                const RefluxItem* __restrict__ items, int n, double beta, double dxc0, double dxc1, int r) {
+  int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n) return;
+  const RefluxItem& it = items[t];
+  double scale2 = 1.0;
+  scale2 *= dxc0; scale2 *= dxc1;
+  scale2 = 1.0 / scale2;
+  double reg = 0.0;
+  for (int k = 0; k < 4; k++) { // incrementCoarse
+    const RefluxFace& f = it.f[k];
+    if (!f.valid) continue;
+    const int dir = k >> 1, side = k & 1;
+    const double dxn = dir == 0 ? dxc0 : dxc1, scale = dir == 0 ? dxc1 : dxc0;
+    const double* bc = dir == 0 ? bXc : bYc;
+    double gradphi = (phicb[f.c_hi] - phicb[f.c_lo]) * (beta * 1 / dxn);
+    double F = -bc[f.c_b] * gradphi;
+    double sgn = side ? 1.0 : -1.0;
+    reg = reg + (-sgn * scale) * F;
+  }
+  for (int k = 0; k < 4; k++) { // incrementFine
+    const RefluxFace& f = it.f[k];
+    if (!f.valid) continue;
+    const int dir = k >> 1, side = k & 1;
+    const double dxn = dir == 0 ? dxc0 : dxc1, scale = dir == 0 ? dxc1 : dxc0;
+    const double* bf = dir == 0 ? bXf : bYf;
+    double sgn = side ? 1.0 : -1.0;
+    double sf = sgn * scale / (double)r;
+    double piece = 0.0;
+    for (int m = 0; m < 2; m++) {
+      double phihi = side ? phifb[f.f_gh[m]] : phifb[f.f_in[m]];
+      double philo = side ? phifb[f.f_in[m]] : phifb[f.f_gh[m]];
+      double gradphi = (phihi - philo) * (beta * r / dxn);
+      double F = -bf[f.f_b[m]] * gradphi;
+      piece = piece + sf * F;
+    }
+    reg = reg + piece;
+  }
+  resb[it.res] = resb[it.res] + (-scale2) * reg;
+}
+
+// FORT_AVERAGE of AMRRestrictS: coarse (coarsened-fine scratch patch k) = sum of the 2x2 fine cells (i fastest) * 1/4
+__global__ void __launch_bounds__(256) k_amr_average(double* __restrict__ cb, const PatchG* __restrict__ ctab, const double* __restrict__ fb,
+                                                     const PatchG* __restrict__ ftab) {
+  const PatchG gc = ctab[blockIdx.z], gf = ftab[blockIdx.z];
+  int ic = blockIdx.x * blockDim.x + threadIdx.x;
+  int jc = blockIdx.y * blockDim.y + threadIdx.y;
+  if (ic >= gc.nx || jc >= gc.ny) return;
+  const double refScale = 1.0 / 4.0;
+  double s = 0.0;
+#pragma unroll
+  for (int jj = 0; jj < 2; jj++)
+#pragma unroll
+    for (int ii = 0; ii < 2; ii++) s = s + fb[gf.off + (ptrdiff_t)(2 * jc + jj) * gf.pitch + (2 * ic + ii)];
+  cb[gc.off + (ptrdiff_t)jc * gc.pitch + ic] = s * refScale;
+}
+
+// PROLONGNL (mode 0) / PROLONG_2_NL (mode 1) from the coarsened-fine scratch patch k into fine patch k
+__global__ void __launch_bounds__(256) k_amr_prolong(double* __restrict__ fb, const PatchG* __restrict__ ftab, const double* __restrict__ cb,
+                                                     const PatchG* __restrict__ ctab, int mode) {
+  const PatchG gf = ftab[blockIdx.z], gc = ctab[blockIdx.z];
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  int j = blockIdx.y * blockDim.y + threadIdx.y;
+  if (i >= gf.nx || j >= gf.ny) return;
+  ptrdiff_t o = gf.off + (ptrdiff_t)j * gf.pitch + i;
+  int ic = i >> 1, jc = j >> 1;
+  ptrdiff_t oc = gc.off + (ptrdiff_t)jc * gc.pitch + ic;
+  if (mode == 0) { fb[o] = fb[o] + cb[oc]; return; }
+  const double den = 1.0 / 16.0;
+  const double fx1 = 3.0 * den, fx2 = 3.0 * 3.0 * den, f0 = 1.0 * den;
+  int o1 = 2 * (i & 1) - 1, o2 = 2 * (j & 1) - 1;
+  double p = fb[o];
+  p = p + fx2 * cb[oc] + f0 * cb[oc + (ptrdiff_t)o2 * gc.pitch + o1];
+  p = p + fx1 * (cb[oc + o1] + cb[oc + (ptrdiff_t)o2 * gc.pitch]);
+  fb[o] = p;
+}
+
+// zeroCovered: rectangles (in patch-local offsets) of a coarse field that lie under the finer level
+struct ZeroSeg { long long off; int nx, ny, pitch, pad; };
+__global__ void k_zero_segs(double* __restrict__ base, const ZeroSeg* __restrict__ segs, int nseg) {
+  int s = blockIdx.x;
+  if (s >= nseg) return;
+  ZeroSeg z = segs[s];
+  for (int t = blockIdx.y * blockDim.x + threadIdx.x; t < z.nx * z.ny; t += gridDim.y * blockDim.x) {
+    int i = t % z.nx, j = t / z.nx;
+    base[z.off + (long long)j * z.pitch + i] = 0.0;
+  }
+}
