@@ -231,6 +231,15 @@ int sg_op_AMRNorm(sg_op* op, const sg_field* coar_resid, const sg_field* fine_re
 int sg_op_reflux(sg_op* op, const sg_field* phi_fine, const sg_field* phi, sg_field* residual, sg_op* finer_op);
 /* QuadCFInterp::coarseFineInterp as used by the op (m_interpWithCoarser) */
 int sg_op_cfInterp(sg_op* op, sg_field* phi, const sg_field* phi_coarse);
+/* createCoarsened (src/AMRNonLinearPoissonOp.cpp:543-554): a field on this level's grids coarsened by ref_rat -- where
+   AMRRestrictS writes (AMRMultiGrid's m_resC) */
+int sg_op_createCoarsened(sg_op* op, sg_field** out, const sg_field* fine, int ref_rat);
+/* zeroCovered (src/AMRNonLinearPoissonOp.cpp:531-541 via m_levelOps): zero the cells of `coarse` that lie under the level
+   `fine_any` lives on */
+int sg_op_zeroCovered(sg_op* op, sg_field* coarse, const sg_field* fine_any);
+/* LevelData::copyTo between two layouts of one index space (e.g. m_resC -> the coarser level's residual): every cell of
+   dst's valid regions grown by `ghosts` that a valid region of src holds (periodic images included) */
+int sg_field_copyTo(sg_field* dst, const sg_field* src, int ghosts);
 
 /* ------------------------------------------------------------------ whole solve -------------------------- */
 /* AMRFASMultiGrid::define + setSolverParameters + solve as driven by AmrHydro::SolveForHead_nl

@@ -78,7 +78,9 @@ class DisjointBoxLayout:
         self.domain = np.ascontiguousarray(domain, dtype=np.int32)
         self.periodic = np.ascontiguousarray(periodic, dtype=np.int32)
         self.owner = None if owner is None else np.ascontiguousarray(owner, dtype=np.int32)
-        if _h is None:
+        if _h is False:
+            _h = None
+        elif _h is None:
             _h = C.c_void_p()
             check(lib().sg_layout_create(ctx.h, C.byref(_h), len(self.boxes), _ip(self.boxes),
                                          None if self.owner is None else _ip(self.owner), _ip(self.domain), _ip(self.periodic)))
@@ -180,6 +182,10 @@ class LevelData:
 
     def exchange(self, corners=True):
         check(lib().sg_exchange(self.h, int(corners)))
+
+    def copyTo(self, dst, ghosts=0):
+        """LevelData::copyTo onto another layout of the same index space"""
+        check(lib().sg_field_copyTo(dst.h, self.h, ghosts))
 
     def destroy(self):
         if self.h:
@@ -306,6 +312,48 @@ class VCAMRNonLinearPoissonOp:
         check(lib().sg_op_localMaxNorm(self.h, x.h, C.byref(out)))
         return out.value
 
+    # ---- AMRLevelOp surface (src/AMRNonLinearPoissonOp.cpp:889-1264); None stands for an undefined LevelData / NULL op
+    def AMRResidual(self, residual, phiFine, phi, phiCoarse, rhs, homogeneousPhysBC, finerOp):
+        check(lib().sg_op_AMRResidual(self.h, residual.h, _h(phiFine), phi.h, _h(phiCoarse), rhs.h, int(homogeneousPhysBC), _h(finerOp)))
+
+    def AMRResidualNF(self, residual, phi, phiCoarse, rhs, homogeneousPhysBC):
+        check(lib().sg_op_AMRResidualNF(self.h, residual.h, phi.h, _h(phiCoarse), rhs.h, int(homogeneousPhysBC)))
+
+    def AMROperator(self, LofPhi, phiFine, phi, phiCoarse, homogeneousPhysBC, finerOp):
+        check(lib().sg_op_AMROperator(self.h, LofPhi.h, _h(phiFine), phi.h, _h(phiCoarse), int(homogeneousPhysBC), _h(finerOp)))
+
+    def AMROperatorNF(self, LofPhi, phi, phiCoarse, homogeneousPhysBC):
+        check(lib().sg_op_AMROperatorNF(self.h, LofPhi.h, phi.h, _h(phiCoarse), int(homogeneousPhysBC)))
+
+    def AMRRestrictS(self, resCoarse, residual, correction, coarseCorrection, scratch, skip_res=False):
+        check(lib().sg_op_AMRRestrictS(self.h, resCoarse.h, residual.h, _h(correction), _h(coarseCorrection), scratch.h, int(skip_res)))
+
+    def AMRProlongS(self, correction, coarseCorrection):
+        check(lib().sg_op_AMRProlongS(self.h, correction.h, coarseCorrection.h))
+
+    def AMRProlongS_2(self, correction, coarseCorrection, crseOp):
+        check(lib().sg_op_AMRProlongS_2(self.h, correction.h, coarseCorrection.h, crseOp.h))
+
+    def AMRUpdateResidual(self, residual, correction, coarseCorrection):
+        check(lib().sg_op_AMRUpdateResidual(self.h, residual.h, correction.h, _h(coarseCorrection)))
+
+    def reflux(self, phiFine, phi, residual, finerOp):
+        check(lib().sg_op_reflux(self.h, phiFine.h, phi.h, residual.h, finerOp.h))
+
+    def coarseFineInterp(self, phi, phiCoarse):
+        """m_interpWithCoarser.coarseFineInterp(phi, phiCoarse)"""
+        check(lib().sg_op_cfInterp(self.h, phi.h, phiCoarse.h))
+
+    def createCoarsened(self, fine, refRat=2):
+        h = C.c_void_p()
+        check(lib().sg_op_createCoarsened(self.h, C.byref(h), fine.h, refRat))
+        lay = DisjointBoxLayout(fine.layout.ctx, fine.layout.boxes // refRat, fine.layout.domain // refRat, fine.layout.periodic,
+                                fine.layout.owner, _h=False)  # python-side description only: the C layout belongs to the operator
+        return LevelData(lay, fine.ncomp, fine.ng, CELL, _h=h)
+
+    def zeroCovered(self, coarse, fineAny):
+        check(lib().sg_op_zeroCovered(self.h, coarse.h, fineAny.h))
+
     def AMRResidualNC(self, residual, phiFine, phi, rhs, homogeneousPhysBC, finerOp):
         check(lib().sg_op_AMRResidualNC(self.h, residual.h, _h(phiFine), phi.h, rhs.h, int(homogeneousPhysBC), _h(finerOp)))
 
@@ -355,6 +403,9 @@ class VCAMRNonLinearPoissonOpFactory:
         check(lib().sg_factory_AMRnewOp(self.h, level, C.byref(h)))
         return VCAMRNonLinearPoissonOp(h, self.grids[level])
 
+    def define_levels(self, *a, **k):
+        return self.define(*a, **k)
+
     def refToFiner(self, level):
         out = C.c_int()
         check(lib().sg_factory_refToFiner(self.h, level, C.byref(out)))
@@ -395,9 +446,11 @@ class AMRFASMultiGrid:
         check(lib().sg_solver_cell_updates_per_cycle(self.h, C.byref(self.params), C.byref(out)))
         return out.value
 
-    def solve(self, phi, rhs, l_max=0, l_base=0, fixed_cycles=0):
+    def solve(self, phi, rhs, l_max=None, l_base=0, fixed_cycles=0):
         """phi, rhs: lists of LevelData per level.  Returns (iterations, residual-norm history, stats)."""
         self.params.fixed_cycles = fixed_cycles
+        if l_max is None:
+            l_max = len(phi) - 1
         n = max(self.params.max_iter, fixed_cycles) + 2
         hist = np.zeros(n)
         stats = capi.SolveStats()

@@ -78,7 +78,8 @@ SIGNATURES = {
     "sg_op_AMROperatorNC": [vp, vp, vp, vp, ci, vp], "sg_op_AMROperatorNF": [vp, vp, vp, vp, ci],
     "sg_op_AMRRestrictS": [vp, vp, vp, vp, vp, vp, ci], "sg_op_AMRProlongS": [vp, vp, vp],
     "sg_op_AMRProlongS_2": [vp, vp, vp, vp], "sg_op_AMRUpdateResidual": [vp, vp, vp, vp],
-    "sg_op_AMRNorm": [vp, vp, vp, ci, ci, dp], "sg_op_reflux": [vp, vp, vp, vp, vp], "sg_op_cfInterp": [vp, vp, vp],
+    "sg_op_AMRNorm": [vp, vp, vp, ci, ci, dp], "sg_op_reflux": [vp, vp, vp, vp, vp], "sg_op_cfInterp": [vp, vp, vp], "sg_op_createCoarsened": [vp, pvp, vp, ci], "sg_op_zeroCovered": [vp, vp, vp],
+    "sg_field_copyTo": [vp, vp, ci],
     "sg_solver_define": [vp, pvp, ci], "sg_solver_destroy": [vp], "sg_solver_depth": [vp, ci, ip],
     "sg_solver_solve": [vp, pvp, pvp, ci, ci, C.POINTER(SolverParams), dp, C.POINTER(SolveStats)],
     "sg_solver_cell_updates_per_cycle": [vp, C.POINTER(SolverParams), dp],

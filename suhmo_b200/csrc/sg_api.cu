@@ -133,7 +133,11 @@ struct sg_factory {
   std::vector<sg_field*> aCoef, bX, bY, B, Pi, zb, mask;
 };
 
+struct AmrLink;
+struct FineLink;
 struct sg_op {
+  AmrLink* link = nullptr;   // coarse-fine interpolator etc. (levels above the base)
+  FineLink* flink = nullptr; // flux register / covered cells with respect to the next finer level
   sg_ctx* ctx;
   sg_layout* lay;
   double dx[2];
@@ -151,9 +155,12 @@ struct sg_solver {
   sg_ctx* ctx;
   sg_factory* fac;
   int num_levels;
-  std::vector<sg_op*> ops;                          // MG depths of level 0
+  std::vector<sg_op*> ops;                          // MG depths of level 0 (ops[0] is the base AMR level's operator)
   std::vector<sg_field*> phi, rhs, save, tmp;       // per depth (depth 0 entries unused except tmp/resid)
-  sg_field* resid = nullptr;
+  sg_field* resid = nullptr;                        // = aresid[0]
+  // AMR levels (index = level; entry 0 of aops aliases ops[0])
+  std::vector<sg_op*> aops;
+  std::vector<sg_field*> aresid, acorr, atmp, ascratch, aresC;
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -510,9 +517,11 @@ extern "C" int sg_layout_nbox(const sg_layout* L, int* nbox) {
   return SG_OK;
 }
 extern "C" int sg_field_destroy(sg_field* f);
+static void copy_plans_forget(const sg_layout* L);
 extern "C" int sg_layout_destroy(sg_layout* L) {
   if (!L) return SG_OK;
   for (sg_field* w : L->ws) sg_field_destroy(w);
+  copy_plans_forget(L);
   cudaFree(L->d_patches);
   cudaFree(L->ex_faces.d);
   for (int k = 0; k < 3; k++) cudaFree(L->ex_full[k].d);
@@ -576,14 +585,15 @@ static int upload_rects(const sg_field* f, int b, Box out[5]) {
   Box F = fab_rect(f, b, f->ng), V = fab_rect(f, b, 0), Pv = patch_rect(f);
   out[n++] = V;
   if (f->ng == 0) return n;
+  // Ghost cells outside the merged patch exist once, but several boxes' FArrayBoxes overlap there: a cell of the strip
+  // below/above (left/right of) the patch is taken from the box whose valid columns (rows) contain it, and a corner of
+  // the patch from the box at that corner -- the box for which the cell is a FACE ghost, not a corner ghost.
   Box r;
-  if (F.lo[1] < Pv.lo[1]) { r = F; r.hi[1] = Pv.lo[1] - 1; out[n++] = r; }
-  if (F.hi[1] > Pv.hi[1]) { r = F; r.lo[1] = Pv.hi[1] + 1; out[n++] = r; }
-  int m0 = std::max(F.lo[1], Pv.lo[1]), m1 = std::min(F.hi[1], Pv.hi[1]);
-  if (m0 <= m1) {
-    if (F.lo[0] < Pv.lo[0]) { r = F; r.lo[1] = m0; r.hi[1] = m1; r.hi[0] = Pv.lo[0] - 1; out[n++] = r; }
-    if (F.hi[0] > Pv.hi[0]) { r = F; r.lo[1] = m0; r.hi[1] = m1; r.lo[0] = Pv.hi[0] + 1; out[n++] = r; }
-  }
+  const int x0 = F.lo[0] < Pv.lo[0] ? F.lo[0] : V.lo[0], x1 = F.hi[0] > Pv.hi[0] ? F.hi[0] : V.hi[0];
+  if (F.lo[1] < Pv.lo[1]) { r = F; r.lo[0] = x0; r.hi[0] = x1; r.hi[1] = Pv.lo[1] - 1; out[n++] = r; }
+  if (F.hi[1] > Pv.hi[1]) { r = F; r.lo[0] = x0; r.hi[0] = x1; r.lo[1] = Pv.hi[1] + 1; out[n++] = r; }
+  if (F.lo[0] < Pv.lo[0]) { r = V; r.lo[0] = F.lo[0]; r.hi[0] = Pv.lo[0] - 1; out[n++] = r; }
+  if (F.hi[0] > Pv.hi[0]) { r = V; r.hi[0] = F.hi[0]; r.lo[0] = Pv.hi[0] + 1; out[n++] = r; }
   return n;
 }
 // element offset from the component base of global index (gi,gj) in the array of the patch that holds box b
@@ -815,14 +825,18 @@ static int phys_bc(sg_field* f, const sg_bc* bc, const double dx[2], int homogen
   return SG_OK;
 }
 
+static int exchange_g(sg_field* f, int depth, int corners);
+static int phys_bc_any(sg_field* f, const sg_bc* bc, const double dx[2], int homogeneous);
+static int extrap_any(sg_field* f, int copy_only);
 extern "C" int sg_exchange(sg_field* f, int corners) {
   REQUIRE(f, "sg_exchange: null");
-  (void)corners; // rows/columns are moved at full width, so corner ghosts are always consistent
+  // streaming-path layouts move rows/columns at full width, so corner ghosts are always consistent there
+  if (!f->lay->fast) return f->lay->has_local ? exchange_g(f, std::max(1, std::min(f->ng, 2)), corners) : SG_OK;
   return fill_ghosts(f, std::max(1, std::min(f->ng, 2)));
 }
 extern "C" int sg_apply_bc(sg_field* f, const sg_bc* bc, const double dx[2], int homogeneous) {
   REQUIRE(f && bc && dx, "sg_apply_bc: null");
-  return phys_bc(f, bc, dx, homogeneous);
+  return phys_bc_any(f, bc, dx, homogeneous);
 }
 static int extrap_ghost(sg_field* f, int copy_only) {
   sg_layout* L = f->lay;
@@ -835,8 +849,10 @@ static int extrap_ghost(sg_field* f, int copy_only) {
   }
   return SG_OK;
 }
-extern "C" int sg_extrap_ghost_cells(sg_field* f) { REQUIRE(f, "null"); return extrap_ghost(f, 0); }
-extern "C" int sg_copy_ghost_cells(sg_field* f) { REQUIRE(f, "null"); return extrap_ghost(f, 1); }
+extern "C" int sg_extrap_ghost_cells(sg_field* f) { REQUIRE(f, "null"); return extrap_any(f, 0); }
+extern "C" int sg_copy_ghost_cells(sg_field* f) { REQUIRE(f, "null"); return extrap_any(f, 1); }
+
+#include "sg_general_host.inc"
 
 // ------------------------------------------------------------------------------------------------
 // stand-alone field kernels
@@ -846,55 +862,74 @@ extern "C" int sg_nonlinear_level(const sg_params* p, sg_field* nl, sg_field* dn
   REQUIRE(p && nl && dnl && u && B && mask && Pi && zb, "sg_nonlinear_level: null");
   sg_layout* L = u->lay;
   if (!L->has_local) return SG_OK;
-  Geom g = make_geom(L, nullptr);
-  LAUNCH(L->ctx, k_nl, grid2(g.nx, g.ny, B2D), B2D, nl->p(), dnl->p(), u->p(), B->p(), mask->p(), Pi->p(), zb->p(), g, phys(*p));
+  LAUNCH(L->ctx, k_nl_g, grid_g(L, 0, 0), B2D, nl->cb(), dnl->cb(), u->cb(), B->cb(), mask->cb(), Pi->cb(), zb->cb(), L->d_patches, phys(*p));
+  return SG_OK;
+}
+static int gradient_cc_any(sg_field* grad2, sg_field* phi, const sg_field* mask, const double dx[2]) {
+  sg_layout* L = phi->lay;
+  if (!L->has_local) return SG_OK;
+  LAUNCH(L->ctx, k_gradient_cc_g, grid_g(L, 0, 0), B2D, grad2->cb(0), grad2->cb(1), phi->cb(), mask ? mask->cb() : nullptr, L->d_patches, dx[0], dx[1]);
   return SG_OK;
 }
 extern "C" int sg_gradient_cc(sg_field* grad2, sg_field* phi, const sg_field* mask, const double dx[2]) {
   REQUIRE(grad2 && phi && dx && grad2->ncomp >= 2, "sg_gradient_cc: bad arguments");
-  sg_layout* L = phi->lay;
-  if (!L->has_local) return SG_OK;
-  Geom g = make_geom(L, nullptr);
-  LAUNCH(L->ctx, k_gradient_cc, grid2(g.nx, g.ny, B2D), B2D, grad2->p(0), grad2->p(1), phi->p(), mask ? mask->p() : nullptr, g, dx[0], dx[1]);
-  return SG_OK;
+  return gradient_cc_any(grad2, phi, mask, dx);
 }
 extern "C" int sg_compute_re(const sg_params* p, sg_field* Re, const sg_field* B, const sg_field* gradH) {
   REQUIRE(p && Re && B && gradH && gradH->ncomp >= 2, "sg_compute_re: bad arguments");
   sg_layout* L = Re->lay;
   if (!L->has_local) return SG_OK;
-  Geom g = make_geom(L, nullptr);
-  LAUNCH(L->ctx, k_compute_re, grid2(g.nx + 2, g.ny + 2, B2D), B2D, Re->p(), B->p(), gradH->p(0), gradH->p(1), g, phys(*p));
+  LAUNCH(L->ctx, k_compute_re_g, grid_g(L, 2, 2), B2D, Re->cb(), B->cb(), gradH->cb(0), gradH->cb(1), L->d_patches, phys(*p));
   return SG_OK;
 }
 extern "C" int sg_divergence(sg_field* div, const sg_field* ux, const sg_field* uy, const double dx[2]) {
   REQUIRE(div && ux && uy && dx, "sg_divergence: null");
   sg_layout* L = div->lay;
   if (!L->has_local) return SG_OK;
-  Geom g = make_geom(L, nullptr);
-  LAUNCH(L->ctx, k_divergence, grid2(g.nx, g.ny, B2D), B2D, div->p(), ux->p(), uy->p(), g, dx[0], dx[1]);
+  LAUNCH(L->ctx, k_divergence_g, grid_g(L, 0, 0), B2D, div->cb(), ux->cb(), uy->cb(), L->d_patches, dx[0], dx[1]);
   return SG_OK;
 }
 
-// AmrHydro::WFlx_level (src/AmrHydro.cpp:1415-1539), no coarser level
-extern "C" int sg_wflx_level(sg_ctx* ctx, const sg_params* p, sg_field* bX, sg_field* bY, sg_field* u, const sg_field* u_coarse,
-                             const sg_field* B, const sg_field* mask, const double dx[2]) {
-  REQUIRE(ctx && p && bX && bY && u && B && mask && dx, "sg_wflx_level: null");
-  if (u_coarse) return fail(SG_ERR_UNSUPPORTED, "sg_wflx_level: coarse-fine gradient interpolation not built yet");
+// AmrHydro::WFlx_level (src/AmrHydro.cpp:1415-1539).  With a coarser level (op->link): coarse gradient with dx*2 and the
+// coarse level's ice mask, exchange + ExtrapGhostCells, QuadCFInterp of both components into the fine coarse-fine ghosts.
+static int wflx_impl(sg_ctx* ctx, sg_op* op, const sg_params* p, sg_field* bX, sg_field* bY, sg_field* u, sg_field* u_coarse,
+                     const sg_field* B, const sg_field* mask, const double dx[2]) {
   sg_layout* L = u->lay;
   if (!L->has_local) return SG_OK;
-  Geom g = make_geom(L, nullptr);
   sg_field *grad, *Re;
   SGCALL(ws_field(L, 1, 2, &grad));
   SGCALL(ws_field(L, 2, 1, &Re));
-  LAUNCH(ctx, k_gradient_cc, grid2(g.nx, g.ny, B2D), B2D, grad->p(0), grad->p(1), u->p(), p->use_mask_grad ? mask->p() : nullptr, g, dx[0], dx[1]);
+  SGCALL(gradient_cc_any(grad, u, p->use_mask_grad ? mask : nullptr, dx));
   int ngsave = grad->ng;
   grad->ng = 1;
-  SGCALL(fill_ghosts(grad, 1)); // lvlgradH.exchange()
-  SGCALL(extrap_ghost(grad, 0)); // ExtrapGhostCells(lvlgradH, levelDomain)
+  if (u_coarse) {
+    REQUIRE(op && op->link, "WFlx_level: a coarse head needs the operator's coarse-fine interpolator (use sg_op_UpdateOperator)");
+    sg_layout* Lc = u_coarse->lay;
+    sg_field* gradC;
+    SGCALL(ws_field(Lc, 3, 2, &gradC));
+    double dxc[2] = {dx[0] * 2, dx[1] * 2}; // "assumes refRatio = 2" (src/AmrHydro.cpp:1467)
+    SGCALL(gradient_cc_any(gradC, u_coarse, p->use_mask_grad ? op->link->crse_mask : nullptr, dxc));
+    int ngc = gradC->ng;
+    gradC->ng = 1;
+    SGCALL(exchange_any(gradC, 1, 1));
+    SGCALL(extrap_any(gradC, 0));
+    gradC->ng = ngc;
+    SGCALL(cf_interp_impl(op, grad, gradC));
+  }
+  SGCALL(exchange_any(grad, 1, 1)); // lvlgradH.exchange()
+  SGCALL(extrap_any(grad, 0));      // ExtrapGhostCells(lvlgradH, levelDomain)
   grad->ng = ngsave;
-  LAUNCH(ctx, k_compute_re, grid2(g.nx + 2, g.ny + 2, B2D), B2D, Re->p(), B->p(), grad->p(0), grad->p(1), g, phys(*p));
-  LAUNCH(ctx, k_bcoef_faces, grid2(g.nx + 1, g.ny + 1, B2D), B2D, bX->p(), bY->p(), Re->p(), B->p(), mask->p(), g, phys(*p));
+  LAUNCH(ctx, k_compute_re_g, grid_g(L, 2, 2), B2D, Re->cb(), B->cb(), grad->cb(0), grad->cb(1), L->d_patches, phys(*p));
+  LAUNCH(ctx, k_bcoef_faces_g, grid_g(L, 1, 1), B2D, bX->cb(), bY->cb(), Re->cb(), B->cb(), mask->cb(), L->d_patches, phys(*p),
+         L->domain.lo[0], L->domain.lo[1], L->domain.hi[0], L->domain.hi[1]);
   return SG_OK;
+}
+extern "C" int sg_wflx_level(sg_ctx* ctx, const sg_params* p, sg_field* bX, sg_field* bY, sg_field* u, const sg_field* u_coarse,
+                             const sg_field* B, const sg_field* mask, const double dx[2]) {
+  REQUIRE(ctx && p && bX && bY && u && B && mask && dx, "sg_wflx_level: null");
+  if (u_coarse) return fail(SG_ERR_UNSUPPORTED, "sg_wflx_level: with a coarse head the coarse-fine stencils of the level's operator "
+                                                "are needed; call sg_op_UpdateOperator(op, phi, phi_coarse, ...)");
+  return wflx_impl(ctx, nullptr, p, bX, bY, u, nullptr, B, mask, dx);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -959,6 +994,8 @@ extern "C" int sg_op_destroy(sg_op* op) {
     sg_field_destroy(op->aCoef); sg_field_destroy(op->bX); sg_field_destroy(op->bY);
     sg_field_destroy(op->B); sg_field_destroy(op->Pi); sg_field_destroy(op->zb); sg_field_destroy(op->mask);
   }
+  amr_link_free(op->link);
+  fine_link_free(op->flink);
   if (op->owns_layout) sg_layout_destroy(op->lay);
   delete op;
   return SG_OK;
@@ -1035,8 +1072,15 @@ extern "C" int sg_factory_MGnewOp(sg_factory* f, int level, int depth, int homo_
 }
 extern "C" int sg_factory_AMRnewOp(sg_factory* f, int level, sg_op** out) {
   REQUIRE(f && out && level >= 0 && level < f->nlevels, "sg_factory_AMRnewOp: bad arguments");
-  if (f->nlevels > 1) return fail(SG_ERR_UNSUPPORTED, "AMRnewOp: multi-level hierarchies are not built yet");
-  return sg_factory_MGnewOp(f, level, 0, 0, out);
+  SGCALL(sg_factory_MGnewOp(f, level, 0, 0, out));
+  // the four defines of src/VCAMRNonLinearPoissonOp.cpp:1215-1253 differ in which neighbours exist: a coarser level brings
+  // the QuadCFInterp + coarsened-fine scratch; the flux register towards a finer level is built on first use (reflux)
+  if (level > 0) {
+    REQUIRE(f->ref_ratios[level - 1] == 2, "AMRnewOp: refinement ratio 2 only (WFlx_level assumes it, src/AmrHydro.cpp:1467)");
+    int r = amr_link_build(*out, f->grids[level - 1], f->mask[level - 1]);
+    if (r != SG_OK) { sg_op_destroy(*out); *out = nullptr; return r; }
+  }
+  return SG_OK;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1044,8 +1088,9 @@ extern "C" int sg_factory_AMRnewOp(sg_factory* f, int level, sg_op** out) {
 // ------------------------------------------------------------------------------------------------
 static int check_same(const sg_op* op, const sg_field* f, const char* what) {
   if (!f) return fail(SG_ERR_INVALID, "%s: null field", what);
-  if (f->lay != op->lay && (f->lay->nx != op->lay->nx || f->lay->ny != op->lay->ny || f->lay->patch.lo[0] != op->lay->patch.lo[0] ||
-                            f->lay->patch.lo[1] != op->lay->patch.lo[1]))
+  const sg_layout *A = f->lay, *B = op->lay;
+  if (A != B && (A->total != B->total || A->patches.size() != B->patches.size() || A->patch.lo[0] != B->patch.lo[0] ||
+                 A->patch.lo[1] != B->patch.lo[1] || A->nx != B->nx || A->ny != B->ny))
     return fail(SG_ERR_INVALID, "%s: field layout differs from the operator's", what);
   return SG_OK;
 }
@@ -1055,6 +1100,7 @@ static int relax_impl(sg_op* op, sg_field* phi, const sg_field* rhs, int iterati
   sg_layout* L = op->lay;
   sg_ctx* c = op->ctx;
   if (!L->has_local || iterations <= 0) return SG_OK;
+  if (!L->fast) return relax_g(op, phi, rhs, iterations);
   OpArgs a = make_args(op);
   bool ghosts = has_ghost_sides(L);
   if (c->relax_mode >= 1) {
@@ -1134,7 +1180,8 @@ extern "C" int sg_op_relax(sg_op* op, sg_field* phi, const sg_field* rhs, int it
 extern "C" int sg_op_relaxNF(sg_op* op, sg_field* phi, const sg_field* phi_coarse, const sg_field* rhs, int iterations,
                              int amr_fasmg_iter, int depth, int print) {
   (void)print;
-  if (phi_coarse) return fail(SG_ERR_UNSUPPORTED, "relaxNF: coarse-fine interpolation not built yet");
+  REQUIRE(op && phi, "sg_op_relaxNF: null");
+  if (phi_coarse) SGCALL(cf_interp_impl(op, phi, phi_coarse));
   return sg_op_relax(op, phi, rhs, iterations, amr_fasmg_iter, depth);
 }
 
@@ -1143,6 +1190,7 @@ static int apply_impl(sg_op* op, sg_field* out, sg_field* phi, const sg_field* r
   sg_layout* L = op->lay;
   sg_ctx* c = op->ctx;
   if (!L->has_local) return SG_OK;
+  if (!L->fast) return apply_g(op, out, phi, rhs, homogeneous, mode, slot, true);
   OpArgs a = make_args(op);
   SGCALL(phys_bc(phi, &op->bc, op->dx, homogeneous));
   if (has_ghost_sides(L)) SGCALL(fill_ghosts(phi, 1));
@@ -1166,9 +1214,9 @@ extern "C" int sg_op_residual(sg_op* op, sg_field* lhs, sg_field* phi, const sg_
 }
 extern "C" int sg_op_residualNF(sg_op* op, sg_field* lhs, sg_field* phi, const sg_field* phi_coarse, const sg_field* rhs, int homogeneous) {
   REQUIRE(op, "sg_op_residualNF: null op");
-  if (phi_coarse) return fail(SG_ERR_UNSUPPORTED, "residualNF: coarse-fine interpolation not built yet");
   if (homogeneous) return fail(SG_ERR_ABORT, "VCAMRNonLinearPoissonOp::residualI homogeneous");
   SGCALL(check_same(op, lhs, "residualNF(lhs)")); SGCALL(check_same(op, phi, "residualNF(phi)")); SGCALL(check_same(op, rhs, "residualNF(rhs)"));
+  if (phi_coarse) SGCALL(cf_interp_impl(op, phi, phi_coarse));
   return apply_impl(op, lhs, phi, rhs, 0, 1, 0);
 }
 extern "C" int sg_op_applyOp(sg_op* op, sg_field* lhs, sg_field* phi, int homogeneous) {
@@ -1179,8 +1227,8 @@ extern "C" int sg_op_applyOp(sg_op* op, sg_field* lhs, sg_field* phi, int homoge
 }
 extern "C" int sg_op_applyOpMg(sg_op* op, sg_field* lhs, sg_field* phi, sg_field* phi_coarse, int homogeneous) {
   REQUIRE(op, "sg_op_applyOpMg: null op");
-  if (phi_coarse) return fail(SG_ERR_UNSUPPORTED, "applyOpMg: coarse-fine interpolation not built yet");
   SGCALL(check_same(op, lhs, "applyOpMg(lhs)")); SGCALL(check_same(op, phi, "applyOpMg(phi)"));
+  if (phi_coarse) SGCALL(cf_interp_impl(op, phi, phi_coarse)); // coarse domains of a single cell do not occur (block factor)
   return apply_impl(op, lhs, phi, nullptr, homogeneous, 0, 0); // applyOpI(lhs, phi, homogeneous)
 }
 extern "C" int sg_op_applyOpNoBoundary(sg_op* op, sg_field* lhs, sg_field* phi) {
@@ -1188,6 +1236,7 @@ extern "C" int sg_op_applyOpNoBoundary(sg_op* op, sg_field* lhs, sg_field* phi) 
   SGCALL(check_same(op, lhs, "applyOpNoBoundary(lhs)")); SGCALL(check_same(op, phi, "applyOpNoBoundary(phi)"));
   sg_layout* L = op->lay;
   if (!L->has_local) return SG_OK;
+  if (!L->fast) return apply_g(op, lhs, phi, nullptr, 0, 0, 0, false);
   OpArgs a = make_args(op);
   if (has_ghost_sides(L)) SGCALL(fill_ghosts(phi, 1));
   LAUNCH(op->ctx, k_apply<0>, grid2(L->nx, L->ny, B2D), B2D, lhs->p(), phi->p(), nullptr, a, nullptr);
@@ -1199,6 +1248,8 @@ static int restrict_impl(sg_op* op, sg_field* resC, sg_field* phiC, sg_field* ph
   sg_ctx* c = op->ctx;
   if (!L->has_local) return SG_OK;
   sg_layout* Lc = resC ? resC->lay : phiC->lay;
+  if (!L->fast || !Lc->fast) return fail(SG_ERR_UNSUPPORTED, "restrictResidual/restrictR: multigrid descent exists below the base AMR level only "
+                                                             "(levels above it use AMRRestrictS), and the base level is one patch per GPU");
   REQUIRE(Lc->nx * 2 == L->nx && Lc->ny * 2 == L->ny, "restrict: coarse layout is not the fine layout coarsened by 2");
   OpArgs a = make_args(op);
   if (resC) {
@@ -1216,7 +1267,7 @@ extern "C" int sg_op_restrictResidual(sg_op* op, sg_field* res_coarse, sg_field*
                                       const sg_field* rhs_fine, int homogeneous) {
   REQUIRE(op && res_coarse, "sg_op_restrictResidual: null");
   if (homogeneous) return fail(SG_ERR_ABORT, "VCAMRNonLinearPoissonOp::restrictResidual homogeneous");
-  if (phi_coarse) return fail(SG_ERR_UNSUPPORTED, "restrictResidual: coarse-fine interpolation not built yet");
+  if (phi_coarse) SGCALL(cf_interp_impl(op, phi_fine, phi_coarse));
   SGCALL(check_same(op, phi_fine, "restrictResidual(phiFine)")); SGCALL(check_same(op, rhs_fine, "restrictResidual(rhsFine)"));
   return restrict_impl(op, res_coarse, nullptr, phi_fine, rhs_fine);
 }
@@ -1230,6 +1281,7 @@ extern "C" int sg_op_prolongIncrement(sg_op* op, sg_field* phi, const sg_field* 
   SGCALL(check_same(op, phi, "prolongIncrement(phi)"));
   sg_layout* L = op->lay;
   if (!L->has_local) return SG_OK;
+  REQUIRE(L->fast && corr->lay->fast, "prolongIncrement: multigrid descent exists below the base AMR level only");
   REQUIRE(corr->lay->nx * 2 == L->nx && corr->lay->ny * 2 == L->ny, "prolongIncrement: coarse layout mismatch");
   LAUNCH(op->ctx, k_prolong, grid2(L->nx, L->ny, B2D), B2D, phi->p(), L->pitch, L->nx, L->ny, corr->p(), nullptr, corr->lay->pitch);
   return SG_OK;
@@ -1242,10 +1294,11 @@ extern "C" int sg_op_UpdateOperator(sg_op* op, sg_field* phi, const sg_field* ph
   SGCALL(check_same(op, phi, "UpdateOperator(phi)"));
   sg_layout* L = op->lay;
   if (!L->has_local) return SG_OK;
-  if (has_ghost_sides(L)) SGCALL(fill_ghosts(phi, 1));
-  SGCALL(phys_bc(phi, &op->bc, op->dx, 0));
-  SGCALL(sg_wflx_level(op->ctx, &op->prm, op->bX, op->bY, phi, phi_coarse, op->B, op->mask, op->dx));
-  SGCALL(coef_ghosts(op, true));
+  if (L->fast) { if (has_ghost_sides(L)) SGCALL(fill_ghosts(phi, 1)); }
+  else SGCALL(exchange_g(phi, 1, 0));
+  SGCALL(phys_bc_any(phi, &op->bc, op->dx, 0));
+  SGCALL(wflx_impl(op->ctx, op, &op->prm, op->bX, op->bY, phi, const_cast<sg_field*>(phi_coarse), op->B, op->mask, op->dx));
+  if (L->fast) SGCALL(coef_ghosts(op, true));
   return SG_OK; // lambda is recomputed inside the kernels
 }
 extern "C" int sg_op_AverageOperator(sg_op* op, const sg_op* finest, int depth) {
@@ -1264,7 +1317,7 @@ extern "C" int sg_op_lambda(sg_op* op, sg_field* lam) {
   SGCALL(check_same(op, lam, "lambda"));
   sg_layout* L = op->lay;
   if (!L->has_local) return SG_OK;
-  LAUNCH(op->ctx, k_lambda, grid2(L->nx, L->ny, B2D), B2D, lam->p(), make_args(op));
+  LAUNCH(op->ctx, k_lambda_g, grid_g(L, 0, 0), B2D, lam->cb(), L->d_patches, make_args_g(op));
   return SG_OK;
 }
 extern "C" int sg_op_createCoarser(sg_op* op, sg_field** coarse, const sg_field* fine, int ghosted) {
@@ -1287,6 +1340,7 @@ template <int OP>
 static int vec_launch(sg_field* y, const sg_field* x, const sg_field* z, double a, double b, bool whole) {
   sg_layout* L = y->lay;
   if (!L->has_local) return SG_OK;
+  if (!L->fast) return vec_g<OP>(y, x, z, a, b, whole);
   int ex = y->cent == SG_XFACE, ey = y->cent == SG_YFACE;
   int i0 = whole ? -y->ng : 0, i1 = L->nx + ex + (whole ? y->ng : 0), j0 = whole ? -y->ng : 0, j1 = L->ny + ey + (whole ? y->ng : 0);
   for (int c = 0; c < y->ncomp; c++)
@@ -1311,6 +1365,7 @@ static int reduce_local(const sg_field* x, const sg_field* y, int mode, int slot
   sg_ctx* c = L->ctx;
   CK(cudaMemsetAsync(c->d_scalar + slot, 0, sizeof(double), c->stream));
   if (!L->has_local) return SG_OK;
+  if (!L->fast) return reduce_g(x, y, mode, slot);
   dim3 g = grid2(L->nx, L->ny, B2D);
   size_t nb = (size_t)g.x * g.y;
   if (mode != 0 && c->partial_cap < nb) {
@@ -1355,44 +1410,137 @@ extern "C" int sg_op_dotProduct(sg_op* op, const sg_field* a, const sg_field* b,
   return fetch_scalar(op->ctx, 1, out);
 }
 
-// ---- AMR surface: declared, multi-level hierarchies come next ---------------------------------------
-#define AMR_UNSUPPORTED(name) return fail(SG_ERR_UNSUPPORTED, name ": multi-level (AMR) operators are not built yet")
-extern "C" int sg_op_AMRResidual(sg_op*, sg_field*, const sg_field*, sg_field*, const sg_field*, const sg_field*, int, sg_op*) { AMR_UNSUPPORTED("AMRResidual"); }
-extern "C" int sg_op_AMRResidualNC(sg_op* op, sg_field* residual, const sg_field* phi_fine, sg_field* phi, const sg_field* rhs, int hom, sg_op*) {
-  if (phi_fine) AMR_UNSUPPORTED("AMRResidualNC");
-  // no finer level: AMROperatorNC = applyOpI; residual = rhs - L(phi) (src/AMRNonLinearPoissonOp.cpp:906-920,977-993)
-  REQUIRE(op, "null op");
-  SGCALL(apply_impl(op, residual, phi, nullptr, hom, 0, 0));
-  return sg_op_axby(op, residual, residual, rhs, -1.0, 1.0);
+// ---- AMR surface (src/AMRNonLinearPoissonOp.cpp:889-1264, VCAMRNonLinearPoissonOp.cpp:555-652) ------------------------
+// AMROperator / NC / NF: coarse-fine interpolation (if a coarse phi is given), applyOpI, refluxing (if a fine phi is given)
+static int amr_operator_impl(sg_op* op, sg_field* lof, sg_field* phiFine, sg_field* phi, const sg_field* phiCoarse, int hom, sg_op* fop) {
+  if (phiCoarse) SGCALL(cf_interp_impl(op, phi, phiCoarse));
+  SGCALL(apply_impl(op, lof, phi, nullptr, hom, 0, 0));
+  if (phiFine) {
+    REQUIRE(fop, "AMROperator: a fine phi needs the finer operator (CH_assert(a_finerOp != NULL))");
+    SGCALL(reflux_impl(op, phiFine, phi, lof, fop));
+  }
+  return SG_OK;
+}
+static int amr_residual_impl(sg_op* op, sg_field* res, sg_field* phiFine, sg_field* phi, const sg_field* phiCoarse, const sg_field* rhs,
+                             int hom, sg_op* fop) {
+  if (!phiFine) { // AMRResidualNF: interpolate, then residualI (which aborts on homogeneous)
+    if (hom) return fail(SG_ERR_ABORT, "VCAMRNonLinearPoissonOp::residualI homogeneous");
+    if (phiCoarse) SGCALL(cf_interp_impl(op, phi, phiCoarse));
+    return apply_impl(op, res, phi, rhs, 0, 1, 0);
+  }
+  SGCALL(amr_operator_impl(op, res, phiFine, phi, phiCoarse, hom, fop));
+  return vec_launch<0>(res, res, rhs, -1.0, 1.0, false); // axby(residual, residual, rhs, -1, 1)
+}
+#define OPCHK(name) REQUIRE(op, name ": null op")
+extern "C" int sg_op_AMRResidual(sg_op* op, sg_field* residual, const sg_field* phi_fine, sg_field* phi, const sg_field* phi_coarse,
+                                 const sg_field* rhs, int hom, sg_op* finer_op) {
+  OPCHK("AMRResidual");
+  return amr_residual_impl(op, residual, const_cast<sg_field*>(phi_fine), phi, phi_coarse, rhs, hom, finer_op);
+}
+extern "C" int sg_op_AMRResidualNC(sg_op* op, sg_field* residual, const sg_field* phi_fine, sg_field* phi, const sg_field* rhs, int hom, sg_op* finer_op) {
+  OPCHK("AMRResidualNC");
+  SGCALL(amr_operator_impl(op, residual, const_cast<sg_field*>(phi_fine), phi, nullptr, hom, finer_op));
+  return vec_launch<0>(residual, residual, rhs, -1.0, 1.0, false);
 }
 extern "C" int sg_op_AMRResidualNF(sg_op* op, sg_field* residual, sg_field* phi, const sg_field* phi_coarse, const sg_field* rhs, int hom) {
-  if (phi_coarse) AMR_UNSUPPORTED("AMRResidualNF");
-  return sg_op_residualNF(op, residual, phi, nullptr, rhs, hom);
+  OPCHK("AMRResidualNF");
+  return amr_residual_impl(op, residual, nullptr, phi, phi_coarse, rhs, hom, nullptr);
 }
-extern "C" int sg_op_AMROperator(sg_op*, sg_field*, const sg_field*, sg_field*, const sg_field*, int, sg_op*) { AMR_UNSUPPORTED("AMROperator"); }
-extern "C" int sg_op_AMROperatorNC(sg_op* op, sg_field* lofphi, const sg_field* phi_fine, sg_field* phi, int hom, sg_op*) {
-  if (phi_fine) AMR_UNSUPPORTED("AMROperatorNC");
-  REQUIRE(op, "null op");
-  return apply_impl(op, lofphi, phi, nullptr, hom, 0, 0);
+extern "C" int sg_op_AMROperator(sg_op* op, sg_field* lofphi, const sg_field* phi_fine, sg_field* phi, const sg_field* phi_coarse, int hom, sg_op* finer_op) {
+  OPCHK("AMROperator");
+  return amr_operator_impl(op, lofphi, const_cast<sg_field*>(phi_fine), phi, phi_coarse, hom, finer_op);
+}
+extern "C" int sg_op_AMROperatorNC(sg_op* op, sg_field* lofphi, const sg_field* phi_fine, sg_field* phi, int hom, sg_op* finer_op) {
+  OPCHK("AMROperatorNC");
+  return amr_operator_impl(op, lofphi, const_cast<sg_field*>(phi_fine), phi, nullptr, hom, finer_op);
 }
 extern "C" int sg_op_AMROperatorNF(sg_op* op, sg_field* lofphi, sg_field* phi, const sg_field* phi_coarse, int hom) {
-  if (phi_coarse) AMR_UNSUPPORTED("AMROperatorNF");
-  REQUIRE(op, "null op");
-  return apply_impl(op, lofphi, phi, nullptr, hom, 0, 0);
+  OPCHK("AMROperatorNF");
+  return amr_operator_impl(op, lofphi, nullptr, phi, phi_coarse, hom, nullptr);
 }
-extern "C" int sg_op_AMRRestrictS(sg_op*, sg_field*, const sg_field*, sg_field*, const sg_field*, sg_field*, int) { AMR_UNSUPPORTED("AMRRestrictS"); }
-extern "C" int sg_op_AMRProlongS(sg_op*, sg_field*, const sg_field*) { AMR_UNSUPPORTED("AMRProlongS"); }
-extern "C" int sg_op_AMRProlongS_2(sg_op*, sg_field*, const sg_field*, sg_op*) { AMR_UNSUPPORTED("AMRProlongS_2"); }
+// createCoarsened (src/AMRNonLinearPoissonOp.cpp:543-554): a field on this level's boxes coarsened by the ratio to the coarser level
+extern "C" int sg_op_createCoarsened(sg_op* op, sg_field** out, const sg_field* fine, int ref_rat) {
+  REQUIRE(op && out && fine && op->link, "createCoarsened: operator has no coarser level");
+  REQUIRE(ref_rat == 2, "createCoarsened: refinement ratio 2 only");
+  return sg_field_create(op->link->clay, out, fine->ncomp, fine->ng, SG_CELL);
+}
+// AMRRestrictS (:1027-1069): res_coarse lives on the coarsened-fine layout (createCoarsened)
+static int amr_restrict_impl(sg_op* op, sg_field* resC, const sg_field* residual, sg_field* correction, const sg_field* coarseCorrection,
+                             sg_field* scratch, int skip_res) {
+  REQUIRE(op->link, "AMRRestrictS: operator has no coarser level");
+  sg_layout* L = op->lay;
+  REQUIRE(resC->lay->patches.size() == L->patches.size(), "AMRRestrictS: res_coarse must live on the coarsened fine layout");
+  if (!skip_res) SGCALL(amr_residual_impl(op, scratch, nullptr, correction, coarseCorrection, residual, 0, nullptr));
+  else SGCALL(vec_launch<3>(scratch, residual, nullptr, 0, 0, true)); // assignLocal
+  sg_layout* Lc = resC->lay;
+  dim3 g((Lc->max_nx + B2D.x - 1) / B2D.x, (Lc->max_ny + B2D.y - 1) / B2D.y, (unsigned)Lc->patches.size());
+  LAUNCH(op->ctx, k_amr_average, g, B2D, resC->cb(), Lc->d_patches, scratch->cb(), L->d_patches);
+  return SG_OK;
+}
+extern "C" int sg_op_AMRRestrictS(sg_op* op, sg_field* res_coarse, const sg_field* residual, sg_field* correction,
+                                  const sg_field* coarse_correction, sg_field* scratch, int skip_res) {
+  REQUIRE(op && res_coarse && residual && scratch, "AMRRestrictS: null");
+  return amr_restrict_impl(op, res_coarse, residual, correction, coarse_correction, scratch, skip_res);
+}
+// AMRProlongS / AMRProlongS_2 (:1105-1206): the coarsened-fine scratch and its copiers are the operator's own
+static int amr_prolong_impl(sg_op* op, sg_field* correction, const sg_field* coarseCorrection, sg_op* crseOp, int second_order) {
+  AmrLink* K = op->link;
+  REQUIRE(K, "AMRProlong: operator has no coarser level");
+  sg_ctx* c = op->ctx;
+  sg_layout* L = op->lay;
+  if (second_order) {
+    REQUIRE(crseOp, "AMRProlongS_2: needs the coarser operator");
+    SGCALL(run_plan(c, K->temp->cb(), coarseCorrection->cb(), K->c2t[1]));
+    int ngs = K->temp->ng;
+    K->temp->ng = 1;
+    SGCALL(phys_bc_any(K->temp, &crseOp->bc, crseOp->dx, 0)); // m_use_FAS: inhomogeneous coarse BC on the scratch
+    K->temp->ng = ngs;
+    sg_field one = *K->temp;
+    one.ncomp = 1;
+    SGCALL(exchange_any(&one, 1, 1)); // CornerCopier exchange among the scratch's boxes
+  } else SGCALL(run_plan(c, K->temp->cb(), coarseCorrection->cb(), K->c2t[0]));
+  LAUNCH(c, k_amr_prolong, grid_g(L, 0, 0), B2D, correction->cb(), L->d_patches, K->temp->cb(), K->clay->d_patches, second_order);
+  return SG_OK;
+}
+extern "C" int sg_op_AMRProlongS(sg_op* op, sg_field* correction, const sg_field* coarse_correction) {
+  REQUIRE(op && correction && coarse_correction, "AMRProlongS: null");
+  return amr_prolong_impl(op, correction, coarse_correction, nullptr, 0);
+}
+extern "C" int sg_op_AMRProlongS_2(sg_op* op, sg_field* correction, const sg_field* coarse_correction, sg_op* coarse_op) {
+  REQUIRE(op && correction && coarse_correction, "AMRProlongS_2: null");
+  return amr_prolong_impl(op, correction, coarse_correction, coarse_op, 1);
+}
 extern "C" int sg_op_AMRUpdateResidual(sg_op* op, sg_field* residual, sg_field* correction, const sg_field* coarse_correction) {
-  if (coarse_correction) AMR_UNSUPPORTED("AMRUpdateResidual");
-  return sg_op_residualNF(op, residual, correction, nullptr, residual, 0);
+  OPCHK("AMRUpdateResidual");
+  return amr_residual_impl(op, residual, nullptr, correction, coarse_correction, residual, 0, nullptr);
 }
-extern "C" int sg_op_AMRNorm(sg_op* op, const sg_field* coar, const sg_field* fine, int, int ord, double* out) {
-  if (fine) AMR_UNSUPPORTED("AMRNorm");
-  return sg_op_norm(op, coar, ord, out);
+extern "C" int sg_op_zeroCovered(sg_op* op, sg_field* coarse, const sg_field* fine_any) {
+  REQUIRE(op && coarse && fine_any, "zeroCovered: null");
+  return zero_covered_impl(op, coarse, fine_any->lay);
 }
-extern "C" int sg_op_reflux(sg_op*, const sg_field*, const sg_field*, sg_field*, sg_op*) { AMR_UNSUPPORTED("reflux"); }
-extern "C" int sg_op_cfInterp(sg_op*, sg_field*, const sg_field*) { AMR_UNSUPPORTED("coarseFineInterp"); }
+extern "C" int sg_op_AMRNorm(sg_op* op, const sg_field* coar, const sg_field* fine, int ref_rat, int ord, double* out) {
+  OPCHK("AMRNorm");
+  if (!fine) return sg_op_norm(op, coar, ord, out);
+  REQUIRE(ref_rat == 2, "AMRNorm: refinement ratio 2 only");
+  sg_field* tmp;
+  SGCALL(ws_field(op->lay, 4, 1, &tmp));
+  SGCALL(vec_launch<3>(tmp, coar, nullptr, 0, 0, false));
+  SGCALL(zero_covered_impl(op, tmp, fine->lay));
+  return sg_op_norm(op, tmp, ord, out);
+}
+extern "C" int sg_op_reflux(sg_op* op, const sg_field* phi_fine, const sg_field* phi, sg_field* residual, sg_op* finer_op) {
+  REQUIRE(op && phi_fine && phi && residual && finer_op, "reflux: null");
+  return reflux_impl(op, const_cast<sg_field*>(phi_fine), phi, residual, finer_op);
+}
+extern "C" int sg_op_cfInterp(sg_op* op, sg_field* phi, const sg_field* phi_coarse) {
+  REQUIRE(op && phi && phi_coarse, "coarseFineInterp: null");
+  return cf_interp_impl(op, phi, phi_coarse);
+}
+// LevelData::copyTo between two layouts of the same index space (valid cells of dst, grown by `ghosts` cells)
+extern "C" int sg_field_copyTo(sg_field* dst, const sg_field* src, int ghosts) {
+  REQUIRE(dst && src && ghosts >= 0 && ghosts <= 2, "sg_field_copyTo: bad arguments");
+  return copy_to_impl(dst, src, ghosts);
+}
 
 // ------------------------------------------------------------------------------------------------
 // FAS multigrid driver, device resident (absent fork's AMRFASMultiGrid / MultiGrid; see DESIGN.md for the
@@ -1400,7 +1548,7 @@ extern "C" int sg_op_cfInterp(sg_op*, sg_field*, const sg_field*) { AMR_UNSUPPOR
 // ------------------------------------------------------------------------------------------------
 extern "C" int sg_solver_define(sg_factory* f, sg_solver** out, int num_levels) {
   REQUIRE(f && out, "sg_solver_define: null");
-  if (num_levels != 1 || f->nlevels != 1) return fail(SG_ERR_UNSUPPORTED, "AMRFASMultiGrid: only single-level hierarchies are built so far");
+  REQUIRE(num_levels >= 1 && num_levels <= f->nlevels, "sg_solver_define: %d levels requested, the factory holds %d", num_levels, f->nlevels);
   sg_solver* s = new sg_solver();
   s->ctx = f->ctx; s->fac = f; s->num_levels = num_levels;
   for (int depth = 0;; depth++) {
@@ -1418,7 +1566,21 @@ extern "C" int sg_solver_define(sg_factory* f, sg_solver** out, int num_levels) 
     }
     s->phi.push_back(phi); s->rhs.push_back(rhs); s->save.push_back(save); s->tmp.push_back(tmp);
   }
-  SGCALL(sg_field_create(s->ops[0]->lay, &s->resid, 1, 0, SG_CELL));
+  for (int l = 0; l < num_levels; l++) {
+    sg_op* op = s->ops[0];
+    if (l > 0) SGCALL(sg_factory_AMRnewOp(f, l, &op));
+    s->aops.push_back(op);
+    sg_field *res = nullptr, *corr = nullptr, *tmp = nullptr, *scr = nullptr, *resC = nullptr;
+    SGCALL(sg_field_create(op->lay, &res, 1, 0, SG_CELL));
+    if (num_levels > 1) {
+      SGCALL(sg_field_create(op->lay, &corr, 1, 1, SG_CELL));
+      SGCALL(sg_field_create(op->lay, &tmp, 1, 0, SG_CELL));
+      SGCALL(sg_field_create(op->lay, &scr, 1, 1, SG_CELL));
+      if (l > 0) SGCALL(sg_field_create(op->link->clay, &resC, 1, 1, SG_CELL));
+    }
+    s->aresid.push_back(res); s->acorr.push_back(corr); s->atmp.push_back(tmp); s->ascratch.push_back(scr); s->aresC.push_back(resC);
+  }
+  s->resid = s->aresid[0];
   *out = s;
   return SG_OK;
 }
@@ -1437,14 +1599,18 @@ extern "C" int sg_solver_destroy(sg_solver* s) {
   for (size_t d = 0; d < s->ops.size(); d++) {
     sg_field_destroy(s->phi[d]); sg_field_destroy(s->rhs[d]); sg_field_destroy(s->save[d]); sg_field_destroy(s->tmp[d]);
   }
-  sg_field_destroy(s->resid);
+  for (size_t l = 0; l < s->aops.size(); l++) {
+    sg_field_destroy(s->aresid[l]); sg_field_destroy(s->acorr[l]); sg_field_destroy(s->atmp[l]); sg_field_destroy(s->ascratch[l]);
+    sg_field_destroy(s->aresC[l]);
+    if (l > 0) sg_op_destroy(s->aops[l]);
+  }
   for (sg_op* op : s->ops) sg_op_destroy(op);
   delete s;
   return SG_OK;
 }
 extern "C" int sg_solver_depth(const sg_solver* s, int level, int* ndepth) {
-  REQUIRE(s && ndepth && level == 0, "sg_solver_depth");
-  *ndepth = (int)s->ops.size();
+  REQUIRE(s && ndepth && level >= 0 && level < s->num_levels, "sg_solver_depth");
+  *ndepth = level == 0 ? (int)s->ops.size() : 1;
   return SG_OK;
 }
 
@@ -1458,6 +1624,7 @@ extern "C" int sg_solver_cell_updates_per_cycle(const sg_solver* s, const sg_sol
   double n = 0;
   int nd = (int)s->ops.size();
   for (int d = 0; d < nd; d++) n += (double)layout_cells_global(s->ops[d]->lay) * (d == nd - 1 ? sp->bottom : sp->pre + sp->post);
+  for (int l = 1; l < s->num_levels; l++) n += (double)layout_cells_global(s->aops[l]->lay) * (sp->pre + sp->post);
   *out = n;
   return SG_OK;
 }
@@ -1482,28 +1649,78 @@ static int mg_cycle(sg_solver* s, int depth, sg_field* phi, sg_field* rhs, const
   }
   return relax_impl(op, phi, rhs, sp->post);
 }
-static int vcycle(sg_solver* s, sg_field* phi, sg_field* rhs, const sg_solver_params* sp, int iter) {
-  sg_op* op0 = s->ops[0];
-  if (op0->update_operator) SGCALL(sg_op_UpdateOperator(op0, phi, nullptr, 0, iter, 0));
-  return mg_cycle(s, 0, phi, rhs, sp);
+// AMRMultiGrid::computeAMRResidualLevel: aresid[l] = rhs[l] - L_composite(phi)
+static int amr_residual_level(sg_solver* s, sg_field* const* phi, sg_field* const* rhs, int l, int l_max) {
+  sg_field* fine = l < l_max ? phi[l + 1] : nullptr;
+  const sg_field* crse = l > 0 ? phi[l - 1] : nullptr;
+  return amr_residual_impl(s->aops[l], s->aresid[l], fine, phi[l], crse, rhs[l], 0, fine ? s->aops[l + 1] : nullptr);
 }
-// computeAMRResidual: max-norm of rhs - L(phi), left in d_scalar[slot] (all ranks)
-static int residual_norm(sg_solver* s, sg_field* phi, sg_field* rhs, int slot) {
-  SGCALL(apply_impl(s->ops[0], s->resid, phi, rhs, 0, 2, slot));
+// AMRFASMultiGrid::VCycle (absent fork; INFERRED, identical to oracle/suhmo_oracle.c:amr_vcycle -- see DESIGN.md)
+static int amr_vcycle(sg_solver* s, sg_field* const* phi, sg_field* const* rhs, int ilev, int l_max, const sg_solver_params* sp, int iter) {
+  sg_op* op = s->aops[ilev];
+  if (op->update_operator) SGCALL(sg_op_UpdateOperator(op, phi[ilev], ilev > 0 ? phi[ilev - 1] : nullptr, ilev, iter, 0));
+  if (ilev == 0) return mg_cycle(s, 0, phi[0], s->aresid[0], sp);
+  sg_op* opc = s->aops[ilev - 1];
+  SGCALL(sg_op_relaxNF(op, phi[ilev], phi[ilev - 1], s->aresid[ilev], sp->pre, iter, ilev, 0));
+  // phi[ilev-1] <- average of phi[ilev] on the covered region (AMRRestrictS with skip_res), kept as the FAS reference state
+  SGCALL(amr_restrict_impl(op, s->aresC[ilev], phi[ilev], phi[ilev], phi[ilev - 1], s->ascratch[ilev], 1));
+  SGCALL(run_plan(s->ctx, phi[ilev - 1]->cb(), s->aresC[ilev]->cb(), op->link->t2c));
+  SGCALL(vec_launch<3>(s->acorr[ilev - 1], phi[ilev - 1], nullptr, 0, 0, true)); // assignLocal
+  SGCALL(amr_residual_level(s, phi, rhs, ilev - 1, l_max));
+  SGCALL(amr_restrict_impl(op, s->aresC[ilev], s->aresid[ilev], phi[ilev], phi[ilev - 1], s->ascratch[ilev], 0));
+  SGCALL(run_plan(s->ctx, s->aresid[ilev - 1]->cb(), s->aresC[ilev]->cb(), op->link->t2c));
+  SGCALL(amr_operator_impl(opc, s->atmp[ilev - 1], nullptr, phi[ilev - 1], ilev - 1 > 0 ? phi[ilev - 2] : nullptr, 0, nullptr));
+  SGCALL(vec_launch<1>(s->aresid[ilev - 1], s->atmp[ilev - 1], nullptr, 1.0, 0, false));
+  SGCALL(amr_vcycle(s, phi, rhs, ilev - 1, l_max, sp, iter));
+  SGCALL(vec_launch<0>(s->acorr[ilev - 1], phi[ilev - 1], s->acorr[ilev - 1], 1.0, -1.0, false));
+  // AMRProlongS_2 with the operator's scratch standing in for m_resC
+  SGCALL(amr_prolong_impl(op, phi[ilev], s->acorr[ilev - 1], opc, 1));
+  return sg_op_relaxNF(op, phi[ilev], phi[ilev - 1], s->aresid[ilev], sp->post, iter, ilev, 0);
+}
+static int vcycle(sg_solver* s, sg_field* const* phi, sg_field* const* rhs, int l_max, const sg_solver_params* sp, int iter) {
+  if (l_max == 0) {
+    sg_op* op0 = s->ops[0];
+    if (op0->update_operator) SGCALL(sg_op_UpdateOperator(op0, phi[0], nullptr, 0, iter, 0));
+    return mg_cycle(s, 0, phi[0], rhs[0], sp);
+  }
+  SGCALL(vec_launch<3>(s->aresid[l_max], rhs[l_max], nullptr, 0, 0, false)); // residual[lmax] = rhs[lmax]
+  return amr_vcycle(s, phi, rhs, l_max, l_max, sp, iter);
+}
+// computeAMRResidual: max over levels of the max-norm of the composite residual (covered cells zeroed), left in
+// d_scalar[slot] on all ranks
+static int residual_norm(sg_solver* s, sg_field* const* phi, sg_field* const* rhs, int l_max, int slot) {
+  if (l_max == 0) {
+    SGCALL(apply_impl(s->ops[0], s->resid, phi[0], rhs[0], 0, 2, slot));
+    return global_reduce(s->ctx, slot, true);
+  }
+  sg_ctx* c = s->ctx;
+  unsigned long long* nb = reinterpret_cast<unsigned long long*>(c->d_scalar) + slot;
+  CK(cudaMemsetAsync(nb, 0, sizeof(double), c->stream));
+  for (int l = l_max; l >= 0; l--) {
+    SGCALL(amr_residual_level(s, phi, rhs, l, l_max));
+    if (l < l_max) SGCALL(zero_covered_impl(s->aops[l], s->aresid[l], s->aops[l + 1]->lay));
+    // max|.| accumulates into the same slot across levels (atomicMax on the bit pattern)
+    sg_layout* L = s->aops[l]->lay;
+    if (L->fast) LAUNCH(c, k_reduce, grid2(L->nx, L->ny, B2D), B2D, s->aresid[l]->p(), nullptr, L->pitch, L->nx, L->ny, 0, c->d_partial, nb);
+    else LAUNCH(c, k_reduce_g, grid_g(L, 0, 0), B2D, s->aresid[l]->cb(), nullptr, L->d_patches, 0, c->d_partial, nb);
+  }
   return global_reduce(s->ctx, slot, true);
 }
 
 extern "C" int sg_solver_solve(sg_solver* s, sg_field* const* phi, sg_field* const* rhs, int l_max, int l_base,
                                const sg_solver_params* sp, double* hist, sg_solve_stats* stats) {
   REQUIRE(s && phi && rhs && sp && phi[0] && rhs[0], "sg_solver_solve: null");
-  REQUIRE(l_max == 0 && l_base == 0, "sg_solver_solve: single-level hierarchies only so far");
+  REQUIRE(l_base == 0 && l_max >= 0 && l_max < s->num_levels, "sg_solver_solve: l_base must be 0 and l_max below the number of levels defined");
   sg_ctx* c = s->ctx;
-  SGCALL(check_same(s->ops[0], phi[0], "solve(phi)")); SGCALL(check_same(s->ops[0], rhs[0], "solve(rhs)"));
+  for (int l = 0; l <= l_max; l++) {
+    REQUIRE(phi[l] && rhs[l], "sg_solver_solve: null field on level %d", l);
+    SGCALL(check_same(s->aops[l], phi[l], "solve(phi)")); SGCALL(check_same(s->aops[l], rhs[l], "solve(rhs)"));
+  }
   long long l0 = c->launches;
   cudaEvent_t e0, e1;
   CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
   double initial = 0, rnorm = 0;
-  SGCALL(residual_norm(s, phi[0], rhs[0], 2));
+  SGCALL(residual_norm(s, phi, rhs, l_max, 2));
   SGCALL(fetch_scalar(c, 2, &initial));
   rnorm = initial;
   if (hist) hist[0] = initial;
@@ -1512,8 +1729,8 @@ extern "C" int sg_solver_solve(sg_solver* s, sg_field* const* phi, sg_field* con
   if (sp->fixed_cycles > 0) {
     REQUIRE(sp->fixed_cycles <= 60, "fixed_cycles <= 60");
     for (iter = 0; iter < sp->fixed_cycles; iter++) {
-      SGCALL(vcycle(s, phi[0], rhs[0], sp, iter));
-      SGCALL(residual_norm(s, phi[0], rhs[0], 3 + iter)); // norms stay on the device until the end
+      SGCALL(vcycle(s, phi, rhs, l_max, sp, iter));
+      SGCALL(residual_norm(s, phi, rhs, l_max, 3 + iter)); // norms stay on the device until the end
     }
     CK(cudaEventRecord(e1, c->stream));
     CK(cudaMemcpyAsync(c->h_scalar + 3, c->d_scalar + 3, sizeof(double) * sp->fixed_cycles, cudaMemcpyDeviceToHost, c->stream));
@@ -1528,9 +1745,9 @@ extern "C" int sg_solver_solve(sg_solver* s, sg_field* const* phi, sg_field* con
     bool goHang = iter < sp->imin || rnorm < (1 - sp->hang) * norm_last, goMin = iter < sp->iter_min;
     while (goMin || (goIter && goRedu && goHang && goNorm)) {
       norm_last = rnorm;
-      SGCALL(vcycle(s, phi[0], rhs[0], sp, iter));
+      SGCALL(vcycle(s, phi, rhs, l_max, sp, iter));
       iter++;
-      SGCALL(residual_norm(s, phi[0], rhs[0], 2));
+      SGCALL(residual_norm(s, phi, rhs, l_max, 2));
       SGCALL(fetch_scalar(c, 2, &rnorm)); // the stop test needs the norm on the host: one sync per V-cycle
       if (hist) hist[iter] = rnorm;
       goNorm = rnorm > sp->norm_thresh; goRedu = rnorm > sp->eps * initial; goIter = iter < sp->max_iter;

@@ -186,3 +186,55 @@ class AmrOracleSide:
         f = self.fields
         return ob.AmrSolver(self.layouts, self.cfg.dx, self.alpha, self.beta, self.bc, self.prm,
                             f("a"), f("bX"), f("bY"), f("B"), f("Pi"), f("zb"), f("mask"))
+
+
+class AmrGpuSide:
+    """Device twin of an AmrOracleSide."""
+
+    def __init__(self, ctx, orc):
+        from suhmo_b200 import amr
+        self.amr, self.ctx, self.orc = amr, ctx, orc
+        cfg = orc.cfg
+        spec = dict(head=(1, CELL), B=(1, CELL), Pi=(1, CELL), zb=(1, CELL), mask=(1, CELL), rhs=(0, CELL),
+                    a=(0, CELL), bX=(0, XFACE), bY=(0, YFACE))
+        self.layouts, self.F = [], []
+        for l in range(orc.nlev):
+            r = 2 ** l
+            lay = amr.DisjointBoxLayout(ctx, orc.level_boxes[l], (0, 0, cfg.nx * r - 1, cfg.ny * r - 1), cfg.periodic)
+            F = {k: amr.LevelData(lay, 1, ng, cent) for k, (ng, cent) in spec.items()}
+            self.layouts.append(lay)
+            self.F.append(F)
+            for k in spec:
+                self.push(l, k)
+        self.bc = amr.make_bc(cfg.bc_lo, cfg.bc_hi, *orc.bc_vals)
+        self.prm = amr.make_params(**orc.prm_kw)
+        f = self.fields
+        self.factory = amr.VCAMRNonLinearPoissonOpFactory().define(
+            ctx, self.layouts, [2] * (orc.nlev - 1), cfg.dx, self.bc, orc.alpha, f("a"), orc.beta, f("bX"), f("bY"),
+            self.prm, f("B"), f("Pi"), f("zb"), f("mask"))
+
+    def fields(self, name):
+        return [F[name] for F in self.F]
+
+    def push(self, l, name, src=None):
+        of = src if src is not None else self.orc.F[l][name]
+        self.F[l][name].upload([of.fab(b)[0].copy() for b in range(len(self.layouts[l].boxes))])
+
+    def new_like(self, l, name):
+        f = self.F[l][name]
+        return self.amr.LevelData(self.layouts[l], f.ncomp, f.ng, f.cent)
+
+
+def fabs_equal(gpu_ld, orc_field, ghosts=True):
+    """compare whole FArrayBoxes box by box (ghost cells included when both sides carry them)"""
+    worst, same = 0.0, True
+    outs = gpu_ld.download()
+    for b in range(len(orc_field.layout.boxes)):
+        o = orc_field.fab(b)[0]
+        g = outs[b]
+        if not ghosts and gpu_ld.ng:
+            n = gpu_ld.ng
+            o, g = o[:, n:-n, n:-n], g[:, n:-n, n:-n]
+        same &= bool(np.array_equal(o, g))
+        worst = max(worst, float(np.abs(o - g).max()))
+    return worst, same
