@@ -1,0 +1,191 @@
+// suhmo_gpu.hpp -- C++ host layer over the C ABI (include/suhmo_gpu.h), mirroring the reference's operator surface:
+//   VCAMRNonLinearPoissonOpFactory (src/VCAMRNonLinearPoissonOp.H:291-403), VCAMRNonLinearPoissonOp
+//   (src/VCAMRNonLinearPoissonOp.H:24-285 + src/AMRNonLinearPoissonOp.H:48-590) and the AMRFASMultiGrid calls of
+//   AmrHydro::SolveForHead_nl (src/AmrHydro.cpp:719-768).  Same method names and argument meaning; LevelData arguments
+//   that may be "undefined"/NULL in the reference are pointers here.  Errors abort after printing the message, the
+//   reference's MayDay::Abort convention.  Header-only; link with -lsuhmo_gpu.  No CPU fallback exists anywhere below.
+#pragma once
+#include <cstdio>
+#include <cstdlib>
+#include <vector>
+
+#include "../../include/suhmo_gpu.h"
+
+namespace sg {
+
+inline void check(int st, const char* what) {
+  if (st != SG_OK) {
+    std::fprintf(stderr, "suhmo_gpu: %s failed (status %d): %s\n", what, st, sg_last_error());
+    std::abort(); // MayDay::Abort
+  }
+}
+#define SG_DO(call) ::sg::check((call), #call)
+
+struct Box { int lo[2], hi[2]; };
+
+class Context {
+ public:
+  sg_ctx* h = nullptr;
+  explicit Context(int device = 0, int rank = 0, int nranks = 1, const void* nccl_uid = nullptr) { SG_DO(sg_ctx_create(&h, device, rank, nranks, nccl_uid)); }
+  ~Context() { sg_ctx_destroy(h); }
+  Context(const Context&) = delete;
+  Context& operator=(const Context&) = delete;
+  void sync() { SG_DO(sg_ctx_sync(h)); }
+  long long kernelLaunches() { long long n; SG_DO(sg_ctx_kernel_launches(h, &n)); return n; }
+};
+
+// DisjointBoxLayout + ProblemDomain (+ procIDs)
+class DisjointBoxLayout {
+ public:
+  sg_layout* h = nullptr;
+  std::vector<Box> boxes;
+  std::vector<int> procs;
+  DisjointBoxLayout(Context& ctx, const std::vector<Box>& a_boxes, const std::vector<int>& a_procs, const Box& domain, const int periodic[2])
+      : boxes(a_boxes), procs(a_procs) {
+    std::vector<int> flat;
+    for (const Box& b : boxes) { flat.push_back(b.lo[0]); flat.push_back(b.lo[1]); flat.push_back(b.hi[0]); flat.push_back(b.hi[1]); }
+    int dom[4] = {domain.lo[0], domain.lo[1], domain.hi[0], domain.hi[1]};
+    SG_DO(sg_layout_create(ctx.h, &h, (int)boxes.size(), flat.data(), procs.empty() ? nullptr : procs.data(), dom, periodic));
+  }
+  ~DisjointBoxLayout() { sg_layout_destroy(h); }
+  DisjointBoxLayout(const DisjointBoxLayout&) = delete;
+  DisjointBoxLayout& operator=(const DisjointBoxLayout&) = delete;
+  bool coarsenable(int r) const { int ok; SG_DO(sg_layout_coarsenable(h, r, &ok)); return ok != 0; }
+  int size() const { return (int)boxes.size(); }
+};
+
+enum Centering { Cell = SG_CELL, XFace = SG_XFACE, YFace = SG_YFACE };
+
+// LevelData<FArrayBox> (Cell) or one direction of a LevelData<FluxBox>; device resident
+class LevelData {
+ public:
+  sg_field* h = nullptr;
+  bool owned = true;
+  LevelData(DisjointBoxLayout& grids, int ncomp, int nghost, Centering c = Cell) { SG_DO(sg_field_create(grids.h, &h, ncomp, nghost, c)); }
+  explicit LevelData(sg_field* adopt) : h(adopt) {}
+  ~LevelData() { if (owned) sg_field_destroy(h); }
+  LevelData(const LevelData&) = delete;
+  LevelData& operator=(const LevelData&) = delete;
+  // FArrayBox::dataPtr() of box `ibox` (ghost cells included, Fortran order)
+  void upload(int ibox, const double* fab) { SG_DO(sg_field_upload_box(h, ibox, fab)); }
+  void download(int ibox, double* fab) const { SG_DO(sg_field_download_box(h, ibox, fab)); }
+  void exchange() { SG_DO(sg_exchange(h, 1)); }
+  void copyTo(LevelData& dst, int ghosts = 0) const { SG_DO(sg_field_copyTo(dst.h, h, ghosts)); }
+};
+inline void ExtrapGhostCells(LevelData& f) { SG_DO(sg_extrap_ghost_cells(f.h)); } // util/ExtrapGhostCells.cpp:47-55
+inline void CopyGhostCells(LevelData& f) { SG_DO(sg_copy_ghost_cells(f.h)); }
+
+class VCAMRNonLinearPoissonOp {
+  static sg_field* hp(LevelData* f) { return f ? f->h : nullptr; }
+  static const sg_field* hp(const LevelData* f) { return f ? f->h : nullptr; }
+  static sg_op* op(VCAMRNonLinearPoissonOp* o) { return o ? o->h : nullptr; }
+ public:
+  sg_op* h = nullptr;
+  explicit VCAMRNonLinearPoissonOp(sg_op* a_h) : h(a_h) {}
+  ~VCAMRNonLinearPoissonOp() { sg_op_destroy(h); }
+  VCAMRNonLinearPoissonOp(const VCAMRNonLinearPoissonOp&) = delete;
+  VCAMRNonLinearPoissonOp& operator=(const VCAMRNonLinearPoissonOp&) = delete;
+  // ---- MGLevelOp
+  void relax(LevelData& e, const LevelData& residual, int iterations, int AMRFASMGiter = 0, int depth = 0) { SG_DO(sg_op_relax(h, e.h, residual.h, iterations, AMRFASMGiter, depth)); }
+  void relaxNF(LevelData& e, const LevelData* eCoarse, const LevelData& residual, int iterations, int AMRFASMGiter = 0, int depth = 0, bool print = false)
+  { SG_DO(sg_op_relaxNF(h, e.h, hp(eCoarse), residual.h, iterations, AMRFASMGiter, depth, print)); }
+  void residual(LevelData& lhs, LevelData& phi, const LevelData& rhs, bool homogeneous = false) { SG_DO(sg_op_residual(h, lhs.h, phi.h, rhs.h, homogeneous)); }
+  void residualNF(LevelData& lhs, LevelData& phi, const LevelData* phiCoarse, const LevelData& rhs, bool homogeneous = false)
+  { SG_DO(sg_op_residualNF(h, lhs.h, phi.h, hp(phiCoarse), rhs.h, homogeneous)); }
+  void applyOp(LevelData& lhs, LevelData& phi, bool homogeneous = false) { SG_DO(sg_op_applyOp(h, lhs.h, phi.h, homogeneous)); }
+  void applyOpNoBoundary(LevelData& lhs, LevelData& phi) { SG_DO(sg_op_applyOpNoBoundary(h, lhs.h, phi.h)); }
+  void applyOpMg(LevelData& lhs, LevelData& phi, LevelData* phiCoarse, bool homogeneous) { SG_DO(sg_op_applyOpMg(h, lhs.h, phi.h, hp(phiCoarse), homogeneous)); }
+  void restrictResidual(LevelData& resCoarse, LevelData& phiFine, const LevelData* phiCoarse, const LevelData& rhsFine, bool homogeneous)
+  { SG_DO(sg_op_restrictResidual(h, resCoarse.h, phiFine.h, hp(phiCoarse), rhsFine.h, homogeneous)); }
+  void restrictR(LevelData& phiCoarse, const LevelData& phiFine) { SG_DO(sg_op_restrictR(h, phiCoarse.h, phiFine.h)); }
+  void prolongIncrement(LevelData& phiThisLevel, const LevelData& correctCoarse) { SG_DO(sg_op_prolongIncrement(h, phiThisLevel.h, correctCoarse.h)); }
+  void UpdateOperator(LevelData& phi, const LevelData* phicoarse, int depth, int AMRFASMGiter, bool homogeneous)
+  { SG_DO(sg_op_UpdateOperator(h, phi.h, hp(phicoarse), depth, AMRFASMGiter, homogeneous)); }
+  void AverageOperator(const VCAMRNonLinearPoissonOp& finest, int depth) { SG_DO(sg_op_AverageOperator(h, finest.h, depth)); }
+  // ---- LinearOp
+  void assign(LevelData& lhs, const LevelData& rhs) { SG_DO(sg_op_assign(h, lhs.h, rhs.h)); }
+  void assignLocal(LevelData& lhs, const LevelData& rhs) { SG_DO(sg_op_assignLocal(h, lhs.h, rhs.h)); }
+  void incr(LevelData& lhs, const LevelData& x, double scale) { SG_DO(sg_op_incr(h, lhs.h, x.h, scale)); }
+  void axby(LevelData& lhs, const LevelData& x, const LevelData& y, double a, double b) { SG_DO(sg_op_axby(h, lhs.h, x.h, y.h, a, b)); }
+  void scale(LevelData& lhs, double s) { SG_DO(sg_op_scale(h, lhs.h, s)); }
+  void setToZero(LevelData& lhs) { SG_DO(sg_op_setToZero(h, lhs.h)); }
+  double dotProduct(const LevelData& a, const LevelData& b) { double r; SG_DO(sg_op_dotProduct(h, a.h, b.h, &r)); return r; }
+  double norm(const LevelData& x, int ord) { double r; SG_DO(sg_op_norm(h, x.h, ord, &r)); return r; }
+  double localMaxNorm(const LevelData& x) { double r; SG_DO(sg_op_localMaxNorm(h, x.h, &r)); return r; }
+  // ---- AMRLevelOp
+  void AMRResidual(LevelData& residual, LevelData* phiFine, LevelData& phi, const LevelData* phiCoarse, const LevelData& rhs, bool homogeneousPhysBC, VCAMRNonLinearPoissonOp* finerOp)
+  { SG_DO(sg_op_AMRResidual(h, residual.h, hp(phiFine), phi.h, hp(phiCoarse), rhs.h, homogeneousPhysBC, op(finerOp))); }
+  void AMROperator(LevelData& LofPhi, LevelData* phiFine, LevelData& phi, const LevelData* phiCoarse, bool homogeneousPhysBC, VCAMRNonLinearPoissonOp* finerOp)
+  { SG_DO(sg_op_AMROperator(h, LofPhi.h, hp(phiFine), phi.h, hp(phiCoarse), homogeneousPhysBC, op(finerOp))); }
+  void AMRRestrictS(LevelData& resCoarse, const LevelData& residual, LevelData& correction, const LevelData* coarseCorrection, LevelData& scratch, bool skip_res = false)
+  { SG_DO(sg_op_AMRRestrictS(h, resCoarse.h, residual.h, correction.h, hp(coarseCorrection), scratch.h, skip_res)); }
+  void AMRProlongS(LevelData& correction, const LevelData& coarseCorrection) { SG_DO(sg_op_AMRProlongS(h, correction.h, coarseCorrection.h)); }
+  void AMRProlongS_2(LevelData& correction, const LevelData& coarseCorrection, VCAMRNonLinearPoissonOp& crseOp) { SG_DO(sg_op_AMRProlongS_2(h, correction.h, coarseCorrection.h, crseOp.h)); }
+  void AMRUpdateResidual(LevelData& residual, LevelData& correction, const LevelData* coarseCorrection) { SG_DO(sg_op_AMRUpdateResidual(h, residual.h, correction.h, hp(coarseCorrection))); }
+  double AMRNorm(const LevelData& coarResid, const LevelData* fineResid, int refRat, int ord) { double r; SG_DO(sg_op_AMRNorm(h, coarResid.h, hp(fineResid), refRat, ord, &r)); return r; }
+  void reflux(const LevelData& phiFine, const LevelData& phi, LevelData& residual, VCAMRNonLinearPoissonOp& finerOp) { SG_DO(sg_op_reflux(h, phiFine.h, phi.h, residual.h, finerOp.h)); }
+};
+
+class VCAMRNonLinearPoissonOpFactory {
+ public:
+  sg_factory* h = nullptr;
+  ~VCAMRNonLinearPoissonOpFactory() { sg_factory_destroy(h); }
+  // define(coarseDomain, grids, refRatios, coarsedx, bc, alpha, aCoef, beta, bCoef, amrHydro, NL, wFlux, print, B, Pi, zb, iceMask, bcoeffOTF):
+  // the AmrHydro pointer and its three member callbacks become sg_params (their arithmetic lives in the kernels)
+  void define(Context& ctx, const std::vector<DisjointBoxLayout*>& grids, const std::vector<int>& refRatios, const double coarsedx[2],
+              const sg_bc& bc, double alpha, const std::vector<LevelData*>& aCoef, double beta, const std::vector<LevelData*>& bCoefX,
+              const std::vector<LevelData*>& bCoefY, const sg_params& prm, const std::vector<LevelData*>& B, const std::vector<LevelData*>& Pi,
+              const std::vector<LevelData*>& zb, const std::vector<LevelData*>& iceMask) {
+    const size_t n = grids.size();
+    std::vector<sg_layout*> g(n);
+    std::vector<sg_field*> a(n), bx(n), by(n), fb(n), fp(n), fz(n), fm(n);
+    for (size_t l = 0; l < n; l++) {
+      g[l] = grids[l]->h; a[l] = aCoef[l]->h; bx[l] = bCoefX[l]->h; by[l] = bCoefY[l]->h;
+      fb[l] = B[l]->h; fp[l] = Pi[l]->h; fz[l] = zb[l]->h; fm[l] = iceMask[l]->h;
+    }
+    std::vector<int> rr(refRatios);
+    rr.push_back(2);
+    SG_DO(sg_factory_define(ctx.h, &h, (int)n, g.data(), rr.data(), coarsedx, &bc, alpha, a.data(), beta, bx.data(), by.data(), &prm,
+                            fb.data(), fp.data(), fz.data(), fm.data()));
+  }
+  // NULL when the boxes cannot coarsen by 2^depth * 2 (src/VCAMRNonLinearPoissonOp.cpp:1053-1055); caller owns the op
+  VCAMRNonLinearPoissonOp* MGnewOp(int level, int depth, bool homoOnly = true) {
+    sg_op* o;
+    SG_DO(sg_factory_MGnewOp(h, level, depth, homoOnly, &o));
+    return o ? new VCAMRNonLinearPoissonOp(o) : nullptr;
+  }
+  VCAMRNonLinearPoissonOp* AMRnewOp(int level) { sg_op* o; SG_DO(sg_factory_AMRnewOp(h, level, &o)); return new VCAMRNonLinearPoissonOp(o); }
+  int refToFiner(int level) const { int r; SG_DO(sg_factory_refToFiner(h, level, &r)); return r; }
+};
+
+// AMRFASMultiGrid<LevelData<FArrayBox>> as SolveForHead_nl drives it; every V-cycle runs on the device
+class AMRFASMultiGrid {
+ public:
+  sg_solver* h = nullptr;
+  sg_solver_params params{4, 4, 16, 1, 100, 0, 2, 1e-7, 0.01, 1e-7, 0};
+  int m_imin = 0, m_iterMin = 2, m_exitStatus = 0;
+  ~AMRFASMultiGrid() { sg_solver_destroy(h); }
+  void define(VCAMRNonLinearPoissonOpFactory& factory, int numLevels) { SG_DO(sg_solver_define(factory.h, &h, numLevels)); }
+  void setSolverParameters(int pre, int post, int bottom, int numMG, int maxIter, double eps, double hang, double normThresh) {
+    params.pre = pre; params.post = post; params.bottom = bottom; params.num_mg = numMG; params.max_iter = maxIter;
+    params.eps = eps; params.hang = hang; params.norm_thresh = normThresh;
+  }
+  // solve(phi, rhs, l_max, l_base, zeroInitialGuess=false); returns the number of V-cycles
+  int solve(const std::vector<LevelData*>& phi, const std::vector<LevelData*>& rhs, int l_max, int l_base, sg_solve_stats* stats = nullptr,
+            std::vector<double>* resnorm = nullptr) {
+    params.imin = m_imin; params.iter_min = m_iterMin;
+    std::vector<sg_field*> p, r;
+    for (LevelData* f : phi) p.push_back(f->h);
+    for (LevelData* f : rhs) r.push_back(f->h);
+    std::vector<double> hist((size_t)(params.max_iter > params.fixed_cycles ? params.max_iter : params.fixed_cycles) + 2, 0.0);
+    sg_solve_stats st;
+    SG_DO(sg_solver_solve(h, p.data(), r.data(), l_max, l_base, &params, hist.data(), &st));
+    m_exitStatus = st.exit_status;
+    if (stats) *stats = st;
+    if (resnorm) resnorm->assign(hist.begin(), hist.begin() + st.iterations + 1);
+    return st.iterations;
+  }
+  void refresh() { SG_DO(sg_solver_refresh(h)); }
+};
+
+} // namespace sg

@@ -1,0 +1,46 @@
+#!/usr/bin/env python
+"""Generates tests/golden/*.npz from the CPU oracle (NOT from the reference, which cannot be built here and ships no
+vectors for this path -- SURVEY.md 8c): frozen inputs and outputs that guard the oracle and the CUDA path against drift.
+  python tests/golden/make_golden.py"""
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, ROOT)
+from oracle import binding as ob  # noqa: E402
+from suhmo_b200 import synthetic as syn  # noqa: E402
+from tests.problem import AmrOracleSide, OracleSide, amr_hierarchy  # noqa: E402
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+def single_level():
+    cfg = syn.config("C1", 1)  # exec/0_convergence_channelized/1lev: 32 x 8 cells, two 16 x 8 boxes
+    boxes = syn.domain_split(cfg.nx, cfg.ny, cfg.max_box_size, cfg.block_factor)
+    orc = OracleSide(cfg, boxes)
+    out = {"in_" + k: orc.F[k].get_global() for k in ("head", "B", "Pi", "zb", "mask", "rhs")}
+    orc.init_bcoef()
+    out["bX0"], out["bY0"] = orc.F["bX"].get_global(), orc.F["bY"].get_global()
+    it, hist = orc.solver().solve(orc.F["head"], orc.F["rhs"], ob.make_solver_params(bottom=10, fixed_cycles=5))
+    out["resnorm"], out["head5"] = hist, orc.F["head"].get_global()
+    np.savez_compressed(os.path.join(HERE, "c1_1lev_vcycles.npz"), **out)
+
+
+def three_levels():
+    cfg, lv = amr_hierarchy()
+    orc = AmrOracleSide(cfg, lv)
+    orc.average_down("head")
+    orc.init_bcoef()
+    it, hist = orc.solver().solve(orc.fields("head"), orc.fields("rhs"), 2, ob.make_solver_params(bottom=10, fixed_cycles=3))
+    out = {"resnorm": hist}
+    for l in range(3):
+        out[f"head3_L{l}"] = np.nan_to_num(orc.F[l]["head"].get_global(), nan=0.0)
+    np.savez_compressed(os.path.join(HERE, "amr_3lev_vcycles.npz"), **out)
+
+
+if __name__ == "__main__":
+    single_level()
+    three_levels()
+    print("wrote", sorted(f for f in os.listdir(HERE) if f.endswith(".npz")))

@@ -158,3 +158,16 @@ def test_amr_solve_with_stop_test(gpu_ctx):
     git, ghist, stats = mg.solve(gpu.fields("head"), gpu.fields("rhs"))
     assert git == it
     assert np.array_equal(ghist, ohist)
+
+
+def test_against_golden_fixture_three_levels(gpu_ctx):
+    """the CUDA path against the committed fixture (tests/golden/amr_3lev_vcycles.npz): 3 levels, 3 FAS V-cycles"""
+    import os
+    z = np.load(os.path.join(os.path.dirname(__file__), "golden", "amr_3lev_vcycles.npz"))
+    cfg, orc, gpu = make(gpu_ctx, 3)
+    mg = gpu.amr.AMRFASMultiGrid().define(gpu.factory, 3)
+    mg.setSolverParameters(4, 4, 10, 1, 100, 1e-10, 1e-4, 1e-7)
+    git, ghist, stats = mg.solve(gpu.fields("head"), gpu.fields("rhs"), fixed_cycles=3)
+    assert np.array_equal(ghist, z["resnorm"])
+    for l in range(3):
+        assert np.array_equal(np.nan_to_num(gpu.F[l]["head"].get_global(), nan=0.0), z[f"head3_L{l}"]), f"level {l}"

@@ -1,0 +1,33 @@
+"""The C++ host layer (suhmo_b200/host/suhmo_gpu.hpp) over the C ABI: compiled with g++ everywhere; on the GPU box the
+program drives a two-level head solve the way AmrHydro::SolveForHead_nl drives the reference."""
+import os
+import subprocess
+
+import pytest
+
+from suhmo_b200 import build
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+EXE = os.path.join(ROOT, "tests", "cpp", "host_smoke")
+
+
+def compile_host():
+    build.build()
+    libdir = os.path.join(ROOT, "suhmo_b200", "lib")
+    cmd = ["g++", "-std=c++14", "-O1", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"),
+           os.path.join(ROOT, "tests", "cpp", "host_smoke.cpp"), "-L", libdir, "-lsuhmo_gpu", f"-Wl,-rpath,{libdir}", "-o", EXE]
+    subprocess.check_call(cmd)
+    return EXE
+
+
+def test_cpp_host_layer_compiles_and_links():
+    exe = compile_host()
+    assert os.path.exists(exe)
+
+
+@pytest.mark.gpu
+def test_cpp_host_layer_solves_two_levels():
+    exe = compile_host()
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "host_smoke: OK" in r.stdout

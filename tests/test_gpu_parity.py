@@ -250,3 +250,16 @@ def test_ghost_utilities(gpu_ctx):
         for b in (0, len(orc.boxes) - 1):
             got, exp = gpu.F["B"].download_box(b), orc.F["B"].fab(b)[0]
             assert np.array_equal(got, exp)
+
+
+def test_against_golden_fixture_c1(gpu_ctx):
+    """the CUDA path against the committed fixture (tests/golden/c1_1lev_vcycles.npz): QuickStart 1lev, 5 FAS V-cycles"""
+    import os
+    z = np.load(os.path.join(os.path.dirname(__file__), "golden", "c1_1lev_vcycles.npz"))
+    cfg, orc, gpu = make(gpu_ctx, "C1", 1, None)
+    assert np.array_equal(gpu.F["bX"].get_global(), z["bX0"]) and np.array_equal(gpu.F["bY"].get_global(), z["bY0"])
+    mg = gpu.amr.AMRFASMultiGrid().define(gpu.factory, 1)
+    mg.setSolverParameters(4, 4, 10, 1, 100, 1e-10, 1e-4, 1e-7)
+    git, ghist, stats = mg.solve([gpu.F["head"]], [gpu.F["rhs"]], fixed_cycles=5)
+    assert np.array_equal(ghist, z["resnorm"])
+    assert np.array_equal(gpu.F["head"].get_global(), z["head5"])
