@@ -241,6 +241,47 @@ int sg_op_zeroCovered(sg_op* op, sg_field* coarse, const sg_field* fine_any);
    dst's valid regions grown by `ghosts` that a valid region of src holds (periodic images included) */
 int sg_field_copyTo(sg_field* dst, const sg_field* src, int ghosts);
 
+/* ------------------------------------------------------------------ Picard body -------------------------- */
+/* Field kernels of AmrHydro::timeStepFAS around the head solve ("gap-height and water-flux updates").
+   The time loop / Picard loop themselves stay host code (C++ in the reference); these are its device kernels.
+   suhmo.* constants they need (src/suhmo_params.cpp:51-74, src/AmrHydro.cpp:864-884): */
+typedef struct sg_picard_params {
+  double rho_i, rho_w, gravity, G, L, ct, cw, ub0;
+  int basal_friction;
+  double A, cutOffbr, maxOffbr, DiffFactor;
+  int n_moulins;
+  double ramp, distributed_input;
+  int use_mask_rhs_b, use_ImplDiff;
+} sg_picard_params;
+/* Chombo CellToEdge / EdgeToCell (src/AmrHydro.cpp:2529-2530,2750,2977-2979) */
+int sg_cell_to_edge(const sg_field* cell, sg_field* ex, sg_field* ey);
+int sg_edge_to_cell(const sg_field* ex, const sg_field* ey, sg_field* cell2);
+/* Gradient::compGradientMAC on one level (util/Gradient.cpp:74-159, NEWMACGRAD util/GradientF.ChF:55-70) */
+int sg_mac_gradient(sg_field* phi, const sg_field* mask_or_null, const double dx[2], sg_field* gx, sg_field* gy);
+/* HydroIBC::setup_iceMask_EC (src/HydroIBC.cpp:138-184) */
+int sg_icemask_ec(const sg_field* mask, sg_field* mx, sg_field* my);
+/* FORT_COMPUTEQW via evaluate_Qw_ec (src/AmrHydroF.ChF:125-153, src/AmrHydro.cpp:1676-1708); one direction per call */
+int sg_compute_qw(const sg_params* p, const sg_field* Bec, const sg_field* Reec, const sg_field* gradHec, sg_field* Qw);
+/* FORT_COMPUTESCAPROD (src/AmrHydroF.ChF:165-186) */
+int sg_compute_scaprod(const sg_field* a, const sg_field* b1, const sg_field* b2, sg_field* p1, sg_field* p2);
+/* FORT_COMPUTEDCOEFF via dCoeff (src/AmrHydroF.ChF:241-265, src/AmrHydro.cpp:1832-1862) */
+int sg_compute_dcoeff(sg_field* D, const sg_field* MRec, const sg_field* Bec, const sg_field* IMec, double rho, int cutOffB);
+/* FORT_COMPUTEDIFTERM2D (src/AmrHydroF.ChF:289-343) */
+int sg_compute_difterm(const sg_field* phi, const double dx[2], sg_field* Dterm, const sg_field* D0, const sg_field* D1);
+/* FORT_COMPUTE_TIMEVARYINGRECHARGE (src/AmrHydroF.ChF:353-373) */
+int sg_time_varying_recharge(const sg_field* zs, sg_field* recharge, double TK, double background);
+/* AmrHydro::Calc_meltingRate (src/AmrHydro.cpp:2175-2252): qgh / qgz = EdgeToCell of Qw*grad(h) / Qw*grad(zb) */
+int sg_calc_melting_rate(const sg_picard_params* q, const sg_field* H, const sg_field* zb, const sg_field* Pi, const sg_field* IM,
+                         const sg_field* B, const sg_field* qgh, const sg_field* qgz, sg_field* Pw, sg_field* mR);
+/* RHS of the head equation (src/AmrHydro.cpp:3044-3077) */
+int sg_rhs_head(const sg_picard_params* q, sg_field* RHSh, const sg_field* mR, const sg_field* B, const sg_field* BH, const sg_field* BL,
+                const sg_field* MV, const sg_field* moulinSrc, const sg_field* Dterm, const sg_field* IM);
+/* AmrHydro::CalcRHS_gapHeightFAS (src/AmrHydro.cpp:2070-2171) */
+int sg_rhs_gap(const sg_picard_params* q, sg_field* RHS, const sg_field* Pi, const sg_field* Pw, const sg_field* mR, const sg_field* B,
+               const sg_field* DT, const sg_field* IM, const sg_field* BH, const sg_field* BL, const sg_field* MV, double dt);
+/* explicit gap-height update newB = RHS*dt + oldB (src/AmrHydro.cpp:3394-3408) */
+int sg_gap_euler(sg_field* newB, const sg_field* oldB, const sg_field* RHS, double dt);
+
 /* ------------------------------------------------------------------ whole solve -------------------------- */
 /* AMRFASMultiGrid::define + setSolverParameters + solve as driven by AmrHydro::SolveForHead_nl
    (src/AmrHydro.cpp:719-768), kept on the device: one call = all V-cycles, residual norms on device. */

@@ -26,6 +26,14 @@ class BC(C.Structure):
                 ("lo_val", C.c_double * 2), ("hi_val", C.c_double * 2)]
 
 
+class PicardParams(C.Structure):
+    _fields_ = [("rho_i", C.c_double), ("rho_w", C.c_double), ("gravity", C.c_double), ("G", C.c_double), ("L", C.c_double),
+                ("ct", C.c_double), ("cw", C.c_double), ("ub0", C.c_double), ("basal_friction", C.c_int),
+                ("A", C.c_double), ("cutOffbr", C.c_double), ("maxOffbr", C.c_double), ("DiffFactor", C.c_double),
+                ("n_moulins", C.c_int), ("ramp", C.c_double), ("distributed_input", C.c_double),
+                ("use_mask_rhs_b", C.c_int), ("use_ImplDiff", C.c_int)]
+
+
 class SolverParams(C.Structure):
     _fields_ = [("pre", C.c_int), ("post", C.c_int), ("bottom", C.c_int), ("max_iter", C.c_int),
                 ("imin", C.c_int), ("iter_min", C.c_int), ("eps", C.c_double), ("hang", C.c_double),
@@ -126,6 +134,16 @@ def lib():
     sig("orc_amr_solver_resnorm", cd, vp, pvp, pvp, ci)
     sig("orc_amr_solver_solve", ci, vp, pvp, pvp, ci, C.POINTER(SolverParams), dp)
     sig("orc_amr_solver_cell_updates", cd, vp, C.POINTER(SolverParams), ci)
+    pq = C.POINTER(PicardParams)
+    sig("orc_compute_qw", None, C.POINTER(Params), vp, vp, vp, vp)
+    sig("orc_compute_scaprod", None, vp, vp, vp, vp, vp)
+    sig("orc_compute_dcoeff", None, vp, vp, vp, vp, cd, ci)
+    sig("orc_compute_difterm", None, vp, dp, vp, vp, vp)
+    sig("orc_time_varying_recharge", None, vp, vp, cd, cd)
+    sig("orc_calc_melting_rate", None, pq, vp, vp, vp, vp, vp, vp, vp, vp, vp)
+    sig("orc_rhs_head", None, pq, vp, vp, vp, vp, vp, vp, vp, vp, vp)
+    sig("orc_rhs_gap", None, pq, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, cd)
+    sig("orc_gap_euler", None, vp, vp, vp, cd)
     _LIB = L
     return L
 

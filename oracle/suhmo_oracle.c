@@ -1578,3 +1578,164 @@ double orc_amr_solver_cell_updates(const orc_amr_solver* s, const orc_solver_par
   for (int l = 1; l <= l_max; l++) n += layout_cells(s->lay[l]) * (sp->pre + sp->post);
   return n;
 }
+
+/* =========================================================================================== */
+/* Picard-body field kernels: gap-height and water-flux updates               */
+/* =========================================================================================== */
+/* FOR_FACES: faces of the valid box of box b in direction of field f */
+#define FOR_REGION(r, i, j) for (int j = (r).lo[1]; j <= (r).hi[1]; j++) for (int i = (r).lo[0]; i <= (r).hi[0]; i++)
+
+/* COMPUTEQW (src/AmrHydroF.ChF:125-153) via evaluate_Qw_ec (src/AmrHydro.cpp:1676-1708), one direction */
+void orc_compute_qw(const orc_params* p, const orc_field* Bec, const orc_field* Reec, const orc_field* gradHec, orc_field* Qw) {
+  const orc_layout* L = Qw->lay;
+#pragma omp parallel for schedule(static)
+  for (int b = 0; b < L->nbox; b++) {
+    obox r = valid_box(Qw, b);
+    FOR_REGION(r, i, j) {
+      double aB = AT(Bec, b, i, j, 0);
+      double num_q = -(aB * aB * aB * 9.8 * AT(gradHec, b, i, j, 0));
+      double denom_q = 12.0 * p->nu * (1.0 + p->omega * AT(Reec, b, i, j, 0));
+      AT(Qw, b, i, j, 0) = num_q / denom_q;
+    }
+  }
+}
+/* COMPUTESCAPROD (src/AmrHydroF.ChF:165-186) */
+void orc_compute_scaprod(const orc_field* a, const orc_field* b1, const orc_field* b2, orc_field* p1, orc_field* p2) {
+  const orc_layout* L = a->lay;
+#pragma omp parallel for schedule(static)
+  for (int b = 0; b < L->nbox; b++) {
+    obox r = valid_box(p1, b);
+    FOR_REGION(r, i, j) {
+      AT(p1, b, i, j, 0) = AT(a, b, i, j, 0) * AT(b1, b, i, j, 0);
+      AT(p2, b, i, j, 0) = AT(a, b, i, j, 0) * AT(b2, b, i, j, 0);
+    }
+  }
+}
+/* COMPUTEDCOEFF (src/AmrHydroF.ChF:241-265) via dCoeff (src/AmrHydro.cpp:1832-1862) */
+void orc_compute_dcoeff(orc_field* D, const orc_field* MRec, const orc_field* Bec, const orc_field* IMec, double rho, int cutOffB) {
+  const orc_layout* L = D->lay;
+#pragma omp parallel for schedule(static)
+  for (int b = 0; b < L->nbox; b++) {
+    obox r = valid_box(D, b);
+    FOR_REGION(r, i, j) {
+      if ((AT(IMec, b, i, j, 0) < 0.0) && (cutOffB > 0)) AT(D, b, i, j, 0) = 0.0;
+      else AT(D, b, i, j, 0) = fmax(AT(Bec, b, i, j, 0) * AT(MRec, b, i, j, 0) / rho, 5.0e-6);
+    }
+  }
+}
+/* COMPUTEDIFTERM2D (src/AmrHydroF.ChF:289-343): Dterm = div(D grad phi) on the valid cells */
+void orc_compute_difterm(orc_field* phi, const double dx[2], orc_field* Dterm, const orc_field* D0, const orc_field* D1) {
+  const orc_layout* L = phi->lay;
+#pragma omp parallel for schedule(static)
+  for (int b = 0; b < L->nbox; b++) {
+    obox r = L->box[b];
+    double dxinv0 = 1.0 / (dx[0] * dx[0]), dxinv1 = 1.0 / (dx[1] * dx[1]);
+    FOR_REGION(r, i, j) {
+      AT(Dterm, b, i, j, 0) =
+          (AT(D0, b, i + 1, j, 0) * (AT(phi, b, i + 1, j, 0) - AT(phi, b, i, j, 0)) * dxinv0 -
+           AT(D0, b, i, j, 0) * (AT(phi, b, i, j, 0) - AT(phi, b, i - 1, j, 0)) * dxinv0 +
+           AT(D1, b, i, j + 1, 0) * (AT(phi, b, i, j + 1, 0) - AT(phi, b, i, j, 0)) * dxinv1 -
+           AT(D1, b, i, j, 0) * (AT(phi, b, i, j, 0) - AT(phi, b, i, j - 1, 0)) * dxinv1);
+    }
+  }
+}
+/* COMPUTE_TIMEVARYINGRECHARGE (src/AmrHydroF.ChF:353-373), whole array of Recharge */
+void orc_time_varying_recharge(const orc_field* zs, orc_field* recharge, double TK, double background) {
+  const orc_layout* L = zs->lay;
+  const double ddf = 0.01 / 86400., dT_dZ = -0.0075;
+#pragma omp parallel for schedule(static)
+  for (int b = 0; b < L->nbox; b++) {
+    obox r = recharge->ab[b];
+    FOR_REGION(r, i, j) AT(recharge, b, i, j, 0) = fmax(ddf * (TK + AT(zs, b, i, j, 0) * dT_dZ), 0.0) + background;
+  }
+}
+
+/* orc_picard_params: suhmo.* constants of the Picard body (src/suhmo_params.cpp:51-74), see the header */
+
+/* Calc_meltingRate (src/AmrHydro.cpp:2175-2252): over the whole (ghosted) array of Pw.  qgh / qgz = EdgeToCell of
+   Qw*grad(h) / Qw*grad(zb) (2 components each); their ghost cells are whatever the caller left (zero here). */
+void orc_calc_melting_rate(const orc_picard_params* q, const orc_field* H, const orc_field* zb, const orc_field* Pi, const orc_field* IM,
+                           const orc_field* B, const orc_field* qgh, const orc_field* qgz, orc_field* Pw, orc_field* mR) {
+  const orc_layout* L = H->lay;
+#pragma omp parallel for schedule(static)
+  for (int b = 0; b < L->nbox; b++) {
+    obox r = Pw->ab[b];
+    FOR_REGION(r, i, j) {
+      AT(Pw, b, i, j, 0) = q->gravity * q->rho_w * (AT(H, b, i, j, 0) - AT(zb, b, i, j, 0));
+      double sca_prod = 0.0;
+      if (q->basal_friction) sca_prod = 20. * 20. * q->ub0 * fabs(AT(Pi, b, i, j, 0) - AT(Pw, b, i, j, 0)) * q->ub0;
+      double t0 = AT(qgh, b, i, j, 0), t1 = AT(qgh, b, i, j, 1);
+      double abs_QPw = t0 + t1 - (AT(qgz, b, i, j, 0) + AT(qgz, b, i, j, 1));
+      if ((abs_QPw < 0) && (AT(B, b, i, j, 0) < 1e-6)) abs_QPw = 0.0;
+      double m = q->G + sca_prod - q->rho_w * q->gravity * (t0 + t1) + q->ct * q->cw * q->rho_w * q->rho_w * q->gravity * abs_QPw;
+      m = m / q->L;
+      m = fmax(m, 0.0);
+      if (AT(IM, b, i, j, 0) < 0.0) m = 0.0;
+      AT(mR, b, i, j, 0) = m;
+    }
+  }
+}
+/* RHS of the head equation (src/AmrHydro.cpp:3044-3077), valid cells */
+void orc_rhs_head(const orc_picard_params* q, orc_field* RHSh, const orc_field* mR, const orc_field* B, const orc_field* BH,
+                  const orc_field* BL, const orc_field* MV, const orc_field* moulinSrc, const orc_field* Dterm, const orc_field* IM) {
+  const orc_layout* L = RHSh->lay;
+  const double rho_coef = (1.0 / q->rho_w - 1.0 / q->rho_i);
+#pragma omp parallel for schedule(static)
+  for (int b = 0; b < L->nbox; b++) {
+    obox r = L->box[b];
+    FOR_REGION(r, i, j) {
+      double v = AT(mR, b, i, j, 0) * rho_coef;
+      double ub_norm = AT(MV, b, i, j, 0);
+      if (AT(B, b, i, j, 0) < AT(BH, b, i, j, 0)) v -= ub_norm * (AT(BH, b, i, j, 0) - AT(B, b, i, j, 0)) / AT(BL, b, i, j, 0);
+      if (q->n_moulins > 0) v += (AT(moulinSrc, b, i, j, 0) * q->ramp + q->distributed_input);
+      else v += AT(moulinSrc, b, i, j, 0);
+      v -= q->DiffFactor * AT(Dterm, b, i, j, 0);
+      if (AT(IM, b, i, j, 0) < 0.0) v = 0.0;
+      AT(RHSh, b, i, j, 0) = v;
+    }
+  }
+}
+/* CalcRHS_gapHeightFAS (src/AmrHydro.cpp:2070-2171), valid cells; std::pow(x, 2) is x*x (exact fold) */
+void orc_rhs_gap(const orc_picard_params* q, orc_field* RHS, const orc_field* Pi, const orc_field* Pw, const orc_field* mR, const orc_field* B,
+                 const orc_field* DT, const orc_field* IM, const orc_field* BH, const orc_field* BL, const orc_field* MV, double dt) {
+  const orc_layout* L = RHS->lay;
+#pragma omp parallel for schedule(static)
+  for (int b = 0; b < L->nbox; b++) {
+    obox r = L->box[b];
+    FOR_REGION(r, i, j) {
+      double Bv = AT(B, b, i, j, 0);
+      double rhs = AT(mR, b, i, j, 0);
+      rhs *= 1.0 / q->rho_i;
+      double ub_norm = AT(MV, b, i, j, 0);
+      if ((AT(IM, b, i, j, 0) < 0.0) && q->use_mask_rhs_b) {
+        rhs = 0.0;
+        if (q->use_ImplDiff) rhs = Bv;
+      } else {
+        if (Bv < AT(BH, b, i, j, 0)) rhs += ub_norm * (AT(BH, b, i, j, 0) - Bv) / AT(BL, b, i, j, 0);
+        double PimPw = (AT(Pi, b, i, j, 0) - AT(Pw, b, i, j, 0));
+        double AbsPimPw = fabs(PimPw);
+        if (q->cutOffbr > Bv) {
+          rhs -= q->A * (AbsPimPw * AbsPimPw) * PimPw * Bv * (1.0 - (q->cutOffbr - Bv) / q->cutOffbr);
+          if (!q->use_ImplDiff) rhs += q->DiffFactor * AT(DT, b, i, j, 0);
+        } else if (q->maxOffbr < Bv) {
+          rhs -= q->A * (AbsPimPw * AbsPimPw) * PimPw * Bv * (1.0 - (q->maxOffbr - Bv) / q->maxOffbr);
+          if (!q->use_ImplDiff) rhs += q->DiffFactor * AT(DT, b, i, j, 0);
+        } else {
+          rhs -= q->A * (AbsPimPw * AbsPimPw) * PimPw * Bv;
+          if (!q->use_ImplDiff) rhs += q->DiffFactor * AT(DT, b, i, j, 0);
+        }
+        if (q->use_ImplDiff) rhs = Bv + dt * rhs;
+      }
+      AT(RHS, b, i, j, 0) = rhs;
+    }
+  }
+}
+/* explicit gap-height update (src/AmrHydro.cpp:3394-3408): newB = RHS*dt + oldB on the valid cells */
+void orc_gap_euler(orc_field* newB, const orc_field* oldB, const orc_field* RHS, double dt) {
+  const orc_layout* L = newB->lay;
+#pragma omp parallel for schedule(static)
+  for (int b = 0; b < L->nbox; b++) {
+    obox r = L->box[b];
+    FOR_REGION(r, i, j) AT(newB, b, i, j, 0) = AT(RHS, b, i, j, 0) * dt + AT(oldB, b, i, j, 0);
+  }
+}

@@ -169,6 +169,28 @@ int orc_amr_solver_solve(orc_amr_solver* s, orc_field* const* phi, orc_field* co
                          const orc_solver_params* sp, double* resnorm);
 double orc_amr_solver_cell_updates(const orc_amr_solver* s, const orc_solver_params* sp, int l_max);
 
+/* ---- Picard-body field kernels ---- */
+typedef struct orc_picard_params {
+  double rho_i, rho_w, gravity, G, L, ct, cw, ub0;
+  int basal_friction;
+  double A, cutOffbr, maxOffbr, DiffFactor;
+  int n_moulins;
+  double ramp, distributed_input;
+  int use_mask_rhs_b, use_ImplDiff;
+} orc_picard_params;
+void orc_compute_qw(const orc_params* p, const orc_field* Bec, const orc_field* Reec, const orc_field* gradHec, orc_field* Qw);
+void orc_compute_scaprod(const orc_field* a, const orc_field* b1, const orc_field* b2, orc_field* p1, orc_field* p2);
+void orc_compute_dcoeff(orc_field* D, const orc_field* MRec, const orc_field* Bec, const orc_field* IMec, double rho, int cutOffB);
+void orc_compute_difterm(orc_field* phi, const double dx[2], orc_field* Dterm, const orc_field* D0, const orc_field* D1);
+void orc_time_varying_recharge(const orc_field* zs, orc_field* recharge, double TK, double background);
+void orc_calc_melting_rate(const orc_picard_params* q, const orc_field* H, const orc_field* zb, const orc_field* Pi, const orc_field* IM,
+                           const orc_field* B, const orc_field* qgh, const orc_field* qgz, orc_field* Pw, orc_field* mR);
+void orc_rhs_head(const orc_picard_params* q, orc_field* RHSh, const orc_field* mR, const orc_field* B, const orc_field* BH,
+                  const orc_field* BL, const orc_field* MV, const orc_field* moulinSrc, const orc_field* Dterm, const orc_field* IM);
+void orc_rhs_gap(const orc_picard_params* q, orc_field* RHS, const orc_field* Pi, const orc_field* Pw, const orc_field* mR, const orc_field* B,
+                 const orc_field* DT, const orc_field* IM, const orc_field* BH, const orc_field* BL, const orc_field* MV, double dt);
+void orc_gap_euler(orc_field* newB, const orc_field* oldB, const orc_field* RHS, double dt);
+
 void orc_set_threads(int n);
 
 #ifdef __cplusplus

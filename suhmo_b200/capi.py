@@ -33,6 +33,14 @@ class SolveStats(C.Structure):
                 ("kernel_launches", C.c_longlong)]
 
 
+class PicardParams(C.Structure):
+    _fields_ = [("rho_i", C.c_double), ("rho_w", C.c_double), ("gravity", C.c_double), ("G", C.c_double), ("L", C.c_double),
+                ("ct", C.c_double), ("cw", C.c_double), ("ub0", C.c_double), ("basal_friction", C.c_int),
+                ("A", C.c_double), ("cutOffbr", C.c_double), ("maxOffbr", C.c_double), ("DiffFactor", C.c_double),
+                ("n_moulins", C.c_int), ("ramp", C.c_double), ("distributed_input", C.c_double),
+                ("use_mask_rhs_b", C.c_int), ("use_ImplDiff", C.c_int)]
+
+
 class SuhmoGpuError(RuntimeError):
     def __init__(self, code, msg):
         super().__init__(f"libsuhmo_gpu status {code}: {msg}")
@@ -80,6 +88,14 @@ SIGNATURES = {
     "sg_op_AMRProlongS_2": [vp, vp, vp, vp], "sg_op_AMRUpdateResidual": [vp, vp, vp, vp],
     "sg_op_AMRNorm": [vp, vp, vp, ci, ci, dp], "sg_op_reflux": [vp, vp, vp, vp, vp], "sg_op_cfInterp": [vp, vp, vp], "sg_op_createCoarsened": [vp, pvp, vp, ci], "sg_op_zeroCovered": [vp, vp, vp],
     "sg_field_copyTo": [vp, vp, ci],
+    "sg_cell_to_edge": [vp, vp, vp], "sg_edge_to_cell": [vp, vp, vp], "sg_mac_gradient": [vp, vp, dp, vp, vp],
+    "sg_icemask_ec": [vp, vp, vp], "sg_compute_qw": [C.POINTER(Params), vp, vp, vp, vp],
+    "sg_compute_scaprod": [vp, vp, vp, vp, vp], "sg_compute_dcoeff": [vp, vp, vp, vp, cd, ci],
+    "sg_compute_difterm": [vp, dp, vp, vp, vp], "sg_time_varying_recharge": [vp, vp, cd, cd],
+    "sg_calc_melting_rate": [C.POINTER(PicardParams), vp, vp, vp, vp, vp, vp, vp, vp, vp],
+    "sg_rhs_head": [C.POINTER(PicardParams), vp, vp, vp, vp, vp, vp, vp, vp, vp],
+    "sg_rhs_gap": [C.POINTER(PicardParams), vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, cd],
+    "sg_gap_euler": [vp, vp, vp, cd],
     "sg_solver_define": [vp, pvp, ci], "sg_solver_destroy": [vp], "sg_solver_depth": [vp, ci, ip],
     "sg_solver_solve": [vp, pvp, pvp, ci, ci, C.POINTER(SolverParams), dp, C.POINTER(SolveStats)],
     "sg_solver_cell_updates_per_cycle": [vp, C.POINTER(SolverParams), dp],

@@ -4,6 +4,7 @@
 #include "../../include/suhmo_gpu.h"
 #include "sg_kernels.cuh"
 #include "sg_general.cuh"
+#include "sg_picard.cuh"
 #include "sg_nccl.h"
 
 #include <algorithm>
@@ -931,6 +932,8 @@ extern "C" int sg_wflx_level(sg_ctx* ctx, const sg_params* p, sg_field* bX, sg_f
                                                 "are needed; call sg_op_UpdateOperator(op, phi, phi_coarse, ...)");
   return wflx_impl(ctx, nullptr, p, bX, bY, u, nullptr, B, mask, dx);
 }
+
+#include "sg_picard_host.inc"
 
 // ------------------------------------------------------------------------------------------------
 // factory
