@@ -305,11 +305,12 @@ def main():
                        "step": "one FAS V-cycle incl. UpdateOperator/AverageOperator and residual max-norm",
                        "pre": 4, "post": 4, "bottom": args.bottom, "partition": f"box-wise y-strips over {world} GPU(s)",
                        "l2_policy": "inputs larger than L2 (finest-level fields 512 MiB each)",
-                       "relax_mode": {0: "separate colour passes", 1: "streaming red+black sweep, cp.async-staged", 2: "register-only fused sweep"}[args.relax_mode],
+                       "relax_mode": {0: "separate colour passes", 1: "streaming red+black sweep, cp.async-staged", 2: "register-only fused sweep", 3: "streaming sweep, two GSRB iterations per pass (temporal blocking), cp.async-staged"}[args.relax_mode],
                        "e2e_step": f"one head solve = H2D of 8 fields + set-up + {args.e2e_cycles} V-cycles + D2H of head"},
-            "roofline": {"bound": "hbm", "kernel": "k_gsrb_stream (finest level)" if args.relax_mode == 1 else "levelGSRB (finest level)", "achieved": achieved, "peak": peak,
+            "roofline": {"bound": "hbm", "kernel": {1: "k_gsrb_stream", 3: "k_gsrb_stream2 (2 iterations per launch)"}.get(args.relax_mode, "levelGSRB") + ", finest level", "achieved": achieved, "peak": peak,
                          "unit": "GB/s", "frac": achieved / peak, "traffic": NCU_TRAFFIC.get((size, args.relax_mode)), "peak_source": peak_src,
-                         "kernel_ms": k_ms, "bytes_per_cell_update": BYTES_PER_UPDATE_SMOOTHER,
+                         "kernel_ms": k_ms, "iterations_per_launch": 2 if args.relax_mode == 3 else 1,
+                         "launch_ms": k_ms * (2 if args.relax_mode == 3 else 1), "bytes_per_cell_update": BYTES_PER_UPDATE_SMOOTHER,
                          "vcycle_gbs_at_97B": value / world * BYTES_PER_UPDATE_VCYCLE / 1e9},
             "cpu_baseline": cpu,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": e2e_bytes_in, "d2h_bytes_per_step": e2e_bytes_out,

@@ -296,8 +296,10 @@ int sg_solver_solve(sg_solver* s, sg_field* const* phi, sg_field* const* rhs, in
                     sg_solve_stats* stats);
 /* cell-updates one V-cycle performs with these parameters (metric of SURVEY.md 8d) */
 int sg_solver_cell_updates_per_cycle(const sg_solver* s, const sg_solver_params* sp, double* out);
-/* relax implementation switch for experiments/tests: 0 = separate colour passes (generic), 1 = streaming red+black
-   sweep staged through shared memory with cp.async (default), 2 = first-generation register-only fused sweep */
+/* relax implementation switch for experiments/tests: 0 = separate colour passes (the reference's flow), 1 = streaming
+   red+black sweep staged through shared memory with cp.async, one iteration per sweep (default), 2 = first-generation register-only
+   fused sweep, 3 = two iterations per sweep (temporal blocking; issue-bound today) with mode 1 for an odd
+   remainder */
 int sg_set_relax_mode(sg_ctx* ctx, int mode);
 /* experiment knobs, 0 = library default.  key 0: rows per warp of the fused sweep; key 1: resident CTAs per SM (3|4) */
 int sg_set_tuning(sg_ctx* ctx, int key, int value);

@@ -297,7 +297,7 @@ extern "C" int sg_set_tuning(sg_ctx* c, int key, int value) {
   return SG_OK;
 }
 extern "C" int sg_set_relax_mode(sg_ctx* c, int mode) {
-  REQUIRE(c && mode >= 0 && mode <= 2, "sg_set_relax_mode");
+  REQUIRE(c && mode >= 0 && mode <= 3, "sg_set_relax_mode");
   c->relax_mode = mode;
   return SG_OK;
 }
@@ -971,14 +971,16 @@ extern "C" int sg_factory_refToFiner(const sg_factory* f, int level, int* out) {
 // coefficient ghosts on SK_GHOST sides (periodic images / neighbouring ranks): depth 1, needed by the fused sweep
 static int coef_ghosts(sg_op* op, bool only_b) {
   if (!has_ghost_sides(op->lay)) return SG_OK;
-  SGCALL(fill_ghosts(op->bX, 1));
-  SGCALL(fill_ghosts(op->bY, 1));
+  // depth 3: the two-iteration sweep recomputes a ring of up to 3 ghost cells on SK_GHOST sides
+  const int d = std::min(3, std::min(op->lay->nx, op->lay->ny));
+  SGCALL(fill_ghosts(op->bX, d));
+  SGCALL(fill_ghosts(op->bY, d));
   if (only_b) return SG_OK;
-  SGCALL(fill_ghosts(op->B, 1));
-  SGCALL(fill_ghosts(op->Pi, 1));
-  SGCALL(fill_ghosts(op->zb, 1));
-  SGCALL(fill_ghosts(op->mask, 1));
-  if (op->alpha != 0.0) SGCALL(fill_ghosts(op->aCoef, 1));
+  SGCALL(fill_ghosts(op->B, d));
+  SGCALL(fill_ghosts(op->Pi, d));
+  SGCALL(fill_ghosts(op->zb, d));
+  SGCALL(fill_ghosts(op->mask, d));
+  if (op->alpha != 0.0) SGCALL(fill_ghosts(op->aCoef, d));
   return SG_OK;
 }
 
@@ -1107,54 +1109,70 @@ static int relax_impl(sg_op* op, sg_field* phi, const sg_field* rhs, int iterati
   OpArgs a = make_args(op);
   bool ghosts = has_ghost_sides(L);
   if (c->relax_mode >= 1) {
-    const bool stream = c->relax_mode == 1;
+    // mode 1: one iteration per sweep (k_gsrb_stream); mode 3 (default): two iterations per sweep (k_gsrb_stream2) and a
+    // single sweep for an odd remainder; mode 2: first-generation register-only sweep
     sg_field* scratch;
     SGCALL(ws_field(L, 0, 1, &scratch));
-    if (ghosts) SGCALL(fill_ghosts(const_cast<sg_field*>(rhs), 1));
+    // temporal blocking recomputes a 4-cell ring: periodic images inside the patch must then be at least 4 cells away
+    const bool can2 = c->relax_mode == 3 && (!L->wrap_local[0] || L->nx >= 4) && (!L->wrap_local[1] || L->ny >= 4) && L->ny >= 4;
+    if (ghosts) SGCALL(fill_ghosts(const_cast<sg_field*>(rhs), can2 ? 3 : 1));
     FusedArgs f;
     f.a = a;
     f.rhs = rhs->p();
     f.sdx[0] = -op->dx[0]; f.sdx[1] = op->dx[0]; f.sdx[2] = -op->dx[1]; f.sdx[3] = op->dx[1];
-    f.nstrips = (L->nx + FUSED_COLS - 1) / FUSED_COLS;
+    static bool attr_set = false;
+    if (!attr_set) {
+      // warp-private staging rings: 4 warps x stages x (8|9) arrays x 32 lanes x 16 B
+      CK(cudaFuncSetAttribute(k_gsrb_stream<0, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 * GS_STAGES * 8 * 512));
+      CK(cudaFuncSetAttribute(k_gsrb_stream<1, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 * GS_STAGES * 9 * 512));
+      CK(cudaFuncSetAttribute(k_gsrb_stream2<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 * GS2_STAGES * 8 * 512));
+      CK(cudaFuncSetAttribute(k_gsrb_stream2<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 * GS2_STAGES * 9 * 512));
+      attr_set = true;
+    }
     // Segments of rows per warp.  Measured on B200 (tools/relax_bench.py): many short segments beat one resident wave
     // (warps marching in lock-step), 32-64 rows per warp is the plateau on HBM-sized levels, and L2-resident levels want
-    // the shortest segments that still amortise the 4 load-only steps of a segment.
-    int minb = stream ? 3 : (c->tune[1] == 3 ? 3 : 4);
-    int capacity = c->num_sms * minb * 4; // resident warps (128-thread CTAs)
-    int nsegs;
-    if (c->tune[0] > 0) nsegs = (L->ny + c->tune[0] - 1) / c->tune[0];
-    else if (stream) {
-      long long rows = ((long long)f.nstrips * L->ny) / (4LL * capacity);
-      rows = std::max(8LL, std::min(48LL, rows));
-      nsegs = (int)((L->ny + rows - 1) / rows);
-    } else if (f.nstrips * ((L->ny + 63) / 64) <= capacity) nsegs = std::max(1, std::min((L->ny + 31) / 32, capacity / f.nstrips));
-    else {
-      nsegs = capacity / f.nstrips;               // one full wave ...
-      if (nsegs < 1 || L->ny / nsegs > 1024) nsegs = (L->ny + 63) / 64; // ... unless segments get too long: many waves
-    }
-    f.rows_per_warp = (L->ny + nsegs - 1) / nsegs;
-    f.nsegs = (L->ny + f.rows_per_warp - 1) / f.rows_per_warp;
-    int nwarps = f.nstrips * f.nsegs;
-    int blocks = (nwarps * 32 + 127) / 128;
-    for (int it = 0; it < iterations; it++) {
-      if (ghosts) SGCALL(fill_ghosts(phi, 2));
+    // the shortest segments that still amortise the load-only steps of a segment (4 for one iteration, 9 for two).
+    auto plan = [&](int kind) { // 1 stream, 2 fused, 3 stream2
+      const int cols = kind == 3 ? GS2_COLS : kind == 1 ? GS_COLS : FUSED_COLS;
+      f.nstrips = (L->nx + cols - 1) / cols;
+      int minb = kind == 3 ? 2 : kind == 1 ? 3 : (c->tune[1] == 3 ? 3 : 4);
+      int capacity = c->num_sms * minb * 4; // resident warps (128-thread CTAs)
+      int nsegs;
+      if (c->tune[0] > 0) nsegs = (L->ny + c->tune[0] - 1) / c->tune[0];
+      else if (kind == 1 || kind == 3) {
+        long long rows = ((long long)f.nstrips * L->ny) / (4LL * capacity);
+        rows = kind == 3 ? std::max(16LL, std::min(96LL, rows)) : std::max(8LL, std::min(48LL, rows));
+        nsegs = (int)((L->ny + rows - 1) / rows);
+      } else if (f.nstrips * ((L->ny + 63) / 64) <= capacity) nsegs = std::max(1, std::min((L->ny + 31) / 32, capacity / f.nstrips));
+      else {
+        nsegs = capacity / f.nstrips;               // one full wave ...
+        if (nsegs < 1 || L->ny / nsegs > 1024) nsegs = (L->ny + 63) / 64; // ... unless segments get too long: many waves
+      }
+      f.rows_per_warp = (L->ny + nsegs - 1) / nsegs;
+      f.nsegs = (L->ny + f.rows_per_warp - 1) / f.rows_per_warp;
+      return (f.nstrips * f.nsegs * 32 + 127) / 128;
+    };
+    int it = 0;
+    while (it < iterations) {
+      const bool two = can2 && it + 2 <= iterations;
+      const int kind = two ? 3 : (c->relax_mode == 2 ? 2 : 1);
+      const int blocks = plan(kind);
+      if (ghosts) SGCALL(fill_ghosts(phi, two ? 4 : 2));
       f.phi_in = phi->p();
       f.phi_out = scratch->p();
-      if (stream) {
-        // 4 warps x GS_STAGES row bundles x (8|9) arrays x 32 lanes x 16 B of warp-private staging rings
-        static bool attr_set = false;
-        if (!attr_set) {
-          CK(cudaFuncSetAttribute(k_gsrb_stream<0, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 * GS_STAGES * 8 * 512));
-          CK(cudaFuncSetAttribute(k_gsrb_stream<1, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 * GS_STAGES * 9 * 512));
-          attr_set = true;
-        }
-        if (a.has_a) { k_gsrb_stream<1, 3><<<blocks, 128, 4 * GS_STAGES * 9 * 512, c->stream>>>(f); c->launches++; }
-        else { k_gsrb_stream<0, 3><<<blocks, 128, 4 * GS_STAGES * 8 * 512, c->stream>>>(f); c->launches++; }
-      }
-      else if (a.has_a) LAUNCH(c, (k_gsrb_fused<1, 4>), blocks, 128, f);
-      else if (minb == 3) LAUNCH(c, (k_gsrb_fused<0, 3>), blocks, 128, f);
+      if (kind == 3) {
+        if (a.has_a) k_gsrb_stream2<1><<<blocks, 128, 4 * GS2_STAGES * 9 * 512, c->stream>>>(f);
+        else k_gsrb_stream2<0><<<blocks, 128, 4 * GS2_STAGES * 8 * 512, c->stream>>>(f);
+        c->launches++;
+      } else if (kind == 1) {
+        if (a.has_a) k_gsrb_stream<1, 3><<<blocks, 128, 4 * GS_STAGES * 9 * 512, c->stream>>>(f);
+        else k_gsrb_stream<0, 3><<<blocks, 128, 4 * GS_STAGES * 8 * 512, c->stream>>>(f);
+        c->launches++;
+      } else if (a.has_a) LAUNCH(c, (k_gsrb_fused<1, 4>), blocks, 128, f);
+      else if (c->tune[1] == 3) LAUNCH(c, (k_gsrb_fused<0, 3>), blocks, 128, f);
       else LAUNCH(c, (k_gsrb_fused<0, 4>), blocks, 128, f);
       std::swap(phi->base, scratch->base); // out-of-place sweep: the field now owns the new buffer
+      it += two ? 2 : 1;
     }
   } else {
     for (int it = 0; it < iterations; it++) {

@@ -5,7 +5,7 @@
 // bit-identical to the CPU oracle (IEEE add/mul/div/sqrt), not merely within 1e-10.
 //
 // Data layout: a level on one GPU is one rectangular patch.  Every field is a pitched 2-D FP64 array,
-// x fastest, with SG_XOFF pad/ghost columns on both sides and SG_YOFF ghost rows below (and >= 3 above),
+// x fastest, with SG_XOFF pad/ghost columns on both sides and SG_YOFF ghost rows below (and SG_YTOP above),
 // so that cell/face (0,0) of the patch sits on a 128-byte boundary and double2 accesses of even columns
 // are aligned.  Kernel pointers are pre-offset to local (0,0): element (i,j) is p[j*pitch + i].
 #pragma once
@@ -13,8 +13,8 @@
 #include <stdint.h>
 
 #define SG_XOFF 16
-#define SG_YOFF 2
-#define SG_YTOP 4
+#define SG_YOFF 4
+#define SG_YTOP 6
 
 // side kinds of the rank-local patch
 enum { SK_PHYS_DIRI = 0, SK_PHYS_NEUM = 1, SK_GHOST = 2, SK_FROZEN = 3, SK_PHYS_NONE = 4 };
@@ -533,6 +533,138 @@ __global__ void __launch_bounds__(128, MINB) k_gsrb_stream(FusedArgs f) {
       else if (st0) o[0] = p0.x;
       else if (st1) o[1] = p0.y;
     }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// k_gsrb_stream2: TWO levelGSRB iterations per sweep (temporal blocking).  Same strip/ring/cp.async scheme as
+// k_gsrb_stream; the second iteration trails the first by three rows inside the same warp:
+//   step q:  RED_1(q+1)  RED_2(q-2)  |  BLACK_1(q)  BLACK_2(q-3)  |  store row q-3
+// so the two chains of a step are independent (ILP 2) and every array is read ONCE per two iterations: 72 B -> 41 B of
+// HBM traffic per cell-update (56 of 64 columns stored).  The reference's ghost refresh between iterations (exchange +
+// BC) is what the ring recompute / on-the-fly BC already provide, so the result is bit-identical to two single sweeps.
+// Coefficient rows are re-read from the shared-memory ring at each of their four uses instead of living in registers.
+// SK_GHOST sides need depth-4 ghosts of phi and depth-3 ghosts of the coefficients.
+// ------------------------------------------------------------------------------------------------
+#define GS2_COLS 56
+#define GS2_D 2
+#define GS2_LIVE 5
+#define GS2_STAGES (GS2_LIVE + GS2_D)
+
+template <int HAS_A>
+__global__ void __launch_bounds__(128, 2) k_gsrb_stream2(FusedArgs f) {
+  extern __shared__ double2 gs_smem[];
+  constexpr int NARR = 8 + HAS_A;
+  const OpArgs& a = f.a;
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  const int warp = blockIdx.x * 4 + wib;
+  if (warp >= f.nstrips * f.nsegs) return;
+  const int strip = warp % f.nstrips, seg = warp / f.nstrips;
+  const int nx = a.g.nx, ny = a.g.ny;
+  const ptrdiff_t P = a.g.pitch;
+  const int x0 = strip * GS2_COLS - 4 + 2 * lane; // columns x0, x0+1 (x0 even)
+  const int r0 = seg * f.rows_per_warp;
+  const int r1 = min(ny, r0 + f.rows_per_warp);
+  GsBC bc;
+  bc.kxlo = a.g.kind[0]; bc.kxhi = a.g.kind[1]; bc.kylo = a.g.kind[2]; bc.kyhi = a.g.kind[3];
+  bc.nx = nx; bc.ny = ny;
+  bc.v0 = a.g.bcval[0]; bc.v1 = a.g.bcval[1]; bc.v2 = a.g.bcval[2]; bc.v3 = a.g.bcval[3];
+  bc.s0 = f.sdx[0]; bc.s1 = f.sdx[1]; bc.s2 = f.sdx[2]; bc.s3 = f.sdx[3];
+  bc.xany = (strip == 0 && bc.kxlo <= SK_PHYS_NEUM) || (strip * GS2_COLS + GS2_COLS + 3 >= nx - 1 && bc.kxhi <= SK_PHYS_NEUM);
+  // cells that exist for updating: valid cells, or ghost cells (images of cells another patch updates identically) on SK_GHOST sides
+  auto cellok = [&](int x) -> bool { return (x >= 0 && x < nx) || (x < 0 && x >= -3 && bc.kxlo == SK_GHOST) || (x >= nx && x <= nx + 2 && bc.kxhi == SK_GHOST); };
+  const bool ok0 = cellok(x0), ok1 = cellok(x0 + 1);
+  // columns each colour pass may commit: the usable part of the warp shrinks by one column per pass
+  const bool r1c0 = ok0 && lane >= 1, r1c1 = ok1 && lane <= 30;                  // RED_1: all but the outermost column
+  const bool b1c0 = ok0 && lane >= 1 && lane <= 30, b1c1 = ok1 && lane >= 1 && lane <= 30; // BLACK_1: columns 2..61
+  const bool r2c0 = ok0 && lane >= 2 && lane <= 30, r2c1 = ok1 && lane >= 1 && lane <= 29; // RED_2: columns 3..60
+  const bool st0 = lane >= 2 && lane <= 29 && x0 >= 0 && x0 < nx;               // BLACK_2 + store: columns 4..59, valid cells
+  const bool st1 = lane >= 2 && lane <= 29 && x0 + 1 >= 0 && x0 + 1 < nx;
+  const int gpar = (a.g.glo0 + a.g.glo1) & 1;
+
+  double2* ring = gs_smem + (size_t)wib * (GS2_STAGES * NARR * 32) + lane;
+  const double* g0 = f.phi_in + x0; const double* g1 = a.bY + x0;
+  const double* g2 = f.rhs + x0; const double* g3 = a.B + x0; const double* g4 = a.Pi + x0; const double* g5 = a.zb + x0;
+  const double* g6 = a.mask + x0; const double* g7 = a.bX + x0; const double* g8 = HAS_A ? a.aC + x0 : nullptr;
+  const int qlast = r1 + 2;
+  auto issue = [&](int q, int stage) {
+    if (q <= qlast) {
+      const ptrdiff_t o2 = (ptrdiff_t)min(q + 2, ny + SG_YTOP - 1) * P, o1 = (ptrdiff_t)max(q + 1, -SG_YOFF) * P;
+      double2* s = ring + (size_t)stage * (NARR * 32);
+      cp_async16(s, g0 + o2); cp_async16(s + 32, g1 + o2);
+      cp_async16(s + 64, g2 + o1); cp_async16(s + 96, g3 + o1); cp_async16(s + 128, g4 + o1); cp_async16(s + 160, g5 + o1);
+      cp_async16(s + 192, g6 + o1); cp_async16(s + 224, g7 + o1);
+      if (HAS_A) cp_async16(s + 256, g8 + o1);
+    }
+    cp_async_commit();
+  };
+  auto coefs = [&](int stage) -> GsRow { // cell coefficients + x-face coefficient of the row that bundle carries
+    const double2* s = ring + (size_t)stage * (NARR * 32);
+    GsRow c;
+    c.rhs = s[64]; c.B = s[96]; c.Pi = s[128]; c.zb = s[160]; c.mk = s[192]; c.bx = s[224];
+    c.ac = HAS_A ? s[256] : make_double2(0.0, 0.0);
+    return c;
+  };
+  auto rowupd = [&](int j) -> bool { return (j >= 0 && j < ny) || (j < 0 && j >= -3 && bc.kylo == SK_GHOST) || (j >= ny && j <= ny + 2 && bc.kyhi == SK_GHOST); };
+  auto back = [&](int stage, int k) -> int { int s = stage - k; return s < 0 ? s + GS2_STAGES : s; };
+
+  const double2 z2 = make_double2(0.0, 0.0);
+  double2 a0 = z2, a1 = z2, a2 = z2, a3 = z2, a4 = z2, a5 = z2, a6 = z2; // phi rows q-4 .. q+2
+  double2 y0 = z2, y1 = z2, y2 = z2, y3 = z2, y4 = z2, y5 = z2;          // y-face coefficient rows q-3 .. q+2
+  const int qstart = r0 - 6;
+#pragma unroll
+  for (int d = 0; d < GS2_D; d++) issue(qstart + d, d);
+  int stage = 0;
+  for (int q = qstart; q <= qlast; q++) {
+    cp_async_wait<GS2_D - 1>();
+    a0 = a1; a1 = a2; a2 = a3; a3 = a4; a4 = a5; a5 = a6;
+    y0 = y1; y1 = y2; y2 = y3; y3 = y4; y4 = y5;
+    {
+      const double2* s = ring + (size_t)stage * (NARR * 32);
+      a6 = s[0]; y5 = s[32];
+    }
+    {
+      int st = stage + GS2_D; // the slot of bundle q - GS2_LIVE, last read one step ago
+      if (st >= GS2_STAGES) st -= GS2_STAGES;
+      issue(q + GS2_D, st);
+    }
+    // ---- four point updates per step, straight-line per row parity so that the two independent chains
+    //      (RED_1 -> BLACK_1 and RED_2 -> BLACK_2) interleave; passes outside their row range compute and do not commit
+    const bool do_r1 = q + 1 >= r0 - 3 && q + 1 <= r1 + 2 && rowupd(q + 1);
+    const bool do_r2 = q - 2 >= r0 - 1 && q - 2 <= r1 && rowupd(q - 2);
+    const bool do_b1 = q >= r0 - 2 && q <= r1 + 1 && rowupd(q);
+    const bool do_b2 = q - 3 >= r0 && q - 3 < r1;
+    { // (in the first steps of a segment some passes read ring slots that were never loaded: they do not commit)
+      const GsRow cr1 = coefs(stage), cr2 = coefs(back(stage, 3));
+      if ((gpar + q + 1) & 1) { // rows q+1 and q-3 have this parity, rows q and q-2 the other
+        double n1 = gs_update<1, HAS_A>(a, bc, q + 1, x0 + 1, cr1, a5, a4, a6, y4, y5);
+        double n2 = gs_update<0, HAS_A>(a, bc, q - 2, x0, cr2, a2, a1, a3, y1, y2);
+        if (do_r1 && r1c1) a5.y = n1;
+        if (do_r2 && r2c0) a2.x = n2;
+        const GsRow cb1 = coefs(back(stage, 1)), cb2 = coefs(back(stage, 4));
+        double m1 = gs_update<1, HAS_A>(a, bc, q, x0 + 1, cb1, a4, a3, a5, y3, y4);
+        double m2 = gs_update<0, HAS_A>(a, bc, q - 3, x0, cb2, a1, a0, a2, y0, y1);
+        if (do_b1 && b1c1) a4.y = m1;
+        if (do_b2 && st0) a1.x = m2;
+      } else {
+        double n1 = gs_update<0, HAS_A>(a, bc, q + 1, x0, cr1, a5, a4, a6, y4, y5);
+        double n2 = gs_update<1, HAS_A>(a, bc, q - 2, x0 + 1, cr2, a2, a1, a3, y1, y2);
+        if (do_r1 && r1c0) a5.x = n1;
+        if (do_r2 && r2c1) a2.y = n2;
+        const GsRow cb1 = coefs(back(stage, 1)), cb2 = coefs(back(stage, 4));
+        double m1 = gs_update<0, HAS_A>(a, bc, q, x0, cb1, a4, a3, a5, y3, y4);
+        double m2 = gs_update<1, HAS_A>(a, bc, q - 3, x0 + 1, cb2, a1, a0, a2, y0, y1);
+        if (do_b1 && b1c0) a4.x = m1;
+        if (do_b2 && st1) a1.y = m2;
+      }
+      if (do_b2) {
+        double* o = f.phi_out + (ptrdiff_t)(q - 3) * P + x0;
+        if (st0 && st1) *reinterpret_cast<double2*>(o) = a1;
+        else if (st0) o[0] = a1.x;
+        else if (st1) o[1] = a1.y;
+      }
+    }
+    stage = stage + 1 == GS2_STAGES ? 0 : stage + 1;
   }
 }
 
