@@ -106,6 +106,13 @@ int sg_layout_coarsen(sg_layout* lay, int ratio, sg_layout** out); /* coarsen_db
 int sg_layout_coarsenable(const sg_layout* lay, int ratio, int* out);
 int sg_layout_nbox(const sg_layout* lay, int* nbox);
 int sg_layout_destroy(sg_layout* lay);
+/* Host-only planning of the box-wise partition (no CUDA device needed).  sg_partition_boxes = LoadBalance for strips
+   (src/AmrHydro.cpp:4847,4929): owner[b] per box, contiguous rows of boxes with equal cell counts.  sg_partition_describe =
+   what `rank` then holds: its rectangle {lo0,lo1,hi0,hi1}, the neighbour rank across each side (x-lo, x-hi, y-lo, y-hi;
+   -1 none) and the doubles per exchanged halo row. */
+int sg_partition_boxes(int nbox, const int* boxes, int nranks, int* owner_out);
+int sg_partition_describe(int nbox, const int* boxes, const int* owner, const int domain[4], const int periodic[2], int rank,
+                          int nranks, int patch_out[4], int nbr_out[4], long long* halo_row_doubles);
 
 /* ------------------------------------------------------------------ fields ------------------------------- */
 /* LevelData<FArrayBox>(grids, ncomp, nghost*IntVect::Unit) / LevelData<FluxBox> direction. */

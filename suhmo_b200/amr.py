@@ -69,6 +69,25 @@ class Context:
             self.h = None
 
 
+def partition_boxes(boxes, nranks):
+    """LoadBalance for the strip partition: owner per box (host only, no device)."""
+    boxes = np.ascontiguousarray(boxes, dtype=np.int32).reshape(-1, 4)
+    owner = np.zeros(len(boxes), dtype=np.int32)
+    check(lib().sg_partition_boxes(len(boxes), _ip(boxes), nranks, _ip(owner)))
+    return owner
+
+
+def partition_describe(boxes, owner, domain, periodic, rank, nranks):
+    """(patch [lo0,lo1,hi0,hi1], neighbour ranks [x-lo,x-hi,y-lo,y-hi], doubles per halo row) of `rank` (host only)."""
+    boxes = np.ascontiguousarray(boxes, dtype=np.int32).reshape(-1, 4)
+    owner = np.ascontiguousarray(owner, dtype=np.int32)
+    dom = np.ascontiguousarray(domain, dtype=np.int32)
+    per = np.ascontiguousarray(periodic, dtype=np.int32)
+    patch, nbr, row = np.zeros(4, dtype=np.int32), np.zeros(4, dtype=np.int32), C.c_longlong()
+    check(lib().sg_partition_describe(len(boxes), _ip(boxes), _ip(owner), _ip(dom), _ip(per), rank, nranks, _ip(patch), _ip(nbr), C.byref(row)))
+    return patch, nbr, row.value
+
+
 class DisjointBoxLayout:
     """boxes [nbox,4] = lo0 lo1 hi0 hi1; domain = ProblemDomain box; periodic flags; owner = procIDs."""
 

@@ -57,6 +57,7 @@ SIGNATURES = {
     "sg_ctx_event_record": [vp, ci], "sg_ctx_event_elapsed_ms": [vp, ci, ci, dp], "sg_solver_refresh": [vp], "sg_set_relax_mode": [vp, ci], "sg_set_tuning": [vp, ci, ci],
     "sg_layout_create": [vp, pvp, ci, ip, ip, ip, ip], "sg_layout_coarsen": [vp, ci, pvp],
     "sg_layout_coarsenable": [vp, ci, ip], "sg_layout_nbox": [vp, ip], "sg_layout_destroy": [vp],
+    "sg_partition_boxes": [ci, ip, ci, ip], "sg_partition_describe": [ci, ip, ip, ip, ip, ci, ci, ip, ip, C.POINTER(C.c_longlong)],
     "sg_field_create": [vp, pvp, ci, ci, ci], "sg_field_destroy": [vp],
     "sg_field_upload_box": [vp, ci, dp], "sg_field_download_box": [vp, ci, dp],
     "sg_field_upload": [vp, pvp], "sg_field_download": [vp, pvp],

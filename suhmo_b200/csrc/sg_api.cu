@@ -359,7 +359,8 @@ static int layout_tables(sg_layout* L) {
   return SG_OK;
 }
 
-static int layout_finish(sg_layout* L) {
+// host part of a layout: ownership, merged patch / per-box patches, neighbour ranks (no device calls)
+static int layout_host(sg_layout* L) {
   sg_ctx* c = L->ctx;
   // per-rank bounding rectangles; a rank whose boxes tile its rectangle exactly stores the level as ONE merged patch
   std::vector<Box> rp(c->nranks);
@@ -406,7 +407,7 @@ static int layout_finish(sg_layout* L) {
       L->patches.push_back(g);
     }
     L->total = tot;
-    return layout_tables(L);
+    return SG_OK;
   }
   if (!L->has_local) return SG_OK;
   L->patch = rp[c->rank];
@@ -469,7 +470,64 @@ static int layout_finish(sg_layout* L) {
     for (int b = 0; b < L->nbox; b++)
       if (L->owner[b] == c->rank) L->patch_of_box[b] = 0;
   }
+  return SG_OK;
+}
+static int layout_finish(sg_layout* L) {
+  SGCALL(layout_host(L));
   return layout_tables(L);
+}
+
+// ---- host-only views of the partition (no CUDA device needed): what the gloo tests and a driver's planning use ----
+// LoadBalance for the box-wise strip partition (absent Chombo LoadBalance as called at src/AmrHydro.cpp:4847,4929):
+// contiguous runs of the (y-major sorted) box list with equal cell counts, cut only between whole rows of boxes so that
+// every rank's boxes tile one rectangle.
+extern "C" int sg_partition_boxes(int nbox, const int* boxes, int nranks, int* owner_out) {
+  REQUIRE(nbox > 0 && boxes && nranks >= 1 && owner_out, "sg_partition_boxes: bad arguments");
+  // distinct box rows (by lo1), cells per row
+  std::map<int, long long> row_cells;
+  long long total = 0;
+  for (int b = 0; b < nbox; b++) {
+    long long n = (long long)(boxes[4 * b + 2] - boxes[4 * b] + 1) * (boxes[4 * b + 3] - boxes[4 * b + 1] + 1);
+    row_cells[boxes[4 * b + 1]] += n;
+    total += n;
+  }
+  REQUIRE((int)row_cells.size() >= nranks, "sg_partition_boxes: %d rows of boxes cannot be cut into %d strips", (int)row_cells.size(), nranks);
+  std::map<int, int> row_owner;
+  long long acc = 0;
+  int r = 0, rows_left = (int)row_cells.size();
+  for (auto& kv : row_cells) {
+    // move on when this rank has its share, but keep at least one row for every remaining rank
+    int ranks_left = nranks - r;
+    if (r < nranks - 1 && (acc >= total * (r + 1) / nranks || rows_left < ranks_left)) r++;
+    row_owner[kv.first] = r;
+    acc += kv.second;
+    rows_left--;
+  }
+  for (int b = 0; b < nbox; b++) owner_out[b] = row_owner[boxes[4 * b + 1]];
+  return SG_OK;
+}
+// the rank-local rectangle, the neighbour ranks across its four sides (-1: none; a periodic image that wraps onto the same
+// rank is "none" here, it needs no message) and the doubles per halo row a field exchange moves
+extern "C" int sg_partition_describe(int nbox, const int* boxes, const int* owner, const int domain[4], const int periodic[2], int rank,
+                                     int nranks, int patch_out[4], int nbr_out[4], long long* halo_row_doubles) {
+  REQUIRE(nbox > 0 && boxes && domain && periodic && patch_out && nbr_out && rank >= 0 && rank < nranks, "sg_partition_describe: bad arguments");
+  sg_ctx fake;
+  fake.rank = rank; fake.nranks = nranks;
+  sg_layout L;
+  L.ctx = &fake; L.nbox = nbox;
+  L.boxes.resize(nbox); L.owner.resize(nbox);
+  for (int b = 0; b < nbox; b++) {
+    L.boxes[b].lo[0] = boxes[4 * b]; L.boxes[b].lo[1] = boxes[4 * b + 1]; L.boxes[b].hi[0] = boxes[4 * b + 2]; L.boxes[b].hi[1] = boxes[4 * b + 3];
+    L.owner[b] = owner ? owner[b] : 0;
+  }
+  L.domain.lo[0] = domain[0]; L.domain.lo[1] = domain[1]; L.domain.hi[0] = domain[2]; L.domain.hi[1] = domain[3];
+  L.periodic[0] = periodic[0]; L.periodic[1] = periodic[1];
+  SGCALL(layout_host(&L));
+  REQUIRE(L.has_local, "sg_partition_describe: rank %d owns no box", rank);
+  patch_out[0] = L.patch.lo[0]; patch_out[1] = L.patch.lo[1]; patch_out[2] = L.patch.hi[0]; patch_out[3] = L.patch.hi[1];
+  for (int s2 = 0; s2 < 4; s2++) nbr_out[s2] = L.nbr[s2];
+  if (halo_row_doubles) *halo_row_doubles = L.pitch;
+  return SG_OK;
 }
 
 extern "C" int sg_layout_create(sg_ctx* ctx, sg_layout** out, int nbox, const int* boxes, const int* owner,
