@@ -978,8 +978,8 @@ static int wflx_impl(sg_ctx* ctx, sg_op* op, const sg_params* p, sg_field* bX, s
   SGCALL(exchange_any(grad, 1, 1)); // lvlgradH.exchange()
   SGCALL(extrap_any(grad, 0));      // ExtrapGhostCells(lvlgradH, levelDomain)
   grad->ng = ngsave;
-  LAUNCH(ctx, k_compute_re_g, grid_g(L, 2, 2), B2D, Re->cb(), B->cb(), grad->cb(0), grad->cb(1), L->d_patches, phys(*p));
-  LAUNCH(ctx, k_bcoef_faces_g, grid_g(L, 1, 1), B2D, bX->cb(), bY->cb(), Re->cb(), B->cb(), mask->cb(), L->d_patches, phys(*p),
+  (void)Re; // Re over the ghosted box is evaluated inside the face kernel (never stored)
+  LAUNCH(ctx, k_re_bcoef_g, dim3((L->max_nx + 1 + RB_TX - 1) / RB_TX, (L->max_ny + 1 + RB_TY - 1) / RB_TY, (unsigned)L->patches.size()), B2D, bX->cb(), bY->cb(), grad->cb(0), grad->cb(1), B->cb(), mask->cb(), L->d_patches, phys(*p),
          L->domain.lo[0], L->domain.lo[1], L->domain.hi[0], L->domain.hi[1]);
   return SG_OK;
 }
@@ -1269,7 +1269,10 @@ static int apply_impl(sg_op* op, sg_field* out, sg_field* phi, const sg_field* r
   sg_layout* L = op->lay;
   sg_ctx* c = op->ctx;
   if (!L->has_local) return SG_OK;
-  if (!L->fast) return apply_g(op, out, phi, rhs, homogeneous, mode, slot, true);
+  if (!L->fast) {
+    if (mode == 4) return fail(SG_ERR_UNSUPPORTED, "FAS coarse right-hand side accumulation exists on uniform (one-patch) levels only");
+    return apply_g(op, out, phi, rhs, homogeneous, mode == 3 ? 2 : mode, slot, true);
+  }
   OpArgs a = make_args(op);
   SGCALL(phys_bc(phi, &op->bc, op->dx, homogeneous));
   if (has_ghost_sides(L)) SGCALL(fill_ghosts(phi, 1));
@@ -1277,9 +1280,11 @@ static int apply_impl(sg_op* op, sg_field* out, sg_field* phi, const sg_field* r
   dim3 g = grid2(L->nx, L->ny, B2D);
   if (mode == 0) LAUNCH(c, k_apply<0>, g, B2D, out->p(), phi->p(), nullptr, a, nb);
   else if (mode == 1) LAUNCH(c, k_apply<1>, g, B2D, out->p(), phi->p(), rhs->p(), a, nb);
+  else if (mode == 4) LAUNCH(c, k_apply<4>, g, B2D, out->p(), phi->p(), nullptr, a, nb);
   else {
     CK(cudaMemsetAsync(nb, 0, sizeof(double), c->stream));
-    LAUNCH(c, k_apply<2>, g, B2D, out->p(), phi->p(), rhs->p(), a, nb);
+    if (mode == 3) LAUNCH(c, k_apply<3>, g, B2D, nullptr, phi->p(), rhs->p(), a, nb);
+    else LAUNCH(c, k_apply<2>, g, B2D, out->p(), phi->p(), rhs->p(), a, nb);
   }
   return SG_OK;
 }
@@ -1322,7 +1327,7 @@ extern "C" int sg_op_applyOpNoBoundary(sg_op* op, sg_field* lhs, sg_field* phi) 
   return SG_OK;
 }
 
-static int restrict_impl(sg_op* op, sg_field* resC, sg_field* phiC, sg_field* phiF, const sg_field* rhsF) {
+static int restrict_impl(sg_op* op, sg_field* resC, sg_field* phiC, sg_field* phiF, const sg_field* rhsF, sg_field* saveC = nullptr) {
   sg_layout* L = op->lay;
   sg_ctx* c = op->ctx;
   if (!L->has_local) return SG_OK;
@@ -1338,8 +1343,8 @@ static int restrict_impl(sg_op* op, sg_field* resC, sg_field* phiC, sg_field* ph
   }
   if (phiC) CK(cudaMemsetAsync(phiC->base, 0, phiC->comp_stride * sizeof(double), c->stream)); // phiCoarse.setVal(0.0)
   dim3 g = grid2(Lc->nx, Lc->ny, B2D);
-  if (phiC) LAUNCH(c, k_restrict<1>, g, B2D, resC ? resC->p() : nullptr, phiC->p(), Lc->pitch, phiF->p(), rhsF ? rhsF->p() : nullptr, a);
-  else LAUNCH(c, k_restrict<0>, g, B2D, resC->p(), nullptr, Lc->pitch, phiF->p(), rhsF->p(), a);
+  if (phiC) LAUNCH(c, k_restrict<1>, g, B2D, resC ? resC->p() : nullptr, phiC->p(), saveC ? saveC->p() : nullptr, Lc->pitch, phiF->p(), rhsF ? rhsF->p() : nullptr, a);
+  else LAUNCH(c, k_restrict<0>, g, B2D, resC->p(), nullptr, nullptr, Lc->pitch, phiF->p(), rhsF->p(), a);
   return SG_OK;
 }
 extern "C" int sg_op_restrictResidual(sg_op* op, sg_field* res_coarse, sg_field* phi_fine, const sg_field* phi_coarse,
@@ -1717,10 +1722,8 @@ static int mg_cycle(sg_solver* s, int depth, sg_field* phi, sg_field* rhs, const
   sg_op* opc = s->ops[dc];
   if (op->update_operator) SGCALL(sg_op_AverageOperator(opc, s->ops[0], dc));
   // restrictR + restrictResidual in one sweep over the fine level
-  SGCALL(restrict_impl(op, s->rhs[dc], s->phi[dc], phi, rhs));
-  SGCALL(vec_launch<3>(s->save[dc], s->phi[dc], nullptr, 0, 0, true));                    // assignLocal
-  SGCALL(apply_impl(opc, s->tmp[dc], s->phi[dc], nullptr, 0, 0, 0));                     // applyOpMg(tmp, phiC, NULL, false)
-  SGCALL(vec_launch<1>(s->rhs[dc], s->tmp[dc], nullptr, 1.0, 0, false));                 // rhsC += L(phiC)
+  SGCALL(restrict_impl(op, s->rhs[dc], s->phi[dc], phi, rhs, s->save[dc]));              // ... and assignLocal(saved, phiC)
+  SGCALL(apply_impl(opc, s->rhs[dc], s->phi[dc], nullptr, 0, 4, 0));                     // rhsC += applyOpMg(phiC, NULL, false)
   SGCALL(mg_cycle(s, dc, s->phi[dc], s->rhs[dc], sp));
   if (op->lay->has_local) {                                                             // phi += I(phiC_new - phiC_saved)
     sg_layout* L = op->lay;
@@ -1769,7 +1772,7 @@ static int vcycle(sg_solver* s, sg_field* const* phi, sg_field* const* rhs, int 
 // d_scalar[slot] on all ranks
 static int residual_norm(sg_solver* s, sg_field* const* phi, sg_field* const* rhs, int l_max, int slot) {
   if (l_max == 0) {
-    SGCALL(apply_impl(s->ops[0], s->resid, phi[0], rhs[0], 0, 2, slot));
+    SGCALL(apply_impl(s->ops[0], s->resid, phi[0], rhs[0], 0, 3, slot)); // max-norm only, the residual itself is not needed
     return global_reduce(s->ctx, slot, true);
   }
   sg_ctx* c = s->ctx;

@@ -222,6 +222,51 @@ __global__ void __launch_bounds__(256) k_bcoef_faces_g(double* __restrict__ bXb,
   }
 }
 
+// COMPUTERE + CellToEdge(Re), CellToEdge(B), setup_iceMask_EC, COMPUTEBCOEFF in one pass.  A 32x8 block evaluates Re on a
+// 32x8 window of cells (one evaluation per thread: Re is FP64 sqrt/div heavy) shifted one cell down/left, shares it
+// through shared memory, and threads (tx>=1, ty>=1) write the two faces of their cell: windows overlap by one row and one
+// column (31x7 outputs per block).  Re is never stored: 48 B per cell instead of 72 B.  Same arithmetic.
+#define RB_TX 31
+#define RB_TY 7
+__global__ void __launch_bounds__(256) k_re_bcoef_g(double* __restrict__ bXb, double* __restrict__ bYb, const double* __restrict__ gxb,
+                                                    const double* __restrict__ gyb, const double* __restrict__ Bb,
+                                                    const double* __restrict__ maskb, const PatchG* __restrict__ tab, PhysP prm, int dlo0,
+                                                    int dlo1, int dhi0, int dhi1) {
+  __shared__ double sRe[8][33], sB[8][33], sM[8][33];
+  const PatchG g = tab[blockIdx.z];
+  const int i = (int)blockIdx.x * RB_TX - 1 + (int)threadIdx.x, j = (int)blockIdx.y * RB_TY - 1 + (int)threadIdx.y;
+  if ((int)blockIdx.x * RB_TX > g.nx || (int)blockIdx.y * RB_TY > g.ny) return;
+  const bool in = i <= g.nx && j <= g.ny;
+  const ptrdiff_t o = g.off + (ptrdiff_t)j * g.pitch + i;
+  double rc = 0.0, bc = 0.0, mc = 0.0;
+  if (in) {
+    bc = Bb[o]; mc = maskb[o];
+    rc = reynolds(prm, bc, gxb[o], gyb[o]);
+  }
+  sRe[threadIdx.y][threadIdx.x] = rc; sB[threadIdx.y][threadIdx.x] = bc; sM[threadIdx.y][threadIdx.x] = mc;
+  __syncthreads();
+  if (!in || threadIdx.x == 0 || threadIdx.y == 0) return;
+  const int lx = threadIdx.x, ly = threadIdx.y;
+  if (j < g.ny) {
+    double r = 0.5 * (rc + sRe[ly][lx - 1]), b = 0.5 * (bc + sB[ly][lx - 1]);
+    double mm = sM[ly][lx - 1];
+    double im = fabs(mc - mm) < 1e-10 ? (mc > 0.0 ? 1.0 : -1.0) : 0.0;
+    int gi = g.glo0 + i;
+    if (gi == dlo0) im = 0.0;
+    if (gi == dhi0 + 1) im = 0.0;
+    bXb[o] = bcoeff_face(prm, b, r, im);
+  }
+  if (i < g.nx) {
+    double r = 0.5 * (rc + sRe[ly - 1][lx]), b = 0.5 * (bc + sB[ly - 1][lx]);
+    double mm = sM[ly - 1][lx];
+    double im = fabs(mc - mm) < 1e-10 ? (mc > 0.0 ? 1.0 : -1.0) : 0.0;
+    int gj = g.glo1 + j;
+    if (gj == dlo1) im = 0.0;
+    if (gj == dhi1 + 1) im = 0.0;
+    bYb[o] = bcoeff_face(prm, b, r, im);
+  }
+}
+
 __global__ void __launch_bounds__(256) k_lambda_g(double* __restrict__ lamb, const PatchG* __restrict__ tab, OpArgsG a) {
   const PatchG g = tab[blockIdx.z];
   int i = blockIdx.x * blockDim.x + threadIdx.x;

@@ -670,7 +670,8 @@ __global__ void __launch_bounds__(128, 2) k_gsrb_stream2(FusedArgs f) {
 
 // ------------------------------------------------------------------------------------------------
 // applyOp / residual (+ max-norm) : VCNLCOMPUTEOP2D / VCNLCOMPUTERES2D (src/VCAMRNonLinearPoissonOpF.ChF:201-406)
-// MODE 0: out = L(phi);  1: out = rhs - L(phi);  2: as 1 plus max|out| accumulated into *norm_bits
+// MODE 0: out = L(phi);  1: out = rhs - L(phi);  2: as 1 plus max|out| accumulated into *norm_bits;  3: only the max-norm of
+// rhs - L(phi) (nothing stored: the solver's residual norm);  4: out += L(phi) (FAS coarse right-hand side, fuses the incr)
 // ------------------------------------------------------------------------------------------------
 __device__ __forceinline__ void block_max_to_global(double v, unsigned long long* dst) {
   // non-negative doubles order like their bit patterns
@@ -702,17 +703,20 @@ __global__ void __launch_bounds__(256) k_apply(double* __restrict__ out, const d
     double nl, dnl;
     nl_terms(a.prm, pc, a.B[o], a.mask[o], a.Pi[o], a.zb[o], nl, dnl);
     double lof = lofphi_cell(a.alpha, ac, a.beta, pc, pw, pe, ps, pn, bw, be, bs, bn, a.dxi0, a.dxi1, nl);
-    r = MODE == 0 ? lof : rhs[o] - (lof);
-    out[o] = r;
+    if (MODE == 4) { out[o] = out[o] + 1.0 * lof; }
+    else {
+      r = MODE == 0 ? lof : rhs[o] - (lof);
+      if (MODE != 3) out[o] = r;
+    }
   }
-  if (MODE == 2) block_max_to_global(fabs(r), norm_bits);
+  if (MODE == 2 || MODE == 3) block_max_to_global(fabs(r), norm_bits);
 }
 
 // restrictResidual + restrictR fused (src/VCAMRNonLinearPoissonOp.cpp:347-460; RESTRICTRESVCNL2D / RESTRICTVCNL,
 // VCAMRNonLinearPoissonOpF.ChF:419-561): one thread per coarse cell, the four fine cells accumulated in the
 // Fortran loop order (i fastest):  acc = 0; acc += v/4 ...
 template <int WITH_PHI>
-__global__ void __launch_bounds__(256) k_restrict(double* __restrict__ resC, double* __restrict__ phiC, int pitchC,
+__global__ void __launch_bounds__(256) k_restrict(double* __restrict__ resC, double* __restrict__ phiC, double* __restrict__ saveC, int pitchC,
                                                   const double* __restrict__ phi, const double* __restrict__ rhs, OpArgs a) {
   int ic = blockIdx.x * blockDim.x + threadIdx.x;
   int jc = blockIdx.y * blockDim.y + threadIdx.y;
@@ -739,7 +743,10 @@ __global__ void __launch_bounds__(256) k_restrict(double* __restrict__ resC, dou
     }
   size_t oc = (size_t)jc * pitchC + ic;
   if (resC) resC[oc] = acc;
-  if (WITH_PHI) phiC[oc] = accp;
+  if (WITH_PHI) {
+    phiC[oc] = accp;
+    if (saveC) saveC[oc] = accp; // the driver's assignLocal(saved, phiCoarse), valid cells
+  }
 }
 
 // prolongIncrement (src/AMRNonLinearPoissonOp.cpp:856-886; PROLONGNL AMRNonLinearPoissonOpF.ChF:607-632), m = 2.
