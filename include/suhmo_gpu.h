@@ -289,6 +289,19 @@ int sg_rhs_gap(const sg_picard_params* q, sg_field* RHS, const sg_field* Pi, con
 /* explicit gap-height update newB = RHS*dt + oldB (src/AmrHydro.cpp:3394-3408) */
 int sg_gap_euler(sg_field* newB, const sg_field* oldB, const sg_field* RHS, double dt);
 
+/* ------------------------------------------------------------------ AMR hierarchy generation ------------- */
+/* AmrHydro::tagCellsLevel (src/AmrHydro.cpp:4539-4604): tag where vmin < phi < vmax on the valid cells, grow by tags_grow
+   (and per direction up to tags_grow_dir), clip to the domain.  tags_host: one byte per cell of the level's domain, x
+   fastest; accumulate != 0 ORs into it (the union over tag variables). */
+int sg_tag_cells_level(const sg_field* phi, double vmin, double vmax, int tags_grow, const int tags_grow_dir[2],
+                       unsigned char* tags_host, int accumulate);
+/* BRMeshRefine(domain0, refRatios=2, fill_ratio, block_factor, nesting_radius, max_box_size).regrid(...)
+   (src/AmrHydro.cpp:4267-4272; absent Chombo -- Berger-Rigoutsos clustering, host only, PARITY UNPINNED): boxes of levels
+   1..top_level+1 from tags on levels 0..top_level.  out_level_counts has top_level+2 entries (entry 0 = nbase). */
+int sg_br_regrid(const int domain0[4], int nbase, const int* base_boxes, int top_level, const unsigned char* const* tags,
+                 double fill_ratio, int block_factor, int nesting_radius, int max_box_size, int max_out_boxes, int* out_boxes,
+                 int* out_level_counts, int* new_finest);
+
 /* ------------------------------------------------------------------ whole solve -------------------------- */
 /* AMRFASMultiGrid::define + setSolverParameters + solve as driven by AmrHydro::SolveForHead_nl
    (src/AmrHydro.cpp:719-768), kept on the device: one call = all V-cycles, residual norms on device. */

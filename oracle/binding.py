@@ -144,6 +144,7 @@ def lib():
     sig("orc_rhs_head", None, pq, vp, vp, vp, vp, vp, vp, vp, vp, vp)
     sig("orc_rhs_gap", None, pq, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, cd)
     sig("orc_gap_euler", None, vp, vp, vp, cd)
+    sig("orc_tag_cells_level", None, vp, cd, cd, ci, ip, vp, ci)
     _LIB = L
     return L
 
@@ -403,3 +404,13 @@ class AmrSolver:
     def free(self):
         lib().orc_amr_solver_free(self.h)
         self.h = None
+
+
+def tag_cells_level(field, vmin, vmax, tags_grow=0, tags_grow_dir=(0, 0), tags=None):
+    d = field.layout.domain
+    nx, ny = d[2] - d[0] + 1, d[3] - d[1] + 1
+    acc = tags is not None
+    out = np.ascontiguousarray(tags, dtype=np.uint8) if acc else np.zeros((ny, nx), dtype=np.uint8)
+    gd, gp = _ia(tags_grow_dir)
+    lib().orc_tag_cells_level(field.h, float(vmin), float(vmax), int(tags_grow), gp, out.ctypes.data_as(C.c_void_p), int(acc))
+    return out

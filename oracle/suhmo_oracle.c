@@ -1739,3 +1739,29 @@ void orc_gap_euler(orc_field* newB, const orc_field* oldB, const orc_field* RHS,
     FOR_REGION(r, i, j) AT(newB, b, i, j, 0) = AT(RHS, b, i, j, 0) * dt + AT(oldB, b, i, j, 0);
   }
 }
+
+/* AmrHydro::tagCellsLevel (src/AmrHydro.cpp:4539-4604): tags = byte map over the level's domain (x fastest).  Tag where
+   vmin < phi < vmax on valid cells; grow(tags_grow); per direction grow up to tags_grow_dir; &= domain; OR into tags. */
+void orc_tag_cells_level(const orc_field* phi, double vmin, double vmax, int tags_grow, const int tags_grow_dir[2], unsigned char* tags,
+                         int accumulate) {
+  const orc_layout* L = phi->lay;
+  int nx = L->domain.hi[0] - L->domain.lo[0] + 1, ny = L->domain.hi[1] - L->domain.lo[1] + 1;
+  unsigned char* m = (unsigned char*)calloc((size_t)nx * ny, 1);
+  for (int b = 0; b < L->nbox; b++) {
+    obox v = L->box[b];
+    for (int j = v.lo[1]; j <= v.hi[1]; j++)
+      for (int i = v.lo[0]; i <= v.hi[0]; i++)
+        if ((AT(phi, b, i, j, 0) > vmin) && (AT(phi, b, i, j, 0) < vmax)) m[(size_t)(j - L->domain.lo[1]) * nx + (i - L->domain.lo[0])] = 1;
+  }
+  int r[2] = {tags_grow, tags_grow};
+  if (tags_grow_dir) for (int d = 0; d < 2; d++) if (tags_grow_dir[d] > tags_grow) r[d] = tags_grow + imax(0, tags_grow_dir[d] - tags_grow);
+  unsigned char* g = (unsigned char*)calloc((size_t)nx * ny, 1);
+  for (int j = 0; j < ny; j++)
+    for (int i = 0; i < nx; i++) {
+      if (!m[(size_t)j * nx + i]) continue;
+      for (int jj = imax(0, j - r[1]); jj <= imin(ny - 1, j + r[1]); jj++)
+        for (int ii = imax(0, i - r[0]); ii <= imin(nx - 1, i + r[0]); ii++) g[(size_t)jj * nx + ii] = 1;
+    }
+  for (size_t k = 0; k < (size_t)nx * ny; k++) tags[k] = accumulate ? (tags[k] | g[k]) : g[k];
+  free(m); free(g);
+}

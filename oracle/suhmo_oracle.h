@@ -191,6 +191,9 @@ void orc_rhs_gap(const orc_picard_params* q, orc_field* RHS, const orc_field* Pi
                  const orc_field* DT, const orc_field* IM, const orc_field* BH, const orc_field* BL, const orc_field* MV, double dt);
 void orc_gap_euler(orc_field* newB, const orc_field* oldB, const orc_field* RHS, double dt);
 
+void orc_tag_cells_level(const orc_field* phi, double vmin, double vmax, int tags_grow, const int tags_grow_dir[2], unsigned char* tags,
+                         int accumulate);
+
 void orc_set_threads(int n);
 
 #ifdef __cplusplus

@@ -482,3 +482,39 @@ class AMRFASMultiGrid:
         if self.h:
             lib().sg_solver_destroy(self.h)
             self.h = None
+
+
+def tagCellsLevel(ld, vmin, vmax, tags_grow=0, tags_grow_dir=(0, 0), tags=None):
+    """AmrHydro::tagCellsLevel (src/AmrHydro.cpp:4539-4604) -> uint8 map [ny, nx] over the level's domain (ORed into `tags`)."""
+    d = ld.layout.domain
+    nx, ny = int(d[2] - d[0] + 1), int(d[3] - d[1] + 1)
+    acc = tags is not None
+    out = np.ascontiguousarray(tags, dtype=np.uint8) if acc else np.zeros((ny, nx), dtype=np.uint8)
+    gd = np.ascontiguousarray(tags_grow_dir, dtype=np.int32)
+    check(lib().sg_tag_cells_level(ld.h, float(vmin), float(vmax), int(tags_grow), _ip(gd), out.ctypes.data_as(C.c_void_p), int(acc)))
+    return out
+
+
+class BRMeshRefine:
+    """BRMeshRefine(domain0, refRatios = 2, fillRatio, blockFactor, bufferSize, maxSize).regrid (host only)."""
+
+    def __init__(self, domain0, fill_ratio, block_factor, nesting_radius, max_box_size):
+        self.domain0 = np.ascontiguousarray(domain0, dtype=np.int32)
+        self.fill_ratio, self.block_factor, self.nesting_radius, self.max_box_size = fill_ratio, block_factor, nesting_radius, max_box_size
+
+    def regrid(self, base_boxes, tags, max_boxes=1 << 16):
+        """tags: list of uint8 maps for levels 0..top.  Returns [base_boxes, boxes_level1, ...] up to the new finest level."""
+        base = np.ascontiguousarray(base_boxes, dtype=np.int32).reshape(-1, 4)
+        top = len(tags) - 1
+        keep = [np.ascontiguousarray(t, dtype=np.uint8) for t in tags]
+        ptrs = (C.c_void_p * len(keep))(*[t.ctypes.data for t in keep])
+        out = np.zeros((max_boxes, 4), dtype=np.int32)
+        counts = np.zeros(top + 2, dtype=np.int32)
+        finest = C.c_int()
+        check(lib().sg_br_regrid(_ip(self.domain0), len(base), _ip(base), top, ptrs, self.fill_ratio, self.block_factor, self.nesting_radius,
+                                 self.max_box_size, max_boxes, _ip(out), _ip(counts), C.byref(finest)))
+        levels, k = [base], 0
+        for l in range(1, finest.value + 1):
+            levels.append(out[k:k + counts[l]].copy())
+            k += counts[l]
+        return levels

@@ -97,6 +97,8 @@ SIGNATURES = {
     "sg_rhs_head": [C.POINTER(PicardParams), vp, vp, vp, vp, vp, vp, vp, vp, vp],
     "sg_rhs_gap": [C.POINTER(PicardParams), vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, cd],
     "sg_gap_euler": [vp, vp, vp, cd],
+    "sg_tag_cells_level": [vp, cd, cd, ci, ip, vp, ci],
+    "sg_br_regrid": [ip, ci, ip, ci, pvp, cd, ci, ci, ci, ci, ip, ip, ip],
     "sg_solver_define": [vp, pvp, ci], "sg_solver_destroy": [vp], "sg_solver_depth": [vp, ci, ip],
     "sg_solver_solve": [vp, pvp, pvp, ci, ci, C.POINTER(SolverParams), dp, C.POINTER(SolveStats)],
     "sg_solver_cell_updates_per_cycle": [vp, C.POINTER(SolverParams), dp],

@@ -992,6 +992,7 @@ extern "C" int sg_wflx_level(sg_ctx* ctx, const sg_params* p, sg_field* bX, sg_f
 }
 
 #include "sg_picard_host.inc"
+#include "sg_regrid.inc"
 
 // ------------------------------------------------------------------------------------------------
 // factory
