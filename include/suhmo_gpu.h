@@ -321,7 +321,8 @@ int sg_solver_cell_updates_per_cycle(const sg_solver* s, const sg_solver_params*
    fused sweep, 3 = two iterations per sweep (temporal blocking; issue-bound today) with mode 1 for an odd
    remainder */
 int sg_set_relax_mode(sg_ctx* ctx, int mode);
-/* experiment knobs, 0 = library default.  key 0: rows per warp of the fused sweep; key 1: resident CTAs per SM (3|4) */
+/* experiment knobs, 0 = library default.  key 0: rows per warp of the streaming sweep; key 1: resident CTAs per SM (3|4) of
+   the register-only sweep; key 2: 1 = do not capture V-cycles into CUDA graphs */
 int sg_set_tuning(sg_ctx* ctx, int key, int value);
 
 #ifdef __cplusplus

@@ -71,7 +71,7 @@ struct sg_ctx {
   // reduction scratch
   double* d_partial = nullptr;
   size_t partial_cap = 0;
-  double* d_scalar = nullptr;            // [0..63] device scalars (as doubles / bit patterns)
+  double* d_scalar = nullptr;            // [0..127] device scalars (as doubles / bit patterns)
   double* h_scalar = nullptr;            // pinned mirror
   double* h_stage = nullptr; size_t h_stage_cap = 0; // pinned staging for batched upload/download
   double* d_stage = nullptr; size_t d_stage_cap = 0;
@@ -162,6 +162,10 @@ struct sg_solver {
   // AMR levels (index = level; entry 0 of aops aliases ops[0])
   std::vector<sg_op*> aops;
   std::vector<sg_field*> aresid, acorr, atmp, ascratch, aresC;
+  // one FAS V-cycle + residual norm captured as a CUDA graph (launch-bound levels: ~110 launches become one)
+  cudaGraphExec_t gexec = nullptr;
+  std::vector<long long> gkey, warm_key;
+  long long glaunches = 0;
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -236,9 +240,9 @@ extern "C" int sg_ctx_create(sg_ctx** out, int device, int rank, int nranks, con
   c->device = device; c->rank = rank; c->nranks = nranks;
   CK(cudaDeviceGetAttribute(&c->num_sms, cudaDevAttrMultiProcessorCount, device));
   CK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
-  CK(cudaMalloc(&c->d_scalar, 64 * sizeof(double)));
-  CK(cudaMemsetAsync(c->d_scalar, 0, 64 * sizeof(double), c->stream));
-  CK(cudaMallocHost(&c->h_scalar, 64 * sizeof(double)));
+  CK(cudaMalloc(&c->d_scalar, 128 * sizeof(double)));
+  CK(cudaMemsetAsync(c->d_scalar, 0, 128 * sizeof(double), c->stream));
+  CK(cudaMallocHost(&c->h_scalar, 128 * sizeof(double)));
   if (nranks > 1) {
     REQUIRE(nccl_unique_id, "sg_ctx_create: nranks > 1 needs an NCCL unique id");
     int r = c->nccl.init(nccl_unique_id, rank, nranks, g_err);
@@ -1690,6 +1694,7 @@ extern "C" int sg_solver_destroy(sg_solver* s) {
     if (l > 0) sg_op_destroy(s->aops[l]);
   }
   for (sg_op* op : s->ops) sg_op_destroy(op);
+  if (s->gexec) cudaGraphExecDestroy(s->gexec);
   delete s;
   return SG_OK;
 }
@@ -1790,6 +1795,55 @@ static int residual_norm(sg_solver* s, sg_field* const* phi, sg_field* const* rh
   return global_reduce(s->ctx, slot, true);
 }
 
+// One V-cycle followed by the residual norm (left in d_scalar[normslot]).  After one ordinary (warm-up) cycle with a given
+// set of fields and parameters, the cycle is captured into a CUDA graph and replayed: valid because every array a kernel
+// names is unchanged from cycle to cycle -- the out-of-place smoother swaps a field with its scratch buffer, and an even
+// number of sweeps per relax call (pre, post and bottom all even, as in every SUHMO configuration) swaps it back.
+static int run_cycle(sg_solver* s, sg_field* const* phi, sg_field* const* rhs, int l_max, const sg_solver_params* sp, int iter, int normslot) {
+  sg_ctx* c = s->ctx;
+  const int FIX = 100; // scratch slot the captured norm lands in
+  const bool even = (sp->pre % 2 == 0 && sp->post % 2 == 0 && sp->bottom % 2 == 0) || c->relax_mode == 0;
+  const bool eligible = c->nranks == 1 && even && c->tune[2] == 0;
+  if (!eligible) {
+    SGCALL(vcycle(s, phi, rhs, l_max, sp, iter));
+    return residual_norm(s, phi, rhs, l_max, normslot);
+  }
+  std::vector<long long> key = {l_max, sp->pre, sp->post, sp->bottom, c->relax_mode, c->tune[0], (long long)(size_t)c->stream};
+  for (int l = 0; l <= l_max; l++) { key.push_back((long long)(size_t)phi[l]->base); key.push_back((long long)(size_t)rhs[l]->base); }
+  for (sg_op* op : s->aops) { key.push_back((long long)(size_t)op->bX->base); key.push_back((long long)(size_t)op->B->base); }
+  if (s->gexec && key == s->gkey) {
+    CK(cudaGraphLaunch(s->gexec, c->stream));
+    c->launches += s->glaunches;
+  } else if (key == s->warm_key) {
+    if (s->gexec) { cudaGraphExecDestroy(s->gexec); s->gexec = nullptr; }
+    long long l0 = c->launches;
+    cudaGraph_t g = nullptr;
+    CK(cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal));
+    int r = vcycle(s, phi, rhs, l_max, sp, iter);
+    if (r == SG_OK) r = residual_norm(s, phi, rhs, l_max, FIX);
+    cudaError_t e = cudaStreamEndCapture(c->stream, &g);
+    if (r != SG_OK || e != cudaSuccess || !g) { // something in the cycle cannot be captured: run it the ordinary way from now on
+      if (g) cudaGraphDestroy(g);
+      cudaGetLastError();
+      c->tune[2] = 1;
+      c->launches = l0;
+      SGCALL(vcycle(s, phi, rhs, l_max, sp, iter));
+      return residual_norm(s, phi, rhs, l_max, normslot);
+    }
+    s->glaunches = c->launches - l0;
+    CK(cudaGraphInstantiate(&s->gexec, g, 0));
+    cudaGraphDestroy(g);
+    s->gkey = key;
+    CK(cudaGraphLaunch(s->gexec, c->stream));
+  } else {
+    s->warm_key = key;
+    SGCALL(vcycle(s, phi, rhs, l_max, sp, iter));
+    return residual_norm(s, phi, rhs, l_max, normslot);
+  }
+  if (normslot != FIX) CK(cudaMemcpyAsync(c->d_scalar + normslot, c->d_scalar + FIX, sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
+  return SG_OK;
+}
+
 extern "C" int sg_solver_solve(sg_solver* s, sg_field* const* phi, sg_field* const* rhs, int l_max, int l_base,
                                const sg_solver_params* sp, double* hist, sg_solve_stats* stats) {
   REQUIRE(s && phi && rhs && sp && phi[0] && rhs[0], "sg_solver_solve: null");
@@ -1812,8 +1866,7 @@ extern "C" int sg_solver_solve(sg_solver* s, sg_field* const* phi, sg_field* con
   if (sp->fixed_cycles > 0) {
     REQUIRE(sp->fixed_cycles <= 60, "fixed_cycles <= 60");
     for (iter = 0; iter < sp->fixed_cycles; iter++) {
-      SGCALL(vcycle(s, phi, rhs, l_max, sp, iter));
-      SGCALL(residual_norm(s, phi, rhs, l_max, 3 + iter)); // norms stay on the device until the end
+      SGCALL(run_cycle(s, phi, rhs, l_max, sp, iter, 3 + iter)); // norms stay on the device until the end
     }
     CK(cudaEventRecord(e1, c->stream));
     CK(cudaMemcpyAsync(c->h_scalar + 3, c->d_scalar + 3, sizeof(double) * sp->fixed_cycles, cudaMemcpyDeviceToHost, c->stream));
@@ -1828,9 +1881,8 @@ extern "C" int sg_solver_solve(sg_solver* s, sg_field* const* phi, sg_field* con
     bool goHang = iter < sp->imin || rnorm < (1 - sp->hang) * norm_last, goMin = iter < sp->iter_min;
     while (goMin || (goIter && goRedu && goHang && goNorm)) {
       norm_last = rnorm;
-      SGCALL(vcycle(s, phi, rhs, l_max, sp, iter));
+      SGCALL(run_cycle(s, phi, rhs, l_max, sp, iter, 2));
       iter++;
-      SGCALL(residual_norm(s, phi, rhs, l_max, 2));
       SGCALL(fetch_scalar(c, 2, &rnorm)); // the stop test needs the norm on the host: one sync per V-cycle
       if (hist) hist[iter] = rnorm;
       goNorm = rnorm > sp->norm_thresh; goRedu = rnorm > sp->eps * initial; goIter = iter < sp->max_iter;
