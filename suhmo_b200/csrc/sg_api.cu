@@ -150,6 +150,7 @@ struct sg_op {
   bool owns_layout = false;
   int level = 0, depth = 0;
   bool update_operator = false;
+  bool mask_needed = true; // false: no negative ice-mask entry on this level (set by op_scan_mask)
 };
 
 struct sg_solver {
@@ -213,6 +214,7 @@ static OpArgs make_args(const sg_op* op) {
   a.dxi0 = 1.0 / (op->dx[0] * op->dx[0]);
   a.dxi1 = 1.0 / (op->dx[1] * op->dx[1]);
   a.has_a = op->alpha != 0.0;
+  a.use_mask = op->mask_needed ? 1 : 0;
   a.aC = op->aCoef ? op->aCoef->p() : nullptr;
   a.bX = op->bX->p(); a.bY = op->bY->p();
   a.B = op->B->p(); a.Pi = op->Pi->p(); a.zb = op->zb->p(); a.mask = op->mask->p();
@@ -1047,6 +1049,26 @@ static int coef_ghosts(sg_op* op, bool only_b) {
   return SG_OK;
 }
 
+// The ice mask only enters the operator through COMPUTENONLINEARTERMS' test `mask < 0` (src/AmrHydroF.ChF:40).  Levels
+// without a negative entry (every configuration but the valley geometry) need not stream the array at all; the scan runs
+// when an operator is built or refreshed.  Multi-rank: decided per rank (a rank-local property of the rank-local cells,
+// ghost cells included since the smoother recomputes the ring on them).
+static int op_scan_mask(sg_op* op) {
+  sg_layout* L = op->lay;
+  op->mask_needed = true;
+  if (!L->has_local || !L->fast) return SG_OK;
+  sg_ctx* c = op->ctx;
+  int* flag = reinterpret_cast<int*>(c->d_scalar + 120);
+  CK(cudaMemsetAsync(flag, 0, sizeof(int), c->stream));
+  // valid cells plus the 3 ghost rows/columns the streaming sweeps may touch
+  LAUNCH(c, k_any_negative, grid2(L->nx + 6, L->ny + 6, B2D), B2D, op->mask->p() - 3 * (ptrdiff_t)L->pitch - 3, L->pitch, L->nx + 6, L->ny + 6, flag);
+  int h = 1;
+  CK(cudaMemcpyAsync(&h, flag, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+  CK(cudaStreamSynchronize(c->stream));
+  op->mask_needed = h != 0;
+  return SG_OK;
+}
+
 static sg_op* new_op(sg_factory* f, int level) {
   sg_op* op = new sg_op();
   op->ctx = f->ctx;
@@ -1135,6 +1157,7 @@ extern "C" int sg_factory_MGnewOp(sg_factory* f, int level, int depth, int homo_
     SGCALL(average_coefficients(f, op, level, coarsening));
   }
   SGCALL(coef_ghosts(op, false));
+  SGCALL(op_scan_mask(op));
   *out = op;
   return SG_OK;
 }
@@ -1680,6 +1703,7 @@ extern "C" int sg_solver_refresh(sg_solver* s) {
   for (size_t d = 0; d < s->ops.size(); d++) {
     if (d > 0) SGCALL(average_coefficients(s->fac, s->ops[d], 0, 1 << d));
     SGCALL(coef_ghosts(s->ops[d], false));
+    SGCALL(op_scan_mask(s->ops[d]));
   }
   return SG_OK;
 }
@@ -1810,7 +1834,8 @@ static int run_cycle(sg_solver* s, sg_field* const* phi, sg_field* const* rhs, i
   }
   std::vector<long long> key = {l_max, sp->pre, sp->post, sp->bottom, c->relax_mode, c->tune[0], (long long)(size_t)c->stream};
   for (int l = 0; l <= l_max; l++) { key.push_back((long long)(size_t)phi[l]->base); key.push_back((long long)(size_t)rhs[l]->base); }
-  for (sg_op* op : s->aops) { key.push_back((long long)(size_t)op->bX->base); key.push_back((long long)(size_t)op->B->base); }
+  for (sg_op* op : s->aops) { key.push_back((long long)(size_t)op->bX->base); key.push_back((long long)(size_t)op->B->base); key.push_back(op->mask_needed); }
+  for (sg_op* op : s->ops) key.push_back(op->mask_needed);
   if (s->gexec && key == s->gkey) {
     CK(cudaGraphLaunch(s->gexec, c->stream));
     c->launches += s->glaunches;

@@ -90,6 +90,7 @@ struct OpArgs {
   PhysP prm;
   double alpha, beta, dxi0, dxi1, dx0, dx1;
   int has_a; // alpha != 0: read aCoef
+  int use_mask; // 0: the level's ice mask has no negative entry, nl_terms can never take its mask branch: the array is not streamed
   const double* aC;
   const double* bX;
   const double* bY;
@@ -205,7 +206,7 @@ __global__ void __launch_bounds__(256) k_gsrb_color(double* __restrict__ phi, co
   double bw = a.bX[o], be = a.bX[o + 1], bs = a.bY[o], bn = a.bY[o + P];
   double ac = a.has_a ? a.aC[o] : 0.0;
   double nl, dnl;
-  nl_terms(a.prm, pc, a.B[o], a.mask[o], a.Pi[o], a.zb[o], nl, dnl);
+  nl_terms(a.prm, pc, a.B[o], a.use_mask ? a.mask[o] : 1.0, a.Pi[o], a.zb[o], nl, dnl);
   double lof = lofphi_cell(a.alpha, ac, a.beta, pc, pw, pe, ps, pn, bw, be, bs, bn, a.dxi0, a.dxi1, nl);
   double lam = lambda_cell(a.alpha, ac, a.beta, bw, be, bs, bn, a.dxi0, a.dxi1);
   double denom = 1.0e-16 + lam + dnl;
@@ -484,7 +485,8 @@ __global__ void __launch_bounds__(128, MINB) k_gsrb_stream(FusedArgs f) {
       double2* s = ring + (size_t)stage * (NARR * 32);
       cp_async16(s, g0 + o2); cp_async16(s + 32, g1 + o2);
       cp_async16(s + 64, g2 + o1); cp_async16(s + 96, g3 + o1); cp_async16(s + 128, g4 + o1); cp_async16(s + 160, g5 + o1);
-      cp_async16(s + 192, g6 + o1); cp_async16(s + 224, g7 + o1);
+      if (a.use_mask) cp_async16(s + 192, g6 + o1);
+      cp_async16(s + 224, g7 + o1);
       if (HAS_A) cp_async16(s + 256, g8 + o1);
     }
     cp_async_commit();
@@ -506,7 +508,8 @@ __global__ void __launch_bounds__(128, MINB) k_gsrb_stream(FusedArgs f) {
     {
       const double2* s = ring + (size_t)stage * (NARR * 32);
       p2 = s[0]; by2 = s[32];
-      c1.rhs = s[64]; c1.B = s[96]; c1.Pi = s[128]; c1.zb = s[160]; c1.mk = s[192]; c1.bx = s[224];
+      c1.rhs = s[64]; c1.B = s[96]; c1.Pi = s[128]; c1.zb = s[160]; c1.bx = s[224];
+      c1.mk = a.use_mask ? s[192] : make_double2(1.0, 1.0);
       if (HAS_A) c1.ac = s[256];
     }
     {
@@ -593,7 +596,8 @@ __global__ void __launch_bounds__(128, 2) k_gsrb_stream2(FusedArgs f) {
       double2* s = ring + (size_t)stage * (NARR * 32);
       cp_async16(s, g0 + o2); cp_async16(s + 32, g1 + o2);
       cp_async16(s + 64, g2 + o1); cp_async16(s + 96, g3 + o1); cp_async16(s + 128, g4 + o1); cp_async16(s + 160, g5 + o1);
-      cp_async16(s + 192, g6 + o1); cp_async16(s + 224, g7 + o1);
+      if (a.use_mask) cp_async16(s + 192, g6 + o1);
+      cp_async16(s + 224, g7 + o1);
       if (HAS_A) cp_async16(s + 256, g8 + o1);
     }
     cp_async_commit();
@@ -601,7 +605,8 @@ __global__ void __launch_bounds__(128, 2) k_gsrb_stream2(FusedArgs f) {
   auto coefs = [&](int stage) -> GsRow { // cell coefficients + x-face coefficient of the row that bundle carries
     const double2* s = ring + (size_t)stage * (NARR * 32);
     GsRow c;
-    c.rhs = s[64]; c.B = s[96]; c.Pi = s[128]; c.zb = s[160]; c.mk = s[192]; c.bx = s[224];
+    c.rhs = s[64]; c.B = s[96]; c.Pi = s[128]; c.zb = s[160]; c.bx = s[224];
+    c.mk = a.use_mask ? s[192] : make_double2(1.0, 1.0);
     c.ac = HAS_A ? s[256] : make_double2(0.0, 0.0);
     return c;
   };
@@ -701,7 +706,7 @@ __global__ void __launch_bounds__(256) k_apply(double* __restrict__ out, const d
     double bw = a.bX[o], be = a.bX[o + 1], bs = a.bY[o], bn = a.bY[o + P];
     double ac = a.has_a ? a.aC[o] : 0.0;
     double nl, dnl;
-    nl_terms(a.prm, pc, a.B[o], a.mask[o], a.Pi[o], a.zb[o], nl, dnl);
+    nl_terms(a.prm, pc, a.B[o], a.use_mask ? a.mask[o] : 1.0, a.Pi[o], a.zb[o], nl, dnl);
     double lof = lofphi_cell(a.alpha, ac, a.beta, pc, pw, pe, ps, pn, bw, be, bs, bn, a.dxi0, a.dxi1, nl);
     if (MODE == 4) { out[o] = out[o] + 1.0 * lof; }
     else {
@@ -735,7 +740,7 @@ __global__ void __launch_bounds__(256) k_restrict(double* __restrict__ resC, dou
         double bw = a.bX[o], be = a.bX[o + 1], bs = a.bY[o], bn = a.bY[o + P];
         double ac = a.has_a ? a.aC[o] : 0.0;
         double nl, dnl;
-        nl_terms(a.prm, pc, a.B[o], a.mask[o], a.Pi[o], a.zb[o], nl, dnl);
+        nl_terms(a.prm, pc, a.B[o], a.use_mask ? a.mask[o] : 1.0, a.Pi[o], a.zb[o], nl, dnl);
         double lof = lofphi_cell(a.alpha, ac, a.beta, pc, pw, pe, ps, pn, bw, be, bs, bn, a.dxi0, a.dxi1, nl);
         acc = acc + (rhs[o] - lof) / denom;
       }
@@ -949,6 +954,13 @@ __global__ void __launch_bounds__(256) k_reduce_final(const double* __restrict__
     __syncthreads();
   }
   if (threadIdx.x == 0) *out = sh[0];
+}
+
+// does a cell field hold a negative value on its valid cells?  (decides whether the smoother has to stream the ice mask)
+__global__ void __launch_bounds__(256) k_any_negative(const double* __restrict__ x, int pitch, int nx, int ny, int* __restrict__ flag) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  int j = blockIdx.y * blockDim.y + threadIdx.y;
+  if (i < nx && j < ny && x[(size_t)j * pitch + i] < 0.0) *flag = 1;
 }
 
 // box <-> patch staging for batched upload/download: segment table {src offset, dst offset, nx, ny, src pitch, dst pitch}
