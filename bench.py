@@ -147,6 +147,60 @@ def run_reference(args, rank):
     print(json.dumps(line), flush=True)
 
 
+def amr_leg(ctx, amr, cfg, layout0, F0, bc, prm, args):
+    """BASELINE configs[4] as named: the AMR_multiMoulins hierarchy (3 levels, refinement around the 63 moulins) on top of the
+    resident 8192^2 base grid, single GPU.  Grids come from the library's own tagging + Berger-Rigoutsos regrid with the
+    input file's parameters (fill_ratio 0.5, block_factor 2, nestingRadius 4, max_box_size 64, tags_grow 4)."""
+    t_setup = time.perf_counter()
+    size = cfg.nx
+    bg = cfg.distributed_input
+    tags0 = amr.tagCellsLevel(F0["rhs"], 20.0 * bg, 1e30, 4)
+    mr = amr.BRMeshRefine((0, 0, cfg.nx - 1, cfg.ny - 1), 0.5, 2, 4, 64)
+    base = layout0.boxes
+    lv = mr.regrid(base, [tags0], max_boxes=1 << 18)
+    if len(lv) < 2:
+        return {"skipped": "no cell tagged"}
+
+    def make_level(l, boxes):
+        r = 2 ** l
+        lay = amr.DisjointBoxLayout(ctx, boxes, (0, 0, cfg.nx * r - 1, cfg.ny * r - 1), cfg.periodic)
+        spec = dict(head=(1, 0), rhs=(0, 0), B=(1, 0), Pi=(1, 0), zb=(1, 0), mask=(1, 0), a=(0, 0), bX=(0, 1), bY=(0, 2))
+        F = {k: amr.LevelData(lay, 1, ng, cent) for k, (ng, cent) in spec.items()}
+        fabs = {k: [] for k in ("head", "rhs", "B", "Pi", "zb", "mask")}
+        for bx in boxes:
+            g = syn.fields(cfg, ng=1, lo=(int(bx[0]), int(bx[1])), shape=(int(bx[2] - bx[0] + 1), int(bx[3] - bx[1] + 1)), level_ratio=r)
+            for k in fabs:
+                fabs[k].append(g[k][None])
+        for k in fabs:
+            F[k].upload(fabs[k])
+        return lay, F
+
+    lay1, F1 = make_level(1, lv[1])
+    tags1 = amr.tagCellsLevel(F1["rhs"], 200.0 * bg, 1e30, 4)
+    lv = mr.regrid(base, [tags0, tags1], max_boxes=1 << 18)
+    levels = [(layout0, F0)]
+    for l in range(1, len(lv)):
+        levels.append(make_level(l, lv[l]))
+    nlev = len(levels)
+    f = lambda k: [F[k] for _, F in levels]  # noqa: E731
+    fac = amr.VCAMRNonLinearPoissonOpFactory().define(ctx, [lay for lay, _ in levels], [2] * (nlev - 1), cfg.dx, bc, 0.0, f("a"), -1.0,
+                                                      f("bX"), f("bY"), prm, f("B"), f("Pi"), f("zb"), f("mask"))
+    ops = [fac.AMRnewOp(l) for l in range(nlev)]
+    for l in range(nlev):  # bCoef = B(h) as the Picard body hands it over
+        ops[l].UpdateOperator(levels[l][1]["head"], levels[l - 1][1]["head"] if l > 0 else None, l, 0, False)
+    mg = amr.AMRFASMultiGrid().define(fac, nlev)
+    mg.setSolverParameters(4, 4, args.bottom, 1, 100, 1e-10, 1e-4, 1e-7)
+    t_setup = time.perf_counter() - t_setup
+    mg.solve(f("head"), f("rhs"), fixed_cycles=2)
+    it, hist, st = mg.solve(f("head"), f("rhs"), fixed_cycles=args.amr_cycles)
+    per = mg.cell_updates_per_cycle()
+    cells = [int(sum((b[2] - b[0] + 1) * (b[3] - b[1] + 1) for b in lay.boxes)) for lay, _ in levels]
+    return {"levels": nlev, "boxes": [len(lay.boxes) for lay, _ in levels], "cells": cells, "vcycles": args.amr_cycles,
+            "ms_per_vcycle": st.device_ms / args.amr_cycles, "cell_updates_per_s": per * args.amr_cycles / (st.device_ms * 1e-3),
+            "launches_per_vcycle": st.kernel_launches / args.amr_cycles, "resnorm": [float(hist[0]), float(hist[-1])],
+            "setup_s": t_setup, "grids": "sg_tag_cells_level + sg_br_regrid (fill 0.5, block factor 2, nesting 4, max box 64, tags_grow 4)"}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -161,6 +215,8 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=2)
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--relax-mode", type=int, default=1)
+    ap.add_argument("--no-amr", action="store_true", help="skip the 3-level AMR leg (N = 1 only)")
+    ap.add_argument("--amr-cycles", type=int, default=3)
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -295,6 +351,13 @@ def main():
                "sample": f"{args.cpu_cycles} FAS V-cycles on a {args.cpu_size}x{args.cpu_size} sample of the workload "
                          f"({dt:.1f} s), oracle C restatement with OpenMP over boxes"}
 
+    amr_info = None
+    if world == 1 and not args.no_amr:
+        try:
+            amr_info = amr_leg(ctx, amr, cfg, layout, F, bc, prm, args)
+        except Exception as e:  # the headline numbers above do not depend on this leg
+            amr_info = {"failed": repr(e)[:300]}
+
     if rank == 0:
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
@@ -318,6 +381,7 @@ def main():
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": e2e_bytes_in, "d2h_bytes_per_step": e2e_bytes_out,
                     "ms_per_step": 1e3 * e2e_t, "vcycles_per_step": args.e2e_cycles},
             "gpu_launches": int(launches),
+            "amr_3level": amr_info,
             "clocks": clk,
             "resnorm": [float(hist[0]), float(hist[-1])],
             "wall_ms_per_step": 1e3 * wall / args.steps,
