@@ -322,7 +322,8 @@ int sg_solver_cell_updates_per_cycle(const sg_solver* s, const sg_solver_params*
    remainder */
 int sg_set_relax_mode(sg_ctx* ctx, int mode);
 /* experiment knobs, 0 = library default.  key 0: rows per warp of the streaming sweep; key 1: resident CTAs per SM (3|4) of
-   the register-only sweep; key 2: 1 = do not capture V-cycles into CUDA graphs */
+   the register-only sweep; key 2: 1 = do not capture V-cycles into CUDA graphs; key 3: 1 = exchange ghost rows before every sweep instead of once
+   per four (communication-avoiding relaxation off) */
 int sg_set_tuning(sg_ctx* ctx, int key, int value);
 
 #ifdef __cplusplus

@@ -1036,8 +1036,8 @@ extern "C" int sg_factory_refToFiner(const sg_factory* f, int level, int* out) {
 // coefficient ghosts on SK_GHOST sides (periodic images / neighbouring ranks): depth 1, needed by the fused sweep
 static int coef_ghosts(sg_op* op, bool only_b) {
   if (!has_ghost_sides(op->lay)) return SG_OK;
-  // depth 3: the two-iteration sweep recomputes a ring of up to 3 ghost cells on SK_GHOST sides
-  const int d = std::min(3, std::min(op->lay->nx, op->lay->ny));
+  // depth 8: communication-avoiding relaxation updates up to 6 ghost rows (+ ring) on SK_GHOST sides; tiny levels get less
+  const int d = std::min(8, std::min(op->lay->nx, op->lay->ny));
   SGCALL(fill_ghosts(op->bX, d));
   SGCALL(fill_ghosts(op->bY, d));
   if (only_b) return SG_OK;
@@ -1060,8 +1060,8 @@ static int op_scan_mask(sg_op* op) {
   sg_ctx* c = op->ctx;
   int* flag = reinterpret_cast<int*>(c->d_scalar + 120);
   CK(cudaMemsetAsync(flag, 0, sizeof(int), c->stream));
-  // valid cells plus the 3 ghost rows/columns the streaming sweeps may touch
-  LAUNCH(c, k_any_negative, grid2(L->nx + 6, L->ny + 6, B2D), B2D, op->mask->p() - 3 * (ptrdiff_t)L->pitch - 3, L->pitch, L->nx + 6, L->ny + 6, flag);
+  // valid cells plus the ghost rows/columns the streaming sweeps may update (8 rows, 3 columns)
+  LAUNCH(c, k_any_negative, grid2(L->nx + 6, L->ny + 16, B2D), B2D, op->mask->p() - 8 * (ptrdiff_t)L->pitch - 3, L->pitch, L->nx + 6, L->ny + 16, flag);
   int h = 1;
   CK(cudaMemcpyAsync(&h, flag, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
   CK(cudaStreamSynchronize(c->stream));
@@ -1187,7 +1187,9 @@ static int check_same(const sg_op* op, const sg_field* f, const char* what) {
 }
 
 // one levelGSRB iteration set
-static int relax_impl(sg_op* op, sg_field* phi, const sg_field* rhs, int iterations) {
+// trailing == false: the caller refills every ghost cell before its next read (the V-cycle driver does: restriction, residual
+// and UpdateOperator all start with BC + exchange), so levelGSRB's closing exchange + homogeneous BC fill are dead stores
+static int relax_impl(sg_op* op, sg_field* phi, const sg_field* rhs, int iterations, bool trailing = true) {
   sg_layout* L = op->lay;
   sg_ctx* c = op->ctx;
   if (!L->has_local || iterations <= 0) return SG_OK;
@@ -1224,41 +1226,56 @@ static int relax_impl(sg_op* op, sg_field* phi, const sg_field* rhs, int iterati
       int minb = kind == 3 ? 2 : kind == 1 ? 3 : (c->tune[1] == 3 ? 3 : 4);
       int capacity = c->num_sms * minb * 4; // resident warps (128-thread CTAs)
       int nsegs;
-      if (c->tune[0] > 0) nsegs = (L->ny + c->tune[0] - 1) / c->tune[0];
+      const int nrows = kind == 1 ? f.yhi - f.ylo : L->ny;
+      if (c->tune[0] > 0) nsegs = (nrows + c->tune[0] - 1) / c->tune[0];
       else if (kind == 1 || kind == 3) {
-        long long rows = ((long long)f.nstrips * L->ny) / (4LL * capacity);
+        long long rows = ((long long)f.nstrips * nrows) / (4LL * capacity);
         rows = kind == 3 ? std::max(16LL, std::min(96LL, rows)) : std::max(8LL, std::min(48LL, rows));
-        nsegs = (int)((L->ny + rows - 1) / rows);
+        nsegs = (int)((nrows + rows - 1) / rows);
       } else if (f.nstrips * ((L->ny + 63) / 64) <= capacity) nsegs = std::max(1, std::min((L->ny + 31) / 32, capacity / f.nstrips));
       else {
         nsegs = capacity / f.nstrips;               // one full wave ...
         if (nsegs < 1 || L->ny / nsegs > 1024) nsegs = (L->ny + 63) / 64; // ... unless segments get too long: many waves
       }
-      f.rows_per_warp = (L->ny + nsegs - 1) / nsegs;
-      f.nsegs = (L->ny + f.rows_per_warp - 1) / f.rows_per_warp;
+      f.rows_per_warp = (nrows + nsegs - 1) / nsegs;
+      f.nsegs = (nrows + f.rows_per_warp - 1) / f.rows_per_warp;
       return (f.nstrips * f.nsegs * 32 + 127) / 128;
     };
+    // Communication-avoiding relaxation (mode 1): instead of exchanging two ghost rows before every sweep, exchange 2k rows
+    // once per k <= 4 sweeps and let sweep s also update the ghost rows it still needs (2(k-1-s) per side) -- the same
+    // arithmetic on the same values as their owner performs, so the result is unchanged while the NCCL (or wrap) calls drop
+    // k-fold.  Needs ghost sides in y only and enough rows on both sides of the cut.
+    const bool ygh_lo = L->side_ghost[2], ygh_hi = L->side_ghost[3];
+    const bool wide = c->relax_mode == 1 && c->tune[3] == 0 && (ygh_lo || ygh_hi) && !L->side_ghost[0] && !L->side_ghost[1] && L->ny >= 16;
+    if (wide && ghosts) SGCALL(fill_ghosts(const_cast<sg_field*>(rhs), 7));
+    f.ylo = 0; f.yhi = L->ny;
     int it = 0;
     while (it < iterations) {
       const bool two = can2 && it + 2 <= iterations;
       const int kind = two ? 3 : (c->relax_mode == 2 ? 2 : 1);
-      const int blocks = plan(kind);
-      if (ghosts) SGCALL(fill_ghosts(phi, two ? 4 : 2));
-      f.phi_in = phi->p();
-      f.phi_out = scratch->p();
-      if (kind == 3) {
-        if (a.has_a) k_gsrb_stream2<1><<<blocks, 128, 4 * GS2_STAGES * 9 * 512, c->stream>>>(f);
-        else k_gsrb_stream2<0><<<blocks, 128, 4 * GS2_STAGES * 8 * 512, c->stream>>>(f);
-        c->launches++;
-      } else if (kind == 1) {
-        if (a.has_a) k_gsrb_stream<1, 3><<<blocks, 128, 4 * GS_STAGES * 9 * 512, c->stream>>>(f);
-        else k_gsrb_stream<0, 3><<<blocks, 128, 4 * GS_STAGES * 8 * 512, c->stream>>>(f);
-        c->launches++;
-      } else if (a.has_a) LAUNCH(c, (k_gsrb_fused<1, 4>), blocks, 128, f);
-      else if (c->tune[1] == 3) LAUNCH(c, (k_gsrb_fused<0, 3>), blocks, 128, f);
-      else LAUNCH(c, (k_gsrb_fused<0, 4>), blocks, 128, f);
-      std::swap(phi->base, scratch->base); // out-of-place sweep: the field now owns the new buffer
-      it += two ? 2 : 1;
+      const int chunk = (wide && kind == 1) ? std::min(4, iterations - it) : 1;
+      if (ghosts) SGCALL(fill_ghosts(phi, two ? 4 : 2 * chunk));
+      for (int sub = 0; sub < chunk; sub++) {
+        const int ext = 2 * (chunk - 1 - sub);
+        f.ylo = ygh_lo ? -ext : 0;
+        f.yhi = L->ny + (ygh_hi ? ext : 0);
+        const int blocks = plan(kind);
+        f.phi_in = phi->p();
+        f.phi_out = scratch->p();
+        if (kind == 3) {
+          if (a.has_a) k_gsrb_stream2<1><<<blocks, 128, 4 * GS2_STAGES * 9 * 512, c->stream>>>(f);
+          else k_gsrb_stream2<0><<<blocks, 128, 4 * GS2_STAGES * 8 * 512, c->stream>>>(f);
+          c->launches++;
+        } else if (kind == 1) {
+          if (a.has_a) k_gsrb_stream<1, 3><<<blocks, 128, 4 * GS_STAGES * 9 * 512, c->stream>>>(f);
+          else k_gsrb_stream<0, 3><<<blocks, 128, 4 * GS_STAGES * 8 * 512, c->stream>>>(f);
+          c->launches++;
+        } else if (a.has_a) LAUNCH(c, (k_gsrb_fused<1, 4>), blocks, 128, f);
+        else if (c->tune[1] == 3) LAUNCH(c, (k_gsrb_fused<0, 3>), blocks, 128, f);
+        else LAUNCH(c, (k_gsrb_fused<0, 4>), blocks, 128, f);
+        std::swap(phi->base, scratch->base); // out-of-place sweep: the field now owns the new buffer
+      }
+      it += two ? 2 : chunk;
     }
   } else {
     for (int it = 0; it < iterations; it++) {
@@ -1271,6 +1288,7 @@ static int relax_impl(sg_op* op, sg_field* phi, const sg_field* rhs, int iterati
     }
   }
   // trailing exchange + homogeneous BC fill (src/VCAMRNonLinearPoissonOp.cpp:751-759)
+  if (!trailing) return SG_OK;
   if (ghosts) SGCALL(fill_ghosts(phi, 1));
   SGCALL(phys_bc(phi, &op->bc, op->dx, 1));
   return SG_OK;
@@ -1746,8 +1764,8 @@ extern "C" int sg_solver_cell_updates_per_cycle(const sg_solver* s, const sg_sol
 static int mg_cycle(sg_solver* s, int depth, sg_field* phi, sg_field* rhs, const sg_solver_params* sp) {
   sg_op* op = s->ops[depth];
   int nd = (int)s->ops.size();
-  if (depth == nd - 1) return relax_impl(op, phi, rhs, sp->bottom);
-  SGCALL(relax_impl(op, phi, rhs, sp->pre));
+  if (depth == nd - 1) return relax_impl(op, phi, rhs, sp->bottom, false);
+  SGCALL(relax_impl(op, phi, rhs, sp->pre, false));
   int dc = depth + 1;
   sg_op* opc = s->ops[dc];
   if (op->update_operator) SGCALL(sg_op_AverageOperator(opc, s->ops[0], dc));
@@ -1759,7 +1777,7 @@ static int mg_cycle(sg_solver* s, int depth, sg_field* phi, sg_field* rhs, const
     sg_layout* L = op->lay;
     LAUNCH(s->ctx, k_prolong, grid2(L->nx, L->ny, B2D), B2D, phi->p(), L->pitch, L->nx, L->ny, s->phi[dc]->p(), s->save[dc]->p(), opc->lay->pitch);
   }
-  return relax_impl(op, phi, rhs, sp->post);
+  return relax_impl(op, phi, rhs, sp->post, false);
 }
 // AMRMultiGrid::computeAMRResidualLevel: aresid[l] = rhs[l] - L_composite(phi)
 static int amr_residual_level(sg_solver* s, sg_field* const* phi, sg_field* const* rhs, int l, int l_max) {

@@ -13,8 +13,8 @@
 #include <stdint.h>
 
 #define SG_XOFF 16
-#define SG_YOFF 4
-#define SG_YTOP 6
+#define SG_YOFF 8
+#define SG_YTOP 10
 
 // side kinds of the rank-local patch
 enum { SK_PHYS_DIRI = 0, SK_PHYS_NEUM = 1, SK_GHOST = 2, SK_FROZEN = 3, SK_PHYS_NONE = 4 };
@@ -238,6 +238,8 @@ struct FusedArgs {
   int rows_per_warp;
   int nstrips, nsegs;
   double sdx[4]; // isign*dx per side for Neumann
+  int ylo, yhi;  // rows [ylo, yhi) are updated and stored: [0, ny) normally; communication-avoiding relaxation widens the range
+                 // into the ghost rows of SK_GHOST sides (k_gsrb_stream only)
 };
 
 __device__ __forceinline__ double2 ld2(const double* p) { return *reinterpret_cast<const double2*>(p); }
@@ -455,8 +457,8 @@ __global__ void __launch_bounds__(128, MINB) k_gsrb_stream(FusedArgs f) {
   const int nx = a.g.nx, ny = a.g.ny;
   const ptrdiff_t P = a.g.pitch;
   const int x0 = strip * GS_COLS - 2 + 2 * lane; // columns x0, x0+1 (x0 even)
-  const int r0 = seg * f.rows_per_warp;
-  const int r1 = min(ny, r0 + f.rows_per_warp);
+  const int r0 = f.ylo + seg * f.rows_per_warp;
+  const int r1 = min(f.yhi, r0 + f.rows_per_warp);
   GsBC bc;
   bc.kxlo = a.g.kind[0]; bc.kxhi = a.g.kind[1]; bc.kylo = a.g.kind[2]; bc.kyhi = a.g.kind[3];
   bc.nx = nx; bc.ny = ny;
@@ -481,7 +483,7 @@ __global__ void __launch_bounds__(128, MINB) k_gsrb_stream(FusedArgs f) {
     if (q < r1) { // bundles past the last step are never consumed
       // rows q+2 / q+1 lie inside the allocated rows [-2, ny+3] for every consumed bundle; the two load-only bundles at the
       // start may name row -3 for the coefficients: clamp (that data is not used)
-      const ptrdiff_t o2 = (ptrdiff_t)(q + 2) * P, o1 = (ptrdiff_t)max(q + 1, -2) * P;
+      const ptrdiff_t o2 = (ptrdiff_t)(q + 2) * P, o1 = (ptrdiff_t)max(q + 1, -SG_YOFF) * P;
       double2* s = ring + (size_t)stage * (NARR * 32);
       cp_async16(s, g0 + o2); cp_async16(s + 32, g1 + o2);
       cp_async16(s + 64, g2 + o1); cp_async16(s + 96, g3 + o1); cp_async16(s + 128, g4 + o1); cp_async16(s + 160, g5 + o1);
@@ -491,7 +493,9 @@ __global__ void __launch_bounds__(128, MINB) k_gsrb_stream(FusedArgs f) {
     }
     cp_async_commit();
   };
-  auto rowupd = [&](int j) -> bool { return (j >= 0 && j < ny) || (j == -1 && bc.kylo == SK_GHOST) || (j == ny && bc.kyhi == SK_GHOST); };
+  // rows that may be updated: the stored range, plus the ring row beyond it on SK_GHOST sides
+  const int jlo = bc.kylo == SK_GHOST ? f.ylo - 1 : 0, jhi = bc.kyhi == SK_GHOST ? f.yhi : ny - 1;
+  auto rowupd = [&](int j) -> bool { return j >= jlo && j <= jhi; };
 
   const double2 z2 = make_double2(0.0, 0.0);
   double2 pm = z2, p0 = z2, p1 = z2, p2 = z2, by0 = z2, by1 = z2, by2 = z2;
