@@ -79,6 +79,14 @@ struct sg_ctx {
   cudaEvent_t ev[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
 };
 
+// one peer of a copy plan that crosses ranks: segments packed into sendbuf / unpacked from recvbuf (ncclSend/ncclRecv)
+struct PeerPlan {
+  int rank = -1;
+  CopySeg *d_send = nullptr, *d_recv = nullptr;
+  int nsend = 0, nrecv = 0;
+  size_t send_count = 0, recv_count = 0;
+  double *sendbuf = nullptr, *recvbuf = nullptr;
+};
 struct sg_field;
 struct sg_layout {
   sg_ctx* ctx;
@@ -104,11 +112,17 @@ struct sg_layout {
   PatchG* d_patches = nullptr;
   size_t total = 0;                // doubles per component
   int max_nx = 0, max_ny = 0;
-  struct Plan { CopySeg* d = nullptr; int n = 0; bool built = false; };
+  struct Plan { CopySeg* d = nullptr; int n = 0; bool built = false; std::vector<PeerPlan> peers; };
   Plan ex_faces, ex_full[3];       // exchange plans (general path): face strips depth 1; all ghosts depth 1 / 2
   // spatial bins over the domain for "which patch holds cell (i,j)"
   int bin_s = 0, bin_nx = 0, bin_ny = 0;
   std::vector<std::vector<int>> bins;
+  // the level as ALL ranks hold it: one entry per rank rectangle (merged levels) or per box (general levels), in an order
+  // every rank computes identically -- copy plans between ranks are enumerated over it
+  struct GPatch { Box b; int owner; int local; }; // local: index into `patches` when owner == this rank, else -1
+  std::vector<GPatch> gp;
+  int gbin_s = 0, gbin_nx = 0, gbin_ny = 0;
+  std::vector<std::vector<int>> gbins;
 };
 #define GEN_GX 2
 #define GEN_GY 2
@@ -311,25 +325,6 @@ extern "C" int sg_set_relax_mode(sg_ctx* c, int mode) {
 // ------------------------------------------------------------------------------------------------
 // layouts
 // ------------------------------------------------------------------------------------------------
-// which local patch holds cell (i,j) in its valid region, periodic images included (-1: none); (*wi,*wj) = wrapped index
-static int patch_at(const sg_layout* L, int i, int j, int* wi, int* wj) {
-  for (int d = 0; d < 2; d++) {
-    int& x = d == 0 ? i : j;
-    int lo = L->domain.lo[d], n = L->domain.hi[d] - lo + 1;
-    if (x < lo || x > L->domain.hi[d]) {
-      if (!L->periodic[d]) return -1;
-      x = lo + (((x - lo) % n) + n) % n;
-    }
-  }
-  if (wi) *wi = i;
-  if (wj) *wj = j;
-  int bx = (i - L->domain.lo[0]) / L->bin_s, by = (j - L->domain.lo[1]) / L->bin_s;
-  for (int k : L->bins[(size_t)by * L->bin_nx + bx]) {
-    const PatchG& g = L->patches[k];
-    if (i >= g.glo0 && i < g.glo0 + g.nx && j >= g.glo1 && j < g.glo1 + g.ny) return k;
-  }
-  return -1;
-}
 static inline bool in_domain_p(const sg_layout* L, int i, int j) {
   if (!L->periodic[0] && (i < L->domain.lo[0] || i > L->domain.hi[0])) return false;
   if (!L->periodic[1] && (j < L->domain.lo[1] || j > L->domain.hi[1])) return false;
@@ -383,21 +378,31 @@ static int layout_host(sg_layout* L) {
     area[r] += bx.npts();
   }
   bool tiles = true;
-  for (int r = 0; r < c->nranks; r++)
+  long long covered = 0;
+  for (int r = 0; r < c->nranks; r++) {
     if (has[r] && area[r] != rp[r].npts()) tiles = false;
+    covered += area[r];
+    // across ranks only full-width y-strips of a level that covers the whole domain are stored merged (NCCL row exchange)
+    if (c->nranks > 1 && has[r] && (rp[r].lo[0] != L->domain.lo[0] || rp[r].hi[0] != L->domain.hi[0])) tiles = false;
+  }
+  if (c->nranks > 1 && covered != L->domain.npts()) tiles = false;
   L->has_local = has[c->rank];
   L->patch_of_box.assign(L->nbox, -1);
+  L->gp.clear();
   if (!tiles) {
-    // refined AMR level: every box is its own patch with a private ghost ring (Chombo's own data model)
-    if (c->nranks != 1)
-      return fail(SG_ERR_UNSUPPORTED, "layout: boxes do not tile one rectangle per rank; multi-patch (refined AMR) levels are "
-                  "single-GPU in this build");
+    // refined AMR level: every box is its own patch with a private ghost ring (Chombo's own data model); a rank stores the
+    // boxes it owns, ghost filling and inter-level copies run over copy plans that may cross ranks
     L->general = true; L->fast = false;
-    L->patch = rp[0];
+    L->patch = has[c->rank] ? rp[c->rank] : L->boxes[0];
     L->nx = L->patch.nx(); L->ny = L->patch.ny(); L->pitch = 0; L->rows = 0;
     size_t tot = 0;
     for (int b = 0; b < L->nbox; b++) {
       const Box& bx = L->boxes[b];
+      sg_layout::GPatch q;
+      q.b = bx; q.owner = L->owner[b]; q.local = -1;
+      if (L->owner[b] != c->rank) { L->gp.push_back(q); continue; }
+      q.local = (int)L->patches.size();
+      L->gp.push_back(q);
       PatchG g;
       g.nx = bx.nx(); g.ny = bx.ny(); g.glo0 = bx.lo[0]; g.glo1 = bx.lo[1];
       g.pitch = ((g.nx + 2 * GEN_GX + 2 + 1) / 2) * 2;
@@ -415,6 +420,12 @@ static int layout_host(sg_layout* L) {
     L->total = tot;
     return SG_OK;
   }
+  for (int r = 0; r < c->nranks; r++)
+    if (has[r]) {
+      sg_layout::GPatch q;
+      q.b = rp[r]; q.owner = r; q.local = r == c->rank ? 0 : -1;
+      L->gp.push_back(q);
+    }
   if (!L->has_local) return SG_OK;
   L->patch = rp[c->rank];
   L->nx = L->patch.nx(); L->ny = L->patch.ny();
@@ -478,8 +489,24 @@ static int layout_host(sg_layout* L) {
   }
   return SG_OK;
 }
+static void layout_global_bins(sg_layout* L) {
+  int smax = 16;
+  for (const auto& q : L->gp) smax = std::max(smax, std::max(q.b.nx(), q.b.ny()));
+  L->gbin_s = smax;
+  L->gbin_nx = (L->domain.hi[0] - L->domain.lo[0]) / smax + 1;
+  L->gbin_ny = (L->domain.hi[1] - L->domain.lo[1]) / smax + 1;
+  L->gbins.assign((size_t)L->gbin_nx * L->gbin_ny, std::vector<int>());
+  for (int k = 0; k < (int)L->gp.size(); k++) {
+    const Box& b = L->gp[k].b;
+    int bx0 = (b.lo[0] - L->domain.lo[0]) / smax, bx1 = (b.hi[0] - L->domain.lo[0]) / smax;
+    int by0 = (b.lo[1] - L->domain.lo[1]) / smax, by1 = (b.hi[1] - L->domain.lo[1]) / smax;
+    for (int by = by0; by <= by1; by++)
+      for (int bx = bx0; bx <= bx1; bx++) L->gbins[(size_t)by * L->gbin_nx + bx].push_back(k);
+  }
+}
 static int layout_finish(sg_layout* L) {
   SGCALL(layout_host(L));
+  layout_global_bins(L);
   return layout_tables(L);
 }
 
@@ -583,13 +610,14 @@ extern "C" int sg_layout_nbox(const sg_layout* L, int* nbox) {
 }
 extern "C" int sg_field_destroy(sg_field* f);
 static void copy_plans_forget(const sg_layout* L);
+static void plan_free(sg_layout::Plan& P);
 extern "C" int sg_layout_destroy(sg_layout* L) {
   if (!L) return SG_OK;
   for (sg_field* w : L->ws) sg_field_destroy(w);
   copy_plans_forget(L);
   cudaFree(L->d_patches);
-  cudaFree(L->ex_faces.d);
-  for (int k = 0; k < 3; k++) cudaFree(L->ex_full[k].d);
+  plan_free(L->ex_faces);
+  for (int k = 0; k < 3; k++) plan_free(L->ex_full[k]);
   delete L;
   return SG_OK;
 }
@@ -960,27 +988,35 @@ extern "C" int sg_divergence(sg_field* div, const sg_field* ux, const sg_field* 
 static int wflx_impl(sg_ctx* ctx, sg_op* op, const sg_params* p, sg_field* bX, sg_field* bY, sg_field* u, sg_field* u_coarse,
                      const sg_field* B, const sg_field* mask, const double dx[2]) {
   sg_layout* L = u->lay;
-  if (!L->has_local) return SG_OK;
-  sg_field *grad, *Re;
-  SGCALL(ws_field(L, 1, 2, &grad));
-  SGCALL(ws_field(L, 2, 1, &Re));
-  SGCALL(gradient_cc_any(grad, u, p->use_mask_grad ? mask : nullptr, dx));
-  int ngsave = grad->ng;
-  grad->ng = 1;
-  if (u_coarse) {
+  sg_field *grad = nullptr, *Re = nullptr;
+  int ngsave = 0;
+  if (L->has_local) {
+    SGCALL(ws_field(L, 1, 2, &grad));
+    SGCALL(ws_field(L, 2, 1, &Re));
+    SGCALL(gradient_cc_any(grad, u, p->use_mask_grad ? mask : nullptr, dx));
+    ngsave = grad->ng;
+    grad->ng = 1;
+  }
+  if (u_coarse) { // collective: every rank computes its part of the coarse gradient and takes part in the copy plan
     REQUIRE(op && op->link, "WFlx_level: a coarse head needs the operator's coarse-fine interpolator (use sg_op_UpdateOperator)");
     sg_layout* Lc = u_coarse->lay;
-    sg_field* gradC;
-    SGCALL(ws_field(Lc, 3, 2, &gradC));
-    double dxc[2] = {dx[0] * 2, dx[1] * 2}; // "assumes refRatio = 2" (src/AmrHydro.cpp:1467)
-    SGCALL(gradient_cc_any(gradC, u_coarse, p->use_mask_grad ? op->link->crse_mask : nullptr, dxc));
-    int ngc = gradC->ng;
-    gradC->ng = 1;
-    SGCALL(exchange_any(gradC, 1, 1));
-    SGCALL(extrap_any(gradC, 0));
-    gradC->ng = ngc;
-    SGCALL(cf_interp_impl(op, grad, gradC));
+    sg_field* gradC = nullptr;
+    if (Lc->has_local) {
+      SGCALL(ws_field(Lc, 3, 2, &gradC));
+      double dxc[2] = {dx[0] * 2, dx[1] * 2}; // "assumes refRatio = 2" (src/AmrHydro.cpp:1467)
+      SGCALL(gradient_cc_any(gradC, u_coarse, p->use_mask_grad ? op->link->crse_mask : nullptr, dxc));
+      int ngc = gradC->ng;
+      gradC->ng = 1;
+      SGCALL(exchange_any(gradC, 1, 1));
+      SGCALL(extrap_any(gradC, 0));
+      gradC->ng = ngc;
+    }
+    sg_field dummyC, dummyF; // ranks without patches on one of the two levels still run the plan (with nothing to move there)
+    dummyC.lay = Lc; dummyC.ncomp = 2; dummyC.ng = 1; dummyC.cent = SG_CELL; dummyC.base = nullptr; dummyC.comp_stride = 0;
+    dummyF.lay = L; dummyF.ncomp = 2; dummyF.ng = 1; dummyF.cent = SG_CELL; dummyF.base = nullptr; dummyF.comp_stride = 0;
+    SGCALL(cf_interp_impl(op, grad ? grad : &dummyF, gradC ? gradC : &dummyC));
   }
+  if (!L->has_local) return SG_OK;
   SGCALL(exchange_any(grad, 1, 1)); // lvlgradH.exchange()
   SGCALL(extrap_any(grad, 0));      // ExtrapGhostCells(lvlgradH, levelDomain)
   grad->ng = ngsave;
@@ -1423,12 +1459,14 @@ extern "C" int sg_op_UpdateOperator(sg_op* op, sg_field* phi, const sg_field* ph
   if (homogeneous) return fail(SG_ERR_ABORT, "VCAMRNonLinearPoissonOp::UpdateOperator homogeneous");
   SGCALL(check_same(op, phi, "UpdateOperator(phi)"));
   sg_layout* L = op->lay;
-  if (!L->has_local) return SG_OK;
-  if (L->fast) { if (has_ghost_sides(L)) SGCALL(fill_ghosts(phi, 1)); }
-  else SGCALL(exchange_g(phi, 1, 0));
-  SGCALL(phys_bc_any(phi, &op->bc, op->dx, 0));
+  if (!L->has_local && !phi_coarse) return SG_OK;
+  if (L->has_local) {
+    if (L->fast) { if (has_ghost_sides(L)) SGCALL(fill_ghosts(phi, 1)); }
+    else SGCALL(exchange_g(phi, 1, 0));
+    SGCALL(phys_bc_any(phi, &op->bc, op->dx, 0));
+  }
   SGCALL(wflx_impl(op->ctx, op, &op->prm, op->bX, op->bY, phi, const_cast<sg_field*>(phi_coarse), op->B, op->mask, op->dx));
-  if (L->fast) SGCALL(coef_ghosts(op, true));
+  if (L->has_local && L->fast) SGCALL(coef_ghosts(op, true));
   return SG_OK; // lambda is recomputed inside the kernels
 }
 extern "C" int sg_op_AverageOperator(sg_op* op, const sg_op* finest, int depth) {
@@ -1603,6 +1641,7 @@ static int amr_restrict_impl(sg_op* op, sg_field* resC, const sg_field* residual
   if (!skip_res) SGCALL(amr_residual_impl(op, scratch, nullptr, correction, coarseCorrection, residual, 0, nullptr));
   else SGCALL(vec_launch<3>(scratch, residual, nullptr, 0, 0, true)); // assignLocal
   sg_layout* Lc = resC->lay;
+  if (!L->has_local) return SG_OK;
   dim3 g((Lc->max_nx + B2D.x - 1) / B2D.x, (Lc->max_ny + B2D.y - 1) / B2D.y, (unsigned)Lc->patches.size());
   LAUNCH(op->ctx, k_amr_average, g, B2D, resC->cb(), Lc->d_patches, scratch->cb(), L->d_patches);
   return SG_OK;
@@ -1621,15 +1660,17 @@ static int amr_prolong_impl(sg_op* op, sg_field* correction, const sg_field* coa
   if (second_order) {
     REQUIRE(crseOp, "AMRProlongS_2: needs the coarser operator");
     SGCALL(run_plan(c, K->temp->cb(), coarseCorrection->cb(), K->c2t[1]));
-    int ngs = K->temp->ng;
-    K->temp->ng = 1;
-    SGCALL(phys_bc_any(K->temp, &crseOp->bc, crseOp->dx, 0)); // m_use_FAS: inhomogeneous coarse BC on the scratch
-    K->temp->ng = ngs;
-    sg_field one = *K->temp;
-    one.ncomp = 1;
-    SGCALL(exchange_any(&one, 1, 1)); // CornerCopier exchange among the scratch's boxes
+    if (L->has_local) {
+      int ngs = K->temp->ng;
+      K->temp->ng = 1;
+      SGCALL(phys_bc_any(K->temp, &crseOp->bc, crseOp->dx, 0)); // m_use_FAS: inhomogeneous coarse BC on the scratch
+      K->temp->ng = ngs;
+      sg_field one = *K->temp;
+      one.ncomp = 1;
+      SGCALL(exchange_any(&one, 1, 1)); // CornerCopier exchange among the scratch's boxes
+    }
   } else SGCALL(run_plan(c, K->temp->cb(), coarseCorrection->cb(), K->c2t[0]));
-  LAUNCH(c, k_amr_prolong, grid_g(L, 0, 0), B2D, correction->cb(), L->d_patches, K->temp->cb(), K->clay->d_patches, second_order);
+  if (L->has_local) LAUNCH(c, k_amr_prolong, grid_g(L, 0, 0), B2D, correction->cb(), L->d_patches, K->temp->cb(), K->clay->d_patches, second_order);
   return SG_OK;
 }
 extern "C" int sg_op_AMRProlongS(sg_op* op, sg_field* correction, const sg_field* coarse_correction) {
@@ -1831,6 +1872,7 @@ static int residual_norm(sg_solver* s, sg_field* const* phi, sg_field* const* rh
     if (l < l_max) SGCALL(zero_covered_impl(s->aops[l], s->aresid[l], s->aops[l + 1]->lay));
     // max|.| accumulates into the same slot across levels (atomicMax on the bit pattern)
     sg_layout* L = s->aops[l]->lay;
+    if (!L->has_local) continue;
     if (L->fast) LAUNCH(c, k_reduce, grid2(L->nx, L->ny, B2D), B2D, s->aresid[l]->p(), nullptr, L->pitch, L->nx, L->ny, 0, c->d_partial, nb);
     else LAUNCH(c, k_reduce_g, grid_g(L, 0, 0), B2D, s->aresid[l]->cb(), nullptr, L->d_patches, 0, c->d_partial, nb);
   }

@@ -353,21 +353,49 @@ __global__ void __launch_bounds__(128) k_cf_interp(double* __restrict__ fineb, c
   fineb[it.fo] = a * x * x + bq * x + pa;
 }
 
-// Flux register (VCAMRNonLinearPoissonOp::reflux over LevelFluxRegister; oracle: orc_op_reflux).  One thread per coarse
-// cell that borders the fine level; faces in the order dir0-Lo, dir0-Hi, dir1-Lo, dir1-Hi.
+// Flux register (VCAMRNonLinearPoissonOp::reflux over LevelFluxRegister; oracle: orc_op_reflux), in two halves so that the
+// fine and the coarse level may live on different GPUs.
+// Fine half (incrementFine): one thread per coarse register cell and (dir, side) -- the two fine face fluxes on that coarse
+// face, each scaled by sign*scale/r, summed in face order, stored in component dir*2+side of the coarsened-fine scratch.
+struct FluxPiece {
+  long long out;                          // register cell in the scratch (a ghost cell of the coarsened fine box)
+  long long f_in[2], f_gh[2], f_b[2];     // per fine face: interior fine cell, its coarse-fine ghost cell, fine face coefficient
+  int dir, side;
+};
+__global__ void __launch_bounds__(128) k_flux_pieces(double* __restrict__ tempb, long long comp_stride, const double* __restrict__ phifb,
+                                                     const double* __restrict__ bXf, const double* __restrict__ bYf,
+                                                     const FluxPiece* __restrict__ items, int n, double beta, double dxc0, double dxc1, int r) {
+  int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n) return;
+  const FluxPiece& f = items[t];
+  const int dir = f.dir, side = f.side;
+  const double dxn = dir == 0 ? dxc0 : dxc1, scale = dir == 0 ? dxc1 : dxc0;
+  const double* bf = dir == 0 ? bXf : bYf;
+  double sgn = side ? 1.0 : -1.0;
+  double sf = sgn * scale / (double)r;
+  double piece = 0.0;
+  for (int m = 0; m < 2; m++) {
+    double phihi = side ? phifb[f.f_gh[m]] : phifb[f.f_in[m]];
+    double philo = side ? phifb[f.f_in[m]] : phifb[f.f_gh[m]];
+    double gradphi = (phihi - philo) * (beta * r / dxn);
+    double F = -bf[f.f_b[m]] * gradphi;
+    piece = piece + sf * F;
+  }
+  tempb[(long long)(dir * 2 + side) * comp_stride + f.out] = piece;
+}
+// Coarse half: one thread per coarse cell that borders the fine level; faces in the order dir0-Lo, dir0-Hi, dir1-Lo, dir1-Hi:
+// the coarse fluxes (incrementCoarse), then the fine sums in the same order, then residual += -(1/dx dy) * register.
 struct RefluxFace {
   int valid, pad;
-  long long c_hi, c_lo, c_b;            // coarse phi cells on the high/low side of the CF face, coarse face coefficient
-  long long f_in[2], f_gh[2], f_b[2];   // per fine face: interior fine cell, its CF ghost cell, fine face coefficient
+  long long c_hi, c_lo, c_b; // coarse phi cells on the high/low side of the CF face, coarse face coefficient
 };
 struct RefluxItem {
   long long res;
   RefluxFace f[4];
 };
 __global__ void __launch_bounds__(128) k_reflux(double* __restrict__ resb, const double* __restrict__ phicb, const double* __restrict__ bXc,
-                                                const double* __restrict__ bYc, const double* __restrict__ phifb,
-                                                const double* __restrict__ bXf, const double* __restrict__ bYf,
-                                                const RefluxItem* __restrict__ items, int n, double beta, double dxc0, double dxc1, int r) {
+                                                const double* __restrict__ bYc, const double* __restrict__ regb, long long reg_stride,
+                                                const RefluxItem* __restrict__ items, int n, double beta, double dxc0, double dxc1) {
   int t = blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= n) return;
   const RefluxItem& it = items[t];
@@ -386,24 +414,8 @@ __global__ void __launch_bounds__(128) k_reflux(double* __restrict__ resb, const
     double sgn = side ? 1.0 : -1.0;
     reg = reg + (-sgn * scale) * F;
   }
-  for (int k = 0; k < 4; k++) { // incrementFine
-    const RefluxFace& f = it.f[k];
-    if (!f.valid) continue;
-    const int dir = k >> 1, side = k & 1;
-    const double dxn = dir == 0 ? dxc0 : dxc1, scale = dir == 0 ? dxc1 : dxc0;
-    const double* bf = dir == 0 ? bXf : bYf;
-    double sgn = side ? 1.0 : -1.0;
-    double sf = sgn * scale / (double)r;
-    double piece = 0.0;
-    for (int m = 0; m < 2; m++) {
-      double phihi = side ? phifb[f.f_gh[m]] : phifb[f.f_in[m]];
-      double philo = side ? phifb[f.f_in[m]] : phifb[f.f_gh[m]];
-      double gradphi = (phihi - philo) * (beta * r / dxn);
-      double F = -bf[f.f_b[m]] * gradphi;
-      piece = piece + sf * F;
-    }
-    reg = reg + piece;
-  }
+  for (int k = 0; k < 4; k++) // the fine sums
+    if (it.f[k].valid) reg = reg + regb[(long long)k * reg_stride + it.res];
   resb[it.res] = resb[it.res] + (-scale2) * reg;
 }
 

@@ -189,9 +189,9 @@ class AmrOracleSide:
 
 
 class AmrGpuSide:
-    """Device twin of an AmrOracleSide."""
+    """Device twin of an AmrOracleSide.  owners: per level, the rank owning each box (None: everything on this rank)."""
 
-    def __init__(self, ctx, orc):
+    def __init__(self, ctx, orc, owners=None):
         from suhmo_b200 import amr
         self.amr, self.ctx, self.orc = amr, ctx, orc
         cfg = orc.cfg
@@ -200,7 +200,8 @@ class AmrGpuSide:
         self.layouts, self.F = [], []
         for l in range(orc.nlev):
             r = 2 ** l
-            lay = amr.DisjointBoxLayout(ctx, orc.level_boxes[l], (0, 0, cfg.nx * r - 1, cfg.ny * r - 1), cfg.periodic)
+            lay = amr.DisjointBoxLayout(ctx, orc.level_boxes[l], (0, 0, cfg.nx * r - 1, cfg.ny * r - 1), cfg.periodic,
+                                        None if owners is None else owners[l])
             F = {k: amr.LevelData(lay, 1, ng, cent) for k, (ng, cent) in spec.items()}
             self.layouts.append(lay)
             self.F.append(F)
@@ -218,7 +219,8 @@ class AmrGpuSide:
 
     def push(self, l, name, src=None):
         of = src if src is not None else self.orc.F[l][name]
-        self.F[l][name].upload([of.fab(b)[0].copy() for b in range(len(self.layouts[l].boxes))])
+        lay = self.layouts[l]
+        self.F[l][name].upload([of.fab(b)[0].copy() if lay.owned(b) else None for b in range(len(lay.boxes))])
 
     def new_like(self, l, name):
         f = self.F[l][name]
