@@ -112,7 +112,8 @@ struct sg_layout {
   PatchG* d_patches = nullptr;
   size_t total = 0;                // doubles per component
   int max_nx = 0, max_ny = 0;
-  struct Plan { CopySeg* d = nullptr; int n = 0; bool built = false; std::vector<PeerPlan> peers; };
+  bool any_phys = false;           // some patch side lies on a non-periodic domain boundary (else physical-BC kernels are skipped)
+  struct Plan { CopySeg* d = nullptr; int n = 0; bool built = false; bool small = false; std::vector<PeerPlan> peers; };
   Plan ex_faces, ex_full[3];       // exchange plans (general path): face strips depth 1; all ghosts depth 1 / 2
   // spatial bins over the domain for "which patch holds cell (i,j)"
   int bin_s = 0, bin_nx = 0, bin_ny = 0;
@@ -342,7 +343,10 @@ static int layout_tables(sg_layout* L) {
   sg_ctx* c = L->ctx;
   if (!L->has_local) return SG_OK;
   L->max_nx = L->max_ny = 0;
-  for (const PatchG& g : L->patches) { L->max_nx = std::max(L->max_nx, g.nx); L->max_ny = std::max(L->max_ny, g.ny); }
+  for (const PatchG& g : L->patches) {
+    L->max_nx = std::max(L->max_nx, g.nx); L->max_ny = std::max(L->max_ny, g.ny);
+    L->any_phys = L->any_phys || g.phys[0] || g.phys[1] || g.phys[2] || g.phys[3];
+  }
   CK(cudaMalloc(&L->d_patches, L->patches.size() * sizeof(PatchG)));
   CK(cudaMemcpyAsync(L->d_patches, L->patches.data(), L->patches.size() * sizeof(PatchG), cudaMemcpyHostToDevice, c->stream));
   CK(cudaStreamSynchronize(c->stream));

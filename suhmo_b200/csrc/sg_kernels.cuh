@@ -978,3 +978,15 @@ __global__ void k_copy_segs(double* __restrict__ dst, const double* __restrict__
     dst[c.dofs + (long long)j * c.dp + i] = src[c.so + (long long)j * c.sp + i];
   }
 }
+// same, one WARP per segment: ghost exchange of refined levels moves ~10^5 strips of <= 64 cells
+__global__ void __launch_bounds__(256) k_copy_segs_warp(double* __restrict__ dst, const double* __restrict__ src, const CopySeg* __restrict__ segs,
+                                                         int nseg) {
+  int s = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (s >= nseg) return;
+  CopySeg c = segs[s];
+  const int n = c.nx * c.ny;
+  for (int t = threadIdx.x & 31; t < n; t += 32) {
+    int i = t % c.nx, j = t / c.nx;
+    dst[c.dofs + (long long)j * c.dp + i] = src[c.so + (long long)j * c.sp + i];
+  }
+}
