@@ -318,7 +318,7 @@ extern "C" int sg_set_tuning(sg_ctx* c, int key, int value) {
   return SG_OK;
 }
 extern "C" int sg_set_relax_mode(sg_ctx* c, int mode) {
-  REQUIRE(c && mode >= 0 && mode <= 3, "sg_set_relax_mode");
+  REQUIRE(c && mode >= 0 && mode <= 4, "sg_set_relax_mode");
   c->relax_mode = mode;
   return SG_OK;
 }
@@ -1242,7 +1242,7 @@ static int relax_impl(sg_op* op, sg_field* phi, const sg_field* rhs, int iterati
     sg_field* scratch;
     SGCALL(ws_field(L, 0, 1, &scratch));
     // temporal blocking recomputes a 4-cell ring: periodic images inside the patch must then be at least 4 cells away
-    const bool can2 = c->relax_mode == 3 && (!L->wrap_local[0] || L->nx >= 4) && (!L->wrap_local[1] || L->ny >= 4) && L->ny >= 4;
+    const bool can2 = (c->relax_mode == 3 || c->relax_mode == 4) && (!L->wrap_local[0] || L->nx >= 4) && (!L->wrap_local[1] || L->ny >= 4) && L->ny >= 4;
     if (ghosts) SGCALL(fill_ghosts(const_cast<sg_field*>(rhs), can2 ? 3 : 1));
     FusedArgs f;
     f.a = a;
@@ -1255,22 +1255,24 @@ static int relax_impl(sg_op* op, sg_field* phi, const sg_field* rhs, int iterati
       CK(cudaFuncSetAttribute(k_gsrb_stream<1, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 * GS_STAGES * 9 * 512));
       CK(cudaFuncSetAttribute(k_gsrb_stream2<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 * GS2_STAGES * 8 * 512));
       CK(cudaFuncSetAttribute(k_gsrb_stream2<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 * GS2_STAGES * 9 * 512));
+      CK(cudaFuncSetAttribute(k_gsrb_pair<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * (GP_STAGES * 8 * 512 + 1024)));
+      CK(cudaFuncSetAttribute(k_gsrb_pair<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * (GP_STAGES * 9 * 512 + 1024)));
       attr_set = true;
     }
     // Segments of rows per warp.  Measured on B200 (tools/relax_bench.py): many short segments beat one resident wave
     // (warps marching in lock-step), 32-64 rows per warp is the plateau on HBM-sized levels, and L2-resident levels want
     // the shortest segments that still amortise the load-only steps of a segment (4 for one iteration, 9 for two).
-    auto plan = [&](int kind) { // 1 stream, 2 fused, 3 stream2
-      const int cols = kind == 3 ? GS2_COLS : kind == 1 ? GS_COLS : FUSED_COLS;
+    auto plan = [&](int kind) { // 1 stream, 2 fused, 3 stream2, 4 producer/consumer pairs
+      const int cols = kind == 3 ? GS2_COLS : kind == 4 ? GP_COLS : kind == 1 ? GS_COLS : FUSED_COLS;
       f.nstrips = (L->nx + cols - 1) / cols;
-      int minb = kind == 3 ? 2 : kind == 1 ? 3 : (c->tune[1] == 3 ? 3 : 4);
-      int capacity = c->num_sms * minb * 4; // resident warps (128-thread CTAs)
+      int minb = kind == 3 ? 2 : (kind == 1 || kind == 4) ? 3 : (c->tune[1] == 3 ? 3 : 4);
+      int capacity = c->num_sms * minb * (kind == 4 ? 2 : 4); // resident warps (pairs for kind 4) of 128-thread CTAs
       int nsegs;
       const int nrows = kind == 1 ? f.yhi - f.ylo : L->ny;
       if (c->tune[0] > 0) nsegs = (nrows + c->tune[0] - 1) / c->tune[0];
-      else if (kind == 1 || kind == 3) {
+      else if (kind == 1 || kind == 3 || kind == 4) {
         long long rows = ((long long)f.nstrips * nrows) / (4LL * capacity);
-        rows = kind == 3 ? std::max(16LL, std::min(96LL, rows)) : std::max(8LL, std::min(48LL, rows));
+        rows = kind != 1 ? std::max(16LL, std::min(96LL, rows)) : std::max(8LL, std::min(48LL, rows));
         nsegs = (int)((nrows + rows - 1) / rows);
       } else if (f.nstrips * ((L->ny + 63) / 64) <= capacity) nsegs = std::max(1, std::min((L->ny + 31) / 32, capacity / f.nstrips));
       else {
@@ -1279,6 +1281,7 @@ static int relax_impl(sg_op* op, sg_field* phi, const sg_field* rhs, int iterati
       }
       f.rows_per_warp = (nrows + nsegs - 1) / nsegs;
       f.nsegs = (nrows + f.rows_per_warp - 1) / f.rows_per_warp;
+      if (kind == 4) return (f.nstrips * f.nsegs + 1) / 2; // two pairs per CTA
       return (f.nstrips * f.nsegs * 32 + 127) / 128;
     };
     // Communication-avoiding relaxation (mode 1): instead of exchanging two ghost rows before every sweep, exchange 2k rows
@@ -1292,7 +1295,7 @@ static int relax_impl(sg_op* op, sg_field* phi, const sg_field* rhs, int iterati
     int it = 0;
     while (it < iterations) {
       const bool two = can2 && it + 2 <= iterations;
-      const int kind = two ? 3 : (c->relax_mode == 2 ? 2 : 1);
+      const int kind = two ? (c->relax_mode == 4 ? 4 : 3) : (c->relax_mode == 2 ? 2 : 1);
       const int chunk = (wide && kind == 1) ? std::min(4, iterations - it) : 1;
       if (ghosts) SGCALL(fill_ghosts(phi, two ? 4 : 2 * chunk));
       for (int sub = 0; sub < chunk; sub++) {
@@ -1302,7 +1305,11 @@ static int relax_impl(sg_op* op, sg_field* phi, const sg_field* rhs, int iterati
         const int blocks = plan(kind);
         f.phi_in = phi->p();
         f.phi_out = scratch->p();
-        if (kind == 3) {
+        if (kind == 4) {
+          if (a.has_a) k_gsrb_pair<1><<<blocks, 128, 2 * (GP_STAGES * 9 * 512 + 1024), c->stream>>>(f);
+          else k_gsrb_pair<0><<<blocks, 128, 2 * (GP_STAGES * 8 * 512 + 1024), c->stream>>>(f);
+          c->launches++;
+        } else if (kind == 3) {
           if (a.has_a) k_gsrb_stream2<1><<<blocks, 128, 4 * GS2_STAGES * 9 * 512, c->stream>>>(f);
           else k_gsrb_stream2<0><<<blocks, 128, 4 * GS2_STAGES * 8 * 512, c->stream>>>(f);
           c->launches++;

@@ -678,6 +678,156 @@ __global__ void __launch_bounds__(128, 2) k_gsrb_stream2(FusedArgs f) {
 }
 
 // ------------------------------------------------------------------------------------------------
+// k_gsrb_pair: two levelGSRB iterations per sweep with a PRODUCER / CONSUMER WARP PAIR.  Warp A runs iteration 1 exactly
+// like k_gsrb_stream (cp.async-staged bundles, red then black) but hands each finished row to warp B through a small
+// shared-memory ring instead of storing it; warp B trails three rows behind, runs iteration 2 on those rows with the
+// coefficient bundles A already staged, and stores the result.  Both warps keep the register footprint and the two-update
+// dependency chain of the one-iteration kernel (12 warps/SM stay resident), yet every array is read once per TWO
+// iterations.  One named barrier per step and pair orders the hand-over.  Geometry as k_gsrb_stream2 (56 of 64 columns).
+// ------------------------------------------------------------------------------------------------
+#define GP_COLS 56
+#define GP_D 3
+#define GP_LAG 3
+#define GP_STAGES (GP_D + GP_LAG + 1)
+
+// named barrier of one producer/consumer pair (64 threads); ids fixed at compile time so only two barriers are reserved
+__device__ __forceinline__ void pair_barrier(int id) {
+  if (id == 1) asm volatile("bar.sync 1, 64;" ::: "memory");
+  else asm volatile("bar.sync 2, 64;" ::: "memory");
+}
+
+template <int HAS_A>
+__global__ void __launch_bounds__(128, 3) k_gsrb_pair(FusedArgs f) {
+  extern __shared__ double2 gs_smem[];
+  constexpr int NARR = 8 + HAS_A;
+  constexpr int PAIR_D2 = GP_STAGES * NARR * 32 + 2 * 32; // double2 elements per pair: bundles + psi ring (2 rows) = GP_STAGES*NARR*512 + 1024 bytes
+  const OpArgs& a = f.a;
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  const int pair = wib >> 1, role = wib & 1;
+  const int item = blockIdx.x * 2 + pair;
+  if (item >= f.nstrips * f.nsegs) return; // both warps of a pair leave together
+  const int strip = item % f.nstrips, seg = item / f.nstrips;
+  const int nx = a.g.nx, ny = a.g.ny;
+  const ptrdiff_t P = a.g.pitch;
+  const int x0 = strip * GP_COLS - 4 + 2 * lane;
+  const int r0 = seg * f.rows_per_warp;
+  const int r1 = min(ny, r0 + f.rows_per_warp);
+  GsBC bc;
+  bc.kxlo = a.g.kind[0]; bc.kxhi = a.g.kind[1]; bc.kylo = a.g.kind[2]; bc.kyhi = a.g.kind[3];
+  bc.nx = nx; bc.ny = ny;
+  bc.v0 = a.g.bcval[0]; bc.v1 = a.g.bcval[1]; bc.v2 = a.g.bcval[2]; bc.v3 = a.g.bcval[3];
+  bc.s0 = f.sdx[0]; bc.s1 = f.sdx[1]; bc.s2 = f.sdx[2]; bc.s3 = f.sdx[3];
+  bc.xany = (strip == 0 && bc.kxlo <= SK_PHYS_NEUM) || (strip * GP_COLS + GP_COLS + 3 >= nx - 1 && bc.kxhi <= SK_PHYS_NEUM);
+  auto cellok = [&](int x) -> bool { return (x >= 0 && x < nx) || (x < 0 && x >= -3 && bc.kxlo == SK_GHOST) || (x >= nx && x <= nx + 2 && bc.kxhi == SK_GHOST); };
+  const bool ok0 = cellok(x0), ok1 = cellok(x0 + 1);
+  const int gpar = (a.g.glo0 + a.g.glo1) & 1;
+  auto rowupd = [&](int j) -> bool { return (j >= 0 && j < ny) || (j < 0 && j >= -3 && bc.kylo == SK_GHOST) || (j >= ny && j <= ny + 2 && bc.kyhi == SK_GHOST); };
+
+  double2* ring = gs_smem + (size_t)pair * PAIR_D2 + lane;         // [stage][arr][32]
+  double2* psi = gs_smem + (size_t)pair * PAIR_D2 + GP_STAGES * NARR * 32 + lane; // [2][32]
+  const int sfirst = r0 - 6, slast = r1 + 2;
+  const int barid = 1 + pair;
+  const double2 z2 = make_double2(0.0, 0.0);
+
+  if (role == 0) {
+    // ------------------------------ warp A: iteration 1 ------------------------------
+    const bool rc0 = ok0 && lane >= 1, rc1 = ok1 && lane <= 30;                              // RED_1
+    const bool bc0 = ok0 && lane >= 1 && lane <= 30, bc1 = ok1 && lane >= 1 && lane <= 30;   // BLACK_1
+    const double* g0 = f.phi_in + x0; const double* g1 = a.bY + x0;
+    const double* g2 = f.rhs + x0; const double* g3 = a.B + x0; const double* g4 = a.Pi + x0; const double* g5 = a.zb + x0;
+    const double* g6 = a.mask + x0; const double* g7 = a.bX + x0; const double* g8 = HAS_A ? a.aC + x0 : nullptr;
+    auto issue = [&](int q, int stage) {
+      if (q <= r1 + 1) {
+        const ptrdiff_t o2 = (ptrdiff_t)min(q + 2, ny + SG_YTOP - 1) * P, o1 = (ptrdiff_t)max(q + 1, -SG_YOFF) * P;
+        double2* s = ring + (size_t)stage * (NARR * 32);
+        cp_async16(s, g0 + o2); cp_async16(s + 32, g1 + o2);
+        cp_async16(s + 64, g2 + o1); cp_async16(s + 96, g3 + o1); cp_async16(s + 128, g4 + o1); cp_async16(s + 160, g5 + o1);
+        if (a.use_mask) cp_async16(s + 192, g6 + o1);
+        cp_async16(s + 224, g7 + o1);
+        if (HAS_A) cp_async16(s + 256, g8 + o1);
+      }
+      cp_async_commit();
+    };
+    double2 pm = z2, p0 = z2, p1 = z2, p2 = z2, by0 = z2, by1 = z2, by2 = z2;
+    GsRow c0, c1;
+    c0.rhs = c0.B = c0.Pi = c0.zb = c0.mk = c0.bx = c0.ac = z2;
+    c1 = c0;
+#pragma unroll
+    for (int d = 0; d < GP_D; d++) issue(sfirst + d, d);
+    int stage = 0;
+    for (int q = sfirst; q <= slast; q++) {
+      cp_async_wait<GP_D - 1>();
+      pm = p0; p0 = p1; p1 = p2; by0 = by1; by1 = by2; c0 = c1;
+      {
+        const double2* s = ring + (size_t)stage * (NARR * 32);
+        p2 = s[0]; by2 = s[32];
+        c1.rhs = s[64]; c1.B = s[96]; c1.Pi = s[128]; c1.zb = s[160]; c1.bx = s[224];
+        c1.mk = a.use_mask ? s[192] : make_double2(1.0, 1.0);
+        if (HAS_A) c1.ac = s[256];
+      }
+      {
+        int st = stage + GP_D; // slot of bundle q - (GP_LAG + 1): warp B read it one step ago (barrier in between)
+        if (st >= GP_STAGES) st -= GP_STAGES;
+        issue(q + GP_D, st);
+      }
+      stage = stage + 1 == GP_STAGES ? 0 : stage + 1;
+      if (q + 1 >= r0 - 3 && q + 1 <= r1 + 2 && rowupd(q + 1)) { // RED_1 on row q+1
+        const int j = q + 1;
+        if ((gpar + j) & 1) { double nv = gs_update<1, HAS_A>(a, bc, j, x0 + 1, c1, p1, p0, p2, by1, by2); if (rc1) p1.y = nv; }
+        else { double nv = gs_update<0, HAS_A>(a, bc, j, x0, c1, p1, p0, p2, by1, by2); if (rc0) p1.x = nv; }
+      }
+      if (q >= r0 - 2 && q <= r1 + 1 && rowupd(q)) { // BLACK_1 on row q
+        const int j = q;
+        if ((gpar + j) & 1) { double nv = gs_update<0, HAS_A>(a, bc, j, x0, c0, p0, pm, p1, by0, by1); if (bc0) p0.x = nv; }
+        else { double nv = gs_update<1, HAS_A>(a, bc, j, x0 + 1, c0, p0, pm, p1, by0, by1); if (bc1) p0.y = nv; }
+      }
+      psi[(q & 1) * 32] = p0; // row q after iteration 1 (or as loaded where it is not updated)
+      pair_barrier(barid);
+    }
+  } else {
+    // ------------------------------ warp B: iteration 2, three rows behind ------------------------------
+    const bool rc0 = ok0 && lane >= 2 && lane <= 30, rc1 = ok1 && lane >= 1 && lane <= 29;   // RED_2: columns 3..60
+    const bool st0 = lane >= 2 && lane <= 29 && x0 >= 0 && x0 < nx;                          // BLACK_2 + store: columns 4..59
+    const bool st1 = lane >= 2 && lane <= 29 && x0 + 1 >= 0 && x0 + 1 < nx;
+    double2 pm = z2, p0 = z2, p1 = z2, p2 = z2, by0 = z2, by1 = z2, by2 = z2;
+    GsRow c0, c1;
+    c0.rhs = c0.B = c0.Pi = c0.zb = c0.mk = c0.bx = c0.ac = z2;
+    c1 = c0;
+    int stage = GP_STAGES - GP_LAG; // slot of bundle sfirst - GP_LAG (not loaded yet: the first steps only rotate)
+    for (int sidx = sfirst; sidx <= slast; sidx++) {
+      const int q = sidx - GP_LAG; // this warp's own step: RED_2 on row q+1, BLACK_2 on row q
+      if (q + 2 >= sfirst) { // psi(q+2) = psi(sidx-1) was handed over before the last barrier
+        pm = p0; p0 = p1; p1 = p2; by0 = by1; by1 = by2; c0 = c1;
+        p2 = psi[((q + 2) & 1) * 32];
+        if (q >= sfirst) {
+          const double2* s = ring + (size_t)stage * (NARR * 32);
+          by2 = s[32];
+          c1.rhs = s[64]; c1.B = s[96]; c1.Pi = s[128]; c1.zb = s[160]; c1.bx = s[224];
+          c1.mk = a.use_mask ? s[192] : make_double2(1.0, 1.0);
+          if (HAS_A) c1.ac = s[256];
+        }
+        if (q + 1 >= r0 - 1 && q + 1 <= r1 && rowupd(q + 1)) { // RED_2 on row q+1
+          const int j = q + 1;
+          if ((gpar + j) & 1) { double nv = gs_update<1, HAS_A>(a, bc, j, x0 + 1, c1, p1, p0, p2, by1, by2); if (rc1) p1.y = nv; }
+          else { double nv = gs_update<0, HAS_A>(a, bc, j, x0, c1, p1, p0, p2, by1, by2); if (rc0) p1.x = nv; }
+        }
+        if (q >= r0 && q < r1) { // BLACK_2 on row q, then store
+          const int j = q;
+          if ((gpar + j) & 1) { double nv = gs_update<0, HAS_A>(a, bc, j, x0, c0, p0, pm, p1, by0, by1); if (st0) p0.x = nv; }
+          else { double nv = gs_update<1, HAS_A>(a, bc, j, x0 + 1, c0, p0, pm, p1, by0, by1); if (st1) p0.y = nv; }
+          double* o = f.phi_out + (ptrdiff_t)j * P + x0;
+          if (st0 && st1) *reinterpret_cast<double2*>(o) = p0;
+          else if (st0) o[0] = p0.x;
+          else if (st1) o[1] = p0.y;
+        }
+      }
+      stage = stage + 1 == GP_STAGES ? 0 : stage + 1;
+      pair_barrier(barid);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
 // applyOp / residual (+ max-norm) : VCNLCOMPUTEOP2D / VCNLCOMPUTERES2D (src/VCAMRNonLinearPoissonOpF.ChF:201-406)
 // MODE 0: out = L(phi);  1: out = rhs - L(phi);  2: as 1 plus max|out| accumulated into *norm_bits;  3: only the max-norm of
 // rhs - L(phi) (nothing stored: the solver's residual norm);  4: out += L(phi) (FAS coarse right-hand side, fuses the incr)
