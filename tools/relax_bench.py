@@ -32,7 +32,7 @@ def main():
     op0 = fac.AMRnewOp(0)
     op0.UpdateOperator(F["head"], None, 0, 0, False)
     res = []
-    variants = [(1, 0, 3), (3, 0, 2)] + [(4, r, 3) for r in (0, 16, 32, 48, 64, 96, 128)]
+    variants = [(1, 0, 3), (1, 32, 3), (1, 64, 3), (4, 0, 3)]
     for extra in os.environ.get("SG_VARIANTS", "").split(";"):
         if extra:
             variants.append(tuple(int(x) for x in extra.split(",")))
