@@ -7,7 +7,9 @@
 A "step" is one complete FAS V-cycle of the head solve (everything between two residual-norm evaluations:
 UpdateOperator, AverageOperator, 4+4 GSRB smooths per depth, 10/16 bottom smooths, restriction, FAS right-hand
 side, prolongation, residual + max-norm) on the synthetic AMR_multiMoulins base grid scaled to 8192 x 8192 cells
-per GPU (weak scaling: the domain grows in y with N; box-wise strip partition, 64^2 boxes).
+per GPU (weak scaling: the domain grows in y with N; box-wise strip partition, 64^2 boxes).  At N = 1 the line also
+carries "amr_3level": the same base grid with two refined levels around the 63 moulins (grids from the library's own
+tagging + Berger-Rigoutsos regrid), timed over composite FAS V-cycles.
 """
 import argparse
 import json

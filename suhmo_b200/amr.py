@@ -291,7 +291,9 @@ class VCAMRNonLinearPoissonOp:
     def createCoarser(self, fine, ghosted=True):
         h = C.c_void_p()
         check(lib().sg_op_createCoarser(self.h, C.byref(h), fine.h, int(ghosted)))
-        return LevelData(fine.layout.coarsen(2), fine.ncomp, fine.ng, fine.cent, _h=h)
+        lay = DisjointBoxLayout(fine.layout.ctx, fine.layout.boxes // 2, fine.layout.domain // 2, fine.layout.periodic,
+                                fine.layout.owner, _h=False)  # python-side description only: the C layout belongs to the field
+        return LevelData(lay, fine.ncomp, fine.ng, fine.cent, _h=h)
 
     def create(self, rhs):
         h = C.c_void_p()

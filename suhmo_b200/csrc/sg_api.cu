@@ -130,6 +130,7 @@ struct sg_layout {
 
 struct sg_field {
   sg_layout* lay;
+  bool owns_layout = false; // createCoarser: the coarsened layout lives and dies with the field
   int ncomp, ng, cent;
   double* base = nullptr;
   size_t comp_stride = 0;
@@ -647,6 +648,7 @@ extern "C" int sg_field_destroy(sg_field* f) {
     cudaStreamSynchronize(f->lay->ctx->stream);
     cudaFree(f->base);
   }
+  if (f->owns_layout) sg_layout_destroy(f->lay);
   delete f;
   return SG_OK;
 }
@@ -1507,7 +1509,10 @@ extern "C" int sg_op_createCoarser(sg_op* op, sg_field** coarse, const sg_field*
   REQUIRE(ok, "createCoarser: layout not coarsenable by 2 (CH_assert)");
   sg_layout* Lc;
   SGCALL(sg_layout_coarsen(fine->lay, 2, &Lc));
-  return sg_field_create(Lc, coarse, fine->ncomp, fine->ng, fine->cent); // note: layout is leaked to the field's lifetime
+  int r = sg_field_create(Lc, coarse, fine->ncomp, fine->ng, fine->cent);
+  if (r != SG_OK) { sg_layout_destroy(Lc); return r; }
+  (*coarse)->owns_layout = true;
+  return SG_OK;
 }
 extern "C" int sg_op_create(sg_op* op, sg_field** lhs, const sg_field* rhs) {
   REQUIRE(op && lhs && rhs, "sg_op_create: null");

@@ -73,6 +73,9 @@ struct SgNccl {
   int recv(double* p, size_t n, int peer, cudaStream_t s, std::string& err) {
     return check(g_nccl_api.Recv(p, n, ncclFloat64, peer, comm, s), "ncclRecv", err);
   }
+  int allreduce_max_u8(unsigned char* p, size_t n, cudaStream_t s, std::string& err) {
+    return check(g_nccl_api.AllReduce(p, p, n, ncclUint8, ncclMax, comm, s), "ncclAllReduce", err);
+  }
   int allreduce(double* p, size_t n, bool is_max, cudaStream_t s, std::string& err) {
     return check(g_nccl_api.AllReduce(p, p, n, ncclFloat64, is_max ? ncclMax : ncclSum, comm, s), "ncclAllReduce", err);
   }
