@@ -263,3 +263,65 @@ def test_against_golden_fixture_c1(gpu_ctx):
     git, ghist, stats = mg.solve([gpu.F["head"]], [gpu.F["rhs"]], fixed_cycles=5)
     assert np.array_equal(ghist, z["resnorm"])
     assert np.array_equal(gpu.F["head"].get_global(), z["head5"])
+
+
+@pytest.mark.parametrize("use_nl", [1, 0])
+@pytest.mark.parametrize("name,scale", [("C2", 2), ("C5", 1)])
+def test_helmholtz_alpha_and_linear_variants(gpu_ctx, name, scale, use_nl):
+    """alpha != 0 (the aCoef-reading kernel variants; what the implicit gap solve's operator needs: alpha = 1, NL = 0) and
+    solver.use_NL = false: relax in every mode, residual, restriction and fixed V-cycles stay bit-exact"""
+    cfg = syn.config(name, scale)
+    boxes = syn.domain_split(cfg.nx, cfg.ny, cfg.max_box_size, cfg.block_factor)
+    orc = OracleSide(cfg, boxes, prm_over=dict(use_NL=use_nl, bcoeff_otf=0))
+    orc.alpha = 0.75
+    rng = np.random.RandomState(7)
+    orc.F["a"].set_global(1e-9 * (1.0 + rng.rand(cfg.ny, cfg.nx)), (0, 0))
+    orc.init_bcoef()
+    gpu = GpuSide(gpu_ctx, orc)
+    oop, gop = orc.op(), gpu.factory.AMRnewOp(0)
+    for mode in (0, 1, 3, 4):
+        gpu_ctx.set_relax_mode(mode)
+        oop.relax(orc.F["head"], orc.F["rhs"], 2)
+        gop.relax(gpu.F["head"], gpu.F["rhs"], 2)
+        assert_same(gpu.F["head"], orc.F["head"], f"relax alpha!=0 mode {mode}")
+    gpu_ctx.set_relax_mode(1)
+    ores, gres = ob.Field(orc.layout, 1, 0), gpu.new_like("rhs")
+    oop.residual(ores, orc.F["head"], orc.F["rhs"])
+    gop.residual(gres, gpu.F["head"], gpu.F["rhs"])
+    assert_same(gres, ores, "residual alpha!=0")
+    glam = gpu.new_like("rhs")
+    gop.lambda_(glam)
+    assert_same(glam, oop.lambda_field(), "lambda alpha!=0")
+    osp = ob.make_solver_params(bottom=10, fixed_cycles=3)
+    it, ohist = orc.solver().solve(orc.F["head"], orc.F["rhs"], osp)
+    mg = gpu.amr.AMRFASMultiGrid().define(gpu.factory, 1)
+    mg.setSolverParameters(4, 4, 10, 1, 100, 1e-10, 1e-4, 1e-7)
+    git, ghist, stats = mg.solve([gpu.F["head"]], [gpu.F["rhs"]], fixed_cycles=3)
+    assert np.array_equal(ghist, ohist), (ghist, ohist)
+    assert_same(gpu.F["head"], orc.F["head"], "V-cycles alpha!=0")
+
+
+def test_error_conventions(gpu_ctx):
+    """where the reference aborts or asserts, the C ABI returns a status: SG_ERR_ABORT for the MayDay::Abort sites,
+    SG_ERR_INVALID for CH_assert-style argument errors -- never a silent fallback"""
+    from suhmo_b200.capi import ERR_ABORT, ERR_INVALID, SuhmoGpuError
+    cfg, orc, gpu = make(gpu_ctx, "C3", 1, None)
+    cfg2, orc2, gpu2 = make(gpu_ctx, "C5", 1, None)
+    gop = gpu.factory.AMRnewOp(0)
+    res = gpu.new_like("rhs")
+    for call in (lambda: gop.restrictResidual(gop.createCoarser(gpu.F["rhs"]), gpu.F["head"], None, gpu.F["rhs"], True),
+                 lambda: gop.UpdateOperator(gpu.F["head"], None, 0, 0, True),
+                 lambda: gop.AMRResidualNF(res, gpu.F["head"], None, gpu.F["rhs"], True)):
+        with pytest.raises(SuhmoGpuError) as e:
+            call()
+        assert e.value.code == ERR_ABORT
+    with pytest.raises(SuhmoGpuError) as e:   # a field of another level handed to the operator
+        gop.relax(gpu2.F["head"], gpu.F["rhs"], 1)
+    assert e.value.code == ERR_INVALID
+    with pytest.raises(SuhmoGpuError) as e:   # no coarser level, but a coarse phi is passed
+        gop.relaxNF(gpu.F["head"], gpu.F["head"], gpu.F["rhs"], 1)
+    assert e.value.code == ERR_INVALID
+    assert gpu.factory.refToFiner(0) == 2
+    with pytest.raises(SuhmoGpuError) as e:
+        gpu.factory.refToFiner(3)              # "Domain not found in AMR hierarchy"
+    assert e.value.code == ERR_ABORT
