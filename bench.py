@@ -32,8 +32,8 @@ UNIT = "cell-updates/s"
 BYTES_PER_UPDATE_SMOOTHER = 72.0   # phi, rhs, bX, bY, B, Pi, zb, mask read + phi written
 BYTES_PER_UPDATE_VCYCLE = 97.0     # whole V-cycle amortised
 # dram__bytes_read.sum + dram__bytes_write.sum of one finest-level smoother launch, from the `ncu --set full` capture of this
-# command committed as profiles/r01_k_gsrb_stream_ncu_full_raw.csv (4.697 GB read + 0.531 GB written; algorithmic 4.832 GB)
-NCU_TRAFFIC = {(8192, 1): 4.696833e9 + 0.531284224e9}
+# command committed as profiles/r01_k_gsrb_stream_ncu_full_raw.csv (4.094 GB read + 0.533 GB written with the ice mask skipped; requested 64 B x 67.1 M = 4.295 GB, algorithmic 72 B -> 4.832 GB)
+NCU_TRAFFIC = {(8192, 1): 4.094115e9 + 0.533116160e9}
 
 
 def bench_config(size, nranks):
