@@ -133,6 +133,20 @@ def lib():
     sig("orc_amr_solver_vcycle", None, vp, pvp, pvp, ci, C.POINTER(SolverParams))
     sig("orc_amr_solver_resnorm", cd, vp, pvp, pvp, ci)
     sig("orc_amr_solver_solve", ci, vp, pvp, pvp, ci, C.POINTER(SolverParams), dp)
+    sig("orc_lin_solver_create", vp, vp, cd, cd, cd, vp, vp, vp)
+    sig("orc_lin_solver_free", None, vp)
+    sig("orc_lin_solver_depth", ci, vp)
+    sig("orc_lin_solver_bottom_iters", ci, vp)
+    sig("orc_linop_lambda", vp, vp, ci)
+    sig("orc_linop_relax", None, vp, ci, vp, vp, ci)
+    sig("orc_linop_residual", None, vp, ci, vp, vp, vp)
+    sig("orc_linop_apply", None, vp, ci, vp, vp)
+    sig("orc_linop_restrict_residual", None, vp, ci, vp, vp, vp)
+    sig("orc_linop_prolong_increment", None, vp, ci, vp, vp)
+    sig("orc_linop_precond", None, vp, ci, vp, vp)
+    sig("orc_lin_solver_bottom_solve", ci, vp, vp, vp)
+    sig("orc_lin_solver_vcycle", None, vp, vp, vp, C.POINTER(SolverParams))
+    sig("orc_lin_solver_solve", ci, vp, vp, vp, C.POINTER(SolverParams), dp)
     sig("orc_amr_solver_cell_updates", cd, vp, C.POINTER(SolverParams), ci)
     pq = C.POINTER(PicardParams)
     sig("orc_compute_qw", None, C.POINTER(Params), vp, vp, vp, vp)
@@ -414,3 +428,60 @@ def tag_cells_level(field, vmin, vmax, tags_grow=0, tags_grow_dir=(0, 0), tags=N
     gd, gp = _ia(tags_grow_dir)
     lib().orc_tag_cells_level(field.h, float(vmin), float(vmax), int(tags_grow), gp, out.ctypes.data_as(C.c_void_p), int(acc))
     return out
+
+
+class LinSolver:
+    """SolveForGap_nl's stock VCAMRPoissonOp2 + linear AMRMultiGrid + RelaxSolver on one AMR level."""
+
+    def __init__(self, layout, dx, alpha, beta, aCoef, bX, bY):
+        self.layout = layout
+        self.keep = (aCoef, bX, bY)
+        self.h = lib().orc_lin_solver_create(layout.h, float(dx), alpha, beta, aCoef.h, bX.h, bY.h)
+
+    @property
+    def depth(self):
+        return lib().orc_lin_solver_depth(self.h)
+
+    @property
+    def bottom_iters(self):
+        return lib().orc_lin_solver_bottom_iters(self.h)
+
+    def layout_at(self, depth):
+        return self.layout if depth == 0 else self.layout.coarsen(1 << depth)
+
+    def lambda_field(self, depth=0):
+        return Field(self.layout_at(depth), 1, 0, CELL, _h=lib().orc_linop_lambda(self.h, depth))
+
+    def relax(self, phi, rhs, iterations, depth=0):
+        lib().orc_linop_relax(self.h, depth, phi.h, rhs.h, iterations)
+
+    def residual(self, res, phi, rhs, depth=0):
+        lib().orc_linop_residual(self.h, depth, res.h, phi.h, rhs.h)
+
+    def applyOp(self, lhs, phi, depth=0):
+        lib().orc_linop_apply(self.h, depth, lhs.h, phi.h)
+
+    def restrictResidual(self, resC, phi, rhs, depth=0):
+        lib().orc_linop_restrict_residual(self.h, depth, resC.h, phi.h, rhs.h)
+
+    def prolongIncrement(self, phi, corrC, depth=0):
+        lib().orc_linop_prolong_increment(self.h, depth, phi.h, corrC.h)
+
+    def preCond(self, phi, rhs, depth=0):
+        lib().orc_linop_precond(self.h, depth, phi.h, rhs.h)
+
+    def bottom_solve(self, phi, rhs):
+        return lib().orc_lin_solver_bottom_solve(self.h, phi.h, rhs.h)
+
+    def vcycle(self, corr, res, sp):
+        lib().orc_lin_solver_vcycle(self.h, corr.h, res.h, C.byref(sp))
+
+    def solve(self, phi, rhs, sp):
+        n = max(sp.max_iter, sp.fixed_cycles) + 2
+        hist = np.zeros(n)
+        it = lib().orc_lin_solver_solve(self.h, phi.h, rhs.h, C.byref(sp), hist.ctypes.data_as(C.POINTER(C.c_double)))
+        return it, hist[:it + 1]
+
+    def free(self):
+        lib().orc_lin_solver_free(self.h)
+        self.h = None

@@ -1765,3 +1765,317 @@ void orc_tag_cells_level(const orc_field* phi, double vmin, double vmax, int tag
   for (size_t k = 0; k < (size_t)nx * ny; k++) tags[k] = accumulate ? (tags[k] | g[k]) : g[k];
   free(m); free(g);
 }
+
+/* =========================================================================================== */
+/* Implicit gap-height solve: AmrHydro::SolveForGap_nl (src/AmrHydro.cpp:594-662) */
+/*                                                                                             */
+/* The reference builds a STOCK Chombo VCAMRPoissonOp2Factory (alpha = 1, aCoef = 1, beta =      */
+/* dt*DiffFactor, bCoef = Dcoef, BC = FixedNeumBCFill src/AmrHydro.cpp:404-436) and a linear,     */
+/* correction-form AMRMultiGrid with a RelaxSolver bottom (setSolverParameters(2,2,4,1,100,1e-7,  */
+/* 1e-6,1e-7), m_imin = 10 while step < 50, m_iterMin = 2).  None of those classes is in the      */
+/* SUHMO tree: everything below restates public Chombo 3.2 (VCAMRPoissonOp2{.cpp,F.ChF},           */
+/* MultiGrid.H, AMRMultiGrid.H, RelaxSolver.H) from recollection -- PARITY UNPINNED, each piece    */
+/* in its own function.  Single AMR level only (the inputs with solver.use_ImplDiff = true, C1 C2  */
+/* C4 C5, are single-level).                                                                     */
+/* =========================================================================================== */
+typedef struct orc_linop {
+  const orc_layout* lay;
+  double dx, alpha, beta;
+  orc_field *aCoef, *bX, *bY; /* borrowed at depth 0, owned below */
+  orc_field* lambda;          /* 1/diagonal (VCAMRPoissonOp2::resetLambda ends with lambdaFab.invert(1.0)) */
+} orc_linop;
+
+struct orc_lin_solver {
+  int ndepth;
+  orc_layout* lay[ORC_MAXDEPTH];
+  orc_linop op[ORC_MAXDEPTH];
+  orc_field *corr[ORC_MAXDEPTH], *res[ORC_MAXDEPTH]; /* MultiGrid::m_correction / m_residual, depth >= 1 */
+  orc_field *uberCorr, *uberRes;                     /* AMRMultiGrid::solveNoInitResid temporaries */
+  orc_field *br, *be;                                /* RelaxSolver r, e on the bottom level */
+  int bottom_iters;                                  /* RelaxSolver iterations of the last bottom solve */
+};
+
+/* FixedNeumBCFill (src/AmrHydro.cpp:404-436): ghost strip = first interior strip, whatever `homogeneous` says */
+static void fixed_neum_bc_fill(orc_field* f) {
+  const orc_layout* L = f->lay;
+#pragma omp parallel for schedule(static)
+  for (int b = 0; b < L->nbox; b++) {
+    if (box_contains(&L->domain, &f->ab[b])) continue;
+    obox valid = L->box[b];
+    for (int dir = 0; dir < 2; dir++) {
+      if (L->periodic[dir]) continue;
+      for (int side = 0; side < 2; side++) {
+        obox gb = box_adj(valid, dir, side);
+        if (box_contains(&L->domain, &gb) || !box_contains(&f->ab[b], &gb)) continue;
+        int isign = side ? 1 : -1;
+        for (int c = 0; c < f->ncomp; c++)
+          for (int j = gb.lo[1]; j <= gb.hi[1]; j++)
+            for (int i = gb.lo[0]; i <= gb.hi[0]; i++)
+              AT(f, b, i, j, c) = AT(f, b, i - (dir == 0 ? isign : 0), j - (dir == 1 ? isign : 0), c);
+      }
+    }
+  }
+}
+
+/* resetLambda: lambda = alpha*a; SUMFACES per direction (lhs += scale*beta*(b(i+e)+b(i)), scale = 1/dx^2); invert */
+static void linop_reset_lambda(orc_linop* op) {
+  const orc_layout* L = op->lay;
+  double scale = 1.0 / (op->dx * op->dx);
+#pragma omp parallel for schedule(static)
+  for (int b = 0; b < L->nbox; b++) {
+    obox v = L->box[b];
+    for (int j = v.lo[1]; j <= v.hi[1]; j++)
+      for (int i = v.lo[0]; i <= v.hi[0]; i++) {
+        double lam = AT(op->aCoef, b, i, j, 0) * op->alpha;
+        double sumVal = AT(op->bX, b, i + 1, j, 0) + AT(op->bX, b, i, j, 0);
+        lam = lam + scale * op->beta * sumVal;
+        sumVal = AT(op->bY, b, i, j + 1, 0) + AT(op->bY, b, i, j, 0);
+        lam = lam + scale * op->beta * sumVal;
+        AT(op->lambda, b, i, j, 0) = 1.0 / lam;
+      }
+  }
+}
+
+/* the stencil of VCCOMPUTEOP2D / VCCOMPUTERES2D / GSRBHELMHOLTZVC2D / RESTRICTRESVC2D (stock VCAMRPoissonOp2F.ChF):
+   alpha*a*phi - beta*( bx(i+1)*(phi(i+1)-phi) - bx(i)*(phi-phi(i-1)) + by(j+1)*(phi(j+1)-phi) - by(j)*(phi-phi(j-1)) )*dxinv */
+#define LIN_LOFPHI(op, phi, b, i, j, dxinv)                                                          \
+  ((op)->alpha * AT((op)->aCoef, b, i, j, 0) * AT(phi, b, i, j, 0) -                                 \
+   (op)->beta * (AT((op)->bX, b, (i) + 1, j, 0) * (AT(phi, b, (i) + 1, j, 0) - AT(phi, b, i, j, 0)) - \
+                 AT((op)->bX, b, i, j, 0) * (AT(phi, b, i, j, 0) - AT(phi, b, (i)-1, j, 0)) +         \
+                 AT((op)->bY, b, i, (j) + 1, 0) * (AT(phi, b, i, (j) + 1, 0) - AT(phi, b, i, j, 0)) - \
+                 AT((op)->bY, b, i, j, 0) * (AT(phi, b, i, j, 0) - AT(phi, b, i, (j)-1, 0))) * (dxinv))
+
+/* VCAMRPoissonOp2::levelGSRB: per colour exchange, homogeneous BC, phi -= lambda*(L(phi) - rhs) on that colour */
+static void linop_level_gsrb(orc_linop* op, orc_field* phi, const orc_field* rhs) {
+  const orc_layout* L = op->lay;
+  double dxinv = 1.0 / (op->dx * op->dx);
+  for (int whichPass = 0; whichPass <= 1; whichPass++) {
+    orc_exchange_faces(phi);
+    fixed_neum_bc_fill(phi);
+#pragma omp parallel for schedule(static)
+    for (int b = 0; b < L->nbox; b++) {
+      obox v = L->box[b];
+      for (int j = v.lo[1]; j <= v.hi[1]; j++) {
+        int imin_ = v.lo[0];
+        int indtot = imin_ + j;
+        imin_ = imin_ + abs((indtot + whichPass) % 2);
+        for (int i = imin_; i <= v.hi[0]; i += 2) {
+          double lofphi = LIN_LOFPHI(op, phi, b, i, j, dxinv);
+          AT(phi, b, i, j, 0) = AT(phi, b, i, j, 0) - AT(op->lambda, b, i, j, 0) * (lofphi - AT(rhs, b, i, j, 0));
+        }
+      }
+    }
+  }
+}
+void orc_linop_relax(orc_lin_solver* s, int depth, orc_field* phi, const orc_field* rhs, int iterations) {
+  for (int it = 0; it < iterations; it++) linop_level_gsrb(&s->op[depth], phi, rhs);
+}
+/* residualI: BC, exchange, res = rhs - L(phi) */
+void orc_linop_residual(orc_lin_solver* s, int depth, orc_field* res, orc_field* phi, const orc_field* rhs) {
+  orc_linop* op = &s->op[depth];
+  const orc_layout* L = op->lay;
+  double dxinv = 1.0 / (op->dx * op->dx);
+  fixed_neum_bc_fill(phi);
+  orc_exchange_faces(phi);
+#pragma omp parallel for schedule(static)
+  for (int b = 0; b < L->nbox; b++) {
+    obox v = L->box[b];
+    for (int j = v.lo[1]; j <= v.hi[1]; j++)
+      for (int i = v.lo[0]; i <= v.hi[0]; i++) AT(res, b, i, j, 0) = AT(rhs, b, i, j, 0) - (LIN_LOFPHI(op, phi, b, i, j, dxinv));
+  }
+}
+/* applyOpI */
+void orc_linop_apply(orc_lin_solver* s, int depth, orc_field* lhs, orc_field* phi) {
+  orc_linop* op = &s->op[depth];
+  const orc_layout* L = op->lay;
+  double dxinv = 1.0 / (op->dx * op->dx);
+  fixed_neum_bc_fill(phi);
+  orc_exchange_faces(phi);
+#pragma omp parallel for schedule(static)
+  for (int b = 0; b < L->nbox; b++) {
+    obox v = L->box[b];
+    for (int j = v.lo[1]; j <= v.hi[1]; j++)
+      for (int i = v.lo[0]; i <= v.hi[0]; i++) AT(lhs, b, i, j, 0) = LIN_LOFPHI(op, phi, b, i, j, dxinv);
+  }
+}
+/* restrictResidual + RESTRICTRESVC2D: resCoarse = average over the 2x2 children of (rhs - L(phi)), accumulated in Fortran order */
+void orc_linop_restrict_residual(orc_lin_solver* s, int depth, orc_field* resCoarse, orc_field* phiFine, const orc_field* rhsFine) {
+  orc_linop* op = &s->op[depth];
+  const orc_layout* L = op->lay;
+  double dxinv = 1.0 / (op->dx * op->dx);
+  fixed_neum_bc_fill(phiFine);
+  orc_exchange_faces(phiFine);
+#pragma omp parallel for schedule(static)
+  for (int b = 0; b < L->nbox; b++) {
+    obox v = L->box[b];
+    double denom = 2 * 2;
+    size_t n = (size_t)NXOF(resCoarse->ab[b]) * NYOF(resCoarse->ab[b]);
+    for (size_t k = 0; k < n; k++) resCoarse->d[b][k] = 0.0;
+    for (int j = v.lo[1]; j <= v.hi[1]; j++)
+      for (int i = v.lo[0]; i <= v.hi[0]; i++) {
+        int ii = fdiv(i, 2), jj = fdiv(j, 2);
+        double lofphi = LIN_LOFPHI(op, phiFine, b, i, j, dxinv);
+        AT(resCoarse, b, ii, jj, 0) = AT(resCoarse, b, ii, jj, 0) + (AT(rhsFine, b, i, j, 0) - lofphi) / denom;
+      }
+  }
+}
+/* AMRPoissonOp::prolongIncrement + PROLONG: phi(fine) += coarse(parent) */
+void orc_linop_prolong_increment(orc_lin_solver* s, int depth, orc_field* phiFine, const orc_field* corrCoarse) {
+  const orc_layout* L = s->op[depth].lay;
+#pragma omp parallel for schedule(static)
+  for (int b = 0; b < L->nbox; b++) {
+    obox v = L->box[b];
+    for (int j = v.lo[1]; j <= v.hi[1]; j++)
+      for (int i = v.lo[0]; i <= v.hi[0]; i++)
+        AT(phiFine, b, i, j, 0) = AT(phiFine, b, i, j, 0) + AT(corrCoarse, b, fdiv(i, 2), fdiv(j, 2), 0);
+  }
+}
+/* VCAMRPoissonOp2::preCond: phi = lambda*rhs on valid cells, then relax(phi, rhs, 2) */
+void orc_linop_precond(orc_lin_solver* s, int depth, orc_field* phi, const orc_field* rhs) {
+  orc_linop* op = &s->op[depth];
+  const orc_layout* L = op->lay;
+#pragma omp parallel for schedule(static)
+  for (int b = 0; b < L->nbox; b++) {
+    obox v = L->box[b];
+    for (int j = v.lo[1]; j <= v.hi[1]; j++)
+      for (int i = v.lo[0]; i <= v.hi[0]; i++) AT(phi, b, i, j, 0) = AT(rhs, b, i, j, 0) * AT(op->lambda, b, i, j, 0);
+  }
+  orc_linop_relax(s, depth, phi, rhs, 2);
+}
+orc_field* orc_linop_lambda(orc_lin_solver* s, int depth) { return s->op[depth].lambda; }
+
+/* norm(LevelData, p = 2): per-box sums of squares (Fortran order), added in layout order, then sqrt */
+static double lin_norm2(const orc_field* f) {
+  double total = 0.0;
+  for (int b = 0; b < f->lay->nbox; b++) {
+    double sb = 0.0;
+    FOR_VALID(f, b, i, j, c) sb += AT(f, b, i, j, c) * AT(f, b, i, j, c);
+    total += sb;
+  }
+  return sqrt(total);
+}
+
+/* VCAMRPoissonOp2Factory::define + MGnewOp at depth 0,1,.. until the layout stops being coarsenable by 2^depth * s_maxCoarse
+   (= 2); coefficients are arithmetic averages of the depth-0 data by 2^depth (m_coefficient_average_type = arithmetic) */
+orc_lin_solver* orc_lin_solver_create(const orc_layout* lay, double dx, double alpha, double beta, orc_field* aCoef, orc_field* bX,
+                                      orc_field* bY) {
+  orc_lin_solver* s = (orc_lin_solver*)calloc(1, sizeof(orc_lin_solver));
+  s->lay[0] = (orc_layout*)lay;
+  s->op[0] = (orc_linop){lay, dx, alpha, beta, aCoef, bX, bY, orc_field_create(lay, 1, 0, ORC_CELL)};
+  linop_reset_lambda(&s->op[0]);
+  s->ndepth = 1;
+  const int s_maxCoarse = 2;
+  for (int depth = 1; depth < ORC_MAXDEPTH; depth++) {
+    int coarsening = 1 << depth;
+    if (!orc_layout_coarsenable(lay, coarsening * s_maxCoarse)) break;
+    orc_layout* Lc = orc_layout_coarsen(lay, coarsening);
+    s->lay[depth] = Lc;
+    orc_field* a = orc_field_create(Lc, 1, aCoef->ng, ORC_CELL);
+    orc_field* bx = orc_field_create(Lc, 1, bX->ng, ORC_XFACE);
+    orc_field* by = orc_field_create(Lc, 1, bY->ng, ORC_YFACE);
+    orc_coarse_average(aCoef, a, coarsening);
+    orc_coarse_average_face(bX, bx, coarsening);
+    orc_coarse_average_face(bY, by, coarsening);
+    s->op[depth] = (orc_linop){Lc, dx * coarsening, alpha, beta, a, bx, by, orc_field_create(Lc, 1, 0, ORC_CELL)};
+    linop_reset_lambda(&s->op[depth]);
+    s->corr[depth] = orc_field_create(Lc, 1, 1, ORC_CELL);
+    s->res[depth] = orc_field_create(Lc, 1, 0, ORC_CELL);
+    s->ndepth = depth + 1;
+  }
+  s->uberCorr = orc_field_create(lay, 1, 1, ORC_CELL);
+  s->uberRes = orc_field_create(lay, 1, 0, ORC_CELL);
+  s->br = orc_field_create(s->lay[s->ndepth - 1], 1, 0, ORC_CELL);
+  s->be = orc_field_create(s->lay[s->ndepth - 1], 1, 1, ORC_CELL);
+  return s;
+}
+void orc_lin_solver_free(orc_lin_solver* s) {
+  if (!s) return;
+  orc_field_free(s->op[0].lambda);
+  for (int d = 1; d < s->ndepth; d++) {
+    orc_field_free(s->op[d].aCoef); orc_field_free(s->op[d].bX); orc_field_free(s->op[d].bY); orc_field_free(s->op[d].lambda);
+    orc_field_free(s->corr[d]); orc_field_free(s->res[d]);
+  }
+  orc_field_free(s->uberCorr); orc_field_free(s->uberRes); orc_field_free(s->br); orc_field_free(s->be);
+  for (int d = 1; d < s->ndepth; d++) orc_layout_free(s->lay[d]);
+  free(s);
+}
+int orc_lin_solver_depth(const orc_lin_solver* s) { return s->ndepth; }
+int orc_lin_solver_bottom_iters(const orc_lin_solver* s) { return s->bottom_iters; }
+
+/* RelaxSolver::solve (m_imax 40, m_eps 1e-6, m_normType 2, homogeneous): r = rhs - L(phi); until ||r||_2 < eps*||r0||_2:
+   e = 0; preCond(e, r); phi += e; r = rhs - L(phi) */
+int orc_lin_solver_bottom_solve(orc_lin_solver* s, orc_field* phi, const orc_field* rhs) {
+  int d = s->ndepth - 1;
+  const int imax = 40;
+  const double eps = 1.0e-6;
+  orc_linop_residual(s, d, s->br, phi, rhs);
+  double norm = lin_norm2(s->br);
+  int iter = 0;
+  if (norm > 0.) {
+    double initialNorm = norm;
+    while (iter < imax) {
+      orc_set_to_zero(s->be);
+      orc_linop_precond(s, d, s->be, s->br);
+      orc_incr(phi, s->be, 1.0);
+      orc_linop_residual(s, d, s->br, phi, rhs);
+      norm = lin_norm2(s->br);
+      iter++;
+      if (norm < eps * initialNorm) break;
+    }
+  }
+  s->bottom_iters = iter;
+  return iter;
+}
+
+/* MultiGrid::cycle, correction form.  [recollection] the bottom branch is relax(m_bottom) followed by the bottom solver */
+static void lin_cycle(orc_lin_solver* s, int depth, orc_field* e, const orc_field* res, const orc_solver_params* sp) {
+  if (depth == s->ndepth - 1) {
+    orc_linop_relax(s, depth, e, res, sp->bottom);
+    orc_lin_solver_bottom_solve(s, e, res);
+    return;
+  }
+  int dc = depth + 1;
+  orc_linop_relax(s, depth, e, res, sp->pre);
+  orc_linop_restrict_residual(s, depth, s->res[dc], e, res);
+  orc_set_to_zero(s->corr[dc]);
+  lin_cycle(s, dc, s->corr[dc], s->res[dc], sp);
+  orc_linop_prolong_increment(s, depth, e, s->corr[dc]);
+  orc_linop_relax(s, depth, e, res, sp->post);
+}
+/* AMRMultiGrid::AMRVCycle with l_max == l_base: m_mg[0]->oneCycle(correction, residual), homogeneous */
+void orc_lin_solver_vcycle(orc_lin_solver* s, orc_field* corr, const orc_field* res, const orc_solver_params* sp) {
+  lin_cycle(s, 0, corr, res, sp);
+}
+static double lin_amr_residual(orc_lin_solver* s, orc_field* phi, const orc_field* rhs) {
+  orc_linop_residual(s, 0, s->uberRes, phi, rhs);
+  return orc_norm(s->uberRes, 0);
+}
+/* AMRMultiGrid::solveNoInitResid: correction = 0; loop { V-cycle on the residual; phi += correction; correction = 0;
+   residual = rhs - L(phi) } with the stock stop logic */
+int orc_lin_solver_solve(orc_lin_solver* s, orc_field* phi, const orc_field* rhs, const orc_solver_params* sp, double* resnorm) {
+  orc_set_to_zero(s->uberCorr);
+  double initial_rnorm = lin_amr_residual(s, phi, rhs);
+  double rnorm = initial_rnorm, norm_last = 2 * initial_rnorm;
+  int iter = 0;
+  if (resnorm) resnorm[0] = initial_rnorm;
+  int goNorm = rnorm > sp->norm_thresh;
+  int goRedu = rnorm > sp->eps * initial_rnorm;
+  int goIter = iter < sp->max_iter;
+  int goHang = iter < sp->imin || rnorm < (1 - sp->hang) * norm_last;
+  int goMin = iter < sp->iter_min;
+  while (sp->fixed_cycles > 0 ? iter < sp->fixed_cycles : (goMin || (goIter && goRedu && goHang && goNorm))) {
+    norm_last = rnorm;
+    orc_lin_solver_vcycle(s, s->uberCorr, s->uberRes, sp);
+    orc_incr(phi, s->uberCorr, 1.0);
+    orc_set_to_zero(s->uberCorr);
+    rnorm = lin_amr_residual(s, phi, rhs);
+    iter++;
+    if (resnorm) resnorm[iter] = rnorm;
+    goNorm = rnorm > sp->norm_thresh;
+    goRedu = rnorm > sp->eps * initial_rnorm;
+    goIter = iter < sp->max_iter;
+    goHang = iter < sp->imin || rnorm < (1 - sp->hang) * norm_last;
+    goMin = iter < sp->iter_min;
+  }
+  return iter;
+}

@@ -194,6 +194,25 @@ void orc_gap_euler(orc_field* newB, const orc_field* oldB, const orc_field* RHS,
 void orc_tag_cells_level(const orc_field* phi, double vmin, double vmax, int tags_grow, const int tags_grow_dir[2], unsigned char* tags,
                          int accumulate);
 
+/* ---- implicit gap-height solve: stock VCAMRPoissonOp2 + linear AMRMultiGrid + RelaxSolver, one AMR level;
+   BC = FixedNeumBCFill (src/AmrHydro.cpp:404-436).  Restated from recollection of public Chombo 3.2: parity unpinned. ---- */
+typedef struct orc_lin_solver orc_lin_solver;
+orc_lin_solver* orc_lin_solver_create(const orc_layout* lay, double dx, double alpha, double beta, orc_field* aCoef, orc_field* bX,
+                                      orc_field* bY);
+void orc_lin_solver_free(orc_lin_solver* s);
+int orc_lin_solver_depth(const orc_lin_solver* s);
+int orc_lin_solver_bottom_iters(const orc_lin_solver* s);
+orc_field* orc_linop_lambda(orc_lin_solver* s, int depth);
+void orc_linop_relax(orc_lin_solver* s, int depth, orc_field* phi, const orc_field* rhs, int iterations);
+void orc_linop_residual(orc_lin_solver* s, int depth, orc_field* res, orc_field* phi, const orc_field* rhs);
+void orc_linop_apply(orc_lin_solver* s, int depth, orc_field* lhs, orc_field* phi);
+void orc_linop_restrict_residual(orc_lin_solver* s, int depth, orc_field* resCoarse, orc_field* phiFine, const orc_field* rhsFine);
+void orc_linop_prolong_increment(orc_lin_solver* s, int depth, orc_field* phiFine, const orc_field* corrCoarse);
+void orc_linop_precond(orc_lin_solver* s, int depth, orc_field* phi, const orc_field* rhs);
+int orc_lin_solver_bottom_solve(orc_lin_solver* s, orc_field* phi, const orc_field* rhs);
+void orc_lin_solver_vcycle(orc_lin_solver* s, orc_field* corr, const orc_field* res, const orc_solver_params* sp);
+int orc_lin_solver_solve(orc_lin_solver* s, orc_field* phi, const orc_field* rhs, const orc_solver_params* sp, double* resnorm);
+
 void orc_set_threads(int n);
 
 #ifdef __cplusplus

@@ -1,0 +1,121 @@
+"""CPU: the oracle's restatement of the implicit gap-height solve (stock VCAMRPoissonOp2 + linear AMRMultiGrid + RelaxSolver,
+src/AmrHydro.cpp:594-662) against an independent numpy restatement of the kernels and a sparse direct solve of the system."""
+import numpy as np
+import pytest
+import scipy.sparse as sp
+import scipy.sparse.linalg as spl
+
+from oracle import binding as ob
+from suhmo_b200 import synthetic as syn
+from tests import gapsolve as gs
+
+
+def make(name, scale, **kw):
+    cfg = syn.config(name, scale)
+    boxes = syn.domain_split(cfg.nx, cfg.ny, cfg.max_box_size, cfg.block_factor)
+    return cfg, gs.OracleGap(cfg, boxes, **kw)
+
+
+@pytest.mark.parametrize("name,scale", [("C1", 2), ("C2", 1), ("C4", 1)])
+def test_kernels_match_numpy(name, scale):
+    cfg, o = make(name, scale)
+    g, S = o.g, o.solver
+    assert np.array_equal(S.lambda_field().get_global(), gs.np_lambda(g, o.dx, o.alpha, o.beta))
+    p = g["b"].copy()
+    for it in range(2):
+        S.relax(o.F["b"], o.F["rhs"], 1)
+        p = gs.np_gsrb(p, g["rhs"], g, cfg, o.dx, o.alpha, o.beta)
+        assert np.array_equal(o.F["b"].get_global(), p[1:-1, 1:-1]), it
+    res = ob.Field(o.layout, 1, 0)
+    S.residual(res, o.F["b"], o.F["rhs"])
+    pr = gs.np_ghosts(p, cfg)
+    want = g["rhs"] - gs.np_lofphi(pr, g, o.dx, o.alpha, o.beta)
+    assert np.array_equal(res.get_global(), want)
+    lhs = ob.Field(o.layout, 1, 0)
+    S.applyOp(lhs, o.F["b"])
+    assert np.array_equal(lhs.get_global(), gs.np_lofphi(pr, g, o.dx, o.alpha, o.beta))
+    if S.depth > 1:
+        Lc = o.layout.coarsen(2)
+        rc = ob.Field(Lc, 1, 0)
+        S.restrictResidual(rc, o.F["b"], o.F["rhs"])
+        s = 0.0 + want[0::2, 0::2] / 4.0
+        s = s + want[0::2, 1::2] / 4.0
+        s = s + want[1::2, 0::2] / 4.0
+        s = s + want[1::2, 1::2] / 4.0
+        assert np.array_equal(rc.get_global(), s)
+        before = o.F["b"].get_global().copy()
+        S.prolongIncrement(o.F["b"], rc)
+        assert np.array_equal(o.F["b"].get_global(), before + np.repeat(np.repeat(s, 2, axis=0), 2, axis=1))
+
+
+def assemble(g, cfg, dx, alpha, beta):
+    ny, nx = g["a"].shape
+    idx = np.arange(nx * ny).reshape(ny, nx)
+    A = sp.lil_matrix((nx * ny, nx * ny))
+    s = beta / (dx * dx)
+    for j in range(ny):
+        for i in range(nx):
+            k = idx[j, i]
+            A[k, k] += alpha * g["a"][j, i]
+            for (dj, di, b) in ((0, 1, g["bX"][j, i + 1]), (0, -1, g["bX"][j, i]), (1, 0, g["bY"][j + 1, i]), (-1, 0, g["bY"][j, i])):
+                jj, ii = j + dj, i + di
+                if not (0 <= ii < nx):
+                    if not cfg.periodic[0]:
+                        continue          # ghost = near: the face carries no flux
+                    ii %= nx
+                if not (0 <= jj < ny):
+                    if not cfg.periodic[1]:
+                        continue
+                    jj %= ny
+                A[k, k] += s * b
+                A[k, idx[jj, ii]] -= s * b
+    return A.tocsr()
+
+
+@pytest.mark.parametrize("name,scale", [("C1", 2), ("C2", 1), ("C4", 1)])
+def test_solve_converges_to_direct_solution(name, scale):
+    cfg, o = make(name, scale)
+    sp_ = ob.make_solver_params(pre=2, post=2, bottom=4, max_iter=100, imin=10, iter_min=2, eps=1e-7, hang=1e-6, norm_thresh=1e-7)
+    sp_.eps, sp_.norm_thresh = 1e-12, 1e-14
+    it, hist = o.solver.solve(o.F["b"], o.F["rhs"], sp_)
+    assert 2 <= it <= 100
+    assert hist[-1] < 1e-9 * hist[0]
+    x = spl.spsolve(assemble(o.g, cfg, o.dx, o.alpha, o.beta).tocsc(), o.g["rhs"].ravel()).reshape(cfg.ny, cfg.nx)
+    got = o.F["b"].get_global()
+    assert np.max(np.abs(got - x)) < 1e-9 * np.max(np.abs(x))
+    assert 0 <= o.solver.bottom_iters <= 40
+
+
+def test_stop_logic_and_bottom_solver():
+    cfg, o = make("C2", 2)
+    # reference parameters: setSolverParameters(2,2,4,1,100,1e-7,1e-6,1e-7), m_imin = 10 (step < 50), m_iterMin = 2
+    sp_ = ob.make_solver_params(pre=2, post=2, bottom=4, max_iter=100, imin=10, iter_min=2, eps=1e-7, hang=1e-6, norm_thresh=1e-7)
+    it, hist = o.solver.solve(o.F["b"], o.F["rhs"], sp_)
+    assert it >= 2 and len(hist) == it + 1
+    assert hist[-1] <= max(1e-7 * hist[0], 1e-7) or it == 100 or hist[-1] >= (1 - 1e-6) * hist[-2]
+    assert np.all(np.diff(hist[:3]) < 0)
+    # fixed-cycle protocol and the V-cycle entry point agree
+    cfg, a = make("C2", 2)
+    cfg, b = make("C2", 2)
+    fx = ob.make_solver_params(pre=2, post=2, bottom=4, fixed_cycles=1)
+    a.solver.solve(a.F["b"], a.F["rhs"], fx)
+    res = ob.Field(b.layout, 1, 0)
+    corr = ob.Field(b.layout, 1, 1)
+    corr.setval(0.0)
+    b.solver.residual(res, b.F["b"], b.F["rhs"])
+    b.solver.vcycle(corr, res, fx)
+    assert np.array_equal(a.F["b"].get_global(), b.F["b"].get_global() + corr.get_global())
+    # bottom solver alone: drives the coarsest-level residual down by 1e-6 in the 2-norm or stops at 40
+    d = b.solver.depth - 1
+    Lb = b.solver.layout_at(d)
+    rng = np.random.RandomState(3)
+    rhs, e, r = ob.Field(Lb, 1, 0), ob.Field(Lb, 1, 1), ob.Field(Lb, 1, 0)
+    dom = Lb.domain
+    rhs.set_global(rng.rand(dom[3] + 1, dom[2] + 1), (0, 0))
+    e.setval(0.0)
+    b.solver.residual(r, e, rhs, depth=d)
+    n0 = np.sqrt(np.sum(r.get_global() ** 2))
+    its = b.solver.bottom_solve(e, rhs)
+    b.solver.residual(r, e, rhs, depth=d)
+    n1 = np.sqrt(np.sum(r.get_global() ** 2))
+    assert 1 <= its <= 40 and (n1 < 1e-6 * n0 * (1 + 1e-12) or its == 40)
