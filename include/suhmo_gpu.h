@@ -326,6 +326,46 @@ int sg_set_relax_mode(sg_ctx* ctx, int mode);
    per four (communication-avoiding relaxation off) */
 int sg_set_tuning(sg_ctx* ctx, int key, int value);
 
+/* ------------------------------------------------------------------ implicit gap-height solve ------------- */
+/* AmrHydro::SolveForGap_nl (src/AmrHydro.cpp:594-662; called at :3425-3455 when solver.use_ImplDiff is set): the reference
+   builds a stock Chombo VCAMRPoissonOp2Factory (:605-613; alpha = 1, aCoef = 1, beta = dt*DiffFactor, bCoef = Dcoef,
+   BC = FixedNeumBCFill :404-436) and a linear, correction-form AMRMultiGrid with a RelaxSolver bottom (:617-628).  L(b) =
+   alpha*a*b - beta*div(D grad b).  sg_gap_solver is that factory + solver pair.  One AMR level (every input that sets
+   use_ImplDiff is single-level), one patch per GPU; num_levels > 1 returns SG_ERR_UNSUPPORTED.  Stock Chombo is absent from the
+   SUHMO tree: the restatement is from recollection of public Chombo 3.2 (parity unpinned). */
+typedef struct sg_gap_solver sg_gap_solver;
+/* VCAMRPoissonOp2Factory::define(domain0, grids, refRatio, dx0, bc, alpha, aCoef, beta, bCoef) + AMRMultiGrid::define */
+int sg_gap_solver_define(sg_ctx* ctx, sg_gap_solver** out, int num_levels, sg_layout* const* grids, const int* ref_ratios,
+                         const double dx0[2], double alpha, sg_field* const* aCoef, double beta, sg_field* const* bX,
+                         sg_field* const* bY);
+int sg_gap_solver_destroy(sg_gap_solver* s);
+/* re-average the depth >= 1 coefficients after aCoef/bCoef changed (MGnewOp's CoarseAverage / CoarseAverageFace) */
+int sg_gap_solver_refresh(sg_gap_solver* s);
+int sg_gap_solver_depth(const sg_gap_solver* s, int* ndepth);
+int sg_gap_solver_layout(const sg_gap_solver* s, int depth, sg_layout** out); /* borrowed */
+/* VCAMRPoissonOp2 at MG depth `depth` of level 0: relax (levelGSRB), residual, applyOp, restrictResidual (to depth+1),
+   prolongIncrement (from depth+1), preCond, and the reciprocal diagonal m_lambda */
+int sg_gap_op_relax(sg_gap_solver* s, int depth, sg_field* phi, const sg_field* rhs, int iterations);
+int sg_gap_op_residual(sg_gap_solver* s, int depth, sg_field* lhs, sg_field* phi, const sg_field* rhs, int homogeneous);
+int sg_gap_op_applyOp(sg_gap_solver* s, int depth, sg_field* lhs, sg_field* phi, int homogeneous);
+int sg_gap_op_restrictResidual(sg_gap_solver* s, int depth, sg_field* res_coarse, sg_field* phi_fine, const sg_field* rhs_fine);
+int sg_gap_op_prolongIncrement(sg_gap_solver* s, int depth, sg_field* phi, const sg_field* corr_coarse);
+int sg_gap_op_preCond(sg_gap_solver* s, int depth, sg_field* phi, const sg_field* rhs);
+int sg_gap_op_lambda(sg_gap_solver* s, int depth, sg_field* lam);
+/* RelaxSolver::solve on the coarsest depth (m_imax 40, m_eps 1e-6, 2-norm); iterations = passes taken */
+int sg_gap_solver_bottom_solve(sg_gap_solver* s, sg_field* phi, const sg_field* rhs, int* iterations);
+/* AMRMultiGrid::AMRVCycle at l_max == l_base: one correction-form V-cycle on `residual`, accumulated into `correction` */
+int sg_gap_solver_vcycle(sg_gap_solver* s, sg_field* correction, const sg_field* residual, const sg_solver_params* sp);
+/* AMRMultiGrid::solve(phi, rhs, l_max, l_base, zeroPhi) (src/AmrHydro.cpp:656); sp = setSolverParameters + m_imin/m_iterMin */
+int sg_gap_solver_solve(sg_gap_solver* s, sg_field* const* phi, sg_field* const* rhs, int l_max, int l_base, int zero_phi,
+                        const sg_solver_params* sp, double* resnorm_history /* max_iter+2 or NULL */, sg_solve_stats* stats);
+/* the whole of SolveForGap_nl with the reference's constants (numSmooth 2, numBottom 4, numMG 1, maxIter 100, eps 1e-7,
+   normThresh 1e-7, hang 1e-6, m_imin = 10 while cur_step < 50, m_iterMin = 2): gap_height is solved in place */
+int sg_solve_for_gap(sg_ctx* ctx, int num_levels, sg_layout* const* grids, const int* ref_ratios, const double dx0[2],
+                     sg_field* const* aCoef, sg_field* const* bX, sg_field* const* bY, sg_field* const* gap_height,
+                     sg_field* const* rhs, double dt, double diff_factor, int cur_step, double* resnorm_history,
+                     sg_solve_stats* stats);
+
 #ifdef __cplusplus
 }
 #endif

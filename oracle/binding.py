@@ -261,7 +261,7 @@ def make_params(A=2.5e-25, cutOffbr=0.0, maxOffbr=10000.0, omega=1e-3, nu=1.787e
     return Params(A, cutOffbr, maxOffbr, omega, nu, cutOffBcoef, use_NL, use_mask_grad, bcoeff_otf)
 
 
-def make_solver_params(pre=4, post=4, bottom=16, max_iter=100, imin=0, iter_min=2, eps=1e-7, hang=0.01,
+def make_solver_params(pre=4, post=4, bottom=16, max_iter=100, imin=5, iter_min=2, eps=1e-7, hang=0.01,
                        norm_thresh=1e-7, fixed_cycles=0):
     return SolverParams(pre, post, bottom, max_iter, imin, iter_min, eps, hang, norm_thresh, fixed_cycles)
 

@@ -234,7 +234,7 @@ def make_params(A=2.5e-25, cutOffbr=0.0, maxOffbr=10000.0, omega=1e-3, nu=1.787e
     return capi.Params(A, cutOffbr, maxOffbr, omega, nu, cutOffBcoef, use_NL, use_mask_grad, bcoeff_otf)
 
 
-def make_solver_params(pre=4, post=4, bottom=16, num_mg=1, max_iter=100, imin=0, iter_min=2, eps=1e-7, hang=0.01,
+def make_solver_params(pre=4, post=4, bottom=16, num_mg=1, max_iter=100, imin=5, iter_min=2, eps=1e-7, hang=0.01,
                        norm_thresh=1e-7, fixed_cycles=0):
     return capi.SolverParams(pre, post, bottom, num_mg, max_iter, imin, iter_min, eps, hang, norm_thresh, fixed_cycles)
 
@@ -520,3 +520,96 @@ class BRMeshRefine:
             levels.append(out[k:k + counts[l]].copy())
             k += counts[l]
         return levels
+
+
+class GapHeightSolver:
+    """The VCAMRPoissonOp2Factory + linear AMRMultiGrid + RelaxSolver trio AmrHydro::SolveForGap_nl builds
+    (src/AmrHydro.cpp:594-662): L(b) = alpha*a*b - beta*div(D grad b) with FixedNeumBCFill, correction-form V-cycles.
+    One AMR level.  Methods named after the Chombo calls they stand for; `depth` selects the MG depth of level 0."""
+
+    def define(self, ctx, grids, refRatios, dx0, alpha, aCoef, beta, bX, bY):
+        self.ctx, self.grids = ctx, grids
+        self.keep = (aCoef, bX, bY)
+        self.h = C.c_void_p()
+        ga = (C.c_void_p * len(grids))(*[g.h.value for g in grids])
+        rr = np.ascontiguousarray(list(refRatios) + [2], dtype=np.int32)
+        dx = np.ascontiguousarray(dx0, dtype=np.float64)
+        arr = lambda fs: (C.c_void_p * len(fs))(*[f.h.value for f in fs])
+        check(lib().sg_gap_solver_define(ctx.h, C.byref(self.h), len(grids), ga, _ip(rr), _dp(dx), float(alpha), arr(aCoef), float(beta),
+                                         arr(bX), arr(bY)))
+        # setSolverParameters(2, 2, 4, 1, 100, 1e-7, 1e-6, 1e-7), m_iterMin = 2 (src/AmrHydro.cpp:630-654); m_imin: class default
+        self.params = make_solver_params(pre=2, post=2, bottom=4, num_mg=1, max_iter=100, imin=5, iter_min=2, eps=1e-7, hang=1e-6,
+                                         norm_thresh=1e-7)
+        return self
+
+    def setSolverParameters(self, pre, post, bottom, numMG, maxIter, eps, hang, normThresh):
+        p = self.params
+        p.pre, p.post, p.bottom, p.num_mg, p.max_iter, p.eps, p.hang, p.norm_thresh = pre, post, bottom, numMG, maxIter, eps, hang, normThresh
+
+    @property
+    def depth(self):
+        out = C.c_int()
+        check(lib().sg_gap_solver_depth(self.h, C.byref(out)))
+        return out.value
+
+    def layout_at(self, depth):
+        return self.grids[0] if depth == 0 else self.grids[0].coarsen(1 << depth)
+
+    def refresh(self):
+        check(lib().sg_gap_solver_refresh(self.h))
+
+    def relax(self, phi, rhs, iterations, depth=0):
+        check(lib().sg_gap_op_relax(self.h, depth, phi.h, rhs.h, iterations))
+
+    def residual(self, lhs, phi, rhs, homogeneous=False, depth=0):
+        check(lib().sg_gap_op_residual(self.h, depth, lhs.h, phi.h, rhs.h, int(homogeneous)))
+
+    def applyOp(self, lhs, phi, homogeneous=False, depth=0):
+        check(lib().sg_gap_op_applyOp(self.h, depth, lhs.h, phi.h, int(homogeneous)))
+
+    def restrictResidual(self, resCoarse, phiFine, rhsFine, depth=0):
+        check(lib().sg_gap_op_restrictResidual(self.h, depth, resCoarse.h, phiFine.h, rhsFine.h))
+
+    def prolongIncrement(self, phi, corrCoarse, depth=0):
+        check(lib().sg_gap_op_prolongIncrement(self.h, depth, phi.h, corrCoarse.h))
+
+    def preCond(self, phi, rhs, depth=0):
+        check(lib().sg_gap_op_preCond(self.h, depth, phi.h, rhs.h))
+
+    def lambda_(self, lam, depth=0):
+        check(lib().sg_gap_op_lambda(self.h, depth, lam.h))
+
+    def bottom_solve(self, phi, rhs):
+        it = C.c_int()
+        check(lib().sg_gap_solver_bottom_solve(self.h, phi.h, rhs.h, C.byref(it)))
+        return it.value
+
+    def vcycle(self, correction, residual):
+        check(lib().sg_gap_solver_vcycle(self.h, correction.h, residual.h, C.byref(self.params)))
+
+    def solve(self, phi, rhs, l_max=0, l_base=0, zeroPhi=False, fixed_cycles=0):
+        self.params.fixed_cycles = fixed_cycles
+        hist = np.zeros(max(self.params.max_iter, fixed_cycles) + 2)
+        stats = capi.SolveStats()
+        pa = (C.c_void_p * len(phi))(*[f.h.value for f in phi])
+        ra = (C.c_void_p * len(rhs))(*[f.h.value for f in rhs])
+        check(lib().sg_gap_solver_solve(self.h, pa, ra, l_max, l_base, int(zeroPhi), C.byref(self.params), _dp(hist), C.byref(stats)))
+        return stats.iterations, hist[:stats.iterations + 1], stats
+
+    def destroy(self):
+        if self.h:
+            lib().sg_gap_solver_destroy(self.h)
+            self.h = None
+
+
+def SolveForGap_nl(ctx, grids, aCoef, bX, bY, refRatio, coarsestDx, gapHeight, RHS, dt, DiffFactor, cur_step):
+    """AmrHydro::SolveForGap_nl (src/AmrHydro.cpp:594-662): gapHeight is solved in place.  Returns (iterations, history, stats)."""
+    arr = lambda fs: (C.c_void_p * len(fs))(*[f.h.value for f in fs])
+    ga = (C.c_void_p * len(grids))(*[g.h.value for g in grids])
+    rr = np.ascontiguousarray(list(refRatio) + [2], dtype=np.int32)
+    dx = np.ascontiguousarray(coarsestDx, dtype=np.float64)
+    hist = np.zeros(102)
+    stats = capi.SolveStats()
+    check(lib().sg_solve_for_gap(ctx.h, len(grids), ga, _ip(rr), _dp(dx), arr(aCoef), arr(bX), arr(bY), arr(gapHeight), arr(RHS), float(dt),
+                                 float(DiffFactor), int(cur_step), _dp(hist), C.byref(stats)))
+    return stats.iterations, hist[:stats.iterations + 1], stats

@@ -102,6 +102,14 @@ SIGNATURES = {
     "sg_solver_define": [vp, pvp, ci], "sg_solver_destroy": [vp], "sg_solver_depth": [vp, ci, ip],
     "sg_solver_solve": [vp, pvp, pvp, ci, ci, C.POINTER(SolverParams), dp, C.POINTER(SolveStats)],
     "sg_solver_cell_updates_per_cycle": [vp, C.POINTER(SolverParams), dp],
+    "sg_gap_solver_define": [vp, pvp, ci, pvp, ip, dp, cd, pvp, cd, pvp, pvp], "sg_gap_solver_destroy": [vp],
+    "sg_gap_solver_refresh": [vp], "sg_gap_solver_depth": [vp, ip], "sg_gap_solver_layout": [vp, ci, pvp],
+    "sg_gap_op_relax": [vp, ci, vp, vp, ci], "sg_gap_op_residual": [vp, ci, vp, vp, vp, ci], "sg_gap_op_applyOp": [vp, ci, vp, vp, ci],
+    "sg_gap_op_restrictResidual": [vp, ci, vp, vp, vp], "sg_gap_op_prolongIncrement": [vp, ci, vp, vp],
+    "sg_gap_op_preCond": [vp, ci, vp, vp], "sg_gap_op_lambda": [vp, ci, vp],
+    "sg_gap_solver_bottom_solve": [vp, vp, vp, ip], "sg_gap_solver_vcycle": [vp, vp, vp, C.POINTER(SolverParams)],
+    "sg_gap_solver_solve": [vp, pvp, pvp, ci, ci, ci, C.POINTER(SolverParams), dp, C.POINTER(SolveStats)],
+    "sg_solve_for_gap": [vp, ci, pvp, ip, dp, pvp, pvp, pvp, pvp, pvp, cd, cd, ci, dp, C.POINTER(SolveStats)],
 }
 
 

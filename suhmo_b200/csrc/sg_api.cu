@@ -5,6 +5,7 @@
 #include "sg_kernels.cuh"
 #include "sg_general.cuh"
 #include "sg_picard.cuh"
+#include "sg_linear.cuh"
 #include "sg_nccl.h"
 
 #include <algorithm>
@@ -2007,3 +2008,5 @@ extern "C" int sg_solver_solve(sg_solver* s, sg_field* const* phi, sg_field* con
   cudaEventDestroy(e0); cudaEventDestroy(e1);
   return SG_OK;
 }
+
+#include "sg_linear_host.inc"

@@ -163,7 +163,7 @@ class AMRFASMultiGrid {
  public:
   sg_solver* h = nullptr;
   sg_solver_params params{4, 4, 16, 1, 100, 0, 2, 1e-7, 0.01, 1e-7, 0};
-  int m_imin = 0, m_iterMin = 2, m_exitStatus = 0;
+  int m_imin = 5 /* stock AMRMultiGrid constructor default (recollection) */, m_iterMin = 2, m_exitStatus = 0;
   ~AMRFASMultiGrid() { sg_solver_destroy(h); }
   void define(VCAMRNonLinearPoissonOpFactory& factory, int numLevels) { SG_DO(sg_solver_define(factory.h, &h, numLevels)); }
   void setSolverParameters(int pre, int post, int bottom, int numMG, int maxIter, double eps, double hang, double normThresh) {
@@ -187,5 +187,56 @@ class AMRFASMultiGrid {
   }
   void refresh() { SG_DO(sg_solver_refresh(h)); }
 };
+
+// The VCAMRPoissonOp2Factory + AMRMultiGrid<LevelData<FArrayBox>> + RelaxSolver trio of AmrHydro::SolveForGap_nl
+// (src/AmrHydro.cpp:594-662): linear VC Helmholtz, correction-form V-cycles, one AMR level
+class GapHeightSolver {
+ public:
+  sg_gap_solver* h = nullptr;
+  sg_solver_params params{2, 2, 4, 1, 100, 5, 2, 1e-7, 1e-6, 1e-7, 0};
+  int m_imin = 5, m_iterMin = 2, m_exitStatus = 0;
+  ~GapHeightSolver() { sg_gap_solver_destroy(h); }
+  void define(Context& ctx, const std::vector<DisjointBoxLayout*>& grids, const std::vector<int>& refRatios, const double dx0[2], double alpha,
+              const std::vector<LevelData*>& aCoef, double beta, const std::vector<LevelData*>& bX, const std::vector<LevelData*>& bY) {
+    std::vector<sg_layout*> g;
+    std::vector<sg_field*> a, x, y;
+    for (auto* l : grids) g.push_back(l->h);
+    for (auto* f : aCoef) a.push_back(f->h);
+    for (auto* f : bX) x.push_back(f->h);
+    for (auto* f : bY) y.push_back(f->h);
+    std::vector<int> rr(refRatios);
+    rr.push_back(2);
+    SG_DO(sg_gap_solver_define(ctx.h, &h, (int)g.size(), g.data(), rr.data(), dx0, alpha, a.data(), beta, x.data(), y.data()));
+  }
+  void setSolverParameters(int pre, int post, int bottom, int numMG, int maxIter, double eps, double hang, double normThresh) {
+    params.pre = pre; params.post = post; params.bottom = bottom; params.num_mg = numMG; params.max_iter = maxIter;
+    params.eps = eps; params.hang = hang; params.norm_thresh = normThresh;
+  }
+  int solve(const std::vector<LevelData*>& phi, const std::vector<LevelData*>& rhs, int l_max, int l_base, bool zeroPhi = false,
+            sg_solve_stats* stats = nullptr, std::vector<double>* resnorm = nullptr) {
+    params.imin = m_imin; params.iter_min = m_iterMin;
+    std::vector<sg_field*> p, r;
+    for (LevelData* f : phi) p.push_back(f->h);
+    for (LevelData* f : rhs) r.push_back(f->h);
+    std::vector<double> hist((size_t)(params.max_iter > params.fixed_cycles ? params.max_iter : params.fixed_cycles) + 2, 0.0);
+    sg_solve_stats st;
+    SG_DO(sg_gap_solver_solve(h, p.data(), r.data(), l_max, l_base, zeroPhi, &params, hist.data(), &st));
+    m_exitStatus = st.exit_status;
+    if (stats) *stats = st;
+    if (resnorm) resnorm->assign(hist.begin(), hist.begin() + st.iterations + 1);
+    return st.iterations;
+  }
+};
+
+// AmrHydro::SolveForGap_nl with the reference's constants; returns the number of V-cycles
+inline int SolveForGap_nl(Context& ctx, const std::vector<DisjointBoxLayout*>& grids, const std::vector<LevelData*>& aCoef,
+                          const std::vector<LevelData*>& bX, const std::vector<LevelData*>& bY, const std::vector<int>& refRatio,
+                          const double coarsestDx[2], const std::vector<LevelData*>& gapHeight, const std::vector<LevelData*>& RHS, double dt,
+                          double DiffFactor, int cur_step) {
+  GapHeightSolver s;
+  s.define(ctx, grids, refRatio, coarsestDx, 1.0, aCoef, dt * DiffFactor, bX, bY);
+  if (cur_step < 50) s.m_imin = 10;
+  return s.solve(gapHeight, RHS, (int)grids.size() - 1, 0);
+}
 
 } // namespace sg

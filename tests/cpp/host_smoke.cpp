@@ -68,6 +68,24 @@ int main() {
   std::printf("host_smoke: %d FAS V-cycles, composite residual %.3e -> %.3e, %lld kernel launches, %.0f cell-updates\n", it, hist.front(),
               hist.back(), st.kernel_launches, st.cell_updates);
   bool ok = std::isfinite(hist.back()) && hist.back() < 1e-3 * hist.front() && st.kernel_launches > 0;
+  // the implicit gap-height solve of the same time step (AmrHydro::SolveForGap_nl, src/AmrHydro.cpp:594-662) on level 0:
+  // (I - dt*DiffFactor div(D grad)) b = b_old + dt*RHS_b with D = 1e-4 everywhere
+  {
+    DisjointBoxLayout& g = g0;
+    LevelData one(g, 1, 0), dX(g, 1, 0, XFace), dY(g, 1, 0, YFace), gap(g, 1, 1), rb(g, 1, 0);
+    fill(one, g, 0, 0, 0, dx0[0], f_one);
+    fill(dX, g, 0, 1, 0, dx0[0], [](double, double) { return 1e-4; });
+    fill(dY, g, 0, 0, 1, dx0[0], [](double, double) { return 1e-4; });
+    fill(gap, g, 1, 0, 0, dx0[0], f_gap);
+    fill(rb, g, 0, 0, 0, dx0[0], [](double x, double y) { return 0.01 + 0.005 * std::sin(0.4 * x) * std::cos(0.3 * y); });
+    std::vector<DisjointBoxLayout*> gl = {&g0};
+    int git = SolveForGap_nl(ctx, gl, {&one}, {&dX}, {&dY}, {}, dx0, {&gap}, {&rb}, 3600.0, 1.0, 0);
+    std::vector<double> fab((size_t)34 * 34);
+    gap.download(0, fab.data());
+    double v = fab[(size_t)17 * 34 + 17];
+    std::printf("host_smoke: implicit gap solve, %d V-cycles, b(16,16) = %.6e\n", git, v);
+    ok = ok && git >= 2 && git < 100 && std::isfinite(v) && v > 0.004 && v < 0.016;
+  }
   delete op0; delete op1;
   for (auto* v : {&head, &rhs, &aC, &bX, &bY, &B, &Pi, &zb, &mask})
     for (LevelData* f : *v) delete f;

@@ -87,3 +87,30 @@ def np_gsrb(p, rhs, g, cfg, dx, alpha, beta):
         sel = ((ii + jj + color) % 2) == 0
         p[1:-1, 1:-1][sel] = new[sel]
     return p
+
+
+class GpuGap:
+    """Device twin of an OracleGap: same bits uploaded, GapHeightSolver on top."""
+
+    def __init__(self, ctx, orc, owner=None):
+        from suhmo_b200 import amr
+        self.amr, self.ctx, self.orc = amr, ctx, orc
+        cfg = orc.cfg
+        self.layout = amr.DisjointBoxLayout(ctx, orc.boxes, (0, 0, cfg.nx - 1, cfg.ny - 1), cfg.periodic, owner)
+        spec = dict(a=(0, 0), bX=(0, XFACE), bY=(0, YFACE), b=(1, 0), rhs=(0, 0))
+        self.F = {}
+        for k, (ng, cent) in spec.items():
+            self.F[k] = amr.LevelData(self.layout, 1, ng, cent)
+            self.push(self.F[k], orc.F[k])
+        self.solver = amr.GapHeightSolver().define(ctx, [self.layout], [], (orc.dx, orc.dx), orc.alpha, [self.F["a"]], orc.beta,
+                                                   [self.F["bX"]], [self.F["bY"]])
+
+    def push(self, ld, of):
+        ld.upload([of.fab(b)[0].copy() if ld.layout.owned(b) else None for b in range(len(ld.layout.boxes))])
+
+    def new(self, depth=0, ng=0, src=None):
+        L = self.layout if depth == 0 else self.layout.coarsen(1 << depth)
+        f = self.amr.LevelData(L, 1, ng, 0)
+        if src is not None:
+            self.push(f, src)
+        return f

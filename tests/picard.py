@@ -1,7 +1,8 @@
 """One single-level Picard step of AmrHydro::timeStepFAS (src/AmrHydro.cpp:2477-3235, 3248-3408) as a sequence of
 kernel calls, written once against a tiny backend interface and run on the oracle (CPU) and on the library (GPU): the time /
 Picard loops are host code in the reference, their field kernels are what the library provides.
-Explicit gap update (solver.use_ImplDiff = false)."""
+Gap update: explicit Euler (solver.use_ImplDiff = false) or the implicit diffusion solve SolveForGap_nl (true; src/AmrHydro.cpp:
+3378-3455, 594-662)."""
 import ctypes as C
 
 import numpy as np
@@ -28,10 +29,11 @@ def _dx(cfg):
 class OracleBackend:
     """kernel calls on oracle fields"""
 
-    def __init__(self, orc):
+    def __init__(self, orc, impl_diff=False):
         self.L, self.orc, self.cfg = ob.lib(), orc, orc.cfg
         self.prm, self.bc = orc.prm, orc.bc
-        self.q = picard_params(ob.PicardParams, orc.cfg)
+        self.impl_diff = impl_diff
+        self.q = picard_params(ob.PicardParams, orc.cfg, use_ImplDiff=int(impl_diff))
 
     def new(self, ncomp=1, ng=0, cent=CELL):
         return ob.Field(self.orc.layout, ncomp, ng, cent)
@@ -62,16 +64,27 @@ class OracleBackend:
         it, hist = self.orc.solver().solve(F["head"], F["rhs"], ob.make_solver_params(bottom=10, fixed_cycles=ncyc))
         return hist
 
+    def setval(self, f, v): f.setval(v)
+
+    def solve_gap(self, aC, Dc, gap, rhs, dt, cur_step):
+        s = ob.LinSolver(self.orc.layout, self.cfg.dx[0], 1.0, dt * self.q.DiffFactor, aC, Dc[0], Dc[1])
+        sp = ob.make_solver_params(pre=2, post=2, bottom=4, max_iter=100, imin=10 if cur_step < 50 else 5, iter_min=2, eps=1e-7,
+                                   hang=1e-6, norm_thresh=1e-7)
+        it, hist = s.solve(gap, rhs, sp)
+        s.free()
+        return hist
+
 
 class GpuBackend:
     """the same calls through the C ABI"""
 
-    def __init__(self, gpu):
+    def __init__(self, gpu, impl_diff=False):
         from suhmo_b200 import amr, capi
         self.amr, self.capi, self.gpu, self.cfg = amr, capi, gpu, gpu.orc.cfg
         self.Lib = capi.lib()
         self.prm, self.bc = gpu.prm, gpu.bc
-        self.q = picard_params(capi.PicardParams, self.cfg)
+        self.impl_diff = impl_diff
+        self.q = picard_params(capi.PicardParams, self.cfg, use_ImplDiff=int(impl_diff))
         self.mg = None
 
     def ck(self, st): self.capi.check(st)
@@ -116,6 +129,15 @@ class GpuBackend:
         return hist
 
 
+    def setval(self, f, v):
+        f.upload([np.full(f.fab_shape(b), float(v)) if f.layout.owned(b) else None for b in range(len(f.layout.boxes))])
+
+    def solve_gap(self, aC, Dc, gap, rhs, dt, cur_step):
+        it, hist, st = self.amr.SolveForGap_nl(self.gpu.ctx, [self.gpu.layout], [aC], [Dc[0]], [Dc[1]], [], self.cfg.dx, [gap], [rhs], dt,
+                                               self.q.DiffFactor, cur_step)
+        return hist
+
+
 def extra_fields(be, setter):
     """fields of the Picard body beyond the head-solve set, with simple deterministic contents"""
     cfg = be.cfg
@@ -139,7 +161,7 @@ def extra_fields(be, setter):
     return X
 
 
-def picard_step(be, F, X, dt=3600.0, npicard=2, ncyc=3):
+def picard_step(be, F, X, dt=3600.0, npicard=2, ncyc=3, cur_step=0):
     """F: head-solve fields (head, B, Pi, zb, mask, rhs, bX, bY); X: extra_fields.  Returns residual histories."""
     use_mask = bool(be.cfg.use_mask_grad)
     hists = []
@@ -179,9 +201,17 @@ def picard_step(be, F, X, dt=3600.0, npicard=2, ncyc=3):
         # coefficients and the head solve (:3087-3119)
         be.bcoeff(F)
         hists.append(be.solve_head(F, ncyc))
-    # gap-height update (:3248-3408), explicit branch
+    # gap-height update (:3248-3408)
     be.rhs_gap(X["RHSb"], F["Pi"], X["Pw"], X["mR"], F["B"], X["Dterm"], F["mask"], X["BH"], X["BL"], X["MV"], dt)
-    be.gap_euler(F["B"], X["oldB"], X["RHSb"], dt)
+    if be.impl_diff:
+        # implicit branch (:3378-3391, 3425-3455): a_gh_curr = B incl. ghosts, aCoef = 1, bCoef = Dcoef, SolveForGap_nl, copy back
+        cur, aC = be.new(1, 1, CELL), be.new(1, 0, CELL)
+        be.copy(cur, F["B"])
+        be.setval(aC, 1.0)
+        hists.append(be.solve_gap(aC, X["Dc"], cur, X["RHSb"], dt, cur_step))
+        be.copy(F["B"], cur)
+    else:
+        be.gap_euler(F["B"], X["oldB"], X["RHSb"], dt)
     be.exchange(F["B"])
     be.copy_ghost(F["B"])
     return hists

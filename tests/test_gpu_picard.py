@@ -11,13 +11,14 @@ from tests.problem import GpuSide, OracleSide, fields_equal, rel_l2
 pytestmark = pytest.mark.gpu
 
 
+@pytest.mark.parametrize("impl_diff", [False, True])
 @pytest.mark.parametrize("name,scale", [("C1", 2), ("C2", 1), ("C4", 1), ("C5", 1)])
-def test_picard_iterations_head_and_gap_parity(gpu_ctx, name, scale):
+def test_picard_iterations_head_and_gap_parity(gpu_ctx, name, scale, impl_diff):
     cfg = syn.config(name, scale)
     boxes = syn.domain_split(cfg.nx, cfg.ny, cfg.max_box_size, cfg.block_factor)
     orc = OracleSide(cfg, boxes)
     gpu = GpuSide(gpu_ctx, orc)
-    obe, gbe = picard.OracleBackend(orc), picard.GpuBackend(gpu)
+    obe, gbe = picard.OracleBackend(orc, impl_diff), picard.GpuBackend(gpu, impl_diff)
     OX = picard.extra_fields(obe, lambda f, g: f.set_global(g, (-1, -1)))
     GX = picard.extra_fields(gbe, lambda f, g: f.set_global(g, (-1, -1)))
     oh = picard.picard_step(obe, orc.F, OX, npicard=2, ncyc=3)

@@ -8,12 +8,13 @@ from tests import picard
 from tests.problem import OracleSide
 
 
+@pytest.mark.parametrize("impl_diff", [False, True])
 @pytest.mark.parametrize("name", ["C1", "C4"])
-def test_picard_step_on_oracle(name):
+def test_picard_step_on_oracle(name, impl_diff):
     cfg = syn.config(name, 2 if name == "C1" else 1)
     boxes = syn.domain_split(cfg.nx, cfg.ny, cfg.max_box_size, cfg.block_factor)
     orc = OracleSide(cfg, boxes)
-    be = picard.OracleBackend(orc)
+    be = picard.OracleBackend(orc, impl_diff)
     X = picard.extra_fields(be, lambda f, g: f.set_global(g, (-1, -1)))
     b0 = orc.F["B"].get_global().copy()
     h0 = orc.F["head"].get_global().copy()
