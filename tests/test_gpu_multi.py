@@ -24,7 +24,7 @@ def test_two_rank_partition_is_bit_exact(cfg, scale):
            "--master-port", "29533", os.path.join(ROOT, "tools", "parity_multi.py"), cfg, str(scale)]
     r = subprocess.run(cmd, cwd=ROOT, capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
-    assert '"head_bit_exact": true' in r.stdout
+    assert '"head_bit_exact": true' in r.stdout and '"gap_solve_bit_exact": true' in r.stdout
 
 
 @pytest.mark.skipif(_ngpu() < 2, reason="needs two GPUs (NCCL refuses two ranks on one device)")

@@ -45,6 +45,15 @@ def main():
     mine = gpu.F["head"].get_global()    # NaN outside this rank's boxes
     parts = [None] * world
     dist.all_gather_object(parts, np.nan_to_num(mine, nan=0.0) * (~np.isnan(mine)))
+    # the implicit gap-height solve (SolveForGap_nl) on the same partition: 2-norm of the bottom solver by ncclAllReduce(sum)
+    from tests import gapsolve as gs
+    ogap = gs.OracleGap(cfg, boxes)
+    ggap = gs.GpuGap(ctx, ogap, owner)
+    gap_it, gap_hist, _ = amr.SolveForGap_nl(ctx, [ggap.layout], [ggap.F["a"]], [ggap.F["bX"]], [ggap.F["bY"]], [], (ogap.dx, ogap.dx),
+                                             [ggap.F["b"]], [ggap.F["rhs"]], ogap.beta, 1.0, 0)
+    gmine = ggap.F["b"].get_global()
+    gparts = [None] * world
+    dist.all_gather_object(gparts, np.nan_to_num(gmine, nan=0.0) * (~np.isnan(gmine)))
     ok = True
     if rank == 0:
         full = sum(parts)
@@ -52,9 +61,13 @@ def main():
         oh = orc.F["head"].get_global()
         exact = bool(np.array_equal(full, oh))
         hist_ok = bool(np.array_equal(ghist, ohist))
-        ok = exact and hist_ok
+        sp = ob.make_solver_params(pre=2, post=2, bottom=4, max_iter=100, imin=10, iter_min=2, eps=1e-7, hang=1e-6, norm_thresh=1e-7)
+        oit, ogh = ogap.solver.solve(ogap.F["b"], ogap.F["rhs"], sp)
+        gap_exact = bool(np.array_equal(sum(gparts), ogap.F["b"].get_global())) and oit == gap_it and bool(np.array_equal(ogh, gap_hist))
+        ok = exact and hist_ok and gap_exact
         print(json.dumps({"check": "multi-rank parity", "config": name, "grid": [cfg.nx, cfg.ny], "ranks": world, "vcycles": ncyc,
                           "head_bit_exact": exact, "resnorm_history_equal": hist_ok,
+                          "gap_solve_bit_exact": gap_exact, "gap_solve_vcycles": int(gap_it),
                           "max_abs_diff": float(np.abs(full - oh).max()), "resnorm": [float(ghist[0]), float(ghist[-1])]}), flush=True)
     flag = [ok]
     dist.broadcast_object_list(flag, src=0)
