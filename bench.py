@@ -203,6 +203,34 @@ def amr_leg(ctx, amr, cfg, layout0, F0, bc, prm, args):
             "setup_s": t_setup, "grids": "sg_tag_cells_level + sg_br_regrid (fill 0.5, block factor 2, nesting 4, max box 64, tags_grow 4)"}
 
 
+def gap_leg(ctx, amr, cfg, layout, F, op0, host, args):
+    """SURVEY.md 8 f2: the implicit gap-height solve of the same time step (AmrHydro::SolveForGap_nl) on the resident base grid,
+    with the reference's solver constants.  aCoef = 1, D = the B(h) face coefficients rescaled so that beta*D/dx^2 ~ 4 (diffusion
+    matters on the finest grid), rhs = b + a perturbation shaped like the moulin sources."""
+    one = amr.LevelData(layout, 1, 0, 0)
+    one.upload_packed(np.ones(one.packed_size()))
+    gap, rhs = amr.LevelData(layout, 1, 1, 0), amr.LevelData(layout, 1, 0, 0)
+    rmax = op0.norm(F["rhs"], 0)
+    dmean = float(host["bX"].mean())
+    dx = cfg.dx[0]
+    beta = 4.0 * dx * dx / dmean
+    res = None
+    for rep in range(2):  # first pass warms up
+        op0.assignLocal(gap, F["B"])
+        op0.axby(rhs, F["B"], F["rhs"], 1.0, 0.005 / rmax)
+        ctx.sync()
+        t0 = time.perf_counter()
+        it, hist, st = amr.SolveForGap_nl(ctx, [layout], [one], [F["bX"]], [F["bY"]], [], cfg.dx, [gap], [rhs], beta, 1.0, 100)
+        ctx.sync()
+        res = {"vcycles": int(it), "ms_per_solve_device": st.device_ms, "ms_per_solve_wall": 1e3 * (time.perf_counter() - t0),
+               "ms_per_vcycle": st.device_ms / max(1, it), "kernel_launches": int(st.kernel_launches),
+               "resnorm": [float(hist[0]), float(hist[-1])],
+               "params": "pre/post 2, bottom 4 + RelaxSolver, eps 1e-7, hang 1e-6, imin 5, iterMin 2 (src/AmrHydro.cpp:630-654)"}
+    for f in (one, gap, rhs):
+        f.destroy()
+    return res
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -219,6 +247,7 @@ def main():
     ap.add_argument("--relax-mode", type=int, default=1)
     ap.add_argument("--no-amr", action="store_true", help="skip the 3-level AMR leg (N = 1 only)")
     ap.add_argument("--amr-cycles", type=int, default=3)
+    ap.add_argument("--no-gap", action="store_true", help="skip the implicit gap-height solve leg (N = 1 only)")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -353,6 +382,13 @@ def main():
                "sample": f"{args.cpu_cycles} FAS V-cycles on a {args.cpu_size}x{args.cpu_size} sample of the workload "
                          f"({dt:.1f} s), oracle C restatement with OpenMP over boxes"}
 
+    gap_info = None
+    if world == 1 and not args.no_gap:
+        try:
+            gap_info = gap_leg(ctx, amr, cfg, layout, F, op0, host, args)
+        except Exception as e:
+            gap_info = {"failed": repr(e)[:300]}
+
     amr_info = None
     if world == 1 and not args.no_amr:
         try:
@@ -384,6 +420,7 @@ def main():
                     "ms_per_step": 1e3 * e2e_t, "vcycles_per_step": args.e2e_cycles},
             "gpu_launches": int(launches),
             "amr_3level": amr_info,
+            "gap_solve": gap_info,
             "clocks": clk,
             "resnorm": [float(hist[0]), float(hist[-1])],
             "wall_ms_per_step": 1e3 * wall / args.steps,

@@ -181,6 +181,7 @@ struct sg_solver {
   std::vector<sg_op*> aops;
   std::vector<sg_field*> aresid, acorr, atmp, ascratch, aresC;
   // one FAS V-cycle + residual norm captured as a CUDA graph (launch-bound levels: ~110 launches become one)
+  bool coefs_averaged = false;                      // this V-cycle's depth >= 1 face coefficients are already averaged (average_all_depths)
   cudaGraphExec_t gexec = nullptr;
   std::vector<long long> gkey, warm_key;
   long long glaunches = 0;
@@ -1819,6 +1820,37 @@ extern "C" int sg_solver_cell_updates_per_cycle(const sg_solver* s, const sg_sol
   return SG_OK;
 }
 
+// AverageOperator(ops[d], ops[0], d) for every depth d >= 1 at once: the finest face coefficients are read once per V-cycle.
+// Same values as the per-depth calls (the depth-0 coefficients do not change inside a V-cycle), so mg_cycle only fills ghosts.
+static int average_all_depths(sg_solver* s) {
+  sg_op* op0 = s->ops[0];
+  sg_layout* L = op0->lay;
+  const int nd = (int)s->ops.size() - 1;
+  s->coefs_averaged = false;
+  if (nd < 1 || !L->fast) return SG_OK;
+  for (int d = 1; d <= nd; d++) if (!s->ops[d]->lay->fast) return SG_OK;
+  if (L->has_local) {
+    for (int first = 1; first <= nd; first += 5) { // five depths per pass; deeper ones (ratio >= 64) take the per-depth kernel
+      if (first > 1) {
+        for (int d = first; d <= nd; d++) { SGCALL(avg_face(s->ops[d]->bX, op0->bX, 1 << d)); SGCALL(avg_face(s->ops[d]->bY, op0->bY, 1 << d)); }
+        break;
+      }
+      AvgMulti ax, ay;
+      ax.nd = ay.nd = std::min(5, nd);
+      for (int k = 0; k < 5; k++) { ax.c[k] = ay.c[k] = nullptr; ax.pitch[k] = ay.pitch[k] = 0; }
+      for (int k = 0; k < ax.nd; k++) {
+        sg_op* o = s->ops[1 + k];
+        ax.c[k] = o->bX->p(); ay.c[k] = o->bY->p();
+        ax.pitch[k] = ay.pitch[k] = o->lay->pitch;
+      }
+      const int R = 1 << ax.nd;
+      LAUNCH(s->ctx, k_avg_face_multi_x, dim3(((L->nx / 2 + 1) + 127) / 128, (L->ny + R - 1) / R), 128, op0->bX->p(), L->pitch, L->nx, L->ny, ax);
+      LAUNCH(s->ctx, k_avg_face_multi_y, dim3(((L->nx + R - 1) / R + 31) / 32, ((L->ny / 2 + 1) + 7) / 8), B2D, op0->bY->p(), L->pitch, L->nx, L->ny, ay);
+    }
+  }
+  s->coefs_averaged = true;
+  return SG_OK;
+}
 static int mg_cycle(sg_solver* s, int depth, sg_field* phi, sg_field* rhs, const sg_solver_params* sp) {
   sg_op* op = s->ops[depth];
   int nd = (int)s->ops.size();
@@ -1826,7 +1858,10 @@ static int mg_cycle(sg_solver* s, int depth, sg_field* phi, sg_field* rhs, const
   SGCALL(relax_impl(op, phi, rhs, sp->pre, false));
   int dc = depth + 1;
   sg_op* opc = s->ops[dc];
-  if (op->update_operator) SGCALL(sg_op_AverageOperator(opc, s->ops[0], dc));
+  if (op->update_operator) {
+    if (s->coefs_averaged) SGCALL(coef_ghosts(opc, true));
+    else SGCALL(sg_op_AverageOperator(opc, s->ops[0], dc));
+  }
   // restrictR + restrictResidual in one sweep over the fine level
   SGCALL(restrict_impl(op, s->rhs[dc], s->phi[dc], phi, rhs, s->save[dc]));              // ... and assignLocal(saved, phiC)
   SGCALL(apply_impl(opc, s->rhs[dc], s->phi[dc], nullptr, 0, 4, 0));                     // rhsC += applyOpMg(phiC, NULL, false)
@@ -1847,7 +1882,12 @@ static int amr_residual_level(sg_solver* s, sg_field* const* phi, sg_field* cons
 static int amr_vcycle(sg_solver* s, sg_field* const* phi, sg_field* const* rhs, int ilev, int l_max, const sg_solver_params* sp, int iter) {
   sg_op* op = s->aops[ilev];
   if (op->update_operator) SGCALL(sg_op_UpdateOperator(op, phi[ilev], ilev > 0 ? phi[ilev - 1] : nullptr, ilev, iter, 0));
-  if (ilev == 0) return mg_cycle(s, 0, phi[0], s->aresid[0], sp);
+  if (ilev == 0) {
+    if (op->update_operator) SGCALL(average_all_depths(s));
+    int r = mg_cycle(s, 0, phi[0], s->aresid[0], sp);
+    s->coefs_averaged = false;
+    return r;
+  }
   sg_op* opc = s->aops[ilev - 1];
   SGCALL(sg_op_relaxNF(op, phi[ilev], phi[ilev - 1], s->aresid[ilev], sp->pre, iter, ilev, 0));
   // phi[ilev-1] <- average of phi[ilev] on the covered region (AMRRestrictS with skip_res), kept as the FAS reference state
@@ -1868,8 +1908,10 @@ static int amr_vcycle(sg_solver* s, sg_field* const* phi, sg_field* const* rhs, 
 static int vcycle(sg_solver* s, sg_field* const* phi, sg_field* const* rhs, int l_max, const sg_solver_params* sp, int iter) {
   if (l_max == 0) {
     sg_op* op0 = s->ops[0];
-    if (op0->update_operator) SGCALL(sg_op_UpdateOperator(op0, phi[0], nullptr, 0, iter, 0));
-    return mg_cycle(s, 0, phi[0], rhs[0], sp);
+    if (op0->update_operator) { SGCALL(sg_op_UpdateOperator(op0, phi[0], nullptr, 0, iter, 0)); SGCALL(average_all_depths(s)); }
+    int r = mg_cycle(s, 0, phi[0], rhs[0], sp);
+    s->coefs_averaged = false;
+    return r;
   }
   SGCALL(vec_launch<3>(s->aresid[l_max], rhs[l_max], nullptr, 0, 0, false)); // residual[lmax] = rhs[lmax]
   return amr_vcycle(s, phi, rhs, l_max, l_max, sp, iter);

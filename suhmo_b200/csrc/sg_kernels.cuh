@@ -1056,6 +1056,64 @@ __global__ void __launch_bounds__(256) k_avg_face(double* __restrict__ c, int pi
   c[(size_t)jc * pitchC + ic] = s / (double)r;
 }
 
+// AverageOperator for ALL coarser MG depths in one pass over the finest face coefficients (the solver's V-cycle calls it
+// once after UpdateOperator instead of k_avg_face once per depth, which re-reads the finest arrays with stride 2^depth).
+// Output d (MG depth d+1, r = 2^(d+1)) gets exactly k_avg_face's value: s = 0; s = s + f_k for k = 0..r-1 in order; s / r.
+struct AvgMulti {
+  double* c[5];
+  int pitch[5];
+  int nd; // number of coarser depths, <= 5 per pass
+};
+// x-faces: thread = even fine column i, block row = 2^nd fine rows.  Coarse face (ic, jc) of ratio r sums fine faces (ic*r, jc*r + k).
+__global__ void __launch_bounds__(128) k_avg_face_multi_x(const double* __restrict__ f, int pitchF, int nx, int ny, AvgMulti a) {
+  int i = 2 * (blockIdx.x * blockDim.x + threadIdx.x);
+  if (i > nx) return;
+  const int R = 1 << a.nd;
+  int nact = i == 0 ? a.nd : min(a.nd, __ffs(i) - 1); // depths whose ratio divides the column index
+  double s[5] = {0.0, 0.0, 0.0, 0.0, 0.0};
+  int j0 = blockIdx.y * R;
+  for (int k = 0; k < R; k++) {
+    int j = j0 + k;
+    if (j >= ny) break;
+    double v = f[(size_t)j * pitchF + i];
+#pragma unroll
+    for (int d = 0; d < 5; d++)
+      if (d < nact) {
+        s[d] = s[d] + v;
+        const int r = 2 << d;
+        if (((k + 1) & (r - 1)) == 0) {
+          a.c[d][(size_t)(j >> (d + 1)) * a.pitch[d] + (i >> (d + 1))] = s[d] / (double)r;
+          s[d] = 0.0;
+        }
+      }
+  }
+}
+// y-faces: thread = (block of 2^nd fine columns, even fine row j).  Coarse face (ic, jc) sums fine faces (ic*r + k, jc*r).
+__global__ void __launch_bounds__(256) k_avg_face_multi_y(const double* __restrict__ f, int pitchF, int nx, int ny, AvgMulti a) {
+  const int R = 1 << a.nd;
+  int i0 = (blockIdx.x * blockDim.x + threadIdx.x) * R;
+  int j = 2 * (blockIdx.y * blockDim.y + threadIdx.y);
+  if (i0 >= nx || j > ny) return;
+  int nact = j == 0 ? a.nd : min(a.nd, __ffs(j) - 1);
+  double s[5] = {0.0, 0.0, 0.0, 0.0, 0.0};
+  const double* row = f + (size_t)j * pitchF;
+  for (int k = 0; k < R; k++) {
+    int i = i0 + k;
+    if (i >= nx) break;
+    double v = row[i];
+#pragma unroll
+    for (int d = 0; d < 5; d++)
+      if (d < nact) {
+        s[d] = s[d] + v;
+        const int r = 2 << d;
+        if (((k + 1) & (r - 1)) == 0) {
+          a.c[d][(size_t)(j >> (d + 1)) * a.pitch[d] + (i >> (d + 1))] = s[d] / (double)r;
+          s[d] = 0.0;
+        }
+      }
+  }
+}
+
 // ------------------------------------------------------------------------------------------------
 // vector ops over the valid region (LevelDataOps)
 // ------------------------------------------------------------------------------------------------
