@@ -247,6 +247,7 @@ def main():
     ap.add_argument("--relax-mode", type=int, default=1)
     ap.add_argument("--no-amr", action="store_true", help="skip the 3-level AMR leg (N = 1 only)")
     ap.add_argument("--amr-cycles", type=int, default=3)
+    ap.add_argument("--tune", action="append", default=[], metavar="KEY=VALUE", help="experiment knob passed to sg_set_tuning")
     ap.add_argument("--no-gap", action="store_true", help="skip the implicit gap-height solve leg (N = 1 only)")
     args = ap.parse_args()
 
@@ -273,6 +274,9 @@ def main():
         uid = obj[0]
     ctx = amr.Context(device=local_rank, rank=rank, nranks=world, nccl_unique_id=uid)
     ctx.set_relax_mode(args.relax_mode)
+    for kv in args.tune:
+        k, v = kv.split("=")
+        ctx.set_tuning(int(k), int(v))
 
     def barrier():
         ctx.sync()

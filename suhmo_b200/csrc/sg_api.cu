@@ -1374,15 +1374,32 @@ static int apply_impl(sg_op* op, sg_field* out, sg_field* phi, const sg_field* r
   SGCALL(phys_bc(phi, &op->bc, op->dx, homogeneous));
   if (has_ghost_sides(L)) SGCALL(fill_ghosts(phi, 1));
   unsigned long long* nb = reinterpret_cast<unsigned long long*>(c->d_scalar) + slot;
-  dim3 g = grid2(L->nx, L->ny, B2D);
-  if (mode == 0) LAUNCH(c, k_apply<0>, g, B2D, out->p(), phi->p(), nullptr, a, nb);
-  else if (mode == 1) LAUNCH(c, k_apply<1>, g, B2D, out->p(), phi->p(), rhs->p(), a, nb);
-  else if (mode == 4) LAUNCH(c, k_apply<4>, g, B2D, out->p(), phi->p(), nullptr, a, nb);
+  // 32 x 32 cells per block on large levels; tune key 4 = 1 forces the 32 x 8 shape, 100*bx + rows picks (bx, 256/bx) threads x rows
+  // measured at 8192^2 (tools/apply_bench.py): 64 x 64 cells per block (16 rows per thread) 0.715 ms vs 0.80 ms for 32 x 8
+  const bool tall = L->ny >= 256 && c->tune[4] != 1; // key 4 = 1: plain 32 x 8 blocks, one row per thread
+  const bool big = tall && (long long)(L->nx / 64) * (L->ny / 64) >= 8LL * c->num_sms;
+  int bx = big ? 64 : 32, rows = big ? 16 : tall ? 4 : 1;
+  if (tall && c->tune[4] >= 100) { bx = c->tune[4] / 100; rows = c->tune[4] % 100; }
+  dim3 blk(bx, 256 / bx);
+  dim3 g((L->nx + bx - 1) / bx, (L->ny + blk.y * rows - 1) / (blk.y * rows));
+#define APPLY_LAUNCH(M, ...)                                                     \
+  do {                                                                           \
+    if (rows == 1) LAUNCH(c, (k_apply<M, 1>), g, blk, __VA_ARGS__);              \
+    else if (rows == 4) LAUNCH(c, (k_apply<M, 4>), g, blk, __VA_ARGS__);         \
+    else if (rows == 8) LAUNCH(c, (k_apply<M, 8>), g, blk, __VA_ARGS__);         \
+    else if (rows == 16) LAUNCH(c, (k_apply<M, 16>), g, blk, __VA_ARGS__);       \
+    else if (rows == 32) LAUNCH(c, (k_apply<M, 32>), g, blk, __VA_ARGS__);       \
+    else return fail(SG_ERR_INVALID, "tune key 4: rows per thread must be 1, 4, 8, 16 or 32"); \
+  } while (0)
+  if (mode == 0) APPLY_LAUNCH(0, out->p(), phi->p(), nullptr, a, nb);
+  else if (mode == 1) APPLY_LAUNCH(1, out->p(), phi->p(), rhs->p(), a, nb);
+  else if (mode == 4) APPLY_LAUNCH(4, out->p(), phi->p(), nullptr, a, nb);
   else {
     CK(cudaMemsetAsync(nb, 0, sizeof(double), c->stream));
-    if (mode == 3) LAUNCH(c, k_apply<3>, g, B2D, nullptr, phi->p(), rhs->p(), a, nb);
-    else LAUNCH(c, k_apply<2>, g, B2D, out->p(), phi->p(), rhs->p(), a, nb);
+    if (mode == 3) APPLY_LAUNCH(3, nullptr, phi->p(), rhs->p(), a, nb);
+    else APPLY_LAUNCH(2, out->p(), phi->p(), rhs->p(), a, nb);
   }
+#undef APPLY_LAUNCH
   return SG_OK;
 }
 
@@ -1420,7 +1437,7 @@ extern "C" int sg_op_applyOpNoBoundary(sg_op* op, sg_field* lhs, sg_field* phi) 
   if (!L->fast) return apply_g(op, lhs, phi, nullptr, 0, 0, 0, false);
   OpArgs a = make_args(op);
   if (has_ghost_sides(L)) SGCALL(fill_ghosts(phi, 1));
-  LAUNCH(op->ctx, k_apply<0>, grid2(L->nx, L->ny, B2D), B2D, lhs->p(), phi->p(), nullptr, a, nullptr);
+  LAUNCH(op->ctx, (k_apply<0, 1>), grid2(L->nx, L->ny, B2D), B2D, lhs->p(), phi->p(), nullptr, a, nullptr);
   return SG_OK;
 }
 
@@ -1439,9 +1456,22 @@ static int restrict_impl(sg_op* op, sg_field* resC, sg_field* phiC, sg_field* ph
     CK(cudaMemsetAsync(resC->base, 0, resC->comp_stride * sizeof(double), c->stream)); // res.setVal(0.0)
   }
   if (phiC) CK(cudaMemsetAsync(phiC->base, 0, phiC->comp_stride * sizeof(double), c->stream)); // phiCoarse.setVal(0.0)
-  dim3 g = grid2(Lc->nx, Lc->ny, B2D);
-  if (phiC) LAUNCH(c, k_restrict<1>, g, B2D, resC ? resC->p() : nullptr, phiC->p(), saveC ? saveC->p() : nullptr, Lc->pitch, phiF->p(), rhsF ? rhsF->p() : nullptr, a);
-  else LAUNCH(c, k_restrict<0>, g, B2D, resC->p(), nullptr, nullptr, Lc->pitch, phiF->p(), rhsF->p(), a);
+  // large levels: 4 coarse rows per thread (tune key 5 = rows per thread: 1, 4, 8 or 16)
+  const bool big = (long long)(Lc->nx / 32) * (Lc->ny / 64) >= 8LL * c->num_sms;
+  const int rows = c->tune[5] > 0 ? c->tune[5] : big ? 4 : 1; // measured at 8192^2: 0.98 ms (1 row) -> 0.72 ms (4 rows), tools/apply_bench.py
+  dim3 g((Lc->nx + 31) / 32, (Lc->ny + 8 * rows - 1) / (8 * rows));
+#define RESTRICT_LAUNCH(R)                                                                                                         \
+  do {                                                                                                                             \
+    if (phiC) LAUNCH(c, (k_restrict<1, R>), g, B2D, resC ? resC->p() : nullptr, phiC->p(), saveC ? saveC->p() : nullptr, Lc->pitch, \
+                     phiF->p(), rhsF ? rhsF->p() : nullptr, a);                                                                      \
+    else LAUNCH(c, (k_restrict<0, R>), g, B2D, resC->p(), nullptr, nullptr, Lc->pitch, phiF->p(), rhsF->p(), a);                    \
+  } while (0)
+  if (rows == 1) RESTRICT_LAUNCH(1);
+  else if (rows == 4) RESTRICT_LAUNCH(4);
+  else if (rows == 8) RESTRICT_LAUNCH(8);
+  else if (rows == 16) RESTRICT_LAUNCH(16);
+  else return fail(SG_ERR_INVALID, "tune key 5: rows per thread must be 1, 4, 8 or 16");
+#undef RESTRICT_LAUNCH
   return SG_OK;
 }
 extern "C" int sg_op_restrictResidual(sg_op* op, sg_field* res_coarse, sg_field* phi_fine, const sg_field* phi_coarse,

@@ -847,64 +847,77 @@ __device__ __forceinline__ void block_max_to_global(double v, unsigned long long
   }
 }
 
-template <int MODE>
+template <int MODE, int ROWS>
 __global__ void __launch_bounds__(256) k_apply(double* __restrict__ out, const double* __restrict__ phi,
                                                const double* __restrict__ rhs, OpArgs a, unsigned long long* norm_bits) {
+  // a block covers blockDim.x columns x blockDim.y*ROWS rows (ROWS > 1: fewer blocks and, for the norm modes, fewer
+  // same-address atomics)
   int i = blockIdx.x * blockDim.x + threadIdx.x;
-  int j = blockIdx.y * blockDim.y + threadIdx.y;
-  double r = 0.0;
-  if (i < a.g.nx && j < a.g.ny) {
-    size_t o = (size_t)j * a.g.pitch + i;
-    ptrdiff_t P = a.g.pitch;
-    double pc = phi[o], pw = phi[o - 1], pe = phi[o + 1], ps = phi[(ptrdiff_t)o - P], pn = phi[o + P];
-    double bw = a.bX[o], be = a.bX[o + 1], bs = a.bY[o], bn = a.bY[o + P];
-    double ac = a.has_a ? a.aC[o] : 0.0;
-    double nl, dnl;
-    nl_terms(a.prm, pc, a.B[o], a.use_mask ? a.mask[o] : 1.0, a.Pi[o], a.zb[o], nl, dnl);
-    double lof = lofphi_cell(a.alpha, ac, a.beta, pc, pw, pe, ps, pn, bw, be, bs, bn, a.dxi0, a.dxi1, nl);
-    if (MODE == 4) { out[o] = out[o] + 1.0 * lof; }
-    else {
-      r = MODE == 0 ? lof : rhs[o] - (lof);
-      if (MODE != 3) out[o] = r;
+  int jb = blockIdx.y * (blockDim.y * ROWS) + threadIdx.y;
+  double rmax = 0.0;
+#pragma unroll
+  for (int m = 0; m < ROWS; m++) {
+    int j = jb + m * blockDim.y;
+    double r = 0.0;
+    if (i < a.g.nx && j < a.g.ny) {
+      size_t o = (size_t)j * a.g.pitch + i;
+      ptrdiff_t P = a.g.pitch;
+      double pc = phi[o], pw = phi[o - 1], pe = phi[o + 1], ps = phi[(ptrdiff_t)o - P], pn = phi[o + P];
+      double bw = a.bX[o], be = a.bX[o + 1], bs = a.bY[o], bn = a.bY[o + P];
+      double ac = a.has_a ? a.aC[o] : 0.0;
+      double nl, dnl;
+      nl_terms(a.prm, pc, a.B[o], a.use_mask ? a.mask[o] : 1.0, a.Pi[o], a.zb[o], nl, dnl);
+      double lof = lofphi_cell(a.alpha, ac, a.beta, pc, pw, pe, ps, pn, bw, be, bs, bn, a.dxi0, a.dxi1, nl);
+      if (MODE == 4) { out[o] = out[o] + 1.0 * lof; }
+      else {
+        r = MODE == 0 ? lof : rhs[o] - (lof);
+        if (MODE != 3) out[o] = r;
+      }
     }
+    rmax = fmax(rmax, fabs(r));
   }
-  if (MODE == 2 || MODE == 3) block_max_to_global(fabs(r), norm_bits);
+  if (MODE == 2 || MODE == 3) block_max_to_global(rmax, norm_bits);
 }
 
 // restrictResidual + restrictR fused (src/VCAMRNonLinearPoissonOp.cpp:347-460; RESTRICTRESVCNL2D / RESTRICTVCNL,
 // VCAMRNonLinearPoissonOpF.ChF:419-561): one thread per coarse cell, the four fine cells accumulated in the
 // Fortran loop order (i fastest):  acc = 0; acc += v/4 ...
-template <int WITH_PHI>
+template <int WITH_PHI, int ROWS>
 __global__ void __launch_bounds__(256) k_restrict(double* __restrict__ resC, double* __restrict__ phiC, double* __restrict__ saveC, int pitchC,
                                                   const double* __restrict__ phi, const double* __restrict__ rhs, OpArgs a) {
   int ic = blockIdx.x * blockDim.x + threadIdx.x;
-  int jc = blockIdx.y * blockDim.y + threadIdx.y;
-  if (ic >= (a.g.nx >> 1) || jc >= (a.g.ny >> 1)) return;
+  int jb = blockIdx.y * (blockDim.y * ROWS) + threadIdx.y;
+  if (ic >= (a.g.nx >> 1)) return;
   const double denom = 4.0;
-  double acc = 0.0, accp = 0.0;
   ptrdiff_t P = a.g.pitch;
 #pragma unroll
-  for (int jj = 0; jj < 2; jj++)
+  for (int m = 0; m < ROWS; m++) {
+    int jc = jb + m * blockDim.y;
+    if (jc >= (a.g.ny >> 1)) break;
+    double acc = 0.0, accp = 0.0;
 #pragma unroll
-    for (int ii = 0; ii < 2; ii++) {
-      size_t o = (size_t)(2 * jc + jj) * a.g.pitch + (2 * ic + ii);
-      double pc = phi[o];
-      if (resC) {
-        double pw = phi[o - 1], pe = phi[o + 1], ps = phi[(ptrdiff_t)o - P], pn = phi[o + P];
-        double bw = a.bX[o], be = a.bX[o + 1], bs = a.bY[o], bn = a.bY[o + P];
-        double ac = a.has_a ? a.aC[o] : 0.0;
-        double nl, dnl;
-        nl_terms(a.prm, pc, a.B[o], a.use_mask ? a.mask[o] : 1.0, a.Pi[o], a.zb[o], nl, dnl);
-        double lof = lofphi_cell(a.alpha, ac, a.beta, pc, pw, pe, ps, pn, bw, be, bs, bn, a.dxi0, a.dxi1, nl);
-        acc = acc + (rhs[o] - lof) / denom;
+    for (int jj = 0; jj < 2; jj++)
+#pragma unroll
+      for (int ii = 0; ii < 2; ii++) {
+        size_t o = (size_t)(2 * jc + jj) * a.g.pitch + (2 * ic + ii);
+        double pc = phi[o];
+        if (resC) {
+          double pw = phi[o - 1], pe = phi[o + 1], ps = phi[(ptrdiff_t)o - P], pn = phi[o + P];
+          double bw = a.bX[o], be = a.bX[o + 1], bs = a.bY[o], bn = a.bY[o + P];
+          double ac = a.has_a ? a.aC[o] : 0.0;
+          double nl, dnl;
+          nl_terms(a.prm, pc, a.B[o], a.use_mask ? a.mask[o] : 1.0, a.Pi[o], a.zb[o], nl, dnl);
+          double lof = lofphi_cell(a.alpha, ac, a.beta, pc, pw, pe, ps, pn, bw, be, bs, bn, a.dxi0, a.dxi1, nl);
+          acc = acc + (rhs[o] - lof) / denom;
+        }
+        if (WITH_PHI) accp = accp + pc / denom;
       }
-      if (WITH_PHI) accp = accp + pc / denom;
+    size_t oc = (size_t)jc * pitchC + ic;
+    if (resC) resC[oc] = acc;
+    if (WITH_PHI) {
+      phiC[oc] = accp;
+      if (saveC) saveC[oc] = accp; // the driver's assignLocal(saved, phiCoarse), valid cells
     }
-  size_t oc = (size_t)jc * pitchC + ic;
-  if (resC) resC[oc] = acc;
-  if (WITH_PHI) {
-    phiC[oc] = accp;
-    if (saveC) saveC[oc] = accp; // the driver's assignLocal(saved, phiCoarse), valid cells
   }
 }
 
