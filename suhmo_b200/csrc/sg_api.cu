@@ -878,39 +878,58 @@ extern "C" int sg_field_device_view(sg_field* f, void** base, long long* pitch, 
 // ghosts that come from other valid cells of the level: periodic images inside the patch, neighbouring ranks.
 // depth <= 2.  Replaces LevelData::exchange (the in-patch box-to-box part needs no copy at all: boxes of one
 // rank are merged into one array).
-static int fill_ghosts(sg_field* f, int depth) {
-  sg_layout* L = f->lay;
-  sg_ctx* c = L->ctx;
-  if (!L->has_local) return SG_OK;
-  Geom g = make_geom(L, nullptr);
-  int ex = f->cent == SG_XFACE, ey = f->cent == SG_YFACE;
-  for (int comp = 0; comp < f->ncomp; comp++) {
-    double* p = f->p(comp);
-    if (L->wrap_local[0]) {
-      int n = (g.ny + ey) * depth;
-      LAUNCH(c, k_wrap_ghost, (n + 127) / 128, 128, p, g, 0, depth, ex, ey);
+// Ghost cells on SK_GHOST sides of one-patch levels: periodic images inside the patch by a wrap kernel, rows owned by the
+// neighbouring ranks by ncclSend/ncclRecv.  Several (field, depth) requests share ONE NCCL group (one fused transfer kernel per
+// peer instead of one per field): the V-cycle is latency-bound on these exchanges at N > 1.
+struct GhostReq { sg_field* f; int depth; };
+static int fill_ghosts_multi(sg_ctx* c, const GhostReq* reqs, int n) {
+  bool any_nccl = false;
+  for (int q = 0; q < n; q++) {
+    sg_field* f = reqs[q].f;
+    const int depth = reqs[q].depth;
+    sg_layout* L = f->lay;
+    if (!L->has_local) continue;
+    Geom g = make_geom(L, nullptr);
+    int ex = f->cent == SG_XFACE, ey = f->cent == SG_YFACE;
+    for (int comp = 0; comp < f->ncomp; comp++) {
+      double* p = f->p(comp);
+      if (L->wrap_local[0]) {
+        int m = (g.ny + ey) * depth;
+        LAUNCH(c, k_wrap_ghost, (m + 127) / 128, 128, p, g, 0, depth, ex, ey);
+      }
+      if (L->wrap_local[1]) {
+        int m = (g.nx + 2 * depth + ex) * depth;
+        LAUNCH(c, k_wrap_ghost, (m + 127) / 128, 128, p, g, 1, depth, ex, ey);
+      }
     }
-    if (L->wrap_local[1]) {
-      int n = (g.nx + 2 * depth + ex) * depth;
-      LAUNCH(c, k_wrap_ghost, (n + 127) / 128, 128, p, g, 1, depth, ex, ey);
-    }
+    any_nccl |= (L->nbr[2] >= 0 || L->nbr[3] >= 0);
   }
-  if (L->nbr[2] >= 0 || L->nbr[3] >= 0) {
+  if (!any_nccl) return SG_OK;
+  SGCALL(c->nccl.group_start(g_err));
+  for (int q = 0; q < n; q++) {
+    sg_field* f = reqs[q].f;
+    const int depth = reqs[q].depth;
+    sg_layout* L = f->lay;
+    if (!L->has_local || (L->nbr[2] < 0 && L->nbr[3] < 0)) continue;
+    const int ny = L->ny, ey = f->cent == SG_YFACE;
     // rows are contiguous (x fastest, full pitch incl. ghost columns): send/recv straight from the field
     size_t cnt = (size_t)depth * L->pitch;
     for (int comp = 0; comp < f->ncomp; comp++) {
       double* p = f->p(comp) - SG_XOFF;
-      SGCALL(c->nccl.group_start(g_err));
       // receives are posted high-side first so that, when both neighbours are the same rank (2 ranks, periodic),
       // the peer's [low send, high send] order pairs with [high recv, low recv] here
-      if (L->nbr[3] >= 0) SGCALL(c->nccl.recv(p + (ptrdiff_t)(g.ny + ey) * L->pitch, cnt, L->nbr[3], c->stream, g_err));
+      if (L->nbr[3] >= 0) SGCALL(c->nccl.recv(p + (ptrdiff_t)(ny + ey) * L->pitch, cnt, L->nbr[3], c->stream, g_err));
       if (L->nbr[2] >= 0) SGCALL(c->nccl.recv(p + (ptrdiff_t)(-depth) * L->pitch, cnt, L->nbr[2], c->stream, g_err));
       if (L->nbr[2] >= 0) SGCALL(c->nccl.send(p + (ptrdiff_t)ey * L->pitch, cnt, L->nbr[2], c->stream, g_err));
-      if (L->nbr[3] >= 0) SGCALL(c->nccl.send(p + (ptrdiff_t)(g.ny - depth) * L->pitch, cnt, L->nbr[3], c->stream, g_err));
-      SGCALL(c->nccl.group_end(g_err));
+      if (L->nbr[3] >= 0) SGCALL(c->nccl.send(p + (ptrdiff_t)(ny - depth) * L->pitch, cnt, L->nbr[3], c->stream, g_err));
     }
   }
+  SGCALL(c->nccl.group_end(g_err));
   return SG_OK;
+}
+static int fill_ghosts(sg_field* f, int depth) {
+  GhostReq r{f, depth};
+  return fill_ghosts_multi(f->lay->ctx, &r, 1);
 }
 static bool has_ghost_sides(const sg_layout* L) { return L->side_ghost[0] || L->side_ghost[1] || L->side_ghost[2] || L->side_ghost[3]; }
 
@@ -1078,19 +1097,13 @@ extern "C" int sg_factory_refToFiner(const sg_factory* f, int level, int* out) {
 }
 
 // coefficient ghosts on SK_GHOST sides (periodic images / neighbouring ranks): depth 1, needed by the fused sweep
+static int coef_ghost_depth(const sg_op* op) { return std::min(8, std::min(op->lay->nx, op->lay->ny)); }
 static int coef_ghosts(sg_op* op, bool only_b) {
   if (!has_ghost_sides(op->lay)) return SG_OK;
   // depth 8: communication-avoiding relaxation updates up to 6 ghost rows (+ ring) on SK_GHOST sides; tiny levels get less
-  const int d = std::min(8, std::min(op->lay->nx, op->lay->ny));
-  SGCALL(fill_ghosts(op->bX, d));
-  SGCALL(fill_ghosts(op->bY, d));
-  if (only_b) return SG_OK;
-  SGCALL(fill_ghosts(op->B, d));
-  SGCALL(fill_ghosts(op->Pi, d));
-  SGCALL(fill_ghosts(op->zb, d));
-  SGCALL(fill_ghosts(op->mask, d));
-  if (op->alpha != 0.0) SGCALL(fill_ghosts(op->aCoef, d));
-  return SG_OK;
+  const int d = coef_ghost_depth(op);
+  GhostReq r[7] = {{op->bX, d}, {op->bY, d}, {op->B, d}, {op->Pi, d}, {op->zb, d}, {op->mask, d}, {op->aCoef, d}};
+  return fill_ghosts_multi(op->ctx, r, only_b ? 2 : (op->alpha != 0.0 ? 7 : 6));
 }
 
 // The ice mask only enters the operator through COMPUTENONLINEARTERMS' test `mask < 0` (src/AmrHydroF.ChF:40).  Levels
@@ -1233,7 +1246,9 @@ static int check_same(const sg_op* op, const sg_field* f, const char* what) {
 // one levelGSRB iteration set
 // trailing == false: the caller refills every ghost cell before its next read (the V-cycle driver does: restriction, residual
 // and UpdateOperator all start with BC + exchange), so levelGSRB's closing exchange + homogeneous BC fill are dead stores
-static int relax_impl(sg_op* op, sg_field* phi, const sg_field* rhs, int iterations, bool trailing = true) {
+// phi_valid: depth to which the caller has just exchanged phi's ghost rows (0: unknown); the first sweep's exchange is skipped when
+// that covers it
+static int relax_impl(sg_op* op, sg_field* phi, const sg_field* rhs, int iterations, bool trailing = true, int phi_valid = 0) {
   sg_layout* L = op->lay;
   sg_ctx* c = op->ctx;
   if (!L->has_local || iterations <= 0) return SG_OK;
@@ -1247,7 +1262,14 @@ static int relax_impl(sg_op* op, sg_field* phi, const sg_field* rhs, int iterati
     SGCALL(ws_field(L, 0, 1, &scratch));
     // temporal blocking recomputes a 4-cell ring: periodic images inside the patch must then be at least 4 cells away
     const bool can2 = (c->relax_mode == 3 || c->relax_mode == 4) && (!L->wrap_local[0] || L->nx >= 4) && (!L->wrap_local[1] || L->ny >= 4) && L->ny >= 4;
-    if (ghosts) SGCALL(fill_ghosts(const_cast<sg_field*>(rhs), can2 ? 3 : 1));
+    // Communication-avoiding relaxation (mode 1): instead of exchanging two ghost rows before every sweep, exchange 2k rows
+    // once per k <= 4 sweeps and let sweep s also update the ghost rows it still needs (2(k-1-s) per side) -- the same
+    // arithmetic on the same values as their owner performs, so the result is unchanged while the NCCL (or wrap) calls drop
+    // k-fold.  Needs ghost sides in y only and enough rows on both sides of the cut.
+    const bool ygh_lo = L->side_ghost[2], ygh_hi = L->side_ghost[3];
+    const bool wide = c->relax_mode == 1 && c->tune[3] == 0 && (ygh_lo || ygh_hi) && !L->side_ghost[0] && !L->side_ghost[1] && L->ny >= 16;
+    bool rhs_pending = ghosts; // the right-hand side's ghost rows travel in the same NCCL group as the first exchange of phi
+    const int rhs_depth = wide ? 7 : can2 ? 3 : 1;
     FusedArgs f;
     f.a = a;
     f.rhs = rhs->p();
@@ -1288,20 +1310,19 @@ static int relax_impl(sg_op* op, sg_field* phi, const sg_field* rhs, int iterati
       if (kind == 4) return (f.nstrips * f.nsegs + 1) / 2; // two pairs per CTA
       return (f.nstrips * f.nsegs * 32 + 127) / 128;
     };
-    // Communication-avoiding relaxation (mode 1): instead of exchanging two ghost rows before every sweep, exchange 2k rows
-    // once per k <= 4 sweeps and let sweep s also update the ghost rows it still needs (2(k-1-s) per side) -- the same
-    // arithmetic on the same values as their owner performs, so the result is unchanged while the NCCL (or wrap) calls drop
-    // k-fold.  Needs ghost sides in y only and enough rows on both sides of the cut.
-    const bool ygh_lo = L->side_ghost[2], ygh_hi = L->side_ghost[3];
-    const bool wide = c->relax_mode == 1 && c->tune[3] == 0 && (ygh_lo || ygh_hi) && !L->side_ghost[0] && !L->side_ghost[1] && L->ny >= 16;
-    if (wide && ghosts) SGCALL(fill_ghosts(const_cast<sg_field*>(rhs), 7));
     f.ylo = 0; f.yhi = L->ny;
     int it = 0;
     while (it < iterations) {
       const bool two = can2 && it + 2 <= iterations;
       const int kind = two ? (c->relax_mode == 4 ? 4 : 3) : (c->relax_mode == 2 ? 2 : 1);
       const int chunk = (wide && kind == 1) ? std::min(4, iterations - it) : 1;
-      if (ghosts) SGCALL(fill_ghosts(phi, two ? 4 : 2 * chunk));
+      if (ghosts) {
+        const int need = two ? 4 : 2 * chunk;
+        GhostReq r[2] = {{phi, need}, {const_cast<sg_field*>(rhs), rhs_depth}};
+        if (it == 0 && phi_valid >= need) { if (rhs_pending) SGCALL(fill_ghosts_multi(c, r + 1, 1)); }
+        else SGCALL(fill_ghosts_multi(c, r, rhs_pending ? 2 : 1));
+        rhs_pending = false;
+      }
       for (int sub = 0; sub < chunk; sub++) {
         const int ext = 2 * (chunk - 1 - sub);
         f.ylo = ygh_lo ? -ext : 0;
@@ -1362,7 +1383,7 @@ extern "C" int sg_op_relaxNF(sg_op* op, sg_field* phi, const sg_field* phi_coars
 }
 
 // BC -> exchange -> (NL fused) kernel; mode 0 apply, 1 residual, 2 residual + max-norm into d_scalar[slot]
-static int apply_impl(sg_op* op, sg_field* out, sg_field* phi, const sg_field* rhs, int homogeneous, int mode, int slot) {
+static int apply_impl(sg_op* op, sg_field* out, sg_field* phi, const sg_field* rhs, int homogeneous, int mode, int slot, int ghost_depth = 1) {
   sg_layout* L = op->lay;
   sg_ctx* c = op->ctx;
   if (!L->has_local) return SG_OK;
@@ -1372,7 +1393,7 @@ static int apply_impl(sg_op* op, sg_field* out, sg_field* phi, const sg_field* r
   }
   OpArgs a = make_args(op);
   SGCALL(phys_bc(phi, &op->bc, op->dx, homogeneous));
-  if (has_ghost_sides(L)) SGCALL(fill_ghosts(phi, 1));
+  if (has_ghost_sides(L)) SGCALL(fill_ghosts(phi, ghost_depth));
   unsigned long long* nb = reinterpret_cast<unsigned long long*>(c->d_scalar) + slot;
   // 32 x 32 cells per block on large levels; tune key 4 = 1 forces the 32 x 8 shape, 100*bx + rows picks (bx, 256/bx) threads x rows
   // measured at 8192^2 (tools/apply_bench.py): 64 x 64 cells per block (16 rows per thread) 0.715 ms vs 0.80 ms for 32 x 8
@@ -1878,24 +1899,33 @@ static int average_all_depths(sg_solver* s) {
       LAUNCH(s->ctx, k_avg_face_multi_y, dim3(((L->nx + R - 1) / R + 31) / 32, ((L->ny / 2 + 1) + 7) / 8), B2D, op0->bY->p(), L->pitch, L->nx, L->ny, ay);
     }
   }
+  // coefficient ghost rows of every depth in one NCCL group (AverageOperator's coef_ghosts, batched)
+  std::vector<GhostReq> reqs;
+  for (int d = 1; d <= nd; d++)
+    if (has_ghost_sides(s->ops[d]->lay)) {
+      reqs.push_back({s->ops[d]->bX, coef_ghost_depth(s->ops[d])});
+      reqs.push_back({s->ops[d]->bY, coef_ghost_depth(s->ops[d])});
+    }
+  if (!reqs.empty()) SGCALL(fill_ghosts_multi(s->ctx, reqs.data(), (int)reqs.size()));
   s->coefs_averaged = true;
   return SG_OK;
 }
-static int mg_cycle(sg_solver* s, int depth, sg_field* phi, sg_field* rhs, const sg_solver_params* sp) {
+static int mg_cycle(sg_solver* s, int depth, sg_field* phi, sg_field* rhs, const sg_solver_params* sp, int phi_valid = 0) {
   sg_op* op = s->ops[depth];
   int nd = (int)s->ops.size();
-  if (depth == nd - 1) return relax_impl(op, phi, rhs, sp->bottom, false);
-  SGCALL(relax_impl(op, phi, rhs, sp->pre, false));
+  if (depth == nd - 1) return relax_impl(op, phi, rhs, sp->bottom, false, phi_valid);
+  SGCALL(relax_impl(op, phi, rhs, sp->pre, false, phi_valid));
   int dc = depth + 1;
   sg_op* opc = s->ops[dc];
   if (op->update_operator) {
-    if (s->coefs_averaged) SGCALL(coef_ghosts(opc, true));
-    else SGCALL(sg_op_AverageOperator(opc, s->ops[0], dc));
+    if (!s->coefs_averaged) SGCALL(sg_op_AverageOperator(opc, s->ops[0], dc)); // else: averaged and ghost-filled by average_all_depths
   }
   // restrictR + restrictResidual in one sweep over the fine level
   SGCALL(restrict_impl(op, s->rhs[dc], s->phi[dc], phi, rhs, s->save[dc]));              // ... and assignLocal(saved, phiC)
-  SGCALL(apply_impl(opc, s->rhs[dc], s->phi[dc], nullptr, 0, 4, 0));                     // rhsC += applyOpMg(phiC, NULL, false)
-  SGCALL(mg_cycle(s, dc, s->phi[dc], s->rhs[dc], sp));
+  // rhsC += applyOpMg(phiC, NULL, false); phiC's ghost rows are exchanged deep enough for the first sweeps of the coarse relax
+  const int gd = std::min(8, std::min(opc->lay->nx, opc->lay->ny));
+  SGCALL(apply_impl(opc, s->rhs[dc], s->phi[dc], nullptr, 0, 4, 0, gd));
+  SGCALL(mg_cycle(s, dc, s->phi[dc], s->rhs[dc], sp, gd));
   if (op->lay->has_local) {                                                             // phi += I(phiC_new - phiC_saved)
     sg_layout* L = op->lay;
     LAUNCH(s->ctx, k_prolong, grid2(L->nx, L->ny, B2D), B2D, phi->p(), L->pitch, L->nx, L->ny, s->phi[dc]->p(), s->save[dc]->p(), opc->lay->pitch);
