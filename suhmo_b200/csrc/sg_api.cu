@@ -67,6 +67,7 @@ struct sg_ctx {
   bool own_stream = true;
   long long launches = 0;
   int relax_mode = 1;
+  bool smem_attr_set = false; // dynamic shared-memory opt-in of the streaming kernels done for this context's device
   int tune[8] = {0, 0, 0, 0, 0, 0, 0, 0}; // experiment knobs (sg_set_tuning): 0 rows per warp, 1 CTAs per SM of the fused sweep
   SgNccl nccl;
   // reduction scratch
@@ -1274,8 +1275,7 @@ static int relax_impl(sg_op* op, sg_field* phi, const sg_field* rhs, int iterati
     f.a = a;
     f.rhs = rhs->p();
     f.sdx[0] = -op->dx[0]; f.sdx[1] = op->dx[0]; f.sdx[2] = -op->dx[1]; f.sdx[3] = op->dx[1];
-    static bool attr_set = false;
-    if (!attr_set) {
+    if (!c->smem_attr_set) {
       // warp-private staging rings: 4 warps x stages x (8|9) arrays x 32 lanes x 16 B
       CK(cudaFuncSetAttribute(k_gsrb_stream<0, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 * GS_STAGES * 8 * 512));
       CK(cudaFuncSetAttribute(k_gsrb_stream<1, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 * GS_STAGES * 9 * 512));
@@ -1283,7 +1283,7 @@ static int relax_impl(sg_op* op, sg_field* phi, const sg_field* rhs, int iterati
       CK(cudaFuncSetAttribute(k_gsrb_stream2<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 * GS2_STAGES * 9 * 512));
       CK(cudaFuncSetAttribute(k_gsrb_pair<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * (GP_STAGES * 8 * 512 + 1024)));
       CK(cudaFuncSetAttribute(k_gsrb_pair<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * (GP_STAGES * 9 * 512 + 1024)));
-      attr_set = true;
+      c->smem_attr_set = true;
     }
     // Segments of rows per warp.  Measured on B200 (tools/relax_bench.py): many short segments beat one resident wave
     // (warps marching in lock-step), 32-64 rows per warp is the plateau on HBM-sized levels, and L2-resident levels want
