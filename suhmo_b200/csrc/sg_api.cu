@@ -272,9 +272,12 @@ extern "C" int sg_ctx_create(sg_ctx** out, int device, int rank, int nranks, con
   *out = c;
   return SG_OK;
 }
+struct sg_layout;
+static void gap_cache_forget(const sg_ctx* ctx, const sg_layout* L);
 extern "C" int sg_ctx_destroy(sg_ctx* c) {
   if (!c) return SG_OK;
   cudaSetDevice(c->device);
+  gap_cache_forget(c, nullptr); // cached implicit gap-height solvers own device fields on this context
   cudaStreamSynchronize(c->stream);
   c->nccl.destroy();
   cudaFree(c->d_partial); cudaFree(c->d_scalar); cudaFreeHost(c->h_scalar);
@@ -618,9 +621,11 @@ extern "C" int sg_layout_nbox(const sg_layout* L, int* nbox) {
 }
 extern "C" int sg_field_destroy(sg_field* f);
 static void copy_plans_forget(const sg_layout* L);
+static void gap_cache_forget(const sg_ctx* ctx, const sg_layout* L);
 static void plan_free(sg_layout::Plan& P);
 extern "C" int sg_layout_destroy(sg_layout* L) {
   if (!L) return SG_OK;
+  gap_cache_forget(nullptr, L);
   for (sg_field* w : L->ws) sg_field_destroy(w);
   copy_plans_forget(L);
   cudaFree(L->d_patches);

@@ -121,3 +121,24 @@ def test_unsupported_shapes(gpu_ctx):
     with pytest.raises(SuhmoGpuError) as e:
         gpu.solver.relax(gpu.new(1, 1), gpu.F["rhs"], 1)   # coarse field handed to depth 0
     assert e.value.code == ERR_INVALID
+
+
+def test_repeated_calls_reuse_the_solver(gpu_ctx):
+    """sg_solve_for_gap keeps factory + solver per (grids, coefficient fields) and refreshes them: a second call with another dt
+    and changed diffusion coefficients must equal a fresh oracle solve"""
+    cfg, orc, gpu = make(gpu_ctx, "C2", 2)
+    sp = ob.make_solver_params(pre=2, post=2, bottom=4, max_iter=100, imin=5, iter_min=2, eps=1e-7, hang=1e-6, norm_thresh=1e-7)
+    for rep, (scale, dtf) in enumerate([(1.0, 1.0), (0.5, 3.0), (2.0, 0.25)]):
+        # change D on both sides, keep the same device fields (same handles -> cache hit)
+        for k in ("bX", "bY"):
+            a = orc.g[k] * scale
+            orc.F[k].set_global(a, (0, 0))
+            gpu.push(gpu.F[k], orc.F[k])
+        beta = orc.beta * dtf
+        osol = ob.LinSolver(orc.layout, orc.dx, 1.0, beta, orc.F["a"], orc.F["bX"], orc.F["bY"])
+        oit, ohist = osol.solve(orc.F["b"], orc.F["rhs"], sp)
+        osol.free()
+        git, ghist, st = gpu.amr.SolveForGap_nl(gpu_ctx, [gpu.layout], [gpu.F["a"]], [gpu.F["bX"]], [gpu.F["bY"]], [], (orc.dx, orc.dx),
+                                                [gpu.F["b"]], [gpu.F["rhs"]], beta, 1.0, 100)
+        assert git == oit and np.array_equal(ghist, ohist), (rep, git, oit)
+        same(gpu.F["b"], orc.F["b"], f"gap height, call {rep}")
