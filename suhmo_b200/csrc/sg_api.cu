@@ -1901,7 +1901,7 @@ static int average_all_depths(sg_solver* s) {
       }
       const int R = 1 << ax.nd;
       LAUNCH(s->ctx, k_avg_face_multi_x, dim3(((L->nx / 2 + 1) + 127) / 128, (L->ny + R - 1) / R), 128, op0->bX->p(), L->pitch, L->nx, L->ny, ax);
-      LAUNCH(s->ctx, k_avg_face_multi_y, dim3(((L->nx + R - 1) / R + 31) / 32, ((L->ny / 2 + 1) + 7) / 8), B2D, op0->bY->p(), L->pitch, L->nx, L->ny, ay);
+      LAUNCH(s->ctx, k_avg_face_multi_y, dim3((L->nx + 255) / 256, ((L->ny / 2 + 1) + AVGY_ROWS - 1) / AVGY_ROWS), 256, op0->bY->p(), L->pitch, L->nx, L->ny, ay);
     }
   }
   // coefficient ghost rows of every depth in one NCCL group (AverageOperator's coef_ghosts, batched)

@@ -1101,29 +1101,31 @@ __global__ void __launch_bounds__(128) k_avg_face_multi_x(const double* __restri
       }
   }
 }
-// y-faces: thread = (block of 2^nd fine columns, even fine row j).  Coarse face (ic, jc) sums fine faces (ic*r + k, jc*r).
+// y-faces: coarse face (ic, jc) sums fine faces (ic*r + k, jc*r).  A block stages 256 columns of an even fine row in shared memory
+// (coalesced), then thread t produces one output of one depth (128 + 64 + 32 + 16 + 8 outputs per row segment), summing its r
+// values in order; 8 even rows per block.
+#define AVGY_ROWS 8
 __global__ void __launch_bounds__(256) k_avg_face_multi_y(const double* __restrict__ f, int pitchF, int nx, int ny, AvgMulti a) {
-  const int R = 1 << a.nd;
-  int i0 = (blockIdx.x * blockDim.x + threadIdx.x) * R;
-  int j = 2 * (blockIdx.y * blockDim.y + threadIdx.y);
-  if (i0 >= nx || j > ny) return;
-  int nact = j == 0 ? a.nd : min(a.nd, __ffs(j) - 1);
-  double s[5] = {0.0, 0.0, 0.0, 0.0, 0.0};
-  const double* row = f + (size_t)j * pitchF;
-  for (int k = 0; k < R; k++) {
-    int i = i0 + k;
-    if (i >= nx) break;
-    double v = row[i];
-#pragma unroll
-    for (int d = 0; d < 5; d++)
-      if (d < nact) {
-        s[d] = s[d] + v;
-        const int r = 2 << d;
-        if (((k + 1) & (r - 1)) == 0) {
-          a.c[d][(size_t)(j >> (d + 1)) * a.pitch[d] + (i >> (d + 1))] = s[d] / (double)r;
-          s[d] = 0.0;
-        }
-      }
+  __shared__ double row[256];
+  const int t = threadIdx.x, i0 = blockIdx.x * 256;
+  int d = -1, icl = 0;
+  for (int dd = 0, base = 0, cnt = 128; dd < a.nd; dd++, base += cnt, cnt >>= 1)
+    if (t >= base && t < base + cnt) { d = dd; icl = t - base; }
+  for (int m = 0; m < AVGY_ROWS; m++) {
+    const int j = 2 * (blockIdx.y * AVGY_ROWS + m);
+    if (j > ny) break; // uniform over the block
+    __syncthreads();
+    row[t] = i0 + t < nx ? f[(size_t)j * pitchF + i0 + t] : 0.0;
+    __syncthreads();
+    if (d < 0) continue;
+    const int r = 2 << d;
+    const int nact = j == 0 ? a.nd : min(a.nd, __ffs(j) - 1);
+    const int i = i0 + icl * r;
+    if (d < nact && i < nx) {
+      double s = 0.0;
+      for (int k = 0; k < r; k++) s = s + row[icl * r + k];
+      a.c[d][(size_t)(j >> (d + 1)) * a.pitch[d] + (i >> (d + 1))] = s / (double)r;
+    }
   }
 }
 
