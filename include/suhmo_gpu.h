@@ -325,7 +325,8 @@ int sg_set_relax_mode(sg_ctx* ctx, int mode);
    the register-only sweep; key 2: 1 = do not capture V-cycles into CUDA graphs; key 3: 1 = exchange ghost rows before every sweep instead of once
    per four (communication-avoiding relaxation off); key 4: block shape of the residual/applyOp kernel, 1 = 32x8 threads with one
    row per thread, 100*bx + rows = (bx, 256/bx) threads x rows per thread (rows 1|4|8|16|32); key 5: coarse rows per thread of the
-   restriction kernel (1|4|8|16) */
+   restriction kernel (1|4|8|16); key 6: 1 = halo exchanges of the smoother stay on the main stream (no overlap with the interior
+   part of the sweep; N > 1 only) */
 int sg_set_tuning(sg_ctx* ctx, int key, int value);
 
 /* ------------------------------------------------------------------ implicit gap-height solve ------------- */

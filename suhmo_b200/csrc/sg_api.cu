@@ -68,6 +68,8 @@ struct sg_ctx {
   long long launches = 0;
   int relax_mode = 1;
   bool smem_attr_set = false; // dynamic shared-memory opt-in of the streaming kernels done for this context's device
+  cudaStream_t comm_stream = nullptr;    // nranks > 1: halo exchanges that overlap the interior part of a sweep run here
+  cudaEvent_t ev_comm[2] = {nullptr, nullptr};
   int tune[8] = {0, 0, 0, 0, 0, 0, 0, 0}; // experiment knobs (sg_set_tuning): 0 rows per warp, 1 CTAs per SM of the fused sweep
   SgNccl nccl;
   // reduction scratch
@@ -268,6 +270,11 @@ extern "C" int sg_ctx_create(sg_ctx** out, int device, int rank, int nranks, con
     REQUIRE(nccl_unique_id, "sg_ctx_create: nranks > 1 needs an NCCL unique id");
     int r = c->nccl.init(nccl_unique_id, rank, nranks, g_err);
     if (r != SG_OK) return r;
+    int lo = 0, hi = 0;
+    CK(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+    CK(cudaStreamCreateWithPriority(&c->comm_stream, cudaStreamNonBlocking, hi));
+    CK(cudaEventCreateWithFlags(&c->ev_comm[0], cudaEventDisableTiming));
+    CK(cudaEventCreateWithFlags(&c->ev_comm[1], cudaEventDisableTiming));
   }
   *out = c;
   return SG_OK;
@@ -279,6 +286,8 @@ extern "C" int sg_ctx_destroy(sg_ctx* c) {
   cudaSetDevice(c->device);
   gap_cache_forget(c, nullptr); // cached implicit gap-height solvers own device fields on this context
   cudaStreamSynchronize(c->stream);
+  if (c->comm_stream) { cudaStreamSynchronize(c->comm_stream); cudaStreamDestroy(c->comm_stream); }
+  for (int k = 0; k < 2; k++) if (c->ev_comm[k]) cudaEventDestroy(c->ev_comm[k]);
   c->nccl.destroy();
   cudaFree(c->d_partial); cudaFree(c->d_scalar); cudaFreeHost(c->h_scalar);
   cudaFreeHost(c->h_stage); cudaFree(c->d_stage); cudaFree(c->d_segs);
@@ -888,7 +897,8 @@ extern "C" int sg_field_device_view(sg_field* f, void** base, long long* pitch, 
 // neighbouring ranks by ncclSend/ncclRecv.  Several (field, depth) requests share ONE NCCL group (one fused transfer kernel per
 // peer instead of one per field): the V-cycle is latency-bound on these exchanges at N > 1.
 struct GhostReq { sg_field* f; int depth; };
-static int fill_ghosts_multi(sg_ctx* c, const GhostReq* reqs, int n) {
+static int fill_ghosts_multi(sg_ctx* c, const GhostReq* reqs, int n, cudaStream_t nccl_stream = nullptr) {
+  if (!nccl_stream) nccl_stream = c->stream; // periodic wraps inside a patch always run on the main stream
   bool any_nccl = false;
   for (int q = 0; q < n; q++) {
     sg_field* f = reqs[q].f;
@@ -924,10 +934,10 @@ static int fill_ghosts_multi(sg_ctx* c, const GhostReq* reqs, int n) {
       double* p = f->p(comp) - SG_XOFF;
       // receives are posted high-side first so that, when both neighbours are the same rank (2 ranks, periodic),
       // the peer's [low send, high send] order pairs with [high recv, low recv] here
-      if (L->nbr[3] >= 0) SGCALL(c->nccl.recv(p + (ptrdiff_t)(ny + ey) * L->pitch, cnt, L->nbr[3], c->stream, g_err));
-      if (L->nbr[2] >= 0) SGCALL(c->nccl.recv(p + (ptrdiff_t)(-depth) * L->pitch, cnt, L->nbr[2], c->stream, g_err));
-      if (L->nbr[2] >= 0) SGCALL(c->nccl.send(p + (ptrdiff_t)ey * L->pitch, cnt, L->nbr[2], c->stream, g_err));
-      if (L->nbr[3] >= 0) SGCALL(c->nccl.send(p + (ptrdiff_t)(ny - depth) * L->pitch, cnt, L->nbr[3], c->stream, g_err));
+      if (L->nbr[3] >= 0) SGCALL(c->nccl.recv(p + (ptrdiff_t)(ny + ey) * L->pitch, cnt, L->nbr[3], nccl_stream, g_err));
+      if (L->nbr[2] >= 0) SGCALL(c->nccl.recv(p + (ptrdiff_t)(-depth) * L->pitch, cnt, L->nbr[2], nccl_stream, g_err));
+      if (L->nbr[2] >= 0) SGCALL(c->nccl.send(p + (ptrdiff_t)ey * L->pitch, cnt, L->nbr[2], nccl_stream, g_err));
+      if (L->nbr[3] >= 0) SGCALL(c->nccl.send(p + (ptrdiff_t)(ny - depth) * L->pitch, cnt, L->nbr[3], nccl_stream, g_err));
     }
   }
   SGCALL(c->nccl.group_end(g_err));
@@ -1321,20 +1331,46 @@ static int relax_impl(sg_op* op, sg_field* phi, const sg_field* rhs, int iterati
       const bool two = can2 && it + 2 <= iterations;
       const int kind = two ? (c->relax_mode == 4 ? 4 : 3) : (c->relax_mode == 2 ? 2 : 1);
       const int chunk = (wide && kind == 1) ? std::min(4, iterations - it) : 1;
+      // N > 1: the exchange of a chunk runs on the communication stream while the first sweep updates the rows that do not
+      // depend on ghost rows ([2, ny-2): a sweep over [a, b) reads rows [a-2, b+2)); the two boundary strips follow once the
+      // ghost rows have landed.  Out of place, so the three launches write disjoint rows and read the same input.
+      bool overlapped = false;
       if (ghosts) {
         const int need = two ? 4 : 2 * chunk;
         GhostReq r[2] = {{phi, need}, {const_cast<sg_field*>(rhs), rhs_depth}};
         if (it == 0 && phi_valid >= need) { if (rhs_pending) SGCALL(fill_ghosts_multi(c, r + 1, 1)); }
-        else SGCALL(fill_ghosts_multi(c, r, rhs_pending ? 2 : 1));
+        else if (wide && kind == 1 && c->comm_stream && c->tune[6] != 1 && L->ny >= 32 && (L->nbr[2] >= 0 || L->nbr[3] >= 0) &&
+                 !L->wrap_local[0] && !L->wrap_local[1]) {
+          CK(cudaEventRecord(c->ev_comm[0], c->stream));
+          CK(cudaStreamWaitEvent(c->comm_stream, c->ev_comm[0], 0));
+          SGCALL(fill_ghosts_multi(c, r, rhs_pending ? 2 : 1, c->comm_stream));
+          CK(cudaEventRecord(c->ev_comm[1], c->comm_stream));
+          overlapped = true;
+        } else SGCALL(fill_ghosts_multi(c, r, rhs_pending ? 2 : 1));
         rhs_pending = false;
       }
       for (int sub = 0; sub < chunk; sub++) {
         const int ext = 2 * (chunk - 1 - sub);
+        f.phi_in = phi->p();
+        f.phi_out = scratch->p();
+        if (overlapped && sub == 0) {
+          auto sweep_rows = [&](int ylo, int yhi) {
+            f.ylo = ylo; f.yhi = yhi;
+            const int nb = plan(1);
+            if (a.has_a) k_gsrb_stream<1, 3><<<nb, 128, 4 * GS_STAGES * 9 * 512, c->stream>>>(f);
+            else k_gsrb_stream<0, 3><<<nb, 128, 4 * GS_STAGES * 8 * 512, c->stream>>>(f);
+            c->launches++;
+          };
+          sweep_rows(2, L->ny - 2);
+          CK(cudaStreamWaitEvent(c->stream, c->ev_comm[1], 0));
+          sweep_rows(ygh_lo ? -ext : 0, 2);
+          sweep_rows(L->ny - 2, L->ny + (ygh_hi ? ext : 0));
+          std::swap(phi->base, scratch->base);
+          continue;
+        }
         f.ylo = ygh_lo ? -ext : 0;
         f.yhi = L->ny + (ygh_hi ? ext : 0);
         const int blocks = plan(kind);
-        f.phi_in = phi->p();
-        f.phi_out = scratch->p();
         if (kind == 4) {
           if (a.has_a) k_gsrb_pair<1><<<blocks, 128, 2 * (GP_STAGES * 9 * 512 + 1024), c->stream>>>(f);
           else k_gsrb_pair<0><<<blocks, 128, 2 * (GP_STAGES * 8 * 512 + 1024), c->stream>>>(f);
