@@ -40,7 +40,19 @@ def three_levels():
     np.savez_compressed(os.path.join(HERE, "amr_3lev_vcycles.npz"), **out)
 
 
+def gap_solve():
+    """implicit gap-height solve (SolveForGap_nl) on the C2 level-0 grid with the reference's solver constants"""
+    from tests import gapsolve as gs
+    cfg = syn.config("C2", 1)
+    boxes = syn.domain_split(cfg.nx, cfg.ny, cfg.max_box_size, cfg.block_factor)
+    o = gs.OracleGap(cfg, boxes)
+    sp = ob.make_solver_params(pre=2, post=2, bottom=4, max_iter=100, imin=10, iter_min=2, eps=1e-7, hang=1e-6, norm_thresh=1e-7)
+    it, hist = o.solver.solve(o.F["b"], o.F["rhs"], sp)
+    np.savez_compressed(os.path.join(HERE, "gap_c2_solve.npz"), resnorm=hist, gap=o.F["b"].get_global(), bottom_iters=o.solver.bottom_iters)
+
+
 if __name__ == "__main__":
     single_level()
     three_levels()
+    gap_solve()
     print("wrote", sorted(f for f in os.listdir(HERE) if f.endswith(".npz")))

@@ -142,3 +142,13 @@ def test_repeated_calls_reuse_the_solver(gpu_ctx):
                                                 [gpu.F["b"]], [gpu.F["rhs"]], beta, 1.0, 100)
         assert git == oit and np.array_equal(ghist, ohist), (rep, git, oit)
         same(gpu.F["b"], orc.F["b"], f"gap height, call {rep}")
+
+
+def test_against_golden_fixture(gpu_ctx):
+    """the CUDA path against the committed fixture tests/golden/gap_c2_solve.npz"""
+    import os
+    z = np.load(os.path.join(os.path.dirname(__file__), "golden", "gap_c2_solve.npz"))
+    cfg, orc, gpu = make(gpu_ctx, "C2", 1)
+    git, ghist, st = gpu.amr.SolveForGap_nl(gpu_ctx, [gpu.layout], [gpu.F["a"]], [gpu.F["bX"]], [gpu.F["bY"]], [], (orc.dx, orc.dx),
+                                            [gpu.F["b"]], [gpu.F["rhs"]], orc.beta, 1.0, 0)
+    assert np.array_equal(ghist, z["resnorm"]) and np.array_equal(gpu.F["b"].get_global(), z["gap"])

@@ -119,3 +119,14 @@ def test_stop_logic_and_bottom_solver():
     b.solver.residual(r, e, rhs, depth=d)
     n1 = np.sqrt(np.sum(r.get_global() ** 2))
     assert 1 <= its <= 40 and (n1 < 1e-6 * n0 * (1 + 1e-12) or its == 40)
+
+
+def test_golden_fixture_gap_solve():
+    """frozen output of tests/golden/make_golden.py:gap_solve (guards the oracle against drift; it does not pin the reference)"""
+    import os
+    z = np.load(os.path.join(os.path.dirname(__file__), "golden", "gap_c2_solve.npz"))
+    cfg, o = make("C2", 1)
+    sp_ = ob.make_solver_params(pre=2, post=2, bottom=4, max_iter=100, imin=10, iter_min=2, eps=1e-7, hang=1e-6, norm_thresh=1e-7)
+    it, hist = o.solver.solve(o.F["b"], o.F["rhs"], sp_)
+    assert np.array_equal(hist, z["resnorm"]) and np.array_equal(o.F["b"].get_global(), z["gap"])
+    assert o.solver.bottom_iters == int(z["bottom_iters"])
