@@ -53,7 +53,7 @@ def test_sample_input(exe):
 
 def test_nl_switches_follow_the_reference_nesting(exe, tmp_path):
     """use_NL is only read under use_fas, bcoeff_otf only under use_NL (src/AmrHydro.cpp:876-881)"""
-    text = open(SAMPLE).read().replace("solver.use_fas=true", "solver.use_fas=false")
+    text = open(SAMPLE).read().replace("solver.use_fas = true", "solver.use_fas = false")
     p = tmp_path / "in.hydro"
     p.write_text(text)
     py = inputs.read(str(p))
