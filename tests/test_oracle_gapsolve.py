@@ -130,3 +130,66 @@ def test_golden_fixture_gap_solve():
     it, hist = o.solver.solve(o.F["b"], o.F["rhs"], sp_)
     assert np.array_equal(hist, z["resnorm"]) and np.array_equal(o.F["b"].get_global(), z["gap"])
     assert o.solver.bottom_iters == int(z["bottom_iters"])
+
+
+# ---- size-independent properties of the implicit gap-height operator and its multigrid cycle ----
+def _rand_field(layout, ng, rng, ghosts=False):
+    f = ob.Field(layout, 1, ng)
+    d = layout.domain
+    ny, nx = d[3] + 1, d[2] + 1
+    f.set_global(rng.rand(ny + 2 * ng, nx + 2 * ng), (-ng, -ng))
+    return f
+
+
+@pytest.mark.parametrize("name", ["C2", "C4", "C5"])
+def test_operator_is_self_adjoint_and_positive(name):
+    """L = alpha*a - beta*div(D grad) with FixedNeumBCFill / periodic sides is symmetric positive definite: <u, Lv> = <Lu, v>,
+    <u, Lu> > 0 (what lets a linear multigrid with GSRB smoothing converge at all)"""
+    cfg, o = make(name, 1)
+    rng = np.random.RandomState(21)
+    u, v = _rand_field(o.layout, 1, rng), _rand_field(o.layout, 1, rng)
+    Lu, Lv = ob.Field(o.layout, 1, 0), ob.Field(o.layout, 1, 0)
+    o.solver.applyOp(Lu, u)
+    o.solver.applyOp(Lv, v)
+    ug, vg, Lug, Lvg = u.get_global(), v.get_global(), Lu.get_global(), Lv.get_global()
+    a, b = float(np.sum(ug * Lvg)), float(np.sum(Lug * vg))
+    assert abs(a - b) <= 1e-11 * max(abs(a), abs(b))
+    assert float(np.sum(ug * Lug)) > 0.0
+
+
+@pytest.mark.parametrize("name", ["C2", "C5"])
+def test_vcycle_commutes_with_power_of_two_scaling(name):
+    """The correction-form cycle is linear in the residual, and scaling by a power of two is exact in binary floating point
+    (the bottom solver's stop test is relative): V(4 r) == 4 V(r) bit for bit, with the same bottom pass count."""
+    cfg, o = make(name, 1)
+    rng = np.random.RandomState(8)
+    r1 = _rand_field(o.layout, 0, rng)
+    r4 = ob.Field(o.layout, 1, 0)
+    r4.set_global(4.0 * r1.get_global(), (0, 0))
+    sp_ = ob.make_solver_params(pre=2, post=2, bottom=4)
+    c1, c4 = ob.Field(o.layout, 1, 1), ob.Field(o.layout, 1, 1)
+    c1.setval(0.0)
+    c4.setval(0.0)
+    o.solver.vcycle(c1, r1, sp_)
+    n1 = o.solver.bottom_iters
+    o.solver.vcycle(c4, r4, sp_)
+    assert o.solver.bottom_iters == n1
+    assert np.array_equal(c4.get_global(), 4.0 * c1.get_global())
+
+
+def test_restriction_is_the_scaled_adjoint_of_prolongation():
+    """<P c, r>_fine = 4 <c, R r>_coarse for piecewise-constant prolongation P and 2x2 averaging R (restrictResidual with phi = 0)"""
+    cfg, o = make("C2", 1)
+    S = o.solver
+    rng = np.random.RandomState(4)
+    Lc = S.layout_at(1)
+    r, c = _rand_field(o.layout, 0, rng), _rand_field(Lc, 0, rng)
+    zero = ob.Field(o.layout, 1, 1)
+    zero.setval(0.0)
+    Rr = ob.Field(Lc, 1, 0)
+    S.restrictResidual(Rr, zero, r)            # residual of phi = 0 is r itself
+    Pc = ob.Field(o.layout, 1, 1)
+    Pc.setval(0.0)
+    S.prolongIncrement(Pc, c)
+    lhs, rhs = float(np.sum(Pc.get_global() * r.get_global())), 4.0 * float(np.sum(c.get_global() * Rr.get_global()))
+    assert abs(lhs - rhs) <= 1e-12 * abs(lhs)
