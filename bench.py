@@ -240,7 +240,7 @@ def main():
     ap.add_argument("--size", type=int, default=8192, help="cells per GPU in x and y")
     ap.add_argument("--bottom", type=int, default=16)
     ap.add_argument("--cpu-size", type=int, default=2048, help="bounded CPU sample (cells in x and y)")
-    ap.add_argument("--cpu-cycles", type=int, default=3)
+    ap.add_argument("--cpu-cycles", type=int, default=30, help="V-cycles of the bounded CPU sample (about 5-25 s of host work)")
     ap.add_argument("--e2e-cycles", type=int, default=5, help="V-cycles per head solve in the end-to-end leg")
     ap.add_argument("--e2e-steps", type=int, default=2)
     ap.add_argument("--no-cpu", action="store_true")
