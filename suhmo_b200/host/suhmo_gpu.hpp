@@ -32,6 +32,13 @@ class Context {
   Context& operator=(const Context&) = delete;
   void sync() { SG_DO(sg_ctx_sync(h)); }
   long long kernelLaunches() { long long n; SG_DO(sg_ctx_kernel_launches(h, &n)); return n; }
+  void setStream(void* cuda_stream) { SG_DO(sg_ctx_set_stream(h, cuda_stream)); }
+  void eventRecord(int slot) { SG_DO(sg_ctx_event_record(h, slot)); }
+  double eventElapsedMs(int slot0, int slot1) { double ms; SG_DO(sg_ctx_event_elapsed_ms(h, slot0, slot1, &ms)); return ms; }
+  void setRelaxMode(int mode) { SG_DO(sg_set_relax_mode(h, mode)); }
+  void setTuning(int key, int value) { SG_DO(sg_set_tuning(h, key, value)); }
+  // 128 bytes made on rank 0 and broadcast by the caller (MPI_Bcast) before every rank constructs its Context
+  static void ncclUniqueId(void* out128) { SG_DO(sg_nccl_unique_id(out128)); }
 };
 
 // DisjointBoxLayout + ProblemDomain (+ procIDs)
@@ -69,11 +76,19 @@ class LevelData {
   // FArrayBox::dataPtr() of box `ibox` (ghost cells included, Fortran order)
   void upload(int ibox, const double* fab) { SG_DO(sg_field_upload_box(h, ibox, fab)); }
   void download(int ibox, double* fab) const { SG_DO(sg_field_download_box(h, ibox, fab)); }
-  void exchange() { SG_DO(sg_exchange(h, 1)); }
+  // all owned FArrayBoxes at once: one pointer per box (NULL for boxes of other ranks), or one packed (ideally pinned) buffer
+  void upload(const std::vector<const double*>& fabs) { SG_DO(sg_field_upload(h, fabs.data())); }
+  void download(const std::vector<double*>& fabs) const { SG_DO(sg_field_download(h, fabs.data())); }
+  void uploadPacked(const double* packed, size_t ndoubles) { SG_DO(sg_field_upload_packed(h, packed, ndoubles)); }
+  void downloadPacked(double* packed, size_t ndoubles) const { SG_DO(sg_field_download_packed(h, packed, ndoubles)); }
+  void exchange() { SG_DO(sg_exchange(h, 1)); }                       // LevelData::exchange(): all ghost cells incl. corners
+  void exchangeNoCorners() { SG_DO(sg_exchange(h, 0)); }              // exchange(m_exchangeCopier): face strips only
   void copyTo(LevelData& dst, int ghosts = 0) const { SG_DO(sg_field_copyTo(dst.h, h, ghosts)); }
 };
 inline void ExtrapGhostCells(LevelData& f) { SG_DO(sg_extrap_ghost_cells(f.h)); } // util/ExtrapGhostCells.cpp:47-55
 inline void CopyGhostCells(LevelData& f) { SG_DO(sg_copy_ghost_cells(f.h)); }
+// mixBCValues (src/AmrHydro.cpp:248-309) on every box that touches a non-periodic domain side
+inline void mixBCValues(LevelData& f, const sg_bc& bc, const double dx[2], bool homogeneous) { SG_DO(sg_apply_bc(f.h, &bc, dx, homogeneous)); }
 
 class VCAMRNonLinearPoissonOp {
   static sg_field* hp(LevelData* f) { return f ? f->h : nullptr; }
@@ -124,6 +139,23 @@ class VCAMRNonLinearPoissonOp {
   void AMRUpdateResidual(LevelData& residual, LevelData& correction, const LevelData* coarseCorrection) { SG_DO(sg_op_AMRUpdateResidual(h, residual.h, correction.h, hp(coarseCorrection))); }
   double AMRNorm(const LevelData& coarResid, const LevelData* fineResid, int refRat, int ord) { double r; SG_DO(sg_op_AMRNorm(h, coarResid.h, hp(fineResid), refRat, ord, &r)); return r; }
   void reflux(const LevelData& phiFine, const LevelData& phi, LevelData& residual, VCAMRNonLinearPoissonOp& finerOp) { SG_DO(sg_op_reflux(h, phiFine.h, phi.h, residual.h, finerOp.h)); }
+  void AMRResidualNC(LevelData& residual, const LevelData& phiFine, LevelData& phi, const LevelData& rhs, bool homogeneousPhysBC, VCAMRNonLinearPoissonOp& finerOp)
+  { SG_DO(sg_op_AMRResidualNC(h, residual.h, phiFine.h, phi.h, rhs.h, homogeneousPhysBC, finerOp.h)); }
+  void AMRResidualNF(LevelData& residual, LevelData& phi, const LevelData* phiCoarse, const LevelData& rhs, bool homogeneousPhysBC)
+  { SG_DO(sg_op_AMRResidualNF(h, residual.h, phi.h, hp(phiCoarse), rhs.h, homogeneousPhysBC)); }
+  void AMROperatorNC(LevelData& LofPhi, const LevelData& phiFine, LevelData& phi, bool homogeneousPhysBC, VCAMRNonLinearPoissonOp& finerOp)
+  { SG_DO(sg_op_AMROperatorNC(h, LofPhi.h, phiFine.h, phi.h, homogeneousPhysBC, finerOp.h)); }
+  void AMROperatorNF(LevelData& LofPhi, LevelData& phi, const LevelData* phiCoarse, bool homogeneousPhysBC)
+  { SG_DO(sg_op_AMROperatorNF(h, LofPhi.h, phi.h, hp(phiCoarse), homogeneousPhysBC)); }
+  // m_interpWithCoarser.coarseFineInterp(phi, phiCoarse) (src/AMRNonLinearPoissonOp.cpp:1563-1597)
+  void coarseFineInterp(LevelData& phi, const LevelData& phiCoarse) { SG_DO(sg_op_cfInterp(h, phi.h, phiCoarse.h)); }
+  void zeroCovered(LevelData& coarse, const LevelData& fineAny) { SG_DO(sg_op_zeroCovered(h, coarse.h, fineAny.h)); }
+  // create / createCoarser / createCoarsened: the caller owns the returned LevelData
+  LevelData* create(const LevelData& rhs) { sg_field* f; SG_DO(sg_op_create(h, &f, rhs.h)); return new LevelData(f); }
+  LevelData* createCoarser(const LevelData& fine, bool ghosted = true) { sg_field* f; SG_DO(sg_op_createCoarser(h, &f, fine.h, ghosted)); return new LevelData(f); }
+  LevelData* createCoarsened(const LevelData& fine, int refRat = 2) { sg_field* f; SG_DO(sg_op_createCoarsened(h, &f, fine.h, refRat)); return new LevelData(f); }
+  // m_lambda as the reference stores it (the diagonal itself, src/VCAMRNonLinearPoissonOp.cpp:505-534)
+  void lambda(LevelData& out) { SG_DO(sg_op_lambda(h, out.h)); }
 };
 
 class VCAMRNonLinearPoissonOpFactory {
@@ -186,7 +218,88 @@ class AMRFASMultiGrid {
     return st.iterations;
   }
   void refresh() { SG_DO(sg_solver_refresh(h)); }
+  int depth(int level = 0) const { int n; SG_DO(sg_solver_depth(h, level, &n)); return n; }
+  double cellUpdatesPerCycle() const { double v; SG_DO(sg_solver_cell_updates_per_cycle(h, &params, &v)); return v; }
 };
+
+// ---- AmrHydro's callbacks and utilities as stand-alone calls (src/AmrHydro.cpp:1415-1574; util/Gradient.cpp, util/DivergenceF.ChF)
+inline void NonLinear_level(const sg_params& p, LevelData& NL, LevelData& dNL, const LevelData& u, const LevelData& B, const LevelData& mask,
+                            const LevelData& Pi, const LevelData& zb) { SG_DO(sg_nonlinear_level(&p, NL.h, dNL.h, u.h, B.h, mask.h, Pi.h, zb.h)); }
+inline void WFlx_level(Context& ctx, const sg_params& p, LevelData& bcoefX, LevelData& bcoefY, LevelData& u, const LevelData& B,
+                       const LevelData& mask, const double dx[2]) { SG_DO(sg_wflx_level(ctx.h, &p, bcoefX.h, bcoefY.h, u.h, nullptr, B.h, mask.h, dx)); }
+inline void compGradientCC(LevelData& grad2, LevelData& phi, const LevelData* maskOrNull, const double dx[2])
+{ SG_DO(sg_gradient_cc(grad2.h, phi.h, maskOrNull ? maskOrNull->h : nullptr, dx)); }
+inline void compGradientMAC(LevelData& phi, const LevelData* maskOrNull, const double dx[2], LevelData& gx, LevelData& gy)
+{ SG_DO(sg_mac_gradient(phi.h, maskOrNull ? maskOrNull->h : nullptr, dx, gx.h, gy.h)); }
+inline void computeRe(const sg_params& p, LevelData& Re, const LevelData& B, const LevelData& gradH) { SG_DO(sg_compute_re(&p, Re.h, B.h, gradH.h)); }
+inline void divergence(LevelData& div, const LevelData& ux, const LevelData& uy, const double dx[2]) { SG_DO(sg_divergence(div.h, ux.h, uy.h, dx)); }
+inline void CellToEdge(const LevelData& cell, LevelData& ex, LevelData& ey) { SG_DO(sg_cell_to_edge(cell.h, ex.h, ey.h)); }
+inline void EdgeToCell(const LevelData& ex, const LevelData& ey, LevelData& cell2) { SG_DO(sg_edge_to_cell(ex.h, ey.h, cell2.h)); }
+inline void setup_iceMask_EC(const LevelData& mask, LevelData& mx, LevelData& my) { SG_DO(sg_icemask_ec(mask.h, mx.h, my.h)); }
+
+// ---- Picard-body field kernels (src/AmrHydroF.ChF:125-373, src/AmrHydro.cpp:2070-2252, 3044-3077, 3394-3408); one direction per
+// call where the reference loops over the FluxBox directions
+inline void evaluate_Qw_ec(const sg_params& p, const LevelData& Bec, const LevelData& Reec, const LevelData& gradHec, LevelData& Qw)
+{ SG_DO(sg_compute_qw(&p, Bec.h, Reec.h, gradHec.h, Qw.h)); }
+inline void computeScaProd(const LevelData& a, const LevelData& b1, const LevelData& b2, LevelData& p1, LevelData& p2)
+{ SG_DO(sg_compute_scaprod(a.h, b1.h, b2.h, p1.h, p2.h)); }
+inline void dCoeff(LevelData& D, const LevelData& mRec, const LevelData& Bec, const LevelData& IMec, double rho, int cutOffB)
+{ SG_DO(sg_compute_dcoeff(D.h, mRec.h, Bec.h, IMec.h, rho, cutOffB)); }
+inline void computeDifTerm(const LevelData& phi, const double dx[2], LevelData& Dterm, const LevelData& D0, const LevelData& D1)
+{ SG_DO(sg_compute_difterm(phi.h, dx, Dterm.h, D0.h, D1.h)); }
+inline void timeVaryingRecharge(const LevelData& zs, LevelData& recharge, double TK, double background)
+{ SG_DO(sg_time_varying_recharge(zs.h, recharge.h, TK, background)); }
+inline void Calc_meltingRate(const sg_picard_params& q, const LevelData& H, const LevelData& zb, const LevelData& Pi, const LevelData& IM,
+                             const LevelData& B, const LevelData& qgh, const LevelData& qgz, LevelData& Pw, LevelData& mR)
+{ SG_DO(sg_calc_melting_rate(&q, H.h, zb.h, Pi.h, IM.h, B.h, qgh.h, qgz.h, Pw.h, mR.h)); }
+inline void CalcRHS_head(const sg_picard_params& q, LevelData& RHSh, const LevelData& mR, const LevelData& B, const LevelData& BH,
+                         const LevelData& BL, const LevelData& MV, const LevelData& moulinSrc, const LevelData& Dterm, const LevelData& IM)
+{ SG_DO(sg_rhs_head(&q, RHSh.h, mR.h, B.h, BH.h, BL.h, MV.h, moulinSrc.h, Dterm.h, IM.h)); }
+inline void CalcRHS_gapHeightFAS(const sg_picard_params& q, LevelData& RHS, const LevelData& Pi, const LevelData& Pw, const LevelData& mR,
+                                 const LevelData& B, const LevelData& DT, const LevelData& IM, const LevelData& BH, const LevelData& BL,
+                                 const LevelData& MV, double dt)
+{ SG_DO(sg_rhs_gap(&q, RHS.h, Pi.h, Pw.h, mR.h, B.h, DT.h, IM.h, BH.h, BL.h, MV.h, dt)); }
+inline void gapEuler(LevelData& newB, const LevelData& oldB, const LevelData& RHS, double dt) { SG_DO(sg_gap_euler(newB.h, oldB.h, RHS.h, dt)); }
+
+// ---- AMR hierarchy generation (src/AmrHydro.cpp:4267-4272, 4539-4604)
+// tagCellsLevel: tags = one byte per cell of the level's domain (x fastest), ORed into when accumulate is set
+inline void tagCellsLevel(const LevelData& phi, double vmin, double vmax, int tagsGrow, const int tagsGrowDir[2], std::vector<unsigned char>& tags,
+                          bool accumulate) { SG_DO(sg_tag_cells_level(phi.h, vmin, vmax, tagsGrow, tagsGrowDir, tags.data(), accumulate)); }
+// BRMeshRefine(domain0, refRatios = 2, fillRatio, blockFactor, bufferSize, maxSize).regrid: boxes of levels 1..newFinest
+class BRMeshRefine {
+ public:
+  Box domain0;
+  double fillRatio;
+  int blockFactor, nestingRadius, maxBoxSize;
+  BRMeshRefine(const Box& a_domain0, double a_fill, int a_block, int a_nesting, int a_maxSize)
+      : domain0(a_domain0), fillRatio(a_fill), blockFactor(a_block), nestingRadius(a_nesting), maxBoxSize(a_maxSize) {}
+  // tags[l]: byte map of level l's domain for l = 0..topLevel; returns the new finest level, newGrids[l] for l = 1..that
+  int regrid(std::vector<std::vector<Box>>& newGrids, const std::vector<Box>& baseBoxes, const std::vector<std::vector<unsigned char>>& tags,
+             int maxBoxes = 1 << 16) const {
+    const int top = (int)tags.size() - 1;
+    std::vector<int> flat, out((size_t)maxBoxes * 4), counts(top + 2, 0);
+    for (const Box& b : baseBoxes) { flat.push_back(b.lo[0]); flat.push_back(b.lo[1]); flat.push_back(b.hi[0]); flat.push_back(b.hi[1]); }
+    std::vector<const unsigned char*> tp;
+    for (const auto& t : tags) tp.push_back(t.data());
+    const int dom[4] = {domain0.lo[0], domain0.lo[1], domain0.hi[0], domain0.hi[1]};
+    int finest = 0;
+    SG_DO(sg_br_regrid(dom, (int)baseBoxes.size(), flat.data(), top, tp.data(), fillRatio, blockFactor, nestingRadius, maxBoxSize, maxBoxes,
+                       out.data(), counts.data(), &finest));
+    newGrids.assign(finest + 1, std::vector<Box>());
+    newGrids[0] = baseBoxes;
+    size_t k = 0;
+    for (int l = 1; l <= finest; l++)
+      for (int b = 0; b < counts[l]; b++, k++) newGrids[l].push_back(Box{{out[4 * k], out[4 * k + 1]}, {out[4 * k + 2], out[4 * k + 3]}});
+    return finest;
+  }
+};
+// LoadBalance on equal boxes: contiguous runs of the sorted box list per rank (one rectangle per rank on uniform levels)
+inline std::vector<int> LoadBalance(const std::vector<Box>& boxes, int nranks) {
+  std::vector<int> flat, owner(boxes.size());
+  for (const Box& b : boxes) { flat.push_back(b.lo[0]); flat.push_back(b.lo[1]); flat.push_back(b.hi[0]); flat.push_back(b.hi[1]); }
+  SG_DO(sg_partition_boxes((int)boxes.size(), flat.data(), nranks, owner.data()));
+  return owner;
+}
 
 // The VCAMRPoissonOp2Factory + AMRMultiGrid<LevelData<FArrayBox>> + RelaxSolver trio of AmrHydro::SolveForGap_nl
 // (src/AmrHydro.cpp:594-662): linear VC Helmholtz, correction-form V-cycles, one AMR level
@@ -212,6 +325,18 @@ class GapHeightSolver {
     params.pre = pre; params.post = post; params.bottom = bottom; params.num_mg = numMG; params.max_iter = maxIter;
     params.eps = eps; params.hang = hang; params.norm_thresh = normThresh;
   }
+  // VCAMRPoissonOp2 at MG depth `depth` of level 0
+  void relax(LevelData& phi, const LevelData& rhs, int iterations, int depth = 0) { SG_DO(sg_gap_op_relax(h, depth, phi.h, rhs.h, iterations)); }
+  void residual(LevelData& lhs, LevelData& phi, const LevelData& rhs, bool homogeneous = false, int depth = 0) { SG_DO(sg_gap_op_residual(h, depth, lhs.h, phi.h, rhs.h, homogeneous)); }
+  void applyOp(LevelData& lhs, LevelData& phi, bool homogeneous = false, int depth = 0) { SG_DO(sg_gap_op_applyOp(h, depth, lhs.h, phi.h, homogeneous)); }
+  void restrictResidual(LevelData& resCoarse, LevelData& phiFine, const LevelData& rhsFine, int depth = 0) { SG_DO(sg_gap_op_restrictResidual(h, depth, resCoarse.h, phiFine.h, rhsFine.h)); }
+  void prolongIncrement(LevelData& phi, const LevelData& corrCoarse, int depth = 0) { SG_DO(sg_gap_op_prolongIncrement(h, depth, phi.h, corrCoarse.h)); }
+  void preCond(LevelData& phi, const LevelData& rhs, int depth = 0) { SG_DO(sg_gap_op_preCond(h, depth, phi.h, rhs.h)); }
+  void lambda(LevelData& out, int depth = 0) { SG_DO(sg_gap_op_lambda(h, depth, out.h)); }
+  int bottomSolve(LevelData& phi, const LevelData& rhs) { int it; SG_DO(sg_gap_solver_bottom_solve(h, phi.h, rhs.h, &it)); return it; } // RelaxSolver::solve
+  void vcycle(LevelData& correction, const LevelData& residual) { SG_DO(sg_gap_solver_vcycle(h, correction.h, residual.h, &params)); }
+  void refresh() { SG_DO(sg_gap_solver_refresh(h)); }
+  int depth() const { int n; SG_DO(sg_gap_solver_depth(h, &n)); return n; }
   int solve(const std::vector<LevelData*>& phi, const std::vector<LevelData*>& rhs, int l_max, int l_base, bool zeroPhi = false,
             sg_solve_stats* stats = nullptr, std::vector<double>* resnorm = nullptr) {
     params.imin = m_imin; params.iter_min = m_iterMin;
@@ -233,6 +358,7 @@ inline int SolveForGap_nl(Context& ctx, const std::vector<DisjointBoxLayout*>& g
                           const std::vector<LevelData*>& bX, const std::vector<LevelData*>& bY, const std::vector<int>& refRatio,
                           const double coarsestDx[2], const std::vector<LevelData*>& gapHeight, const std::vector<LevelData*>& RHS, double dt,
                           double DiffFactor, int cur_step) {
+  // (sg_solve_for_gap is the C entry point that additionally keeps the factory/solver pair alive between calls)
   GapHeightSolver s;
   s.define(ctx, grids, refRatio, coarsestDx, 1.0, aCoef, dt * DiffFactor, bX, bY);
   if (cur_step < 50) s.m_imin = 10;

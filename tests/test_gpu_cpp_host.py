@@ -25,6 +25,18 @@ def test_cpp_host_layer_compiles_and_links():
     assert os.path.exists(exe)
 
 
+def test_whole_cpp_mirror_links_without_a_gpu():
+    """every wrapper of suhmo_gpu.hpp (operator surface, callbacks, Picard-body kernels, tagging/regrid, gap solver) and
+    suhmo_inputs.hpp compiles with -Wall -Wextra -Werror and links; the program only asks the library for its version"""
+    build.build()
+    libdir = os.path.join(ROOT, "suhmo_b200", "lib")
+    exe = os.path.join(ROOT, "tests", "cpp", "api_touch")
+    subprocess.check_call(["g++", "-std=c++14", "-O0", "-Wall", "-Wextra", "-Werror", "-I", os.path.join(ROOT, "include"),
+                           os.path.join(ROOT, "tests", "cpp", "api_touch.cpp"), "-L", libdir, "-lsuhmo_gpu", f"-Wl,-rpath,{libdir}", "-o", exe])
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=60)
+    assert r.returncode == 0 and "free functions referenced" in r.stdout, r.stdout + r.stderr
+
+
 @pytest.mark.gpu
 def test_cpp_host_layer_solves_two_levels():
     exe = compile_host()
