@@ -170,7 +170,9 @@ int sg_factory_refToFiner(const sg_factory* f, int level, int* out);
 int sg_op_destroy(sg_op* op);
 
 /* ------------------------------------------------------------------ MGLevelOp surface -------------------- */
-/* relax (src/AMRNonLinearPoissonOp.cpp:707-750) -> levelGSRB (src/VCAMRNonLinearPoissonOp.cpp:654-760) */
+/* relax (src/AMRNonLinearPoissonOp.cpp:707-750) -> levelGSRB (src/VCAMRNonLinearPoissonOp.cpp:654-760).
+   The sweep is out of place on uniform levels: after an odd number of iterations phi owns another device buffer than before
+   (pointers from sg_field_device_view are then stale; the field handle stays valid). */
 int sg_op_relax(sg_op* op, sg_field* phi, const sg_field* rhs, int iterations, int amr_fasmg_iter, int depth);
 /* relaxNF (src/AMRNonLinearPoissonOp.cpp:690-704) */
 int sg_op_relaxNF(sg_op* op, sg_field* phi, const sg_field* phi_coarse, const sg_field* rhs, int iterations,
@@ -248,6 +250,40 @@ int sg_op_zeroCovered(sg_op* op, sg_field* coarse, const sg_field* fine_any);
    dst's valid regions grown by `ghosts` that a valid region of src holds (periodic images included) */
 int sg_field_copyTo(sg_field* dst, const sg_field* src, int ghosts);
 
+/* ---- virtuals the FAS path never calls but the cited classes expose (a subclass that forwards only part of the surface would mix
+   host and device state): every one of them is served from the device too ---- */
+/* AMRRestrict (src/AMRNonLinearPoissonOp.cpp:1011-1025): AMRRestrictS with a scratch created on the spot */
+int sg_op_AMRRestrict(sg_op* op, sg_field* res_coarse, const sg_field* residual, sg_field* correction,
+                      const sg_field* coarse_correction, int skip_res);
+/* AMRProlong (src/AMRNonLinearPoissonOp.cpp:1073-1103): piecewise-constant, private coarsened-fine scratch */
+int sg_op_AMRProlong(sg_op* op, sg_field* correction, const sg_field* coarse_correction);
+/* preCond, 2- and 3-argument forms (src/VCAMRNonLinearPoissonOp.cpp:174-208, 233-271): phi = rhs / lambda, then relax(phi, rhs, 2);
+   the 3-argument form only relaxes (its initial guess is commented out in the reference).  Not used by the FAS solve. */
+int sg_op_preCond(sg_op* op, sg_field* phi, const sg_field* rhs);
+int sg_op_preCond3(sg_op* op, sg_field* phi, const sg_field* res, const sg_field* rhs);
+/* getFlux, FluxBox form (src/VCAMRNonLinearPoissonOp.H:226-241 over VCAMRNonLinearPoissonOp.cpp:792-841), one direction per
+   call: flux = -bCoef * (phi_hi - phi_lo) * beta*ref/dx[dir] * scale on every face of every box; phi's ghost cells as they are */
+int sg_op_getFlux(sg_op* op, sg_field* flux, const sg_field* phi, int dir, int ref, double scale);
+/* finerOperatorChanged (src/VCAMRNonLinearPoissonOp.cpp:1353-1438): re-coarsen ALL operator data (aCoef, bCoef, B, Pi, zb, iceMask)
+   of this multigrid operator from `finer` by `coarsening_factor`, exchange */
+int sg_op_finerOperatorChanged(sg_op* op, const sg_op* finer, int coarsening_factor);
+/* mDotProduct (src/AMRNonLinearPoissonOp.cpp:624-632): out[k] = dotProduct(a, b[k]) */
+int sg_op_mDotProduct(sg_op* op, const sg_field* a, int n, const sg_field* const* b, double* out);
+/* buildCopier / assignCopier (src/AMRNonLinearPoissonOp.cpp:577-597): Copier(rhs layout -> lhs layout, no ghost cells) */
+typedef struct sg_copier sg_copier;
+int sg_op_buildCopier(sg_op* op, sg_copier** out, const sg_field* lhs, const sg_field* rhs);
+int sg_op_assignCopier(sg_op* op, sg_field* lhs, const sg_field* rhs, const sg_copier* copier);
+int sg_copier_destroy(sg_copier* c);
+/* setAlphaAndBeta / computeCoeffsOTF (src/VCAMRNonLinearPoissonOp.cpp:462-475) */
+int sg_op_setAlphaAndBeta(sg_op* op, double alpha, double beta);
+int sg_op_computeCoeffsOTF(sg_op* op, int update_operator);
+/* diagonalScale / divideByIdentityCoef (src/VCAMRNonLinearPoissonOp.H:157-175, "For TGA"): rhs *= aCoef ; rhs /= aCoef */
+int sg_op_diagonalScale(sg_op* op, sg_field* rhs, int kappa_weighted);
+int sg_op_divideByIdentityCoef(sg_op* op, sg_field* rhs);
+/* homogeneousCFInterp (src/AMRNonLinearPoissonOp.cpp:1599-1795): coarse-fine ghost cells from a zero coarse level; dead under FAS
+   (m_use_FAS is hard-wired, VCAMRNonLinearPoissonOp.cpp:946) */
+int sg_op_homogeneousCFInterp(sg_op* op, sg_field* phi);
+
 /* ------------------------------------------------------------------ Picard body -------------------------- */
 /* Field kernels of AmrHydro::timeStepFAS around the head solve ("gap-height and water-flux updates").
    The time loop / Picard loop themselves stay host code (C++ in the reference); these are its device kernels.
@@ -308,8 +344,15 @@ int sg_br_regrid(const int domain0[4], int nbase, const int* base_boxes, int top
 int sg_solver_define(sg_factory* f, sg_solver** out, int num_levels);
 int sg_solver_destroy(sg_solver* s);
 /* re-derive the MG-depth coefficient sets from the (updated) finest fields: what rebuilding factory + solver per
-   Picard iteration does in the reference (src/AmrHydro.cpp:704-735), without reallocating */
+   Picard iteration does in the reference (src/AmrHydro.cpp:704-735), without reallocating.
+   REQUIRED after any change (upload or device write) to a coefficient field handed to the factory -- aCoef, bCoef, B, Pi, zb,
+   iceMask: the depth-0 operator aliases those fields, but their halo rows on periodic / neighbour-GPU sides, the coarser
+   depths' averages and the decision to skip streaming the ice mask are only recomputed here (and in MGnewOp / AMRnewOp).
+   Solving after such a change without a refresh uses stale halo coefficients or a stale mask decision, silently.
+   sg_solver_refresh_bcoef re-derives only aCoef / bCoef: B, Pi, zb and the ice mask do not change between the Picard
+   iterations of one time step (the reference deep-copies the same fields into every new factory, src/AmrHydro.cpp:685-702). */
 int sg_solver_refresh(sg_solver* s);
+int sg_solver_refresh_bcoef(sg_solver* s);
 int sg_solver_depth(const sg_solver* s, int level, int* ndepth);
 int sg_solver_solve(sg_solver* s, sg_field* const* phi, sg_field* const* rhs, int l_max, int l_base,
                     const sg_solver_params* sp, double* resnorm_history /* max_iter+2 or NULL */,

@@ -42,7 +42,7 @@ class SolverParams(C.Structure):
 
 def build(force=False):
     so = os.path.join(_HERE, "libsuhmo_oracle.so")
-    src = [os.path.join(_HERE, f) for f in ("suhmo_oracle.c", "suhmo_oracle.h")]
+    src = [os.path.join(_HERE, f) for f in ("suhmo_oracle.c", "suhmo_oracle_r2.inc", "suhmo_oracle.h")]
     if force or not os.path.exists(so) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in src):
         subprocess.check_call(["make", "-C", _HERE, "all"], stdout=subprocess.DEVNULL)
     return so
@@ -159,6 +159,14 @@ def lib():
     sig("orc_rhs_gap", None, pq, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, cd)
     sig("orc_gap_euler", None, vp, vp, vp, cd)
     sig("orc_tag_cells_level", None, vp, cd, cd, ci, ip, vp, ci)
+    sig("orc_op_set_alpha_beta", None, vp, cd, cd)
+    sig("orc_op_precond", None, vp, vp, vp)
+    sig("orc_op_precond3", None, vp, vp, vp, vp)
+    sig("orc_op_get_flux", None, vp, vp, vp, ci, ci, cd)
+    sig("orc_op_finer_operator_changed", None, vp, vp, ci)
+    sig("orc_homogeneous_cf_interp", None, vp, dp, dp)
+    sig("orc_op_diagonal_scale", None, vp, vp)
+    sig("orc_op_divide_by_identity_coef", None, vp, vp)
     _LIB = L
     return L
 
@@ -355,6 +363,28 @@ class Op:
 
     def update_operator_amr(self, phi, phiC, maskC):
         lib().orc_op_update_operator_amr(self.h, phi.h, _h(phiC), _h(maskC))
+
+    # ---- virtuals the FAS path never calls (oracle/suhmo_oracle_r2.inc part 1) ----
+    def set_alpha_beta(self, alpha, beta):
+        lib().orc_op_set_alpha_beta(self.h, alpha, beta)
+
+    def precond(self, phi, rhs):
+        lib().orc_op_precond(self.h, phi.h, rhs.h)
+
+    def precond3(self, phi, res, rhs):
+        lib().orc_op_precond3(self.h, phi.h, res.h, rhs.h)
+
+    def get_flux(self, flux, phi, dir_, ref=1, scale=1.0):
+        lib().orc_op_get_flux(self.h, flux.h, phi.h, dir_, ref, scale)
+
+    def finer_operator_changed(self, finer, factor):
+        lib().orc_op_finer_operator_changed(self.h, finer.h, factor)
+
+    def diagonal_scale(self, rhs):
+        lib().orc_op_diagonal_scale(self.h, rhs.h)
+
+    def divide_by_identity_coef(self, rhs):
+        lib().orc_op_divide_by_identity_coef(self.h, rhs.h)
 
 
 class Solver:

@@ -2079,3 +2079,6 @@ int orc_lin_solver_solve(orc_lin_solver* s, orc_field* phi, const orc_field* rhs
   }
   return iter;
 }
+
+/* round-2 additions: remaining operator virtuals, multi-level Picard-body pieces, regrid transfer, Berger-Rigoutsos */
+#include "suhmo_oracle_r2.inc"

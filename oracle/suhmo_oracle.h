@@ -213,6 +213,16 @@ int orc_lin_solver_bottom_solve(orc_lin_solver* s, orc_field* phi, const orc_fie
 void orc_lin_solver_vcycle(orc_lin_solver* s, orc_field* corr, const orc_field* res, const orc_solver_params* sp);
 int orc_lin_solver_solve(orc_lin_solver* s, orc_field* phi, const orc_field* rhs, const orc_solver_params* sp, double* resnorm);
 
+/* ---- remaining operator virtuals (oracle/suhmo_oracle_r2.inc part 1) ---- */
+void orc_op_set_alpha_beta(orc_op* op, double alpha, double beta);
+void orc_op_precond(orc_op* op, orc_field* phi, const orc_field* rhs);
+void orc_op_precond3(orc_op* op, orc_field* phi, const orc_field* res, const orc_field* rhs);
+void orc_op_get_flux(const orc_op* op, orc_field* flux, const orc_field* phi, int dir, int ref, double scale);
+void orc_op_finer_operator_changed(orc_op* op, const orc_op* finer, int coarseningFactor);
+void orc_homogeneous_cf_interp(orc_field* phiF, const double dxFine[2], const double dxCrse[2]);
+void orc_op_diagonal_scale(const orc_op* op, orc_field* rhs);
+void orc_op_divide_by_identity_coef(const orc_op* op, orc_field* rhs);
+
 void orc_set_threads(int n);
 
 #ifdef __cplusplus

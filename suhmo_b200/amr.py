@@ -381,6 +381,55 @@ class VCAMRNonLinearPoissonOp:
     def AMROperatorNC(self, LofPhi, phiFine, phi, homogeneousPhysBC, finerOp):
         check(lib().sg_op_AMROperatorNC(self.h, LofPhi.h, _h(phiFine), phi.h, int(homogeneousPhysBC), _h(finerOp)))
 
+    # ---- virtuals the FAS path never calls (src/AMRNonLinearPoissonOp.cpp:1011-1103,577-632; VCAMRNonLinearPoissonOp.{H,cpp})
+    def AMRRestrict(self, resCoarse, residual, correction, coarseCorrection, skip_res=False):
+        check(lib().sg_op_AMRRestrict(self.h, resCoarse.h, residual.h, _h(correction), _h(coarseCorrection), int(skip_res)))
+
+    def AMRProlong(self, correction, coarseCorrection):
+        check(lib().sg_op_AMRProlong(self.h, correction.h, coarseCorrection.h))
+
+    def preCond(self, correction, residual, rhs=None):
+        """2-argument form preCond(phi, rhs); 3-argument form preCond(phi, res, rhs) (fork signature)"""
+        if rhs is None:
+            check(lib().sg_op_preCond(self.h, correction.h, residual.h))
+        else:
+            check(lib().sg_op_preCond3(self.h, correction.h, residual.h, rhs.h))
+
+    def getFlux(self, flux, data, dir_, ref=1, scale=1.0):
+        check(lib().sg_op_getFlux(self.h, flux.h, data.h, dir_, ref, scale))
+
+    def finerOperatorChanged(self, operator, coarseningFactor):
+        check(lib().sg_op_finerOperatorChanged(self.h, operator.h, coarseningFactor))
+
+    def mDotProduct(self, a, bs):
+        out = np.zeros(len(bs))
+        arr = (C.c_void_p * len(bs))(*[b.h.value for b in bs])
+        check(lib().sg_op_mDotProduct(self.h, a.h, len(bs), arr, _dp(out)))
+        return out
+
+    def buildCopier(self, lhs, rhs):
+        h = C.c_void_p()
+        check(lib().sg_op_buildCopier(self.h, C.byref(h), lhs.h, rhs.h))
+        return h
+
+    def assignCopier(self, lhs, rhs, copier):
+        check(lib().sg_op_assignCopier(self.h, lhs.h, rhs.h, copier))
+
+    def setAlphaAndBeta(self, alpha, beta):
+        check(lib().sg_op_setAlphaAndBeta(self.h, alpha, beta))
+
+    def computeCoeffsOTF(self, flag):
+        check(lib().sg_op_computeCoeffsOTF(self.h, int(flag)))
+
+    def diagonalScale(self, rhs, kappaWeighted=False):
+        check(lib().sg_op_diagonalScale(self.h, rhs.h, int(kappaWeighted)))
+
+    def divideByIdentityCoef(self, rhs):
+        check(lib().sg_op_divideByIdentityCoef(self.h, rhs.h))
+
+    def homogeneousCFInterp(self, phi):
+        check(lib().sg_op_homogeneousCFInterp(self.h, phi.h))
+
     def AMRNorm(self, coarResid, fineResid, refRat, ord_):
         out = C.c_double()
         check(lib().sg_op_AMRNorm(self.h, coarResid.h, _h(fineResid), refRat, ord_, C.byref(out)))
@@ -459,8 +508,9 @@ class AMRFASMultiGrid:
         check(lib().sg_solver_depth(self.h, 0, C.byref(out)))
         return out.value
 
-    def refresh(self):
-        check(lib().sg_solver_refresh(self.h))
+    def refresh(self, bcoef_only=False):
+        """after the finest coefficient fields changed; bcoef_only: B, Pi, zb, iceMask are unchanged (Picard iterations of one step)"""
+        check(lib().sg_solver_refresh_bcoef(self.h) if bcoef_only else lib().sg_solver_refresh(self.h))
 
     def cell_updates_per_cycle(self):
         out = C.c_double()

@@ -54,7 +54,7 @@ pvp, ip, dp = C.POINTER(C.c_void_p), C.POINTER(C.c_int), C.POINTER(C.c_double)
 SIGNATURES = {
     "sg_ctx_create": [pvp, ci, ci, ci, vp], "sg_ctx_destroy": [vp], "sg_ctx_sync": [vp], "sg_ctx_set_stream": [vp, vp],
     "sg_ctx_kernel_launches": [vp, C.POINTER(C.c_longlong)], "sg_nccl_unique_id": [vp],
-    "sg_ctx_event_record": [vp, ci], "sg_ctx_event_elapsed_ms": [vp, ci, ci, dp], "sg_solver_refresh": [vp], "sg_set_relax_mode": [vp, ci], "sg_set_tuning": [vp, ci, ci],
+    "sg_ctx_event_record": [vp, ci], "sg_ctx_event_elapsed_ms": [vp, ci, ci, dp], "sg_solver_refresh": [vp], "sg_solver_refresh_bcoef": [vp], "sg_set_relax_mode": [vp, ci], "sg_set_tuning": [vp, ci, ci],
     "sg_layout_create": [vp, pvp, ci, ip, ip, ip, ip], "sg_layout_coarsen": [vp, ci, pvp],
     "sg_layout_coarsenable": [vp, ci, ip], "sg_layout_nbox": [vp, ip], "sg_layout_destroy": [vp],
     "sg_partition_boxes": [ci, ip, ci, ip], "sg_partition_describe": [ci, ip, ip, ip, ip, ci, ci, ip, ip, C.POINTER(C.c_longlong)],
@@ -89,6 +89,12 @@ SIGNATURES = {
     "sg_op_AMRProlongS_2": [vp, vp, vp, vp], "sg_op_AMRUpdateResidual": [vp, vp, vp, vp],
     "sg_op_AMRNorm": [vp, vp, vp, ci, ci, dp], "sg_op_reflux": [vp, vp, vp, vp, vp], "sg_op_cfInterp": [vp, vp, vp], "sg_op_createCoarsened": [vp, pvp, vp, ci], "sg_op_zeroCovered": [vp, vp, vp],
     "sg_field_copyTo": [vp, vp, ci],
+    "sg_op_AMRRestrict": [vp, vp, vp, vp, vp, ci], "sg_op_AMRProlong": [vp, vp, vp],
+    "sg_op_preCond": [vp, vp, vp], "sg_op_preCond3": [vp, vp, vp, vp], "sg_op_getFlux": [vp, vp, vp, ci, ci, cd],
+    "sg_op_finerOperatorChanged": [vp, vp, ci], "sg_op_mDotProduct": [vp, vp, ci, pvp, dp],
+    "sg_op_buildCopier": [vp, pvp, vp, vp], "sg_op_assignCopier": [vp, vp, vp, vp], "sg_copier_destroy": [vp],
+    "sg_op_setAlphaAndBeta": [vp, cd, cd], "sg_op_computeCoeffsOTF": [vp, ci], "sg_op_diagonalScale": [vp, vp, ci],
+    "sg_op_divideByIdentityCoef": [vp, vp], "sg_op_homogeneousCFInterp": [vp, vp],
     "sg_cell_to_edge": [vp, vp, vp], "sg_edge_to_cell": [vp, vp, vp], "sg_mac_gradient": [vp, vp, dp, vp, vp],
     "sg_icemask_ec": [vp, vp, vp], "sg_compute_qw": [C.POINTER(Params), vp, vp, vp, vp],
     "sg_compute_scaprod": [vp, vp, vp, vp, vp], "sg_compute_dcoeff": [vp, vp, vp, vp, cd, ci],

@@ -897,6 +897,14 @@ extern "C" int sg_field_device_view(sg_field* f, void** base, long long* pitch, 
 // neighbouring ranks by ncclSend/ncclRecv.  Several (field, depth) requests share ONE NCCL group (one fused transfer kernel per
 // peer instead of one per field): the V-cycle is latency-bound on these exchanges at N > 1.
 struct GhostReq { sg_field* f; int depth; };
+// closes an NCCL group on every exit path (an error between group_start and group_end must not leave the group open)
+struct NcclGroup {
+  SgNccl& n; bool open = false;
+  explicit NcclGroup(SgNccl& a) : n(a) {}
+  int start() { int r = n.group_start(g_err); open = r == SG_OK; return r; }
+  int end() { open = false; return n.group_end(g_err); }
+  ~NcclGroup() { if (open) { std::string keep = g_err; n.group_end(g_err); g_err = keep; } }
+};
 static int fill_ghosts_multi(sg_ctx* c, const GhostReq* reqs, int n, cudaStream_t nccl_stream = nullptr) {
   if (!nccl_stream) nccl_stream = c->stream; // periodic wraps inside a patch always run on the main stream
   bool any_nccl = false;
@@ -921,7 +929,8 @@ static int fill_ghosts_multi(sg_ctx* c, const GhostReq* reqs, int n, cudaStream_
     any_nccl |= (L->nbr[2] >= 0 || L->nbr[3] >= 0);
   }
   if (!any_nccl) return SG_OK;
-  SGCALL(c->nccl.group_start(g_err));
+  NcclGroup grp(c->nccl);
+  SGCALL(grp.start());
   for (int q = 0; q < n; q++) {
     sg_field* f = reqs[q].f;
     const int depth = reqs[q].depth;
@@ -940,7 +949,7 @@ static int fill_ghosts_multi(sg_ctx* c, const GhostReq* reqs, int n, cudaStream_
       if (L->nbr[3] >= 0) SGCALL(c->nccl.send(p + (ptrdiff_t)(ny - depth) * L->pitch, cnt, L->nbr[3], nccl_stream, g_err));
     }
   }
-  SGCALL(c->nccl.group_end(g_err));
+  SGCALL(grp.end());
   return SG_OK;
 }
 static int fill_ghosts(sg_field* f, int depth) {
@@ -1427,7 +1436,11 @@ extern "C" int sg_op_relaxNF(sg_op* op, sg_field* phi, const sg_field* phi_coars
 static int apply_impl(sg_op* op, sg_field* out, sg_field* phi, const sg_field* rhs, int homogeneous, int mode, int slot, int ghost_depth = 1) {
   sg_layout* L = op->lay;
   sg_ctx* c = op->ctx;
-  if (!L->has_local) return SG_OK;
+  if (!L->has_local) {
+    // a rank without cells on this level still takes part in the allreduce of the norm: its contribution must be zero, not stale
+    if (mode == 2 || mode == 3) CK(cudaMemsetAsync(reinterpret_cast<unsigned long long*>(c->d_scalar) + slot, 0, sizeof(double), c->stream));
+    return SG_OK;
+  }
   if (!L->fast) {
     if (mode == 4) return fail(SG_ERR_UNSUPPORTED, "FAS coarse right-hand side accumulation exists on uniform (one-patch) levels only");
     return apply_g(op, out, phi, rhs, homogeneous, mode == 3 ? 2 : mode, slot, true);
@@ -1823,6 +1836,128 @@ extern "C" int sg_field_copyTo(sg_field* dst, const sg_field* src, int ghosts) {
   return copy_to_impl(dst, src, ghosts);
 }
 
+// ---- virtuals the FAS path never calls but a Chombo-side subclass inherits ---------------------------------------
+// AMRRestrict (src/AMRNonLinearPoissonOp.cpp:1011-1025): AMRRestrictS with a scratch created on the spot
+extern "C" int sg_op_AMRRestrict(sg_op* op, sg_field* res_coarse, const sg_field* residual, sg_field* correction,
+                                 const sg_field* coarse_correction, int skip_res) {
+  REQUIRE(op && res_coarse && residual, "AMRRestrict: null");
+  sg_field* scratch = nullptr;
+  SGCALL(ws_field(op->lay, 5, 1, &scratch));
+  return amr_restrict_impl(op, res_coarse, residual, correction, coarse_correction, scratch, skip_res);
+}
+// AMRProlong (:1073-1103): coarse correction copied onto the coarsened fine layout, PROLONGNL
+extern "C" int sg_op_AMRProlong(sg_op* op, sg_field* correction, const sg_field* coarse_correction) {
+  REQUIRE(op && correction && coarse_correction, "AMRProlong: null");
+  return amr_prolong_impl(op, correction, coarse_correction, nullptr, 0);
+}
+// preCond, 2- and 3-argument forms (src/VCAMRNonLinearPoissonOp.cpp:174-208,233-271).  "Preconditioner is not used for FAS solve".
+extern "C" int sg_op_preCond(sg_op* op, sg_field* phi, const sg_field* rhs) {
+  REQUIRE(op, "preCond: null op");
+  SGCALL(check_same(op, phi, "preCond(phi)")); SGCALL(check_same(op, rhs, "preCond(rhs)"));
+  sg_layout* L = op->lay;
+  if (L->has_local) LAUNCH(op->ctx, k_precond_init_g, grid_g(L, 0, 0), B2D, phi->cb(), rhs->cb(), L->d_patches, make_args_g(op));
+  return relax_impl(op, phi, rhs, 2);
+}
+extern "C" int sg_op_preCond3(sg_op* op, sg_field* phi, const sg_field* res, const sg_field* rhs) {
+  (void)res; // the initial guess from the residual is commented out in the reference (:254-265)
+  REQUIRE(op, "preCond: null op");
+  SGCALL(check_same(op, phi, "preCond(phi)")); SGCALL(check_same(op, rhs, "preCond(rhs)"));
+  return relax_impl(op, phi, rhs, 2);
+}
+// getFlux, FluxBox form (src/VCAMRNonLinearPoissonOp.H:226-241 over VCAMRNonLinearPoissonOp.cpp:792-841): one direction per call
+extern "C" int sg_op_getFlux(sg_op* op, sg_field* flux, const sg_field* phi, int dir, int ref, double scale) {
+  REQUIRE(op && flux && phi && (dir == 0 || dir == 1), "getFlux: bad arguments (CH_assert(a_dir >= 0 && a_dir < SpaceDim))");
+  REQUIRE(flux->cent == (dir == 0 ? SG_XFACE : SG_YFACE), "getFlux: flux must be face-centred in `dir` (CH_assert on the box type)");
+  SGCALL(check_same(op, phi, "getFlux(phi)")); SGCALL(check_same(op, flux, "getFlux(flux)"));
+  REQUIRE(phi->ng >= 1, "getFlux: phi needs a ghost cell (CH_assert(a_data.box().contains(ivlo)))");
+  sg_layout* L = op->lay;
+  if (!L->has_local) return SG_OK;
+  const sg_field* bf = dir == 0 ? op->bX : op->bY;
+  LAUNCH(op->ctx, k_get_flux_g, grid_g(L, dir == 0, dir == 1), B2D, flux->cb(), phi->cb(), bf->cb(), L->d_patches, dir, op->beta * ref / op->dx[dir], scale);
+  return SG_OK;
+}
+// finerOperatorChanged (src/VCAMRNonLinearPoissonOp.cpp:1353-1438): multigrid coarsening of ALL operator data from `finer`
+extern "C" int sg_op_finerOperatorChanged(sg_op* op, const sg_op* finer, int coarsening_factor) {
+  REQUIRE(op && finer && coarsening_factor >= 1, "finerOperatorChanged: bad arguments");
+  sg_layout *Lc = op->lay, *Lf = finer->lay;
+  if (coarsening_factor != 1) {
+    if (!Lc->fast || !Lf->fast) return fail(SG_ERR_UNSUPPORTED, "finerOperatorChanged: multigrid operators exist below the base AMR level only (one patch per GPU)");
+    REQUIRE(op->owns_coefs, "finerOperatorChanged: this operator aliases the caller's coefficient fields (depth 0)");
+    REQUIRE(Lc->nx * coarsening_factor == Lf->nx && Lc->ny * coarsening_factor == Lf->ny, "finerOperatorChanged: layouts do not differ by the coarsening factor");
+    sg_field* cc[7] = {op->aCoef, op->B, op->Pi, op->zb, op->mask, op->bX, op->bY};
+    const sg_field* cf[7] = {finer->aCoef, finer->B, finer->Pi, finer->zb, finer->mask, finer->bX, finer->bY};
+    for (int k = 0; k < 7; k++) {
+      if (Lc->has_local) CK(cudaMemsetAsync(cc[k]->base, 0, cc[k]->comp_stride * sizeof(double), op->ctx->stream)); // setVal(0.) on whole FABs
+      if (k < 5) SGCALL(avg_cell(cc[k], cf[k], coarsening_factor));
+      else SGCALL(avg_face(cc[k], cf[k], coarsening_factor));
+    }
+  }
+  SGCALL(coef_ghosts(op, false)); // exchange(): box-to-box ghosts are the neighbours' cells in the merged storage
+  return op_scan_mask(op);        // lambda is recomputed in the kernels; the mask-skip decision is what "needs resetting" here
+}
+// LevelDataOps::mDotProduct (src/AMRNonLinearPoissonOp.cpp:624-632)
+extern "C" int sg_op_mDotProduct(sg_op* op, const sg_field* a, int n, const sg_field* const* b, double* out) {
+  REQUIRE(op && a && n >= 0 && (n == 0 || (b && out)), "mDotProduct: bad arguments");
+  for (int k = 0; k < n; k++) SGCALL(sg_op_dotProduct(op, a, b[k], out + k));
+  return SG_OK;
+}
+// buildCopier / assignCopier (:577-597): Copier(rhs layout -> lhs layout, no ghost cells); the plan lives in the copy-plan cache
+struct sg_copier { const sg_layout* src; const sg_layout* dst; };
+extern "C" int sg_op_buildCopier(sg_op* op, sg_copier** out, const sg_field* lhs, const sg_field* rhs) {
+  REQUIRE(op && out && lhs && rhs, "buildCopier: null");
+  sg_copier* c = new sg_copier();
+  c->src = rhs->lay; c->dst = lhs->lay;
+  *out = c;
+  return SG_OK;
+}
+extern "C" int sg_op_assignCopier(sg_op* op, sg_field* lhs, const sg_field* rhs, const sg_copier* copier) {
+  REQUIRE(op && lhs && rhs && copier, "assignCopier: null");
+  REQUIRE(copier->src == rhs->lay && copier->dst == lhs->lay, "assignCopier: copier was built for other layouts");
+  return copy_to_impl(lhs, rhs, 0);
+}
+extern "C" int sg_copier_destroy(sg_copier* c) { delete c; return SG_OK; }
+// setAlphaAndBeta / computeCoeffsOTF (src/VCAMRNonLinearPoissonOp.cpp:462-475)
+extern "C" int sg_op_setAlphaAndBeta(sg_op* op, double alpha, double beta) {
+  REQUIRE(op, "setAlphaAndBeta: null op");
+  REQUIRE(alpha == 0.0 || op->aCoef, "setAlphaAndBeta: alpha != 0 needs an aCoef field");
+  op->alpha = alpha; op->beta = beta; // lambda is never stored: nothing to reset ...
+  return coef_ghosts(op, false);      // ... but with alpha != 0 the halo rows of aCoef on periodic / neighbour-GPU sides are now read
+}
+extern "C" int sg_op_computeCoeffsOTF(sg_op* op, int update_operator) {
+  REQUIRE(op, "computeCoeffsOTF: null op");
+  op->update_operator = update_operator != 0;
+  return SG_OK;
+}
+// diagonalScale / divideByIdentityCoef (src/VCAMRNonLinearPoissonOp.H:157-175, "For TGA"): rhs *= aCoef, rhs /= aCoef
+extern "C" int sg_op_diagonalScale(sg_op* op, sg_field* rhs, int kappa_weighted) {
+  (void)kappa_weighted;
+  REQUIRE(op && rhs && op->aCoef, "diagonalScale: null");
+  SGCALL(check_same(op, rhs, "diagonalScale(rhs)"));
+  return vec_launch<5>(rhs, op->aCoef, nullptr, 0, 0, false);
+}
+extern "C" int sg_op_divideByIdentityCoef(sg_op* op, sg_field* rhs) {
+  REQUIRE(op && rhs && op->aCoef, "divideByIdentityCoef: null");
+  SGCALL(check_same(op, rhs, "divideByIdentityCoef(rhs)"));
+  return vec_launch<6>(rhs, op->aCoef, nullptr, 0, 0, false);
+}
+// homogeneousCFInterp (src/AMRNonLinearPoissonOp.cpp:1599-1795): dead under FAS (m_use_FAS hard-wired), kept for the surface
+extern "C" int sg_op_homogeneousCFInterp(sg_op* op, sg_field* phi) {
+  REQUIRE(op && phi, "homogeneousCFInterp: null");
+  REQUIRE(phi->ng >= 1, "homogeneousCFInterp: phi needs one ghost cell (CH_assert)");
+  AmrLink* K = op->link;
+  if (!K) return SG_OK; // no coarser level: the CF region is empty
+  SGCALL(check_same(op, phi, "homogeneousCFInterp(phi)"));
+  CFHomo h;
+  for (int d = 0; d < 2; d++) {
+    const double dxf = op->dx[d], dxc = 2 * op->dx[d]; // m_dxCrse_vect = refRatio * dx
+    h.c1[d] = 2 * (dxc - dxf) / (dxc + dxf); h.c2[d] = -(dxc - dxf) / (dxc + 3 * dxf); h.factor[d] = 1 - 2 * dxf / (dxf + dxc);
+  }
+  if (K->ncf)
+    for (int comp = 0; comp < phi->ncomp; comp++)
+      LAUNCH(op->ctx, k_cf_homogeneous, (K->ncf + 127) / 128, 128, phi->cb(comp), K->d_cf, K->ncf, h);
+  return SG_OK;
+}
+
 // ------------------------------------------------------------------------------------------------
 // FAS multigrid driver, device resident (absent fork's AMRFASMultiGrid / MultiGrid; see DESIGN.md for the
 // inferred pieces, identical to oracle/suhmo_oracle.c)
@@ -1873,6 +2008,24 @@ extern "C" int sg_solver_refresh(sg_solver* s) {
     if (d > 0) SGCALL(average_coefficients(s->fac, s->ops[d], 0, 1 << d));
     SGCALL(coef_ghosts(s->ops[d], false));
     SGCALL(op_scan_mask(s->ops[d]));
+  }
+  return SG_OK;
+}
+// same, for the coefficients that change between the Picard iterations of one time step only (aCoef, bCoef)
+extern "C" int sg_solver_refresh_bcoef(sg_solver* s) {
+  REQUIRE(s, "sg_solver_refresh_bcoef: null");
+  for (size_t d = 0; d < s->ops.size(); d++) {
+    sg_op* op = s->ops[d];
+    if (d > 0) {
+      if (s->fac->alpha != 0.0) SGCALL(avg_cell(op->aCoef, s->fac->aCoef[0], 1 << d));
+      SGCALL(avg_face(op->bX, s->fac->bX[0], 1 << d));
+      SGCALL(avg_face(op->bY, s->fac->bY[0], 1 << d));
+    }
+    if (has_ghost_sides(op->lay)) {
+      const int gd = coef_ghost_depth(op);
+      GhostReq r[3] = {{op->bX, gd}, {op->bY, gd}, {op->aCoef, gd}};
+      SGCALL(fill_ghosts_multi(op->ctx, r, op->alpha != 0.0 ? 3 : 2));
+    }
   }
   return SG_OK;
 }
@@ -2052,10 +2205,23 @@ static int run_cycle(sg_solver* s, sg_field* const* phi, sg_field* const* rhs, i
     SGCALL(vcycle(s, phi, rhs, l_max, sp, iter));
     return residual_norm(s, phi, rhs, l_max, normslot);
   }
-  std::vector<long long> key = {l_max, sp->pre, sp->post, sp->bottom, c->relax_mode, c->tune[0], (long long)(size_t)c->stream};
+  // Everything a captured kernel names or a launch shape depends on: parameters, every tuning knob, the fields, and -- because the
+  // out-of-place smoother swaps a field's buffer with the layout's scratch buffer (ws slot 0) -- the scratch buffers of every
+  // level and depth: a public relax with an odd sweep count on ANOTHER field of the same layout hands that field the scratch the
+  // graph would still write to.
+  std::vector<long long> key = {l_max, sp->pre, sp->post, sp->bottom, c->relax_mode, (long long)(size_t)c->stream};
+  for (int k = 0; k < 8; k++) key.push_back(c->tune[k]);
+  auto scratch_of = [](const sg_layout* L) { return (long long)(size_t)((!L->ws.empty() && L->ws[0]) ? L->ws[0]->base : nullptr); };
   for (int l = 0; l <= l_max; l++) { key.push_back((long long)(size_t)phi[l]->base); key.push_back((long long)(size_t)rhs[l]->base); }
-  for (sg_op* op : s->aops) { key.push_back((long long)(size_t)op->bX->base); key.push_back((long long)(size_t)op->B->base); key.push_back(op->mask_needed); }
-  for (sg_op* op : s->ops) key.push_back(op->mask_needed);
+  for (sg_op* op : s->aops) {
+    key.push_back((long long)(size_t)op->bX->base); key.push_back((long long)(size_t)op->bY->base); key.push_back((long long)(size_t)op->B->base);
+    key.push_back((long long)(size_t)op->Pi->base); key.push_back((long long)(size_t)op->zb->base); key.push_back((long long)(size_t)op->mask->base);
+    key.push_back(op->mask_needed); key.push_back(scratch_of(op->lay));
+  }
+  for (size_t d = 0; d < s->ops.size(); d++) {
+    key.push_back(s->ops[d]->mask_needed); key.push_back(scratch_of(s->ops[d]->lay));
+    if (s->phi[d]) key.push_back((long long)(size_t)s->phi[d]->base);
+  }
   if (s->gexec && key == s->gkey) {
     CK(cudaGraphLaunch(s->gexec, c->stream));
     c->launches += s->glaunches;
@@ -2063,6 +2229,11 @@ static int run_cycle(sg_solver* s, sg_field* const* phi, sg_field* const* rhs, i
     if (s->gexec) { cudaGraphExecDestroy(s->gexec); s->gexec = nullptr; }
     long long l0 = c->launches;
     cudaGraph_t g = nullptr;
+    // buffer ownership before the capture: an aborted capture may stop between two swaps of the out-of-place smoother
+    std::vector<std::pair<sg_field*, double*>> saved;
+    auto remember = [&](sg_field* f) { if (f) saved.push_back({f, f->base}); };
+    for (int l = 0; l <= l_max; l++) { remember(phi[l]); if (!s->aops[l]->lay->ws.empty()) remember(s->aops[l]->lay->ws[0]); }
+    for (size_t d = 0; d < s->ops.size(); d++) { remember(s->phi[d]); if (!s->ops[d]->lay->ws.empty()) remember(s->ops[d]->lay->ws[0]); }
     CK(cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal));
     int r = vcycle(s, phi, rhs, l_max, sp, iter);
     if (r == SG_OK) r = residual_norm(s, phi, rhs, l_max, FIX);
@@ -2070,6 +2241,7 @@ static int run_cycle(sg_solver* s, sg_field* const* phi, sg_field* const* rhs, i
     if (r != SG_OK || e != cudaSuccess || !g) { // something in the cycle cannot be captured: run it the ordinary way from now on
       if (g) cudaGraphDestroy(g);
       cudaGetLastError();
+      for (auto& kv : saved) kv.first->base = kv.second; // nothing captured has run: the buffers are as they were
       c->tune[2] = 1;
       c->launches = l0;
       SGCALL(vcycle(s, phi, rhs, l_max, sp, iter));
@@ -2099,8 +2271,12 @@ extern "C" int sg_solver_solve(sg_solver* s, sg_field* const* phi, sg_field* con
     SGCALL(check_same(s->aops[l], phi[l], "solve(phi)")); SGCALL(check_same(s->aops[l], rhs[l], "solve(rhs)"));
   }
   long long l0 = c->launches;
-  cudaEvent_t e0, e1;
-  CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
+  struct Events { // destroyed on every exit path
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    ~Events() { if (e0) cudaEventDestroy(e0); if (e1) cudaEventDestroy(e1); }
+  } evs;
+  CK(cudaEventCreate(&evs.e0)); CK(cudaEventCreate(&evs.e1));
+  cudaEvent_t e0 = evs.e0, e1 = evs.e1;
   double initial = 0, rnorm = 0;
   SGCALL(residual_norm(s, phi, rhs, l_max, 2));
   SGCALL(fetch_scalar(c, 2, &initial));
@@ -2148,7 +2324,6 @@ extern "C" int sg_solver_solve(sg_solver* s, sg_field* const* phi, sg_field* con
     stats->cell_updates = per * iter; stats->device_ms = ms;
     stats->kernel_launches = c->launches - l0;
   }
-  cudaEventDestroy(e0); cudaEventDestroy(e1);
   return SG_OK;
 }
 

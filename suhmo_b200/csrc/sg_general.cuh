@@ -127,6 +127,38 @@ __global__ void __launch_bounds__(256) k_vec_g(double* __restrict__ y, const dou
   if (OP == 2) y[o] = y[o] * a;
   if (OP == 3) y[o] = x[o];
   if (OP == 4) y[o] = a;
+  if (OP == 5) y[o] = y[o] * x[o];
+  if (OP == 6) y[o] = y[o] / x[o];
+}
+
+// VCAMRNonLinearPoissonOp::preCond's initial guess (src/VCAMRNonLinearPoissonOp.cpp:196-205): phi = rhs / lambda on the valid cells,
+// lambda (the diagonal) recomputed from the face coefficients as everywhere else
+__global__ void __launch_bounds__(256) k_precond_init_g(double* __restrict__ phib, const double* __restrict__ rhsb,
+                                                        const PatchG* __restrict__ tab, OpArgsG a) {
+  const PatchG g = tab[blockIdx.z];
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  int j = blockIdx.y * blockDim.y + threadIdx.y;
+  if (i >= g.nx || j >= g.ny) return;
+  ptrdiff_t o = g.off + (ptrdiff_t)j * g.pitch + i;
+  double ac = a.has_a ? a.aC[o] : 0.0;
+  double lam = lambda_cell(a.alpha, ac, a.beta, a.bX[o], a.bX[o + 1], a.bY[o], a.bY[o + g.pitch], a.dxi0, a.dxi1);
+  phib[o] = rhsb[o] / lam;
+}
+
+// VCAMRNonLinearPoissonOp::getFlux (src/VCAMRNonLinearPoissonOp.cpp:792-841 under the FluxBox form, VCAMRNonLinearPoissonOp.H:226-241):
+// flux = -bCoef * ((phi_hi - phi_lo) * s) * scale on every face of direction `dir` of every patch, s = beta*ref/dx[dir]
+__global__ void __launch_bounds__(256) k_get_flux_g(double* __restrict__ fluxb, const double* __restrict__ phib,
+                                                    const double* __restrict__ bfb, const PatchG* __restrict__ tab, int dir, double s,
+                                                    double scale) {
+  const PatchG g = tab[blockIdx.z];
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  int j = blockIdx.y * blockDim.y + threadIdx.y;
+  if (i >= g.nx + (dir == 0) || j >= g.ny + (dir == 1)) return;
+  ptrdiff_t o = g.off + (ptrdiff_t)j * g.pitch + i;
+  double phihi = phib[o], philo = phib[o - (dir == 0 ? 1 : g.pitch)];
+  double gradphi = (phihi - philo) * s;
+  double f = -bfb[o] * gradphi;
+  fluxb[o] = f * scale;
 }
 
 // reductions over valid cells of all patches: mode 0 max|x| (exact), 1 sum|x|, 2 sum x^2, 3 sum x*y (fixed-shape partials)
@@ -351,6 +383,20 @@ __global__ void __launch_bounds__(128) k_cf_interp(double* __restrict__ fineb, c
   const double bq = (pb - pa) / h - a * h;
   const double x = 2. * h;
   fineb[it.fo] = a * x * x + bq * x + pa;
+}
+
+// AMRNonLinearPoissonOp::homogeneousCFInterp (src/AMRNonLinearPoissonOp.cpp:1599-1795; dead under FAS): the coarse-fine ghost
+// cells of k_cf_interp's table get c1*phi(near) + c2*phi(far); patches one cell wide in the normal direction (pad = 1): factor*phi(near)
+struct CFHomo { double c1[2], c2[2], factor[2]; }; // per normal direction (m_dx_vect[a_idir], m_dxCrse_vect[a_idir])
+__global__ void __launch_bounds__(128) k_cf_homogeneous(double* __restrict__ fineb, const CFItem* __restrict__ items, int n, CFHomo h) {
+  int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n) return;
+  const CFItem it = items[t];
+  const int dir = (it.fstep == 1 || it.fstep == -1) ? 0 : 1;
+  const double pb = fineb[it.fo + it.fstep];
+  if (it.pad) { fineb[it.fo] = h.factor[dir] * pb; return; }
+  const double pa = fineb[it.fo + 2 * (ptrdiff_t)it.fstep];
+  fineb[it.fo] = h.c1[dir] * pb + h.c2[dir] * pa;
 }
 
 // Flux register (VCAMRNonLinearPoissonOp::reflux over LevelFluxRegister; oracle: orc_op_reflux), in two halves so that the

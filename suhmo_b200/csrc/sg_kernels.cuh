@@ -832,9 +832,11 @@ __global__ void __launch_bounds__(128, 3) k_gsrb_pair(FusedArgs f) {
 // MODE 0: out = L(phi);  1: out = rhs - L(phi);  2: as 1 plus max|out| accumulated into *norm_bits;  3: only the max-norm of
 // rhs - L(phi) (nothing stored: the solver's residual norm);  4: out += L(phi) (FAS coarse right-hand side, fuses the incr)
 // ------------------------------------------------------------------------------------------------
+// max that keeps a NaN (fmax drops it): a diverged relaxation must show up in the residual norm, not vanish from it
+__device__ __forceinline__ double nanmax(double a, double b) { return a != a ? a : (b != b ? b : fmax(a, b)); }
 __device__ __forceinline__ void block_max_to_global(double v, unsigned long long* dst) {
-  // non-negative doubles order like their bit patterns
-  for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
+  // non-negative doubles order like their bit patterns (+NaN above +inf, so atomicMax keeps a NaN too)
+  for (int o = 16; o > 0; o >>= 1) v = nanmax(v, __shfl_xor_sync(0xffffffffu, v, o));
   __shared__ double wmax[32];
   int lane = threadIdx.x & 31, w = (threadIdx.y * blockDim.x + threadIdx.x) >> 5;
   int nw = (blockDim.x * blockDim.y + 31) >> 5;
@@ -842,8 +844,8 @@ __device__ __forceinline__ void block_max_to_global(double v, unsigned long long
   __syncthreads();
   if (w == 0) {
     v = lane < nw ? wmax[lane] : 0.0;
-    for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
-    if (lane == 0) atomicMax(dst, (unsigned long long)__double_as_longlong(v));
+    for (int o = 16; o > 0; o >>= 1) v = nanmax(v, __shfl_xor_sync(0xffffffffu, v, o));
+    if (lane == 0) atomicMax(dst, (unsigned long long)__double_as_longlong(fabs(v)));
   }
 }
 
@@ -874,7 +876,7 @@ __global__ void __launch_bounds__(256) k_apply(double* __restrict__ out, const d
         if (MODE != 3) out[o] = r;
       }
     }
-    rmax = fmax(rmax, fabs(r));
+    rmax = nanmax(rmax, fabs(r));
   }
   if (MODE == 2 || MODE == 3) block_max_to_global(rmax, norm_bits);
 }
@@ -1132,7 +1134,7 @@ __global__ void __launch_bounds__(256) k_avg_face_multi_y(const double* __restri
 // ------------------------------------------------------------------------------------------------
 // vector ops over the valid region (LevelDataOps)
 // ------------------------------------------------------------------------------------------------
-// op 0: y = a*x + b*z ; 1: y = y + a*x ; 2: y = y*a ; 3: y = x (copy) ; 4: y = a (set)
+// op 0: y = a*x + b*z ; 1: y = y + a*x ; 2: y = y*a ; 3: y = x (copy) ; 4: y = a (set) ; 5: y = y*x ; 6: y = y/x
 template <int OP>
 __global__ void __launch_bounds__(256) k_vec(double* __restrict__ y, const double* __restrict__ x, const double* __restrict__ z,
                                              double a, double b, int pitch, int i0, int i1, int j0, int j1) {
@@ -1145,6 +1147,8 @@ __global__ void __launch_bounds__(256) k_vec(double* __restrict__ y, const doubl
   if (OP == 2) y[o] = y[o] * a;
   if (OP == 3) y[o] = x[o];
   if (OP == 4) y[o] = a;
+  if (OP == 5) y[o] = y[o] * x[o];
+  if (OP == 6) y[o] = y[o] / x[o];
 }
 
 // reductions: mode 0 max|x| (exact, order independent), 1 sum|x|, 2 sum x^2, 3 sum x*y.

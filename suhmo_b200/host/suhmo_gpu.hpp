@@ -156,6 +156,27 @@ class VCAMRNonLinearPoissonOp {
   LevelData* createCoarsened(const LevelData& fine, int refRat = 2) { sg_field* f; SG_DO(sg_op_createCoarsened(h, &f, fine.h, refRat)); return new LevelData(f); }
   // m_lambda as the reference stores it (the diagonal itself, src/VCAMRNonLinearPoissonOp.cpp:505-534)
   void lambda(LevelData& out) { SG_DO(sg_op_lambda(h, out.h)); }
+  // ---- virtuals the FAS path never calls (src/AMRNonLinearPoissonOp.cpp:577-632,1011-1103,1599-1795; VCAMRNonLinearPoissonOp.{H,cpp})
+  void AMRRestrict(LevelData& resCoarse, const LevelData& residual, LevelData& correction, const LevelData* coarseCorrection, bool skip_res = false)
+  { SG_DO(sg_op_AMRRestrict(h, resCoarse.h, residual.h, correction.h, hp(coarseCorrection), skip_res)); }
+  void AMRProlong(LevelData& correction, const LevelData& coarseCorrection) { SG_DO(sg_op_AMRProlong(h, correction.h, coarseCorrection.h)); }
+  void preCond(LevelData& correction, const LevelData& residual) { SG_DO(sg_op_preCond(h, correction.h, residual.h)); }
+  void preCond(LevelData& correction, const LevelData& residual, const LevelData& rhs) { SG_DO(sg_op_preCond3(h, correction.h, residual.h, rhs.h)); }
+  // getFlux(FluxBox&, data, grid, dit, scale): one direction of the FluxBox per call, every box of the level at once
+  void getFlux(LevelData& flux, const LevelData& data, int dir, int ref = 1, double scale = 1.0) { SG_DO(sg_op_getFlux(h, flux.h, data.h, dir, ref, scale)); }
+  void finerOperatorChanged(const VCAMRNonLinearPoissonOp& a_operator, int coarseningFactor) { SG_DO(sg_op_finerOperatorChanged(h, a_operator.h, coarseningFactor)); }
+  void mDotProduct(const LevelData& a, int sz, const LevelData* const b[], double mdots[]) {
+    std::vector<const sg_field*> p;
+    for (int k = 0; k < sz; k++) p.push_back(b[k]->h);
+    SG_DO(sg_op_mDotProduct(h, a.h, sz, p.data(), mdots));
+  }
+  sg_copier* buildCopier(const LevelData& lhs, const LevelData& rhs) { sg_copier* c; SG_DO(sg_op_buildCopier(h, &c, lhs.h, rhs.h)); return c; }
+  void assignCopier(LevelData& lhs, const LevelData& rhs, const sg_copier* copier) { SG_DO(sg_op_assignCopier(h, lhs.h, rhs.h, copier)); }
+  void setAlphaAndBeta(double alpha, double beta) { SG_DO(sg_op_setAlphaAndBeta(h, alpha, beta)); }
+  void computeCoeffsOTF(bool update) { SG_DO(sg_op_computeCoeffsOTF(h, update)); }
+  void diagonalScale(LevelData& rhs, bool kappaWeighted = false) { SG_DO(sg_op_diagonalScale(h, rhs.h, kappaWeighted)); }
+  void divideByIdentityCoef(LevelData& rhs) { SG_DO(sg_op_divideByIdentityCoef(h, rhs.h)); }
+  void homogeneousCFInterp(LevelData& phi) { SG_DO(sg_op_homogeneousCFInterp(h, phi.h)); }
 };
 
 class VCAMRNonLinearPoissonOpFactory {
@@ -217,7 +238,7 @@ class AMRFASMultiGrid {
     if (resnorm) resnorm->assign(hist.begin(), hist.begin() + st.iterations + 1);
     return st.iterations;
   }
-  void refresh() { SG_DO(sg_solver_refresh(h)); }
+  void refresh(bool bcoefOnly = false) { SG_DO(bcoefOnly ? sg_solver_refresh_bcoef(h) : sg_solver_refresh(h)); }
   int depth(int level = 0) const { int n; SG_DO(sg_solver_depth(h, level, &n)); return n; }
   double cellUpdatesPerCycle() const { double v; SG_DO(sg_solver_cell_updates_per_cycle(h, &params, &v)); return v; }
 };

@@ -94,13 +94,19 @@ def fields_equal(gpu_ld, orc_field, valid_only=True):
     """max abs difference and exact-equality flag between a device field and an oracle field (valid cells)."""
     g = gpu_ld.get_global()
     o = orc_field.get_global()
-    m = ~np.isnan(o) & ~np.isnan(g)
+    # NaN marks cells no box of the level holds (get_global's fill) -- and a diverged computation.  The two patterns must agree
+    # before the finite values are compared: a NaN on the device where the oracle is finite is a failure, not a hole.
+    if not np.array_equal(np.isnan(g), np.isnan(o)):
+        return float("inf"), False
+    m = ~np.isnan(o)
     diff = np.abs(g[m] - o[m])
     return (float(diff.max()) if diff.size else 0.0), bool(np.array_equal(g[m], o[m]))
 
 
 def rel_l2(a, b):
-    m = ~np.isnan(a) & ~np.isnan(b)
+    if not np.array_equal(np.isnan(a), np.isnan(b)):
+        return float("inf")
+    m = ~np.isnan(b)
     den = np.sqrt(np.sum(b[m] ** 2))
     return float(np.sqrt(np.sum((a[m] - b[m]) ** 2)) / (den if den > 0 else 1.0))
 

@@ -1,5 +1,6 @@
 """The C++ host layer (suhmo_b200/host/suhmo_gpu.hpp) over the C ABI: compiled with g++ everywhere; on the GPU box the
-program drives a two-level head solve the way AmrHydro::SolveForHead_nl drives the reference."""
+program drives a two-level head solve the way AmrHydro::SolveForHead_nl drives the reference and asserts BIT equality of the head and
+the residual history with the oracle fixture tests/golden/host_smoke_2lev.bin, then drives the remaining wrappers on the device."""
 import os
 import subprocess
 
@@ -40,6 +41,6 @@ def test_whole_cpp_mirror_links_without_a_gpu():
 @pytest.mark.gpu
 def test_cpp_host_layer_solves_two_levels():
     exe = compile_host()
-    r = subprocess.run([exe], capture_output=True, text=True, timeout=300)
+    r = subprocess.run([exe, os.path.join(ROOT, "tests", "golden", "host_smoke_2lev.bin")], capture_output=True, text=True, timeout=300)
     assert r.returncode == 0, r.stdout + r.stderr
-    assert "host_smoke: OK" in r.stdout
+    assert "host_smoke: OK" in r.stdout and "0 differ" in r.stdout
