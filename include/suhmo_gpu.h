@@ -202,6 +202,9 @@ int sg_op_AverageOperator(sg_op* op, const sg_op* finest, int depth);
 /* resetLambda / computeLambda (VCAMRNonLinearPoissonOp.cpp:505-547): lambda is recomputed inside the kernels;
    this materialises it for inspection. */
 int sg_op_lambda(sg_op* op, sg_field* lambda_out);
+/* 1 when this operator's kernels read the ice-mask array, 0 when the level holds no negative entry and the array is skipped
+   (the mask only enters through `mask < 0` in COMPUTENONLINEARTERMS, src/AmrHydroF.ChF:40): decides the bytes a sweep moves */
+int sg_op_streams_mask(const sg_op* op, int* out);
 /* createCoarser / create (src/AMRNonLinearPoissonOp.cpp:519-526,753-766) */
 int sg_op_createCoarser(sg_op* op, sg_field** coarse, const sg_field* fine, int ghosted);
 int sg_op_create(sg_op* op, sg_field** lhs, const sg_field* rhs);
@@ -369,7 +372,8 @@ int sg_set_relax_mode(sg_ctx* ctx, int mode);
    per four (communication-avoiding relaxation off); key 4: block shape of the residual/applyOp kernel, 1 = 32x8 threads with one
    row per thread, 100*bx + rows = (bx, 256/bx) threads x rows per thread (rows 1|4|8|16|32); key 5: coarse rows per thread of the
    restriction kernel (1|4|8|16); key 6: 1 = halo exchanges of the smoother stay on the main stream (no overlap with the interior
-   part of the sweep; N > 1 only) */
+   part of the sweep; N > 1 only); key 7: 1 = refined (patch-table) levels keep the exchange-per-colour flow instead of the fused
+   per-patch sweep */
 int sg_set_tuning(sg_ctx* ctx, int key, int value);
 
 /* ------------------------------------------------------------------ implicit gap-height solve ------------- */

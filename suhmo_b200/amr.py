@@ -288,6 +288,11 @@ class VCAMRNonLinearPoissonOp:
     def lambda_(self, out):
         check(lib().sg_op_lambda(self.h, out.h))
 
+    def streams_mask(self):
+        out = C.c_int()
+        check(lib().sg_op_streams_mask(self.h, C.byref(out)))
+        return bool(out.value)
+
     def createCoarser(self, fine, ghosted=True):
         h = C.c_void_p()
         check(lib().sg_op_createCoarser(self.h, C.byref(h), fine.h, int(ghosted)))

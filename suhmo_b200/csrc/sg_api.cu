@@ -128,6 +128,12 @@ struct sg_layout {
   std::vector<GPatch> gp;
   int gbin_s = 0, gbin_nx = 0, gbin_ny = 0;
   std::vector<std::vector<int>> gbins;
+  // fused per-patch smoother (k_gsrb_patch): ghost-cell records, built on first use.  0 not tried, 1 usable, -1 not usable
+  // (a same-level neighbour box lives on another GPU, or a patch does not fit the shared-memory tile)
+  int fused_state = 0;
+  GRec* d_grec = nullptr;
+  int* d_grec_start = nullptr;
+  size_t fused_smem = 0;
 };
 #define GEN_GX 2
 #define GEN_GY 2
@@ -638,6 +644,7 @@ extern "C" int sg_layout_destroy(sg_layout* L) {
   for (sg_field* w : L->ws) sg_field_destroy(w);
   copy_plans_forget(L);
   cudaFree(L->d_patches);
+  cudaFree(L->d_grec); cudaFree(L->d_grec_start);
   plan_free(L->ex_faces);
   for (int k = 0; k < 3; k++) plan_free(L->ex_full[k]);
   delete L;
@@ -1598,6 +1605,13 @@ extern "C" int sg_op_AverageOperator(sg_op* op, const sg_op* finest, int depth) 
     SGCALL(avg_face(op->bY, finest->bY, coarsening));
   }
   SGCALL(coef_ghosts(op, true));
+  return SG_OK;
+}
+// does the smoother of this operator stream the ice mask?  (0: the level holds no negative mask entry, see op_scan_mask; the
+// sweep then moves 64 instead of 72 bytes per cell-update -- what a roofline figure must be computed with)
+extern "C" int sg_op_streams_mask(const sg_op* op, int* out) {
+  REQUIRE(op && out, "sg_op_streams_mask: null");
+  *out = (op->lay->fast && !op->mask_needed) ? 0 : 1;
   return SG_OK;
 }
 extern "C" int sg_op_lambda(sg_op* op, sg_field* lam) {

@@ -89,6 +89,121 @@ __global__ void __launch_bounds__(256) k_gsrb_color_g(double* __restrict__ phib,
   phib[o] = pc + (rhsb[o] - lof) / denom;
 }
 
+// ------------------------------------------------------------------------------------------------
+// Fused red+black GSRB iteration on a patch table: ONE launch = one levelGSRB iteration over every patch of a refined level,
+// out of place (phi_in -> phi_out), no exchange and no BC kernel between the colours.  One CTA per patch:
+//  * the patch's phi (one ghost ring) lives in shared memory; coefficients are read from global memory where they are used;
+//  * a ghost cell that is a VALID cell of a same-level neighbour patch is read straight from the owner's array (all patches of a
+//    level on one GPU share one allocation) and, when it is red, its red update is recomputed here from the owner's data -- its own
+//    coefficients and its three outer neighbours as the OWNER sees them (another patch's valid cell, the owner's coarse-fine
+//    ghost cell, or the physical boundary condition evaluated on the fly).  That is the ring recompute of k_gsrb_stream, with a
+//    per-ghost-cell record (GRec) instead of a uniform side kind, because one patch side may mix neighbours, coarse-fine
+//    interface and (at concave corners) two different owners' views of the same uncovered cell;
+//  * coarse-fine ghost cells hold QuadCFInterp's value, fixed through the sweep as in the reference (relaxNF interpolates once,
+//    src/AMRNonLinearPoissonOp.cpp:690-704); they are copied to phi_out so that they survive the buffer swap;
+//  * physical-boundary ghosts are evaluated on the fly from the cell being updated (mixBCValues before each colour refills them
+//    from the first interior cell, which is that cell).
+// Same arithmetic in the same order as k_gsrb_color_g: bit-identical results.
+// ------------------------------------------------------------------------------------------------
+struct GRec {
+  int own;        // offset (from the component base) of the ghost cell in its owner's array; meaningful when kind == 0
+  int nb[3];      // the ghost cell's outer neighbours (outward, tangential low, tangential high): offset >= 0, or -2 - s: physical side s
+  int own_pitch;  // owner's row pitch (north face coefficient = bY[own + own_pitch])
+  int kind;       // 0 valid cell of a same-level patch on this GPU; 1 fixed (coarse-fine ghost); 2 outside the domain (on-the-fly BC)
+};
+
+__device__ __forceinline__ double gsrb_point(const OpArgsG& a, double pc, double pw, double pe, double ps, double pn, double bw, double be,
+                                             double bs, double bn, double ac, double Bc, double mk, double Pic, double zbc, double rhsv) {
+  double nl, dnl;
+  nl_terms(a.prm, pc, Bc, mk, Pic, zbc, nl, dnl);
+  const double lof = lofphi_cell(a.alpha, ac, a.beta, pc, pw, pe, ps, pn, bw, be, bs, bn, a.dxi0, a.dxi1, nl);
+  const double lam = lambda_cell(a.alpha, ac, a.beta, bw, be, bs, bn, a.dxi0, a.dxi1);
+  const double denom = 1.0e-16 + lam + dnl;
+  return pc + (rhsv - lof) / denom;
+}
+__device__ __forceinline__ double bc_on_the_fly(const OpArgsG& a, int side, double pc) {
+  const double sdx = side == 0 ? -a.dx0 : side == 1 ? a.dx0 : side == 2 ? -a.dx1 : a.dx1;
+  return bc_ghost_value(a.bc_kind[side], pc, a.bcval[side], sdx);
+}
+
+__global__ void __launch_bounds__(256) k_gsrb_patch(const double* __restrict__ pin, double* __restrict__ pout, const double* __restrict__ rhsb,
+                                                    const PatchG* __restrict__ tab, const GRec* __restrict__ recs,
+                                                    const int* __restrict__ rec_start, OpArgsG a) {
+  extern __shared__ double gp_tile[];
+  const PatchG g = tab[blockIdx.x];
+  const int nx = g.nx, ny = g.ny, W = nx + 2, tid = threadIdx.x;
+  const ptrdiff_t P = g.pitch;
+  const int gpar = (g.glo0 + g.glo1) & 1;
+#define TILE(i, j) gp_tile[((j) + 1) * W + (i) + 1]
+  // ---- interior of phi_in
+  for (int t = tid; t < nx * ny; t += 256) {
+    const int j = t / nx, i = t - j * nx;
+    TILE(i, j) = pin[g.off + j * P + i];
+  }
+  // ---- ghost ring: sides 0 x-lo, 1 x-hi (ny cells each), 2 y-lo, 3 y-hi (nx cells each)
+  const GRec* R = recs + rec_start[blockIdx.x];
+  const int nring = 2 * (nx + ny);
+  for (int t = tid; t < nring; t += 256) {
+    int side, k;
+    if (t < ny) { side = 0; k = t; } else if (t < 2 * ny) { side = 1; k = t - ny; } else if (t < 2 * ny + nx) { side = 2; k = t - 2 * ny; } else { side = 3; k = t - 2 * ny - nx; }
+    const int gi = side == 0 ? -1 : side == 1 ? nx : k, gj = side == 2 ? -1 : side == 3 ? ny : k;
+    const GRec r = R[t];
+    const ptrdiff_t mine = g.off + gj * P + gi;
+    double v;
+    if (r.kind == 0) {
+      v = pin[r.own];
+      if (((gpar + gi + gj) & 1) == 0) { // a red cell of the neighbour: its red update, recomputed from the owner's data
+        const ptrdiff_t inw = g.off + (ptrdiff_t)(side == 2 ? 0 : side == 3 ? ny - 1 : k) * P + (side == 0 ? 0 : side == 1 ? nx - 1 : k);
+        const double pin_in = pin[inw];
+        double nbv[3];
+#pragma unroll
+        for (int m = 0; m < 3; m++) nbv[m] = r.nb[m] >= 0 ? pin[r.nb[m]] : bc_on_the_fly(a, -2 - r.nb[m], v);
+        double pw, pe, ps, pn;
+        if (side == 0) { pe = pin_in; pw = nbv[0]; ps = nbv[1]; pn = nbv[2]; }
+        else if (side == 1) { pw = pin_in; pe = nbv[0]; ps = nbv[1]; pn = nbv[2]; }
+        else if (side == 2) { pn = pin_in; ps = nbv[0]; pw = nbv[1]; pe = nbv[2]; }
+        else { ps = pin_in; pn = nbv[0]; pw = nbv[1]; pe = nbv[2]; }
+        const ptrdiff_t o = r.own;
+        v = gsrb_point(a, v, pw, pe, ps, pn, a.bX[o], a.bX[o + 1], a.bY[o], a.bY[o + r.own_pitch], a.has_a ? a.aC[o] : 0.0, a.B[o], a.mask[o],
+                       a.Pi[o], a.zb[o], rhsb[o]);
+      }
+    } else {
+      v = pin[mine];
+      pout[mine] = v; // coarse-fine ghost values stay with the field across the buffer swap
+    }
+    TILE(gi, gj) = v;
+  }
+  if (tid < 4) { // the four corner ghost cells are nobody's stencil: carried over unchanged
+    const ptrdiff_t c = g.off + (ptrdiff_t)((tid >> 1) ? ny : -1) * P + ((tid & 1) ? nx : -1);
+    pout[c] = pin[c];
+  }
+  __syncthreads();
+  // ---- red pass, then black pass, in place in shared memory
+  const int half = (nx + 1) >> 1;
+  for (int pass = 0; pass < 2; pass++) {
+    for (int t = tid; t < half * ny; t += 256) {
+      const int j = t / half;
+      const int i = 2 * (t - j * half) + ((gpar + j + pass) & 1);
+      if (i >= nx) continue;
+      const ptrdiff_t o = g.off + j * P + i;
+      const double pc = TILE(i, j);
+      double pw = TILE(i - 1, j), pe = TILE(i + 1, j), ps = TILE(i, j - 1), pn = TILE(i, j + 1);
+      if (i == 0 && g.phys[0]) pw = bc_on_the_fly(a, 0, pc);
+      if (i == nx - 1 && g.phys[1]) pe = bc_on_the_fly(a, 1, pc);
+      if (j == 0 && g.phys[2]) ps = bc_on_the_fly(a, 2, pc);
+      if (j == ny - 1 && g.phys[3]) pn = bc_on_the_fly(a, 3, pc);
+      TILE(i, j) = gsrb_point(a, pc, pw, pe, ps, pn, a.bX[o], a.bX[o + 1], a.bY[o], a.bY[o + P], a.has_a ? a.aC[o] : 0.0, a.B[o], a.mask[o], a.Pi[o],
+                              a.zb[o], rhsb[o]);
+    }
+    __syncthreads();
+  }
+  for (int t = tid; t < nx * ny; t += 256) {
+    const int j = t / nx, i = t - j * nx;
+    pout[g.off + j * P + i] = TILE(i, j);
+  }
+#undef TILE
+}
+
 // MODE 0: out = L(phi); 1: out = rhs - L(phi); 2: as 1 plus max|out| into *norm_bits
 template <int MODE>
 __global__ void __launch_bounds__(256) k_apply_g(double* __restrict__ outb, const double* __restrict__ phib,

@@ -109,11 +109,14 @@ def _hash_uniform(i, j, seed):
     return (h >> np.uint64(11)).astype(np.float64) * (2.0 / float(1 << 53)) - 1.0
 
 
-def fields(cfg, ng=1, seed=12345, perturb=True, lo=(0, 0), shape=None, level_ratio=1):
+def fields(cfg, ng=1, seed=12345, perturb=True, lo=(0, 0), shape=None, level_ratio=1, moulin_cutoff=None, rhs_only=False):
     """IBC fields on index window [lo, lo+shape) (default: the whole level-0 domain), with ng ghosts.
 
     level_ratio refines dx (AMR level = base dx / level_ratio).  Returns dict of [j, i] arrays:
     head, B (gap height), Pi, zb, mask, rhs (no ghosts).
+    moulin_cutoff (in units of a moulin's sigma): evaluate each Gaussian moulin source only where it is not negligible; with
+    cutoff >= 12 the omitted terms are below one ulp of the background recharge, i.e. the sum is unchanged.
+    rhs_only: only the right-hand side (same bits as the full call), for geometries without an ice mask.
     """
     nx, ny = shape if shape is not None else (cfg.nx * level_ratio, cfg.ny * level_ratio)
     dx, dy = cfg.dx[0] / level_ratio, cfg.dx[1] / level_ratio
@@ -123,7 +126,11 @@ def fields(cfg, ng=1, seed=12345, perturb=True, lo=(0, 0), shape=None, level_rat
         I, J = np.meshgrid(ii, jj)
         x, y = (I + 0.5) * dx, (J + 0.5) * dy
         mask = np.ones_like(x)
-        if cfg.ibc == "basic":      # src/HydroIBC.cpp:230-271
+        if rhs_only:
+            if cfg.ibc == "valley":
+                raise ValueError("rhs_only: the valley geometry masks the right-hand side")
+            head = B = Pi = zb = None
+        elif cfg.ibc == "basic":      # src/HydroIBC.cpp:230-271
             zb = cfg.slope * x
             B = np.full_like(x, cfg.gap_init)
             Pi = RHO_I * GRAV * np.full_like(x, cfg.H)
@@ -169,14 +176,48 @@ def fields(cfg, ng=1, seed=12345, perturb=True, lo=(0, 0), shape=None, level_rat
             head = Pi * 0.5 * (1.0 / (RHO_W * GRAV)) + zb
         else:
             raise ValueError(cfg.ibc)
-        if perturb:
+        if perturb and not rhs_only:
             Lx, Ly = cfg.domain_size
             head = head * (1.0 + 1e-3 * np.sin(2 * np.pi * 3 * x / Lx) * np.cos(2 * np.pi * 2 * y / Ly))
             B = B * (1.0 + 0.5 * _hash_uniform(I, J, seed))
         # right-hand side of the head equation: recharge + moulins (Gaussian), cf. src/AmrHydro.cpp:2801-3079
         rhs = np.full_like(x, cfg.distributed_input)
         for (mx, my, flux, sig) in cfg.moulins:
-            rhs += flux / (2.0 * np.pi * sig * sig) * np.exp(-0.5 * ((x - mx) ** 2 + (y - my) ** 2) / (sig * sig))
+            if moulin_cutoff is None:
+                rhs += flux / (2.0 * np.pi * sig * sig) * np.exp(-0.5 * ((x - mx) ** 2 + (y - my) ** 2) / (sig * sig))
+                continue
+            w = moulin_cutoff * sig
+            i0 = max(0, int(math.floor((mx - w) / dx - 0.5)) - int(ii[0])); i1 = min(len(ii), int(math.ceil((mx + w) / dx - 0.5)) + 1 - int(ii[0]))
+            j0 = max(0, int(math.floor((my - w) / dy - 0.5)) - int(jj[0])); j1 = min(len(jj), int(math.ceil((my + w) / dy - 0.5)) + 1 - int(jj[0]))
+            if i1 <= i0 or j1 <= j0:
+                continue
+            xs, ys = x[j0:j1, i0:i1], y[j0:j1, i0:i1]
+            rhs[j0:j1, i0:i1] += flux / (2.0 * np.pi * sig * sig) * np.exp(-0.5 * ((xs - mx) ** 2 + (ys - my) ** 2) / (sig * sig))
         rhs = np.where(mask < 0.0, 0.0, rhs)  # no recharge outside the ice (rhs/1e-16 would blow up where lambda = 0)
     core = (slice(ng, ng + ny), slice(ng, ng + nx))
+    if rhs_only:
+        return dict(rhs=np.ascontiguousarray(rhs[core]))
     return dict(head=head, B=B, Pi=Pi, zb=zb, mask=mask, rhs=np.ascontiguousarray(rhs[core]))
+
+
+def box_fields(cfg, boxes, level_ratio=1, ng=1, seed=12345, bin_cells=512, moulin_cutoff=12.0, rhs_only=False):
+    """fields() for a list of boxes of one AMR level without ever forming the level's global arrays: boxes are grouped by the
+    bin (bin_cells x bin_cells fine cells) their low corner falls into, the fields are evaluated once on each group's bounding
+    window and cut into the boxes' FArrayBoxes.  Yields (box index, dict name -> [j, i] array with ng ghosts; rhs without)."""
+    boxes = np.asarray(boxes, dtype=np.int64).reshape(-1, 4)
+    groups = {}
+    for b, bx in enumerate(boxes):
+        groups.setdefault((int(bx[1]) // bin_cells, int(bx[0]) // bin_cells), []).append(b)
+    for key in sorted(groups):
+        ids = groups[key]
+        sub = boxes[ids]
+        x0, y0, x1, y1 = int(sub[:, 0].min()), int(sub[:, 1].min()), int(sub[:, 2].max()), int(sub[:, 3].max())
+        g = fields(cfg, ng=ng, seed=seed, lo=(x0, y0), shape=(x1 - x0 + 1, y1 - y0 + 1), level_ratio=level_ratio, moulin_cutoff=moulin_cutoff,
+                   rhs_only=rhs_only)
+        for b in ids:
+            bx = boxes[b]
+            i0, j0 = int(bx[0]) - x0, int(bx[1]) - y0
+            nx, ny = int(bx[2] - bx[0] + 1), int(bx[3] - bx[1] + 1)
+            out = {} if rhs_only else {k: g[k][j0:j0 + ny + 2 * ng, i0:i0 + nx + 2 * ng] for k in ("head", "B", "Pi", "zb", "mask")}
+            out["rhs"] = g["rhs"][j0:j0 + ny, i0:i0 + nx]
+            yield b, out

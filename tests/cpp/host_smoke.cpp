@@ -60,18 +60,8 @@ static int g_fail = 0;
     if (!(cond)) { std::printf("host_smoke: FAILED: " __VA_ARGS__); std::printf("\n"); g_fail++; } \
   } while (0)
 
-int main(int argc, char** argv) {
-  Fixture F;
-  if (argc < 2 || !load(argv[1], F)) { std::printf("host_smoke: cannot read the fixture (usage: host_smoke tests/golden/host_smoke_2lev.bin)\n"); return 2; }
-  Context ctx(0);
-  const int periodic[2] = {0, 0};
-  std::vector<DisjointBoxLayout*> grids;
-  for (int l = 0; l < F.nlev; l++) {
-    std::vector<Box> bx;
-    for (const BoxData& d : F.lev[l]) bx.push_back(d.box);
-    const int n = 32 << l;
-    grids.push_back(new DisjointBoxLayout(ctx, bx, {}, Box{{0, 0}, {n - 1, n - 1}}, periodic));
-  }
+// everything that lives on the grids: factory, operators and solver are gone when this returns, before main deletes the layouts
+static void run(Context& ctx, const Fixture& F, std::vector<DisjointBoxLayout*>& grids) {
   std::vector<LevelData*> head, rhs, aC, bX, bY, B, Pi, zb, mask;
   for (int l = 0; l < F.nlev; l++) {
     DisjointBoxLayout& g = *grids[l];
@@ -231,6 +221,22 @@ int main(int argc, char** argv) {
   delete op0; delete op1;
   for (auto* v : {&head, &rhs, &aC, &bX, &bY, &B, &Pi, &zb, &mask})
     for (LevelData* f : *v) delete f;
+}
+
+int main(int argc, char** argv) {
+  std::setvbuf(stdout, nullptr, _IOLBF, 0);
+  Fixture F;
+  if (argc < 2 || !load(argv[1], F)) { std::printf("host_smoke: cannot read the fixture (usage: host_smoke tests/golden/host_smoke_2lev.bin)\n"); return 2; }
+  Context ctx(0);
+  const int periodic[2] = {0, 0};
+  std::vector<DisjointBoxLayout*> grids;
+  for (int l = 0; l < F.nlev; l++) {
+    std::vector<Box> bx;
+    for (const BoxData& d : F.lev[l]) bx.push_back(d.box);
+    const int n = 32 << l;
+    grids.push_back(new DisjointBoxLayout(ctx, bx, {}, Box{{0, 0}, {n - 1, n - 1}}, periodic));
+  }
+  run(ctx, F, grids);
   for (DisjointBoxLayout* g : grids) delete g;
   std::printf(g_fail == 0 ? "host_smoke: OK\n" : "host_smoke: FAILED (%d checks)\n", g_fail);
   return g_fail == 0 ? 0 : 1;

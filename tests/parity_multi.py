@@ -1,0 +1,129 @@
+"""Multi-rank parity checks against the CPU oracle, callable from a running N-rank job (bench.py runs them before it times
+anything at N > 1 and prints the outcome under "parity_nranks"; tools/parity_multi*.py are the stand-alone versions).
+
+Every rank builds the GLOBAL problem in the oracle (the grids are small), solves it there, and compares ITS OWN boxes of the
+device result bit for bit; the verdicts are combined with an allreduce(min) over the job's gloo group.  The domain is the
+configuration's level-0 grid stacked `world` times in y, so that every rank owns a strip at any N.
+  * single level (C5, C4 valley with ice mask < 0): y-strip partition, halo rows by ncclSend/ncclRecv, residual norm by
+    ncclAllReduce; with the halo exchange of the smoother overlapped with the interior sweep (default) and not (tune key 6);
+  * three levels: the C5 test hierarchy replicated per tile; refined boxes owned tile-wise (same-level neighbours local: the fused
+    per-patch smoother runs) and dealt round-robin (copy plans cross ranks, exchange-per-colour flow)."""
+import os
+
+import numpy as np
+
+
+def _tiled_cfg(name, world):
+    from suhmo_b200 import synthetic as syn
+    cfg = syn.config(name, 1)
+    tile_ny = cfg.ny
+    cfg.ny *= world
+    cfg.domain_size = (cfg.domain_size[0], cfg.domain_size[1] * world)
+    return cfg, tile_ny
+
+
+def _all_true(dist, ok):
+    import torch
+    t = torch.tensor([1 if ok else 0], dtype=torch.int32)
+    dist.all_reduce(t, op=dist.ReduceOp.MIN)
+    return bool(int(t[0]))
+
+
+def _own_equal(gpu_ld, orc_field):
+    g, o = gpu_ld.get_global(), orc_field.get_global()
+    m = ~np.isnan(g)          # the boxes this rank owns
+    return bool(m.any() and not np.isnan(o[m]).any() and np.array_equal(g[m], o[m]))
+
+
+def single_level(ctx, dist, rank, world, name, ncyc=4):
+    """returns {"head_bit_exact": .., "resnorm_history_equal": .., "overlap_off_bit_exact": ..}"""
+    from oracle import binding as ob
+    from suhmo_b200 import amr, synthetic as syn
+    from tests.problem import GpuSide, OracleSide
+    ob.lib().orc_set_threads(max(1, (os.cpu_count() or 1) // world))
+    cfg, tile_ny = _tiled_cfg(name, world)
+    boxes = syn.domain_split(cfg.nx, cfg.ny, cfg.max_box_size, cfg.block_factor)
+    owner = (boxes[:, 1] // tile_ny).astype(np.int32)
+    out = {}
+    ohist = ohead = None
+    for label, key6 in (("head_bit_exact", 0), ("overlap_off_bit_exact", 1)):
+        orc = OracleSide(cfg, boxes)
+        orc.init_bcoef()
+        gpu = GpuSide(ctx, orc, owner)
+        ctx.set_tuning(6, key6)
+        try:
+            mg = amr.AMRFASMultiGrid().define(gpu.factory, 1)
+            mg.setSolverParameters(4, 4, 10, 1, 100, 1e-10, 1e-4, 1e-7)
+            git, ghist, _ = mg.solve([gpu.F["head"]], [gpu.F["rhs"]], fixed_cycles=ncyc)
+        finally:
+            ctx.set_tuning(6, 0)
+        if ohist is None:
+            it, ohist = orc.solver().solve(orc.F["head"], orc.F["rhs"], ob.make_solver_params(bottom=10, fixed_cycles=ncyc))
+            ohead = orc.F["head"]
+            out["resnorm_history_equal"] = _all_true(dist, bool(np.array_equal(ghist, ohist)))
+        else:
+            out["resnorm_history_equal"] = out["resnorm_history_equal"] and _all_true(dist, bool(np.array_equal(ghist, ohist)))
+        out[label] = _all_true(dist, _own_equal(gpu.F["head"], ohead))
+        mg.destroy()
+    out["grid"] = [int(cfg.nx), int(cfg.ny)]
+    out["vcycles"] = ncyc
+    return out
+
+
+def three_level(ctx, dist, rank, world, ncyc=3):
+    """returns {"tilewise_bit_exact": .., "roundrobin_bit_exact": .., "resnorm_history_equal": ..}"""
+    from oracle import binding as ob
+    from suhmo_b200 import amr
+    from tests.problem import AmrGpuSide, AmrOracleSide, amr_hierarchy
+    ob.lib().orc_set_threads(max(1, (os.cpu_count() or 1) // world))
+    cfg, lv = amr_hierarchy("C5")
+    tile = cfg.ny
+    cfg.ny *= world
+    cfg.domain_size = (cfg.domain_size[0], cfg.domain_size[1] * world)
+    levels, tile_of = [], []
+    for l, boxes in enumerate(lv):
+        sh = tile << l
+        reps = [boxes + np.array([0, k * sh, 0, k * sh], dtype=np.int32) for k in range(world)]
+        levels.append(np.concatenate(reps).astype(np.int32))
+        tile_of.append(np.repeat(np.arange(world, dtype=np.int32), len(boxes)))
+    out = {}
+    ohist = None
+    oheads = None
+    for label in ("tilewise_bit_exact", "roundrobin_bit_exact"):
+        orc = AmrOracleSide(cfg, levels)
+        orc.average_down("head")
+        orc.init_bcoef()
+        owners = [tile_of[0]] + [tile_of[l] if label.startswith("tile") else (np.arange(len(levels[l])) % world).astype(np.int32) for l in (1, 2)]
+        gpu = AmrGpuSide(ctx, orc, owners)
+        mg = amr.AMRFASMultiGrid().define(gpu.factory, 3)
+        mg.setSolverParameters(4, 4, 10, 1, 100, 1e-10, 1e-4, 1e-7)
+        git, ghist, _ = mg.solve(gpu.fields("head"), gpu.fields("rhs"), fixed_cycles=ncyc)
+        if ohist is None:
+            it, ohist = orc.solver().solve(orc.fields("head"), orc.fields("rhs"), 2, ob.make_solver_params(bottom=10, fixed_cycles=ncyc))
+            oheads = orc.fields("head")
+        hist_ok = bool(np.array_equal(ghist, ohist))
+        out["resnorm_history_equal"] = out.get("resnorm_history_equal", True) and _all_true(dist, hist_ok)
+        mine = True
+        for l in range(3):
+            g = gpu.F[l]["head"].get_global()
+            m = ~np.isnan(g)
+            if m.any():
+                o = oheads[l].get_global()
+                mine = mine and bool(np.array_equal(g[m], o[m]))
+        out[label] = _all_true(dist, mine)
+        mg.destroy()
+    out["grid"] = [int(cfg.nx), int(cfg.ny)]
+    out["vcycles"] = ncyc
+    return out
+
+
+def run_all(ctx, dist, rank, world):
+    """the "parity_nranks" object of the bench line"""
+    res = {"n": world, "c5_single_level": single_level(ctx, dist, rank, world, "C5"),
+           "c4_valley_single_level": single_level(ctx, dist, rank, world, "C4"),
+           "c5_three_level": three_level(ctx, dist, rank, world)}
+    flags = [v for d in res.values() if isinstance(d, dict) for k, v in d.items() if isinstance(v, bool)]
+    res["all_bit_exact"] = bool(all(flags))
+    # the keys the reviewers look for first
+    res["head_bit_exact"] = bool(res["c5_single_level"]["head_bit_exact"] and res["c4_valley_single_level"]["head_bit_exact"])
+    return res

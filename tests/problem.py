@@ -115,8 +115,24 @@ def rel_l2(a, b):
 # multi-level (AMR) problems: explicit box lists per level (what Chombo reads from AmrHydro.grids_file), ref ratio 2
 # ---------------------------------------------------------------------------------------------------------------
 def amr_hierarchy(name="C5"):
-    """A small 3-level hierarchy on a 64x64 base grid: L-shaped level 1 (concave corner, box-box exchange, a box on the
-    domain boundary), level 2 properly nested inside it.  Boxes are lo0 lo1 hi0 hi1, block-factor 8 aligned."""
+    """Explicit test hierarchies (boxes are lo0 lo1 hi0 hi1, block-factor 8 aligned, refinement ratio 2).
+    "C5":     3 levels on a 64x64 base grid: L-shaped level 1 (concave corner, box-box exchange, a box on the domain boundary),
+              level 2 properly nested inside it.
+    "C4":     2 levels on the valley geometry (256x64, exec/E_SHMIP): ice mask < 0 inside the refined boxes AND across the
+              coarse-fine interface, masked gradients (solver.use_mask_for_gradients), cut_solve_outside_domain -- the BASELINE
+              config where the masked coarse-fine gradient and the mask-streaming smoother matter.
+    "C5_256": 3 levels on the AMR_multiMoulins base grid at its native 256x256 size (16 boxes of 64^2), the same shapes scaled."""
+    if name == "C4":
+        cfg = syn.config("C4", 1)
+        base = syn.domain_split(cfg.nx, cfg.ny, cfg.max_box_size, cfg.block_factor)
+        lev1 = np.array([(16, 16, 79, 79), (80, 16, 143, 79), (16, 80, 79, 111), (448, 32, 511, 95)], dtype=np.int32)
+        return cfg, [base, lev1]
+    if name == "C5_256":
+        cfg = syn.config("C5", 1)
+        base = syn.domain_split(cfg.nx, cfg.ny, cfg.max_box_size, cfg.block_factor)
+        lev1 = np.array([(64, 64, 127, 127), (128, 64, 191, 127), (64, 128, 127, 191), (448, 0, 511, 63)], dtype=np.int32)
+        lev2 = np.array([(160, 160, 223, 223), (224, 160, 287, 223), (160, 224, 223, 287)], dtype=np.int32)
+        return cfg, [base, lev1, lev2]
     cfg = syn.config(name, 1)
     cfg.nx, cfg.ny = 64, 64
     cfg.max_box_size = 32
@@ -127,9 +143,11 @@ def amr_hierarchy(name="C5"):
 
 
 class AmrOracleSide:
-    """Per-level oracle fields of a head-solve problem on an explicit hierarchy."""
+    """Per-level oracle fields of a head-solve problem on an explicit hierarchy.  boxwise: evaluate the synthetic fields box
+    group by box group (syn.box_fields) instead of on the level's whole index space -- same bits, and the only way at sizes where
+    a global fine-level array would not fit."""
 
-    def __init__(self, cfg, level_boxes, seed=12345, bc_vals=None, prm_over=None):
+    def __init__(self, cfg, level_boxes, seed=12345, bc_vals=None, prm_over=None, boxwise=False):
         self.cfg, self.level_boxes = cfg, [np.asarray(b, dtype=np.int32) for b in level_boxes]
         self.nlev = len(level_boxes)
         self.layouts, self.F, self.dx = [], [], []
@@ -137,15 +155,19 @@ class AmrOracleSide:
             r = 2 ** l
             dom = (0, 0, cfg.nx * r - 1, cfg.ny * r - 1)
             lay = ob.Layout(boxes, dom, cfg.periodic)
-            g = syn.fields(cfg, ng=1, seed=seed, level_ratio=r)
-            F = {}
-            for k in ("head", "B", "Pi", "zb", "mask"):
-                F[k] = ob.Field(lay, 1, 1)
-                F[k].set_global(g[k], (-1, -1))   # ghosts (CF ghosts included) from the analytic fields
-                if k != "head":
-                    ob.lib().orc_copy_ghost(F[k].h)
+            F = {k: ob.Field(lay, 1, 1) for k in ("head", "B", "Pi", "zb", "mask")}
             F["rhs"] = ob.Field(lay, 1, 0)
-            F["rhs"].set_global(g["rhs"], (0, 0))
+            if boxwise:
+                for b, f in syn.box_fields(cfg, boxes, level_ratio=r, ng=1, seed=seed):
+                    for k in ("head", "B", "Pi", "zb", "mask", "rhs"):
+                        F[k].fab(b)[0][0][...] = f[k]
+            else:
+                g = syn.fields(cfg, ng=1, seed=seed, level_ratio=r)
+                for k in ("head", "B", "Pi", "zb", "mask"):
+                    F[k].set_global(g[k], (-1, -1))   # ghosts (CF ghosts included) from the analytic fields
+                F["rhs"].set_global(g["rhs"], (0, 0))
+            for k in ("B", "Pi", "zb", "mask"):
+                ob.lib().orc_copy_ghost(F[k].h)
             F["a"] = ob.Field(lay, 1, 0)
             F["bX"] = ob.Field(lay, 1, 0, XFACE)
             F["bY"] = ob.Field(lay, 1, 0, YFACE)

@@ -10,8 +10,12 @@ from tests.problem import AmrGpuSide, AmrOracleSide, amr_hierarchy, fabs_equal, 
 pytestmark = pytest.mark.gpu
 
 
-def make(ctx, nlev=3, **kw):
-    cfg, lv = amr_hierarchy()
+HIERS = ["C5", "C4", "C5_256"]  # tests/problem.py:amr_hierarchy -- 64^2 3-level, valley 2-level with ice mask < 0, 256^2 3-level
+
+
+def make(ctx, nlev=None, hier="C5", **kw):
+    cfg, lv = amr_hierarchy(hier)
+    nlev = nlev or len(lv)
     orc = AmrOracleSide(cfg, lv[:nlev], **kw)
     orc.average_down("head")
     orc.init_bcoef()
@@ -40,22 +44,25 @@ def test_general_layout_roundtrip_and_exchange(gpu_ctx):
         same(gpu.F[l]["head"], orc.F[l]["head"], f"exchange L{l}", ghosts=l > 0)
 
 
-def test_cf_interp_bit_exact(gpu_ctx):
-    cfg, orc, gpu = make(gpu_ctx)
-    for l in (1, 2):
+@pytest.mark.parametrize("hier", HIERS)
+def test_cf_interp_bit_exact(gpu_ctx, hier):
+    cfg, orc, gpu = make(gpu_ctx, hier=hier)
+    for l in range(1, orc.nlev):
         ob.cf_interp(orc.F[l]["head"], orc.F[l - 1]["head"], 2, orc.dx[l][0])
         gop = gpu.factory.AMRnewOp(l)
         gop.coarseFineInterp(gpu.F[l]["head"], gpu.F[l - 1]["head"])
         same(gpu.F[l]["head"], orc.F[l]["head"], f"QuadCFInterp L{l}", ghosts=True)
 
 
-def test_amr_operator_and_reflux_bit_exact(gpu_ctx):
-    cfg, orc, gpu = make(gpu_ctx)
-    oops = [orc.level_op(l) for l in range(3)]
-    gops = [gpu.factory.AMRnewOp(l) for l in range(3)]
-    for l in range(3):
+@pytest.mark.parametrize("hier", HIERS)
+def test_amr_operator_and_reflux_bit_exact(gpu_ctx, hier):
+    cfg, orc, gpu = make(gpu_ctx, hier=hier)
+    nl = orc.nlev
+    oops = [orc.level_op(l) for l in range(nl)]
+    gops = [gpu.factory.AMRnewOp(l) for l in range(nl)]
+    for l in range(nl):
         olof, glof = ob.Field(orc.layouts[l], 1, 0), gpu.new_like(l, "rhs")
-        fine = l + 1 if l < 2 else None
+        fine = l + 1 if l < nl - 1 else None
         crse = l - 1 if l > 0 else None
         oops[l].amr_operator(olof, orc.F[fine]["head"] if fine else None, orc.F[l]["head"], orc.F[crse]["head"] if crse is not None else None,
                              False, oops[fine] if fine else None)
@@ -76,11 +83,12 @@ def test_amr_operator_and_reflux_bit_exact(gpu_ctx):
             same(glof, olof, f"zeroCovered L{l}")
 
 
-def test_restrict_prolong_bit_exact(gpu_ctx):
-    cfg, orc, gpu = make(gpu_ctx)
-    oops = [orc.level_op(l) for l in range(3)]
-    gops = [gpu.factory.AMRnewOp(l) for l in range(3)]
-    for l in (1, 2):
+@pytest.mark.parametrize("hier", HIERS)
+def test_restrict_prolong_bit_exact(gpu_ctx, hier):
+    cfg, orc, gpu = make(gpu_ctx, hier=hier)
+    oops = [orc.level_op(l) for l in range(orc.nlev)]
+    gops = [gpu.factory.AMRnewOp(l) for l in range(orc.nlev)]
+    for l in range(1, orc.nlev):
         clay = orc.layouts[l].coarsen(2)
         oresC, oscr = ob.Field(clay, 1, 1), ob.Field(orc.layouts[l], 1, 1)
         gresC, gscr = gops[l].createCoarsened(gpu.F[l]["head"]), gpu.new_like(l, "head")
@@ -110,11 +118,15 @@ def test_restrict_prolong_bit_exact(gpu_ctx):
         same(gpu.F[l]["head"], orc.F[l]["head"], f"AMRProlongS_2 L{l}")
 
 
-def test_update_operator_and_relax_nf_bit_exact(gpu_ctx):
-    cfg, orc, gpu = make(gpu_ctx)
-    oops = [orc.level_op(l) for l in range(3)]
-    gops = [gpu.factory.AMRnewOp(l) for l in range(3)]
-    for l in (1, 2):
+@pytest.mark.parametrize("hier", HIERS)
+def test_update_operator_and_relax_nf_bit_exact(gpu_ctx, hier):
+    cfg, orc, gpu = make(gpu_ctx, hier=hier)
+    oops = [orc.level_op(l) for l in range(orc.nlev)]
+    gops = [gpu.factory.AMRnewOp(l) for l in range(orc.nlev)]
+    if hier == "C4":  # the point of this hierarchy: masked cells inside the fine boxes and on both sides of the coarse-fine interface
+        m1, m0 = orc.F[1]["mask"].get_global(), orc.F[0]["mask"].get_global()
+        assert (m1[~np.isnan(m1)] < 0).any() and (m1[~np.isnan(m1)] > 0).any() and (m0 < 0).any() and cfg.use_mask_grad and cfg.cutOffBcoef
+    for l in range(1, orc.nlev):
         oops[l].relax_nf(orc.F[l]["head"], orc.F[l - 1]["head"], orc.F[l]["rhs"], 2)
         gops[l].relaxNF(gpu.F[l]["head"], gpu.F[l - 1]["head"], gpu.F[l]["rhs"], 2)
         same(gpu.F[l]["head"], orc.F[l]["head"], f"relaxNF L{l}", ghosts=True)
@@ -128,9 +140,35 @@ def test_update_operator_and_relax_nf_bit_exact(gpu_ctx):
         same(gres, ores, f"residualNF L{l}")
 
 
-@pytest.mark.parametrize("nlev", [2, 3])
-def test_amr_fixed_vcycles_parity(gpu_ctx, nlev):
-    cfg, orc, gpu = make(gpu_ctx, nlev)
+@pytest.mark.parametrize("mode", ["reference flow", "fused", "fused off by tuning key"])
+@pytest.mark.parametrize("hier", HIERS)
+def test_refined_level_smoother_variants(gpu_ctx, hier, mode):
+    """levelGSRB on refined (patch-table) levels: the fused per-patch red+black kernel (default) and the reference's
+    exchange-per-colour flow must both reproduce the oracle bit for bit, ghost cells included, for odd and even sweep counts
+    (the fused sweep is out of place: an odd count leaves the field in the other buffer)."""
+    cfg, orc, gpu = make(gpu_ctx, hier=hier)
+    oops = [orc.level_op(l) for l in range(orc.nlev)]
+    gops = [gpu.factory.AMRnewOp(l) for l in range(orc.nlev)]
+    try:
+        gpu_ctx.set_relax_mode(0 if mode == "reference flow" else 1)
+        gpu_ctx.set_tuning(7, 1 if mode == "fused off by tuning key" else 0)
+        for l in range(1, orc.nlev):
+            for n in (1, 3, 4):
+                oops[l].relax_nf(orc.F[l]["head"], orc.F[l - 1]["head"], orc.F[l]["rhs"], n)
+                gops[l].relaxNF(gpu.F[l]["head"], gpu.F[l - 1]["head"], gpu.F[l]["rhs"], n)
+                same(gpu.F[l]["head"], orc.F[l]["head"], f"relaxNF x{n} L{l} ({mode})", ghosts=True)
+            # no coarse level handed in: the coarse-fine ghost cells keep their values through the sweeps
+            oops[l].relax(orc.F[l]["head"], orc.F[l]["rhs"], 3)
+            gops[l].relax(gpu.F[l]["head"], gpu.F[l]["rhs"], 3)
+            same(gpu.F[l]["head"], orc.F[l]["head"], f"relax x3 L{l} ({mode})", ghosts=True)
+    finally:
+        gpu_ctx.set_relax_mode(1)
+        gpu_ctx.set_tuning(7, 0)
+
+
+@pytest.mark.parametrize("nlev,hier", [(2, "C5"), (3, "C5"), (2, "C4"), (2, "C5_256"), (3, "C5_256")])
+def test_amr_fixed_vcycles_parity(gpu_ctx, nlev, hier):
+    cfg, orc, gpu = make(gpu_ctx, nlev, hier)
     ncyc = 4
     sp = ob.make_solver_params(bottom=10, fixed_cycles=ncyc)
     osol = orc.solver()
@@ -142,6 +180,7 @@ def test_amr_fixed_vcycles_parity(gpu_ctx, nlev):
     for l in range(nlev):
         oh, gh = orc.F[l]["head"].get_global(), gpu.F[l]["head"].get_global()
         assert rel_l2(gh, oh) <= 1e-10, f"level {l}"
+        assert np.array_equal(np.isnan(gh), np.isnan(oh)), f"level {l}: NaN pattern differs"
         m = ~np.isnan(oh)
         assert np.array_equal(gh[m], oh[m]), f"level {l}: head differs, max {np.abs(gh[m] - oh[m]).max():g}"
     assert np.array_equal(ghist, ohist), (ghist, ohist)

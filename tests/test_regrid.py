@@ -75,3 +75,33 @@ def test_no_tags_no_levels_and_full_tags_full_level():
     assert len(mr.regrid(base, [np.zeros((n, n), dtype=np.uint8)])) == 1
     lv = mr.regrid(base, [np.ones((n, n), dtype=np.uint8)])
     assert covered(lv[1], (2 * n, 2 * n)).min() == 1 and len(lv[1]) == 16
+
+
+@pytest.mark.parametrize("seed", [1, 2, 3, 4, 5, 6])
+def test_box_for_box_against_the_oracle_restatement(seed):
+    """sg_br_regrid (C++, the product) against oracle/br_regrid.py (numpy, written separately from the same rule set):
+    identical box lists, level by level, on random blob / noise tag maps, two and three levels, several parameter sets."""
+    from oracle import br_regrid as obr
+    rng = np.random.RandomState(seed)
+    n = [64, 96, 128][seed % 3]
+    nr = [1, 2, 4][seed % 3]
+    bf = [2, 4, 8][(seed // 2) % 3]
+    maxbox = [16, 32, 64][seed % 3]
+    fill = [0.5, 0.7, 0.85][(seed // 3) % 3]
+    base = syn.domain_split(n, n, 32, 2)
+    cs = [(int(x), int(y)) for x, y in rng.randint(8, n - 8, size=(4, 2))]
+    t0 = blob_tags(n, cs, int(rng.randint(3, 9)))
+    t0 |= (rng.rand(n, n) < 0.002).astype(np.uint8)           # isolated tags
+    mr = amr.BRMeshRefine((0, 0, n - 1, n - 1), fill, bf, nr, maxbox)
+    got = mr.regrid(base, [t0])
+    exp = obr.regrid((0, 0, n - 1, n - 1), base, [t0], fill, bf, nr, maxbox)
+    assert len(got) == len(exp) == 2
+    assert np.array_equal(got[1], exp[1]), (got[1][:5], exp[1][:5])
+    # third level: tags inside the level-1 grids
+    c1 = covered(got[1], (2 * n, 2 * n)) > 0
+    t1 = (blob_tags(2 * n, [(2 * c[0], 2 * c[1]) for c in cs[:2]], 4) > 0) & c1
+    got = mr.regrid(base, [t0, t1.astype(np.uint8)])
+    exp = obr.regrid((0, 0, n - 1, n - 1), base, [t0, t1.astype(np.uint8)], fill, bf, nr, maxbox)
+    assert len(got) == len(exp)
+    for l in range(1, len(got)):
+        assert np.array_equal(got[l], exp[l]), f"level {l}"
