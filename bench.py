@@ -2,14 +2,20 @@
 """bench.py -- head-solve cell-updates/s per FAS V-cycle (BASELINE.json metric) on N B200s.
 
   python bench.py --gpus N --steps K --warmup W            (N > 1: launched by torch.distributed.run)
-  python bench.py --impl reference ...                     (the CPU path, timed on the box's host cores)
+  python bench.py --impl reference ...                     (the same workload through the CPU path, on the box's host cores)
+  python bench.py --scaling strong --gpus N ...            (one 8192^2 problem cut over N GPUs instead of one per GPU)
 
-A "step" is one complete FAS V-cycle of the head solve (everything between two residual-norm evaluations:
-UpdateOperator, AverageOperator, 4+4 GSRB smooths per depth, 10/16 bottom smooths, restriction, FAS right-hand
-side, prolongation, residual + max-norm) on the synthetic AMR_multiMoulins base grid scaled to 8192 x 8192 cells
-per GPU (weak scaling: the domain grows in y with N; box-wise strip partition, 64^2 boxes).  At N = 1 the line also
-carries "amr_3level": the same base grid with two refined levels around the 63 moulins (grids from the library's own
-tagging + Berger-Rigoutsos regrid), timed over composite FAS V-cycles.
+Workload = BASELINE.json configs[4]: the AMR_multiMoulins problem on an 8192 x 8192 base grid (64^2 boxes) with TWO REFINED
+LEVELS around the 63 moulins, grids from the library's own tagging + Berger-Rigoutsos regrid with the input file's parameters
+(tools/workload.py).  A "step" is one complete composite FAS V-cycle of the head solve over the three levels (everything
+between two residual-norm evaluations: UpdateOperator on every level, AverageOperator, 4+4 GSRB smooths per level and per
+multigrid depth of the base level, 16 bottom smooths, restrictions, coarse-fine interpolation, refluxed composite residual,
+prolongations, residual max-norm).  Weak scaling: one such problem ("tile") per GPU, stacked in y; strong scaling: one problem.
+
+Secondary keys of the line: "single_level" (the base grid alone, round 1's headline), "roofline_kernels" (both smoothers),
+"parity_full_size" (GPU residual-norm history vs the CPU oracle's on THIS workload), "parity_nranks" (N > 1: multi-rank parity
+against the oracle incl. the overlapped halo path, run before anything is timed), "small_configs" (C1-C4 at their native sizes,
+GPU vs CPU ms per V-cycle), "gap_solve" (SolveForGap_nl on the base grid).
 """
 import argparse
 import json
@@ -26,39 +32,17 @@ if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
 from suhmo_b200 import synthetic as syn  # noqa: E402
+from tools import workload as wl  # noqa: E402
 
 METRIC = "head-solve cell-updates/sec (V-cycle)"
 UNIT = "cell-updates/s"
-BYTES_PER_UPDATE_SMOOTHER = 72.0   # phi, rhs, bX, bY, B, Pi, zb, mask read + phi written (SURVEY.md 8d)
+# the smoother reads phi, rhs, bX, bY, B, Pi, zb, mask and writes phi = 72 B per cell-update.  A level whose ice
+# mask has no negative entry does not stream the mask (the only use is `mask < 0`, AmrHydroF.ChF:40): 64 B are then what a
+# launch has to move, and that is the figure the roofline fraction is computed from (bytes_per_cell_update in the line).
+BYTES_SMOOTHER_MASK, BYTES_SMOOTHER_NOMASK = 72.0, 64.0
 BYTES_PER_UPDATE_VCYCLE = 97.0     # whole V-cycle amortised (SURVEY.md 8d)
-# dram__bytes_read.sum + dram__bytes_write.sum of one finest-level smoother launch, from the `ncu --set full` capture of this
-# command committed as profiles/r01_k_gsrb_stream_ncu_full_raw.csv (4.094 GB read + 0.533 GB written with the ice mask skipped; requested 64 B x 67.1 M = 4.295 GB, algorithmic 72 B -> 4.832 GB)
-NCU_TRAFFIC = {(8192, 1): 4.094115e9 + 0.533116160e9}
-
-
-def bench_config(size, nranks):
-    cfg = syn.config("C5", 1)
-    cfg.nx, cfg.ny = size, size * nranks
-    cfg.domain_size = (100000.0, 100000.0 * nranks)
-    return cfg
-
-
-def strip_boxes(cfg, nranks):
-    boxes = syn.domain_split(cfg.nx, cfg.ny, cfg.max_box_size, cfg.block_factor)
-    rows = cfg.ny // nranks
-    owner = (boxes[:, 1] // rows).astype(np.int32)
-    return boxes, owner
-
-
-def pack_boxes(garr, nbx, nby, bs, ng, ex=0, ey=0, pinned=None):
-    """[j,i] strip array with ng ghosts -> all boxes' FArrayBoxes consecutively (box order: x fastest)."""
-    from numpy.lib.stride_tricks import as_strided
-    s0, s1 = garr.strides
-    w, h = bs + 2 * ng + ex, bs + 2 * ng + ey
-    v = as_strided(garr, shape=(nby, nbx, h, w), strides=(bs * s0, bs * s1, s0, s1))
-    out = pinned if pinned is not None else np.empty((nby * nbx, h, w))
-    out.reshape(nby, nbx, h, w)[...] = v
-    return out
+SPEC = dict(head=(1, 0), rhs=(0, 0), B=(1, 0), Pi=(1, 0), zb=(1, 0), mask=(1, 0), a=(0, 0), bX=(0, 1), bY=(0, 2))
+INPUTS = ("head", "rhs", "B", "Pi", "zb", "mask")
 
 
 class Clocks(threading.Thread):
@@ -73,7 +57,7 @@ class Clocks(threading.Thread):
     def run(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.device), f"--query-gpu={self.Q}",
-                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE, text=True)
+                                          "--format=csv,noheader,nounits", "-lms", "50"], stdout=subprocess.PIPE, text=True)
             for line in self.proc.stdout:
                 if self.stop_flag:
                     break
@@ -106,104 +90,253 @@ def measured_peak():
     return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
-def cpu_vcycles(size, cycles, threads, bottom):
-    """the CPU restatement of the reference path (oracle, OpenMP over boxes) on a bounded sample of the workload"""
+def ncu_traffic(kernel):
+    """dram__bytes_read.sum + dram__bytes_write.sum of one launch of `kernel` on this workload, from the newest `ncu --set full`
+    summary committed under profiles/ (profiles/ncu_traffic.json: kernel -> {bytes, file, commit}); None when there is none."""
+    p = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    try:
+        e = json.load(open(p)).get(kernel)
+        return (float(e["bytes"]), e.get("file")) if e else (None, None)
+    except Exception:
+        return None, None
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# CPU arm: the oracle (C restatement of the reference path, OpenMP over boxes) on the same workload
+# ---------------------------------------------------------------------------------------------------------------------
+def cpu_tile_hierarchy(cfg, nlevels):
+    """grids of one tile from the oracle's own tagging (orc_tag_cells_level) and the library's host-side Berger-Rigoutsos (pure
+    host integer code; the numpy restatement oracle/br_regrid.py gives the same boxes but needs dense integral images)"""
     from oracle import binding as ob
-    from tests.problem import OracleSide
-    ob.lib().orc_set_threads(threads)
-    cfg = bench_config(size, 1)
-    boxes = syn.domain_split(cfg.nx, cfg.ny, cfg.max_box_size, cfg.block_factor)
-    orc = OracleSide(cfg, boxes)
-    orc.init_bcoef()
-    sol = orc.solver()
-    sp1 = ob.make_solver_params(bottom=bottom, fixed_cycles=1)
-    sol.solve(orc.F["head"], orc.F["rhs"], sp1)  # warm-up cycle (page faults, plans)
-    sp = ob.make_solver_params(bottom=bottom, fixed_cycles=cycles)
-    t0 = time.perf_counter()
-    sol.solve(orc.F["head"], orc.F["rhs"], sp)
-    dt = time.perf_counter() - t0
-    # solve() also evaluates the residual norm after each cycle, as the GPU arm does
-    return sol.cell_updates(sp) * cycles / dt, dt, sol.depth
+    from suhmo_b200 import amr
+
+    def tag_level(l, boxes, rhs_fabs, thr):
+        lay = ob.Layout(np.asarray(boxes, dtype=np.int32), (0, 0, (cfg.nx << l) - 1, (cfg.ny << l) - 1), cfg.periodic)
+        f = ob.Field(lay, 1, 0)
+        if l == 0:
+            f.set_global(syn.fields(cfg, ng=1, rhs_only=True, moulin_cutoff=12.0)["rhs"], (0, 0))
+        else:
+            for b, r in enumerate(rhs_fabs):
+                f.fab(b)[0][0][...] = r
+        return ob.tag_cells_level(f, thr, 1e30, wl.REGRID["tags_grow"])
+
+    mr = amr.BRMeshRefine((0, 0, cfg.nx - 1, cfg.ny - 1), wl.REGRID["fill_ratio"], wl.REGRID["block_factor"], wl.REGRID["nesting_radius"],
+                          wl.REGRID["max_box_size"])
+    return wl.build_tile_hierarchy(cfg, tag_level, lambda base, tags: mr.regrid(base, tags, max_boxes=1 << 18), nlevels)
+
+
+class CpuProblem:
+    def __init__(self, size, nlevels, threads, levels=None):
+        from oracle import binding as ob
+        from tests.problem import AmrOracleSide
+        ob.lib().orc_set_threads(threads)
+        self.ob = ob
+        cfg = wl.tile_config(size)
+        self.levels = levels if levels is not None else cpu_tile_hierarchy(cfg, nlevels)
+        self.orc = AmrOracleSide(cfg, self.levels, boxwise=True)
+        self.orc.init_bcoef()
+        self.sol = self.orc.solver()
+        self.nlev = len(self.levels)
+
+    def solve(self, cycles, bottom):
+        sp = self.ob.make_solver_params(bottom=bottom, fixed_cycles=cycles)
+        t0 = time.perf_counter()
+        it, hist = self.sol.solve(self.orc.fields("head"), self.orc.fields("rhs"), self.nlev - 1, sp)
+        dt = time.perf_counter() - t0
+        return self.sol.cell_updates(sp, self.nlev - 1) * cycles / dt, dt, hist
 
 
 def run_reference(args, rank):
     if rank != 0:
         return
     threads = os.cpu_count() or 1
-    size = args.cpu_size
-    total = args.steps + args.warmup
-    # one "step" = one V-cycle on the bounded sample
-    _ = cpu_vcycles(size, max(1, args.warmup), threads, args.bottom) if args.warmup > 0 else None
-    v, dt, depth = cpu_vcycles(size, args.steps, threads, args.bottom)
-    cfgname = f"AMR_multiMoulins base grid, synthetic, bounded sample {size}x{size} (64^2 boxes, MG depth {depth})"
+    t0 = time.perf_counter()
+    cp = CpuProblem(args.size, args.levels, threads)
+    setup = time.perf_counter() - t0
+    hist_w = None
+    if args.warmup > 0:
+        _, _, hist_w = cp.solve(args.warmup, args.bottom)
+    v, dt, hist = cp.solve(args.steps, args.bottom)
+    cells = [int(sum((b[2] - b[0] + 1) * (b[3] - b[1] + 1) for b in boxes)) for boxes in cp.levels]
     line = {
         "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
+        "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": args.scaling,
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": cfgname, "pre": 4, "post": 4, "bottom": args.bottom, "threads": threads, "total_cycles": total},
+        "config": workload_config(args, 1, cells, [len(b) for b in cp.levels]),
         "cpu_baseline": {"value": v, "unit": UNIT, "cores": threads, "kind": "port",
-                         "sample": f"{args.steps} FAS V-cycles on a {size}x{size} sample of the workload, oracle (C restatement, "
-                                   f"OpenMP over boxes); the reference's Chombo/Fortran/MPI build cannot be produced here"},
+                         "sample": f"{args.steps} composite FAS V-cycles on the whole workload ({dt:.1f} s), oracle C restatement with OpenMP over "
+                                   f"boxes; the reference's Chombo/Fortran/MPI build cannot be produced here (no gfortran, MPI, Chombo)"},
         "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "resnorm": [float(x) for x in (hist_w if hist_w is not None else hist)[:4]],
+        "setup_s": setup,
     }
     print(json.dumps(line), flush=True)
 
 
-def amr_leg(ctx, amr, cfg, layout0, F0, bc, prm, args):
-    """BASELINE configs[4] as named: the AMR_multiMoulins hierarchy (3 levels, refinement around the 63 moulins) on top of the
-    resident 8192^2 base grid, single GPU.  Grids come from the library's own tagging + Berger-Rigoutsos regrid with the
-    input file's parameters (fill_ratio 0.5, block_factor 2, nestingRadius 4, max_box_size 64, tags_grow 4)."""
-    t_setup = time.perf_counter()
-    size = cfg.nx
-    bg = cfg.distributed_input
-    tags0 = amr.tagCellsLevel(F0["rhs"], 20.0 * bg, 1e30, 4)
-    mr = amr.BRMeshRefine((0, 0, cfg.nx - 1, cfg.ny - 1), 0.5, 2, 4, 64)
-    base = layout0.boxes
-    lv = mr.regrid(base, [tags0], max_boxes=1 << 18)
-    if len(lv) < 2:
-        return {"skipped": "no cell tagged"}
-
-    def make_level(l, boxes):
-        r = 2 ** l
-        lay = amr.DisjointBoxLayout(ctx, boxes, (0, 0, cfg.nx * r - 1, cfg.ny * r - 1), cfg.periodic)
-        spec = dict(head=(1, 0), rhs=(0, 0), B=(1, 0), Pi=(1, 0), zb=(1, 0), mask=(1, 0), a=(0, 0), bX=(0, 1), bY=(0, 2))
-        F = {k: amr.LevelData(lay, 1, ng, cent) for k, (ng, cent) in spec.items()}
-        fabs = {k: [] for k in ("head", "rhs", "B", "Pi", "zb", "mask")}
-        for bx in boxes:
-            g = syn.fields(cfg, ng=1, lo=(int(bx[0]), int(bx[1])), shape=(int(bx[2] - bx[0] + 1), int(bx[3] - bx[1] + 1)), level_ratio=r)
-            for k in fabs:
-                fabs[k].append(g[k][None])
-        for k in fabs:
-            F[k].upload(fabs[k])
-        return lay, F
-
-    lay1, F1 = make_level(1, lv[1])
-    tags1 = amr.tagCellsLevel(F1["rhs"], 200.0 * bg, 1e30, 4)
-    lv = mr.regrid(base, [tags0, tags1], max_boxes=1 << 18)
-    levels = [(layout0, F0)]
-    for l in range(1, len(lv)):
-        levels.append(make_level(l, lv[l]))
-    nlev = len(levels)
-    f = lambda k: [F[k] for _, F in levels]  # noqa: E731
-    fac = amr.VCAMRNonLinearPoissonOpFactory().define(ctx, [lay for lay, _ in levels], [2] * (nlev - 1), cfg.dx, bc, 0.0, f("a"), -1.0,
-                                                      f("bX"), f("bY"), prm, f("B"), f("Pi"), f("zb"), f("mask"))
-    ops = [fac.AMRnewOp(l) for l in range(nlev)]
-    for l in range(nlev):  # bCoef = B(h) as the Picard body hands it over
-        ops[l].UpdateOperator(levels[l][1]["head"], levels[l - 1][1]["head"] if l > 0 else None, l, 0, False)
-    mg = amr.AMRFASMultiGrid().define(fac, nlev)
-    mg.setSolverParameters(4, 4, args.bottom, 1, 100, 1e-10, 1e-4, 1e-7)
-    t_setup = time.perf_counter() - t_setup
-    mg.solve(f("head"), f("rhs"), fixed_cycles=2)
-    it, hist, st = mg.solve(f("head"), f("rhs"), fixed_cycles=args.amr_cycles)
-    per = mg.cell_updates_per_cycle()
-    cells = [int(sum((b[2] - b[0] + 1) * (b[3] - b[1] + 1) for b in lay.boxes)) for lay, _ in levels]
-    return {"levels": nlev, "boxes": [len(lay.boxes) for lay, _ in levels], "cells": cells, "vcycles": args.amr_cycles,
-            "ms_per_vcycle": st.device_ms / args.amr_cycles, "cell_updates_per_s": per * args.amr_cycles / (st.device_ms * 1e-3),
-            "launches_per_vcycle": st.kernel_launches / args.amr_cycles, "resnorm": [float(hist[0]), float(hist[-1])],
-            "setup_s": t_setup, "grids": "sg_tag_cells_level + sg_br_regrid (fill 0.5, block factor 2, nesting 4, max box 64, tags_grow 4)"}
+def workload_config(args, world, cells, boxes):
+    return {"workload": f"AMR_multiMoulins, {len(cells)}-level AMR on a {args.size}x{args.size} base grid per "
+                        f"{'GPU (weak scaling: tiles stacked in y)' if args.scaling == 'weak' else 'job (strong scaling)'}; "
+                        f"boxes per level {boxes}, cells per level {cells}, 64^2 boxes, base-level MG depths 0-5",
+            "step": "one composite FAS V-cycle over all levels incl. UpdateOperator/AverageOperator and the composite residual max-norm",
+            "pre": 4, "post": 4, "bottom": args.bottom,
+            "grids": "tagging (rhs > 20x / 200x background recharge, tags_grow 4) + Berger-Rigoutsos (fill 0.5, block factor 2, nesting 4, max box 64)",
+            "l2_policy": "inputs larger than L2 (base-level fields 512 MiB each, ~9 GB touched per V-cycle)"}
 
 
-def gap_leg(ctx, amr, cfg, layout, F, op0, host, args):
+# ---------------------------------------------------------------------------------------------------------------------
+# GPU arm
+# ---------------------------------------------------------------------------------------------------------------------
+def gpu_tile_hierarchy(device, cfg, nlevels, rhs0_packed=None):
+    """grids of one tile: sg_tag_cells_level on the device + sg_br_regrid, in a private single-rank context"""
+    from suhmo_b200 import amr
+    ctx1 = amr.Context(device=device)
+    keep = []
+
+    def tag_level(l, boxes, rhs_fabs, thr):
+        lay = amr.DisjointBoxLayout(ctx1, boxes, (0, 0, (cfg.nx << l) - 1, (cfg.ny << l) - 1), cfg.periodic)
+        ld = amr.LevelData(lay, 1, 0, 0)
+        keep.append((lay, ld))
+        if l == 0:
+            if rhs0_packed is not None:
+                ld.upload_packed(rhs0_packed)
+            else:
+                ld.set_global(syn.fields(cfg, ng=1, rhs_only=True, moulin_cutoff=12.0)["rhs"], (0, 0))
+        else:
+            ld.upload(rhs_fabs)
+        return amr.tagCellsLevel(ld, thr, 1e30, wl.REGRID["tags_grow"])
+
+    mr = amr.BRMeshRefine((0, 0, cfg.nx - 1, cfg.ny - 1), wl.REGRID["fill_ratio"], wl.REGRID["block_factor"], wl.REGRID["nesting_radius"],
+                          wl.REGRID["max_box_size"])
+    levels = wl.build_tile_hierarchy(cfg, tag_level, lambda base, tags: mr.regrid(base, tags, max_boxes=1 << 18), nlevels)
+    for lay, ld in keep:
+        ld.destroy()
+    ctx1.destroy()
+    return levels
+
+
+def pack_boxes(garr, nbx, nby, bs, ng, out):
+    """[j,i] strip array with ng ghosts -> all boxes' FArrayBoxes consecutively (box order: x fastest)."""
+    from numpy.lib.stride_tricks import as_strided
+    s0, s1 = garr.strides
+    w = bs + 2 * ng
+    v = as_strided(garr, shape=(nby, nbx, w, w), strides=(bs * s0, bs * s1, s0, s1))
+    out.reshape(nby, nbx, w, w)[...] = v
+
+
+class GpuProblem:
+    """device twin of the workload: layouts, fields (uploaded from pinned host FArrayBox memory), factory, solver"""
+
+    def __init__(self, ctx, prob, rank, pinned=True, timers=None):
+        import torch
+        from suhmo_b200 import amr
+        self.amr, self.ctx, self.prob, self.rank = amr, ctx, prob, rank
+        cfg = prob.cfg
+        T = timers if timers is not None else {}
+        t = time.perf_counter()
+        self.layouts = [amr.DisjointBoxLayout(ctx, prob.levels[l], prob.domain(l), cfg.periodic, prob.owners[l]) for l in range(prob.nlev)]
+        T["layouts_s"] = time.perf_counter() - t
+        self.F, self.host = [], []
+        t_gen = t_up = 0.0
+        for l in range(prob.nlev):
+            lay = self.layouts[l]
+            F = {k: amr.LevelData(lay, 1, ng, cent) for k, (ng, cent) in SPEC.items()}
+            H = {}
+            ids = prob.owned(l, rank)
+            t = time.perf_counter()
+            if l == 0 and len(ids):
+                # the strip of the base level this rank owns, generated in one piece and cut into 64^2 FArrayBoxes
+                bx = prob.to_tile(0, prob.levels[0][ids])
+                y0, y1 = int(bx[:, 1].min()), int(bx[:, 3].max())
+                g = syn.fields(prob.tile_cfg, ng=1, lo=(0, y0), shape=(prob.size, y1 - y0 + 1), moulin_cutoff=12.0)
+                nbx, nby = prob.size // wl.BOX, (y1 - y0 + 1) // wl.BOX
+                for k in INPUTS:
+                    ng = SPEC[k][0]
+                    H[k] = torch.empty(F[k].packed_size(), dtype=torch.float64, pin_memory=pinned)
+                    pack_boxes(np.ascontiguousarray(g[k]), nbx, nby, wl.BOX, ng, H[k].numpy())
+                del g
+            elif len(ids):
+                fabs = prob.level_fabs(l, rank)
+                for k in INPUTS:
+                    H[k] = torch.empty(F[k].packed_size(), dtype=torch.float64, pin_memory=pinned)
+                    buf, off = H[k].numpy(), 0
+                    for b in ids:
+                        a = fabs[k][b]
+                        buf[off:off + a.size].reshape(a.shape)[...] = a
+                        off += a.size
+                del fabs
+            t_gen += time.perf_counter() - t
+            t = time.perf_counter()
+            for k in H:
+                F[k].upload_packed(H[k])
+            for k in ("B", "Pi", "zb", "mask"):
+                amr.CopyGhostCells(F[k])  # AmrHydro fills domain ghosts by copy before the solve
+            t_up += time.perf_counter() - t
+            self.F.append(F)
+            self.host.append(H)
+        T["field_synthesis_s"], T["upload_s"] = t_gen, t_up
+        t = time.perf_counter()
+        self.bc = amr.make_bc(cfg.bc_lo, cfg.bc_hi)
+        self.prm = amr.make_params(A=cfg.A, omega=cfg.omega, nu=cfg.nu, cutOffbr=cfg.cutOffbr, maxOffbr=cfg.maxOffbr)
+        f = self.fields
+        self.factory = amr.VCAMRNonLinearPoissonOpFactory().define(ctx, self.layouts, [2] * (prob.nlev - 1), cfg.dx, self.bc, 0.0, f("a"), -1.0,
+                                                                   f("bX"), f("bY"), self.prm, f("B"), f("Pi"), f("zb"), f("mask"))
+        self.ops = [self.factory.AMRnewOp(l) for l in range(prob.nlev)]
+        self.init_bcoef()
+        self.mg = amr.AMRFASMultiGrid().define(self.factory, prob.nlev)
+        ctx.sync()
+        T["operators_solver_s"] = time.perf_counter() - t
+
+    def fields(self, name, nlev=None):
+        return [F[name] for F in self.F[:nlev]]
+
+    def init_bcoef(self):
+        """bCoef = B(h) of the current head on every level, as the Picard body hands it to the solver (aCoeff_bCoeff)"""
+        for l in range(self.prob.nlev):
+            if l > 0:
+                self.ops[l].coarseFineInterp(self.F[l]["head"], self.F[l - 1]["head"])
+            self.ops[l].UpdateOperator(self.F[l]["head"], self.F[l - 1]["head"] if l > 0 else None, l, 0, False)
+
+    def upload_inputs(self, names):
+        for F, H in zip(self.F, self.host):
+            for k in names:
+                if k in H:
+                    F[k].upload_packed(H[k])
+
+    def host_bytes(self, names):
+        return int(sum(H[k].numel() * 8 for H in self.host for k in names if k in H))
+
+
+def small_configs(ctx, amr, threads, cycles=20):
+    """BASELINE configs[0..3] at their native level-0 sizes: launch-bound on a GPU, reported as time per V-cycle, CPU beside it"""
+    from oracle import binding as ob
+    from tests.problem import GpuSide, OracleSide
+    out = []
+    for name, scale in (("C1", 1), ("C1", 64), ("C2", 16), ("C3", 1), ("C4", 1)):
+        cfg = syn.config(name, scale)
+        boxes = syn.domain_split(cfg.nx, cfg.ny, cfg.max_box_size, cfg.block_factor)
+        orc = OracleSide(cfg, boxes)
+        orc.init_bcoef()
+        gpu = GpuSide(ctx, orc)
+        mg = amr.AMRFASMultiGrid().define(gpu.factory, 1)
+        mg.setSolverParameters(4, 4, 16, 1, 100, 1e-10, 1e-4, 1e-7)
+        mg.solve([gpu.F["head"]], [gpu.F["rhs"]], fixed_cycles=3)
+        _, ghist, st = mg.solve([gpu.F["head"]], [gpu.F["rhs"]], fixed_cycles=cycles)
+        ob.lib().orc_set_threads(threads)
+        sol = orc.solver()
+        sp = ob.make_solver_params(bottom=16, fixed_cycles=3)
+        sol.solve(orc.F["head"], orc.F["rhs"], sp)
+        sp = ob.make_solver_params(bottom=16, fixed_cycles=cycles)
+        t0 = time.perf_counter()
+        _, ohist = sol.solve(orc.F["head"], orc.F["rhs"], sp)
+        cpu_ms = 1e3 * (time.perf_counter() - t0) / cycles
+        out.append({"config": name, "grid": [int(cfg.nx), int(cfg.ny)], "mg_depths": mg.depth, "gpu_ms_per_vcycle": st.device_ms / cycles,
+                    "cpu_ms_per_vcycle": cpu_ms, "cpu_threads": threads, "launches_per_vcycle": st.kernel_launches / cycles,
+                    "resnorm_history_equal": bool(np.array_equal(ghist, ohist))})
+        mg.destroy()
+    return out
+
+
+def gap_leg(ctx, amr, cfg, layout, F, op0, bx_mean):
     """SURVEY.md 8 f2: the implicit gap-height solve of the same time step (AmrHydro::SolveForGap_nl) on the resident base grid,
     with the reference's solver constants.  aCoef = 1, D = the B(h) face coefficients rescaled so that beta*D/dx^2 ~ 4 (diffusion
     matters on the finest grid), rhs = b + a perturbation shaped like the moulin sources."""
@@ -211,9 +344,8 @@ def gap_leg(ctx, amr, cfg, layout, F, op0, host, args):
     one.upload_packed(np.ones(one.packed_size()))
     gap, rhs = amr.LevelData(layout, 1, 1, 0), amr.LevelData(layout, 1, 0, 0)
     rmax = op0.norm(F["rhs"], 0)
-    dmean = float(host["bX"].mean())
     dx = cfg.dx[0]
-    beta = 4.0 * dx * dx / dmean
+    beta = 4.0 * dx * dx / bx_mean
     res = None
     for rep in range(2):  # first pass warms up
         op0.assignLocal(gap, F["B"])
@@ -237,18 +369,20 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--size", type=int, default=8192, help="cells per GPU in x and y")
+    ap.add_argument("--size", type=int, default=8192, help="base-grid cells in x and y (per GPU when weak scaling)")
+    ap.add_argument("--levels", type=int, default=3, help="AMR levels (1: the base grid alone)")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"])
     ap.add_argument("--bottom", type=int, default=16)
-    ap.add_argument("--cpu-size", type=int, default=2048, help="bounded CPU sample (cells in x and y)")
-    ap.add_argument("--cpu-cycles", type=int, default=30, help="V-cycles of the bounded CPU sample (about 5-25 s of host work)")
+    ap.add_argument("--cpu-cycles", type=int, default=3, help="V-cycles of the CPU baseline leg (the whole workload; about 5 s each)")
     ap.add_argument("--e2e-cycles", type=int, default=5, help="V-cycles per head solve in the end-to-end leg")
     ap.add_argument("--e2e-steps", type=int, default=2)
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--relax-mode", type=int, default=1)
-    ap.add_argument("--no-amr", action="store_true", help="skip the 3-level AMR leg (N = 1 only)")
-    ap.add_argument("--amr-cycles", type=int, default=3)
     ap.add_argument("--tune", action="append", default=[], metavar="KEY=VALUE", help="experiment knob passed to sg_set_tuning")
     ap.add_argument("--no-gap", action="store_true", help="skip the implicit gap-height solve leg (N = 1 only)")
+    ap.add_argument("--no-small", action="store_true", help="skip the C1-C4 native-size table (N = 1 only)")
+    ap.add_argument("--no-parity", action="store_true", help="skip the multi-rank parity checks (N > 1)")
+    ap.add_argument("--profile", action="store_true", help="cudaProfilerStart/Stop around the timed V-cycles (ncu --profile-from-start off)")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -290,163 +424,192 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t[0])
 
-    # ---------------- synthetic inputs: this rank's strip of the global grid, as per-box FArrayBoxes in pinned memory
-    size, bs = args.size, 64
-    cfg = bench_config(size, world)
-    boxes, owner = strip_boxes(cfg, world)
-    nbx, nby = size // bs, size // bs
-    g = syn.fields(cfg, ng=1, lo=(0, rank * size), shape=(size, size))
-    layout = amr.DisjointBoxLayout(ctx, boxes, (0, 0, cfg.nx - 1, cfg.ny - 1), cfg.periodic, owner)
-    F, host = {}, {}
-    spec = dict(head=(1, 0), rhs=(0, 0), B=(1, 0), Pi=(1, 0), zb=(1, 0), mask=(1, 0), a=(0, 0), bX=(0, 1), bY=(0, 2))
-    for k, (ng, cent) in spec.items():
-        F[k] = amr.LevelData(layout, 1, ng, cent)
-    for k in ("head", "rhs", "B", "Pi", "zb", "mask"):
-        ng = spec[k][0]
-        n = F[k].packed_size()
-        host[k] = torch.empty(n, dtype=torch.float64, pin_memory=True)
-        src = g[k] if ng == 1 else g[k]
-        pack_boxes(np.ascontiguousarray(src), nbx, nby, bs, ng, pinned=host[k].numpy().reshape(nbx * nby, bs + 2 * ng, bs + 2 * ng))
-        F[k].upload_packed(host[k])
-    del g
-    for k in ("B", "Pi", "zb", "mask"):
-        amr.CopyGhostCells(F[k])  # AmrHydro fills domain ghosts by copy before the solve
-    bc = amr.make_bc(cfg.bc_lo, cfg.bc_hi)
-    prm = amr.make_params(A=cfg.A, omega=cfg.omega, nu=cfg.nu, cutOffbr=cfg.cutOffbr, maxOffbr=cfg.maxOffbr)
-    fac = amr.VCAMRNonLinearPoissonOpFactory().define(ctx, [layout], [], cfg.dx, bc, 0.0, [F["a"]], -1.0, [F["bX"]], [F["bY"]],
-                                                      prm, [F["B"]], [F["Pi"]], [F["zb"]], [F["mask"]])
-    op0 = fac.AMRnewOp(0)
-    op0.UpdateOperator(F["head"], None, 0, 0, False)  # bCoef = B(h) as the Picard body hands it over
-    mg = amr.AMRFASMultiGrid().define(fac, 1)
-    mg.setSolverParameters(4, 4, args.bottom, 1, 100, 1e-10, 1e-4, 1e-7)
-    head_out = torch.empty(F["head"].packed_size(), dtype=torch.float64, pin_memory=True)
-    host["bX"] = torch.empty(F["bX"].packed_size(), dtype=torch.float64, pin_memory=True)
-    host["bY"] = torch.empty(F["bY"].packed_size(), dtype=torch.float64, pin_memory=True)
-    F["bX"].download_packed(host["bX"])
-    F["bY"].download_packed(host["bY"])
-    ndepth = mg.depth
-    updates_per_cycle = mg.cell_updates_per_cycle()  # global (all ranks)
+    # ---------------- N > 1: multi-rank parity against the oracle before anything is timed (small grids, every rank checks its boxes)
+    parity_n = None
+    if world > 1 and not args.no_parity:
+        from tests import parity_multi
+        t0 = time.perf_counter()
+        parity_n = parity_multi.run_all(ctx, dist, rank, world)
+        parity_n["seconds"] = time.perf_counter() - t0
 
-    # ---------------- device-resident V-cycles: W warm-up, K timed (CUDA events inside the library, max over ranks)
+    # ---------------- the workload: grids (this arm's own tagging + regrid), owners, fields from pinned host FArrayBox memory
+    timers = {}
+    t0 = time.perf_counter()
+    tile_cfg = wl.tile_config(args.size)
+    levels = gpu_tile_hierarchy(local_rank, tile_cfg, args.levels)
+    timers["grid_generation_s"] = time.perf_counter() - t0
+    prob = wl.Problem(args.size, world, args.scaling, levels)
+    gp = GpuProblem(ctx, prob, rank, timers=timers)
+    nlev = prob.nlev
+    mg = gp.mg
+    mg.setSolverParameters(4, 4, args.bottom, 1, 100, 1e-10, 1e-4, 1e-7)
+    phi, rhs = gp.fields("head"), gp.fields("rhs")
+    updates_per_cycle = mg.cell_updates_per_cycle()  # global (all ranks, all levels)
+    timers["total_setup_s"] = time.perf_counter() - t0
+    info = prob.describe()
+
+    # ---------------- device-resident composite V-cycles: W warm-up, K timed (CUDA events inside the library, max over ranks)
+    hist_w = None
     if args.warmup > 0:
-        mg.solve([F["head"]], [F["rhs"]], fixed_cycles=args.warmup)
+        _, hist_w, _ = mg.solve(phi, rhs, fixed_cycles=args.warmup)
     clocks = Clocks(local_rank)
     if rank == 0:
         clocks.start()
         time.sleep(0.3)
     barrier()
     l0 = ctx.kernel_launches()
+    if args.profile:
+        torch.cuda.profiler.start()
     t0 = time.perf_counter()
-    it, hist, stats = mg.solve([F["head"]], [F["rhs"]], fixed_cycles=args.steps)
+    it, hist, stats = mg.solve(phi, rhs, fixed_cycles=args.steps)
     barrier()
     wall = time.perf_counter() - t0
+    if args.profile:
+        torch.cuda.profiler.stop()
     launches = ctx.kernel_launches() - l0
     dev_ms = max_over_ranks(stats.device_ms)
     value = updates_per_cycle * args.steps / (dev_ms * 1e-3)
 
-    # ---------------- dominant kernel alone: fused red+black GSRB sweep of the finest level, CUDA events on its stream
-    nrel = 16
-    op0.relax(F["head"], F["rhs"], 4)
-    ctx.event_record(0)
-    op0.relax(F["head"], F["rhs"], nrel)
-    ctx.event_record(1)
-    k_ms = ctx.event_elapsed_ms(0, 1) / nrel
-    clk = clocks.finish() if rank == 0 else None
-    cells_local = size * size
+    # ---------------- dominant kernels alone, CUDA events on the library's stream: the base level's streaming red+black sweep
+    # (k_gsrb_stream) and the refined levels' per-patch red+black sweep (k_gsrb_patch, finest level)
     peak, peak_src = measured_peak()
-    achieved = BYTES_PER_UPDATE_SMOOTHER * cells_local / (k_ms * 1e-3) / 1e9
+    nrel = 16
+    roof = []
+    for l in sorted({0, nlev - 1}):
+        cells_local = int(info["cells_per_rank"][l][rank])
+        if cells_local == 0:
+            continue
+        op = gp.ops[l]
+        op.relax(gp.F[l]["head"], gp.F[l]["rhs"], 4)
+        ctx.event_record(0)
+        op.relax(gp.F[l]["head"], gp.F[l]["rhs"], nrel)
+        ctx.event_record(1)
+        k_ms = ctx.event_elapsed_ms(0, 1) / nrel
+        bpu = BYTES_SMOOTHER_MASK if op.streams_mask() else BYTES_SMOOTHER_NOMASK
+        kname = "k_gsrb_stream" if l == 0 else "k_gsrb_patch"
+        achieved = bpu * cells_local / (k_ms * 1e-3) / 1e9
+        traffic, tfile = ncu_traffic(kname)
+        roof.append({"bound": "hbm", "kernel": f"{kname} (one GSRB iteration, level {l}: {cells_local} cells on this GPU)", "achieved": achieved,
+                     "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "traffic_source": tfile, "peak_source": peak_src,
+                     "kernel_ms": k_ms, "bytes_per_cell_update": bpu, "cells_per_launch": cells_local,
+                     "note": "achieved = bytes_per_cell_update x cells_per_launch / kernel_ms; 72 B/update algorithmic (SURVEY 8d), 64 B when the "
+                             "level's ice mask has no negative entry and is not streamed"})
+    clk = clocks.finish() if rank == 0 else None
+    roofline = dict(roof[0]) if roof else None
+    if roofline:
+        roofline["vcycle_gbs_at_97B"] = value / world * BYTES_PER_UPDATE_VCYCLE / 1e9
 
-    # ---------------- end to end through the public API with HOST buffers: one head solve = upload of all inputs from
-    # pinned FArrayBox memory, per-solve operator set-up, E2E_CYCLES V-cycles, download of the head
-    e2e_bytes_in = sum(host[k].numel() * 8 for k in ("head", "rhs", "B", "Pi", "zb", "mask", "bX", "bY"))
-    e2e_bytes_out = head_out.numel() * 8
-    e2e_times = []
-    for s in range(args.e2e_steps + 1 if args.e2e_steps > 0 else 0):  # --e2e-steps 0: profiling runs skip this leg
+    # ---------------- the base grid alone (round 1's headline), same resident fields
+    single = None
+    if nlev > 1:
+        mg.solve(phi[:1], rhs[:1], l_max=0, fixed_cycles=max(2, args.warmup))
         barrier()
-        t0 = time.perf_counter()
-        for k in ("head", "rhs", "B", "Pi", "zb", "mask", "bX", "bY"):
-            F[k].upload_packed(host[k])
-        for k in ("B", "Pi", "zb", "mask"):
-            amr.CopyGhostCells(F[k])
-        mg.refresh()
-        mg.solve([F["head"]], [F["rhs"]], fixed_cycles=args.e2e_cycles)
-        F["head"].download_packed(head_out)
-        barrier()
-        if s > 0:
-            e2e_times.append(time.perf_counter() - t0)
-    e2e_t = max_over_ranks(float(np.mean(e2e_times))) if e2e_times else float("nan")
-    e2e_value = updates_per_cycle * args.e2e_cycles / e2e_t
+        _, h1, st1 = mg.solve(phi[:1], rhs[:1], l_max=0, fixed_cycles=args.steps)
+        ms1 = max_over_ranks(st1.device_ms)
+        upd1 = st1.cell_updates / args.steps
+        single = {"ms_per_vcycle": ms1 / args.steps, "cell_updates_per_s": upd1 * args.steps / (ms1 * 1e-3), "cells": info["cells"][0],
+                  "launches_per_vcycle": st1.kernel_launches / args.steps, "resnorm": [float(h1[0]), float(h1[-1])]}
+
+    # ---------------- end to end through the public API with HOST buffers: one head solve = upload of all inputs of all levels from
+    # pinned FArrayBox memory, per-solve operator set-up, E2E_CYCLES V-cycles, download of the head of every level
+    head_out = [torch.empty(F["head"].packed_size(), dtype=torch.float64, pin_memory=True) for F in gp.F]
+    for F, H in zip(gp.F, gp.host):
+        for k in ("bX", "bY"):
+            H[k] = torch.empty(F[k].packed_size(), dtype=torch.float64, pin_memory=True)
+            if H[k].numel():
+                F[k].download_packed(H[k])
+    bx_mean = float(gp.host[0]["bX"].mean()) if gp.host[0]["bX"].numel() else 0.0
+
+    def e2e_leg(names, bcoef_only):
+        times = []
+        for s in range(args.e2e_steps + 1 if args.e2e_steps > 0 else 0):  # --e2e-steps 0: profiling runs skip this leg
+            barrier()
+            t0 = time.perf_counter()
+            gp.upload_inputs(names)
+            if not bcoef_only:
+                for F in gp.F:
+                    for k in ("B", "Pi", "zb", "mask"):
+                        amr.CopyGhostCells(F[k])
+            mg.refresh(bcoef_only=bcoef_only)
+            mg.solve(phi, rhs, fixed_cycles=args.e2e_cycles)
+            for F, out in zip(gp.F, head_out):
+                if out.numel():
+                    F["head"].download_packed(out)
+            barrier()
+            if s > 0:
+                times.append(time.perf_counter() - t0)
+        return max_over_ranks(float(np.mean(times))) if times else float("nan")
+
+    all_names = INPUTS + ("bX", "bY")
+    e2e_t = e2e_leg(all_names, False)
     # the same call inside a Picard loop: gap height, overburden pressure, bed elevation and ice mask do not change between the
     # Picard iterations of a time step (src/AmrHydro.cpp:2477-3235), so only head, rhs and bCoef are re-sent
-    pic_fields = ("head", "rhs", "bX", "bY")
-    pic_times = []
-    for s in range(args.e2e_steps + 1 if args.e2e_steps > 0 else 0):
-        barrier()
-        t0 = time.perf_counter()
-        for k in pic_fields:
-            F[k].upload_packed(host[k])
-        mg.refresh()
-        mg.solve([F["head"]], [F["rhs"]], fixed_cycles=args.e2e_cycles)
-        F["head"].download_packed(head_out)
-        barrier()
-        if s > 0:
-            pic_times.append(time.perf_counter() - t0)
-    pic_t = max_over_ranks(float(np.mean(pic_times))) if pic_times else float("nan")
+    pic_names = ("head", "rhs", "bX", "bY")
+    pic_t = e2e_leg(pic_names, True)
+    e2e_out = int(sum(o.numel() * 8 for o in head_out))
 
-    # ---------------- CPU baseline beside it (rank 0, N = 1 only): bounded sample, all host threads
-    cpu = None
+    # ---------------- CPU baseline beside it (rank 0, N = 1 only): the oracle on the SAME workload (same grids, same fields), a few
+    # V-cycles with all host threads; its residual-norm history must equal the GPU's warm-up history bit for bit
+    cpu = parity_full = None
+    threads = os.cpu_count() or 1
     if rank == 0 and world == 1 and not args.no_cpu:
-        threads = os.cpu_count() or 1
-        v, dt, d = cpu_vcycles(args.cpu_size, args.cpu_cycles, threads, args.bottom)
-        cpu = {"value": v, "unit": UNIT, "cores": threads, "kind": "port",
-               "sample": f"{args.cpu_cycles} FAS V-cycles on a {args.cpu_size}x{args.cpu_size} sample of the workload "
-                         f"({dt:.1f} s), oracle C restatement with OpenMP over boxes"}
+        t0 = time.perf_counter()
+        cp = CpuProblem(args.size, args.levels, threads, levels=levels)
+        cpu_setup = time.perf_counter() - t0
+        v, dt, ohist = cp.solve(args.cpu_cycles, args.bottom)
+        cpu = {"value": v, "unit": UNIT, "cores": threads, "kind": "port", "ms_per_vcycle": 1e3 * dt / args.cpu_cycles,
+               "sample": f"{args.cpu_cycles} composite FAS V-cycles on the whole workload ({dt:.1f} s + {cpu_setup:.0f} s set-up), oracle C "
+                         f"restatement with OpenMP over boxes"}
+        if hist_w is not None:
+            n = min(len(ohist), len(hist_w))
+            parity_full = {"resnorm_history_equal": bool(np.array_equal(ohist[:n], hist_w[:n])), "vcycles_compared": n - 1,
+                           "gpu": [float(x) for x in hist_w[:n]], "oracle": [float(x) for x in ohist[:n]],
+                           "what": "composite residual max-norm before and after each V-cycle, full-size workload, GPU library vs CPU oracle"}
+        del cp
 
-    gap_info = None
+    gap_info = small = None
     if world == 1 and not args.no_gap:
         try:
-            gap_info = gap_leg(ctx, amr, cfg, layout, F, op0, host, args)
-        except Exception as e:
-            gap_info = {"failed": repr(e)[:300]}
-
-    amr_info = None
-    if world == 1 and not args.no_amr:
-        try:
-            amr_info = amr_leg(ctx, amr, cfg, layout, F, bc, prm, args)
+            gap_info = gap_leg(ctx, amr, prob.cfg, gp.layouts[0], gp.F[0], gp.ops[0], bx_mean)
         except Exception as e:  # the headline numbers above do not depend on this leg
-            amr_info = {"failed": repr(e)[:300]}
+            gap_info = {"failed": repr(e)[:300]}
+    if rank == 0 and world == 1 and not args.no_small and not args.no_cpu:
+        try:
+            small = small_configs(ctx, amr, threads)
+        except Exception as e:
+            small = {"failed": repr(e)[:300]}
 
     if rank == 0:
+        cfgd = workload_config(args, world, info["cells"], info["boxes"])
+        cfgd.update({"partition": f"base level: box-wise y-strips over {world} GPU(s); refined levels: "
+                                  + ("the tile's boxes on the tile's GPU" if args.scaling == "weak" else "connected clusters balanced by cell count"),
+                     "cells_per_rank": info["cells_per_rank"],
+                     "relax_mode": {0: "separate colour passes", 1: "fused red+black sweeps (k_gsrb_stream on the base level and its MG depths, "
+                                    "k_gsrb_patch on refined levels)", 2: "register-only fused sweep", 3: "two GSRB iterations per pass"}.get(args.relax_mode),
+                     "e2e_step": f"one head solve = H2D of 8 fields x {nlev} levels + set-up + {args.e2e_cycles} V-cycles + D2H of the head of every level"})
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f64", "data": "synthetic",
-            "config": {"workload": f"AMR_multiMoulins base grid scaled to {size}x{size} cells per GPU (global {cfg.nx}x{cfg.ny}), "
-                                   f"single level, {len(boxes)} boxes of 64^2, MG depths 0-{ndepth - 1}",
-                       "step": "one FAS V-cycle incl. UpdateOperator/AverageOperator and residual max-norm",
-                       "pre": 4, "post": 4, "bottom": args.bottom, "partition": f"box-wise y-strips over {world} GPU(s)",
-                       "l2_policy": "inputs larger than L2 (finest-level fields 512 MiB each)",
-                       "relax_mode": {0: "separate colour passes", 1: "streaming red+black sweep, cp.async-staged", 2: "register-only fused sweep", 3: "streaming sweep, two GSRB iterations per pass (temporal blocking), cp.async-staged"}[args.relax_mode],
-                       "e2e_step": f"one head solve = H2D of 8 fields + set-up + {args.e2e_cycles} V-cycles + D2H of head"},
-            "roofline": {"bound": "hbm", "kernel": {1: "k_gsrb_stream", 3: "k_gsrb_stream2 (2 iterations per launch)"}.get(args.relax_mode, "levelGSRB") + ", finest level", "achieved": achieved, "peak": peak,
-                         "unit": "GB/s", "frac": achieved / peak, "traffic": NCU_TRAFFIC.get((size, args.relax_mode)), "peak_source": peak_src,
-                         "kernel_ms": k_ms, "iterations_per_launch": 2 if args.relax_mode == 3 else 1,
-                         "launch_ms": k_ms * (2 if args.relax_mode == 3 else 1), "bytes_per_cell_update": BYTES_PER_UPDATE_SMOOTHER,
-                         "note": "algorithmic 72 B/update (SURVEY 8d); on this data set the ice mask has no negative entry, so the kernel "
-                                 "skips streaming it (64 B/update actually requested)",
-                         "vcycle_gbs_at_97B": value / world * BYTES_PER_UPDATE_VCYCLE / 1e9},
+            "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic", "config": cfgd,
+            "roofline": roofline, "roofline_kernels": roof,
             "cpu_baseline": cpu,
-            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": e2e_bytes_in, "d2h_bytes_per_step": e2e_bytes_out,
-                    "ms_per_step": 1e3 * e2e_t, "vcycles_per_step": args.e2e_cycles},
+            "e2e": {"value": updates_per_cycle * args.e2e_cycles / e2e_t, "unit": UNIT, "h2d_bytes_per_step": gp.host_bytes(all_names),
+                    "d2h_bytes_per_step": e2e_out, "ms_per_step": 1e3 * e2e_t, "vcycles_per_step": args.e2e_cycles,
+                    "note": "bytes are this rank's; every rank moves its own share"},
             "e2e_picard_iteration": {"value": updates_per_cycle * args.e2e_cycles / pic_t, "unit": UNIT,
-                                     "h2d_bytes_per_step": sum(host[k].numel() * 8 for k in pic_fields), "d2h_bytes_per_step": e2e_bytes_out,
-                                     "ms_per_step": 1e3 * pic_t,
+                                     "h2d_bytes_per_step": gp.host_bytes(pic_names), "d2h_bytes_per_step": e2e_out, "ms_per_step": 1e3 * pic_t,
                                      "note": "head solve inside a Picard loop: only head, rhs, bCoef re-sent; static fields stay resident"},
             "gpu_launches": int(launches),
-            "amr_3level": amr_info,
+            "launches_per_vcycle": launches / args.steps,
+            "single_level": single,
+            "parity_full_size": parity_full,
+            "parity_nranks": parity_n,
+            "small_configs": small,
             "gap_solve": gap_info,
+            "setup": timers,
             "clocks": clk,
-            "resnorm": [float(hist[0]), float(hist[-1])],
+            "resnorm": [float(x) for x in (hist_w if hist_w is not None else hist)[:4]],
+            "resnorm_timed": [float(hist[0]), float(hist[-1])],
             "wall_ms_per_step": 1e3 * wall / args.steps,
         }
         print(json.dumps(line), flush=True)
