@@ -133,7 +133,7 @@ class CpuProblem:
         self.ob = ob
         cfg = wl.tile_config(size)
         self.levels = levels if levels is not None else cpu_tile_hierarchy(cfg, nlevels)
-        self.orc = AmrOracleSide(cfg, self.levels, boxwise=True)
+        self.orc = AmrOracleSide(cfg, self.levels, boxwise=True, periodic_ghosts=True)
         self.orc.init_bcoef()
         self.sol = self.orc.solver()
         self.nlev = len(self.levels)
@@ -247,7 +247,7 @@ class GpuProblem:
                 # the strip of the base level this rank owns, generated in one piece and cut into 64^2 FArrayBoxes
                 bx = prob.to_tile(0, prob.levels[0][ids])
                 y0, y1 = int(bx[:, 1].min()), int(bx[:, 3].max())
-                g = syn.fields(prob.tile_cfg, ng=1, lo=(0, y0), shape=(prob.size, y1 - y0 + 1), moulin_cutoff=12.0)
+                g = syn.fields(prob.tile_cfg, ng=1, lo=(0, y0), shape=(prob.size, y1 - y0 + 1), moulin_cutoff=12.0, periodic_ghosts=True)
                 nbx, nby = prob.size // wl.BOX, (y1 - y0 + 1) // wl.BOX
                 for k in INPUTS:
                     ng = SPEC[k][0]

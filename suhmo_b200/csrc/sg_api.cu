@@ -70,7 +70,7 @@ struct sg_ctx {
   bool smem_attr_set = false; // dynamic shared-memory opt-in of the streaming kernels done for this context's device
   cudaStream_t comm_stream = nullptr;    // nranks > 1: halo exchanges that overlap the interior part of a sweep run here
   cudaEvent_t ev_comm[2] = {nullptr, nullptr};
-  int tune[8] = {0, 0, 0, 0, 0, 0, 0, 0}; // experiment knobs (sg_set_tuning): 0 rows per warp, 1 CTAs per SM of the fused sweep
+  int tune[16] = {0}; // experiment knobs (sg_set_tuning): 0 rows per warp, 1 CTAs per SM of the fused sweep
   SgNccl nccl;
   // reduction scratch
   double* d_partial = nullptr;
@@ -134,6 +134,7 @@ struct sg_layout {
   GRec* d_grec = nullptr;
   int* d_grec_start = nullptr;
   size_t fused_smem = 0;
+  int fused_carveout = 0;
 };
 #define GEN_GX 2
 #define GEN_GY 2
@@ -189,6 +190,7 @@ struct sg_solver {
   // AMR levels (index = level; entry 0 of aops aliases ops[0])
   std::vector<sg_op*> aops;
   std::vector<sg_field*> aresid, acorr, atmp, ascratch, aresC;
+  std::vector<sg_field*> asave;                     // level l > 0: the coarser level's phi under and around level l before the coarse solve (coarsened-fine layout)
   // one FAS V-cycle + residual norm captured as a CUDA graph (launch-bound levels: ~110 launches become one)
   bool coefs_averaged = false;                      // this V-cycle's depth >= 1 face coefficients are already averaged (average_all_depths)
   cudaGraphExec_t gexec = nullptr;
@@ -335,7 +337,7 @@ extern "C" int sg_ctx_event_elapsed_ms(sg_ctx* c, int slot0, int slot1, double* 
   return SG_OK;
 }
 extern "C" int sg_set_tuning(sg_ctx* c, int key, int value) {
-  REQUIRE(c && key >= 0 && key < 8, "sg_set_tuning: key 0..7");
+  REQUIRE(c && key >= 0 && key < 16, "sg_set_tuning: key 0..15");
   c->tune[key] = value;
   return SG_OK;
 }
@@ -1145,12 +1147,21 @@ static int coef_ghosts(sg_op* op, bool only_b) {
 static int op_scan_mask(sg_op* op) {
   sg_layout* L = op->lay;
   op->mask_needed = true;
-  if (!L->has_local || !L->fast) return SG_OK;
+  if (!L->has_local) return SG_OK;
   sg_ctx* c = op->ctx;
   int* flag = reinterpret_cast<int*>(c->d_scalar + 120);
   CK(cudaMemsetAsync(flag, 0, sizeof(int), c->stream));
-  // valid cells plus the ghost rows/columns the streaming sweeps may update (8 rows, 3 columns)
-  LAUNCH(c, k_any_negative, grid2(L->nx + 6, L->ny + 16, B2D), B2D, op->mask->p() - 8 * (ptrdiff_t)L->pitch - 3, L->pitch, L->nx + 6, L->ny + 16, flag);
+  if (L->fast) {
+    // valid cells plus the ghost rows/columns the streaming sweeps may update (8 rows, 3 columns)
+    LAUNCH(c, k_any_negative, grid2(L->nx + 6, L->ny + 16, B2D), B2D, op->mask->p() - 8 * (ptrdiff_t)L->pitch - 3, L->pitch, L->nx + 6, L->ny + 16, flag);
+  } else {
+    // patch table: the whole allocation (every patch with its ghost ring; padding is zero-filled at creation), as rows of 4096
+    const long long n = (long long)op->mask->comp_stride;
+    const int w = 4096, rows = (int)((n + w - 1) / w);
+    if (rows > 1) LAUNCH(c, k_any_negative, grid2(w, rows - 1, B2D), B2D, op->mask->cb(), w, w, rows - 1, flag);
+    const int tail = (int)(n - (long long)(rows - 1) * w);
+    LAUNCH(c, k_any_negative, grid2(tail, 1, B2D), B2D, op->mask->cb() + (long long)(rows - 1) * w, w, tail, 1, flag);
+  }
   int h = 1;
   CK(cudaMemcpyAsync(&h, flag, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
   CK(cudaStreamSynchronize(c->stream));
@@ -1440,7 +1451,8 @@ extern "C" int sg_op_relaxNF(sg_op* op, sg_field* phi, const sg_field* phi_coars
 }
 
 // BC -> exchange -> (NL fused) kernel; mode 0 apply, 1 residual, 2 residual + max-norm into d_scalar[slot]
-static int apply_impl(sg_op* op, sg_field* out, sg_field* phi, const sg_field* rhs, int homogeneous, int mode, int slot, int ghost_depth = 1) {
+static int apply_impl(sg_op* op, sg_field* out, sg_field* phi, const sg_field* rhs, int homogeneous, int mode, int slot, int ghost_depth = 1,
+                      const unsigned char* special = nullptr) {
   sg_layout* L = op->lay;
   sg_ctx* c = op->ctx;
   if (!L->has_local) {
@@ -1449,7 +1461,7 @@ static int apply_impl(sg_op* op, sg_field* out, sg_field* phi, const sg_field* r
     return SG_OK;
   }
   if (!L->fast) {
-    if (mode == 4) return fail(SG_ERR_UNSUPPORTED, "FAS coarse right-hand side accumulation exists on uniform (one-patch) levels only");
+    if (mode >= 4) return fail(SG_ERR_UNSUPPORTED, "FAS coarse right-hand side accumulation and the fused composite sweeps exist on uniform (one-patch) levels only");
     return apply_g(op, out, phi, rhs, homogeneous, mode == 3 ? 2 : mode, slot, true);
   }
   OpArgs a = make_args(op);
@@ -1476,6 +1488,8 @@ static int apply_impl(sg_op* op, sg_field* out, sg_field* phi, const sg_field* r
   if (mode == 0) APPLY_LAUNCH(0, out->p(), phi->p(), nullptr, a, nb);
   else if (mode == 1) APPLY_LAUNCH(1, out->p(), phi->p(), rhs->p(), a, nb);
   else if (mode == 4) APPLY_LAUNCH(4, out->p(), phi->p(), nullptr, a, nb);
+  else if (mode == 5) APPLY_LAUNCH(5, out->p(), phi->p(), rhs->p(), a, nb);
+  else if (mode == 6) APPLY_LAUNCH(6, nullptr, phi->p(), rhs->p(), a, nb, special + ((ptrdiff_t)SG_YOFF * L->pitch + SG_XOFF)); // the map is addressed from the component base
   else {
     CK(cudaMemsetAsync(nb, 0, sizeof(double), c->stream));
     if (mode == 3) APPLY_LAUNCH(3, nullptr, phi->p(), rhs->p(), a, nb);
@@ -1611,7 +1625,7 @@ extern "C" int sg_op_AverageOperator(sg_op* op, const sg_op* finest, int depth) 
 // sweep then moves 64 instead of 72 bytes per cell-update -- what a roofline figure must be computed with)
 extern "C" int sg_op_streams_mask(const sg_op* op, int* out) {
   REQUIRE(op && out, "sg_op_streams_mask: null");
-  *out = (op->lay->fast && !op->mask_needed) ? 0 : 1;
+  *out = op->mask_needed ? 1 : 0;
   return SG_OK;
 }
 extern "C" int sg_op_lambda(sg_op* op, sg_field* lam) {
@@ -1771,16 +1785,18 @@ extern "C" int sg_op_createCoarsened(sg_op* op, sg_field** out, const sg_field* 
 }
 // AMRRestrictS (:1027-1069): res_coarse lives on the coarsened-fine layout (createCoarsened)
 static int amr_restrict_impl(sg_op* op, sg_field* resC, const sg_field* residual, sg_field* correction, const sg_field* coarseCorrection,
-                             sg_field* scratch, int skip_res) {
+                             sg_field* scratch, int skip_res, bool keep_scratch = true) {
   REQUIRE(op->link, "AMRRestrictS: operator has no coarser level");
   sg_layout* L = op->lay;
   REQUIRE(resC->lay->patches.size() == L->patches.size(), "AMRRestrictS: res_coarse must live on the coarsened fine layout");
+  const sg_field* from = scratch;
   if (!skip_res) SGCALL(amr_residual_impl(op, scratch, nullptr, correction, coarseCorrection, residual, 0, nullptr));
-  else SGCALL(vec_launch<3>(scratch, residual, nullptr, 0, 0, true)); // assignLocal
+  else if (keep_scratch) SGCALL(vec_launch<3>(scratch, residual, nullptr, 0, 0, true)); // assignLocal
+  else from = residual; // the V-cycle driver never reads the scratch copy: average straight from the field
   sg_layout* Lc = resC->lay;
   if (!L->has_local) return SG_OK;
   dim3 g((Lc->max_nx + B2D.x - 1) / B2D.x, (Lc->max_ny + B2D.y - 1) / B2D.y, (unsigned)Lc->patches.size());
-  LAUNCH(op->ctx, k_amr_average, g, B2D, resC->cb(), Lc->d_patches, scratch->cb(), L->d_patches);
+  LAUNCH(op->ctx, k_amr_average, g, B2D, resC->cb(), Lc->d_patches, from->cb(), L->d_patches);
   return SG_OK;
 }
 extern "C" int sg_op_AMRRestrictS(sg_op* op, sg_field* res_coarse, const sg_field* residual, sg_field* correction,
@@ -1789,7 +1805,11 @@ extern "C" int sg_op_AMRRestrictS(sg_op* op, sg_field* res_coarse, const sg_fiel
   return amr_restrict_impl(op, res_coarse, residual, correction, coarse_correction, scratch, skip_res);
 }
 // AMRProlongS / AMRProlongS_2 (:1105-1206): the coarsened-fine scratch and its copiers are the operator's own
-static int amr_prolong_impl(sg_op* op, sg_field* correction, const sg_field* coarseCorrection, sg_op* crseOp, int second_order) {
+// saved != nullptr (the V-cycle driver): coarseCorrection is the coarse level's NEW phi and `saved` its state before the coarse solve,
+// copied onto the scratch's layout with the same plan; the correction phi_new - phi_saved (the driver's axby over the whole coarse
+// level in the reference) is formed on the scratch, i.e. only where the prolongation reads it
+static int amr_prolong_impl(sg_op* op, sg_field* correction, const sg_field* coarseCorrection, sg_op* crseOp, int second_order,
+                            const sg_field* saved = nullptr) {
   AmrLink* K = op->link;
   REQUIRE(K, "AMRProlong: operator has no coarser level");
   sg_ctx* c = op->ctx;
@@ -1797,6 +1817,14 @@ static int amr_prolong_impl(sg_op* op, sg_field* correction, const sg_field* coa
   if (second_order) {
     REQUIRE(crseOp, "AMRProlongS_2: needs the coarser operator");
     SGCALL(run_plan(c, K->temp->cb(), coarseCorrection->cb(), K->c2t[1]));
+    if (saved && L->has_local) {
+      sg_field one = *K->temp;
+      one.ncomp = 1;
+      const int ngs = one.ng;
+      one.ng = 1;
+      SGCALL(vec_launch<0>(&one, &one, saved, 1.0, -1.0, true)); // scratch = 1*phi_new + (-1)*phi_saved, ghost ring included
+      one.ng = ngs;
+    }
     if (L->has_local) {
       int ngs = K->temp->ng;
       K->temp->ng = 1;
@@ -2000,15 +2028,15 @@ extern "C" int sg_solver_define(sg_factory* f, sg_solver** out, int num_levels) 
     sg_op* op = s->ops[0];
     if (l > 0) SGCALL(sg_factory_AMRnewOp(f, l, &op));
     s->aops.push_back(op);
-    sg_field *res = nullptr, *corr = nullptr, *tmp = nullptr, *scr = nullptr, *resC = nullptr;
+    sg_field *res = nullptr, *corr = nullptr, *tmp = nullptr, *scr = nullptr, *resC = nullptr, *sav = nullptr;
     SGCALL(sg_field_create(op->lay, &res, 1, 0, SG_CELL));
     if (num_levels > 1) {
-      SGCALL(sg_field_create(op->lay, &corr, 1, 1, SG_CELL));
       SGCALL(sg_field_create(op->lay, &tmp, 1, 0, SG_CELL));
       SGCALL(sg_field_create(op->lay, &scr, 1, 1, SG_CELL));
-      if (l > 0) SGCALL(sg_field_create(op->link->clay, &resC, 1, 1, SG_CELL));
+      if (l > 0) { SGCALL(sg_field_create(op->link->clay, &resC, 1, 1, SG_CELL)); SGCALL(sg_field_create(op->link->clay, &sav, 1, 1, SG_CELL)); }
     }
     s->aresid.push_back(res); s->acorr.push_back(corr); s->atmp.push_back(tmp); s->ascratch.push_back(scr); s->aresC.push_back(resC);
+    s->asave.push_back(sav);
   }
   s->resid = s->aresid[0];
   *out = s;
@@ -2050,7 +2078,7 @@ extern "C" int sg_solver_destroy(sg_solver* s) {
   }
   for (size_t l = 0; l < s->aops.size(); l++) {
     sg_field_destroy(s->aresid[l]); sg_field_destroy(s->acorr[l]); sg_field_destroy(s->atmp[l]); sg_field_destroy(s->ascratch[l]);
-    sg_field_destroy(s->aresC[l]);
+    sg_field_destroy(s->aresC[l]); sg_field_destroy(s->asave[l]);
     if (l > 0) sg_op_destroy(s->aops[l]);
   }
   for (sg_op* op : s->ops) sg_op_destroy(op);
@@ -2157,21 +2185,39 @@ static int amr_vcycle(sg_solver* s, sg_field* const* phi, sg_field* const* rhs, 
     return r;
   }
   sg_op* opc = s->aops[ilev - 1];
-  SGCALL(sg_op_relaxNF(op, phi[ilev], phi[ilev - 1], s->aresid[ilev], sp->pre, iter, ilev, 0));
+  sg_ctx* c = s->ctx;
+  // this level's right-hand side: the top level solves against the caller's rhs itself (the reference copies it into residual[lmax])
+  sg_field* rl = ilev == l_max ? rhs[ilev] : s->aresid[ilev];
+  SGCALL(sg_op_relaxNF(op, phi[ilev], phi[ilev - 1], rl, sp->pre, iter, ilev, 0));
   // phi[ilev-1] <- average of phi[ilev] on the covered region (AMRRestrictS with skip_res), kept as the FAS reference state
-  SGCALL(amr_restrict_impl(op, s->aresC[ilev], phi[ilev], phi[ilev], phi[ilev - 1], s->ascratch[ilev], 1));
-  SGCALL(run_plan(s->ctx, phi[ilev - 1]->cb(), s->aresC[ilev]->cb(), op->link->t2c));
-  SGCALL(vec_launch<3>(s->acorr[ilev - 1], phi[ilev - 1], nullptr, 0, 0, true)); // assignLocal
-  SGCALL(amr_residual_level(s, phi, rhs, ilev - 1, l_max));
-  SGCALL(amr_restrict_impl(op, s->aresC[ilev], s->aresid[ilev], phi[ilev], phi[ilev - 1], s->ascratch[ilev], 0));
-  SGCALL(run_plan(s->ctx, s->aresid[ilev - 1]->cb(), s->aresC[ilev]->cb(), op->link->t2c));
-  SGCALL(amr_operator_impl(opc, s->atmp[ilev - 1], nullptr, phi[ilev - 1], ilev - 1 > 0 ? phi[ilev - 2] : nullptr, 0, nullptr));
-  SGCALL(vec_launch<1>(s->aresid[ilev - 1], s->atmp[ilev - 1], nullptr, 1.0, 0, false));
+  SGCALL(amr_restrict_impl(op, s->aresC[ilev], phi[ilev], phi[ilev], phi[ilev - 1], s->ascratch[ilev], 1, false));
+  SGCALL(run_plan(c, phi[ilev - 1]->cb(), s->aresC[ilev]->cb(), op->link->t2c));
+  // the reference state is only ever read back under and around level ilev (AMRProlongS_2's scratch): keep it there
+  SGCALL(run_plan(c, s->asave[ilev]->cb(), phi[ilev - 1]->cb(), op->link->c2t[1]));
+  // coarse right-hand side: composite residual, its covered part replaced by the averaged fine residual, plus AMROperatorNF(phi)
+  const bool fused = opc->lay->fast && ilev - 1 == 0 && c->tune[9] != 1;
+  if (fused) {
+    // one sweep over the base level: (rhs - L phi) + L phi; the cells next to level ilev are refluxed and those under it redone below
+    sg_field* res = s->aresid[ilev - 1];
+    SGCALL(fine_link_build(opc, op->lay));
+    SGCALL(apply_impl(opc, res, phi[ilev - 1], rhs[ilev - 1], 0, 5, 0));
+    SGCALL(reflux_impl(opc, phi[ilev], phi[ilev - 1], res, op, 1, rhs[ilev - 1], 0));
+    SGCALL(amr_restrict_impl(op, s->aresC[ilev], rl, phi[ilev], phi[ilev - 1], s->ascratch[ilev], 0));
+    SGCALL(run_plan(c, res->cb(), s->aresC[ilev]->cb(), op->link->t2c));
+    FineLink* F = opc->flink;
+    if (F->nzero && opc->lay->has_local)
+      LAUNCH(c, k_add_lof_segs, dim3((unsigned)F->nzero, 2), 128, res->cb(), phi[ilev - 1]->cb(), make_args(opc), opc->lay->patches[0].off, F->d_zero, F->nzero);
+  } else {
+    SGCALL(amr_residual_level(s, phi, rhs, ilev - 1, l_max));
+    SGCALL(amr_restrict_impl(op, s->aresC[ilev], rl, phi[ilev], phi[ilev - 1], s->ascratch[ilev], 0));
+    SGCALL(run_plan(c, s->aresid[ilev - 1]->cb(), s->aresC[ilev]->cb(), op->link->t2c));
+    SGCALL(amr_operator_impl(opc, s->atmp[ilev - 1], nullptr, phi[ilev - 1], ilev - 1 > 0 ? phi[ilev - 2] : nullptr, 0, nullptr));
+    SGCALL(vec_launch<1>(s->aresid[ilev - 1], s->atmp[ilev - 1], nullptr, 1.0, 0, false));
+  }
   SGCALL(amr_vcycle(s, phi, rhs, ilev - 1, l_max, sp, iter));
-  SGCALL(vec_launch<0>(s->acorr[ilev - 1], phi[ilev - 1], s->acorr[ilev - 1], 1.0, -1.0, false));
-  // AMRProlongS_2 with the operator's scratch standing in for m_resC
-  SGCALL(amr_prolong_impl(op, phi[ilev], s->acorr[ilev - 1], opc, 1));
-  return sg_op_relaxNF(op, phi[ilev], phi[ilev - 1], s->aresid[ilev], sp->post, iter, ilev, 0);
+  // AMRProlongS_2 of phi[ilev-1] - saved, with the operator's scratch standing in for m_resC
+  SGCALL(amr_prolong_impl(op, phi[ilev], phi[ilev - 1], opc, 1, s->asave[ilev]));
+  return sg_op_relaxNF(op, phi[ilev], phi[ilev - 1], rl, sp->post, iter, ilev, 0);
 }
 static int vcycle(sg_solver* s, sg_field* const* phi, sg_field* const* rhs, int l_max, const sg_solver_params* sp, int iter) {
   if (l_max == 0) {
@@ -2181,8 +2227,7 @@ static int vcycle(sg_solver* s, sg_field* const* phi, sg_field* const* rhs, int 
     s->coefs_averaged = false;
     return r;
   }
-  SGCALL(vec_launch<3>(s->aresid[l_max], rhs[l_max], nullptr, 0, 0, false)); // residual[lmax] = rhs[lmax]
-  return amr_vcycle(s, phi, rhs, l_max, l_max, sp, iter);
+  return amr_vcycle(s, phi, rhs, l_max, l_max, sp, iter); // residual[lmax] = rhs[lmax]: aliased, not copied
 }
 // computeAMRResidual: max over levels of the max-norm of the composite residual (covered cells zeroed), left in
 // d_scalar[slot] on all ranks
@@ -2195,6 +2240,21 @@ static int residual_norm(sg_solver* s, sg_field* const* phi, sg_field* const* rh
   unsigned long long* nb = reinterpret_cast<unsigned long long*>(c->d_scalar) + slot;
   CK(cudaMemsetAsync(nb, 0, sizeof(double), c->stream));
   for (int l = l_max; l >= 0; l--) {
+    sg_op* opl = s->aops[l];
+    if (l == l_max && c->tune[9] != 1) {
+      // finest level: nothing to reflux or zero, the max-norm rides on the residual sweep
+      if (l > 0) SGCALL(cf_interp_impl(opl, phi[l], phi[l - 1]));
+      SGCALL(apply_impl(opl, s->aresid[l], phi[l], rhs[l], 0, 2, slot));
+      continue;
+    }
+    if (l == 0 && opl->lay->fast && c->tune[9] != 1) {
+      // base level under a finer one: norm-only sweep over the cells away from the finer level, register cells by the sparse kernel,
+      // covered cells count as zero
+      SGCALL(fine_link_build(opl, s->aops[1]->lay));
+      if (opl->lay->has_local) SGCALL(apply_impl(opl, nullptr, phi[0], rhs[0], 0, 6, slot, 1, opl->flink->d_special));
+      SGCALL(reflux_impl(opl, phi[1], phi[0], nullptr, s->aops[1], 2, rhs[0], slot));
+      continue;
+    }
     SGCALL(amr_residual_level(s, phi, rhs, l, l_max));
     if (l < l_max) SGCALL(zero_covered_impl(s->aops[l], s->aresid[l], s->aops[l + 1]->lay));
     // max|.| accumulates into the same slot across levels (atomicMax on the bit pattern)
@@ -2224,7 +2284,7 @@ static int run_cycle(sg_solver* s, sg_field* const* phi, sg_field* const* rhs, i
   // level and depth: a public relax with an odd sweep count on ANOTHER field of the same layout hands that field the scratch the
   // graph would still write to.
   std::vector<long long> key = {l_max, sp->pre, sp->post, sp->bottom, c->relax_mode, (long long)(size_t)c->stream};
-  for (int k = 0; k < 8; k++) key.push_back(c->tune[k]);
+  for (int k = 0; k < 16; k++) key.push_back(c->tune[k]);
   auto scratch_of = [](const sg_layout* L) { return (long long)(size_t)((!L->ws.empty() && L->ws[0]) ? L->ws[0]->base : nullptr); };
   for (int l = 0; l <= l_max; l++) { key.push_back((long long)(size_t)phi[l]->base); key.push_back((long long)(size_t)rhs[l]->base); }
   for (sg_op* op : s->aops) {

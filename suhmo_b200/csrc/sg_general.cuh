@@ -126,19 +126,38 @@ __device__ __forceinline__ double bc_on_the_fly(const OpArgsG& a, int side, doub
   return bc_ghost_value(a.bc_kind[side], pc, a.bcval[side], sdx);
 }
 
-__global__ void __launch_bounds__(256) k_gsrb_patch(const double* __restrict__ pin, double* __restrict__ pout, const double* __restrict__ rhsb,
-                                                    const PatchG* __restrict__ tab, const GRec* __restrict__ recs,
-                                                    const int* __restrict__ rec_start, OpArgsG a) {
+// Work distribution: a thread owns cells t = tid, tid + 256, ... of the flattened list of one colour's cells (or of the patch's
+// cells in the copy phases); (row, column) come from a float reciprocal (exact for these sizes, see gp_div) instead of an integer
+// division.  The colour passes run in batches of GP_U cells per thread: all global loads of a batch (9 per cell) are issued
+// before the first is used, so a thread keeps ~36 loads in flight instead of one cell's worth.  USE_MASK = 0: the level's ice
+// mask has no negative entry (scanned when the operator is built), the array is not read.
+// floor(t / d) for 0 <= t < 2^16, 1 <= d < 2^8: (t + 0.5) / d is at least 0.5/d away from an integer, the float error is < 1e-3 of that
+__device__ __forceinline__ int gp_div(int t, float rd) { return __float2int_rz(((float)t + 0.5f) * rd); }
+
+template <int USE_MASK, int GP_U, int MINB>
+__global__ void __launch_bounds__(256, MINB) k_gsrb_patch(const double* __restrict__ pin, double* __restrict__ pout, const double* __restrict__ rhsb,
+                                                       const PatchG* __restrict__ tab, const GRec* __restrict__ recs,
+                                                       const int* __restrict__ rec_start, OpArgsG a) {
   extern __shared__ double gp_tile[];
   const PatchG g = tab[blockIdx.x];
   const int nx = g.nx, ny = g.ny, W = nx + 2, tid = threadIdx.x;
   const ptrdiff_t P = g.pitch;
   const int gpar = (g.glo0 + g.glo1) & 1;
+  const float rnx = 1.0f / (float)nx;
 #define TILE(i, j) gp_tile[((j) + 1) * W + (i) + 1]
   // ---- interior of phi_in
-  for (int t = tid; t < nx * ny; t += 256) {
-    const int j = t / nx, i = t - j * nx;
-    TILE(i, j) = pin[g.off + j * P + i];
+  for (int t0 = tid; t0 < nx * ny; t0 += 256 * 8) {
+    double v[8];
+#pragma unroll
+    for (int u = 0; u < 8; u++) {
+      const int t = t0 + 256 * u;
+      if (t < nx * ny) { const int j = gp_div(t, rnx); v[u] = pin[g.off + j * P + (t - j * nx)]; }
+    }
+#pragma unroll
+    for (int u = 0; u < 8; u++) {
+      const int t = t0 + 256 * u;
+      if (t < nx * ny) { const int j = gp_div(t, rnx); TILE(t - j * nx, j) = v[u]; }
+    }
   }
   // ---- ghost ring: sides 0 x-lo, 1 x-hi (ny cells each), 2 y-lo, 3 y-hi (nx cells each)
   const GRec* R = recs + rec_start[blockIdx.x];
@@ -164,8 +183,8 @@ __global__ void __launch_bounds__(256) k_gsrb_patch(const double* __restrict__ p
         else if (side == 2) { pn = pin_in; ps = nbv[0]; pw = nbv[1]; pe = nbv[2]; }
         else { ps = pin_in; pn = nbv[0]; pw = nbv[1]; pe = nbv[2]; }
         const ptrdiff_t o = r.own;
-        v = gsrb_point(a, v, pw, pe, ps, pn, a.bX[o], a.bX[o + 1], a.bY[o], a.bY[o + r.own_pitch], a.has_a ? a.aC[o] : 0.0, a.B[o], a.mask[o],
-                       a.Pi[o], a.zb[o], rhsb[o]);
+        v = gsrb_point(a, v, pw, pe, ps, pn, a.bX[o], a.bX[o + 1], a.bY[o], a.bY[o + r.own_pitch], a.has_a ? a.aC[o] : 0.0, a.B[o],
+                       USE_MASK ? a.mask[o] : 1.0, a.Pi[o], a.zb[o], rhsb[o]);
       }
     } else {
       v = pin[mine];
@@ -179,26 +198,45 @@ __global__ void __launch_bounds__(256) k_gsrb_patch(const double* __restrict__ p
   }
   __syncthreads();
   // ---- red pass, then black pass, in place in shared memory
-  const int half = (nx + 1) >> 1;
+  const int half = (nx + 1) >> 1, ncol = half * ny;
+  const float rhalf = 1.0f / (float)half;
   for (int pass = 0; pass < 2; pass++) {
-    for (int t = tid; t < half * ny; t += 256) {
-      const int j = t / half;
-      const int i = 2 * (t - j * half) + ((gpar + j + pass) & 1);
-      if (i >= nx) continue;
-      const ptrdiff_t o = g.off + j * P + i;
-      const double pc = TILE(i, j);
-      double pw = TILE(i - 1, j), pe = TILE(i + 1, j), ps = TILE(i, j - 1), pn = TILE(i, j + 1);
-      if (i == 0 && g.phys[0]) pw = bc_on_the_fly(a, 0, pc);
-      if (i == nx - 1 && g.phys[1]) pe = bc_on_the_fly(a, 1, pc);
-      if (j == 0 && g.phys[2]) ps = bc_on_the_fly(a, 2, pc);
-      if (j == ny - 1 && g.phys[3]) pn = bc_on_the_fly(a, 3, pc);
-      TILE(i, j) = gsrb_point(a, pc, pw, pe, ps, pn, a.bX[o], a.bX[o + 1], a.bY[o], a.bY[o + P], a.has_a ? a.aC[o] : 0.0, a.B[o], a.mask[o], a.Pi[o],
-                              a.zb[o], rhsb[o]);
+    for (int t0 = tid; t0 < ncol; t0 += 256 * GP_U) {
+      double bw[GP_U], be[GP_U], bs[GP_U], bn[GP_U], Bc[GP_U], mk[GP_U], Pic[GP_U], zbc[GP_U], rh[GP_U], ac[GP_U];
+      int ci[GP_U], cj[GP_U];
+#pragma unroll
+      for (int u = 0; u < GP_U; u++) {
+        const int t = t0 + 256 * u;
+        ci[u] = -1; cj[u] = 0;
+        if (t < ncol) {
+          const int j = gp_div(t, rhalf);
+          const int i = 2 * (t - j * half) + ((gpar + j + pass) & 1);
+          if (i < nx) {
+            ci[u] = i; cj[u] = j;
+            const ptrdiff_t o = g.off + j * P + i;
+            bw[u] = a.bX[o]; be[u] = a.bX[o + 1]; bs[u] = a.bY[o]; bn[u] = a.bY[o + P];
+            Bc[u] = a.B[o]; mk[u] = USE_MASK ? a.mask[o] : 1.0; Pic[u] = a.Pi[o]; zbc[u] = a.zb[o]; rh[u] = rhsb[o];
+            ac[u] = a.has_a ? a.aC[o] : 0.0;
+          }
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < GP_U; u++) {
+        const int i = ci[u], j = cj[u];
+        if (i < 0) continue;
+        const double pc = TILE(i, j);
+        double pw = TILE(i - 1, j), pe = TILE(i + 1, j), ps = TILE(i, j - 1), pn = TILE(i, j + 1);
+        if (i == 0 && g.phys[0]) pw = bc_on_the_fly(a, 0, pc);
+        if (i == nx - 1 && g.phys[1]) pe = bc_on_the_fly(a, 1, pc);
+        if (j == 0 && g.phys[2]) ps = bc_on_the_fly(a, 2, pc);
+        if (j == ny - 1 && g.phys[3]) pn = bc_on_the_fly(a, 3, pc);
+        TILE(i, j) = gsrb_point(a, pc, pw, pe, ps, pn, bw[u], be[u], bs[u], bn[u], ac[u], Bc[u], mk[u], Pic[u], zbc[u], rh[u]);
+      }
     }
     __syncthreads();
   }
   for (int t = tid; t < nx * ny; t += 256) {
-    const int j = t / nx, i = t - j * nx;
+    const int j = gp_div(t, rnx), i = t - j * nx;
     pout[g.off + j * P + i] = TILE(i, j);
   }
 #undef TILE
@@ -580,6 +618,68 @@ __global__ void __launch_bounds__(128) k_reflux(double* __restrict__ resb, const
   resb[it.res] = resb[it.res] + (-scale2) * reg;
 }
 
+struct ZeroSeg { long long off; int nx, ny, pitch, pad; };
+// k_reflux for a one-patch coarse level whose residual was produced by k_apply<1|5|6> instead of AMROperator + axby: L(phi) is
+// evaluated again at the register cell (same operands, same bits), refluxed, and the cell is finished the way the fused sweep
+// finished the others.  MODE 0: res = rhs - Lc; 1: res = (rhs - Lc) + L; 2: max|rhs - Lc| into *norm_bits.  off0 = offset of cell
+// (0,0) of the patch from the component base (the register items address cells from the component base).
+template <int MODE>
+__global__ void __launch_bounds__(128) k_reflux_fused(double* __restrict__ resb, const double* __restrict__ phicb, const double* __restrict__ rhsb,
+                                                      OpArgs a, long long off0, const double* __restrict__ regb, long long reg_stride,
+                                                      const RefluxItem* __restrict__ items, int n, double beta, double dxc0, double dxc1,
+                                                      unsigned long long* norm_bits) {
+  int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n) return;
+  const RefluxItem& it = items[t];
+  double scale2 = 1.0;
+  scale2 *= dxc0; scale2 *= dxc1;
+  scale2 = 1.0 / scale2;
+  double reg = 0.0;
+  for (int k = 0; k < 4; k++) { // incrementCoarse
+    const RefluxFace& f = it.f[k];
+    if (!f.valid) continue;
+    const int dir = k >> 1, side = k & 1;
+    const double dxn = dir == 0 ? dxc0 : dxc1, scale = dir == 0 ? dxc1 : dxc0;
+    const double* bc = (dir == 0 ? a.bX : a.bY) - off0;
+    double gradphi = (phicb[f.c_hi] - phicb[f.c_lo]) * (beta * 1 / dxn);
+    double F = -bc[f.c_b] * gradphi;
+    double sgn = side ? 1.0 : -1.0;
+    reg = reg + (-sgn * scale) * F;
+  }
+  for (int k = 0; k < 4; k++) // the fine sums
+    if (it.f[k].valid) reg = reg + regb[(long long)k * reg_stride + it.res];
+  const size_t o = (size_t)(it.res - off0);
+  const double lof = lof_at(a, phicb + off0, o);
+  const double lofc = lof + (-scale2) * reg;
+  const double r = rhsb[it.res] - (lofc);
+  if (MODE == 0) resb[it.res] = r;
+  else if (MODE == 1) resb[it.res] = r + 1.0 * lof;
+  else atomicMax(norm_bits, (unsigned long long)__double_as_longlong(fabs(r)));
+}
+// res += L(phi) on rectangles of a one-patch level (the cells under the finer level, after the restricted fine residual landed there)
+__global__ void k_add_lof_segs(double* __restrict__ resb, const double* __restrict__ phicb, OpArgs a, long long off0, const ZeroSeg* __restrict__ segs,
+                               int nseg) {
+  int s = blockIdx.x;
+  if (s >= nseg) return;
+  ZeroSeg z = segs[s];
+  for (int t = blockIdx.y * blockDim.x + threadIdx.x; t < z.nx * z.ny; t += gridDim.y * blockDim.x) {
+    int i = t % z.nx, j = t / z.nx;
+    const long long c = z.off + (long long)j * z.pitch + i;
+    resb[c] = resb[c] + 1.0 * lof_at(a, phicb + off0, (size_t)(c - off0));
+  }
+}
+// byte map of the cells the sparse kernels own: covered rectangles and flux-register cells
+__global__ void k_mark_segs(unsigned char* __restrict__ m, const ZeroSeg* __restrict__ segs, int nseg) {
+  int s = blockIdx.x;
+  if (s >= nseg) return;
+  ZeroSeg z = segs[s];
+  for (int t = blockIdx.y * blockDim.x + threadIdx.x; t < z.nx * z.ny; t += gridDim.y * blockDim.x) m[z.off + (long long)(t / z.nx) * z.pitch + t % z.nx] = 1;
+}
+__global__ void k_mark_items(unsigned char* __restrict__ m, const RefluxItem* __restrict__ items, int n) {
+  int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t < n) m[items[t].res] = 1;
+}
+
 // FORT_AVERAGE of AMRRestrictS: coarse (coarsened-fine scratch patch k) = sum of the 2x2 fine cells (i fastest) * 1/4
 __global__ void __launch_bounds__(256) k_amr_average(double* __restrict__ cb, const PatchG* __restrict__ ctab, const double* __restrict__ fb,
                                                      const PatchG* __restrict__ ftab) {
@@ -617,7 +717,6 @@ __global__ void __launch_bounds__(256) k_amr_prolong(double* __restrict__ fb, co
 }
 
 // zeroCovered: rectangles (in patch-local offsets) of a coarse field that lie under the finer level
-struct ZeroSeg { long long off; int nx, ny, pitch, pad; };
 __global__ void k_zero_segs(double* __restrict__ base, const ZeroSeg* __restrict__ segs, int nseg) {
   int s = blockIdx.x;
   if (s >= nseg) return;

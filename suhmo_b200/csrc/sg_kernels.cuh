@@ -849,9 +849,25 @@ __device__ __forceinline__ void block_max_to_global(double v, unsigned long long
   }
 }
 
+// L(phi) at cell offset o of a one-patch level (ghost cells of phi in memory)
+__device__ __forceinline__ double lof_at(const OpArgs& a, const double* __restrict__ phi, size_t o) {
+  const ptrdiff_t P = a.g.pitch;
+  double pc = phi[o], pw = phi[o - 1], pe = phi[o + 1], ps = phi[(ptrdiff_t)o - P], pn = phi[o + P];
+  double bw = a.bX[o], be = a.bX[o + 1], bs = a.bY[o], bn = a.bY[o + P];
+  double ac = a.has_a ? a.aC[o] : 0.0;
+  double nl, dnl;
+  nl_terms(a.prm, pc, a.B[o], a.use_mask ? a.mask[o] : 1.0, a.Pi[o], a.zb[o], nl, dnl);
+  return lofphi_cell(a.alpha, ac, a.beta, pc, pw, pe, ps, pn, bw, be, bs, bn, a.dxi0, a.dxi1, nl);
+}
+// MODE 0 out = L(phi); 1 out = rhs - L(phi); 2 as 1 + max|out|; 3 max|rhs - L(phi)| only; 4 out += L(phi);
+// 5 out = (rhs - L(phi)) + L(phi): the composite residual followed by the FAS tau term AMROperatorNF(phi), both of which evaluate the
+//   same L(phi) on cells away from the finer level (the few cells next to or under it are redone by k_reflux_fused / k_add_lof_segs);
+// 6 max|rhs - L(phi)| over the cells whose byte in `special` is 0 (cells under or next to the finer level are the sparse kernels'), nothing
+//   stored, accumulated into *norm_bits
 template <int MODE, int ROWS>
 __global__ void __launch_bounds__(256) k_apply(double* __restrict__ out, const double* __restrict__ phi,
-                                               const double* __restrict__ rhs, OpArgs a, unsigned long long* norm_bits) {
+                                               const double* __restrict__ rhs, OpArgs a, unsigned long long* norm_bits,
+                                               const unsigned char* __restrict__ special = nullptr) {
   // a block covers blockDim.x columns x blockDim.y*ROWS rows (ROWS > 1: fewer blocks and, for the norm modes, fewer
   // same-address atomics)
   int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -871,14 +887,16 @@ __global__ void __launch_bounds__(256) k_apply(double* __restrict__ out, const d
       nl_terms(a.prm, pc, a.B[o], a.use_mask ? a.mask[o] : 1.0, a.Pi[o], a.zb[o], nl, dnl);
       double lof = lofphi_cell(a.alpha, ac, a.beta, pc, pw, pe, ps, pn, bw, be, bs, bn, a.dxi0, a.dxi1, nl);
       if (MODE == 4) { out[o] = out[o] + 1.0 * lof; }
+      else if (MODE == 5) { double t = rhs[o] - (lof); out[o] = t + 1.0 * lof; }
       else {
         r = MODE == 0 ? lof : rhs[o] - (lof);
-        if (MODE != 3) out[o] = r;
+        if (MODE != 3 && MODE != 6) out[o] = r;
+        if (MODE == 6 && special[o]) r = 0.0;
       }
     }
     rmax = nanmax(rmax, fabs(r));
   }
-  if (MODE == 2 || MODE == 3) block_max_to_global(rmax, norm_bits);
+  if (MODE == 2 || MODE == 3 || MODE == 6) block_max_to_global(rmax, norm_bits);
 }
 
 // restrictResidual + restrictR fused (src/VCAMRNonLinearPoissonOp.cpp:347-460; RESTRICTRESVCNL2D / RESTRICTVCNL,

@@ -109,7 +109,7 @@ def _hash_uniform(i, j, seed):
     return (h >> np.uint64(11)).astype(np.float64) * (2.0 / float(1 << 53)) - 1.0
 
 
-def fields(cfg, ng=1, seed=12345, perturb=True, lo=(0, 0), shape=None, level_ratio=1, moulin_cutoff=None, rhs_only=False):
+def fields(cfg, ng=1, seed=12345, perturb=True, lo=(0, 0), shape=None, level_ratio=1, moulin_cutoff=None, rhs_only=False, periodic_ghosts=False):
     """IBC fields on index window [lo, lo+shape) (default: the whole level-0 domain), with ng ghosts.
 
     level_ratio refines dx (AMR level = base dx / level_ratio).  Returns dict of [j, i] arrays:
@@ -117,12 +117,20 @@ def fields(cfg, ng=1, seed=12345, perturb=True, lo=(0, 0), shape=None, level_rat
     moulin_cutoff (in units of a moulin's sigma): evaluate each Gaussian moulin source only where it is not negligible; with
     cutoff >= 12 the omitted terms are below one ulp of the background recharge, i.e. the sum is unchanged.
     rhs_only: only the right-hand side (same bits as the full call), for geometries without an ice mask.
+    periodic_ghosts: in periodic directions, cells outside the domain take the values of their periodic images (indices wrapped
+    before the formulas are evaluated) instead of the formulas' continuation -- the state LevelData::exchange leaves behind.
     """
     nx, ny = shape if shape is not None else (cfg.nx * level_ratio, cfg.ny * level_ratio)
     dx, dy = cfg.dx[0] / level_ratio, cfg.dx[1] / level_ratio
     with np.errstate(over="ignore"):
         ii = np.arange(lo[0] - ng, lo[0] + nx + ng, dtype=np.int64)
         jj = np.arange(lo[1] - ng, lo[1] + ny + ng, dtype=np.int64)
+        i_org, j_org = int(ii[0]), int(jj[0])
+        if periodic_ghosts:
+            if cfg.periodic[0]:
+                ii = np.mod(ii, cfg.nx * level_ratio)
+            if cfg.periodic[1]:
+                jj = np.mod(jj, cfg.ny * level_ratio)
         I, J = np.meshgrid(ii, jj)
         x, y = (I + 0.5) * dx, (J + 0.5) * dy
         mask = np.ones_like(x)
@@ -187,8 +195,8 @@ def fields(cfg, ng=1, seed=12345, perturb=True, lo=(0, 0), shape=None, level_rat
                 rhs += flux / (2.0 * np.pi * sig * sig) * np.exp(-0.5 * ((x - mx) ** 2 + (y - my) ** 2) / (sig * sig))
                 continue
             w = moulin_cutoff * sig
-            i0 = max(0, int(math.floor((mx - w) / dx - 0.5)) - int(ii[0])); i1 = min(len(ii), int(math.ceil((mx + w) / dx - 0.5)) + 1 - int(ii[0]))
-            j0 = max(0, int(math.floor((my - w) / dy - 0.5)) - int(jj[0])); j1 = min(len(jj), int(math.ceil((my + w) / dy - 0.5)) + 1 - int(jj[0]))
+            i0 = max(0, int(math.floor((mx - w) / dx - 0.5)) - i_org); i1 = min(len(ii), int(math.ceil((mx + w) / dx - 0.5)) + 1 - i_org)
+            j0 = max(0, int(math.floor((my - w) / dy - 0.5)) - j_org); j1 = min(len(jj), int(math.ceil((my + w) / dy - 0.5)) + 1 - j_org)
             if i1 <= i0 or j1 <= j0:
                 continue
             xs, ys = x[j0:j1, i0:i1], y[j0:j1, i0:i1]
@@ -200,7 +208,7 @@ def fields(cfg, ng=1, seed=12345, perturb=True, lo=(0, 0), shape=None, level_rat
     return dict(head=head, B=B, Pi=Pi, zb=zb, mask=mask, rhs=np.ascontiguousarray(rhs[core]))
 
 
-def box_fields(cfg, boxes, level_ratio=1, ng=1, seed=12345, bin_cells=512, moulin_cutoff=12.0, rhs_only=False):
+def box_fields(cfg, boxes, level_ratio=1, ng=1, seed=12345, bin_cells=512, moulin_cutoff=12.0, rhs_only=False, periodic_ghosts=False):
     """fields() for a list of boxes of one AMR level without ever forming the level's global arrays: boxes are grouped by the
     bin (bin_cells x bin_cells fine cells) their low corner falls into, the fields are evaluated once on each group's bounding
     window and cut into the boxes' FArrayBoxes.  Yields (box index, dict name -> [j, i] array with ng ghosts; rhs without)."""
@@ -213,7 +221,7 @@ def box_fields(cfg, boxes, level_ratio=1, ng=1, seed=12345, bin_cells=512, mouli
         sub = boxes[ids]
         x0, y0, x1, y1 = int(sub[:, 0].min()), int(sub[:, 1].min()), int(sub[:, 2].max()), int(sub[:, 3].max())
         g = fields(cfg, ng=ng, seed=seed, lo=(x0, y0), shape=(x1 - x0 + 1, y1 - y0 + 1), level_ratio=level_ratio, moulin_cutoff=moulin_cutoff,
-                   rhs_only=rhs_only)
+                   rhs_only=rhs_only, periodic_ghosts=periodic_ghosts)
         for b in ids:
             bx = boxes[b]
             i0, j0 = int(bx[0]) - x0, int(bx[1]) - y0

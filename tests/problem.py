@@ -147,7 +147,7 @@ class AmrOracleSide:
     group by box group (syn.box_fields) instead of on the level's whole index space -- same bits, and the only way at sizes where
     a global fine-level array would not fit."""
 
-    def __init__(self, cfg, level_boxes, seed=12345, bc_vals=None, prm_over=None, boxwise=False):
+    def __init__(self, cfg, level_boxes, seed=12345, bc_vals=None, prm_over=None, boxwise=False, periodic_ghosts=False):
         self.cfg, self.level_boxes = cfg, [np.asarray(b, dtype=np.int32) for b in level_boxes]
         self.nlev = len(level_boxes)
         self.layouts, self.F, self.dx = [], [], []
@@ -158,7 +158,7 @@ class AmrOracleSide:
             F = {k: ob.Field(lay, 1, 1) for k in ("head", "B", "Pi", "zb", "mask")}
             F["rhs"] = ob.Field(lay, 1, 0)
             if boxwise:
-                for b, f in syn.box_fields(cfg, boxes, level_ratio=r, ng=1, seed=seed):
+                for b, f in syn.box_fields(cfg, boxes, level_ratio=r, ng=1, seed=seed, periodic_ghosts=periodic_ghosts):
                     for k in ("head", "B", "Pi", "zb", "mask", "rhs"):
                         F[k].fab(b)[0][0][...] = f[k]
             else:

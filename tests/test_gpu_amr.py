@@ -210,3 +210,31 @@ def test_against_golden_fixture_three_levels(gpu_ctx):
     assert np.array_equal(ghist, z["resnorm"])
     for l in range(3):
         assert np.array_equal(np.nan_to_num(gpu.F[l]["head"].get_global(), nan=0.0), z[f"head3_L{l}"]), f"level {l}"
+
+
+@pytest.mark.parametrize("hier,nlev", [("C5", 3), ("C4", 2), ("C5_256", 3)])
+def test_composite_sweeps_fused_vs_reference_flow(gpu_ctx, hier, nlev):
+    """The V-cycle driver's shortcuts on the base level under a finer one -- (rhs - L phi) + L phi in one sweep with the cells next to /
+    under the finer level redone by sparse kernels, norm-only residual sweeps, the FAS reference state kept on the coarsened-fine
+    layout -- against the reference's own sequence (tune key 9 = 1: AMROperator, reflux, axby, AMROperatorNF, incr, whole-level
+    axby for the correction).  Both must reproduce the oracle bit for bit, residual history included."""
+    cfg, orc, gpu = make(gpu_ctx, nlev, hier)
+    ncyc = 3
+    sp = ob.make_solver_params(bottom=10, fixed_cycles=ncyc)
+    it, ohist = orc.solver().solve(orc.fields("head"), orc.fields("rhs"), nlev - 1, sp)
+    keep = {k: [f.download() for f in gpu.fields(k)] for k in ("head", "bX", "bY")}   # what a solve changes
+    for key9 in (0, 1):
+        for k, fabs in keep.items():
+            for l, f in enumerate(gpu.fields(k)):
+                f.upload(fabs[l])
+        gpu_ctx.set_tuning(9, key9)
+        try:
+            mg = gpu.amr.AMRFASMultiGrid().define(gpu.factory, nlev)
+            mg.setSolverParameters(4, 4, 10, 1, 100, 1e-10, 1e-4, 1e-7)
+            git, ghist, stats = mg.solve(gpu.fields("head"), gpu.fields("rhs"), fixed_cycles=ncyc)
+        finally:
+            gpu_ctx.set_tuning(9, 0)
+        assert np.array_equal(ghist, ohist), (key9, ghist, ohist)
+        for l in range(nlev):
+            same(gpu.F[l]["head"], orc.F[l]["head"], f"head L{l} (tune 9 = {key9})")
+        mg.destroy()

@@ -1,12 +1,12 @@
 """The bench workload: BASELINE.json configs[4], "AMR_multiMoulins 3-level AMR scaled to a synthetic 8192^2 base grid".
 
 One TILE = the AMR_multiMoulins problem (exec/AMR_multiMoulins/run_C_3lev/input.hydro: MountainIBC-like geometry, 63 moulins,
-y-periodic) on a size x size base grid of 64^2 boxes, with two refined levels built from tags exactly as the input file asks
+Dirichlet / Neumann sides) on a size x size base grid of 64^2 boxes, with two refined levels built from tags exactly as the input file asks
 (fill_ratio 0.5, block_factor 2, nestingRadius 4, max_box_size 64, tags_grow 4).
 
-  weak scaling   : N tiles stacked in y, one per GPU.  The tiles are bit-identical and the stack is y-periodic, so the global
-                   problem is the periodic replication of the one-tile problem: its residual-norm history at any N must equal
-                   the N = 1 history bit for bit (a full-size parity property the bench line carries).
+  weak scaling   : N tiles stacked in y, one per GPU, every tile built from the same tile-local formulas (so every GPU has the same
+                   grids and the same amount of work); the stack is one problem with the physical boundary conditions of the input
+                   file on its outer sides (the configuration is not periodic) and ordinary box-to-box coupling between tiles.
   strong scaling : one tile, base level cut into N y-strips, refined boxes dealt out cluster by cluster (connected groups of
                    boxes stay on one GPU; clusters are balanced by cell count) -- Chombo's LoadBalance with the constraint that
                    same-level neighbours share a rank.
@@ -193,7 +193,7 @@ class Problem:
         if len(ids) == 0:
             return out
         local = self.to_tile(l, self.levels[l][ids])
-        for b, f in syn.box_fields(self.tile_cfg, local, level_ratio=2 ** l, ng=1):
+        for b, f in syn.box_fields(self.tile_cfg, local, level_ratio=2 ** l, ng=1, periodic_ghosts=True):
             for k in names:
                 out[k][ids[b]] = f[k]
         return out
