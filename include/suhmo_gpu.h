@@ -328,6 +328,33 @@ int sg_rhs_gap(const sg_picard_params* q, sg_field* RHS, const sg_field* Pi, con
 /* explicit gap-height update newB = RHS*dt + oldB (src/AmrHydro.cpp:3394-3408) */
 int sg_gap_euler(sg_field* newB, const sg_field* oldB, const sg_field* RHS, double dt);
 
+/* ---- multi-level pieces of the Picard body and of regridding.  `op` is the FINE level's operator (from
+   sg_factory_AMRnewOp on a level > 0: it owns the coarsened-fine scratch and the copy plans to the coarser level). ---- */
+/* PiecewiseLinearFillPatch(...).fillInterp(fine, coarse, coarse, coef, 0, 0, ncomp) with one ghost cell (absent Chombo; call sites
+   src/AmrHydro.cpp:2373-2380, 2499-2507, 2713-2721, 2754-2762, 3010-3018, 3148-3156, 4200-4207): every ghost cell of the fine boxes
+   (corners included) that lies inside the domain and in no fine box = coarse value + van Leer-limited slopes.  Restated from
+   recollection of public Chombo 3.2: UNPINNED. */
+/* aCoeff_bCoeff (src/AmrHydro.cpp:1782-1812): bCoef of one face direction = COMPUTEBCOEFF(B_ec, Re_ec, iceMask_ec) (src/AmrHydroF.ChF:199-231) */
+int sg_compute_bcoeff(const sg_params* p, const sg_field* Bec, const sg_field* Reec, const sg_field* IMec, sg_field* bC);
+int sg_op_pwlFillPatch(sg_op* op, sg_field* fine, const sg_field* coarse);
+/* FineInterp(...).interpToFine(fine, coarse) with m_boundary_limit_type = 3 (absent Chombo; src/AmrHydro.cpp:4190-4198): every valid
+   fine cell = coarse value + multi-dimensionally limited slopes.  UNPINNED like the above.  SG_ERR_UNSUPPORTED when the fine level
+   is not nested in the coarse level with one coarse cell to spare. */
+int sg_op_fineInterp(sg_op* op, sg_field* fine, const sg_field* coarse);
+/* CoarseAverage(fineGrids, 1, 2).averageToCoarse(coarse, fine) (src/AmrHydro.cpp:2822-2823, 3139-3140, 3593-3594) */
+int sg_op_averageToCoarse(sg_op* op, sg_field* coarse, const sg_field* fine);
+/* destructiveRegrid (src/AmrHydro.cpp:4176-4223): new_data (on the NEW fine grids, op built on them) = FineInterp(coarse_data), ghost
+   cells by PiecewiseLinearFillPatch, old_data (old grids, may be NULL) copied over where it exists, exchange */
+int sg_regrid_transfer(sg_op* op, sg_field* new_data, const sg_field* old_data, const sg_field* coarse_data);
+/* Calc_moulin_integral (src/AmrHydro.cpp:1867-2019), one level per call, finest level first: integ[m] += sum over this level's valid
+   cells not covered by finer_op's level (NULL on the finest level) of the 3x3 Gauss-Legendre quadrature of moulin m's Gaussian
+   (the reference's truncated weights and nodes) times dx*dy.  pos = x0 y0 x1 y1 ...; collective (the ranks' sums are added). */
+int sg_moulin_integral_level(sg_op* op, sg_op* finer_op, int n_moulins, const double* pos, const double* sigma, double* integ);
+/* Calc_moulin_source_term_distributed (src/AmrHydro.cpp:2022-2069) on the valid cells of one level:
+   src = sum_m quadrature_m * max(1 - runoff sin(2 pi time / 86400), 0) / integ[m] * flux[m]; 0 under the finer level */
+int sg_moulin_source_level(sg_op* op, sg_op* finer_op, sg_field* src, int n_moulins, const double* pos, const double* sigma,
+                           const double* integ, const double* flux, double runoff, double time);
+
 /* ------------------------------------------------------------------ AMR hierarchy generation ------------- */
 /* AmrHydro::tagCellsLevel (src/AmrHydro.cpp:4539-4604): tag where vmin < phi < vmax on the valid cells, grow by tags_grow
    (and per direction up to tags_grow_dir), clip to the domain.  tags_host: one byte per cell of the level's domain, x

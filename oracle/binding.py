@@ -42,7 +42,7 @@ class SolverParams(C.Structure):
 
 def build(force=False):
     so = os.path.join(_HERE, "libsuhmo_oracle.so")
-    src = [os.path.join(_HERE, f) for f in ("suhmo_oracle.c", "suhmo_oracle_r2.inc", "suhmo_oracle.h")]
+    src = [os.path.join(_HERE, f) for f in ("suhmo_oracle.c", "suhmo_oracle_r2.inc", "suhmo_oracle_r3.inc", "suhmo_oracle.h")]
     if force or not os.path.exists(so) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in src):
         subprocess.check_call(["make", "-C", _HERE, "all"], stdout=subprocess.DEVNULL)
     return so
@@ -167,6 +167,13 @@ def lib():
     sig("orc_homogeneous_cf_interp", None, vp, dp, dp)
     sig("orc_op_diagonal_scale", None, vp, vp)
     sig("orc_op_divide_by_identity_coef", None, vp, vp)
+    sig("orc_pwl_fill_patch", None, vp, vp, ci)
+    sig("orc_fine_interp", None, vp, vp, ci)
+    sig("orc_regrid_transfer", None, vp, vp, vp, ci)
+    sig("orc_compute_bcoeff", None, C.POINTER(Params), vp, vp, vp, vp)
+    sig("orc_moulin_nonorm", None, vp, dp, ci, dp, dp)
+    sig("orc_moulin_integral", None, vp, vp, dp, ci, dp)
+    sig("orc_moulin_source", None, vp, vp, ci, dp, dp, cd, cd)
     _LIB = L
     return L
 

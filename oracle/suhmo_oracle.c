@@ -2082,3 +2082,4 @@ int orc_lin_solver_solve(orc_lin_solver* s, orc_field* phi, const orc_field* rhs
 
 /* round-2 additions: remaining operator virtuals, multi-level Picard-body pieces, regrid transfer, Berger-Rigoutsos */
 #include "suhmo_oracle_r2.inc"
+#include "suhmo_oracle_r3.inc"

@@ -223,6 +223,16 @@ void orc_homogeneous_cf_interp(orc_field* phiF, const double dxFine[2], const do
 void orc_op_diagonal_scale(const orc_op* op, orc_field* rhs);
 void orc_op_divide_by_identity_coef(const orc_op* op, orc_field* rhs);
 
+/* multi-level pieces of the Picard body and of regridding (suhmo_oracle_r3.inc): PiecewiseLinearFillPatch::fillInterp,
+   FineInterp::interpToFine (both absent Chombo, restated from recollection: UNPINNED), destructiveRegrid (src/AmrHydro.cpp:4176-4223),
+   Calc_moulin_integral / Calc_moulin_source_term_distributed (src/AmrHydro.cpp:1867-2069) */
+void orc_pwl_fill_patch(orc_field* fine, const orc_field* coarse, int r);
+void orc_fine_interp(orc_field* fine, const orc_field* coarse, int r);
+void orc_regrid_transfer(orc_field* newData, const orc_field* oldData, const orc_field* crseData, int r);
+void orc_compute_bcoeff(const orc_params* p, const orc_field* Bec, const orc_field* Reec, const orc_field* IMec, orc_field* bC);
+void orc_moulin_nonorm(orc_field* ms, const double dx[2], int n, const double* pos, const double* sigma);
+void orc_moulin_integral(orc_field* ms, const orc_layout* fineLay, const double dx[2], int n, double* integ);
+void orc_moulin_source(orc_field* src, const orc_field* ms, int n, const double* integ, const double* flux, double runoff, double time);
 void orc_set_threads(int n);
 
 #ifdef __cplusplus

@@ -435,6 +435,23 @@ class VCAMRNonLinearPoissonOp:
     def homogeneousCFInterp(self, phi):
         check(lib().sg_op_homogeneousCFInterp(self.h, phi.h))
 
+    # -- multi-level pieces of the Picard body / regridding (this operator = the FINE level's) --------------------------------
+    def pwlFillPatch(self, fine, coarse):
+        """PiecewiseLinearFillPatch(...).fillInterp(fine, coarse, coarse, ...) with one ghost cell"""
+        check(lib().sg_op_pwlFillPatch(self.h, fine.h, coarse.h))
+
+    def fineInterp(self, fine, coarse):
+        """FineInterp(...).interpToFine(fine, coarse), m_boundary_limit_type = 3"""
+        check(lib().sg_op_fineInterp(self.h, fine.h, coarse.h))
+
+    def averageToCoarse(self, coarse, fine):
+        """CoarseAverage(fineGrids, 1, 2).averageToCoarse(coarse, fine)"""
+        check(lib().sg_op_averageToCoarse(self.h, coarse.h, fine.h))
+
+    def regridTransfer(self, newData, oldData, crseData):
+        """destructiveRegrid (src/AmrHydro.cpp:4176-4223)"""
+        check(lib().sg_regrid_transfer(self.h, newData.h, None if oldData is None else oldData.h, crseData.h))
+
     def AMRNorm(self, coarResid, fineResid, refRat, ord_):
         out = C.c_double()
         check(lib().sg_op_AMRNorm(self.h, coarResid.h, _h(fineResid), refRat, ord_, C.byref(out)))
@@ -668,3 +685,20 @@ def SolveForGap_nl(ctx, grids, aCoef, bX, bY, refRatio, coarsestDx, gapHeight, R
     check(lib().sg_solve_for_gap(ctx.h, len(grids), ga, _ip(rr), _dp(dx), arr(aCoef), arr(bX), arr(bY), arr(gapHeight), arr(RHS), float(dt),
                                  float(DiffFactor), int(cur_step), _dp(hist), C.byref(stats)))
     return stats.iterations, hist[:stats.iterations + 1], stats
+
+
+def moulin_source_terms(ops, srcs, moulins, runoff=0.0, time=0.0):
+    """Calc_moulin_integral + Calc_moulin_source_term_distributed (src/AmrHydro.cpp:1867-2069) over the levels' operators `ops`
+    (coarsest first) into the cell fields `srcs`.  moulins: [(x, y, flux, sigma), ...].  Returns the per-moulin integrals."""
+    n = len(moulins)
+    pos = np.ascontiguousarray([[m[0], m[1]] for m in moulins], dtype=np.float64).ravel()
+    flux = np.ascontiguousarray([m[2] for m in moulins], dtype=np.float64)
+    sig = np.ascontiguousarray([m[3] for m in moulins], dtype=np.float64)
+    integ = np.zeros(n)
+    for l in range(len(ops) - 1, -1, -1):
+        finer = ops[l + 1].h if l + 1 < len(ops) else None
+        check(lib().sg_moulin_integral_level(ops[l].h, finer, n, _dp(pos), _dp(sig), _dp(integ)))
+    for l in range(len(ops)):
+        finer = ops[l + 1].h if l + 1 < len(ops) else None
+        check(lib().sg_moulin_source_level(ops[l].h, finer, srcs[l].h, n, _dp(pos), _dp(sig), _dp(integ), _dp(flux), float(runoff), float(time)))
+    return integ

@@ -103,6 +103,10 @@ SIGNATURES = {
     "sg_rhs_head": [C.POINTER(PicardParams), vp, vp, vp, vp, vp, vp, vp, vp, vp],
     "sg_rhs_gap": [C.POINTER(PicardParams), vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, cd],
     "sg_gap_euler": [vp, vp, vp, cd],
+    "sg_compute_bcoeff": [C.POINTER(Params), vp, vp, vp, vp],
+    "sg_op_pwlFillPatch": [vp, vp, vp], "sg_op_fineInterp": [vp, vp, vp], "sg_op_averageToCoarse": [vp, vp, vp],
+    "sg_regrid_transfer": [vp, vp, vp, vp],
+    "sg_moulin_integral_level": [vp, vp, ci, dp, dp, dp], "sg_moulin_source_level": [vp, vp, vp, ci, dp, dp, dp, dp, cd, cd],
     "sg_tag_cells_level": [vp, cd, cd, ci, ip, vp, ci],
     "sg_br_regrid": [ip, ci, ip, ci, pvp, cd, ci, ci, ci, ci, ip, ip, ip],
     "sg_solver_define": [vp, pvp, ci], "sg_solver_destroy": [vp], "sg_solver_depth": [vp, ci, ip],

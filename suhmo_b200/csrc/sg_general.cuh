@@ -716,6 +716,90 @@ __global__ void __launch_bounds__(256) k_amr_prolong(double* __restrict__ fb, co
   fb[o] = p;
 }
 
+// PiecewiseLinearFillPatch::fillInterp, one ghost cell, ratio 2 (absent Chombo, restated: see oracle/suhmo_oracle_r3.inc and
+// DESIGN.md): one thread per ghost cell of a fine patch that lies inside the domain and in no fine box.  The coarse data sit in the
+// coarsened-fine scratch (clay box grown by 2).  flags: bit 0/1 coarse neighbour exists at -x/+x, 2/3 at -y/+y, 4/5 the fine cell is
+// the high child in x/y.
+struct PWLItem { long long fo, c0; int cpitch, flags; };
+__device__ __forceinline__ double pwl_slope(double c0, double clo, double chi, int has_lo, int has_hi) {
+  if (has_lo && has_hi) {
+    const double dcenter = 0.5 * (chi - clo), dlo = c0 - clo, dhi = chi - c0;
+    double dlim = 2.0 * fmin(fabs(dlo), fabs(dhi));
+    if (dlo * dhi < 0.0) dlim = 0.0;
+    double sl = fmin(fabs(dcenter), dlim);
+    return dcenter < 0.0 ? -sl : sl;
+  }
+  if (has_hi) return chi - c0;
+  if (has_lo) return c0 - clo;
+  return 0.0;
+}
+__global__ void __launch_bounds__(128) k_pwl_fill(double* __restrict__ fb, const double* __restrict__ cb, const PWLItem* __restrict__ items, int n) {
+  int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n) return;
+  const PWLItem it = items[t];
+  const double c0 = cb[it.c0];
+  double val = c0;
+#pragma unroll
+  for (int dir = 0; dir < 2; dir++) {
+    const ptrdiff_t st = dir == 0 ? 1 : it.cpitch;
+    const int has_lo = (it.flags >> (2 * dir)) & 1, has_hi = (it.flags >> (2 * dir + 1)) & 1;
+    const double clo = has_lo ? cb[it.c0 - st] : 0.0, chi = has_hi ? cb[it.c0 + st] : 0.0;
+    const double slope = pwl_slope(c0, clo, chi, has_lo, has_hi);
+    const int off = (it.flags >> (4 + dir)) & 1;
+    const double coef = -0.5 + (off + 0.5) / 2;
+    val = val + slope * coef;
+  }
+  fb[it.fo] = val;
+}
+// FineInterp::interpToFine, limitTangentialOnly, ratio 2 (absent Chombo, restated): one thread per valid fine cell; the coarse cell
+// under it and its 3x3 neighbourhood come from the coarsened-fine scratch patch; a coarse neighbour exists when it lies inside the
+// (periodically extended) coarse domain -- proper nesting, checked when the link is built, guarantees the coarse level holds it.
+__global__ void __launch_bounds__(256) k_fine_interp(double* __restrict__ fb, const PatchG* __restrict__ ftab, const double* __restrict__ cb,
+                                                     const PatchG* __restrict__ ctab, int dlo0, int dlo1, int dhi0, int dhi1, int per0, int per1) {
+  const PatchG gf = ftab[blockIdx.z], gc = ctab[blockIdx.z];
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  int j = blockIdx.y * blockDim.y + threadIdx.y;
+  if (i >= gf.nx || j >= gf.ny) return;
+  const int ic = i >> 1, jc = j >> 1;
+  const int gi = gc.glo0 + ic, gj = gc.glo1 + jc;
+  const ptrdiff_t oc = gc.off + (ptrdiff_t)jc * gc.pitch + ic;
+  const double c0 = cb[oc];
+  const bool hx0 = per0 || gi - 1 >= dlo0, hx1 = per0 || gi + 1 <= dhi0, hy0 = per1 || gj - 1 >= dlo1, hy1 = per1 || gj + 1 <= dhi1;
+  double slope[2];
+  bool onesided[2];
+  {
+    const double clo = hx0 ? cb[oc - 1] : 0.0, chi = hx1 ? cb[oc + 1] : 0.0;
+    slope[0] = (hx0 && hx1) ? 0.5 * (chi - clo) : hx1 ? chi - c0 : hx0 ? c0 - clo : 0.0;
+    onesided[0] = !(hx0 && hx1) && (hx0 || hx1);
+  }
+  {
+    const double clo = hy0 ? cb[oc - gc.pitch] : 0.0, chi = hy1 ? cb[oc + gc.pitch] : 0.0;
+    slope[1] = (hy0 && hy1) ? 0.5 * (chi - clo) : hy1 ? chi - c0 : hy0 ? c0 - clo : 0.0;
+    onesided[1] = !(hy0 && hy1) && (hy0 || hy1);
+  }
+  double smax = c0, smin = c0;
+#pragma unroll
+  for (int dj = -1; dj <= 1; dj++)
+#pragma unroll
+    for (int di = -1; di <= 1; di++) {
+      const bool ok = (di == 0 || (di < 0 ? hx0 : hx1)) && (dj == 0 || (dj < 0 ? hy0 : hy1));
+      if (!ok) continue;
+      const double sv = cb[oc + (ptrdiff_t)dj * gc.pitch + di];
+      smax = fmax(smax, sv); smin = fmin(smin, sv);
+    }
+  double deltasum = 0.0;
+  for (int dir = 0; dir < 2; dir++) if (!onesided[dir]) deltasum = deltasum + 0.5 * fabs(slope[dir]);
+  if (deltasum > 0.0) {
+    const double etamax = (smax - c0) / deltasum, etamin = (c0 - smin) / deltasum;
+    const double eta = fmax(fmin(fmin(etamin, etamax), 1.0), 0.0);
+    for (int dir = 0; dir < 2; dir++) if (!onesided[dir]) slope[dir] = slope[dir] * eta;
+  }
+  double val = c0;
+  val = val + slope[0] * (-0.5 + ((i & 1) + 0.5) / 2);
+  val = val + slope[1] * (-0.5 + ((j & 1) + 0.5) / 2);
+  fb[gf.off + (ptrdiff_t)j * gf.pitch + i] = val;
+}
+
 // zeroCovered: rectangles (in patch-local offsets) of a coarse field that lie under the finer level
 __global__ void k_zero_segs(double* __restrict__ base, const ZeroSeg* __restrict__ segs, int nseg) {
   int s = blockIdx.x;

@@ -66,6 +66,12 @@ __global__ void __launch_bounds__(256) k_compute_qw(double* __restrict__ Qw, con
   double denom_q = 12.0 * nu * (1.0 + omega * Reec[o]);
   Qw[o] = num_q / denom_q;
 }
+// aCoeff_bCoeff (src/AmrHydro.cpp:1782-1812): COMPUTEBCOEFF (src/AmrHydroF.ChF:199-231) on the face data of one direction
+__global__ void __launch_bounds__(256) k_compute_bcoeff(double* __restrict__ bC, const double* __restrict__ Bec, const double* __restrict__ Reec,
+                                                        const double* __restrict__ IMec, const PatchG* __restrict__ tab, PhysP prm, int ex, int ey) {
+  PK_IDX(ex, ey, 0)
+  bC[o] = bcoeff_face(prm, Bec[o], Reec[o], IMec[o]);
+}
 // COMPUTESCAPROD (src/AmrHydroF.ChF:165-186)
 __global__ void __launch_bounds__(256) k_scaprod(double* __restrict__ p1, double* __restrict__ p2, const double* __restrict__ a,
                                                  const double* __restrict__ b1, const double* __restrict__ b2, const PatchG* __restrict__ tab,
@@ -170,4 +176,86 @@ __global__ void __launch_bounds__(256) k_gap_euler(double* __restrict__ newB, co
                                                    const PatchG* __restrict__ tab, double dt) {
   PK_IDX(0, 0, 0)
   newB[o] = RHS[o] * dt + oldB[o];
+}
+
+// ------------------------------------------------------------------------------------------------
+// moulin recharge (src/AmrHydro.cpp:1867-2069): every moulin is a Gaussian integrated over each cell with the reference's 3x3
+// Gauss-Legendre rule (truncated literal weights/nodes), normalised by its integral over the composite grid.  The reference keeps a
+// field with one component per moulin; here the quadrature is recomputed where it is needed (integral pass, source pass).
+// ------------------------------------------------------------------------------------------------
+#define SG_MAX_MOULINS 128
+struct MoulinTab { int n; double x[SG_MAX_MOULINS], y[SG_MAX_MOULINS], sigma[SG_MAX_MOULINS]; };
+__device__ __forceinline__ double moulin_cell(double xc, double yc, double dx0, double dx1, double mx, double my, double sig) {
+  const double vw[3] = {0.5555555555, 0.8888888888, 0.5555555555};
+  const double lo[3] = {-0.77459666924 / 2.0, 0.0, 0.77459666924 / 2.0};
+  const double prefac = 1.0 / (sig * sqrt(2.0 * 3.14));
+  double MS[9];
+#pragma unroll
+  for (int q = 0; q < 9; q++) {
+    const double ddx = (xc + lo[q % 3]) * dx0 - mx, ddy = (yc + lo[q / 3]) * dx1 - my;
+    const double rad = ddx * ddx + ddy * ddy;
+    MS[q] = prefac * exp(-1.0 / (2.0 * sig * sig) * rad);
+  }
+  return vw[0] * vw[0] * MS[0] + vw[1] * vw[0] * MS[1] + vw[2] * vw[0] * MS[2] + vw[0] * vw[1] * MS[3] + vw[1] * vw[1] * MS[4] +
+         vw[2] * vw[1] * MS[5] + vw[0] * vw[2] * MS[6] + vw[1] * vw[2] * MS[7] + vw[2] * vw[2] * MS[8];
+}
+// a cell farther than this from the moulin contributes exactly 0: exp underflows below -745.2
+__device__ __forceinline__ bool moulin_far(double xc, double yc, double dx0, double dx1, double mx, double my, double sig) {
+  const double ax = fmax(fabs((xc)*dx0 - mx) - dx0, 0.0), ay = fmax(fabs((yc)*dx1 - my) - dx1, 0.0);
+  return (ax * ax + ay * ay) / (2.0 * sig * sig) > 760.0;
+}
+// partial[m * nblocks + block] = sum over the block's valid, uncovered cells of the quadrature of moulin m (times dx*dy)
+__global__ void __launch_bounds__(256) k_moulin_partial(double* __restrict__ partial, const PatchG* __restrict__ tab, const unsigned char* __restrict__ covered,
+                                                        const MoulinTab* __restrict__ mt, double dx0, double dx1) {
+  const PatchG g = tab[blockIdx.z];
+  const int i = blockIdx.x * blockDim.x + threadIdx.x, j = blockIdx.y * blockDim.y + threadIdx.y;
+  const bool in = i < g.nx && j < g.ny && !(covered && covered[g.off + (ptrdiff_t)j * g.pitch + i]);
+  const double xc = g.glo0 + i + 0.5, yc = g.glo1 + j + 0.5;
+  __shared__ double sh[8];
+  const int tid = threadIdx.y * blockDim.x + threadIdx.x, lane = tid & 31, w = tid >> 5;
+  const size_t nblocks = (size_t)gridDim.x * gridDim.y * gridDim.z;
+  const size_t blk = ((size_t)blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x;
+  const int n = mt->n;
+  for (int m = 0; m < n; m++) {
+    double v = 0.0;
+    if (in && !moulin_far(xc, yc, dx0, dx1, mt->x[m], mt->y[m], mt->sigma[m])) v = moulin_cell(xc, yc, dx0, dx1, mt->x[m], mt->y[m], mt->sigma[m]) * dx0 * dx1;
+    for (int o = 16; o > 0; o >>= 1) v = v + __shfl_xor_sync(0xffffffffu, v, o);
+    if (lane == 0) sh[w] = v;
+    __syncthreads();
+    if (tid == 0) {
+      double t = 0.0;
+      for (int k = 0; k < 8; k++) t = t + sh[k];
+      partial[(size_t)m * nblocks + blk] = t;
+    }
+    __syncthreads();
+  }
+}
+__global__ void __launch_bounds__(256) k_moulin_reduce(const double* __restrict__ partial, size_t nblocks, double* __restrict__ out) {
+  __shared__ double sh[256];
+  const double* p = partial + (size_t)blockIdx.x * nblocks;
+  double v = 0.0;
+  for (size_t k = threadIdx.x; k < nblocks; k += 256) v = v + p[k];
+  sh[threadIdx.x] = v;
+  __syncthreads();
+  for (int s = 128; s > 0; s >>= 1) {
+    if (threadIdx.x < s) sh[threadIdx.x] = sh[threadIdx.x] + sh[threadIdx.x + s];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) out[blockIdx.x] = out[blockIdx.x] + sh[0];
+}
+// Calc_moulin_source_term_distributed (:2022-2069) on the valid cells; cells under the finer level get 0 (their quadrature was zeroed)
+__global__ void __launch_bounds__(256) k_moulin_source(double* __restrict__ src, const PatchG* __restrict__ tab, const unsigned char* __restrict__ covered,
+                                                       const MoulinTab* __restrict__ mt, const double* __restrict__ integ, const double* __restrict__ flux,
+                                                       double dx0, double dx1, double tfac) {
+  PK_IDX(0, 0, 0)
+  if (covered && covered[o]) { src[o] = 0.0; return; }
+  const double xc = g.glo0 + i + 0.5, yc = g.glo1 + j + 0.5;
+  double s = 0.0;
+  const int n = mt->n;
+  for (int m = 0; m < n; m++) {
+    double q = 0.0;
+    if (!moulin_far(xc, yc, dx0, dx1, mt->x[m], mt->y[m], mt->sigma[m])) q = moulin_cell(xc, yc, dx0, dx1, mt->x[m], mt->y[m], mt->sigma[m]);
+    s += q * tfac / integ[m] * flux[m];
+  }
+  src[o] = s;
 }
