@@ -452,6 +452,94 @@ __global__ void __launch_bounds__(256) k_re_bcoef_g(double* __restrict__ bXb, do
   }
 }
 
+// UpdateOperator on a one-patch level in ONE pass (WFlx_level, src/AmrHydro.cpp:1415-1539, without a coarser level): cell-centred
+// gradient (NEWMACGRAD + EdgeToCell), its ghost cells (neighbour rank / periodic image: the same formula on phi's depth-2 ghost rows;
+// physical boundary: ExtrapGhostCells, 2 g1 - g2), COMPUTERE over the ghosted box, CellToEdge(Re), CellToEdge(B), setup_iceMask_EC,
+// COMPUTEBCOEFF.  Neither the gradient nor Re is stored: phi, B, mask in, bX, bY out (40 B per cell instead of 24 + 48).  Physical
+// boundary ghost cells of phi are evaluated on the fly from the first interior cell (mixBCValues, inhomogeneous), so the kernel
+// does not depend on a BC pass over the ghost rows.  Same arithmetic as k_gradient_cc_g + k_extrap_ghost_g + k_re_bcoef_g.
+template <int MASKGRAD>
+struct UpdOp {
+  const double* __restrict__ phi; const double* __restrict__ mask;
+  const OpArgs& a;
+  __device__ __forceinline__ bool phys(int s) const { return a.g.kind[s] == SK_PHYS_DIRI || a.g.kind[s] == SK_PHYS_NEUM; }
+  // phi at (i, j), |offset from the valid region| <= 1 in one direction at a time
+  __device__ __forceinline__ double ph(int i, int j) const {
+    const ptrdiff_t P = a.g.pitch;
+    if (i < 0 && phys(0)) return bc_ghost_value(a.g.kind[0], phi[(ptrdiff_t)j * P], a.g.bcval[0], -a.dx0);
+    if (i >= a.g.nx && phys(1)) return bc_ghost_value(a.g.kind[1], phi[(ptrdiff_t)j * P + a.g.nx - 1], a.g.bcval[1], a.dx0);
+    if (j < 0 && phys(2)) return bc_ghost_value(a.g.kind[2], phi[i], a.g.bcval[2], -a.dx1);
+    if (j >= a.g.ny && phys(3)) return bc_ghost_value(a.g.kind[3], phi[(ptrdiff_t)(a.g.ny - 1) * P + i], a.g.bcval[3], a.dx1);
+    return phi[(ptrdiff_t)j * P + i];
+  }
+  // gradient from phi at a cell that is valid or a neighbour-rank / periodic ghost cell
+  __device__ __forceinline__ void grad(int i, int j, double& gx, double& gy) const {
+    const ptrdiff_t P = a.g.pitch, o = (ptrdiff_t)j * P + i;
+    const double fx = 1.0 / a.dx0, fy = 1.0 / a.dx1;
+    const double pc = ph(i, j), pw = ph(i - 1, j), pe = ph(i + 1, j), ps = ph(i, j - 1), pn = ph(i, j + 1);
+    double gxl, gxh, gyl, gyh;
+    if (MASKGRAD) {
+      const double mc = mask[o], mw = mask[o - 1], me = mask[o + 1], ms = mask[o - P], mn = mask[o + P];
+      gxl = (mc < 1E-6 || mw < 1E-6) ? 0.0 : fx * (pc - pw);
+      gxh = (me < 1E-6 || mc < 1E-6) ? 0.0 : fx * (pe - pc);
+      gyl = (mc < 1E-6 || ms < 1E-6) ? 0.0 : fy * (pc - ps);
+      gyh = (mn < 1E-6 || mc < 1E-6) ? 0.0 : fy * (pn - pc);
+    } else {
+      gxl = fx * (pc - pw); gxh = fx * (pe - pc); gyl = fy * (pc - ps); gyh = fy * (pn - pc);
+    }
+    gx = 0.5 * (gxl + gxh);
+    gy = 0.5 * (gyl + gyh);
+  }
+};
+template <int MASKGRAD>
+__global__ void __launch_bounds__(256) k_update_op_fused(double* __restrict__ bX, double* __restrict__ bY, const double* __restrict__ phi,
+                                                         OpArgs a) {
+  __shared__ double sRe[8][33], sB[8][33], sM[8][33];
+  const int nx = a.g.nx, ny = a.g.ny;
+  const int i = (int)blockIdx.x * RB_TX - 1 + (int)threadIdx.x, j = (int)blockIdx.y * RB_TY - 1 + (int)threadIdx.y;
+  const bool in = i <= nx && j <= ny;
+  const ptrdiff_t o = (ptrdiff_t)j * a.g.pitch + i;
+  const UpdOp<MASKGRAD> u{phi, a.mask, a};
+  double rc = 0.0, bc = 0.0, mc = 0.0;
+  if (in) {
+    bc = a.B[o]; mc = a.mask[o];
+    const bool ox = (i < 0 && u.phys(0)) || (i >= nx && u.phys(1)), oy = (j < 0 && u.phys(2)) || (j >= ny && u.phys(3));
+    double gx = 0.0, gy = 0.0;
+    if (!ox && !oy) u.grad(i, j, gx, gy);
+    else if (ox != oy) { // ExtrapGhostCells: ghost = 2 * first interior - second interior, along the outward direction
+      const int i1 = ox ? (i < 0 ? 0 : nx - 1) : i, i2 = ox ? (i < 0 ? 1 : nx - 2) : i;
+      const int j1 = oy ? (j < 0 ? 0 : ny - 1) : j, j2 = oy ? (j < 0 ? 1 : ny - 2) : j;
+      double ax, ay, bx, by;
+      u.grad(i1, j1, ax, ay);
+      u.grad(i2, j2, bx, by);
+      gx = 2.0 * ax - bx; gy = 2.0 * ay - by;
+    }
+    rc = reynolds(a.prm, bc, gx, gy);
+  }
+  sRe[threadIdx.y][threadIdx.x] = rc; sB[threadIdx.y][threadIdx.x] = bc; sM[threadIdx.y][threadIdx.x] = mc;
+  __syncthreads();
+  if (!in || threadIdx.x == 0 || threadIdx.y == 0) return;
+  const int lx = threadIdx.x, ly = threadIdx.y;
+  if (j < ny && i >= 0) {
+    double r = 0.5 * (rc + sRe[ly][lx - 1]), b = 0.5 * (bc + sB[ly][lx - 1]);
+    double mm = sM[ly][lx - 1];
+    double im = fabs(mc - mm) < 1e-10 ? (mc > 0.0 ? 1.0 : -1.0) : 0.0;
+    int gi = a.g.glo0 + i;
+    if (gi == a.g.dlo0) im = 0.0;
+    if (gi == a.g.dhi0 + 1) im = 0.0;
+    if (j >= 0) bX[o] = bcoeff_face(a.prm, b, r, im);
+  }
+  if (i < nx && j >= 0) {
+    double r = 0.5 * (rc + sRe[ly - 1][lx]), b = 0.5 * (bc + sB[ly - 1][lx]);
+    double mm = sM[ly - 1][lx];
+    double im = fabs(mc - mm) < 1e-10 ? (mc > 0.0 ? 1.0 : -1.0) : 0.0;
+    int gj = a.g.glo1 + j;
+    if (gj == a.g.dlo1) im = 0.0;
+    if (gj == a.g.dhi1 + 1) im = 0.0;
+    if (i >= 0) bY[o] = bcoeff_face(a.prm, b, r, im);
+  }
+}
+
 __global__ void __launch_bounds__(256) k_lambda_g(double* __restrict__ lamb, const PatchG* __restrict__ tab, OpArgsG a) {
   const PatchG g = tab[blockIdx.z];
   int i = blockIdx.x * blockDim.x + threadIdx.x;

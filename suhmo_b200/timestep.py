@@ -213,6 +213,21 @@ def picard_iteration(be, F, X, solve):
 def update_gap(be, F, X, dt, cur_step):
     """Gap-height update after the Picard loop (src/AmrHydro.cpp:3248-3455).  Returns the implicit solve's history or None."""
     hist = None
+    use_mask = bool(be.cfg.use_mask_grad)
+    # Re, Qw and the melt rate once more with the fresh head (evaluate_Re_quadratic(lev, true) ... Calc_meltingRate, :3256-3330)
+    be.mac_gradient(F["head"], F["mask"] if use_mask else None, *X["gH"])
+    be.edge_to_cell(*X["gH"], X["gradH"])
+    be.exchange(X["gradH"])
+    be.extrap_ghost(X["gradH"])
+    be.compute_re(X["Re"], F["B"], X["gradH"])
+    be.exchange(X["Re"])
+    be.cell_to_edge(X["Re"], *X["Reec"])
+    for d in range(2):
+        be.compute_qw(X["Bec"][d], X["Reec"][d], X["gH"][d], X["Qw"][d])
+        be.scaprod(X["Qw"][d], X["gH"][d], X["gZ"][d], X["t1"][d], X["t2"][d])
+    be.edge_to_cell(*X["t1"], X["qgh"])
+    be.edge_to_cell(*X["t2"], X["qgz"])
+    be.melting_rate(F["head"], F["zb"], F["Pi"], F["mask"], F["B"], X["qgh"], X["qgz"], X["Pw"], X["mR"])
     be.rhs_gap(X["RHSb"], F["Pi"], X["Pw"], X["mR"], F["B"], X["Dterm"], F["mask"], X["BH"], X["BL"], X["MV"], dt)
     if be.impl_diff:
         # implicit branch (:3378-3391, 3425-3455): a_gh_curr = B incl. ghosts, aCoef = 1, bCoef = Dcoef, SolveForGap_nl, copy back
@@ -237,6 +252,8 @@ def picard_step(be, F, X, dt=3600.0, npicard=2, ncyc=3, cur_step=0):
     be.icemask_ec(F["mask"], *X["IMec"])
     for _ in range(npicard):
         hists.append(picard_iteration(be, F, X, lambda F_: be.solve_head(F_, ncyc)))
+        be.exchange(F["head"])
+        be.apply_bc(F["head"])                 # head ghost cells refilled after the solve (:3143-3165)
     h = update_gap(be, F, X, dt, cur_step)
     if h is not None:
         hists.append(h)

@@ -15,9 +15,9 @@ levels = bench.gpu_tile_hierarchy(0, wl.tile_config(size), 3)
 prob = wl.Problem(size, 1, "weak", levels)
 gp = bench.GpuProblem(ctx, prob, 0)
 cells = prob.cells()
-for k8, k10, k11 in ((0, 0, 0), (0, 0, 4), (0, 50, 0), (0, 50, 4), (0, 100, 4), (0, 75, 4), (2, 0, 0), (4, 0, 0), (0, 0, 0)):
+for k8, k10, k11 in ((0, 0, 0), (0, 0, 3), (0, 50, 0), (0, 100, 0), (0, 75, 0), (2, 0, 0), (4, 0, 0), (0, 0, 0)):
     ctx.set_tuning(8, k8); ctx.set_tuning(10, k10); ctx.set_tuning(11, k11)
-    out = {"batch": k8 or 1, "carveout_pct": k10, "ctas_per_sm": k11 or 3}
+    out = {"batch": k8 or 1, "carveout_pct": k10, "ctas_per_sm": k11 or 4}
     for l in (1, 2):
         op = gp.ops[l]
         op.relax(gp.F[l]["head"], gp.F[l]["rhs"], 4)
