@@ -336,6 +336,43 @@ def small_configs(ctx, amr, threads, cycles=20):
     return out
 
 
+def valley_leg(ctx, amr, peak, nrel=16):
+    """The smoother on a level whose ice mask has negative entries (BASELINE configs[3], the SHMIP valley geometry, scaled 64x to
+    16384 x 4096 = 6.7e7 cells): the mask is streamed, 72 B per cell-update is what a launch has to move."""
+    cfg = syn.config("C4", 64)
+    boxes = syn.domain_split(cfg.nx, cfg.ny, cfg.max_box_size, cfg.block_factor)
+    layout = amr.DisjointBoxLayout(ctx, boxes, (0, 0, cfg.nx - 1, cfg.ny - 1), cfg.periodic)
+    F = {k: amr.LevelData(layout, 1, ng, cent) for k, (ng, cent) in SPEC.items()}
+    g = syn.fields(cfg, ng=1, moulin_cutoff=12.0)
+    for k in INPUTS:
+        F[k].set_global(g[k], (-1, -1) if SPEC[k][0] else (0, 0))
+    del g
+    for k in ("B", "Pi", "zb", "mask"):
+        amr.CopyGhostCells(F[k])
+    bc = amr.make_bc(cfg.bc_lo, cfg.bc_hi)
+    prm = amr.make_params(A=cfg.A, omega=cfg.omega, nu=cfg.nu, cutOffbr=cfg.cutOffbr, maxOffbr=cfg.maxOffbr, cutOffBcoef=cfg.cutOffBcoef,
+                          use_mask_grad=cfg.use_mask_grad)
+    fac = amr.VCAMRNonLinearPoissonOpFactory().define(ctx, [layout], [], cfg.dx, bc, 0.0, [F["a"]], -1.0, [F["bX"]], [F["bY"]], prm, [F["B"]],
+                                                      [F["Pi"]], [F["zb"]], [F["mask"]])
+    op = fac.AMRnewOp(0)
+    op.UpdateOperator(F["head"], None, 0, 0, False)
+    op.relax(F["head"], F["rhs"], 4)
+    ctx.event_record(0)
+    op.relax(F["head"], F["rhs"], nrel)
+    ctx.event_record(1)
+    k_ms = ctx.event_elapsed_ms(0, 1) / nrel
+    cells = cfg.nx * cfg.ny
+    streams = bool(op.streams_mask())
+    bpu = BYTES_SMOOTHER_MASK if streams else BYTES_SMOOTHER_NOMASK
+    achieved = bpu * cells / (k_ms * 1e-3) / 1e9
+    out = {"bound": "hbm", "kernel": f"k_gsrb_stream with the ice mask streamed (valley geometry, {cfg.nx}x{cfg.ny} cells)", "achieved": achieved,
+           "peak": peak, "unit": "GB/s", "frac": achieved / peak, "kernel_ms": k_ms, "bytes_per_cell_update": bpu, "cells_per_launch": cells,
+           "mask_streamed": streams}
+    for f in F.values():
+        f.destroy()
+    return out
+
+
 def gap_leg(ctx, amr, cfg, layout, F, op0, bx_mean):
     """SURVEY.md 8 f2: the implicit gap-height solve of the same time step (AmrHydro::SolveForGap_nl) on the resident base grid,
     with the reference's solver constants.  aCoef = 1, D = the B(h) face coefficients rescaled so that beta*D/dx^2 ~ 4 (diffusion
@@ -382,6 +419,8 @@ def main():
     ap.add_argument("--no-gap", action="store_true", help="skip the implicit gap-height solve leg (N = 1 only)")
     ap.add_argument("--no-small", action="store_true", help="skip the C1-C4 native-size table (N = 1 only)")
     ap.add_argument("--no-parity", action="store_true", help="skip the multi-rank parity checks (N > 1)")
+    ap.add_argument("--no-valley", action="store_true", help="skip the mask-streaming smoother leg on the valley geometry (N = 1 only)")
+    ap.add_argument("--no-strong", action="store_true", help="skip the strong-scaling leg of a weak-scaling run (N > 1)")
     ap.add_argument("--profile", action="store_true", help="cudaProfilerStart/Stop around the timed V-cycles (ncu --profile-from-start off)")
     args = ap.parse_args()
 
@@ -510,6 +549,27 @@ def main():
         single = {"ms_per_vcycle": ms1 / args.steps, "cell_updates_per_s": upd1 * args.steps / (ms1 * 1e-3), "cells": info["cells"][0],
                   "launches_per_vcycle": st1.kernel_launches / args.steps, "resnorm": [float(h1[0]), float(h1[-1])]}
 
+    # ---------------- N > 1, weak-scaling run: the same ONE-tile problem cut over the N GPUs (strong scaling) as a secondary leg
+    strong = None
+    if world > 1 and args.scaling == "weak" and not args.no_strong:
+        t0 = time.perf_counter()
+        probS = wl.Problem(args.size, world, "strong", levels)
+        gpS = GpuProblem(ctx, probS, rank)
+        gpS.mg.setSolverParameters(4, 4, args.bottom, 1, 100, 1e-10, 1e-4, 1e-7)
+        updS = gpS.mg.cell_updates_per_cycle()
+        _, hS, _ = gpS.mg.solve(gpS.fields("head"), gpS.fields("rhs"), fixed_cycles=max(2, args.warmup))
+        barrier()
+        _, _, stS = gpS.mg.solve(gpS.fields("head"), gpS.fields("rhs"), fixed_cycles=args.steps)
+        msS = max_over_ranks(stS.device_ms)
+        dS = probS.describe()
+        strong = {"scaling": "strong", "ms_per_vcycle": msS / args.steps, "cell_updates_per_s": updS * args.steps / (msS * 1e-3),
+                  "cells": dS["cells"], "cells_per_rank": dS["cells_per_rank"], "resnorm": [float(x) for x in hS[:4]],
+                  "partition": "base level in y-strips, refined boxes by connected cluster balanced by cell count",
+                  "setup_s": time.perf_counter() - t0,
+                  "note": "one-tile problem; its residual history must equal the N = 1 line's (the decomposition does not change the arithmetic)"}
+        gpS.mg.destroy()
+        del gpS
+
     # ---------------- end to end through the public API with HOST buffers: one head solve = upload of all inputs of all levels from
     # pinned FArrayBox memory, per-solve operator set-up, E2E_CYCLES V-cycles, download of the head of every level
     head_out = [torch.empty(F["head"].packed_size(), dtype=torch.float64, pin_memory=True) for F in gp.F]
@@ -567,6 +627,13 @@ def main():
                            "what": "composite residual max-norm before and after each V-cycle, full-size workload, GPU library vs CPU oracle"}
         del cp
 
+    valley = None
+    if world == 1 and not args.no_valley:
+        try:
+            valley = valley_leg(ctx, amr, peak)
+            roof.append(valley)
+        except Exception as e:
+            valley = {"failed": repr(e)[:300]}
     gap_info = small = None
     if world == 1 and not args.no_gap:
         try:
@@ -602,6 +669,7 @@ def main():
             "gpu_launches": int(launches),
             "launches_per_vcycle": launches / args.steps,
             "single_level": single,
+            "strong_scaling": strong,
             "parity_full_size": parity_full,
             "parity_nranks": parity_n,
             "small_configs": small,

@@ -1601,6 +1601,20 @@ extern "C" int sg_op_UpdateOperator(sg_op* op, sg_field* phi, const sg_field* ph
   SGCALL(check_same(op, phi, "UpdateOperator(phi)"));
   sg_layout* L = op->lay;
   if (!L->has_local && !phi_coarse) return SG_OK;
+  if (L->has_local && L->fast && !phi_coarse && L->nx >= 2 && L->ny >= 2 && op->ctx->tune[12] == 1) {
+    // tune key 12 = 1 -- one-patch level without a coarser one: gradient, its ghost cells, Re and both face coefficients in one pass
+    // (k_update_op_fused).  The gradient's ghost rows towards a neighbouring GPU are computed from phi's second ghost row instead of
+    // being exchanged: one halo exchange of phi (depth 2) replaces the two of phi and grad(phi).  Bit-exact, but NOT the default:
+    // measured at 8192^2 on B200 (tools/updop_bench.py) 1.205 ms against 1.138 ms for the gradient + face kernels -- the pass is bound
+    // by the FP64 sqrt/divide chain of COMPUTERE, which the fusion does not shorten, and the on-the-fly boundary logic adds to it.
+    if (has_ghost_sides(L)) SGCALL(fill_ghosts(phi, 2));
+    SGCALL(phys_bc(phi, &op->bc, op->dx, 0)); // the caller may read phi's boundary ghost cells afterwards, as after the reference's call
+    OpArgs a = make_args(op);
+    dim3 g((L->nx + 1 + RB_TX - 1) / RB_TX, (L->ny + 1 + RB_TY - 1) / RB_TY);
+    if (op->prm.use_mask_grad) LAUNCH(op->ctx, k_update_op_fused<1>, g, B2D, op->bX->p(), op->bY->p(), phi->p(), a);
+    else LAUNCH(op->ctx, k_update_op_fused<0>, g, B2D, op->bX->p(), op->bY->p(), phi->p(), a);
+    return coef_ghosts(op, true);
+  }
   if (L->has_local) {
     if (L->fast) { if (has_ghost_sides(L)) SGCALL(fill_ghosts(phi, 1)); }
     else SGCALL(exchange_g(phi, 1, 0));
@@ -2274,7 +2288,10 @@ static int run_cycle(sg_solver* s, sg_field* const* phi, sg_field* const* rhs, i
   sg_ctx* c = s->ctx;
   const int FIX = 100; // scratch slot the captured norm lands in
   const bool even = (sp->pre % 2 == 0 && sp->post % 2 == 0 && sp->bottom % 2 == 0) || c->relax_mode == 0;
-  const bool eligible = c->nranks == 1 && even && c->tune[2] == 0;
+  // N > 1: the cycle holds NCCL send/recv groups and the cross-stream events of the overlapped halo exchange; both are captured (every
+  // rank issues the same sequence; a rank whose capture fails falls back to eager launches, which issue the same NCCL calls in the same
+  // order).  Measured at N = 2: 23.97 -> 23.64 ms per 3-level V-cycle, same residual history.  tune key 13 = 2 turns it off.
+  const bool eligible = (c->nranks == 1 || c->tune[13] != 2) && even && c->tune[2] == 0;
   if (!eligible) {
     SGCALL(vcycle(s, phi, rhs, l_max, sp, iter));
     return residual_norm(s, phi, rhs, l_max, normslot);

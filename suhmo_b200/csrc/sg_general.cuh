@@ -463,6 +463,8 @@ struct UpdOp {
   const double* __restrict__ phi; const double* __restrict__ mask;
   const OpArgs& a;
   __device__ __forceinline__ bool phys(int s) const { return a.g.kind[s] == SK_PHYS_DIRI || a.g.kind[s] == SK_PHYS_NEUM; }
+  // a non-periodic problem-domain side (Robin included: mixBCValues leaves phi's ghost cells alone there, ExtrapGhostCells does not)
+  __device__ __forceinline__ bool dom(int s) const { return phys(s) || a.g.kind[s] == SK_PHYS_NONE; }
   // phi at (i, j), |offset from the valid region| <= 1 in one direction at a time
   __device__ __forceinline__ double ph(int i, int j) const {
     const ptrdiff_t P = a.g.pitch;
@@ -503,7 +505,7 @@ __global__ void __launch_bounds__(256) k_update_op_fused(double* __restrict__ bX
   double rc = 0.0, bc = 0.0, mc = 0.0;
   if (in) {
     bc = a.B[o]; mc = a.mask[o];
-    const bool ox = (i < 0 && u.phys(0)) || (i >= nx && u.phys(1)), oy = (j < 0 && u.phys(2)) || (j >= ny && u.phys(3));
+    const bool ox = (i < 0 && u.dom(0)) || (i >= nx && u.dom(1)), oy = (j < 0 && u.dom(2)) || (j >= ny && u.dom(3));
     double gx = 0.0, gy = 0.0;
     if (!ox && !oy) u.grad(i, j, gx, gy);
     else if (ox != oy) { // ExtrapGhostCells: ghost = 2 * first interior - second interior, along the outward direction

@@ -56,9 +56,16 @@ def test_geometry_parity(gpu_ctx, geom):
     gop.residual(gres, gpu.F["head"], gpu.F["rhs"])
     same(gres, ores, f"{geom}: residual")
     oop.update_operator(orc.F["head"])
-    gop.UpdateOperator(gpu.F["head"], None, 0, 0, False)
-    same(gpu.F["bX"], orc.F["bX"], f"{geom}: bX after UpdateOperator")
-    same(gpu.F["bY"], orc.F["bY"], f"{geom}: bY after UpdateOperator")
+    for key12, flow in ((0, "gradient / exchange / extrapolation / face kernels"), (1, "one pass")):   # tune key 12 = 1: k_update_op_fused
+        gpu_ctx.set_tuning(12, key12)
+        try:
+            for f in (gpu.F["bX"], gpu.F["bY"]):
+                gop.setToZero(f)
+            gop.UpdateOperator(gpu.F["head"], None, 0, 0, False)
+        finally:
+            gpu_ctx.set_tuning(12, 0)
+        same(gpu.F["bX"], orc.F["bX"], f"{geom}: bX after UpdateOperator ({flow})")
+        same(gpu.F["bY"], orc.F["bY"], f"{geom}: bY after UpdateOperator ({flow})")
     osolver = orc.solver()
     mg = gpu.amr.AMRFASMultiGrid().define(gpu.factory, 1)
     assert mg.depth == osolver.depth
