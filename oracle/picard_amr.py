@@ -237,3 +237,31 @@ class TimeStep:
             self.exchange(S["B"])
             L.orc_copy_ghost(S["B"].h)
         self.average_down("B")
+
+    # ---- the whole step (:2255-3620): Picard iterations until the reference's test passes, then the gap update ------------------------
+    def time_step(self, dt, cur_step=0, eps_picard=1.0e-6):
+        early = cur_step < 50
+        sp = ob.make_solver_params(pre=4, post=4, bottom=10 if early else 16, max_iter=100, imin=20 if early else 5, iter_min=2,
+                                   eps=1e-10 if early else 1e-7, hang=1e-4 if early else 0.01, norm_thresh=1e-7)    # :737-762
+        self.begin_step()
+        out = {"x_h": [], "head_cycles": []}
+        ite_idx = 0
+        while True:
+            hist = self.picard_iteration(sp)
+            out["head_cycles"].append(len(hist) - 1)
+            max_resH = self.picard_change()
+            out["x_h"].append(max_resH)
+            if ite_idx > 100:
+                raise RuntimeError("Abort")                                # MayDay::Error("Abort"), :3190-3195
+            if cur_step < 2:
+                converged = max_resH < 0.05 and ite_idx > 2                # m_cur_PicardIte > 2 (:3198)
+            elif cur_step < 50:
+                converged = max_resH < 0.05
+            else:
+                converged = max_resH < eps_picard
+            ite_idx += 1
+            if converged:
+                break
+        out["picard_iterations"] = ite_idx
+        self.update_gap(dt)
+        return out

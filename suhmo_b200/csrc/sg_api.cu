@@ -70,6 +70,7 @@ struct sg_ctx {
   bool smem_attr_set = false; // dynamic shared-memory opt-in of the streaming kernels done for this context's device
   cudaStream_t comm_stream = nullptr;    // nranks > 1: halo exchanges that overlap the interior part of a sweep run here
   cudaEvent_t ev_comm[2] = {nullptr, nullptr};
+  std::vector<struct sg_solver*> solvers; // live head solvers: their captured graphs (which hold NCCL kernels at N > 1) go before the communicator
   int tune[16] = {0}; // experiment knobs (sg_set_tuning): 0 rows per warp, 1 CTAs per SM of the fused sweep
   SgNccl nccl;
   // reduction scratch
@@ -289,11 +290,13 @@ extern "C" int sg_ctx_create(sg_ctx** out, int device, int rank, int nranks, con
 }
 struct sg_layout;
 static void gap_cache_forget(const sg_ctx* ctx, const sg_layout* L);
+static void drop_solver_graphs(sg_ctx* c);
 extern "C" int sg_ctx_destroy(sg_ctx* c) {
   if (!c) return SG_OK;
   cudaSetDevice(c->device);
   gap_cache_forget(c, nullptr); // cached implicit gap-height solvers own device fields on this context
   cudaStreamSynchronize(c->stream);
+  drop_solver_graphs(c); // ncclCommDestroy waits for every graph that captured one of its kernels
   if (c->comm_stream) { cudaStreamSynchronize(c->comm_stream); cudaStreamDestroy(c->comm_stream); }
   for (int k = 0; k < 2; k++) if (c->ev_comm[k]) cudaEventDestroy(c->ev_comm[k]);
   c->nccl.destroy();
@@ -1065,7 +1068,10 @@ static int wflx_impl(sg_ctx* ctx, sg_op* op, const sg_params* p, sg_field* bX, s
     if (Lc->has_local) {
       SGCALL(ws_field(Lc, 3, 2, &gradC));
       double dxc[2] = {dx[0] * 2, dx[1] * 2}; // "assumes refRatio = 2" (src/AmrHydro.cpp:1467)
-      SGCALL(gradient_cc_any(gradC, u_coarse, p->use_mask_grad ? op->link->crse_mask : nullptr, dxc));
+      // (the coarse field's boundary ghost cells were filled by the caller / the coarse level's own UpdateOperator, as in the reference)
+      if (Lc->fast && Lc->patches.size() == 1 && ctx->tune[9] != 1)
+        SGCALL(coarse_gradient_near_fine(op, gradC, u_coarse, p->use_mask_grad ? op->link->crse_mask : nullptr, dxc));
+      else SGCALL(gradient_cc_any(gradC, u_coarse, p->use_mask_grad ? op->link->crse_mask : nullptr, dxc));
       int ngc = gradC->ng;
       gradC->ng = 1;
       SGCALL(exchange_any(gradC, 1, 1));
@@ -1286,6 +1292,22 @@ static int check_same(const sg_op* op, const sg_field* f, const char* what) {
   return SG_OK;
 }
 
+// does relax_impl run this level's sweeps four at a time in shared-memory tiles (k_gsrb_tile)?  One buffer swap per four iterations
+// then, which the CUDA-graph eligibility test has to know (run_cycle)
+static bool tile_smoother_applies(const sg_op* op) {
+  const sg_layout* L = op->lay;
+  const sg_ctx* c = op->ctx;
+  if (!L->fast || c->relax_mode != 1 || c->tune[15] == 1 || (long long)L->nx * L->ny > (1LL << 21) || L->nx < 16 || L->ny < 16) return false;
+  const Geom g = make_geom(L, &op->bc);
+  const bool ygh = L->side_ghost[2] || L->side_ghost[3];
+  if (ygh && (c->tune[3] != 0 || L->side_ghost[0] || L->side_ghost[1])) return false; // needs the 8-row exchange of the wide mode
+  return g.kind[0] <= SK_PHYS_NEUM && g.kind[1] <= SK_PHYS_NEUM && (g.kind[2] <= SK_PHYS_NEUM || g.kind[2] == SK_GHOST) &&
+         (g.kind[3] <= SK_PHYS_NEUM || g.kind[3] == SK_GHOST);
+}
+static int relax_swaps(const sg_op* op, int iterations) { // buffer swaps of one relax call
+  return tile_smoother_applies(op) ? iterations / 4 + iterations % 4 : iterations;
+}
+
 // one levelGSRB iteration set
 // trailing == false: the caller refills every ghost cell before its next read (the V-cycle driver does: restriction, residual
 // and UpdateOperator all start with BC + exchange), so levelGSRB's closing exchange + homogeneous BC fill are dead stores
@@ -1295,7 +1317,7 @@ static int relax_impl(sg_op* op, sg_field* phi, const sg_field* rhs, int iterati
   sg_layout* L = op->lay;
   sg_ctx* c = op->ctx;
   if (!L->has_local || iterations <= 0) return SG_OK;
-  if (!L->fast) return relax_g(op, phi, rhs, iterations);
+  if (!L->fast) return relax_g(op, phi, rhs, iterations, trailing);
   OpArgs a = make_args(op);
   bool ghosts = has_ghost_sides(L);
   if (c->relax_mode >= 1) {
@@ -1340,7 +1362,7 @@ static int relax_impl(sg_op* op, sg_field* phi, const sg_field* rhs, int iterati
       if (c->tune[0] > 0) nsegs = (nrows + c->tune[0] - 1) / c->tune[0];
       else if (kind == 1 || kind == 3 || kind == 4) {
         long long rows = ((long long)f.nstrips * nrows) / (4LL * capacity);
-        rows = kind != 1 ? std::max(16LL, std::min(96LL, rows)) : std::max(8LL, std::min(48LL, rows));
+        rows = kind != 1 ? std::max(16LL, std::min(96LL, rows)) : std::max((long long)(c->tune[15] > 0 ? c->tune[15] : 8), std::min(48LL, rows));
         nsegs = (int)((nrows + rows - 1) / rows);
       } else if (f.nstrips * ((L->ny + 63) / 64) <= capacity) nsegs = std::max(1, std::min((L->ny + 31) / 32, capacity / f.nstrips));
       else {
@@ -1354,7 +1376,27 @@ static int relax_impl(sg_op* op, sg_field* phi, const sg_field* rhs, int iterati
     };
     f.ylo = 0; f.yhi = L->ny;
     int it = 0;
+    // levels that sit in L2 (the coarser multigrid depths): four iterations per launch in shared-memory tiles (k_gsrb_tile) while at
+    // least four remain.  x sides physical (Dirichlet / Neumann), y sides physical or ghost rows (then the eight rows of the
+    // communication-avoiding exchange are exactly its halo).  tune key 15 = 1 turns it off.
+    const bool tile_ok = tile_smoother_applies(op) && (!ghosts || wide);
     while (it < iterations) {
+      if (tile_ok && iterations - it >= 4) {
+        if (ghosts) {
+          GhostReq r[2] = {{phi, 8}, {const_cast<sg_field*>(rhs), rhs_depth}};
+          if (it == 0 && phi_valid >= 8) { if (rhs_pending) SGCALL(fill_ghosts_multi(c, r + 1, 1)); }
+          else SGCALL(fill_ghosts_multi(c, r, rhs_pending ? 2 : 1));
+          rhs_pending = false;
+        }
+        f.phi_in = phi->p();
+        f.phi_out = scratch->p();
+        dim3 tg((L->nx + GT_TX - 1) / GT_TX, (L->ny + GT_TY - 1) / GT_TY);
+        if (a.has_a) LAUNCH(c, (k_gsrb_tile<1, 4>), tg, B2D, f);
+        else LAUNCH(c, (k_gsrb_tile<0, 4>), tg, B2D, f);
+        std::swap(phi->base, scratch->base);
+        it += 4;
+        continue;
+      }
       const bool two = can2 && it + 2 <= iterations;
       const int kind = two ? (c->relax_mode == 4 ? 4 : 3) : (c->relax_mode == 2 ? 2 : 1);
       const int chunk = (wide && kind == 1) ? std::min(4, iterations - it) : 1;
@@ -2018,6 +2060,10 @@ extern "C" int sg_op_homogeneousCFInterp(sg_op* op, sg_field* phi) {
 // FAS multigrid driver, device resident (absent fork's AMRFASMultiGrid / MultiGrid; see DESIGN.md for the
 // inferred pieces, identical to oracle/suhmo_oracle.c)
 // ------------------------------------------------------------------------------------------------
+static void drop_solver_graphs(sg_ctx* c) {
+  for (sg_solver* s : c->solvers)
+    if (s->gexec) { cudaGraphExecDestroy(s->gexec); s->gexec = nullptr; s->gkey.clear(); }
+}
 extern "C" int sg_solver_define(sg_factory* f, sg_solver** out, int num_levels) {
   REQUIRE(f && out, "sg_solver_define: null");
   REQUIRE(num_levels >= 1 && num_levels <= f->nlevels, "sg_solver_define: %d levels requested, the factory holds %d", num_levels, f->nlevels);
@@ -2053,6 +2099,7 @@ extern "C" int sg_solver_define(sg_factory* f, sg_solver** out, int num_levels) 
     s->asave.push_back(sav);
   }
   s->resid = s->aresid[0];
+  s->ctx->solvers.push_back(s);
   *out = s;
   return SG_OK;
 }
@@ -2097,6 +2144,8 @@ extern "C" int sg_solver_destroy(sg_solver* s) {
   }
   for (sg_op* op : s->ops) sg_op_destroy(op);
   if (s->gexec) cudaGraphExecDestroy(s->gexec);
+  auto& live = s->ctx->solvers;
+  live.erase(std::remove(live.begin(), live.end(), s), live.end());
   delete s;
   return SG_OK;
 }
@@ -2202,7 +2251,9 @@ static int amr_vcycle(sg_solver* s, sg_field* const* phi, sg_field* const* rhs, 
   sg_ctx* c = s->ctx;
   // this level's right-hand side: the top level solves against the caller's rhs itself (the reference copies it into residual[lmax])
   sg_field* rl = ilev == l_max ? rhs[ilev] : s->aresid[ilev];
-  SGCALL(sg_op_relaxNF(op, phi[ilev], phi[ilev - 1], rl, sp->pre, iter, ilev, 0));
+  // relaxNF = QuadCFInterp + levelGSRB; its closing exchange + homogeneous BC fill are dead stores here (see relax_impl)
+  SGCALL(cf_interp_impl(op, phi[ilev], phi[ilev - 1]));
+  SGCALL(relax_impl(op, phi[ilev], rl, sp->pre, c->tune[14] == 1));
   // phi[ilev-1] <- average of phi[ilev] on the covered region (AMRRestrictS with skip_res), kept as the FAS reference state
   SGCALL(amr_restrict_impl(op, s->aresC[ilev], phi[ilev], phi[ilev], phi[ilev - 1], s->ascratch[ilev], 1, false));
   SGCALL(run_plan(c, phi[ilev - 1]->cb(), s->aresC[ilev]->cb(), op->link->t2c));
@@ -2231,7 +2282,8 @@ static int amr_vcycle(sg_solver* s, sg_field* const* phi, sg_field* const* rhs, 
   SGCALL(amr_vcycle(s, phi, rhs, ilev - 1, l_max, sp, iter));
   // AMRProlongS_2 of phi[ilev-1] - saved, with the operator's scratch standing in for m_resC
   SGCALL(amr_prolong_impl(op, phi[ilev], phi[ilev - 1], opc, 1, s->asave[ilev]));
-  return sg_op_relaxNF(op, phi[ilev], phi[ilev - 1], rl, sp->post, iter, ilev, 0);
+  SGCALL(cf_interp_impl(op, phi[ilev], phi[ilev - 1]));
+  return relax_impl(op, phi[ilev], rl, sp->post, c->tune[14] == 1);
 }
 static int vcycle(sg_solver* s, sg_field* const* phi, sg_field* const* rhs, int l_max, const sg_solver_params* sp, int iter) {
   if (l_max == 0) {
@@ -2287,7 +2339,17 @@ static int residual_norm(sg_solver* s, sg_field* const* phi, sg_field* const* rh
 static int run_cycle(sg_solver* s, sg_field* const* phi, sg_field* const* rhs, int l_max, const sg_solver_params* sp, int iter, int normslot) {
   sg_ctx* c = s->ctx;
   const int FIX = 100; // scratch slot the captured norm lands in
-  const bool even = (sp->pre % 2 == 0 && sp->post % 2 == 0 && sp->bottom % 2 == 0) || c->relax_mode == 0;
+  // every field must own the same buffer after a cycle as before it: an even number of out-of-place launches per field
+  bool even = c->relax_mode == 0;
+  if (!even) {
+    even = true;
+    const int nd = (int)s->ops.size();
+    for (int d = 0; d < nd; d++) {
+      const int sw = d == nd - 1 ? relax_swaps(s->ops[d], sp->bottom) : relax_swaps(s->ops[d], sp->pre) + relax_swaps(s->ops[d], sp->post);
+      if (sw % 2) even = false;
+    }
+    if (l_max > 0 && (sp->pre + sp->post) % 2) even = false; // refined levels: one swap per iteration
+  }
   // N > 1: the cycle holds NCCL send/recv groups and the cross-stream events of the overlapped halo exchange; both are captured (every
   // rank issues the same sequence; a rank whose capture fails falls back to eager launches, which issue the same NCCL calls in the same
   // order).  Measured at N = 2: 23.97 -> 23.64 ms per 3-level V-cycle, same residual history.  tune key 13 = 2 turns it off.

@@ -365,6 +365,34 @@ __global__ void __launch_bounds__(256) k_gradient_cc_g(double* __restrict__ gxb,
   gyb[o] = 0.5 * (gyl + gyh);
 }
 
+// the same on a list of rectangles of one array (ZeroSeg: offset of the low corner from the component base, extent, pitch): the coarse
+// level's gradient is only needed under and around the finer level (WFlx_level computes it over the whole coarse level)
+__global__ void __launch_bounds__(256) k_gradient_cc_segs(double* __restrict__ gxb, double* __restrict__ gyb, const double* __restrict__ phib,
+                                                          const double* __restrict__ maskb, const long long* __restrict__ soff,
+                                                          const int* __restrict__ sdim, double dx0, double dx1) {
+  const long long off = soff[blockIdx.z];
+  const int nx = sdim[3 * blockIdx.z], ny = sdim[3 * blockIdx.z + 1];
+  const ptrdiff_t P = sdim[3 * blockIdx.z + 2];
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  int j = blockIdx.y * blockDim.y + threadIdx.y;
+  if (i >= nx || j >= ny) return;
+  ptrdiff_t o = off + (ptrdiff_t)j * P + i;
+  double fx = 1.0 / dx0, fy = 1.0 / dx1;
+  double pc = phib[o], pw = phib[o - 1], pe = phib[o + 1], ps = phib[o - P], pn = phib[o + P];
+  double gxl, gxh, gyl, gyh;
+  if (maskb) {
+    double mc = maskb[o], mw = maskb[o - 1], me = maskb[o + 1], ms = maskb[o - P], mn = maskb[o + P];
+    gxl = (mc < 1E-6 || mw < 1E-6) ? 0.0 : fx * (pc - pw);
+    gxh = (me < 1E-6 || mc < 1E-6) ? 0.0 : fx * (pe - pc);
+    gyl = (mc < 1E-6 || ms < 1E-6) ? 0.0 : fy * (pc - ps);
+    gyh = (mn < 1E-6 || mc < 1E-6) ? 0.0 : fy * (pn - pc);
+  } else {
+    gxl = fx * (pc - pw); gxh = fx * (pe - pc); gyl = fy * (pc - ps); gyh = fy * (pn - pc);
+  }
+  gxb[o] = 0.5 * (gxl + gxh);
+  gyb[o] = 0.5 * (gyl + gyh);
+}
+
 // COMPUTERE over the ghosted box
 __global__ void __launch_bounds__(256) k_compute_re_g(double* __restrict__ Reb, const double* __restrict__ Bb, const double* __restrict__ gxb,
                                                       const double* __restrict__ gyb, const PatchG* __restrict__ tab, PhysP prm) {
@@ -744,7 +772,7 @@ __global__ void __launch_bounds__(128) k_reflux_fused(double* __restrict__ resb,
   const double r = rhsb[it.res] - (lofc);
   if (MODE == 0) resb[it.res] = r;
   else if (MODE == 1) resb[it.res] = r + 1.0 * lof;
-  else atomicMax(norm_bits, (unsigned long long)__double_as_longlong(fabs(r)));
+  else { const unsigned long long bits = (unsigned long long)__double_as_longlong(fabs(r)); if (bits > *(volatile unsigned long long*)norm_bits) atomicMax(norm_bits, bits); }
 }
 // res += L(phi) on rectangles of a one-patch level (the cells under the finer level, after the restricted fine residual landed there)
 __global__ void k_add_lof_segs(double* __restrict__ resb, const double* __restrict__ phicb, OpArgs a, long long off0, const ZeroSeg* __restrict__ segs,

@@ -845,7 +845,11 @@ __device__ __forceinline__ void block_max_to_global(double v, unsigned long long
   if (w == 0) {
     v = lane < nw ? wmax[lane] : 0.0;
     for (int o = 16; o > 0; o >>= 1) v = nanmax(v, __shfl_xor_sync(0xffffffffu, v, o));
-    if (lane == 0) atomicMax(dst, (unsigned long long)__double_as_longlong(fabs(v)));
+    if (lane == 0) {
+      // most blocks do not raise the running maximum: look before the read-modify-write (thousands of same-address atomics serialise)
+      const unsigned long long bits = (unsigned long long)__double_as_longlong(fabs(v));
+      if (bits > *(volatile unsigned long long*)dst) atomicMax(dst, bits);
+    }
   }
 }
 
@@ -897,6 +901,69 @@ __global__ void __launch_bounds__(256) k_apply(double* __restrict__ out, const d
     rmax = nanmax(rmax, fabs(r));
   }
   if (MODE == 2 || MODE == 3 || MODE == 6) block_max_to_global(rmax, norm_bits);
+}
+
+// ------------------------------------------------------------------------------------------------
+// K GSRB iterations in ONE launch for one-patch levels that sit in L2 (the coarser multigrid depths: <= 2 M cells).  There a sweep of
+// k_gsrb_stream is latency-bound (14 us for 65 k cells: one warp per SM marching through its rows), and a relax call is 4-16 of them.
+// A CTA owns a GT_TX x GT_TY tile, loads it with a halo of 2K cells into shared memory and runs the 2K colour passes in place; pass d
+// (1..2K) updates the cells at least d cells away from every OPEN edge of what the CTA holds (a tile edge, or the last ghost row the
+// neighbouring GPU / periodic image supplied), so the tile itself ends up exactly K iterations ahead; physical sides are closed edges
+// (ghost value from the first interior cell on the fly, as in gs_update).  The halo is recomputed redundantly ((80 x 48)/(64 x 32) =
+// 1.9 x the updates for K = 4): irrelevant where latency is the cost.  Coefficients come from global memory (L2 hits).  Same point
+// arithmetic as gs_update / GSRBHELMHOLTZVCNL2D.  x sides must be physical; y sides physical or ghost rows of depth 2K in memory.
+#define GT_TX 64
+#define GT_TY 32
+template <int HAS_A, int K>
+__global__ void __launch_bounds__(256) k_gsrb_tile(FusedArgs f) {
+  constexpr int H = 2 * K, W = GT_TX + 2 * H, HT = GT_TY + 2 * H;
+  __shared__ double t[HT][W + 1];
+  const OpArgs& a = f.a;
+  const int nx = a.g.nx, ny = a.g.ny;
+  const ptrdiff_t P = a.g.pitch;
+  const int x0 = (int)blockIdx.x * GT_TX - H, y0 = (int)blockIdx.y * GT_TY - H; // index of t[0][0]
+  const bool ghlo = a.g.kind[2] == SK_GHOST, ghhi = a.g.kind[3] == SK_GHOST;
+  // existing cells held by this CTA: [ib, ie) x [jb, je); an edge is closed when it is a physical side of the level
+  const int ib = max(x0, 0), ie = min(x0 + W, nx), jb = max(y0, ghlo ? -H : 0), je = min(y0 + HT, ghhi ? ny + H : ny);
+  const bool open_l = ib > 0, open_r = ie < nx, open_b = !(jb == 0 && !ghlo), open_t = !(je == ny && !ghhi);
+  const int tid = threadIdx.y * blockDim.x + threadIdx.x;
+  for (int q = tid; q < W * HT; q += 256) {
+    const int lj = q / W, li = q - lj * W, gi = x0 + li, gj = y0 + lj;
+    t[lj][li] = (gi >= ib && gi < ie && gj >= jb && gj < je) ? f.phi_in[(ptrdiff_t)gj * P + gi] : 0.0;
+  }
+  __syncthreads();
+  const int gpar = (a.g.glo0 + a.g.glo1) & 1;
+  const int hw = (W + 1) / 2;
+#pragma unroll 1
+  for (int d = 1; d <= 2 * K; d++) {
+    const int pass = (d - 1) & 1;
+    const int il = open_l ? ib + d : ib, ir = open_r ? ie - d : ie, jl = open_b ? jb + d : jb, jr = open_t ? je - d : je; // updatable box
+    for (int q = tid; q < hw * HT; q += 256) {
+      const int lj = q / hw, gj = y0 + lj;
+      const int li = 2 * (q - lj * hw) + ((gpar + x0 + gj + pass) & 1), gi = x0 + li;
+      if (li >= W || gi < il || gi >= ir || gj < jl || gj >= jr) continue;
+      const ptrdiff_t o = (ptrdiff_t)gj * P + gi;
+      const double pc = t[lj][li];
+      double pw = li > 0 ? t[lj][li - 1] : 0.0, pe = li < W - 1 ? t[lj][li + 1] : 0.0, ps = lj > 0 ? t[lj - 1][li] : 0.0, pn = lj < HT - 1 ? t[lj + 1][li] : 0.0;
+      if (gi == 0 && a.g.kind[0] <= SK_PHYS_NEUM) pw = bc_ghost_value(a.g.kind[0], pc, a.g.bcval[0], f.sdx[0]);
+      if (gi == nx - 1 && a.g.kind[1] <= SK_PHYS_NEUM) pe = bc_ghost_value(a.g.kind[1], pc, a.g.bcval[1], f.sdx[1]);
+      if (gj == 0 && a.g.kind[2] <= SK_PHYS_NEUM) ps = bc_ghost_value(a.g.kind[2], pc, a.g.bcval[2], f.sdx[2]);
+      if (gj == ny - 1 && a.g.kind[3] <= SK_PHYS_NEUM) pn = bc_ghost_value(a.g.kind[3], pc, a.g.bcval[3], f.sdx[3]);
+      const double bw = a.bX[o], be = a.bX[o + 1], bs = a.bY[o], bn = a.bY[o + P];
+      const double ac = HAS_A ? a.aC[o] : 0.0;
+      double nl, dnl;
+      nl_terms(a.prm, pc, a.B[o], a.use_mask ? a.mask[o] : 1.0, a.Pi[o], a.zb[o], nl, dnl);
+      const double lof = lofphi_cell(a.alpha, ac, a.beta, pc, pw, pe, ps, pn, bw, be, bs, bn, a.dxi0, a.dxi1, nl);
+      const double lam = lambda_cell(a.alpha, ac, a.beta, bw, be, bs, bn, a.dxi0, a.dxi1);
+      const double denom = 1.0e-16 + lam + dnl;
+      t[lj][li] = pc + (f.rhs[o] - lof) / denom;
+    }
+    __syncthreads();
+  }
+  for (int q = tid; q < GT_TX * GT_TY; q += 256) {
+    const int lj = q / GT_TX, li = q - lj * GT_TX, gi = x0 + H + li, gj = y0 + H + lj;
+    if (gi < nx && gj < ny) f.phi_out[(ptrdiff_t)gj * P + gi] = t[H + lj][H + li];
+  }
 }
 
 // restrictResidual + restrictR fused (src/VCAMRNonLinearPoissonOp.cpp:347-460; RESTRICTRESVCNL2D / RESTRICTVCNL,

@@ -177,6 +177,22 @@ class VCAMRNonLinearPoissonOp {
   void diagonalScale(LevelData& rhs, bool kappaWeighted = false) { SG_DO(sg_op_diagonalScale(h, rhs.h, kappaWeighted)); }
   void divideByIdentityCoef(LevelData& rhs) { SG_DO(sg_op_divideByIdentityCoef(h, rhs.h)); }
   void homogeneousCFInterp(LevelData& phi) { SG_DO(sg_op_homogeneousCFInterp(h, phi.h)); }
+  // ---- multi-level pieces of the Picard body and of regridding; *this is the FINE level's operator
+  // PiecewiseLinearFillPatch(...).fillInterp(fine, coarse, coarse, ...), one ghost cell (src/AmrHydro.cpp:2373-2380 and friends)
+  void pwlFillPatch(LevelData& fine, const LevelData& coarse) { SG_DO(sg_op_pwlFillPatch(h, fine.h, coarse.h)); }
+  // FineInterp(...).interpToFine(fine, coarse), m_boundary_limit_type = 3 (src/AmrHydro.cpp:4190-4198)
+  void fineInterp(LevelData& fine, const LevelData& coarse) { SG_DO(sg_op_fineInterp(h, fine.h, coarse.h)); }
+  // CoarseAverage(fineGrids, 1, 2).averageToCoarse(coarse, fine) (src/AmrHydro.cpp:3139-3140)
+  void averageToCoarse(LevelData& coarse, const LevelData& fine) { SG_DO(sg_op_averageToCoarse(h, coarse.h, fine.h)); }
+  // destructiveRegrid (src/AmrHydro.cpp:4176-4223); oldData may be null
+  void regridTransfer(LevelData& newData, const LevelData* oldData, const LevelData& crseData)
+  { SG_DO(sg_regrid_transfer(h, newData.h, oldData ? oldData->h : nullptr, crseData.h)); }
+  // Calc_moulin_integral / Calc_moulin_source_term_distributed (src/AmrHydro.cpp:1867-2069), one level per call
+  void moulinIntegralLevel(VCAMRNonLinearPoissonOp* finer, int n, const double* pos, const double* sigma, double* integ)
+  { SG_DO(sg_moulin_integral_level(h, finer ? finer->h : nullptr, n, pos, sigma, integ)); }
+  void moulinSourceLevel(VCAMRNonLinearPoissonOp* finer, LevelData& src, int n, const double* pos, const double* sigma, const double* integ,
+                         const double* flux, double runoff, double time)
+  { SG_DO(sg_moulin_source_level(h, finer ? finer->h : nullptr, src.h, n, pos, sigma, integ, flux, runoff, time)); }
 };
 
 class VCAMRNonLinearPoissonOpFactory {
@@ -262,6 +278,9 @@ inline void setup_iceMask_EC(const LevelData& mask, LevelData& mx, LevelData& my
 // call where the reference loops over the FluxBox directions
 inline void evaluate_Qw_ec(const sg_params& p, const LevelData& Bec, const LevelData& Reec, const LevelData& gradHec, LevelData& Qw)
 { SG_DO(sg_compute_qw(&p, Bec.h, Reec.h, gradHec.h, Qw.h)); }
+// aCoeff_bCoeff (src/AmrHydro.cpp:1782-1812), one face direction
+inline void aCoeff_bCoeff(const sg_params& p, const LevelData& Bec, const LevelData& Reec, const LevelData& IMec, LevelData& bC)
+{ SG_DO(sg_compute_bcoeff(&p, Bec.h, Reec.h, IMec.h, bC.h)); }
 inline void computeScaProd(const LevelData& a, const LevelData& b1, const LevelData& b2, LevelData& p1, LevelData& p2)
 { SG_DO(sg_compute_scaprod(a.h, b1.h, b2.h, p1.h, p2.h)); }
 inline void dCoeff(LevelData& D, const LevelData& mRec, const LevelData& Bec, const LevelData& IMec, double rho, int cutOffB)

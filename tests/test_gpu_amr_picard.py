@@ -121,3 +121,21 @@ def test_multilevel_picard_and_gap_update_bit_exact(gpu_ctx, hier):
         for k in ("B", "mR", "Re", "RHSb"):
             same(st.S[l][k], H.S[l][k], f"gap update {k} L{l}")
         same(st.S[l]["B"], H.S[l]["B"], f"gap update B with ghosts L{l}", ghosts=l > 0)
+
+
+@pytest.mark.parametrize("hier,cur_step", [("C5", 0), ("C5", 60), ("C4", 10)])
+def test_multilevel_time_steps_same_decisions(gpu_ctx, hier, cur_step):
+    """two whole time steps with convergence-driven head solves and Picard loops: the same number of V-cycles per solve, the same
+    Picard iteration count, the same convergence measures, and bit-identical head and gap height on every level"""
+    from suhmo_b200.timestep_amr import AmrTimeStep
+    cfg, lv = amr_hierarchy(hier)
+    H, st = build_oracle(cfg, lv), build_device(gpu_ctx, cfg, lv)
+    ots, gts = opa.TimeStep(H), AmrTimeStep(st)
+    for step in range(2):
+        o = ots.time_step(1800.0, cur_step + step)
+        g = gts.time_step(1800.0, cur_step + step)
+        assert g["picard_iterations"] == o["picard_iterations"] and g["head_cycles"] == o["head_cycles"], (g, o)
+        assert g["x_h"] == o["x_h"], (g["x_h"], o["x_h"])
+        for l in range(H.nlev):
+            same(st.S[l]["head"], H.S[l]["head"], f"step {step} head L{l}")
+            same(st.S[l]["B"], H.S[l]["B"], f"step {step} gap height L{l}")

@@ -22,7 +22,7 @@ def _ngpu():
 def test_two_rank_partition_is_bit_exact(cfg, scale):
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
            "--master-port", "29533", os.path.join(ROOT, "tools", "parity_multi.py"), cfg, str(scale)]
-    r = subprocess.run(cmd, cwd=ROOT, capture_output=True, text=True, timeout=600)
+    r = subprocess.run(cmd, cwd=ROOT, capture_output=True, text=True, timeout=240)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
     assert '"head_bit_exact": true' in r.stdout and '"gap_solve_bit_exact": true' in r.stdout
 
@@ -33,6 +33,6 @@ def test_two_rank_amr_hierarchy_is_bit_exact(deal):
     """3-level hierarchy, refined-level boxes dealt out to the ranks: copy plans cross ranks (pack / ncclSend-Recv / unpack)"""
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
            "--master-port", "29534", os.path.join(ROOT, "tools", "parity_multi_amr.py"), "3", deal]
-    r = subprocess.run(cmd, cwd=ROOT, capture_output=True, text=True, timeout=600)
+    r = subprocess.run(cmd, cwd=ROOT, capture_output=True, text=True, timeout=240)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
     assert '"head_bit_exact_per_level": [true, true, true]' in r.stdout
