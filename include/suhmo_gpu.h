@@ -400,7 +400,13 @@ int sg_set_relax_mode(sg_ctx* ctx, int mode);
    row per thread, 100*bx + rows = (bx, 256/bx) threads x rows per thread (rows 1|4|8|16|32); key 5: coarse rows per thread of the
    restriction kernel (1|4|8|16); key 6: 1 = halo exchanges of the smoother stay on the main stream (no overlap with the interior
    part of the sweep; N > 1 only); key 7: 1 = refined (patch-table) levels keep the exchange-per-colour flow instead of the fused
-   per-patch sweep */
+   per-patch sweep; key 8: cells per thread and batch of the per-patch sweep (1 default | 2 | 4); key 9: 1 = the V-cycle driver runs the
+   reference's own sequence on the base level under a finer one (AMROperator, reflux, axby, AMROperatorNF, incr, whole-level
+   correction) instead of the fused composite sweeps; key 10: preferred shared-memory carve-out of the per-patch sweep in percent;
+   key 11: 3 = per-patch sweep compiled for 3 CTAs per SM (80 registers) instead of 4 (64); key 12: 1 = one-pass UpdateOperator kernel
+   on one-patch levels; key 13: 2 = no CUDA-graph capture of the V-cycle at N > 1; key 14: threads per tile of the L2-resident tile
+   smoother (256 | 512 | 1024); key 15: 1 = tile smoother off; key 16: 1 = the implicit gap solve's smoother keeps the per-colour flow;
+   key 17: 1 = its tile smoother does one iteration per launch instead of two.  Keys 0..31. */
 int sg_set_tuning(sg_ctx* ctx, int key, int value);
 
 /* ------------------------------------------------------------------ implicit gap-height solve ------------- */

@@ -71,7 +71,7 @@ struct sg_ctx {
   cudaStream_t comm_stream = nullptr;    // nranks > 1: halo exchanges that overlap the interior part of a sweep run here
   cudaEvent_t ev_comm[2] = {nullptr, nullptr};
   std::vector<struct sg_solver*> solvers; // live head solvers: their captured graphs (which hold NCCL kernels at N > 1) go before the communicator
-  int tune[16] = {0}; // experiment knobs (sg_set_tuning): 0 rows per warp, 1 CTAs per SM of the fused sweep
+  int tune[32] = {0}; // experiment knobs (sg_set_tuning): 0 rows per warp, 1 CTAs per SM of the fused sweep
   SgNccl nccl;
   // reduction scratch
   double* d_partial = nullptr;
@@ -340,7 +340,7 @@ extern "C" int sg_ctx_event_elapsed_ms(sg_ctx* c, int slot0, int slot1, double* 
   return SG_OK;
 }
 extern "C" int sg_set_tuning(sg_ctx* c, int key, int value) {
-  REQUIRE(c && key >= 0 && key < 16, "sg_set_tuning: key 0..15");
+  REQUIRE(c && key >= 0 && key < 32, "sg_set_tuning: key 0..31");
   c->tune[key] = value;
   return SG_OK;
 }
@@ -1391,8 +1391,9 @@ static int relax_impl(sg_op* op, sg_field* phi, const sg_field* rhs, int iterati
         f.phi_in = phi->p();
         f.phi_out = scratch->p();
         dim3 tg((L->nx + GT_TX - 1) / GT_TX, (L->ny + GT_TY - 1) / GT_TY);
-        if (a.has_a) LAUNCH(c, (k_gsrb_tile<1, 4>), tg, B2D, f);
-        else LAUNCH(c, (k_gsrb_tile<0, 4>), tg, B2D, f);
+        const int nt = c->tune[14] >= 256 ? c->tune[14] : 1024; // threads per tile (tune key 14: 256 / 512 / 1024)
+        if (a.has_a) { if (nt == 256) LAUNCH(c, (k_gsrb_tile<1, 4, 256>), tg, 256, f); else if (nt == 512) LAUNCH(c, (k_gsrb_tile<1, 4, 512>), tg, 512, f); else LAUNCH(c, (k_gsrb_tile<1, 4, 1024>), tg, 1024, f); }
+        else { if (nt == 256) LAUNCH(c, (k_gsrb_tile<0, 4, 256>), tg, 256, f); else if (nt == 512) LAUNCH(c, (k_gsrb_tile<0, 4, 512>), tg, 512, f); else LAUNCH(c, (k_gsrb_tile<0, 4, 1024>), tg, 1024, f); }
         std::swap(phi->base, scratch->base);
         it += 4;
         continue;
@@ -2253,7 +2254,7 @@ static int amr_vcycle(sg_solver* s, sg_field* const* phi, sg_field* const* rhs, 
   sg_field* rl = ilev == l_max ? rhs[ilev] : s->aresid[ilev];
   // relaxNF = QuadCFInterp + levelGSRB; its closing exchange + homogeneous BC fill are dead stores here (see relax_impl)
   SGCALL(cf_interp_impl(op, phi[ilev], phi[ilev - 1]));
-  SGCALL(relax_impl(op, phi[ilev], rl, sp->pre, c->tune[14] == 1));
+  SGCALL(relax_impl(op, phi[ilev], rl, sp->pre, false));
   // phi[ilev-1] <- average of phi[ilev] on the covered region (AMRRestrictS with skip_res), kept as the FAS reference state
   SGCALL(amr_restrict_impl(op, s->aresC[ilev], phi[ilev], phi[ilev], phi[ilev - 1], s->ascratch[ilev], 1, false));
   SGCALL(run_plan(c, phi[ilev - 1]->cb(), s->aresC[ilev]->cb(), op->link->t2c));
@@ -2283,7 +2284,7 @@ static int amr_vcycle(sg_solver* s, sg_field* const* phi, sg_field* const* rhs, 
   // AMRProlongS_2 of phi[ilev-1] - saved, with the operator's scratch standing in for m_resC
   SGCALL(amr_prolong_impl(op, phi[ilev], phi[ilev - 1], opc, 1, s->asave[ilev]));
   SGCALL(cf_interp_impl(op, phi[ilev], phi[ilev - 1]));
-  return relax_impl(op, phi[ilev], rl, sp->post, c->tune[14] == 1);
+  return relax_impl(op, phi[ilev], rl, sp->post, false);
 }
 static int vcycle(sg_solver* s, sg_field* const* phi, sg_field* const* rhs, int l_max, const sg_solver_params* sp, int iter) {
   if (l_max == 0) {
@@ -2363,7 +2364,7 @@ static int run_cycle(sg_solver* s, sg_field* const* phi, sg_field* const* rhs, i
   // level and depth: a public relax with an odd sweep count on ANOTHER field of the same layout hands that field the scratch the
   // graph would still write to.
   std::vector<long long> key = {l_max, sp->pre, sp->post, sp->bottom, c->relax_mode, (long long)(size_t)c->stream};
-  for (int k = 0; k < 16; k++) key.push_back(c->tune[k]);
+  for (int k = 0; k < 32; k++) key.push_back(c->tune[k]);
   auto scratch_of = [](const sg_layout* L) { return (long long)(size_t)((!L->ws.empty() && L->ws[0]) ? L->ws[0]->base : nullptr); };
   for (int l = 0; l <= l_max; l++) { key.push_back((long long)(size_t)phi[l]->base); key.push_back((long long)(size_t)rhs[l]->base); }
   for (sg_op* op : s->aops) {

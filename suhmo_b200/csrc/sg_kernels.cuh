@@ -914,8 +914,8 @@ __global__ void __launch_bounds__(256) k_apply(double* __restrict__ out, const d
 // arithmetic as gs_update / GSRBHELMHOLTZVCNL2D.  x sides must be physical; y sides physical or ghost rows of depth 2K in memory.
 #define GT_TX 64
 #define GT_TY 32
-template <int HAS_A, int K>
-__global__ void __launch_bounds__(256) k_gsrb_tile(FusedArgs f) {
+template <int HAS_A, int K, int NT>
+__global__ void __launch_bounds__(NT) k_gsrb_tile(FusedArgs f) {
   constexpr int H = 2 * K, W = GT_TX + 2 * H, HT = GT_TY + 2 * H;
   __shared__ double t[HT][W + 1];
   const OpArgs& a = f.a;
@@ -926,8 +926,8 @@ __global__ void __launch_bounds__(256) k_gsrb_tile(FusedArgs f) {
   // existing cells held by this CTA: [ib, ie) x [jb, je); an edge is closed when it is a physical side of the level
   const int ib = max(x0, 0), ie = min(x0 + W, nx), jb = max(y0, ghlo ? -H : 0), je = min(y0 + HT, ghhi ? ny + H : ny);
   const bool open_l = ib > 0, open_r = ie < nx, open_b = !(jb == 0 && !ghlo), open_t = !(je == ny && !ghhi);
-  const int tid = threadIdx.y * blockDim.x + threadIdx.x;
-  for (int q = tid; q < W * HT; q += 256) {
+  const int tid = threadIdx.x;
+  for (int q = tid; q < W * HT; q += NT) {
     const int lj = q / W, li = q - lj * W, gi = x0 + li, gj = y0 + lj;
     t[lj][li] = (gi >= ib && gi < ie && gj >= jb && gj < je) ? f.phi_in[(ptrdiff_t)gj * P + gi] : 0.0;
   }
@@ -938,7 +938,7 @@ __global__ void __launch_bounds__(256) k_gsrb_tile(FusedArgs f) {
   for (int d = 1; d <= 2 * K; d++) {
     const int pass = (d - 1) & 1;
     const int il = open_l ? ib + d : ib, ir = open_r ? ie - d : ie, jl = open_b ? jb + d : jb, jr = open_t ? je - d : je; // updatable box
-    for (int q = tid; q < hw * HT; q += 256) {
+    for (int q = tid; q < hw * HT; q += NT) {
       const int lj = q / hw, gj = y0 + lj;
       const int li = 2 * (q - lj * hw) + ((gpar + x0 + gj + pass) & 1), gi = x0 + li;
       if (li >= W || gi < il || gi >= ir || gj < jl || gj >= jr) continue;
@@ -960,7 +960,7 @@ __global__ void __launch_bounds__(256) k_gsrb_tile(FusedArgs f) {
     }
     __syncthreads();
   }
-  for (int q = tid; q < GT_TX * GT_TY; q += 256) {
+  for (int q = tid; q < GT_TX * GT_TY; q += NT) {
     const int lj = q / GT_TX, li = q - lj * GT_TX, gi = x0 + H + li, gj = y0 + H + lj;
     if (gi < nx && gj < ny) f.phi_out[(ptrdiff_t)gj * P + gi] = t[H + lj][H + li];
   }

@@ -62,6 +62,61 @@ __global__ void __launch_bounds__(256) k_lin_gsrb_color(double* __restrict__ phi
   phi[o] = pc - lin_lambda(a, ac, bw, be, bs, bn) * (lof - rhs[o]);
 }
 
+// K iterations of VCAMRPoissonOp2::levelGSRB in ONE launch, out of place, in shared-memory tiles: the structure of k_gsrb_tile
+// (sg_kernels.cuh) with this operator's point update.  The reference exchanges and applies FixedNeumBCFill before each colour; here a
+// CTA recomputes a halo of 2K cells instead (ghost rows of depth 2K from the neighbouring GPU / periodic image are exchanged once
+// per launch), and a physical-boundary ghost value is the first interior cell's, i.e. the updated cell's own value, taken on the fly.
+// One read of phi and of the coefficients per K iterations instead of two passes over every array per iteration.
+#define LT_TX 64
+#define LT_TY 32
+template <int K>
+__global__ void __launch_bounds__(512) k_lin_gsrb_tile(const double* __restrict__ pin, double* __restrict__ pout, const double* __restrict__ rhs,
+                                                       LinArgs a) {
+  constexpr int H = 2 * K, W = LT_TX + 2 * H, HT = LT_TY + 2 * H, NT = 512;
+  __shared__ double t[HT][W + 1];
+  const int nx = a.g.nx, ny = a.g.ny;
+  const ptrdiff_t P = a.g.pitch;
+  const int x0 = (int)blockIdx.x * LT_TX - H, y0 = (int)blockIdx.y * LT_TY - H;
+  const bool gxlo = a.g.kind[0] == SK_GHOST, gxhi = a.g.kind[1] == SK_GHOST, gylo = a.g.kind[2] == SK_GHOST, gyhi = a.g.kind[3] == SK_GHOST;
+  const int ib = max(x0, gxlo ? -H : 0), ie = min(x0 + W, gxhi ? nx + H : nx), jb = max(y0, gylo ? -H : 0), je = min(y0 + HT, gyhi ? ny + H : ny);
+  const bool open_l = !(ib == 0 && !gxlo), open_r = !(ie == nx && !gxhi), open_b = !(jb == 0 && !gylo), open_t = !(je == ny && !gyhi);
+  const int tid = threadIdx.x;
+  for (int q = tid; q < W * HT; q += NT) {
+    const int lj = q / W, li = q - lj * W, gi = x0 + li, gj = y0 + lj;
+    t[lj][li] = (gi >= ib && gi < ie && gj >= jb && gj < je) ? pin[(ptrdiff_t)gj * P + gi] : 0.0;
+  }
+  __syncthreads();
+  const int gpar = (a.g.glo0 + a.g.glo1) & 1;
+  const int hw = (W + 1) / 2;
+#pragma unroll 1
+  for (int d = 1; d <= 2 * K; d++) {
+    const int pass = (d - 1) & 1;
+    const int il = open_l ? ib + d : ib, ir = open_r ? ie - d : ie, jl = open_b ? jb + d : jb, jr = open_t ? je - d : je;
+    for (int q = tid; q < hw * HT; q += NT) {
+      const int lj = q / hw, gj = y0 + lj;
+      const int li = 2 * (q - lj * hw) + ((gpar + x0 + gj + pass) & 1), gi = x0 + li;
+      if (li >= W || gi < il || gi >= ir || gj < jl || gj >= jr) continue;
+      const ptrdiff_t o = (ptrdiff_t)gj * P + gi;
+      const double pc = t[lj][li];
+      double pw = li > 0 ? t[lj][li - 1] : 0.0, pe = li < W - 1 ? t[lj][li + 1] : 0.0, ps = lj > 0 ? t[lj - 1][li] : 0.0, pn = lj < HT - 1 ? t[lj + 1][li] : 0.0;
+      // FixedNeumBCFill on every non-periodic domain side: ghost = first interior cell
+      if (gi == 0 && !gxlo) pw = pc;
+      if (gi == nx - 1 && !gxhi) pe = pc;
+      if (gj == 0 && !gylo) ps = pc;
+      if (gj == ny - 1 && !gyhi) pn = pc;
+      const double bw = a.bX[o], be = a.bX[o + 1], bs = a.bY[o], bn = a.bY[o + P];
+      const double ac = a.aC[o];
+      const double lof = lin_lofphi(a, ac, pc, pw, pe, ps, pn, bw, be, bs, bn);
+      t[lj][li] = pc - lin_lambda(a, ac, bw, be, bs, bn) * (lof - rhs[o]);
+    }
+    __syncthreads();
+  }
+  for (int q = tid; q < LT_TX * LT_TY; q += NT) {
+    const int lj = q / LT_TX, li = q - lj * LT_TX, gi = x0 + H + li, gj = y0 + H + lj;
+    if (gi < nx && gj < ny) pout[(ptrdiff_t)gj * P + gi] = t[H + lj][H + li];
+  }
+}
+
 // MODE 0: out = L(phi); 1: out = rhs - L(phi); 2: as 1 plus max|out| into *norm_bits; 3: out = rhs*lambda (preCond's first guess);
 // 4: out = lambda (inspection)
 template <int MODE>
