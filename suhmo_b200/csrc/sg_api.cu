@@ -61,6 +61,7 @@ struct Box {
 };
 static inline int fdiv(int a, int r) { return a >= 0 ? a / r : -((-a + r - 1) / r); }
 
+#define SG_MAXPART (1u << 20) // blocks of one residual sweep whose maxima are folded by k_max_partials (more: atomics)
 struct sg_ctx {
   int device = 0, rank = 0, nranks = 1, num_sms = 148;
   cudaStream_t stream = nullptr;
@@ -76,6 +77,7 @@ struct sg_ctx {
   // reduction scratch
   double* d_partial = nullptr;
   size_t partial_cap = 0;
+  unsigned long long* d_maxpart = nullptr; // per-block maxima of the residual sweeps (k_max_partials), SG_MAXPART entries
   double* d_scalar = nullptr;            // [0..127] device scalars (as doubles / bit patterns)
   double* h_scalar = nullptr;            // pinned mirror
   double* h_stage = nullptr; size_t h_stage_cap = 0; // pinned staging for batched upload/download
@@ -273,6 +275,7 @@ extern "C" int sg_ctx_create(sg_ctx** out, int device, int rank, int nranks, con
   CK(cudaDeviceGetAttribute(&c->num_sms, cudaDevAttrMultiProcessorCount, device));
   CK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
   CK(cudaMalloc(&c->d_scalar, 128 * sizeof(double)));
+  CK(cudaMalloc(&c->d_maxpart, SG_MAXPART * sizeof(unsigned long long)));
   CK(cudaMemsetAsync(c->d_scalar, 0, 128 * sizeof(double), c->stream));
   CK(cudaMallocHost(&c->h_scalar, 128 * sizeof(double)));
   if (nranks > 1) {
@@ -300,7 +303,7 @@ extern "C" int sg_ctx_destroy(sg_ctx* c) {
   if (c->comm_stream) { cudaStreamSynchronize(c->comm_stream); cudaStreamDestroy(c->comm_stream); }
   for (int k = 0; k < 2; k++) if (c->ev_comm[k]) cudaEventDestroy(c->ev_comm[k]);
   c->nccl.destroy();
-  cudaFree(c->d_partial); cudaFree(c->d_scalar); cudaFreeHost(c->h_scalar);
+  cudaFree(c->d_partial); cudaFree(c->d_maxpart); cudaFree(c->d_scalar); cudaFreeHost(c->h_scalar);
   cudaFreeHost(c->h_stage); cudaFree(c->d_stage); cudaFree(c->d_segs);
   if (c->own_stream) cudaStreamDestroy(c->stream);
   delete c;
@@ -1519,6 +1522,8 @@ static int apply_impl(sg_op* op, sg_field* out, sg_field* phi, const sg_field* r
   if (tall && c->tune[4] >= 100) { bx = c->tune[4] / 100; rows = c->tune[4] % 100; }
   dim3 blk(bx, 256 / bx);
   dim3 g((L->nx + bx - 1) / bx, (L->ny + blk.y * rows - 1) / (blk.y * rows));
+  const size_t nblk = (size_t)g.x * g.y;
+  unsigned long long* part = (mode == 2 || mode == 3 || mode == 6) && nblk <= SG_MAXPART && nblk >= 64 ? c->d_maxpart : nullptr;
 #define APPLY_LAUNCH(M, ...)                                                     \
   do {                                                                           \
     if (rows == 1) LAUNCH(c, (k_apply<M, 1>), g, blk, __VA_ARGS__);              \
@@ -1532,12 +1537,13 @@ static int apply_impl(sg_op* op, sg_field* out, sg_field* phi, const sg_field* r
   else if (mode == 1) APPLY_LAUNCH(1, out->p(), phi->p(), rhs->p(), a, nb);
   else if (mode == 4) APPLY_LAUNCH(4, out->p(), phi->p(), nullptr, a, nb);
   else if (mode == 5) APPLY_LAUNCH(5, out->p(), phi->p(), rhs->p(), a, nb);
-  else if (mode == 6) APPLY_LAUNCH(6, nullptr, phi->p(), rhs->p(), a, nb, special + ((ptrdiff_t)SG_YOFF * L->pitch + SG_XOFF)); // the map is addressed from the component base
+  else if (mode == 6) APPLY_LAUNCH(6, nullptr, phi->p(), rhs->p(), a, nb, special + ((ptrdiff_t)SG_YOFF * L->pitch + SG_XOFF), part); // the map is addressed from the component base
   else {
     CK(cudaMemsetAsync(nb, 0, sizeof(double), c->stream));
-    if (mode == 3) APPLY_LAUNCH(3, nullptr, phi->p(), rhs->p(), a, nb);
-    else APPLY_LAUNCH(2, out->p(), phi->p(), rhs->p(), a, nb);
+    if (mode == 3) APPLY_LAUNCH(3, nullptr, phi->p(), rhs->p(), a, nb, nullptr, part);
+    else APPLY_LAUNCH(2, out->p(), phi->p(), rhs->p(), a, nb, nullptr, part);
   }
+  if (part) LAUNCH(c, k_max_partials, 1, 1024, part, nblk, nb);
 #undef APPLY_LAUNCH
   return SG_OK;
 }

@@ -246,7 +246,7 @@ __global__ void __launch_bounds__(256, MINB) k_gsrb_patch(const double* __restri
 template <int MODE>
 __global__ void __launch_bounds__(256) k_apply_g(double* __restrict__ outb, const double* __restrict__ phib,
                                                  const double* __restrict__ rhsb, const PatchG* __restrict__ tab, OpArgsG a,
-                                                 unsigned long long* norm_bits) {
+                                                 unsigned long long* norm_bits, unsigned long long* partial = nullptr) {
   const PatchG g = tab[blockIdx.z];
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   int j = blockIdx.y * blockDim.y + threadIdx.y;
@@ -263,7 +263,7 @@ __global__ void __launch_bounds__(256) k_apply_g(double* __restrict__ outb, cons
     r = MODE == 0 ? lof : rhsb[o] - (lof);
     outb[o] = r;
   }
-  if (MODE == 2) block_max_to_global(fabs(r), norm_bits);
+  if (MODE == 2) block_max_to_global(fabs(r), norm_bits, partial);
 }
 
 // vector ops over valid cells (whole != 0: ghost ring of width ng included). op as k_vec.

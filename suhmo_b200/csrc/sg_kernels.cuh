@@ -834,7 +834,10 @@ __global__ void __launch_bounds__(128, 3) k_gsrb_pair(FusedArgs f) {
 // ------------------------------------------------------------------------------------------------
 // max that keeps a NaN (fmax drops it): a diverged relaxation must show up in the residual norm, not vanish from it
 __device__ __forceinline__ double nanmax(double a, double b) { return a != a ? a : (b != b ? b : fmax(a, b)); }
-__device__ __forceinline__ void block_max_to_global(double v, unsigned long long* dst) {
+// partial != nullptr: the block's maximum goes to partial[linear block index] (k_max_partials folds them into *dst afterwards) instead
+// of an atomic on *dst -- a residual sweep has 10^4..10^5 blocks, and that many operations on one address cost more than the sweep's
+// own norm arithmetic (measured: 0.58 vs 0.28 ms for the 17.7 M-cell level's residual with / without the norm)
+__device__ __forceinline__ void block_max_to_global(double v, unsigned long long* dst, unsigned long long* partial = nullptr) {
   // non-negative doubles order like their bit patterns (+NaN above +inf, so atomicMax keeps a NaN too)
   for (int o = 16; o > 0; o >>= 1) v = nanmax(v, __shfl_xor_sync(0xffffffffu, v, o));
   __shared__ double wmax[32];
@@ -846,10 +849,23 @@ __device__ __forceinline__ void block_max_to_global(double v, unsigned long long
     v = lane < nw ? wmax[lane] : 0.0;
     for (int o = 16; o > 0; o >>= 1) v = nanmax(v, __shfl_xor_sync(0xffffffffu, v, o));
     if (lane == 0) {
-      // most blocks do not raise the running maximum: look before the read-modify-write (thousands of same-address atomics serialise)
       const unsigned long long bits = (unsigned long long)__double_as_longlong(fabs(v));
-      if (bits > *(volatile unsigned long long*)dst) atomicMax(dst, bits);
+      if (partial) partial[((size_t)blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x] = bits;
+      else if (bits > *(volatile unsigned long long*)dst) atomicMax(dst, bits); // look before the read-modify-write
     }
+  }
+}
+__global__ void __launch_bounds__(1024) k_max_partials(const unsigned long long* __restrict__ partial, size_t n, unsigned long long* __restrict__ dst) {
+  __shared__ unsigned long long sh[32];
+  unsigned long long m = 0; // bit patterns of non-negative doubles order like the values; +NaN sits above +inf
+  for (size_t k = threadIdx.x; k < n; k += 1024) m = max(m, partial[k]);
+  for (int o = 16; o > 0; o >>= 1) m = max(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = m;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    m = sh[threadIdx.x];
+    for (int o = 16; o > 0; o >>= 1) m = max(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if (threadIdx.x == 0) atomicMax(dst, m);
   }
 }
 
@@ -871,7 +887,7 @@ __device__ __forceinline__ double lof_at(const OpArgs& a, const double* __restri
 template <int MODE, int ROWS>
 __global__ void __launch_bounds__(256) k_apply(double* __restrict__ out, const double* __restrict__ phi,
                                                const double* __restrict__ rhs, OpArgs a, unsigned long long* norm_bits,
-                                               const unsigned char* __restrict__ special = nullptr) {
+                                               const unsigned char* __restrict__ special = nullptr, unsigned long long* partial = nullptr) {
   // a block covers blockDim.x columns x blockDim.y*ROWS rows (ROWS > 1: fewer blocks and, for the norm modes, fewer
   // same-address atomics)
   int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -900,7 +916,7 @@ __global__ void __launch_bounds__(256) k_apply(double* __restrict__ out, const d
     }
     rmax = nanmax(rmax, fabs(r));
   }
-  if (MODE == 2 || MODE == 3 || MODE == 6) block_max_to_global(rmax, norm_bits);
+  if (MODE == 2 || MODE == 3 || MODE == 6) block_max_to_global(rmax, norm_bits, partial);
 }
 
 // ------------------------------------------------------------------------------------------------

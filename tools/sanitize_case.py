@@ -37,6 +37,25 @@ def main():
     mg = amr.AMRFASMultiGrid().define(gpu.factory, 3)
     mg.setSolverParameters(4, 4, 10, 1, 100, 1e-10, 1e-4, 1e-7)
     mg.solve(gpu.fields("head"), gpu.fields("rhs"), fixed_cycles=2)
+    # multi-level Picard body, moulin recharge, explicit gap update, regrid transfer (round-2 kernels)
+    from suhmo_b200.timestep_amr import AmrTimeStep
+    from tests.amr_picard import build_device
+    cfg.moulins = [(30000.0, 40000.0, 80.0, 3000.0), (70000.0, 20000.0, 40.0, 2500.0)]
+    st = build_device(ctx, cfg, lv)
+    ts = AmrTimeStep(st)
+    ts.begin_step()
+    ts.moulin_sources()
+    ts.picard_iteration(fixed_cycles=2)
+    ts.update_gap(1800.0)
+    st.ops[1].regridTransfer(st.S[1]["work"], st.S[1]["head"], st.S[0]["head"])
+    # implicit gap-height solve (tile smoother of the linear operator) on a level without periodic sides
+    cfg5 = syn.config("C5", 1)
+    boxes5 = syn.domain_split(cfg5.nx, cfg5.ny, cfg5.max_box_size, cfg5.block_factor)
+    from tests import gapsolve as gs
+    ogap = gs.OracleGap(cfg5, boxes5)
+    ggap = gs.GpuGap(ctx, ogap, None)
+    amr.SolveForGap_nl(ctx, [ggap.layout], [ggap.F["a"]], [ggap.F["bX"]], [ggap.F["bY"]], [], (ogap.dx, ogap.dx), [ggap.F["b"]], [ggap.F["rhs"]],
+                       ogap.beta, 1.0, 0)
     ctx.sync()
     print("sanitize_case: OK")
 
