@@ -333,6 +333,21 @@ def small_configs(ctx, amr, threads, cycles=20):
                     "cpu_ms_per_vcycle": cpu_ms, "cpu_threads": threads, "launches_per_vcycle": st.kernel_launches / cycles,
                     "resnorm_history_equal": bool(np.array_equal(ghist, ohist))})
         mg.destroy()
+    # BASELINE configs[4] at its native size: AMR_multiMoulins on a 256^2 base grid with two refined levels (grids from each arm's own
+    # tagging, the same Berger-Rigoutsos)
+    size = 256
+    levels = gpu_tile_hierarchy(0, wl.tile_config(size), 3)
+    gp = GpuProblem(ctx, wl.Problem(size, 1, "weak", levels), 0, pinned=False)
+    gp.mg.setSolverParameters(4, 4, 16, 1, 100, 1e-10, 1e-4, 1e-7)
+    _, gh0, _ = gp.mg.solve(gp.fields("head"), gp.fields("rhs"), fixed_cycles=3)
+    _, _, st = gp.mg.solve(gp.fields("head"), gp.fields("rhs"), fixed_cycles=cycles)
+    cp = CpuProblem(size, 3, threads, levels=levels)
+    _, _, oh0 = cp.solve(3, 16)
+    _, dt, _ = cp.solve(cycles, 16)
+    out.append({"config": "C5 (3-level AMR)", "grid": [size, size], "boxes": [int(len(b)) for b in levels], "gpu_ms_per_vcycle": st.device_ms / cycles,
+                "cpu_ms_per_vcycle": 1e3 * dt / cycles, "cpu_threads": threads, "launches_per_vcycle": st.kernel_launches / cycles,
+                "resnorm_history_equal": bool(np.array_equal(gh0, oh0))})
+    gp.mg.destroy()
     return out
 
 

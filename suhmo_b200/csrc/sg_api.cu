@@ -2,6 +2,7 @@
 // VCAMRNonLinearPoissonOp surface, the factory and the device-resident FAS multigrid driver.
 // Host logic only; all arithmetic is in sg_kernels.cuh.  There is no CPU fallback anywhere in this file.
 #include "../../include/suhmo_gpu.h"
+#include <nvtx3/nvToolsExt.h> // header-only NVTX 3: ranges cost a predicted branch unless a profiler injected itself
 #include "sg_kernels.cuh"
 #include "sg_general.cuh"
 #include "sg_picard.cuh"
@@ -22,6 +23,11 @@
 // ------------------------------------------------------------------------------------------------
 // errors
 // ------------------------------------------------------------------------------------------------
+// NVTX range for the timeline views of Nsight Systems / Compute (V-cycle, level relaxations, operator update, residual norm)
+struct NvtxRange {
+  explicit NvtxRange(const char* name) { nvtxRangePushA(name); }
+  ~NvtxRange() { nvtxRangePop(); }
+};
 static thread_local std::string g_err;
 static int fail(int code, const char* fmt, ...) {
   char buf[1024];
@@ -1317,6 +1323,7 @@ static int relax_swaps(const sg_op* op, int iterations) { // buffer swaps of one
 // phi_valid: depth to which the caller has just exchanged phi's ghost rows (0: unknown); the first sweep's exchange is skipped when
 // that covers it
 static int relax_impl(sg_op* op, sg_field* phi, const sg_field* rhs, int iterations, bool trailing = true, int phi_valid = 0) {
+  NvtxRange nvtx_("levelGSRB");
   sg_layout* L = op->lay;
   sg_ctx* c = op->ctx;
   if (!L->has_local || iterations <= 0) return SG_OK;
@@ -1646,6 +1653,7 @@ extern "C" int sg_op_prolongIncrement(sg_op* op, sg_field* phi, const sg_field* 
 extern "C" int sg_op_UpdateOperator(sg_op* op, sg_field* phi, const sg_field* phi_coarse, int depth, int amr_fasmg_iter, int homogeneous) {
   (void)depth; (void)amr_fasmg_iter;
   REQUIRE(op, "sg_op_UpdateOperator: null op");
+  NvtxRange nvtx_("UpdateOperator");
   if (homogeneous) return fail(SG_ERR_ABORT, "VCAMRNonLinearPoissonOp::UpdateOperator homogeneous");
   SGCALL(check_same(op, phi, "UpdateOperator(phi)"));
   sg_layout* L = op->lay;
@@ -2217,6 +2225,7 @@ static int average_all_depths(sg_solver* s) {
   return SG_OK;
 }
 static int mg_cycle(sg_solver* s, int depth, sg_field* phi, sg_field* rhs, const sg_solver_params* sp, int phi_valid = 0) {
+  NvtxRange nvtx_("MultiGrid::cycle");
   sg_op* op = s->ops[depth];
   int nd = (int)s->ops.size();
   if (depth == nd - 1) return relax_impl(op, phi, rhs, sp->bottom, false, phi_valid);
@@ -2246,6 +2255,7 @@ static int amr_residual_level(sg_solver* s, sg_field* const* phi, sg_field* cons
 }
 // AMRFASMultiGrid::VCycle (absent fork; INFERRED, identical to oracle/suhmo_oracle.c:amr_vcycle -- see DESIGN.md)
 static int amr_vcycle(sg_solver* s, sg_field* const* phi, sg_field* const* rhs, int ilev, int l_max, const sg_solver_params* sp, int iter) {
+  NvtxRange nvtx_("AMRFASMultiGrid::VCycle level");
   sg_op* op = s->aops[ilev];
   if (op->update_operator) SGCALL(sg_op_UpdateOperator(op, phi[ilev], ilev > 0 ? phi[ilev - 1] : nullptr, ilev, iter, 0));
   if (ilev == 0) {
@@ -2305,6 +2315,7 @@ static int vcycle(sg_solver* s, sg_field* const* phi, sg_field* const* rhs, int 
 // computeAMRResidual: max over levels of the max-norm of the composite residual (covered cells zeroed), left in
 // d_scalar[slot] on all ranks
 static int residual_norm(sg_solver* s, sg_field* const* phi, sg_field* const* rhs, int l_max, int slot) {
+  NvtxRange nvtx_("computeAMRResidual + norm");
   if (l_max == 0) {
     SGCALL(apply_impl(s->ops[0], s->resid, phi[0], rhs[0], 0, 3, slot)); // max-norm only, the residual itself is not needed
     return global_reduce(s->ctx, slot, true);
@@ -2424,6 +2435,7 @@ static int run_cycle(sg_solver* s, sg_field* const* phi, sg_field* const* rhs, i
 extern "C" int sg_solver_solve(sg_solver* s, sg_field* const* phi, sg_field* const* rhs, int l_max, int l_base,
                                const sg_solver_params* sp, double* hist, sg_solve_stats* stats) {
   REQUIRE(s && phi && rhs && sp && phi[0] && rhs[0], "sg_solver_solve: null");
+  NvtxRange nvtx_("SolveForHead_nl");
   REQUIRE(l_base == 0 && l_max >= 0 && l_max < s->num_levels, "sg_solver_solve: l_base must be 0 and l_max below the number of levels defined");
   sg_ctx* c = s->ctx;
   for (int l = 0; l <= l_max; l++) {
