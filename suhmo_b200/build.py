@@ -5,7 +5,7 @@ import subprocess
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(_HERE)
-SRC = [os.path.join(_HERE, "csrc", f) for f in ("sg_api.cu", "sg_kernels.cuh", "sg_general.cuh", "sg_picard.cuh", "sg_general_host.inc",
+SRC = [os.path.join(_HERE, "csrc", f) for f in ("sg_api.cu", "sg_kernels.cuh", "sg_twin.cuh", "sg_general.cuh", "sg_picard.cuh", "sg_general_host.inc",
                                                  "sg_picard_host.inc", "sg_regrid.inc", "sg_linear.cuh", "sg_linear_host.inc", "sg_nccl.h")]
 HDR = os.path.join(ROOT, "include", "suhmo_gpu.h")
 SO = os.path.join(_HERE, "lib", "libsuhmo_gpu.so")

@@ -3,7 +3,9 @@
 // Host logic only; all arithmetic is in sg_kernels.cuh.  There is no CPU fallback anywhere in this file.
 #include "../../include/suhmo_gpu.h"
 #include <nvtx3/nvToolsExt.h> // header-only NVTX 3: ranges cost a predicted branch unless a profiler injected itself
+#include <type_traits>
 #include "sg_kernels.cuh"
+#include "sg_twin.cuh"
 #include "sg_general.cuh"
 #include "sg_picard.cuh"
 #include "sg_linear.cuh"
@@ -354,7 +356,7 @@ extern "C" int sg_set_tuning(sg_ctx* c, int key, int value) {
   return SG_OK;
 }
 extern "C" int sg_set_relax_mode(sg_ctx* c, int mode) {
-  REQUIRE(c && mode >= 0 && mode <= 4, "sg_set_relax_mode");
+  REQUIRE(c && mode >= 0 && mode <= 5, "sg_set_relax_mode");
   c->relax_mode = mode;
   return SG_OK;
 }
@@ -1336,7 +1338,7 @@ static int relax_impl(sg_op* op, sg_field* phi, const sg_field* rhs, int iterati
     sg_field* scratch;
     SGCALL(ws_field(L, 0, 1, &scratch));
     // temporal blocking recomputes a 4-cell ring: periodic images inside the patch must then be at least 4 cells away
-    const bool can2 = (c->relax_mode == 3 || c->relax_mode == 4) && (!L->wrap_local[0] || L->nx >= 4) && (!L->wrap_local[1] || L->ny >= 4) && L->ny >= 4;
+    const bool can2 = (c->relax_mode == 3 || c->relax_mode == 4 || c->relax_mode == 5) && (!L->wrap_local[0] || L->nx >= 4) && (!L->wrap_local[1] || L->ny >= 4) && L->ny >= 4;
     // Communication-avoiding relaxation (mode 1): instead of exchanging two ghost rows before every sweep, exchange 2k rows
     // once per k <= 4 sweeps and let sweep s also update the ghost rows it still needs (2(k-1-s) per side) -- the same
     // arithmetic on the same values as their owner performs, so the result is unchanged while the NCCL (or wrap) calls drop
@@ -1357,20 +1359,23 @@ static int relax_impl(sg_op* op, sg_field* phi, const sg_field* rhs, int iterati
       CK(cudaFuncSetAttribute(k_gsrb_stream2<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 * GS2_STAGES * 9 * 512));
       CK(cudaFuncSetAttribute(k_gsrb_pair<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * (GP_STAGES * 8 * 512 + 1024)));
       CK(cudaFuncSetAttribute(k_gsrb_pair<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * (GP_STAGES * 9 * 512 + 1024)));
+      CK(cudaFuncSetAttribute((k_gsrb_twin<0, 0>), cudaFuncAttributeMaxDynamicSharedMemorySize, 4 * TW_STAGES * 8 * 512));
+      CK(cudaFuncSetAttribute((k_gsrb_twin<0, 1>), cudaFuncAttributeMaxDynamicSharedMemorySize, 4 * TW_STAGES * 8 * 512));
+      CK(cudaFuncSetAttribute((k_gsrb_twin<1, 1>), cudaFuncAttributeMaxDynamicSharedMemorySize, 4 * TW_STAGES * 9 * 512));
       c->smem_attr_set = true;
     }
     // Segments of rows per warp.  Measured on B200 (tools/relax_bench.py): many short segments beat one resident wave
     // (warps marching in lock-step), 32-64 rows per warp is the plateau on HBM-sized levels, and L2-resident levels want
     // the shortest segments that still amortise the load-only steps of a segment (4 for one iteration, 9 for two).
-    auto plan = [&](int kind) { // 1 stream, 2 fused, 3 stream2, 4 producer/consumer pairs
-      const int cols = kind == 3 ? GS2_COLS : kind == 4 ? GP_COLS : kind == 1 ? GS_COLS : FUSED_COLS;
+    auto plan = [&](int kind) { // 1 stream, 2 fused, 3 stream2, 4 producer/consumer pairs, 5 twin
+      const int cols = kind == 3 ? GS2_COLS : kind == 4 ? GP_COLS : kind == 5 ? TW_COLS : kind == 1 ? GS_COLS : FUSED_COLS;
       f.nstrips = (L->nx + cols - 1) / cols;
-      int minb = kind == 3 ? 2 : (kind == 1 || kind == 4) ? 3 : (c->tune[1] == 3 ? 3 : 4);
+      int minb = (kind == 3 || kind == 5) ? 2 : (kind == 1 || kind == 4) ? 3 : (c->tune[1] == 3 ? 3 : 4);
       int capacity = c->num_sms * minb * (kind == 4 ? 2 : 4); // resident warps (pairs for kind 4) of 128-thread CTAs
       int nsegs;
-      const int nrows = kind == 1 ? f.yhi - f.ylo : L->ny;
+      const int nrows = (kind == 1 || kind == 5) ? f.yhi - f.ylo : L->ny;
       if (c->tune[0] > 0) nsegs = (nrows + c->tune[0] - 1) / c->tune[0];
-      else if (kind == 1 || kind == 3 || kind == 4) {
+      else if (kind == 1 || kind == 3 || kind == 4 || kind == 5) {
         long long rows = ((long long)f.nstrips * nrows) / (4LL * capacity);
         rows = kind != 1 ? std::max(16LL, std::min(96LL, rows)) : std::max((long long)(c->tune[15] > 0 ? c->tune[15] : 8), std::min(48LL, rows));
         nsegs = (int)((nrows + rows - 1) / rows);
@@ -1409,7 +1414,7 @@ static int relax_impl(sg_op* op, sg_field* phi, const sg_field* rhs, int iterati
         continue;
       }
       const bool two = can2 && it + 2 <= iterations;
-      const int kind = two ? (c->relax_mode == 4 ? 4 : 3) : (c->relax_mode == 2 ? 2 : 1);
+      const int kind = two ? (c->relax_mode == 4 ? 4 : c->relax_mode == 5 ? 5 : 3) : (c->relax_mode == 2 ? 2 : 1);
       const int chunk = (wide && kind == 1) ? std::min(4, iterations - it) : 1;
       // N > 1: the exchange of a chunk runs on the communication stream while the first sweep updates the rows that do not
       // depend on ghost rows ([2, ny-2): a sweep over [a, b) reads rows [a-2, b+2)); the two boundary strips follow once the
@@ -1454,6 +1459,11 @@ static int relax_impl(sg_op* op, sg_field* phi, const sg_field* rhs, int iterati
         if (kind == 4) {
           if (a.has_a) k_gsrb_pair<1><<<blocks, 128, 2 * (GP_STAGES * 9 * 512 + 1024), c->stream>>>(f);
           else k_gsrb_pair<0><<<blocks, 128, 2 * (GP_STAGES * 8 * 512 + 1024), c->stream>>>(f);
+          c->launches++;
+        } else if (kind == 5) {
+          if (a.has_a) k_gsrb_twin<1, 1><<<blocks, 128, 4 * TW_STAGES * 9 * 512, c->stream>>>(f);
+          else if (a.use_mask || !a.prm.use_NL) k_gsrb_twin<0, 1><<<blocks, 128, 4 * TW_STAGES * 8 * 512, c->stream>>>(f);
+          else k_gsrb_twin<0, 0><<<blocks, 128, 4 * TW_STAGES * 8 * 512, c->stream>>>(f);
           c->launches++;
         } else if (kind == 3) {
           if (a.has_a) k_gsrb_stream2<1><<<blocks, 128, 4 * GS2_STAGES * 9 * 512, c->stream>>>(f);

@@ -43,7 +43,7 @@ def test_geometry_parity(gpu_ctx, geom):
     gpu = GpuSide(gpu_ctx, orc)
     oop, gop = orc.op(), gpu.factory.AMRnewOp(0)
     try:
-        for mode in (0, 1, 2, 3, 4):
+        for mode in (0, 1, 2, 3, 4, 5):
             gpu_ctx.set_relax_mode(mode)
             for n in (1, 2):
                 oop.relax(orc.F["head"], orc.F["rhs"], n)
@@ -70,7 +70,7 @@ def test_geometry_parity(gpu_ctx, geom):
     mg = gpu.amr.AMRFASMultiGrid().define(gpu.factory, 1)
     assert mg.depth == osolver.depth
     mg.setSolverParameters(4, 4, 10, 1, 100, 1e-10, 1e-4, 1e-7)
-    for mode in (1, 0, 3):
+    for mode in (1, 0, 3, 5):
         gpu_ctx.set_relax_mode(mode)
         it, ohist = osolver.solve(orc.F["head"], orc.F["rhs"], ob.make_solver_params(bottom=10, fixed_cycles=3))
         git, ghist, st = mg.solve([gpu.F["head"]], [gpu.F["rhs"]], fixed_cycles=3)

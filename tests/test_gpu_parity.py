@@ -44,10 +44,10 @@ def test_upload_download_roundtrip(gpu_ctx, name, scale, mb):
         assert np.array_equal(got[core], exp[core])
 
 
-@pytest.mark.parametrize("mode", [0, 1, 2, 3, 4])
+@pytest.mark.parametrize("mode", [0, 1, 2, 3, 4, 5])
 @pytest.mark.parametrize("name,scale,mb", CASES)
 def test_relax_bit_exact(gpu_ctx, name, scale, mb, mode):
-    """a1/a2/a8: levelGSRB with fused NL + lambda; generic colour passes (mode 0), cp.async-staged streaming sweep (mode 1), register-only fused sweep (mode 2), two iterations per sweep (mode 3)."""
+    """a1/a2/a8: levelGSRB with fused NL + lambda; generic colour passes (mode 0), cp.async-staged streaming sweep (mode 1), register-only fused sweep (mode 2), two iterations per sweep (modes 3, 4; mode 5 = the lean k_gsrb_twin with the deferred division slow path)."""
     cfg, orc, gpu = make(gpu_ctx, name, scale, mb)
     gpu_ctx.set_relax_mode(mode)
     try:
@@ -69,7 +69,7 @@ def test_relax_inhomogeneous_bc_values(gpu_ctx):
     orc.init_bcoef()
     gpu = GpuSide(gpu_ctx, orc)
     oop, gop = orc.op(), gpu.factory.AMRnewOp(0)
-    for mode in (0, 1, 2, 3, 4):
+    for mode in (0, 1, 2, 3, 4, 5):
         gpu_ctx.set_relax_mode(mode)
         oop.relax(orc.F["head"], orc.F["rhs"], 2)
         gop.relax(gpu.F["head"], gpu.F["rhs"], 2)
@@ -279,7 +279,7 @@ def test_helmholtz_alpha_and_linear_variants(gpu_ctx, name, scale, use_nl):
     orc.init_bcoef()
     gpu = GpuSide(gpu_ctx, orc)
     oop, gop = orc.op(), gpu.factory.AMRnewOp(0)
-    for mode in (0, 1, 3, 4):
+    for mode in (0, 1, 3, 4, 5):
         gpu_ctx.set_relax_mode(mode)
         oop.relax(orc.F["head"], orc.F["rhs"], 2)
         gop.relax(gpu.F["head"], gpu.F["rhs"], 2)

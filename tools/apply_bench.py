@@ -8,14 +8,21 @@ import sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 from suhmo_b200 import amr, synthetic as syn  # noqa: E402
-import bench  # noqa: E402
+
+
+def single_level_setup(size):
+    """the bench workload's base level alone (AMR_multiMoulins, size^2 cells, 64^2 boxes, one GPU)"""
+    from tools import workload as wl
+    cfg = wl.tile_config(size)
+    boxes = syn.domain_split(cfg.nx, cfg.ny, wl.BOX, cfg.block_factor)
+    owner = [0] * len(boxes)
+    return cfg, boxes, owner
 
 
 def main():
     size = int(sys.argv[1]) if len(sys.argv) > 1 else 8192
     ctx = amr.Context(device=0)
-    cfg = bench.bench_config(size, 1)
-    boxes, owner = bench.strip_boxes(cfg, 1)
+    cfg, boxes, owner = single_level_setup(size)
     g = syn.fields(cfg, ng=1)
     layout = amr.DisjointBoxLayout(ctx, boxes, (0, 0, cfg.nx - 1, cfg.ny - 1), cfg.periodic, owner)
     spec = dict(head=(1, 0), rhs=(0, 0), B=(1, 0), Pi=(1, 0), zb=(1, 0), mask=(1, 0), a=(0, 0), bX=(0, 1), bY=(0, 2))

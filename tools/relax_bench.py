@@ -10,14 +10,21 @@ import numpy as np
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 from suhmo_b200 import amr, synthetic as syn  # noqa: E402
-import bench  # noqa: E402
+
+
+def single_level_setup(size):
+    """the bench workload's base level alone (AMR_multiMoulins, size^2 cells, 64^2 boxes, one GPU)"""
+    from tools import workload as wl
+    cfg = wl.tile_config(size)
+    boxes = syn.domain_split(cfg.nx, cfg.ny, wl.BOX, cfg.block_factor)
+    owner = [0] * len(boxes)
+    return cfg, boxes, owner
 
 
 def main():
     size = int(sys.argv[1]) if len(sys.argv) > 1 else 8192
     ctx = amr.Context(device=0)
-    cfg = bench.bench_config(size, 1)
-    boxes, owner = bench.strip_boxes(cfg, 1)
+    cfg, boxes, owner = single_level_setup(size)
     g = syn.fields(cfg, ng=1)
     layout = amr.DisjointBoxLayout(ctx, boxes, (0, 0, cfg.nx - 1, cfg.ny - 1), cfg.periodic, owner)
     spec = dict(head=(1, 0), rhs=(0, 0), B=(1, 0), Pi=(1, 0), zb=(1, 0), mask=(1, 0), a=(0, 0), bX=(0, 1), bY=(0, 2))
@@ -32,7 +39,7 @@ def main():
     op0 = fac.AMRnewOp(0)
     op0.UpdateOperator(F["head"], None, 0, 0, False)
     res = []
-    variants = [(1, 0, 3), (1, 32, 3), (1, 64, 3), (4, 0, 3)]
+    variants = [] if os.environ.get("SG_ONLY") else [(1, 0, 3), (1, 32, 3), (1, 64, 3), (4, 0, 3)]
     for extra in os.environ.get("SG_VARIANTS", "").split(";"):
         if extra:
             variants.append(tuple(int(x) for x in extra.split(",")))
@@ -41,7 +48,7 @@ def main():
         ctx.set_tuning(0, rows)
         ctx.set_tuning(1, minb)
         op0.relax(F["head"], F["rhs"], 3)
-        n = 12
+        n = int(os.environ.get("SG_ITERS", "48"))
         ctx.event_record(0)
         op0.relax(F["head"], F["rhs"], n)
         ctx.event_record(1)
