@@ -205,6 +205,11 @@ int sg_op_lambda(sg_op* op, sg_field* lambda_out);
 /* 1 when this operator's kernels read the ice-mask array, 0 when the level holds no negative entry and the array is skipped
    (the mask only enters through `mask < 0` in COMPUTENONLINEARTERMS, src/AmrHydroF.ChF:40): decides the bytes a sweep moves */
 int sg_op_streams_mask(const sg_op* op, int* out);
+/* the kernel levelGSRB (VCAMRNonLinearPoissonOp.cpp:654-760) runs on this operator's level with the context's current relax mode
+   and knobs: colour passes of the reference flow, k_gsrb_stream (one iteration per launch), k_gsrb_twin (two), k_gsrb_tile
+   (four, L2-resident levels), k_gsrb_patch (refined levels) */
+enum { SG_SMOOTHER_COLOUR = 0, SG_SMOOTHER_STREAM = 1, SG_SMOOTHER_TWIN = 2, SG_SMOOTHER_TILE = 3, SG_SMOOTHER_PATCH = 4 };
+int sg_op_smoother_kind(const sg_op* op, int* out);
 /* createCoarser / create (src/AMRNonLinearPoissonOp.cpp:519-526,753-766) */
 int sg_op_createCoarser(sg_op* op, sg_field** coarse, const sg_field* fine, int ghosted);
 int sg_op_create(sg_op* op, sg_field** lhs, const sg_field* rhs);
@@ -389,10 +394,11 @@ int sg_solver_solve(sg_solver* s, sg_field* const* phi, sg_field* const* rhs, in
                     sg_solve_stats* stats);
 /* cell-updates one V-cycle performs with these parameters (metric of SURVEY.md 8d) */
 int sg_solver_cell_updates_per_cycle(const sg_solver* s, const sg_solver_params* sp, double* out);
-/* relax implementation switch for experiments/tests: 0 = separate colour passes (the reference's flow), 1 = streaming
-   red+black sweep staged through shared memory with cp.async, one iteration per sweep (default), 2 = first-generation register-only
-   fused sweep, 3 = two iterations per sweep (temporal blocking; issue-bound today) with mode 1 for an odd
-   remainder */
+/* relax implementation switch for experiments/tests: 0 = separate colour passes (the reference's flow), 1 = the default:
+   fused red+black sweeps staged through shared memory with cp.async -- two iterations per launch on HBM-sized levels
+   (k_gsrb_twin), four per launch in shared-memory tiles on L2-resident levels (k_gsrb_tile), one per launch for what remains
+   (k_gsrb_stream); 2 = first-generation register-only fused sweep; 3 / 4 / 5 = two iterations per launch on every level with
+   k_gsrb_stream2 / k_gsrb_pair (earlier temporal-blocking kernels, slower) / k_gsrb_twin, one per launch for an odd remainder */
 int sg_set_relax_mode(sg_ctx* ctx, int mode);
 /* experiment knobs, 0 = library default.  key 0: rows per warp of the streaming sweep; key 1: resident CTAs per SM (3|4) of
    the register-only sweep; key 2: 1 = do not capture V-cycles into CUDA graphs; key 3: 1 = exchange ghost rows before every sweep instead of once
@@ -406,7 +412,8 @@ int sg_set_relax_mode(sg_ctx* ctx, int mode);
    key 11: 3 = per-patch sweep compiled for 3 CTAs per SM (80 registers) instead of 4 (64); key 12: 1 = one-pass UpdateOperator kernel
    on one-patch levels; key 13: 2 = no CUDA-graph capture of the V-cycle at N > 1; key 14: threads per tile of the L2-resident tile
    smoother (256 | 512 | 1024); key 15: 1 = tile smoother off; key 16: 1 = the implicit gap solve's smoother keeps the per-colour flow;
-   key 17: 1 = its tile smoother does one iteration per launch instead of two.  Keys 0..31. */
+   key 17: 1 = its tile smoother does one iteration per launch instead of two; key 18: 1 = HBM-sized levels keep one GSRB iteration
+   per launch (k_gsrb_stream) instead of two (k_gsrb_twin).  Keys 0..31. */
 int sg_set_tuning(sg_ctx* ctx, int key, int value);
 
 /* ------------------------------------------------------------------ implicit gap-height solve ------------- */

@@ -293,6 +293,12 @@ class VCAMRNonLinearPoissonOp:
         check(lib().sg_op_streams_mask(self.h, C.byref(out)))
         return bool(out.value)
 
+    def smoother_kind(self):
+        """name of the kernel levelGSRB runs on this level now (relax mode and knobs of the context)"""
+        out = C.c_int()
+        check(lib().sg_op_smoother_kind(self.h, C.byref(out)))
+        return ("colour passes", "k_gsrb_stream", "k_gsrb_twin", "k_gsrb_tile", "k_gsrb_patch")[out.value]
+
     def createCoarser(self, fine, ghosted=True):
         h = C.c_void_p()
         check(lib().sg_op_createCoarser(self.h, C.byref(h), fine.h, int(ghosted)))

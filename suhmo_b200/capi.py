@@ -77,7 +77,7 @@ SIGNATURES = {
     "sg_op_applyOp": [vp, vp, vp, ci], "sg_op_applyOpNoBoundary": [vp, vp, vp], "sg_op_applyOpMg": [vp, vp, vp, vp, ci],
     "sg_op_restrictResidual": [vp, vp, vp, vp, vp, ci], "sg_op_restrictR": [vp, vp, vp],
     "sg_op_prolongIncrement": [vp, vp, vp], "sg_op_UpdateOperator": [vp, vp, vp, ci, ci, ci],
-    "sg_op_AverageOperator": [vp, vp, ci], "sg_op_lambda": [vp, vp], "sg_op_streams_mask": [vp, ip],
+    "sg_op_AverageOperator": [vp, vp, ci], "sg_op_lambda": [vp, vp], "sg_op_streams_mask": [vp, ip], "sg_op_smoother_kind": [vp, ip],
     "sg_op_createCoarser": [vp, pvp, vp, ci], "sg_op_create": [vp, pvp, vp],
     "sg_op_assign": [vp, vp, vp], "sg_op_assignLocal": [vp, vp, vp], "sg_op_incr": [vp, vp, vp, cd],
     "sg_op_axby": [vp, vp, vp, vp, cd, cd], "sg_op_scale": [vp, vp, cd], "sg_op_setToZero": [vp, vp],

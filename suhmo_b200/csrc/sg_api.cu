@@ -1303,12 +1303,30 @@ static int check_same(const sg_op* op, const sg_field* f, const char* what) {
   return SG_OK;
 }
 
+// temporal blocking recomputes a 4-cell ring: periodic images inside the patch must then be at least 4 cells away
+static bool two_iterations_fit(const sg_layout* L) {
+  return (!L->wrap_local[0] || L->nx >= 4) && (!L->wrap_local[1] || L->ny >= 4) && L->ny >= 4;
+}
+// does relax_impl, in the default relax mode, run this level two iterations per launch (k_gsrb_twin)?  Levels the tile smoother
+// does not take (more than 2 M cells: they stream from HBM) with enough rows to amortise a segment's nine load-only steps.
+// tune key 18 = 1 turns it off (one iteration per launch, k_gsrb_stream).
+static bool twin_smoother_applies(const sg_op* op) {
+  const sg_layout* L = op->lay;
+  const sg_ctx* c = op->ctx;
+  if (!L->fast || c->relax_mode != 1 || c->tune[18] == 1 || !two_iterations_fit(L)) return false;
+  if (c->tune[19] > 0) return (long long)L->nx * L->ny >= c->tune[19]; // tests: every level of at least that many cells
+  // the variants that also stage the ice mask or aCoef hold 250 registers and measured slower than k_gsrb_stream (valley geometry,
+  // 16384 x 4096: 0.91 against 0.88 ms per iteration): the default takes the plain variant only
+  if (op->mask_needed || op->alpha != 0.0 || !op->prm.use_NL) return false;
+  return (long long)L->nx * L->ny > (1LL << 21) && L->ny >= 64 && L->nx >= 64;
+}
 // does relax_impl run this level's sweeps four at a time in shared-memory tiles (k_gsrb_tile)?  One buffer swap per four iterations
 // then, which the CUDA-graph eligibility test has to know (run_cycle)
 static bool tile_smoother_applies(const sg_op* op) {
   const sg_layout* L = op->lay;
   const sg_ctx* c = op->ctx;
   if (!L->fast || c->relax_mode != 1 || c->tune[15] == 1 || (long long)L->nx * L->ny > (1LL << 21) || L->nx < 16 || L->ny < 16) return false;
+  if (twin_smoother_applies(op)) return false;
   const Geom g = make_geom(L, &op->bc);
   const bool ygh = L->side_ghost[2] || L->side_ghost[3];
   if (ygh && (c->tune[3] != 0 || L->side_ghost[0] || L->side_ghost[1])) return false; // needs the 8-row exchange of the wide mode
@@ -1316,7 +1334,9 @@ static bool tile_smoother_applies(const sg_op* op) {
          (g.kind[3] <= SK_PHYS_NEUM || g.kind[3] == SK_GHOST);
 }
 static int relax_swaps(const sg_op* op, int iterations) { // buffer swaps of one relax call
-  return tile_smoother_applies(op) ? iterations / 4 + iterations % 4 : iterations;
+  if (tile_smoother_applies(op)) return iterations / 4 + iterations % 4;
+  if (twin_smoother_applies(op) || ((op->ctx->relax_mode >= 3) && two_iterations_fit(op->lay))) return iterations / 2 + iterations % 2;
+  return iterations;
 }
 
 // one levelGSRB iteration set
@@ -1333,12 +1353,15 @@ static int relax_impl(sg_op* op, sg_field* phi, const sg_field* rhs, int iterati
   OpArgs a = make_args(op);
   bool ghosts = has_ghost_sides(L);
   if (c->relax_mode >= 1) {
-    // mode 1: one iteration per sweep (k_gsrb_stream); mode 3 (default): two iterations per sweep (k_gsrb_stream2) and a
-    // single sweep for an odd remainder; mode 2: first-generation register-only sweep
+    // mode 1 (default): two iterations per sweep on HBM-sized levels (k_gsrb_twin), four per sweep in shared-memory tiles on
+    // L2-resident ones (k_gsrb_tile), one iteration per sweep (k_gsrb_stream) for what remains; modes 3 / 4 / 5: two iterations
+    // per sweep everywhere with k_gsrb_stream2 / k_gsrb_pair / k_gsrb_twin and a single sweep for an odd remainder; mode 2:
+    // first-generation register-only sweep
     sg_field* scratch;
     SGCALL(ws_field(L, 0, 1, &scratch));
-    // temporal blocking recomputes a 4-cell ring: periodic images inside the patch must then be at least 4 cells away
-    const bool can2 = (c->relax_mode == 3 || c->relax_mode == 4 || c->relax_mode == 5) && (!L->wrap_local[0] || L->nx >= 4) && (!L->wrap_local[1] || L->ny >= 4) && L->ny >= 4;
+    const bool can2 = (c->relax_mode == 3 || c->relax_mode == 4 || c->relax_mode == 5) && two_iterations_fit(L);
+    // default mode: levels too large for the tile smoother run two iterations per launch (k_gsrb_twin), one for an odd remainder
+    const bool twin_default = twin_smoother_applies(op);
     // Communication-avoiding relaxation (mode 1): instead of exchanging two ghost rows before every sweep, exchange 2k rows
     // once per k <= 4 sweeps and let sweep s also update the ghost rows it still needs (2(k-1-s) per side) -- the same
     // arithmetic on the same values as their owner performs, so the result is unchanged while the NCCL (or wrap) calls drop
@@ -1346,7 +1369,7 @@ static int relax_impl(sg_op* op, sg_field* phi, const sg_field* rhs, int iterati
     const bool ygh_lo = L->side_ghost[2], ygh_hi = L->side_ghost[3];
     const bool wide = c->relax_mode == 1 && c->tune[3] == 0 && (ygh_lo || ygh_hi) && !L->side_ghost[0] && !L->side_ghost[1] && L->ny >= 16;
     bool rhs_pending = ghosts; // the right-hand side's ghost rows travel in the same NCCL group as the first exchange of phi
-    const int rhs_depth = wide ? 7 : can2 ? 3 : 1;
+    const int rhs_depth = wide ? 7 : (can2 || twin_default) ? 3 : 1;
     FusedArgs f;
     f.a = a;
     f.rhs = rhs->p();
@@ -1359,9 +1382,9 @@ static int relax_impl(sg_op* op, sg_field* phi, const sg_field* rhs, int iterati
       CK(cudaFuncSetAttribute(k_gsrb_stream2<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 * GS2_STAGES * 9 * 512));
       CK(cudaFuncSetAttribute(k_gsrb_pair<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * (GP_STAGES * 8 * 512 + 1024)));
       CK(cudaFuncSetAttribute(k_gsrb_pair<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * (GP_STAGES * 9 * 512 + 1024)));
-      CK(cudaFuncSetAttribute((k_gsrb_twin<0, 0>), cudaFuncAttributeMaxDynamicSharedMemorySize, 4 * TW_STAGES * 8 * 512));
-      CK(cudaFuncSetAttribute((k_gsrb_twin<0, 1>), cudaFuncAttributeMaxDynamicSharedMemorySize, 4 * TW_STAGES * 8 * 512));
-      CK(cudaFuncSetAttribute((k_gsrb_twin<1, 1>), cudaFuncAttributeMaxDynamicSharedMemorySize, 4 * TW_STAGES * 9 * 512));
+      CK(cudaFuncSetAttribute((k_gsrb_twin<0, 0, 4, 2>), cudaFuncAttributeMaxDynamicSharedMemorySize, 4 * TW_WARP_D2(5) * 16));
+      CK(cudaFuncSetAttribute((k_gsrb_twin<0, 1, 4, 2>), cudaFuncAttributeMaxDynamicSharedMemorySize, 4 * TW_WARP_D2(6) * 16));
+      CK(cudaFuncSetAttribute((k_gsrb_twin<1, 1, 4, 2>), cudaFuncAttributeMaxDynamicSharedMemorySize, 4 * TW_WARP_D2(7) * 16));
       c->smem_attr_set = true;
     }
     // Segments of rows per warp.  Measured on B200 (tools/relax_bench.py): many short segments beat one resident wave
@@ -1370,8 +1393,9 @@ static int relax_impl(sg_op* op, sg_field* phi, const sg_field* rhs, int iterati
     auto plan = [&](int kind) { // 1 stream, 2 fused, 3 stream2, 4 producer/consumer pairs, 5 twin
       const int cols = kind == 3 ? GS2_COLS : kind == 4 ? GP_COLS : kind == 5 ? TW_COLS : kind == 1 ? GS_COLS : FUSED_COLS;
       f.nstrips = (L->nx + cols - 1) / cols;
-      int minb = (kind == 3 || kind == 5) ? 2 : (kind == 1 || kind == 4) ? 3 : (c->tune[1] == 3 ? 3 : 4);
-      int capacity = c->num_sms * minb * (kind == 4 ? 2 : 4); // resident warps (pairs for kind 4) of 128-thread CTAs
+      int minb = (kind == 5 || kind == 3) ? 2 : (kind == 1 || kind == 4) ? 3 : (c->tune[1] == 3 ? 3 : 4);
+      const int wpc = 4;                                        // warps per CTA
+      int capacity = c->num_sms * minb * (kind == 4 ? 2 : wpc); // resident warps (pairs for kind 4)
       int nsegs;
       const int nrows = (kind == 1 || kind == 5) ? f.yhi - f.ylo : L->ny;
       if (c->tune[0] > 0) nsegs = (nrows + c->tune[0] - 1) / c->tune[0];
@@ -1387,7 +1411,7 @@ static int relax_impl(sg_op* op, sg_field* phi, const sg_field* rhs, int iterati
       f.rows_per_warp = (nrows + nsegs - 1) / nsegs;
       f.nsegs = (nrows + f.rows_per_warp - 1) / f.rows_per_warp;
       if (kind == 4) return (f.nstrips * f.nsegs + 1) / 2; // two pairs per CTA
-      return (f.nstrips * f.nsegs * 32 + 127) / 128;
+      return (f.nstrips * f.nsegs + wpc - 1) / wpc;
     };
     f.ylo = 0; f.yhi = L->ny;
     int it = 0;
@@ -1413,18 +1437,30 @@ static int relax_impl(sg_op* op, sg_field* phi, const sg_field* rhs, int iterati
         it += 4;
         continue;
       }
-      const bool two = can2 && it + 2 <= iterations;
-      const int kind = two ? (c->relax_mode == 4 ? 4 : c->relax_mode == 5 ? 5 : 3) : (c->relax_mode == 2 ? 2 : 1);
-      const int chunk = (wide && kind == 1) ? std::min(4, iterations - it) : 1;
+      const bool two = (can2 || twin_default) && it + 2 <= iterations;
+      const int kind = two ? (c->relax_mode == 4 ? 4 : (c->relax_mode == 5 || twin_default) ? 5 : 3) : (c->relax_mode == 2 ? 2 : 1);
+      const int ipl = two ? 2 : 1;                                                        // iterations per launch
+      const int chunk = (wide && (kind == 1 || kind == 5)) ? std::min(4, iterations - it) / ipl : 1; // launches per ghost exchange
       // N > 1: the exchange of a chunk runs on the communication stream while the first sweep updates the rows that do not
-      // depend on ghost rows ([2, ny-2): a sweep over [a, b) reads rows [a-2, b+2)); the two boundary strips follow once the
-      // ghost rows have landed.  Out of place, so the three launches write disjoint rows and read the same input.
+      // depend on ghost rows ([m, ny-m) with m = 2 per iteration of a launch: a sweep over [a, b) reads rows [a-m, b+m)); the two
+      // boundary strips follow once the ghost rows have landed.  Out of place, so the three launches write disjoint rows and read
+      // the same input.
+      auto launch_sweep = [&](int k) {
+        const int blocks = plan(k);
+        if (k == 5) {
+          if (a.has_a) k_gsrb_twin<1, 1, 4, 2><<<blocks, 128, 4 * TW_WARP_D2(7) * 16, c->stream>>>(f);
+          else if (a.use_mask || !a.prm.use_NL) k_gsrb_twin<0, 1, 4, 2><<<blocks, 128, 4 * TW_WARP_D2(6) * 16, c->stream>>>(f);
+          else k_gsrb_twin<0, 0, 4, 2><<<blocks, 128, 4 * TW_WARP_D2(5) * 16, c->stream>>>(f);
+        } else if (a.has_a) k_gsrb_stream<1, 3><<<blocks, 128, 4 * GS_STAGES * 9 * 512, c->stream>>>(f);
+        else k_gsrb_stream<0, 3><<<blocks, 128, 4 * GS_STAGES * 8 * 512, c->stream>>>(f);
+        c->launches++;
+      };
       bool overlapped = false;
       if (ghosts) {
-        const int need = two ? 4 : 2 * chunk;
+        const int need = 2 * ipl * chunk;
         GhostReq r[2] = {{phi, need}, {const_cast<sg_field*>(rhs), rhs_depth}};
         if (it == 0 && phi_valid >= need) { if (rhs_pending) SGCALL(fill_ghosts_multi(c, r + 1, 1)); }
-        else if (wide && kind == 1 && c->comm_stream && c->tune[6] != 1 && L->ny >= 32 && (L->nbr[2] >= 0 || L->nbr[3] >= 0) &&
+        else if (wide && (kind == 1 || kind == 5) && c->comm_stream && c->tune[6] != 1 && L->ny >= 32 && (L->nbr[2] >= 0 || L->nbr[3] >= 0) &&
                  !L->wrap_local[0] && !L->wrap_local[1]) {
           CK(cudaEventRecord(c->ev_comm[0], c->stream));
           CK(cudaStreamWaitEvent(c->comm_stream, c->ev_comm[0], 0));
@@ -1435,50 +1471,41 @@ static int relax_impl(sg_op* op, sg_field* phi, const sg_field* rhs, int iterati
         rhs_pending = false;
       }
       for (int sub = 0; sub < chunk; sub++) {
-        const int ext = 2 * (chunk - 1 - sub);
+        const int ext = 2 * ipl * (chunk - 1 - sub); // ghost rows this launch still has to update for the launches after it
         f.phi_in = phi->p();
         f.phi_out = scratch->p();
         if (overlapped && sub == 0) {
-          auto sweep_rows = [&](int ylo, int yhi) {
-            f.ylo = ylo; f.yhi = yhi;
-            const int nb = plan(1);
-            if (a.has_a) k_gsrb_stream<1, 3><<<nb, 128, 4 * GS_STAGES * 9 * 512, c->stream>>>(f);
-            else k_gsrb_stream<0, 3><<<nb, 128, 4 * GS_STAGES * 8 * 512, c->stream>>>(f);
-            c->launches++;
-          };
-          sweep_rows(2, L->ny - 2);
+          const int m = 2 * ipl;
+          auto sweep_rows = [&](int ylo, int yhi) { f.ylo = ylo; f.yhi = yhi; launch_sweep(kind); };
+          sweep_rows(m, L->ny - m);
           CK(cudaStreamWaitEvent(c->stream, c->ev_comm[1], 0));
-          sweep_rows(ygh_lo ? -ext : 0, 2);
-          sweep_rows(L->ny - 2, L->ny + (ygh_hi ? ext : 0));
+          sweep_rows(ygh_lo ? -ext : 0, m);
+          sweep_rows(L->ny - m, L->ny + (ygh_hi ? ext : 0));
           std::swap(phi->base, scratch->base);
           continue;
         }
         f.ylo = ygh_lo ? -ext : 0;
         f.yhi = L->ny + (ygh_hi ? ext : 0);
-        const int blocks = plan(kind);
         if (kind == 4) {
+          const int blocks = plan(kind);
           if (a.has_a) k_gsrb_pair<1><<<blocks, 128, 2 * (GP_STAGES * 9 * 512 + 1024), c->stream>>>(f);
           else k_gsrb_pair<0><<<blocks, 128, 2 * (GP_STAGES * 8 * 512 + 1024), c->stream>>>(f);
           c->launches++;
-        } else if (kind == 5) {
-          if (a.has_a) k_gsrb_twin<1, 1><<<blocks, 128, 4 * TW_STAGES * 9 * 512, c->stream>>>(f);
-          else if (a.use_mask || !a.prm.use_NL) k_gsrb_twin<0, 1><<<blocks, 128, 4 * TW_STAGES * 8 * 512, c->stream>>>(f);
-          else k_gsrb_twin<0, 0><<<blocks, 128, 4 * TW_STAGES * 8 * 512, c->stream>>>(f);
-          c->launches++;
-        } else if (kind == 3) {
+        } else if (kind == 5 || kind == 1) launch_sweep(kind);
+        else if (kind == 3) {
+          const int blocks = plan(kind);
           if (a.has_a) k_gsrb_stream2<1><<<blocks, 128, 4 * GS2_STAGES * 9 * 512, c->stream>>>(f);
           else k_gsrb_stream2<0><<<blocks, 128, 4 * GS2_STAGES * 8 * 512, c->stream>>>(f);
           c->launches++;
-        } else if (kind == 1) {
-          if (a.has_a) k_gsrb_stream<1, 3><<<blocks, 128, 4 * GS_STAGES * 9 * 512, c->stream>>>(f);
-          else k_gsrb_stream<0, 3><<<blocks, 128, 4 * GS_STAGES * 8 * 512, c->stream>>>(f);
-          c->launches++;
-        } else if (a.has_a) LAUNCH(c, (k_gsrb_fused<1, 4>), blocks, 128, f);
-        else if (c->tune[1] == 3) LAUNCH(c, (k_gsrb_fused<0, 3>), blocks, 128, f);
-        else LAUNCH(c, (k_gsrb_fused<0, 4>), blocks, 128, f);
+        } else {
+          const int blocks = plan(kind);
+          if (a.has_a) LAUNCH(c, (k_gsrb_fused<1, 4>), blocks, 128, f);
+          else if (c->tune[1] == 3) LAUNCH(c, (k_gsrb_fused<0, 3>), blocks, 128, f);
+          else LAUNCH(c, (k_gsrb_fused<0, 4>), blocks, 128, f);
+        }
         std::swap(phi->base, scratch->base); // out-of-place sweep: the field now owns the new buffer
       }
-      it += two ? 2 : chunk;
+      it += ipl * chunk;
     }
   } else {
     for (int it = 0; it < iterations; it++) {
@@ -1707,6 +1734,18 @@ extern "C" int sg_op_AverageOperator(sg_op* op, const sg_op* finest, int depth) 
 extern "C" int sg_op_streams_mask(const sg_op* op, int* out) {
   REQUIRE(op && out, "sg_op_streams_mask: null");
   *out = op->mask_needed ? 1 : 0;
+  return SG_OK;
+}
+// which kernel levelGSRB runs for this operator with the context's current relax mode and knobs: what a bench line names
+extern "C" int sg_op_smoother_kind(const sg_op* op, int* out) {
+  REQUIRE(op && out, "sg_op_smoother_kind: null");
+  const sg_layout* L = op->lay;
+  const sg_ctx* c = op->ctx;
+  if (!L->fast) *out = (c->relax_mode != 0 && L->fused_state == 1 && c->tune[7] != 1) ? SG_SMOOTHER_PATCH : SG_SMOOTHER_COLOUR;
+  else if (c->relax_mode == 0) *out = SG_SMOOTHER_COLOUR;
+  else if (twin_smoother_applies(op) || (c->relax_mode == 5 && two_iterations_fit(L))) *out = SG_SMOOTHER_TWIN;
+  else if (tile_smoother_applies(op)) *out = SG_SMOOTHER_TILE;
+  else *out = SG_SMOOTHER_STREAM;
   return SG_OK;
 }
 extern "C" int sg_op_lambda(sg_op* op, sg_field* lam) {

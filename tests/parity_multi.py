@@ -36,7 +36,7 @@ def _own_equal(gpu_ld, orc_field):
 
 
 def single_level(ctx, dist, rank, world, name, ncyc=4):
-    """returns {"head_bit_exact": .., "resnorm_history_equal": .., "overlap_off_bit_exact": ..}"""
+    """returns {"head_bit_exact": .., "resnorm_history_equal": .., "overlap_off_bit_exact": .., "twin_bit_exact": .., "twin_overlap_off_bit_exact": ..}"""
     from oracle import binding as ob
     from suhmo_b200 import amr, synthetic as syn
     from tests.problem import GpuSide, OracleSide
@@ -46,17 +46,23 @@ def single_level(ctx, dist, rank, world, name, ncyc=4):
     owner = (boxes[:, 1] // tile_ny).astype(np.int32)
     out = {}
     ohist = ohead = None
-    for label, key6 in (("head_bit_exact", 0), ("overlap_off_bit_exact", 1)):
+    # tune key 19 = 1: every multigrid depth runs the two-iterations-per-launch smoother (k_gsrb_twin), which the default
+    # reserves for levels of more than 2 M cells -- the depth-0 smoother of the timed workload, with its eight-row exchange per four
+    # iterations and the interior-first overlap
+    for label, key6, key19 in (("head_bit_exact", 0, 0), ("overlap_off_bit_exact", 1, 0), ("twin_bit_exact", 0, 1),
+                               ("twin_overlap_off_bit_exact", 1, 1)):
         orc = OracleSide(cfg, boxes)
         orc.init_bcoef()
         gpu = GpuSide(ctx, orc, owner)
         ctx.set_tuning(6, key6)
+        ctx.set_tuning(19, key19)
         try:
             mg = amr.AMRFASMultiGrid().define(gpu.factory, 1)
             mg.setSolverParameters(4, 4, 10, 1, 100, 1e-10, 1e-4, 1e-7)
             git, ghist, _ = mg.solve([gpu.F["head"]], [gpu.F["rhs"]], fixed_cycles=ncyc)
         finally:
             ctx.set_tuning(6, 0)
+            ctx.set_tuning(19, 0)
         if ohist is None:
             it, ohist = orc.solver().solve(orc.F["head"], orc.F["rhs"], ob.make_solver_params(bottom=10, fixed_cycles=ncyc))
             ohead = orc.F["head"]

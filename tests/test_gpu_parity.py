@@ -44,12 +44,18 @@ def test_upload_download_roundtrip(gpu_ctx, name, scale, mb):
         assert np.array_equal(got[core], exp[core])
 
 
-@pytest.mark.parametrize("mode", [0, 1, 2, 3, 4, 5])
+def set_mode(ctx, mode):
+    """relax mode; "1t" = the default mode with its two-iterations-per-launch smoother on every level (tune key 19), not only above 2 M cells"""
+    ctx.set_relax_mode(1 if mode == "1t" else mode)
+    ctx.set_tuning(19, 1 if mode == "1t" else 0)
+
+
+@pytest.mark.parametrize("mode", [0, 1, 2, 3, 4, 5, "1t"])
 @pytest.mark.parametrize("name,scale,mb", CASES)
 def test_relax_bit_exact(gpu_ctx, name, scale, mb, mode):
     """a1/a2/a8: levelGSRB with fused NL + lambda; generic colour passes (mode 0), cp.async-staged streaming sweep (mode 1), register-only fused sweep (mode 2), two iterations per sweep (modes 3, 4; mode 5 = the lean k_gsrb_twin with the deferred division slow path)."""
     cfg, orc, gpu = make(gpu_ctx, name, scale, mb)
-    gpu_ctx.set_relax_mode(mode)
+    set_mode(gpu_ctx, mode)
     try:
         oop = orc.op()
         gop = gpu.factory.AMRnewOp(0)
@@ -58,7 +64,7 @@ def test_relax_bit_exact(gpu_ctx, name, scale, mb, mode):
             gop.relax(gpu.F["head"], gpu.F["rhs"], n)
             assert_same(gpu.F["head"], orc.F["head"], f"relax x{n} mode {mode}")
     finally:
-        gpu_ctx.set_relax_mode(1)
+        set_mode(gpu_ctx, 1)
 
 
 def test_relax_inhomogeneous_bc_values(gpu_ctx):
