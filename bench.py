@@ -459,6 +459,9 @@ def main():
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device; this framework has no CPU fallback (use --impl reference for the CPU arm)")
     torch.cuda.set_device(local_rank)
+    # pinned staging buffers next to this rank's GPU (no effect on single-NUMA hosts such as the pool's VMs; tools/h2d_probe.py)
+    from suhmo_b200 import hostmem
+    placement = hostmem.bind_to_gpu_numa(local_rank, ranks_on_node=1, slot=0)
     uid = None
     if world > 1:
         dist.init_process_group(backend="gloo")
@@ -690,7 +693,7 @@ def main():
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None,
             "dtype": "f64", "data": "synthetic", "config": cfgd,
-            "roofline": roofline, "roofline_kernels": roof,
+            "roofline": roofline, "roofline_kernels": roof, "host_placement": placement,
             "cpu_baseline": cpu,
             "e2e": {"value": updates_per_cycle * args.e2e_cycles / e2e_t, "unit": UNIT, "h2d_bytes_per_step": gp.host_bytes(all_names),
                     "d2h_bytes_per_step": e2e_out, "ms_per_step": 1e3 * e2e_t, "vcycles_per_step": args.e2e_cycles,

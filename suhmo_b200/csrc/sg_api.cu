@@ -1382,9 +1382,9 @@ static int relax_impl(sg_op* op, sg_field* phi, const sg_field* rhs, int iterati
       CK(cudaFuncSetAttribute(k_gsrb_stream2<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 * GS2_STAGES * 9 * 512));
       CK(cudaFuncSetAttribute(k_gsrb_pair<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * (GP_STAGES * 8 * 512 + 1024)));
       CK(cudaFuncSetAttribute(k_gsrb_pair<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * (GP_STAGES * 9 * 512 + 1024)));
-      CK(cudaFuncSetAttribute((k_gsrb_twin<0, 0, 4, 2>), cudaFuncAttributeMaxDynamicSharedMemorySize, 4 * TW_WARP_D2(5) * 16));
-      CK(cudaFuncSetAttribute((k_gsrb_twin<0, 1, 4, 2>), cudaFuncAttributeMaxDynamicSharedMemorySize, 4 * TW_WARP_D2(6) * 16));
-      CK(cudaFuncSetAttribute((k_gsrb_twin<1, 1, 4, 2>), cudaFuncAttributeMaxDynamicSharedMemorySize, 4 * TW_WARP_D2(7) * 16));
+      CK(cudaFuncSetAttribute((k_gsrb_twin<0, 0>), cudaFuncAttributeMaxDynamicSharedMemorySize, 4 * TW_WARP_D2(5) * 16));
+      CK(cudaFuncSetAttribute((k_gsrb_twin<0, 1>), cudaFuncAttributeMaxDynamicSharedMemorySize, 4 * TW_WARP_D2(6) * 16));
+      CK(cudaFuncSetAttribute((k_gsrb_twin<1, 1>), cudaFuncAttributeMaxDynamicSharedMemorySize, 4 * TW_WARP_D2(7) * 16));
       c->smem_attr_set = true;
     }
     // Segments of rows per warp.  Measured on B200 (tools/relax_bench.py): many short segments beat one resident wave
@@ -1448,9 +1448,9 @@ static int relax_impl(sg_op* op, sg_field* phi, const sg_field* rhs, int iterati
       auto launch_sweep = [&](int k) {
         const int blocks = plan(k);
         if (k == 5) {
-          if (a.has_a) k_gsrb_twin<1, 1, 4, 2><<<blocks, 128, 4 * TW_WARP_D2(7) * 16, c->stream>>>(f);
-          else if (a.use_mask || !a.prm.use_NL) k_gsrb_twin<0, 1, 4, 2><<<blocks, 128, 4 * TW_WARP_D2(6) * 16, c->stream>>>(f);
-          else k_gsrb_twin<0, 0, 4, 2><<<blocks, 128, 4 * TW_WARP_D2(5) * 16, c->stream>>>(f);
+          if (a.has_a) k_gsrb_twin<1, 1><<<blocks, 128, 4 * TW_WARP_D2(7) * 16, c->stream>>>(f);
+          else if (a.use_mask || !a.prm.use_NL) k_gsrb_twin<0, 1><<<blocks, 128, 4 * TW_WARP_D2(6) * 16, c->stream>>>(f);
+          else k_gsrb_twin<0, 0><<<blocks, 128, 4 * TW_WARP_D2(5) * 16, c->stream>>>(f);
         } else if (a.has_a) k_gsrb_stream<1, 3><<<blocks, 128, 4 * GS_STAGES * 9 * 512, c->stream>>>(f);
         else k_gsrb_stream<0, 3><<<blocks, 128, 4 * GS_STAGES * 8 * 512, c->stream>>>(f);
         c->launches++;

@@ -48,7 +48,6 @@ def main():
         ctx.set_relax_mode(mode)
         ctx.set_tuning(0, rows)
         ctx.set_tuning(1, minb)
-        ctx.set_tuning(18, v[3] if len(v) > 3 else 0)   # occupancy variant of k_gsrb_twin
         op0.relax(F["head"], F["rhs"], 3)
         n = int(os.environ.get("SG_ITERS", "48"))
         ctx.event_record(0)
@@ -56,7 +55,7 @@ def main():
         ctx.event_record(1)
         ms = ctx.event_elapsed_ms(0, 1) / n
         gbs = 72.0 * size * size / (ms * 1e-3) / 1e9
-        res.append(dict(mode=mode, rows_per_warp=rows, ctas_per_sm=minb, twin_variant=v[3] if len(v) > 3 else 0, ms=ms, gbs_at_72B=gbs))
+        res.append(dict(mode=mode, rows_per_warp=rows, ctas_per_sm=minb, ms=ms, gbs_at_72B=gbs))
         print(json.dumps(res[-1]), flush=True)
     ctx.destroy()
 
