@@ -645,6 +645,8 @@ def main():
 
     # ---------------- CPU baseline beside it (rank 0, N = 1 only): the oracle on the SAME workload (same grids, same fields), a few
     # V-cycles with all host threads; its residual-norm history must equal the GPU's warm-up history bit for bit
+    hostmem.restore(placement)  # every pinned buffer exists by now: the CPU arm below gets all host cores back
+    placement.pop("_prev", None)
     cpu = parity_full = None
     threads = os.cpu_count() or 1
     if rank == 0 and world == 1 and not args.no_cpu:

@@ -66,6 +66,7 @@ def bind_to_gpu_numa(device, ranks_on_node=1, slot=0):
         if node is None:
             return info
         allowed = set(os.sched_getaffinity(0))
+        info["_prev"] = sorted(allowed)
         cpus = [c for c in node_cpus(node) if c in allowed]
         if not cpus:
             return info
@@ -79,3 +80,13 @@ def bind_to_gpu_numa(device, ranks_on_node=1, slot=0):
     except Exception as e:  # placement is an optimisation: never fail a solve over it
         info["error"] = repr(e)
     return info
+
+
+def restore(info):
+    """give the process back the CPUs it had before `bind_to_gpu_numa` (pages already allocated stay where they are)"""
+    prev = info.pop("_prev", None) if isinstance(info, dict) else None
+    if prev and info.get("bound"):
+        try:
+            os.sched_setaffinity(0, prev)
+        except OSError:
+            pass
