@@ -242,28 +242,38 @@ __global__ void __launch_bounds__(256, MINB) k_gsrb_patch(const double* __restri
 #undef TILE
 }
 
-// MODE 0: out = L(phi); 1: out = rhs - L(phi); 2: as 1 plus max|out| into *norm_bits
-template <int MODE>
+// MODE 0: out = L(phi); 1: out = rhs - L(phi); 2: as 1 plus max|out| into *norm_bits.  A block of 32 x 8 threads covers 32 x 8*ROWS
+// cells of one patch (ROWS rows per thread, 8 apart): a refined level is ~10^4 patches of ~40^2 cells, and with one row per thread
+// the grid is ~2*10^5 blocks of a handful of loads each (level 2 of the bench hierarchy: residual + norm 0.57 ms with ROWS = 1)
+#define AG_ROWS 4
+template <int MODE, int ROWS>
 __global__ void __launch_bounds__(256) k_apply_g(double* __restrict__ outb, const double* __restrict__ phib,
                                                  const double* __restrict__ rhsb, const PatchG* __restrict__ tab, OpArgsG a,
                                                  unsigned long long* norm_bits, unsigned long long* partial = nullptr) {
   const PatchG g = tab[blockIdx.z];
-  int i = blockIdx.x * blockDim.x + threadIdx.x;
-  int j = blockIdx.y * blockDim.y + threadIdx.y;
-  double r = 0.0;
-  if (i < g.nx && j < g.ny) {
-    ptrdiff_t P = g.pitch;
-    ptrdiff_t o = g.off + (ptrdiff_t)j * P + i;
-    double pc = phib[o], pw = phib[o - 1], pe = phib[o + 1], ps = phib[o - P], pn = phib[o + P];
-    double bw = a.bX[o], be = a.bX[o + 1], bs = a.bY[o], bn = a.bY[o + P];
-    double ac = a.has_a ? a.aC[o] : 0.0;
-    double nl, dnl;
-    nl_terms(a.prm, pc, a.B[o], a.mask[o], a.Pi[o], a.zb[o], nl, dnl);
-    double lof = lofphi_cell(a.alpha, ac, a.beta, pc, pw, pe, ps, pn, bw, be, bs, bn, a.dxi0, a.dxi1, nl);
-    r = MODE == 0 ? lof : rhsb[o] - (lof);
-    outb[o] = r;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int j0 = blockIdx.y * (blockDim.y * ROWS) + threadIdx.y;
+  double rmax = 0.0;
+  if (i < g.nx) {
+    const ptrdiff_t P = g.pitch;
+#pragma unroll
+    for (int m = 0; m < ROWS; m++) {
+      const int j = j0 + m * 8;
+      if (j < g.ny) {
+        const ptrdiff_t o = g.off + (ptrdiff_t)j * P + i;
+        double pc = phib[o], pw = phib[o - 1], pe = phib[o + 1], ps = phib[o - P], pn = phib[o + P];
+        double bw = a.bX[o], be = a.bX[o + 1], bs = a.bY[o], bn = a.bY[o + P];
+        double ac = a.has_a ? a.aC[o] : 0.0;
+        double nl, dnl;
+        nl_terms(a.prm, pc, a.B[o], a.mask[o], a.Pi[o], a.zb[o], nl, dnl);
+        double lof = lofphi_cell(a.alpha, ac, a.beta, pc, pw, pe, ps, pn, bw, be, bs, bn, a.dxi0, a.dxi1, nl);
+        const double r = MODE == 0 ? lof : rhsb[o] - (lof);
+        outb[o] = r;
+        if (MODE == 2) rmax = nanmax(rmax, fabs(r));
+      }
+    }
   }
-  if (MODE == 2) block_max_to_global(fabs(r), norm_bits, partial);
+  if (MODE == 2) block_max_to_global(rmax, norm_bits, partial);
 }
 
 // vector ops over valid cells (whole != 0: ghost ring of width ng included). op as k_vec.
