@@ -1,6 +1,12 @@
 /*
  * suhmo_oracle.c -- CPU restatement of SUHMO's hydraulic-head solve hot path.  See suhmo_oracle.h.
- * TEST INFRASTRUCTURE ONLY (checker + CPU baseline); "parity unpinned" at the Chombo boundary.
+ * TEST INFRASTRUCTURE ONLY (checker + CPU baseline).
+ * Pinning: the kernel arithmetic restated here from the reference's .ChF files is held, bit for bit, to golden vectors produced by
+ * EXECUTING those .ChF sources (tools/chf_translate.py -> tests/golden/chf_kernels.npz -> tests/test_oracle_chf_golden.py):
+ * COMPUTENONLINEARTERMS, COMPUTERE, COMPUTEBCOEFF, COMPUTEQW/SCAPROD/DCOEFF/DIFTERM2D/_TIMEVARYINGRECHARGE, SUMFACESNL,
+ * GSRBHELMHOLTZVCNL2D, VCNLCOMPUTE{OP,RES}2D, RESTRICT{RES}VCNL, PROLONGNL, NEWMACGRAD, DIVERGENCE.  "parity unpinned" still holds
+ * for everything the absent Chombo fork supplies (boundary-condition functions, QuadCFInterp, flux register, the multigrid driver,
+ * FineInterp / PiecewiseLinearFillPatch, Berger-Rigoutsos): restated from the in-tree call sites and public Chombo 3.2 behaviour.
  *
  * Build: see oracle/Makefile (-O2 -ffp-contract=off: the reference's gfortran/x86-64 build has no
  * FMA contraction, so neither does this file).  All citations are relative to /root/reference/.

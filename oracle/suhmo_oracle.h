@@ -5,10 +5,13 @@
  * Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs use it,
  * and only as the checker / CPU baseline -- never as the product path.
  *
- * PARITY UNPINNED at the Chombo boundary: the reference ships no golden vectors, known-answer
- * tests or fixtures for this path and cannot be built here (no gfortran,
- * MPI, HDF5 or Chombo).  This file restates, operation by operation and in the Fortran
- * evaluation order, the in-tree kernels
+ * PINNING: the reference ships no golden vectors, known-answer tests or fixtures for this path
+ *  and cannot be built here (no gfortran, MPI, HDF5 or Chombo).  The in-tree
+ * Fortran kernels restated below ARE pinned: tools/chf_translate.py executes the reference's .ChF
+ * sources (translated in memory) on seeded inputs, tests/golden/chf_kernels.npz keeps the outputs and
+ * tests/test_oracle_chf_golden.py holds this oracle to them bit for bit.  PARITY UNPINNED remains
+ * true at the Chombo boundary (next paragraph).  This file restates, operation by operation and in
+ * the Fortran evaluation order, the in-tree kernels
  *     src/VCAMRNonLinearPoissonOpF.ChF, src/AMRNonLinearPoissonOpF.ChF:607-741,
  *     src/AmrHydroF.ChF, util/GradientF.ChF, util/ExtrapBCF.ChF, util/DivergenceF.ChF
  * and the C++ orchestration in src/VCAMRNonLinearPoissonOp.cpp, src/AMRNonLinearPoissonOp.cpp,
