@@ -1,0 +1,132 @@
+"""The CUDA library, through the C ABI, against golden vectors of the REFERENCE's own Fortran kernels
+(tests/golden/chf_kernels.npz: the .ChF sources of the reference executed through tools/chf_translate.py, see
+tests/golden/make_chf_golden.py).  Same cases as tests/test_oracle_chf_golden.py, no oracle in between: lambda, two levelGSRB
+iterations (every relax mode), residual, applyOp, restrictResidual, restrictR, prolongIncrement on one doubly periodic box with
+alpha != 0, the ice mask < 0 on a fifth of the cells and both cut-offs of COMPUTENONLINEARTERMS active; NonLinear_level alone;
+the MAC gradient with and without mask; the divergence.  Bit for bit."""
+import ctypes as C
+import os
+
+import numpy as np
+import pytest
+
+from suhmo_b200 import amr
+from suhmo_b200.capi import check, lib
+
+pytestmark = pytest.mark.gpu
+
+Z = np.load(os.path.join(os.path.dirname(__file__), "golden", "chf_kernels.npz"))
+NX, NY = int(Z["nx"]), int(Z["ny"])
+DX = tuple(float(v) for v in Z["dx"])
+A, OMEGA, NU, CUT, MX = (float(v) for v in Z["prm"])
+CELL, XF, YF = 0, 1, 2
+
+
+def wrap(a):
+    g = np.zeros((a.shape[0] + 2, a.shape[1] + 2))
+    g[1:-1, 1:-1] = a
+    g[1:-1, 0], g[1:-1, -1] = a[:, -1], a[:, 0]
+    g[0, 1:-1], g[-1, 1:-1] = a[-1, :], a[0, :]
+    return g
+
+
+def same(ld, name):
+    got, exp = ld.get_global(), Z[name]
+    assert got.shape == exp.shape, (name, got.shape, exp.shape)
+    assert np.array_equal(got, exp), f"{name}: max abs diff {np.nanmax(np.abs(got - exp)):g} (the reference kernel's output, expected bit for bit)"
+
+
+class Side:
+    def __init__(self, ctx):
+        self.ctx = ctx
+        self.lay = amr.DisjointBoxLayout(ctx, np.array([[0, 0, NX - 1, NY - 1]], dtype=np.int32), (0, 0, NX - 1, NY - 1), (1, 1), None)
+        self.F = {}
+        for k in ("head", "B", "Pi", "zb", "mask"):
+            self.F[k] = self.field(wrap(Z[k]), 1)
+        self.F["rhs"] = self.field(Z["rhs"])
+        self.F["a"] = self.field(Z["aC"])
+        self.F["bX"] = self.field(Z["bX"], 0, XF)
+        self.F["bY"] = self.field(Z["bY"], 0, YF)
+        self.bc = amr.make_bc((0, 0), (0, 0))
+        self.prm = amr.make_params(A=A, omega=OMEGA, nu=NU, cutOffbr=CUT, maxOffbr=MX)
+        F = self.F
+        self.factory = amr.VCAMRNonLinearPoissonOpFactory().define(ctx, [self.lay], [], DX, self.bc, float(Z["alpha"]), [F["a"]], float(Z["beta"]),
+                                                                   [F["bX"]], [F["bY"]], self.prm, [F["B"]], [F["Pi"]], [F["zb"]], [F["mask"]])
+        self.op = self.factory.AMRnewOp(0)
+
+    def field(self, a, ng=0, cent=CELL):
+        a = np.asarray(a)
+        f = amr.LevelData(self.lay, a.shape[0] if a.ndim == 3 else 1, ng, cent)
+        f.set_global(a, (-ng, -ng))
+        return f
+
+    def new(self, ng=0, cent=CELL, ncomp=1):
+        return amr.LevelData(self.lay, ncomp, ng, cent)
+
+
+@pytest.mark.parametrize("mode", [0, 1, 2, 3, 4, 5])
+def test_operator_against_reference_kernels(gpu_ctx, mode):
+    s = Side(gpu_ctx)
+    op, F = s.op, s.F
+    lam = s.new()
+    op.lambda_(lam)
+    same(lam, "lam")
+    gpu_ctx.set_relax_mode(mode)
+    try:
+        for it in (1, 2):
+            op.relax(F["head"], F["rhs"], 1)
+            same(F["head"], f"gsrb_iter{it}")
+        # the same two iterations in ONE call from the initial state (modes 3-5: one launch of the two-iteration kernels)
+        h2 = s.field(wrap(Z["head"]), 1)
+        op.relax(h2, F["rhs"], 2)
+        same(h2, "gsrb_iter2")
+    finally:
+        gpu_ctx.set_relax_mode(1)
+    res, lof = s.new(), s.new()
+    op.residual(res, F["head"], F["rhs"])
+    same(res, "residual")
+    op.applyOp(lof, F["head"], False)
+    same(lof, "applyop")
+    resc, phic = op.createCoarser(F["rhs"]), op.createCoarser(F["head"])
+    op.restrictResidual(resc, F["head"], None, F["rhs"], False)
+    same(resc, "restrict_res")
+    op.restrictR(phic, F["head"])
+    same(phic, "restrict_r")
+    corr = op.createCoarser(F["head"])
+    g = np.zeros((NY // 2 + 2, NX // 2 + 2))
+    g[1:-1, 1:-1] = Z["prolong_corr"]
+    corr.set_global(g, (-1, -1))
+    op.prolongIncrement(F["head"], corr)
+    same(F["head"], "prolong_out")
+
+
+def test_twin_kernel_every_level_against_reference_kernels(gpu_ctx):
+    """the default relax mode with k_gsrb_twin on every level (tune key 19): the two reference iterations in one launch"""
+    s = Side(gpu_ctx)
+    gpu_ctx.set_relax_mode(1)
+    gpu_ctx.set_tuning(19, 1)
+    try:
+        assert s.op.smoother_kind() == "k_gsrb_twin"
+        s.op.relax(s.F["head"], s.F["rhs"], 2)
+        same(s.F["head"], "gsrb_iter2")
+    finally:
+        gpu_ctx.set_tuning(19, 0)
+
+
+def test_nonlinear_level_gradient_divergence(gpu_ctx):
+    s = Side(gpu_ctx)
+    F = s.F
+    nl, dnl = s.new(), s.new()
+    check(lib().sg_nonlinear_level(C.byref(s.prm), nl.h, dnl.h, F["head"].h, F["B"].h, F["mask"].h, F["Pi"].h, F["zb"].h))
+    same(nl, "nl")
+    same(dnl, "dnl")
+    dx = (C.c_double * 2)(*DX)
+    for has in (0, 1):
+        gx, gy = s.new(0, XF), s.new(0, YF)
+        check(lib().sg_mac_gradient(F["head"].h, F["mask"].h if has else None, dx, gx.h, gy.h))
+        same(gx, f"macgrad_x_mask{has}")
+        same(gy, f"macgrad_y_mask{has}")
+    div = s.new()
+    s.op.setToZero(div)
+    check(lib().sg_divergence(div.h, s.field(Z["div_ux"], 0, XF).h, s.field(Z["div_uy"], 0, YF).h, dx))
+    same(div, "div")
