@@ -130,3 +130,38 @@ def test_nonlinear_level_gradient_divergence(gpu_ctx):
     s.op.setToZero(div)
     check(lib().sg_divergence(div.h, s.field(Z["div_ux"], 0, XF).h, s.field(Z["div_uy"], 0, YF).h, dx))
     same(div, "div")
+
+
+def test_reynolds_face_coefficient_and_picard_kernels(gpu_ctx):
+    """COMPUTERE, COMPUTEBCOEFF (with and without cutOffBcoef), COMPUTEQW, COMPUTESCAPROD, COMPUTEDCOEFF, COMPUTEDIFTERM2D,
+    COMPUTE_TIMEVARYINGRECHARGE (src/AmrHydroF.ChF:81-373)"""
+    s = Side(gpu_ctx)
+    L = lib()
+    prm = amr.make_params(A=A, omega=OMEGA, nu=NU)
+    Re = s.new()
+    check(L.sg_compute_re(C.byref(prm), Re.h, s.field(Z["B"]).h, s.field(Z["gradH"]).h))
+    same(Re, "Re")
+    Bec, Reec, IMec = (s.field(Z[k], 0, XF) for k in ("Bec", "Reec", "IMec"))
+    for c in (0, 1):
+        p = amr.make_params(A=A, omega=OMEGA, nu=NU, cutOffBcoef=c)
+        bc = s.new(0, XF)
+        check(L.sg_compute_bcoeff(C.byref(p), Bec.h, Reec.h, IMec.h, bc.h))
+        same(bc, f"bcoeff_cut{c}")
+    qw = s.new(0, XF)
+    check(L.sg_compute_qw(C.byref(prm), Bec.h, Reec.h, s.field(Z["gradHec"], 0, XF).h, qw.h))
+    same(qw, "Qw")
+    p1, p2 = s.new(0, XF), s.new(0, XF)
+    check(L.sg_compute_scaprod(qw.h, s.field(Z["sp_b1"], 0, XF).h, s.field(Z["sp_b2"], 0, XF).h, p1.h, p2.h))
+    same(p1, "sp_p1")
+    same(p2, "sp_p2")
+    for c in (0, 1):
+        D = s.new(0, XF)
+        check(L.sg_compute_dcoeff(D.h, s.field(Z["MRec"], 0, XF).h, Bec.h, IMec.h, 910.0, c))
+        same(D, f"dcoeff_cut{c}")
+    dx = (C.c_double * 2)(*DX)
+    dterm = s.new()
+    check(L.sg_compute_difterm(s.field(wrap(Z["B"]), 1).h, dx, dterm.h, s.field(Z["D0"], 0, XF).h, s.field(Z["D1"], 0, YF).h))
+    same(dterm, "difterm")
+    rech = s.new()
+    check(L.sg_time_varying_recharge(s.field(Z["zs"]).h, rech.h, 4.5, 7.93e-11))
+    same(rech, "recharge")
