@@ -45,6 +45,7 @@ def main():
     K.update(T.load(f"{REF}/src/AMRNonLinearPoissonOpF.ChF", names={"PROLONGNL", "PROLONG_2_NL"}))
     K.update(T.load(f"{REF}/util/GradientF.ChF", names={"NEWMACGRAD"}))
     K.update(T.load(f"{REF}/util/DivergenceF.ChF"))
+    K.update(T.load(f"{REF}/util/ExtrapBCF.ChF", names={"SIMPLEEXTRAPBC", "SIMPLECOPYBC"}))
     rng = np.random.RandomState(20261018)
     box = T.Box((0, 0), (NX - 1, NY - 1))
     out = {"nx": NX, "ny": NY, "dx": np.array(DX)}
@@ -172,6 +173,22 @@ def main():
     for d, u in ((0, ux), (1, uy)):
         K["DIVERGENCE"](uedge=fab(u), div=fab(div), gridint=box, dx=DX[d], idir=d)
     out.update(div_ux=ux, div_uy=uy, div=div[0])
+
+    # ---- 8. ExtrapGhostCells / CopyGhostCells on cell data, one ghost cell, non-periodic domain (util/ExtrapGhostCells.cpp:94-269): per
+    # direction the one-cell strip outside the domain (adjCellLo / adjCellHi), grown by the ghost radius tangentially so that the
+    # second direction also fills the corners from the first direction's strip; SIMPLEEXTRAPBC / SIMPLECOPYBC on it
+    for name, kern in (("extrap", "SIMPLEEXTRAPBC"), ("copy", "SIMPLECOPYBC")):
+        g = np.zeros((1, NY + 2, NX + 2))
+        g[0, 1:-1, 1:-1] = head
+        hi = (NX - 1, NY - 1)
+        for d in (0, 1):
+            t = 1 - d
+            for hilo, pos in ((0, -1), (1, hi[d] + 1)):
+                lo_, hi_ = [0, 0], [0, 0]
+                lo_[d] = hi_[d] = pos
+                lo_[t], hi_[t] = -1, hi[t] + 1
+                K[kern](phi=fab(g, (-1, -1)), bcbox=T.Box(lo_, hi_), dir=d, hilo=hilo)
+        out[f"ghost_{name}"] = g[0]
 
     path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "chf_kernels.npz")
     np.savez_compressed(path, **out)

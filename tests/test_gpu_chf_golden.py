@@ -165,3 +165,17 @@ def test_reynolds_face_coefficient_and_picard_kernels(gpu_ctx):
     rech = s.new()
     check(L.sg_time_varying_recharge(s.field(Z["zs"]).h, rech.h, 4.5, 7.93e-11))
     same(rech, "recharge")
+
+
+def test_extrap_and_copy_ghost_cells(gpu_ctx):
+    """ExtrapGhostCells / CopyGhostCells on cell data (util/ExtrapGhostCells.cpp:94-269 + SIMPLEEXTRAPBC / SIMPLECOPYBC), corners included"""
+    lay = amr.DisjointBoxLayout(gpu_ctx, np.array([[0, 0, NX - 1, NY - 1]], dtype=np.int32), (0, 0, NX - 1, NY - 1), (0, 0), None)
+    for name, fn in (("extrap", amr.ExtrapGhostCells), ("copy", amr.CopyGhostCells)):
+        g = np.zeros((NY + 2, NX + 2))
+        g[1:-1, 1:-1] = Z["head"]
+        f = amr.LevelData(lay, 1, 1, CELL)
+        f.set_global(g, (-1, -1))
+        fn(f)
+        got = f.download_box(0).reshape(NY + 2, NX + 2)
+        exp = Z[f"ghost_{name}"]
+        assert np.array_equal(got, exp), f"ghost_{name}: max abs diff {np.abs(got - exp).max():g}"

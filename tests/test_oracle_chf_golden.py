@@ -153,3 +153,16 @@ def test_mac_gradient_and_divergence():
     div.setval(0.0)
     ob.lib().orc_divergence(field(lay, Z["div_ux"], 0, XF).h, field(lay, Z["div_uy"], 0, YF).h, p, div.h)
     same(div.get_global(), "div")
+
+
+def test_extrap_and_copy_ghost_cells():
+    """ExtrapGhostCells / CopyGhostCells on cell data (util/ExtrapGhostCells.cpp:94-269 + SIMPLEEXTRAPBC / SIMPLECOPYBC), corners included"""
+    lay = layout((0, 0))
+    for name, fn in (("extrap", ob.lib().orc_extrap_ghost), ("copy", ob.lib().orc_copy_ghost)):
+        g = np.zeros((NY + 2, NX + 2))
+        g[1:-1, 1:-1] = Z["head"]
+        f = field(lay, g, 1)
+        fn(f.h)
+        got = f.fab(0)[0][0]
+        exp = Z[f"ghost_{name}"]
+        assert np.array_equal(got, exp), f"ghost_{name}: max abs diff {np.abs(got - exp).max():g}"
