@@ -1,0 +1,361 @@
+// suhmo_amrhydro.hpp -- the time step of the reference's driver class, AmrHydro::timeStepFAS (src/AmrHydro.cpp:2255-3620), as C++ host
+// code over the device-resident layer of suhmo_gpu.hpp.  Same member names (m_head, m_gapheight, m_Re, m_meltRate, ...), the same
+// member functions (compute_grad_head, compute_grad_zb_ec, evaluate_Re_quadratic, evaluate_Qw_ec, aCoeff_bCoeff, dCoeff,
+// Calc_meltingRate, CalcRHS_gapHeightFAS, Calc_moulin_source_term_distributed, SolveForHead_nl, SolveForGap_nl, timeStepFAS) in the
+// order the reference calls them; every field stays on the device from the first Picard iteration to the end of the step, and each
+// statement of the reference that touches field data is one call into the C ABI.  What the reference does around the step (run():
+// dt control, plot / checkpoint cadence; regrid(): tagCells + BRMeshRefine + destructiveRegrid, available here as
+// tagCellsLevel / BRMeshRefine / regridTransfer in suhmo_gpu.hpp) stays with the caller.
+//
+// The explicit gap-height update runs on any number of levels; the implicit one (solver.use_ImplDiff) on one level, as every
+// reference input that sets it is single-level (the C ABI answers SG_ERR_UNSUPPORTED otherwise).
+//
+// Checked on the GPU by tests/cpp/timestep_host.cpp against the CPU oracle's independent restatement of the same function
+// (oracle/picard_amr.py): Picard iteration counts, V-cycle counts, convergence measures, head and gap height, bit for bit.
+#pragma once
+#include <algorithm>
+#include <array>
+#include <memory>
+#include <stdexcept>
+
+#include "suhmo_gpu.hpp"
+
+namespace sg {
+
+// one moulin of the input file: position, peak recharge, width of the Gaussian (suhmo.moulin_position / moulin_flux / moulin_sigma)
+struct Moulin { double x, y, flux, sigma; };
+
+// what one call of timeStepFAS decided: the reference prints these (pout() lines at src/AmrHydro.cpp:3187-3229)
+struct TimeStepReport {
+  int picard_iterations = 0;
+  std::vector<int> head_cycles;     // V-cycles of each head solve
+  std::vector<double> x_h;          // max|h_lag - h| / max h after each Picard iteration
+  int gap_cycles = -1;              // V-cycles of the implicit gap solve, -1 when explicit
+};
+
+class AmrHydro {
+ public:
+  typedef std::unique_ptr<LevelData> Ptr;
+  struct FluxPtr {                  // LevelData<FluxBox>: one LevelData per face direction
+    Ptr d[2];
+    LevelData& operator[](int dir) { return *d[dir]; }
+  };
+
+  Context& m_ctx;
+  std::vector<DisjointBoxLayout*> m_amrGrids;   // borrowed, coarsest first; refinement ratio 2 throughout (src/AmrHydro.cpp:1467)
+  std::vector<std::array<double, 2>> m_amrDx;
+  sg_params m_prm;                              // suhmo.* / solver.* values of the head operator
+  sg_bc m_bc;                                   // bc.lo_bc / bc.hi_bc / values (ParseBC)
+  sg_picard_params m_suhmoParm;                 // suhmo_params
+  bool m_use_mask_gradients = false, m_use_ImplDiff = false;
+  int m_cur_step = 0;
+  double m_time = 0.0;
+  double m_eps_PicardIte = 1.0e-6;              // solver.eps_PicardIte
+  std::vector<Moulin> m_moulins;
+
+  // persistent state, one entry per level (names of src/AmrHydro.H:466-497)
+  std::vector<Ptr> m_head, m_gapheight, m_old_head, m_old_gapheight, m_gradhead, m_Pw, m_Re, m_meltRate, m_magVel, m_bedelevation,
+      m_overburdenpress, m_moulin_source_term, m_bumpHeight, m_bumpSpacing, m_iceMask;
+  std::vector<FluxPtr> m_gradhead_ec, m_iceMask_ec;
+  // the locals of timeStepFAS that live across its loops (src/AmrHydro.cpp:2281-2353)
+  std::vector<Ptr> a_head_lagged, RHS_h, RHS_b, a_diffusiveTerm, aCoef, a_qgh, a_qgz, a_work, a_gh_curr, aCoef_GH;
+  std::vector<FluxPtr> a_gapheight_ec, a_meltRate_ec, a_gradZb_ec, a_Dcoef, a_Re_ec, a_Qw_ec, a_tmp1_ec, a_tmp2_ec, bCoef;
+
+  VCAMRNonLinearPoissonOpFactory m_opFactory;
+  std::vector<std::unique_ptr<VCAMRNonLinearPoissonOp>> m_ops;
+  std::unique_ptr<AMRFASMultiGrid> m_amrSolver;
+
+  // levelSetup (src/AmrHydro.cpp:5059-5088) for every level + the operator factory on the solver's coefficient fields
+  AmrHydro(Context& ctx, const std::vector<DisjointBoxLayout*>& grids, const double coarsestDx[2], const sg_params& prm, const sg_bc& bc,
+           const sg_picard_params& suhmoParm)
+      : m_ctx(ctx), m_amrGrids(grids), m_prm(prm), m_bc(bc), m_suhmoParm(suhmoParm) {
+    m_use_mask_gradients = prm.use_mask_grad != 0;
+    m_use_ImplDiff = suhmoParm.use_ImplDiff != 0;
+    const size_t n = grids.size();
+    double f = 1.0;
+    for (size_t l = 0; l < n; l++, f *= 2.0) m_amrDx.push_back({coarsestDx[0] / f, coarsestDx[1] / f});
+    for (std::vector<Ptr>* v : {&m_head, &m_gapheight, &m_old_head, &m_old_gapheight, &m_Pw, &m_Re, &m_meltRate, &m_magVel, &m_bedelevation,
+                                &m_overburdenpress, &m_moulin_source_term, &m_bumpHeight, &m_bumpSpacing, &m_iceMask, &a_head_lagged, &a_work})
+      for (size_t l = 0; l < n; l++) v->emplace_back(new LevelData(*grids[l], 1, 1));
+    for (std::vector<Ptr>* v : {&m_gradhead, &a_qgh, &a_qgz})
+      for (size_t l = 0; l < n; l++) v->emplace_back(new LevelData(*grids[l], 2, 1));
+    for (std::vector<Ptr>* v : {&RHS_h, &RHS_b, &a_diffusiveTerm, &aCoef})
+      for (size_t l = 0; l < n; l++) v->emplace_back(new LevelData(*grids[l], 1, 0));
+    for (std::vector<FluxPtr>* v : {&m_gradhead_ec, &m_iceMask_ec, &a_gapheight_ec, &a_meltRate_ec, &a_gradZb_ec, &a_Dcoef, &a_Re_ec, &a_Qw_ec,
+                                    &a_tmp1_ec, &a_tmp2_ec, &bCoef})
+      for (size_t l = 0; l < n; l++) {
+        v->emplace_back();
+        v->back().d[0].reset(new LevelData(*grids[l], 1, 0, XFace));
+        v->back().d[1].reset(new LevelData(*grids[l], 1, 0, YFace));
+      }
+    // opFactory.define(..., alpha = 0, aCoef, beta = -1, bCoef, ..., B, Pi, zb, iceMask) (src/AmrHydro.cpp:704-717)
+    std::vector<LevelData*> a, bx, by;
+    for (size_t l = 0; l < n; l++) { a.push_back(aCoef[l].get()); bx.push_back(bCoef[l].d[0].get()); by.push_back(bCoef[l].d[1].get()); }
+    m_opFactory.define(ctx, grids, std::vector<int>(n > 0 ? n - 1 : 0, 2), coarsestDx, bc, 0.0, a, -1.0, bx, by, prm, raw(m_gapheight),
+                       raw(m_overburdenpress), raw(m_bedelevation), raw(m_iceMask));
+    for (size_t l = 0; l < n; l++) m_ops.emplace_back(m_opFactory.AMRnewOp((int)l));
+  }
+  // solver and operators go before the factory and the fields they were defined on
+  ~AmrHydro() { m_amrSolver.reset(); m_ops.clear(); }
+
+  int finestLevel() const { return (int)m_amrGrids.size() - 1; }
+  static std::vector<LevelData*> raw(std::vector<Ptr>& v) {
+    std::vector<LevelData*> r;
+    for (Ptr& p : v) r.push_back(p.get());
+    return r;
+  }
+
+  // ---- ghost cells ----------------------------------------------------------------------------------------------------------
+  // PiecewiseLinearFillPatch(levelGrids, coarseGrids, 1, domain, 2, 1).fillInterp(fine, coarse, coarse, 0, 0, 0, ncomp)
+  void fillInterp(int lev, std::vector<Ptr>& f) { m_ops[lev]->pwlFillPatch(*f[lev], *f[lev - 1]); }
+  // QuadCFInterp(...).coarseFineInterp(fine, coarse)
+  void quadCFInterp(int lev, std::vector<Ptr>& f) { m_ops[lev]->coarseFineInterp(*f[lev], *f[lev - 1]); }
+  void headBC(int lev) { mixBCValues(*m_head[lev], m_bc, m_amrDx[lev].data(), false); }
+  // CoarseAverage(fineGrids, 1, 2).averageToCoarse(coarse, fine), finest level first (src/AmrHydro.cpp:2822,3139,3593)
+  void averageDown(std::vector<Ptr>& f) {
+    for (int lev = finestLevel(); lev > 0; lev--) m_ops[lev]->averageToCoarse(*f[lev - 1], *f[lev]);
+  }
+
+  // ---- the member functions timeStepFAS calls -------------------------------------------------------------------------------
+  // src/AmrHydro.cpp:1611-1656
+  void compute_grad_head(int lev) {
+    if (lev > 0) quadCFInterp(lev, m_head);   // levelGradientMAC's coarse-fine boundary condition, util/Gradient.cpp:85-93
+    compGradientMAC(*m_head[lev], m_use_mask_gradients ? m_iceMask[lev].get() : nullptr, m_amrDx[lev].data(), m_gradhead_ec[lev][0],
+                    m_gradhead_ec[lev][1]);
+    EdgeToCell(m_gradhead_ec[lev][0], m_gradhead_ec[lev][1], *m_gradhead[lev]);
+    if (lev > 0) quadCFInterp(lev, m_gradhead);
+    m_gradhead[lev]->exchange();
+    ExtrapGhostCells(*m_gradhead[lev]);
+  }
+  // src/AmrHydro.cpp:1578-1608
+  void compute_grad_zb_ec(int lev) {
+    if (lev > 0) quadCFInterp(lev, m_bedelevation);
+    compGradientMAC(*m_bedelevation[lev], m_use_mask_gradients ? m_iceMask[lev].get() : nullptr, m_amrDx[lev].data(), a_gradZb_ec[lev][0],
+                    a_gradZb_ec[lev][1]);
+  }
+  // src/AmrHydro.cpp:1712-1780
+  void evaluate_Re_quadratic(int lev, bool computeGrad) {
+    if (computeGrad) compute_grad_head(lev);
+    computeRe(m_prm, *m_Re[lev], *m_gapheight[lev], *m_gradhead[lev]);
+  }
+  // src/AmrHydro.cpp:1678-1708 (after the ghost fill and CellToEdge of Re, :2713-2750)
+  void evaluate_Qw_ec(int lev) {
+    if (lev > 0) fillInterp(lev, m_Re);
+    m_Re[lev]->exchange();
+    CellToEdge(*m_Re[lev], a_Re_ec[lev][0], a_Re_ec[lev][1]);
+    for (int dir = 0; dir < 2; dir++) sg::evaluate_Qw_ec(m_prm, a_gapheight_ec[lev][dir], a_Re_ec[lev][dir], m_gradhead_ec[lev][dir], a_Qw_ec[lev][dir]);
+  }
+  // src/AmrHydro.cpp:1782-1812: aCoef = 0, bCoef = COMPUTEBCOEFF(B_ec, Re_ec, iceMask_ec)
+  void aCoeff_bCoeff(int lev) {
+    m_ops[lev]->setToZero(*aCoef[lev]);
+    for (int dir = 0; dir < 2; dir++) sg::aCoeff_bCoeff(m_prm, a_gapheight_ec[lev][dir], a_Re_ec[lev][dir], m_iceMask_ec[lev][dir], bCoef[lev][dir]);
+  }
+  // src/AmrHydro.cpp:1832-1862
+  void dCoeff(int lev) {
+    for (int dir = 0; dir < 2; dir++)
+      sg::dCoeff(a_Dcoef[lev][dir], a_meltRate_ec[lev][dir], a_gapheight_ec[lev][dir], m_iceMask_ec[lev][dir], m_suhmoParm.rho_i, m_prm.cutOffBcoef);
+  }
+  // COMPUTESCAPROD + EdgeToCell of Qw grad(h) and Qw grad(zb), then Calc_meltingRate (src/AmrHydro.cpp:2964-2990, 2175-2252)
+  void Calc_meltingRate(int lev) {
+    for (int dir = 0; dir < 2; dir++) computeScaProd(a_Qw_ec[lev][dir], m_gradhead_ec[lev][dir], a_gradZb_ec[lev][dir], a_tmp1_ec[lev][dir], a_tmp2_ec[lev][dir]);
+    EdgeToCell(a_tmp1_ec[lev][0], a_tmp1_ec[lev][1], *a_qgh[lev]);
+    EdgeToCell(a_tmp2_ec[lev][0], a_tmp2_ec[lev][1], *a_qgz[lev]);
+    sg::Calc_meltingRate(m_suhmoParm, *m_head[lev], *m_bedelevation[lev], *m_overburdenpress[lev], *m_iceMask[lev], *m_gapheight[lev], *a_qgh[lev],
+                         *a_qgz[lev], *m_Pw[lev], *m_meltRate[lev]);
+  }
+  // src/AmrHydro.cpp:2070-2171
+  void CalcRHS_gapHeightFAS(int lev, double dt) {
+    sg::CalcRHS_gapHeightFAS(m_suhmoParm, *RHS_b[lev], *m_overburdenpress[lev], *m_Pw[lev], *m_meltRate[lev], *m_gapheight[lev],
+                             *a_diffusiveTerm[lev], *m_iceMask[lev], *m_bumpHeight[lev], *m_bumpSpacing[lev], *m_magVel[lev], dt);
+  }
+  // Calc_moulin_integral + Calc_moulin_source_term_distributed over the hierarchy, then the average-down and ghost fill of the
+  // source term (src/AmrHydro.cpp:1867-2069, 2800-2836).  Returns the per-moulin integrals.
+  std::vector<double> Calc_moulin_source_term_distributed(double runoff = 0.0) {
+    const int n = (int)m_moulins.size();
+    std::vector<double> pos, sig, flux, integ(n, 0.0);
+    for (const Moulin& m : m_moulins) { pos.push_back(m.x); pos.push_back(m.y); sig.push_back(m.sigma); flux.push_back(m.flux); }
+    if (n > 0) {
+      for (int lev = finestLevel(); lev >= 0; lev--)
+        m_ops[lev]->moulinIntegralLevel(lev < finestLevel() ? m_ops[lev + 1].get() : nullptr, n, pos.data(), sig.data(), integ.data());
+      for (int lev = 0; lev <= finestLevel(); lev++)
+        m_ops[lev]->moulinSourceLevel(lev < finestLevel() ? m_ops[lev + 1].get() : nullptr, *m_moulin_source_term[lev], n, pos.data(), sig.data(),
+                                      integ.data(), flux.data(), runoff, m_time);
+    }
+    averageDown(m_moulin_source_term);
+    for (int lev = 0; lev <= finestLevel(); lev++) {
+      if (lev > 0) quadCFInterp(lev, m_moulin_source_term);
+      m_moulin_source_term[lev]->exchange();
+      ExtrapGhostCells(*m_moulin_source_term[lev]);
+    }
+    return integ;
+  }
+
+  // src/AmrHydro.cpp:666-769: solver parameters by m_cur_step, solve from the current head.  fixedCycles > 0 is the parity protocol.
+  std::vector<double> SolveForHead_nl(int fixedCycles = 0) {
+    if (!m_amrSolver) {
+      m_amrSolver.reset(new AMRFASMultiGrid);
+      m_amrSolver->define(m_opFactory, (int)m_amrGrids.size());
+    } else {
+      m_amrSolver->refresh();   // the reference rebuilds factory and solver per call (:704-735); the coefficients changed, the grids did not
+    }
+    const bool early = m_cur_step < 50;
+    if (fixedCycles > 0) {
+      m_amrSolver->setSolverParameters(4, 4, 10, 1, 100, 1e-10, 1e-4, 1e-7);
+    } else {
+      m_amrSolver->setSolverParameters(4, 4, early ? 10 : 16, 1, 100, early ? 1e-10 : 1e-7, early ? 1e-4 : 0.01, 1e-7);
+      m_amrSolver->m_imin = early ? 20 : 5;
+      m_amrSolver->m_iterMin = 2;
+    }
+    m_amrSolver->params.fixed_cycles = fixedCycles;
+    std::vector<double> hist;
+    m_amrSolver->solve(raw(m_head), raw(RHS_h), finestLevel(), 0, nullptr, &hist);
+    return hist;
+  }
+
+  // ---- timeStepFAS, in the reference's four parts -----------------------------------------------------------------------------
+  // I (src/AmrHydro.cpp:2356-2445): consistent head and gap height, old-time copies, edge-centred ice mask
+  void beginStep() {
+    for (int lev = 0; lev <= finestLevel(); lev++) {
+      if (lev > 0) { fillInterp(lev, m_head); fillInterp(lev, m_gapheight); }
+      m_head[lev]->exchange();
+      m_gapheight[lev]->exchange();
+      CopyGhostCells(*m_gapheight[lev]);
+      headBC(lev);
+      m_ops[lev]->assignLocal(*m_old_head[lev], *m_head[lev]);
+      m_ops[lev]->assignLocal(*m_old_gapheight[lev], *m_gapheight[lev]);
+      setup_iceMask_EC(*m_iceMask[lev], m_iceMask_ec[lev][0], m_iceMask_ec[lev][1]);
+    }
+  }
+  // II (src/AmrHydro.cpp:2477-3105): one Picard iteration up to the head solve
+  void picardBody() {
+    for (int lev = 0; lev <= finestLevel(); lev++) {
+      if (lev > 0) { fillInterp(lev, m_head); fillInterp(lev, m_gapheight); fillInterp(lev, m_meltRate); }
+      m_head[lev]->exchange();
+      m_gapheight[lev]->exchange();
+      m_meltRate[lev]->exchange();
+      CopyGhostCells(*m_gapheight[lev]);
+      headBC(lev);
+      m_ops[lev]->assignLocal(*a_head_lagged[lev], *m_head[lev]);
+      ExtrapGhostCells(*m_meltRate[lev]);
+      CellToEdge(*m_gapheight[lev], a_gapheight_ec[lev][0], a_gapheight_ec[lev][1]);
+      CellToEdge(*m_meltRate[lev], a_meltRate_ec[lev][0], a_meltRate_ec[lev][1]);
+    }
+    for (int lev = 0; lev <= finestLevel(); lev++) {
+      compute_grad_head(lev);
+      compute_grad_zb_ec(lev);
+      dCoeff(lev);
+    }
+    for (int lev = 0; lev <= finestLevel(); lev++) {
+      evaluate_Re_quadratic(lev, false);
+      evaluate_Qw_ec(lev);
+    }
+    for (int lev = 0; lev <= finestLevel(); lev++) {
+      // q.grad(h), q.grad(zb), div(D grad b), melt rate, RHS_h (:2920-3079)
+      for (int dir = 0; dir < 2; dir++) computeScaProd(a_Qw_ec[lev][dir], m_gradhead_ec[lev][dir], a_gradZb_ec[lev][dir], a_tmp1_ec[lev][dir], a_tmp2_ec[lev][dir]);
+      EdgeToCell(a_tmp1_ec[lev][0], a_tmp1_ec[lev][1], *a_qgh[lev]);
+      EdgeToCell(a_tmp2_ec[lev][0], a_tmp2_ec[lev][1], *a_qgz[lev]);
+      computeDifTerm(*m_gapheight[lev], m_amrDx[lev].data(), *a_diffusiveTerm[lev], a_Dcoef[lev][0], a_Dcoef[lev][1]);
+      sg::Calc_meltingRate(m_suhmoParm, *m_head[lev], *m_bedelevation[lev], *m_overburdenpress[lev], *m_iceMask[lev], *m_gapheight[lev], *a_qgh[lev],
+                           *a_qgz[lev], *m_Pw[lev], *m_meltRate[lev]);
+      CalcRHS_head(m_suhmoParm, *RHS_h[lev], *m_meltRate[lev], *m_gapheight[lev], *m_bumpHeight[lev], *m_bumpSpacing[lev], *m_magVel[lev],
+                   *m_moulin_source_term[lev], *a_diffusiveTerm[lev], *m_iceMask[lev]);
+    }
+    for (int lev = 0; lev <= finestLevel(); lev++) aCoeff_bCoeff(lev);
+  }
+  // III (src/AmrHydro.cpp:3134-3185): average the head down, refill its ghost cells, measure the change against the lagged head
+  void afterSolve() {
+    averageDown(m_head);
+    for (int lev = 0; lev <= finestLevel(); lev++) {
+      if (lev > 0) fillInterp(lev, m_head);
+      m_head[lev]->exchange();
+      headBC(lev);
+    }
+  }
+  // max |h_lag - h| / max h over the cells no finer level covers (computeMax, :3168-3185); head is positive in every SUHMO set-up
+  double picardChange() {
+    double maxHead = 0.0, res = 0.0;
+    for (int lev = 0; lev <= finestLevel(); lev++) maxHead = std::max(maxHead, m_ops[lev]->norm(*m_head[lev], 0));
+    for (int lev = 0; lev <= finestLevel(); lev++) {
+      m_ops[lev]->axby(*a_work[lev], *a_head_lagged[lev], *m_head[lev], 1.0, -1.0);
+      if (lev < finestLevel()) m_ops[lev]->zeroCovered(*a_work[lev], *m_head[lev + 1]);
+      res = std::max(res, m_ops[lev]->norm(*a_work[lev], 0) / maxHead);
+    }
+    return res;
+  }
+  // IV (src/AmrHydro.cpp:3248-3455, 3590-3595): Re, Qw and the melt rate with the converged head, then the gap height
+  int updateGap(double dt) {
+    int gapCycles = -1;
+    for (int lev = 0; lev <= finestLevel(); lev++) {
+      evaluate_Re_quadratic(lev, true);
+      evaluate_Qw_ec(lev);
+      Calc_meltingRate(lev);
+      CalcRHS_gapHeightFAS(lev, dt);
+      if (m_use_ImplDiff) {
+        // a_gh_curr = gap height incl. ghost cells, aCoef = 1, bCoef = Dcoef, SolveForGap_nl, copy back (:3378-3391, 3425-3455)
+        if (a_gh_curr.empty())
+          for (size_t l = 0; l < m_amrGrids.size(); l++) {
+            a_gh_curr.emplace_back(new LevelData(*m_amrGrids[l], 1, 1));
+            aCoef_GH.emplace_back(new LevelData(*m_amrGrids[l], 1, 0));
+            for (int b = 0; b < m_amrGrids[l]->size(); b++) {
+              const Box& bx = m_amrGrids[l]->boxes[b];
+              std::vector<double> ones((size_t)(bx.hi[0] - bx.lo[0] + 1) * (bx.hi[1] - bx.lo[1] + 1), 1.0);
+              aCoef_GH[l]->upload(b, ones.data());
+            }
+          }
+        m_ops[lev]->assignLocal(*a_gh_curr[lev], *m_gapheight[lev]);
+      } else {
+        gapEuler(*m_gapheight[lev], *m_old_gapheight[lev], *RHS_b[lev], dt);
+      }
+      if (!m_use_ImplDiff) {
+        if (lev > 0) fillInterp(lev, m_gapheight);
+        m_gapheight[lev]->exchange();
+        CopyGhostCells(*m_gapheight[lev]);
+      }
+    }
+    if (m_use_ImplDiff) {
+      std::vector<LevelData*> dx, dy;
+      for (size_t l = 0; l < m_amrGrids.size(); l++) { dx.push_back(a_Dcoef[l].d[0].get()); dy.push_back(a_Dcoef[l].d[1].get()); }
+      gapCycles = sg::SolveForGap_nl(m_ctx, m_amrGrids, raw(aCoef_GH), dx, dy, {}, m_amrDx[0].data(), raw(a_gh_curr), raw(RHS_b), dt,
+                                     m_suhmoParm.DiffFactor, m_cur_step);
+      for (int lev = 0; lev <= finestLevel(); lev++) {
+        m_ops[lev]->assignLocal(*m_gapheight[lev], *a_gh_curr[lev]);
+        m_gapheight[lev]->exchange();
+        CopyGhostCells(*m_gapheight[lev]);
+      }
+    }
+    averageDown(m_gapheight);
+    return gapCycles;
+  }
+
+  // src/AmrHydro.cpp:2255-3620.  Picard iterations until the reference's test passes (:3187-3229): x_h < 0.05 while m_cur_step < 50
+  // (and more than two iterations while m_cur_step < 2), x_h < solver.eps_PicardIte afterwards; more than 100 iterations abort.
+  TimeStepReport timeStepFAS(double a_dt) {
+    TimeStepReport rep;
+    m_cur_step += 1;   // :2259 -- the solver parameters and the Picard test below read the incremented counter
+    beginStep();
+    int ite_idx = 0;
+    bool converged_h = false;
+    while (!converged_h) {
+      picardBody();
+      std::vector<double> hist = SolveForHead_nl();
+      rep.head_cycles.push_back((int)hist.size() - 1);
+      afterSolve();
+      const double x_h = picardChange();
+      rep.x_h.push_back(x_h);
+      if (ite_idx > 100) {
+        std::fprintf(stderr, "suhmo_gpu: timeStepFAS does not converge (Picard iterations > 100)\n");
+        std::abort();   // MayDay::Error("Abort")
+      }
+      if (m_cur_step < 2) converged_h = x_h < 0.05 && ite_idx > 2;
+      else if (m_cur_step < 50) converged_h = x_h < 0.05;
+      else converged_h = x_h < m_eps_PicardIte;
+      ite_idx++;
+    }
+    rep.picard_iterations = ite_idx;
+    rep.gap_cycles = updateGap(a_dt);
+    m_time += a_dt;    // :4108
+    return rep;
+  }
+};
+
+} // namespace sg

@@ -1,0 +1,174 @@
+// timestep_host.cpp -- whole time steps of AmrHydro::timeStepFAS (src/AmrHydro.cpp:2255-3620) driven from C++ through
+// suhmo_b200/host/suhmo_amrhydro.hpp, every field resident on the GPU, replaying a fixture that the CPU oracle's independent
+// restatement of the same function produced (tests/amr_timestep_fixture.py documents the layout).
+//
+//   timestep_host <fixture.bin> [--parse-only]
+//
+// --parse-only reads the fixture, prints what it holds and exits (no GPU needed: the CPU-side check that writer and reader agree).
+
+// Asserted per step: the number of Picard iterations, the number of V-cycles of every head solve (and of the implicit gap solve),
+// the convergence measure of every Picard iteration bit for bit, and BIT equality of head and gap height on every valid cell of every
+// level.  Exit code 0 iff everything holds.
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <vector>
+
+#include "../../suhmo_b200/host/suhmo_amrhydro.hpp"
+
+using namespace sg;
+
+static const int N_IN = 10;   // head B Pi zb mask MV BH BL mR MS
+struct BoxIn { Box box; std::vector<double> in[N_IN]; };
+struct StepOut {
+  int picard = 0, gap_cycles = -1;
+  std::vector<int> cycles;
+  std::vector<double> x_h;
+  std::vector<std::vector<std::vector<double>>> head, gap;   // [level][box][cell]
+};
+struct Fixture {
+  int nlev = 0, nsteps = 0, cur_step = 0, impl = 0, nx = 0, ny = 0, periodic[2] = {0, 0};
+  double dx0[2] = {0, 0}, dt = 0;
+  sg_params prm;
+  sg_bc bc;
+  sg_picard_params q;
+  std::vector<std::vector<BoxIn>> lev;
+  std::vector<StepOut> steps;
+};
+
+static bool rd(FILE* f, void* p, size_t n) { return std::fread(p, 1, n, f) == n; }
+static bool rd_struct(FILE* f, void* p, size_t n) {
+  int sz = 0;
+  return rd(f, &sz, 4) && (size_t)sz == n && rd(f, p, n);
+}
+static bool load(const char* path, Fixture& F) {
+  FILE* f = std::fopen(path, "rb");
+  if (!f) return false;
+  int hdr[9];
+  double r3[3];
+  bool ok = rd(f, hdr, sizeof hdr) && hdr[0] == 0x53474832 && rd(f, r3, sizeof r3);
+  F.nlev = hdr[1]; F.nsteps = hdr[2]; F.cur_step = hdr[3]; F.impl = hdr[4]; F.nx = hdr[5]; F.ny = hdr[6]; F.periodic[0] = hdr[7]; F.periodic[1] = hdr[8];
+  F.dx0[0] = r3[0]; F.dx0[1] = r3[1]; F.dt = r3[2];
+  ok = ok && rd_struct(f, &F.prm, sizeof F.prm) && rd_struct(f, &F.bc, sizeof F.bc) && rd_struct(f, &F.q, sizeof F.q);
+  for (int l = 0; ok && l < F.nlev; l++) {
+    int nbox = 0;
+    ok = rd(f, &nbox, 4);
+    F.lev.emplace_back();
+    for (int b = 0; ok && b < nbox; b++) {
+      BoxIn d;
+      int bx[4];
+      ok = rd(f, bx, sizeof bx);
+      d.box = Box{{bx[0], bx[1]}, {bx[2], bx[3]}};
+      const size_t ng = (size_t)(bx[2] - bx[0] + 3) * (bx[3] - bx[1] + 3);
+      for (int k = 0; ok && k < N_IN; k++) { d.in[k].resize(ng); ok = rd(f, d.in[k].data(), ng * 8); }
+      F.lev.back().push_back(std::move(d));
+    }
+  }
+  for (int s = 0; ok && s < F.nsteps; s++) {
+    StepOut o;
+    ok = rd(f, &o.picard, 4) && o.picard > 0 && o.picard < 200;
+    if (!ok) break;
+    o.cycles.resize(o.picard); o.x_h.resize(o.picard);
+    ok = rd(f, o.cycles.data(), 4 * (size_t)o.picard) && rd(f, o.x_h.data(), 8 * (size_t)o.picard) && rd(f, &o.gap_cycles, 4);
+    o.head.resize(F.nlev); o.gap.resize(F.nlev);
+    for (int l = 0; ok && l < F.nlev; l++)
+      for (size_t b = 0; ok && b < F.lev[l].size(); b++) {
+        const Box& bx = F.lev[l][b].box;
+        const size_t nv = (size_t)(bx.hi[0] - bx.lo[0] + 1) * (bx.hi[1] - bx.lo[1] + 1);
+        o.head[l].emplace_back(nv); o.gap[l].emplace_back(nv);
+        ok = rd(f, o.head[l].back().data(), nv * 8) && rd(f, o.gap[l].back().data(), nv * 8);
+      }
+    F.steps.push_back(std::move(o));
+  }
+  char extra;
+  ok = ok && std::fread(&extra, 1, 1, f) == 0;   // nothing left over
+  std::fclose(f);
+  return ok;
+}
+
+static int g_fail = 0;
+#define EXPECT(cond, ...)                                        \
+  do {                                                           \
+    if (!(cond)) { std::printf("timestep_host: FAILED: " __VA_ARGS__); std::printf("\n"); g_fail++; } \
+  } while (0)
+
+// valid cells of a one-ghost-cell field against the fixture; returns the number of cells that differ
+static long long compare(LevelData& f, const std::vector<BoxIn>& boxes, const std::vector<std::vector<double>>& expect, long long& cells) {
+  long long differ = 0;
+  for (size_t b = 0; b < boxes.size(); b++) {
+    const Box& bx = boxes[b].box;
+    const int nx = bx.hi[0] - bx.lo[0] + 1, ny = bx.hi[1] - bx.lo[1] + 1;
+    std::vector<double> fab((size_t)(nx + 2) * (ny + 2));
+    f.download((int)b, fab.data());
+    for (int j = 0; j < ny; j++)
+      for (int i = 0; i < nx; i++, cells++)
+        differ += std::memcmp(&fab[(size_t)(j + 1) * (nx + 2) + i + 1], &expect[b][(size_t)j * nx + i], 8) != 0;
+  }
+  return differ;
+}
+
+static void run(Context& ctx, const Fixture& F, std::vector<DisjointBoxLayout*>& grids) {
+  AmrHydro amrObject(ctx, grids, F.dx0, F.prm, F.bc, F.q);
+  amrObject.m_cur_step = F.cur_step - 1;     // timeStepFAS increments it first (src/AmrHydro.cpp:2259)
+  std::vector<AmrHydro::Ptr>* inputs[N_IN] = {&amrObject.m_head, &amrObject.m_gapheight, &amrObject.m_overburdenpress, &amrObject.m_bedelevation,
+                                              &amrObject.m_iceMask, &amrObject.m_magVel, &amrObject.m_bumpHeight, &amrObject.m_bumpSpacing,
+                                              &amrObject.m_meltRate, &amrObject.m_moulin_source_term};
+  for (int l = 0; l < F.nlev; l++)
+    for (size_t b = 0; b < F.lev[l].size(); b++)
+      for (int k = 0; k < N_IN; k++) (*inputs[k])[l]->upload((int)b, F.lev[l][b].in[k].data());
+  for (int s = 0; s < F.nsteps; s++) {
+    const StepOut& o = F.steps[s];
+    const long long launches0 = ctx.kernelLaunches();
+    TimeStepReport rep = amrObject.timeStepFAS(F.dt);
+    ctx.sync();
+    std::printf("timestep_host: step %d (m_cur_step %d): %d Picard iterations, V-cycles per head solve", s, amrObject.m_cur_step, rep.picard_iterations);
+    for (int c : rep.head_cycles) std::printf(" %d", c);
+    std::printf(", gap solve %d, x_h %.17g, %lld kernel launches\n", rep.gap_cycles, rep.x_h.back(), ctx.kernelLaunches() - launches0);
+    EXPECT(rep.picard_iterations == o.picard, "step %d: %d Picard iterations, the oracle took %d", s, rep.picard_iterations, o.picard);
+    EXPECT(rep.gap_cycles == o.gap_cycles, "step %d: %d V-cycles of the gap solve, the oracle took %d", s, rep.gap_cycles, o.gap_cycles);
+    for (int k = 0; k < rep.picard_iterations && k < o.picard; k++) {
+      EXPECT(rep.head_cycles[k] == o.cycles[k], "step %d Picard %d: %d V-cycles, the oracle took %d", s, k, rep.head_cycles[k], o.cycles[k]);
+      EXPECT(std::memcmp(&rep.x_h[k], &o.x_h[k], 8) == 0, "step %d Picard %d: x_h %.17g, the oracle has %.17g", s, k, rep.x_h[k], o.x_h[k]);
+    }
+    long long cells = 0, dh = 0, db = 0;
+    for (int l = 0; l < F.nlev; l++) {
+      dh += compare(*amrObject.m_head[l], F.lev[l], o.head[l], cells);
+      db += compare(*amrObject.m_gapheight[l], F.lev[l], o.gap[l], cells);
+    }
+    std::printf("timestep_host: step %d: head and gap height compared with the oracle on %lld values, %lld + %lld differ\n", s, cells, dh, db);
+    EXPECT(dh == 0 && db == 0 && cells > 0, "step %d: head / gap height not bit-identical to the oracle's", s);
+  }
+  // the moulin recharge of the same hierarchy through the class (Calc_moulin_source_term_distributed): positive integrals, finite source
+  amrObject.m_moulins = {{0.3 * F.nx * F.dx0[0], 0.4 * F.ny * F.dx0[1], 80.0, 2.5 * F.dx0[0]}, {0.7 * F.nx * F.dx0[0], 0.2 * F.ny * F.dx0[1], 40.0, 2.0 * F.dx0[0]}};
+  std::vector<double> integ = amrObject.Calc_moulin_source_term_distributed(0.3);
+  for (double v : integ) EXPECT(std::isfinite(v) && v > 0, "moulin integral %g", v);
+  const double ms = amrObject.m_ops[0]->norm(*amrObject.m_moulin_source_term[0], 0);
+  EXPECT(std::isfinite(ms) && ms > 0, "moulin source term max %g", ms);
+}
+
+int main(int argc, char** argv) {
+  std::setvbuf(stdout, nullptr, _IOLBF, 0);
+  Fixture F;
+  if (argc < 2 || !load(argv[1], F)) { std::printf("timestep_host: cannot read the fixture (usage: timestep_host <fixture.bin>)\n"); return 2; }
+  if (argc > 2 && std::strcmp(argv[2], "--parse-only") == 0) {
+    long long cells = 0;
+    for (const auto& lv : F.lev)
+      for (const BoxIn& d : lv) cells += (long long)(d.box.hi[0] - d.box.lo[0] + 1) * (d.box.hi[1] - d.box.lo[1] + 1);
+    std::printf("timestep_host: fixture holds %d levels, %lld cells, %d steps from m_cur_step %d, implicit gap solve %d, Picard iterations", F.nlev, cells,
+                F.nsteps, F.cur_step, F.impl);
+    for (const StepOut& o : F.steps) std::printf(" %d", o.picard);
+    std::printf("\n");
+    return 0;
+  }
+  Context ctx(0);
+  std::vector<DisjointBoxLayout*> grids;
+  for (int l = 0; l < F.nlev; l++) {
+    std::vector<Box> bx;
+    for (const BoxIn& d : F.lev[l]) bx.push_back(d.box);
+    grids.push_back(new DisjointBoxLayout(ctx, bx, {}, Box{{0, 0}, {(F.nx << l) - 1, (F.ny << l) - 1}}, F.periodic));
+  }
+  run(ctx, F, grids);
+  for (DisjointBoxLayout* g : grids) delete g;
+  std::printf(g_fail == 0 ? "timestep_host: OK\n" : "timestep_host: FAILED (%d checks)\n", g_fail);
+  return g_fail == 0 ? 0 : 1;
+}

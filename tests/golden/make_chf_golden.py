@@ -190,6 +190,17 @@ def main():
                 K[kern](phi=fab(g, (-1, -1)), bcbox=T.Box(lo_, hi_), dir=d, hilo=hilo)
         out[f"ghost_{name}"] = g[0]
 
+    # ---- 9. AMRProlongS_2 (src/AMRNonLinearPoissonOp.cpp:1141-1206): PROLONG_2_NL over a fine box that refines coarse cells
+    # [2..7] x [2..6] of the periodic coarse box; `coarse` is the coarsened-fine scratch with one ghost cell, here the coarse
+    # correction itself on [1..8] x [1..7] (copyTo with ghost cells; no physical boundary, no second fine box); m = 2
+    p2c = 1e-2 * (rng.rand(NY, NX) - 0.5)
+    flo, fhi = (4, 4), (15, 13)
+    p2f = (1e-3 * rng.rand(fhi[1] - flo[1] + 1, fhi[0] - flo[0] + 1))[None]
+    out.update(prolong2_coarse=p2c, prolong2_fine_in=p2f[0].copy(), prolong2_box=np.array(flo + fhi, dtype=np.int32))
+    temp = p2c[1:8, 1:9].copy()
+    K["PROLONG_2_NL"](phi=fab(p2f, flo), coarse=fab(temp, (1, 1)), region=T.Box(flo, fhi), m=2)
+    out.update(prolong2_out=p2f[0])
+
     path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "chf_kernels.npz")
     np.savez_compressed(path, **out)
     print("wrote", path, "with", len(out), "arrays")

@@ -179,3 +179,33 @@ def test_extrap_and_copy_ghost_cells(gpu_ctx):
         got = f.download_box(0).reshape(NY + 2, NX + 2)
         exp = Z[f"ghost_{name}"]
         assert np.array_equal(got, exp), f"ghost_{name}: max abs diff {np.abs(got - exp).max():g}"
+
+
+def test_prolong_2_nl_through_amr_prolong_s2(gpu_ctx):
+    """sg_op_AMRProlongS_2 against the reference's PROLONG_2_NL (src/AMRNonLinearPoissonOpF.ChF:646-709) as AMRProlongS_2 calls it
+    (src/AMRNonLinearPoissonOp.cpp:1141-1206): one fine box inside the doubly periodic coarse box"""
+    bx = [int(v) for v in Z["prolong2_box"]]
+    layC = amr.DisjointBoxLayout(gpu_ctx, np.array([[0, 0, NX - 1, NY - 1]], dtype=np.int32), (0, 0, NX - 1, NY - 1), (1, 1), None)
+    layF = amr.DisjointBoxLayout(gpu_ctx, np.array([bx], dtype=np.int32), (0, 0, 2 * NX - 1, 2 * NY - 1), (1, 1), None)
+    lays = [layC, layF]
+
+    def ones(lay, ng=0, cent=CELL):
+        f = amr.LevelData(lay, 1, ng, cent)
+        f.upload([np.ones(f.fab_shape(b)) for b in range(len(lay.boxes))])
+        return f
+
+    F = {k: [ones(l, ng, c) for l in lays] for k, (ng, c) in dict(a=(0, CELL), bX=(0, XF), bY=(0, YF), B=(1, CELL), Pi=(1, CELL), zb=(1, CELL),
+                                                                  mask=(1, CELL)).items()}
+    factory = amr.VCAMRNonLinearPoissonOpFactory().define(gpu_ctx, lays, [2], DX, amr.make_bc((0, 0), (0, 0)), 0.0, F["a"], -1.0, F["bX"], F["bY"],
+                                                          amr.make_params(A=A, omega=OMEGA, nu=NU, cutOffbr=CUT, maxOffbr=MX), F["B"], F["Pi"],
+                                                          F["zb"], F["mask"])
+    opC, opF = factory.AMRnewOp(0), factory.AMRnewOp(1)
+    coarse = amr.LevelData(layC, 1, 1, CELL)
+    coarse.set_global(wrap(Z["prolong2_coarse"]), (-1, -1))
+    fine = amr.LevelData(layF, 1, 1, CELL)
+    g = np.zeros((2 * NY + 2, 2 * NX + 2))
+    g[bx[1] + 1:bx[3] + 2, bx[0] + 1:bx[2] + 2] = Z["prolong2_fine_in"]
+    fine.set_global(g, (-1, -1))
+    opF.AMRProlongS_2(fine, coarse, opC)
+    got = fine.get_global()[bx[1]:bx[3] + 1, bx[0]:bx[2] + 1]
+    assert np.array_equal(got, Z["prolong2_out"]), f"PROLONG_2_NL: max abs diff {np.abs(got - Z['prolong2_out']).max():g}"

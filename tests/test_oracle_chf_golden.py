@@ -166,3 +166,30 @@ def test_extrap_and_copy_ghost_cells():
         got = f.fab(0)[0][0]
         exp = Z[f"ghost_{name}"]
         assert np.array_equal(got, exp), f"ghost_{name}: max abs diff {np.abs(got - exp).max():g}"
+
+
+def test_prolong_2_nl_through_amr_prolong_s2():
+    """AMRProlongS_2 (src/AMRNonLinearPoissonOp.cpp:1141-1206) around PROLONG_2_NL (src/AMRNonLinearPoissonOpF.ChF:646-709): one fine box
+    inside the doubly periodic coarse box, so the scratch's ghost cells are coarse cells (copyTo) and no BC function enters"""
+    bx = [int(v) for v in Z["prolong2_box"]]
+    layC = layout()
+    layF = ob.Layout(np.array([bx], dtype=np.int32), (0, 0, 2 * NX - 1, 2 * NY - 1), (1, 1))
+    bc = ob.make_bc((0, 0), (0, 0))
+    prm = ob.make_params(A=A, omega=OMEGA, nu=NU, cutOffbr=CUT, maxOffbr=MX)
+
+    def op(lay, dx):
+        f = [ob.Field(lay, 1, 0), ob.Field(lay, 1, 0, XF), ob.Field(lay, 1, 0, YF)] + [ob.Field(lay, 1, 1) for _ in range(4)]
+        for x in f:
+            x.setval(1.0)
+        return ob.Op(lay, dx, 0.0, -1.0, bc, prm, *f)
+
+    opC, opF = op(layC, DX), op(layF, (DX[0] / 2, DX[1] / 2))
+    coarse = field(layC, wrap(Z["prolong2_coarse"]), 1)
+    fine = ob.Field(layF, 1, 1)
+    g = np.zeros((2 * NY + 2, 2 * NX + 2))
+    g[bx[1] + 1:bx[3] + 2, bx[0] + 1:bx[2] + 2] = Z["prolong2_fine_in"]
+    fine.set_global(g, (-1, -1))
+    temp = ob.Field(layF.coarsen(2), 1, 1)
+    opF.amr_prolong_s2(fine, coarse, temp, opC)
+    got = fine.get_global()[bx[1]:bx[3] + 1, bx[0]:bx[2] + 1]
+    same(got, "prolong2_out")
