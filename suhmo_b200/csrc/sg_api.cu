@@ -427,7 +427,11 @@ static int layout_host(sg_layout* L) {
     // across ranks only full-width y-strips of a level that covers the whole domain are stored merged (NCCL row exchange)
     if (c->nranks > 1 && has[r] && (rp[r].lo[0] != L->domain.lo[0] || rp[r].hi[0] != L->domain.hi[0])) tiles = false;
   }
-  if (c->nranks > 1 && covered != L->domain.npts()) tiles = false;
+  // A level is stored merged only when its boxes cover the whole domain (every base level does).  A refined level whose boxes
+  // happen to tile a rectangle stays a list of per-box patches: merged storage has no private ghost cells between boxes, and
+  // AMRProlongS_2 reads such cells where two boxes meet on a physical boundary (the corner ghost cell of the coarsened scratch outside
+  // the domain, which neither the boundary condition nor the corner exchange fills, src/AMRNonLinearPoissonOp.cpp:1155-1172).
+  if (covered != L->domain.npts()) tiles = false;
   L->has_local = has[c->rank];
   L->patch_of_box.assign(L->nbox, -1);
   L->gp.clear();

@@ -3,20 +3,23 @@
 // member functions (compute_grad_head, compute_grad_zb_ec, evaluate_Re_quadratic, evaluate_Qw_ec, aCoeff_bCoeff, dCoeff,
 // Calc_meltingRate, CalcRHS_gapHeightFAS, Calc_moulin_source_term_distributed, SolveForHead_nl, SolveForGap_nl, timeStepFAS) in the
 // order the reference calls them; every field stays on the device from the first Picard iteration to the end of the step, and each
-// statement of the reference that touches field data is one call into the C ABI.  What the reference does around the step (run():
-// dt control, plot / checkpoint cadence; regrid(): tagCells + BRMeshRefine + destructiveRegrid, available here as
-// tagCellsLevel / BRMeshRefine / regridTransfer in suhmo_gpu.hpp) stays with the caller.
+// statement of the reference that touches field data is one call into the C ABI.  AmrHydro::regrid (src/AmrHydro.cpp:4227-4511:
+// tagCells, BRMeshRefine::regrid, destructiveRegrid of every persistent field, ghost fills) is here too; the analytic
+// re-initialisation it calls on the IBC object is a hook (HydroIBC below: the IBC classes are outside this path).  What the
+// reference does around these two (run(): dt control, plot / checkpoint cadence) stays with the caller.
 //
 // The explicit gap-height update runs on any number of levels; the implicit one (solver.use_ImplDiff) on one level, as every
 // reference input that sets it is single-level (the C ABI answers SG_ERR_UNSUPPORTED otherwise).
 //
-// Checked on the GPU by tests/cpp/timestep_host.cpp against the CPU oracle's independent restatement of the same function
-// (oracle/picard_amr.py): Picard iteration counts, V-cycle counts, convergence measures, head and gap height, bit for bit.
+// Checked on the GPU by tests/cpp/timestep_host.cpp against the CPU oracle's independent restatement of the same functions
+// (oracle/picard_amr.py, oracle/br_regrid.py): Picard iteration counts, V-cycle counts, convergence measures, head and gap height bit
+// for bit, and after a regrid the same boxes, box for box.
 #pragma once
 #include <algorithm>
 #include <array>
 #include <memory>
-#include <stdexcept>
+#include <map>
+#include <string>
 
 #include "suhmo_gpu.hpp"
 
@@ -33,6 +36,23 @@ struct TimeStepReport {
   int gap_cycles = -1;              // V-cycles of the implicit gap solve, -1 when explicit
 };
 
+class AmrHydro;
+// The part of HydroIBC that AmrHydro::regrid calls on a redefined level (src/AmrHydro.cpp:4348-4392): initializeBed + initializePi
+// re-evaluate the closed-form bed / overburden pressure on the new boxes, setup_iceMask derives the mask from the pressure.  The
+// default keeps what destructiveRegrid interpolated from the coarser level and the old boxes.
+struct HydroIBC {
+  virtual ~HydroIBC() {}
+  virtual void initializeBedAndPi(AmrHydro&, int /*lev*/) {}
+  virtual void setup_iceMask(AmrHydro&, int /*lev*/) {}
+};
+
+// one tagging variable of the input file (amr.tag_var / tagging_val_min / tagging_val_max / tag_cap / tag_min)
+struct TagVar {
+  std::string var;   // "meltingRate", "Pi" or "GapHeight" (src/AmrHydro.cpp:4549-4571)
+  double val_min, val_max;
+  int cap, min_level;
+};
+
 class AmrHydro {
  public:
   typedef std::unique_ptr<LevelData> Ptr;
@@ -42,7 +62,17 @@ class AmrHydro {
   };
 
   Context& m_ctx;
-  std::vector<DisjointBoxLayout*> m_amrGrids;   // borrowed, coarsest first; refinement ratio 2 throughout (src/AmrHydro.cpp:1467)
+  std::vector<DisjointBoxLayout*> m_amrGrids;   // coarsest first; refinement ratio 2 throughout (src/AmrHydro.cpp:1467); the caller's
+                                                // until a regrid replaces levels >= 1 with layouts this object owns:
+  std::vector<std::unique_ptr<DisjointBoxLayout>> m_ownedGrids;
+  double m_coarsestDx[2];
+  // regrid controls (amr.* keys, src/AmrHydro.cpp:892-1122)
+  Box m_domain0{{0, 0}, {-1, -1}};
+  int m_periodic[2] = {0, 0};
+  int m_max_level = 0, m_block_factor = 8, m_nesting_radius = 1, m_max_box_size = 64, m_tags_grow = 1, m_tags_grow_dir[2] = {0, 0}, m_n_regrids = 0;
+  double m_fill_ratio = 0.85;
+  std::vector<TagVar> m_tag_vars;
+  bool m_regrid = false;
   std::vector<std::array<double, 2>> m_amrDx;
   sg_params m_prm;                              // suhmo.* / solver.* values of the head operator
   sg_bc m_bc;                                   // bc.lo_bc / bc.hi_bc / values (ParseBC)
@@ -61,42 +91,59 @@ class AmrHydro {
   std::vector<Ptr> a_head_lagged, RHS_h, RHS_b, a_diffusiveTerm, aCoef, a_qgh, a_qgz, a_work, a_gh_curr, aCoef_GH;
   std::vector<FluxPtr> a_gapheight_ec, a_meltRate_ec, a_gradZb_ec, a_Dcoef, a_Re_ec, a_Qw_ec, a_tmp1_ec, a_tmp2_ec, bCoef;
 
-  VCAMRNonLinearPoissonOpFactory m_opFactory;
+  std::unique_ptr<VCAMRNonLinearPoissonOpFactory> m_opFactory;
   std::vector<std::unique_ptr<VCAMRNonLinearPoissonOp>> m_ops;
   std::unique_ptr<AMRFASMultiGrid> m_amrSolver;
 
-  // levelSetup (src/AmrHydro.cpp:5059-5088) for every level + the operator factory on the solver's coefficient fields
   AmrHydro(Context& ctx, const std::vector<DisjointBoxLayout*>& grids, const double coarsestDx[2], const sg_params& prm, const sg_bc& bc,
            const sg_picard_params& suhmoParm)
       : m_ctx(ctx), m_amrGrids(grids), m_prm(prm), m_bc(bc), m_suhmoParm(suhmoParm) {
+    m_coarsestDx[0] = coarsestDx[0]; m_coarsestDx[1] = coarsestDx[1];
     m_use_mask_gradients = prm.use_mask_grad != 0;
     m_use_ImplDiff = suhmoParm.use_ImplDiff != 0;
-    const size_t n = grids.size();
-    double f = 1.0;
-    for (size_t l = 0; l < n; l++, f *= 2.0) m_amrDx.push_back({coarsestDx[0] / f, coarsestDx[1] / f});
-    for (std::vector<Ptr>* v : {&m_head, &m_gapheight, &m_old_head, &m_old_gapheight, &m_Pw, &m_Re, &m_meltRate, &m_magVel, &m_bedelevation,
-                                &m_overburdenpress, &m_moulin_source_term, &m_bumpHeight, &m_bumpSpacing, &m_iceMask, &a_head_lagged, &a_work})
-      for (size_t l = 0; l < n; l++) v->emplace_back(new LevelData(*grids[l], 1, 1));
-    for (std::vector<Ptr>* v : {&m_gradhead, &a_qgh, &a_qgz})
-      for (size_t l = 0; l < n; l++) v->emplace_back(new LevelData(*grids[l], 2, 1));
-    for (std::vector<Ptr>* v : {&RHS_h, &RHS_b, &a_diffusiveTerm, &aCoef})
-      for (size_t l = 0; l < n; l++) v->emplace_back(new LevelData(*grids[l], 1, 0));
-    for (std::vector<FluxPtr>* v : {&m_gradhead_ec, &m_iceMask_ec, &a_gapheight_ec, &a_meltRate_ec, &a_gradZb_ec, &a_Dcoef, &a_Re_ec, &a_Qw_ec,
-                                    &a_tmp1_ec, &a_tmp2_ec, &bCoef})
-      for (size_t l = 0; l < n; l++) {
-        v->emplace_back();
-        v->back().d[0].reset(new LevelData(*grids[l], 1, 0, XFace));
-        v->back().d[1].reset(new LevelData(*grids[l], 1, 0, YFace));
-      }
-    // opFactory.define(..., alpha = 0, aCoef, beta = -1, bCoef, ..., B, Pi, zb, iceMask) (src/AmrHydro.cpp:704-717)
-    std::vector<LevelData*> a, bx, by;
-    for (size_t l = 0; l < n; l++) { a.push_back(aCoef[l].get()); bx.push_back(bCoef[l].d[0].get()); by.push_back(bCoef[l].d[1].get()); }
-    m_opFactory.define(ctx, grids, std::vector<int>(n > 0 ? n - 1 : 0, 2), coarsestDx, bc, 0.0, a, -1.0, bx, by, prm, raw(m_gapheight),
-                       raw(m_overburdenpress), raw(m_bedelevation), raw(m_iceMask));
-    for (size_t l = 0; l < n; l++) m_ops.emplace_back(m_opFactory.AMRnewOp((int)l));
+    for (size_t l = 0; l < grids.size(); l++) levelSetup((int)l);
+    defineOperators();
   }
   // solver and operators go before the factory and the fields they were defined on
-  ~AmrHydro() { m_amrSolver.reset(); m_ops.clear(); }
+  ~AmrHydro() { dropOperators(); }
+
+  std::vector<std::vector<Ptr>*> cellFields1() {   // one component, one ghost cell
+    return {&m_head, &m_gapheight, &m_old_head, &m_old_gapheight, &m_Pw, &m_Re, &m_meltRate, &m_magVel, &m_bedelevation, &m_overburdenpress,
+            &m_moulin_source_term, &m_bumpHeight, &m_bumpSpacing, &m_iceMask, &a_head_lagged, &a_work};
+  }
+  std::vector<std::vector<Ptr>*> cellFields2() { return {&m_gradhead, &a_qgh, &a_qgz}; }                   // two components, one ghost cell
+  std::vector<std::vector<Ptr>*> cellFields0() { return {&RHS_h, &RHS_b, &a_diffusiveTerm, &aCoef}; }      // no ghost cell
+  std::vector<std::vector<FluxPtr>*> faceFields() {
+    return {&m_gradhead_ec, &m_iceMask_ec, &a_gapheight_ec, &a_meltRate_ec, &a_gradZb_ec, &a_Dcoef, &a_Re_ec, &a_Qw_ec, &a_tmp1_ec, &a_tmp2_ec, &bCoef};
+  }
+  // levelSetup (src/AmrHydro.cpp:5059-5088): every field of level lev on m_amrGrids[lev]; what was there before is released
+  void levelSetup(int lev) {
+    DisjointBoxLayout& g = *m_amrGrids[lev];
+    const size_t n = (size_t)lev + 1;
+    if (m_amrDx.size() < n) m_amrDx.resize(n);
+    m_amrDx[lev] = {m_coarsestDx[0] / (double)(1 << lev), m_coarsestDx[1] / (double)(1 << lev)};
+    for (std::vector<Ptr>* v : cellFields1()) { if (v->size() < n) v->resize(n); (*v)[lev].reset(new LevelData(g, 1, 1)); }
+    for (std::vector<Ptr>* v : cellFields2()) { if (v->size() < n) v->resize(n); (*v)[lev].reset(new LevelData(g, 2, 1)); }
+    for (std::vector<Ptr>* v : cellFields0()) { if (v->size() < n) v->resize(n); (*v)[lev].reset(new LevelData(g, 1, 0)); }
+    for (std::vector<FluxPtr>* v : faceFields()) {
+      if (v->size() < n) v->resize(n);
+      (*v)[lev].d[0].reset(new LevelData(g, 1, 0, XFace));
+      (*v)[lev].d[1].reset(new LevelData(g, 1, 0, YFace));
+    }
+    if (!a_gh_curr.empty()) { a_gh_curr.clear(); aCoef_GH.clear(); }   // re-made on the next implicit gap solve
+  }
+  // opFactory.define(..., alpha = 0, aCoef, beta = -1, bCoef, ..., B, Pi, zb, iceMask) (src/AmrHydro.cpp:704-717) + one operator per level
+  void defineOperators() {
+    dropOperators();
+    const size_t n = m_amrGrids.size();
+    std::vector<LevelData*> a, bx, by;
+    for (size_t l = 0; l < n; l++) { a.push_back(aCoef[l].get()); bx.push_back(bCoef[l].d[0].get()); by.push_back(bCoef[l].d[1].get()); }
+    m_opFactory.reset(new VCAMRNonLinearPoissonOpFactory);
+    m_opFactory->define(m_ctx, m_amrGrids, std::vector<int>(n > 0 ? n - 1 : 0, 2), m_coarsestDx, m_bc, 0.0, a, -1.0, bx, by, m_prm, raw(m_gapheight),
+                        raw(m_overburdenpress), raw(m_bedelevation), raw(m_iceMask));
+    for (size_t l = 0; l < n; l++) m_ops.emplace_back(m_opFactory->AMRnewOp((int)l));
+  }
+  void dropOperators() { m_amrSolver.reset(); m_ops.clear(); m_opFactory.reset(); }
 
   int finestLevel() const { return (int)m_amrGrids.size() - 1; }
   static std::vector<LevelData*> raw(std::vector<Ptr>& v) {
@@ -194,7 +241,7 @@ class AmrHydro {
   std::vector<double> SolveForHead_nl(int fixedCycles = 0) {
     if (!m_amrSolver) {
       m_amrSolver.reset(new AMRFASMultiGrid);
-      m_amrSolver->define(m_opFactory, (int)m_amrGrids.size());
+      m_amrSolver->define(*m_opFactory, (int)m_amrGrids.size());
     } else {
       m_amrSolver->refresh();   // the reference rebuilds factory and solver per call (:704-735); the coefficients changed, the grids did not
     }
@@ -210,6 +257,91 @@ class AmrHydro {
     std::vector<double> hist;
     m_amrSolver->solve(raw(m_head), raw(RHS_h), finestLevel(), 0, nullptr, &hist);
     return hist;
+  }
+
+  // ---- regridding ------------------------------------------------------------------------------------------------------------
+  // what regrid() needs beyond the constructor's arguments: the level-0 domain (amr.num_cells, amr.is_periodic)
+  void setDomain(const Box& domain0, const int periodic[2]) { m_domain0 = domain0; m_periodic[0] = periodic[0]; m_periodic[1] = periodic[1]; }
+  std::vector<Box> levelBoxes(int lev) const { return m_amrGrids[lev]->boxes; }
+
+  // tagCells + tagCellsLevel (src/AmrHydro.cpp:4514-4604): one byte map per level 0..top, tags of every variable ORed together
+  void tagCells(std::vector<std::vector<unsigned char>>& a_tags) {
+    for (size_t l = 0; l < a_tags.size(); l++) a_tags[l].assign((size_t)(m_domain0.hi[0] - m_domain0.lo[0] + 1) * (m_domain0.hi[1] - m_domain0.lo[1] + 1) << (2 * l), 0);
+    for (const TagVar& t : m_tag_vars) {
+      const int top_level = std::min(t.cap, std::min((int)a_tags.size() - 1, finestLevel()));
+      for (int lev = std::max(t.min_level, 0); lev <= top_level; lev++) {
+        std::vector<Ptr>* src = t.var == "meltingRate" ? &m_meltRate : t.var == "Pi" ? &m_overburdenpress : t.var == "GapHeight" ? &m_gapheight : nullptr;
+        if (!src) { std::fprintf(stderr, "suhmo_gpu: tagCellsLevel: wrong tagging value %s\n", t.var.c_str()); std::abort(); }   // MayDay::Error
+        tagCellsLevel(*(*src)[lev], t.val_min, t.val_max, m_tags_grow, m_tags_grow_dir, a_tags[lev], true);
+      }
+    }
+  }
+
+  // AmrHydro::regrid (src/AmrHydro.cpp:4227-4511).  Returns the new finest level.  Level 0 keeps its grids (m_regrid_lbase = 0).
+  // m_moulin_source_term: the reference re-allocates it and recomputes it from the moulins in the next time step (:2799-2836); here it
+  // is recomputed the same way when moulins are set and carried over by destructiveRegrid otherwise (it is an input field then).
+  int regrid(HydroIBC* ibc = nullptr) {
+    if (m_tag_vars.empty()) { std::fprintf(stderr, "suhmo_gpu: regrid needs a tagging variable\n"); std::abort(); }   // MayDay::Error, :4235
+    if (m_max_level <= 0) { m_regrid = true; return finestLevel(); }
+    if (m_domain0.hi[0] < m_domain0.lo[0]) { std::fprintf(stderr, "suhmo_gpu: regrid needs setDomain()\n"); std::abort(); }
+    m_n_regrids++;
+    std::vector<std::vector<unsigned char>> tagVect((size_t)std::min(finestLevel(), m_max_level - 1) + 1);
+    tagCells(tagVect);
+    BRMeshRefine meshrefine(m_domain0, m_fill_ratio, m_block_factor, m_nesting_radius, m_max_box_size);
+    std::vector<std::vector<Box>> new_grids;
+    const int new_finest_level = meshrefine.regrid(new_grids, levelBoxes(0), tagVect);
+    // the operators and the solver hold the old grids and fields: gone before either is
+    dropOperators();
+    const int old_finest_level = finestLevel();
+    std::vector<std::vector<Ptr>*> transfer = {&m_head, &m_gapheight, &m_bumpHeight, &m_bumpSpacing, &m_bedelevation, &m_overburdenpress,
+                                               &m_magVel, &m_meltRate, &m_Pw, &m_iceMask};
+    if (m_moulins.empty()) transfer.push_back(&m_moulin_source_term);
+    std::vector<std::unique_ptr<DisjointBoxLayout>> oldGrids;                       // declared first: outlives the old fields below
+    std::map<std::vector<Ptr>*, std::vector<Ptr>> oldData;
+    for (std::vector<Ptr>* v : transfer) {
+      oldData[v].resize((size_t)std::max(old_finest_level, new_finest_level) + 1);
+      for (int lev = 1; lev <= old_finest_level; lev++) oldData[v][lev] = std::move((*v)[lev]);
+    }
+    // levels above the new finest one disappear; the others are redefined on the new boxes
+    for (std::vector<Ptr>* v : cellFields1()) v->resize((size_t)new_finest_level + 1);
+    for (std::vector<Ptr>* v : cellFields2()) v->resize((size_t)new_finest_level + 1);
+    for (std::vector<Ptr>* v : cellFields0()) v->resize((size_t)new_finest_level + 1);
+    for (std::vector<FluxPtr>* v : faceFields()) v->resize((size_t)new_finest_level + 1);
+    std::vector<std::unique_ptr<DisjointBoxLayout>> newOwned((size_t)new_finest_level + 1);
+    m_amrGrids.resize((size_t)new_finest_level + 1);
+    m_amrDx.resize((size_t)new_finest_level + 1);
+    for (int lev = 1; lev <= new_finest_level; lev++) {
+      const Box dom{{m_domain0.lo[0] << lev, m_domain0.lo[1] << lev}, {((m_domain0.hi[0] + 1) << lev) - 1, ((m_domain0.hi[1] + 1) << lev) - 1}};
+      newOwned[lev].reset(new DisjointBoxLayout(m_ctx, new_grids[lev], std::vector<int>(), dom, m_periodic));   // LoadBalance: one rank
+      m_amrGrids[lev] = newOwned[lev].get();
+      levelSetup(lev);
+    }
+    defineOperators();   // on the new grids: their copy plans serve the transfers below
+    for (int lev = 1; lev <= new_finest_level; lev++) {
+      // destructiveRegrid (:4176-4223): FineInterp from the coarser level, old data where the old boxes were, coarse-fine ghost cells
+      for (std::vector<Ptr>* v : transfer) m_ops[lev]->regridTransfer(*(*v)[lev], oldData[v][lev].get(), *(*v)[lev - 1]);
+      for (std::vector<Ptr>* v : {&m_bumpHeight, &m_bumpSpacing, &m_magVel, &m_meltRate, &m_Pw}) ExtrapGhostCells(*(*v)[lev]);
+      if (ibc) ibc->initializeBedAndPi(*this, lev);
+      fillInterp(lev, m_bedelevation);
+      fillInterp(lev, m_overburdenpress);
+      m_bedelevation[lev]->exchange();
+      m_overburdenpress[lev]->exchange();
+      CopyGhostCells(*m_bedelevation[lev]);
+      ExtrapGhostCells(*m_overburdenpress[lev]);
+      if (ibc) ibc->setup_iceMask(*this, lev);
+      fillInterp(lev, m_iceMask);
+      m_iceMask[lev]->exchange();
+      CopyGhostCells(*m_iceMask[lev]);
+      setup_iceMask_EC(*m_iceMask[lev], m_iceMask_ec[lev][0], m_iceMask_ec[lev][1]);
+    }
+    // old fields first, then the layouts they lived on
+    oldData.clear();
+    for (size_t lev = 1; lev < m_ownedGrids.size(); lev++) oldGrids.push_back(std::move(m_ownedGrids[lev]));
+    m_ownedGrids = std::move(newOwned);
+    oldGrids.clear();
+    defineOperators();   // once more, now that the coefficient fields hold data
+    m_regrid = true;
+    return new_finest_level;
   }
 
   // ---- timeStepFAS, in the reference's four parts -----------------------------------------------------------------------------
@@ -333,6 +465,8 @@ class AmrHydro {
     TimeStepReport rep;
     m_cur_step += 1;   // :2259 -- the solver parameters and the Picard test below read the incremented counter
     beginStep();
+    if (m_regrid && !m_moulins.empty()) Calc_moulin_source_term_distributed();   // :2799-2836, "useful for insane amount of moulins"
+    m_regrid = false;
     int ite_idx = 0;
     bool converged_h = false;
     while (!converged_h) {

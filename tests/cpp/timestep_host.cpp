@@ -20,8 +20,11 @@ using namespace sg;
 
 static const int N_IN = 10;   // head B Pi zb mask MV BH BL mR MS
 struct BoxIn { Box box; std::vector<double> in[N_IN]; };
+struct RegridSpec { int var = 0, tags_grow = 0, grow_dir[2] = {0, 0}, block_factor = 0, nesting_radius = 0, max_box_size = 0, max_level = 0; double val_min = 0, val_max = 0, fill_ratio = 0; };
 struct StepOut {
-  int picard = 0, gap_cycles = -1;
+  int picard = 0, gap_cycles = -1, regrid = 0;
+  RegridSpec rg;
+  std::vector<std::vector<Box>> boxes;   // the hierarchy this step runs on (levels >= 1 rewritten by a regrid)
   std::vector<int> cycles;
   std::vector<double> x_h;
   std::vector<std::vector<std::vector<double>>> head, gap;   // [level][box][cell]
@@ -64,16 +67,40 @@ static bool load(const char* path, Fixture& F) {
       F.lev.back().push_back(std::move(d));
     }
   }
+  std::vector<std::vector<Box>> cur(F.nlev);
+  for (int l = 0; l < F.nlev; l++)
+    for (const BoxIn& d : F.lev[l]) cur[l].push_back(d.box);
   for (int s = 0; ok && s < F.nsteps; s++) {
     StepOut o;
-    ok = rd(f, &o.picard, 4) && o.picard > 0 && o.picard < 200;
+    ok = rd(f, &o.regrid, 4);
+    if (ok && o.regrid) {
+      double r3[3];
+      int i7[7], nlev = 0;
+      ok = rd(f, &o.rg.var, 4) && rd(f, r3, sizeof r3) && rd(f, i7, sizeof i7) && rd(f, &nlev, 4) && nlev >= 1 && nlev < 8;
+      o.rg.val_min = r3[0]; o.rg.val_max = r3[1]; o.rg.fill_ratio = r3[2];
+      o.rg.tags_grow = i7[0]; o.rg.grow_dir[0] = i7[1]; o.rg.grow_dir[1] = i7[2]; o.rg.block_factor = i7[3]; o.rg.nesting_radius = i7[4];
+      o.rg.max_box_size = i7[5]; o.rg.max_level = i7[6];
+      cur.resize(ok ? nlev : 1);
+      for (int l = 1; ok && l < nlev; l++) {
+        int nbox = 0;
+        ok = rd(f, &nbox, 4) && nbox > 0 && nbox < (1 << 20);
+        cur[l].assign(ok ? nbox : 0, Box{{0, 0}, {0, 0}});
+        for (int b = 0; ok && b < nbox; b++) {
+          int bx[4];
+          ok = rd(f, bx, sizeof bx);
+          cur[l][b] = Box{{bx[0], bx[1]}, {bx[2], bx[3]}};
+        }
+      }
+    }
+    o.boxes = cur;
+    ok = ok && rd(f, &o.picard, 4) && o.picard > 0 && o.picard < 200;
     if (!ok) break;
     o.cycles.resize(o.picard); o.x_h.resize(o.picard);
     ok = rd(f, o.cycles.data(), 4 * (size_t)o.picard) && rd(f, o.x_h.data(), 8 * (size_t)o.picard) && rd(f, &o.gap_cycles, 4);
-    o.head.resize(F.nlev); o.gap.resize(F.nlev);
-    for (int l = 0; ok && l < F.nlev; l++)
-      for (size_t b = 0; ok && b < F.lev[l].size(); b++) {
-        const Box& bx = F.lev[l][b].box;
+    o.head.resize(cur.size()); o.gap.resize(cur.size());
+    for (size_t l = 0; ok && l < cur.size(); l++)
+      for (size_t b = 0; ok && b < cur[l].size(); b++) {
+        const Box& bx = cur[l][b];
         const size_t nv = (size_t)(bx.hi[0] - bx.lo[0] + 1) * (bx.hi[1] - bx.lo[1] + 1);
         o.head[l].emplace_back(nv); o.gap[l].emplace_back(nv);
         ok = rd(f, o.head[l].back().data(), nv * 8) && rd(f, o.gap[l].back().data(), nv * 8);
@@ -93,10 +120,10 @@ static int g_fail = 0;
   } while (0)
 
 // valid cells of a one-ghost-cell field against the fixture; returns the number of cells that differ
-static long long compare(LevelData& f, const std::vector<BoxIn>& boxes, const std::vector<std::vector<double>>& expect, long long& cells) {
+static long long compare(LevelData& f, const std::vector<Box>& boxes, const std::vector<std::vector<double>>& expect, long long& cells) {
   long long differ = 0;
   for (size_t b = 0; b < boxes.size(); b++) {
-    const Box& bx = boxes[b].box;
+    const Box& bx = boxes[b];
     const int nx = bx.hi[0] - bx.lo[0] + 1, ny = bx.hi[1] - bx.lo[1] + 1;
     std::vector<double> fab((size_t)(nx + 2) * (ny + 2));
     f.download((int)b, fab.data());
@@ -116,8 +143,29 @@ static void run(Context& ctx, const Fixture& F, std::vector<DisjointBoxLayout*>&
   for (int l = 0; l < F.nlev; l++)
     for (size_t b = 0; b < F.lev[l].size(); b++)
       for (int k = 0; k < N_IN; k++) (*inputs[k])[l]->upload((int)b, F.lev[l][b].in[k].data());
+  const char* tagNames[3] = {"meltingRate", "Pi", "GapHeight"};
+  const int periodic[2] = {F.periodic[0], F.periodic[1]};
+  amrObject.setDomain(Box{{0, 0}, {F.nx - 1, F.ny - 1}}, periodic);
   for (int s = 0; s < F.nsteps; s++) {
     const StepOut& o = F.steps[s];
+    if (o.regrid) {
+      // AmrHydro::regrid with the fixture's amr.* values: the same boxes as the oracle's Berger-Rigoutsos, box for box
+      amrObject.m_tag_vars = {TagVar{tagNames[o.rg.var], o.rg.val_min, o.rg.val_max, 100, 0}};
+      amrObject.m_max_level = o.rg.max_level; amrObject.m_fill_ratio = o.rg.fill_ratio; amrObject.m_block_factor = o.rg.block_factor;
+      amrObject.m_nesting_radius = o.rg.nesting_radius; amrObject.m_max_box_size = o.rg.max_box_size; amrObject.m_tags_grow = o.rg.tags_grow;
+      amrObject.m_tags_grow_dir[0] = o.rg.grow_dir[0]; amrObject.m_tags_grow_dir[1] = o.rg.grow_dir[1];
+      const int finest = amrObject.regrid();
+      EXPECT(finest + 1 == (int)o.boxes.size(), "step %d: regrid gave %d levels, the oracle %zu", s, finest + 1, o.boxes.size());
+      long long nb = 0, bad = 0;
+      for (int l = 1; l <= finest && l < (int)o.boxes.size(); l++) {
+        std::vector<Box> got = amrObject.levelBoxes(l);
+        EXPECT(got.size() == o.boxes[l].size(), "step %d: regrid gave %zu boxes on level %d, the oracle %zu", s, got.size(), l, o.boxes[l].size());
+        for (size_t b = 0; b < got.size() && b < o.boxes[l].size(); b++, nb++) bad += std::memcmp(&got[b], &o.boxes[l][b], sizeof(Box)) != 0;
+      }
+      std::printf("timestep_host: step %d: regrid -> %d levels, %lld boxes compared with the oracle's, %lld differ\n", s, finest + 1, nb, bad);
+      EXPECT(bad == 0, "step %d: regrid boxes differ from the oracle's", s);
+      if (g_fail) return;
+    }
     const long long launches0 = ctx.kernelLaunches();
     TimeStepReport rep = amrObject.timeStepFAS(F.dt);
     ctx.sync();
@@ -131,9 +179,9 @@ static void run(Context& ctx, const Fixture& F, std::vector<DisjointBoxLayout*>&
       EXPECT(std::memcmp(&rep.x_h[k], &o.x_h[k], 8) == 0, "step %d Picard %d: x_h %.17g, the oracle has %.17g", s, k, rep.x_h[k], o.x_h[k]);
     }
     long long cells = 0, dh = 0, db = 0;
-    for (int l = 0; l < F.nlev; l++) {
-      dh += compare(*amrObject.m_head[l], F.lev[l], o.head[l], cells);
-      db += compare(*amrObject.m_gapheight[l], F.lev[l], o.gap[l], cells);
+    for (int l = 0; l <= amrObject.finestLevel() && l < (int)o.boxes.size(); l++) {
+      dh += compare(*amrObject.m_head[l], o.boxes[l], o.head[l], cells);
+      db += compare(*amrObject.m_gapheight[l], o.boxes[l], o.gap[l], cells);
     }
     std::printf("timestep_host: step %d: head and gap height compared with the oracle on %lld values, %lld + %lld differ\n", s, cells, dh, db);
     EXPECT(dh == 0 && db == 0 && cells > 0, "step %d: head / gap height not bit-identical to the oracle's", s);

@@ -121,7 +121,10 @@ def amr_hierarchy(name="C5"):
     "C4":     2 levels on the valley geometry (256x64, exec/E_SHMIP): ice mask < 0 inside the refined boxes AND across the
               coarse-fine interface, masked gradients (solver.use_mask_for_gradients), cut_solve_outside_domain -- the BASELINE
               config where the masked coarse-fine gradient and the mask-streaming smoother matter.
-    "C5_256": 3 levels on the AMR_multiMoulins base grid at its native 256x256 size (16 boxes of 64^2), the same shapes scaled."""
+    "C5_256": 3 levels on the AMR_multiMoulins base grid at its native 256x256 size (16 boxes of 64^2), the same shapes scaled.
+    "C5_BR":  3 levels on the 64x64 base grid as AmrHydro::regrid leaves them (tags on Pi > 5e6, fill ratio 0.7, block factor 8, nesting
+              radius 2, max box 32): Berger-Rigoutsos shapes -- 16x8 and 8x16 boxes, re-entrant corners one box wide, refined boxes
+              along two physical boundaries on both levels."""
     if name == "C4":
         cfg = syn.config("C4", 1)
         base = syn.domain_split(cfg.nx, cfg.ny, cfg.max_box_size, cfg.block_factor)
@@ -133,6 +136,12 @@ def amr_hierarchy(name="C5"):
         lev1 = np.array([(64, 64, 127, 127), (128, 64, 191, 127), (64, 128, 127, 191), (448, 0, 511, 63)], dtype=np.int32)
         lev2 = np.array([(160, 160, 223, 223), (224, 160, 287, 223), (160, 224, 223, 287)], dtype=np.int32)
         return cfg, [base, lev1, lev2]
+    if name == "C5_BR":
+        cfg, lv = amr_hierarchy("C5")
+        lev1 = np.array([(64, 0, 95, 15), (96, 0, 127, 31), (80, 16, 95, 23), (88, 24, 95, 39), (96, 32, 127, 63)], dtype=np.int32)
+        lev2 = np.array([(184, 0, 215, 31), (216, 0, 231, 31), (232, 0, 255, 31), (184, 32, 215, 47), (216, 32, 231, 47), (232, 32, 255, 47),
+                         (184, 48, 215, 71), (216, 48, 231, 71), (232, 48, 255, 71)], dtype=np.int32)
+        return cfg, [lv[0], lev1, lev2]
     cfg = syn.config(name, 1)
     cfg.nx, cfg.ny = 64, 64
     cfg.max_box_size = 32

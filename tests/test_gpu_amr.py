@@ -10,7 +10,8 @@ from tests.problem import AmrGpuSide, AmrOracleSide, amr_hierarchy, fabs_equal, 
 pytestmark = pytest.mark.gpu
 
 
-HIERS = ["C5", "C4", "C5_256"]  # tests/problem.py:amr_hierarchy -- 64^2 3-level, valley 2-level with ice mask < 0, 256^2 3-level
+HIERS = ["C5", "C4", "C5_256", "C5_BR"]  # tests/problem.py:amr_hierarchy -- 64^2 3-level, valley 2-level with ice mask < 0, 256^2 3-level,
+# 64^2 3-level with the Berger-Rigoutsos shapes a regrid leaves (narrow boxes, refined boxes along the physical boundary on both levels)
 
 
 def make(ctx, nlev=None, hier="C5", **kw):
@@ -166,7 +167,7 @@ def test_refined_level_smoother_variants(gpu_ctx, hier, mode):
         gpu_ctx.set_tuning(7, 0)
 
 
-@pytest.mark.parametrize("nlev,hier", [(2, "C5"), (3, "C5"), (2, "C4"), (2, "C5_256"), (3, "C5_256")])
+@pytest.mark.parametrize("nlev,hier", [(2, "C5"), (3, "C5"), (2, "C4"), (2, "C5_256"), (3, "C5_256"), (2, "C5_BR"), (3, "C5_BR")])
 def test_amr_fixed_vcycles_parity(gpu_ctx, nlev, hier):
     cfg, orc, gpu = make(gpu_ctx, nlev, hier)
     ncyc = 4
@@ -212,7 +213,7 @@ def test_against_golden_fixture_three_levels(gpu_ctx):
         assert np.array_equal(np.nan_to_num(gpu.F[l]["head"].get_global(), nan=0.0), z[f"head3_L{l}"]), f"level {l}"
 
 
-@pytest.mark.parametrize("hier,nlev", [("C5", 3), ("C4", 2), ("C5_256", 3)])
+@pytest.mark.parametrize("hier,nlev", [("C5", 3), ("C4", 2), ("C5_256", 3), ("C5_BR", 3)])
 def test_composite_sweeps_fused_vs_reference_flow(gpu_ctx, hier, nlev):
     """The V-cycle driver's shortcuts on the base level under a finer one -- (rhs - L phi) + L phi in one sweep with the cells next to /
     under the finer level redone by sparse kernels, norm-only residual sweeps, the FAS reference state kept on the coarsened-fine

@@ -20,7 +20,7 @@ def same(gpu_ld, orc_f, what, ghosts=False):
     assert eq, f"{what}: max abs diff {d:g} (expected bit-exact)"
 
 
-@pytest.mark.parametrize("hier", ["C5", "C4", "C5_256"])
+@pytest.mark.parametrize("hier", ["C5", "C4", "C5_256", "C5_BR"])
 def test_interlevel_transfers_bit_exact(gpu_ctx, hier):
     cfg, lv = amr_hierarchy(hier)
     H, st = build_oracle(cfg, lv), build_device(gpu_ctx, cfg, lv)
@@ -85,7 +85,7 @@ def test_moulin_recharge_to_tolerance(gpu_ctx):
         assert o[m].max() > 0
 
 
-@pytest.mark.parametrize("hier", ["C5", "C4"])
+@pytest.mark.parametrize("hier", ["C5", "C4", "C5_BR"])
 def test_multilevel_picard_and_gap_update_bit_exact(gpu_ctx, hier):
     from suhmo_b200.timestep_amr import AmrTimeStep
     cfg, lv = amr_hierarchy(hier)
