@@ -1,12 +1,12 @@
 // suhmo_amrhydro.hpp -- the time step of the reference's driver class, AmrHydro::timeStepFAS (src/AmrHydro.cpp:2255-3620), as C++ host
 // code over the device-resident layer of suhmo_gpu.hpp.  Same member names (m_head, m_gapheight, m_Re, m_meltRate, ...), the same
 // member functions (compute_grad_head, compute_grad_zb_ec, evaluate_Re_quadratic, evaluate_Qw_ec, aCoeff_bCoeff, dCoeff,
-// Calc_meltingRate, CalcRHS_gapHeightFAS, Calc_moulin_source_term_distributed, SolveForHead_nl, SolveForGap_nl, timeStepFAS) in the
+// Calc_meltingRate, CalcRHS_gapHeightFAS, Calc_moulin_source_term_distributed, SolveForHead_nl, SolveForGap_nl, timeStepFAS, computeDt, run) in the
 // order the reference calls them; every field stays on the device from the first Picard iteration to the end of the step, and each
 // statement of the reference that touches field data is one call into the C ABI.  AmrHydro::regrid (src/AmrHydro.cpp:4227-4511:
 // tagCells, BRMeshRefine::regrid, destructiveRegrid of every persistent field, ghost fills) is here too; the analytic
-// re-initialisation it calls on the IBC object is a hook (HydroIBC below: the IBC classes are outside this path).  What the
-// reference does around these two (run(): dt control, plot / checkpoint cadence) stays with the caller.
+// re-initialisation it calls on the IBC object is a hook (HydroIBC below: the IBC classes are outside this path), and so is
+// AmrHydro::run (:1283-1366) with the plot file as a hook; checkpoint files stay with the caller (no HDF5 in this build).
 //
 // The explicit gap-height update runs on any number of levels; the implicit one (solver.use_ImplDiff) on one level, as every
 // reference input that sets it is single-level (the C ABI answers SG_ERR_UNSUPPORTED otherwise).
@@ -44,6 +44,9 @@ struct HydroIBC {
   virtual ~HydroIBC() {}
   virtual void initializeBedAndPi(AmrHydro&, int /*lev*/) {}
   virtual void setup_iceMask(AmrHydro&, int /*lev*/) {}
+  // run() calls this where the reference writes its HDF5 plot file (src/AmrHydro.cpp:1312, 1344, 1350): the fields are on the device,
+  // LevelData::download brings back what the caller wants to keep
+  virtual void writePlotFile(AmrHydro&) {}
 };
 
 // one tagging variable of the input file (amr.tag_var / tagging_val_min / tagging_val_max / tag_cap / tag_min)
@@ -73,6 +76,11 @@ class AmrHydro {
   double m_fill_ratio = 0.85;
   std::vector<TagVar> m_tag_vars;
   bool m_regrid = false;
+  // time stepping controls of run() (amr.fixed_dt, cfl, initial_cfl, max_dt_grow_factor, regrid_interval, plot_interval, plot_time_interval)
+  double m_fixed_dt = 0.0, m_cfl = 0.25, m_initial_cfl = 0.25, m_max_dt_grow = 1.5, m_stable_dt = 0.0, m_plot_time_interval = 1.0e12;
+  int m_regrid_interval = 10000000, m_plot_interval = 10000000, m_restart_step = 0;
+  HydroIBC* m_IBCPtr = nullptr;                 // setIBC: what regrid() re-initialises a redefined level with
+  TimeStepReport m_lastReport;                  // of the most recent timeStepFAS
   std::vector<std::array<double, 2>> m_amrDx;
   sg_params m_prm;                              // suhmo.* / solver.* values of the head operator
   sg_bc m_bc;                                   // bc.lo_bc / bc.hi_bc / values (ParseBC)
@@ -489,6 +497,36 @@ class AmrHydro {
     rep.gap_cycles = updateGap(a_dt);
     m_time += a_dt;    // :4108
     return rep;
+  }
+  // computeDt / computeInitialDt (src/AmrHydro.cpp:5166-5224): amr.fixed_dt when set; otherwise the reference's "stable" dt is the
+  // constant 1e50 scaled by the CFL number and limited by max_dt_grow_factor -- kept as written
+  double computeDt() {
+    if (m_fixed_dt > 1.0e-8) return m_fixed_dt;   // TINY_NORM
+    double dt = 1.0e50;
+    dt *= m_cur_step == 0 ? m_initial_cfl : m_cfl;
+    if (m_max_dt_grow > 0 && dt > m_max_dt_grow * m_stable_dt && m_stable_dt > 0) dt = m_max_dt_grow * m_stable_dt;
+    m_stable_dt = dt;
+    return dt;
+  }
+  // run (src/AmrHydro.cpp:1283-1366): time steps until a_max_time or a_max_step, regridding every m_regrid_interval steps, the plot
+  // cadence handed to the IBC hook; checkpoints are the caller's business (no HDF5 here)
+  void run(double a_max_time, int a_max_step) {
+    const double TIME_EPS = 1.0e-12;
+    double dt = computeDt();   // computeInitialDt
+    if (!(m_plot_time_interval > TIME_EPS) || m_plot_time_interval > a_max_time) m_plot_time_interval = a_max_time;
+    while (a_max_time > m_time && m_cur_step < a_max_step) {
+      double next_plot_time = m_plot_time_interval * (1.0 + (double)(int)(m_time / m_plot_time_interval));
+      if (!(next_plot_time > m_time)) next_plot_time += m_plot_time_interval;
+      next_plot_time = std::min(next_plot_time, a_max_time);
+      while (next_plot_time > m_time && m_cur_step < a_max_step && dt > TIME_EPS) {
+        if (m_plot_interval > 0 && m_cur_step % m_plot_interval == 0 && m_IBCPtr) m_IBCPtr->writePlotFile(*this);
+        if (m_cur_step != 0 && m_cur_step != m_restart_step && m_cur_step % m_regrid_interval == 0) regrid(m_IBCPtr);
+        if (m_cur_step != 0) dt = computeDt();
+        if (next_plot_time - m_time + TIME_EPS < dt) dt = std::max(2 * TIME_EPS, next_plot_time - m_time);
+        m_lastReport = timeStepFAS(dt);
+      }
+      if (m_plot_interval >= 0 && m_IBCPtr) m_IBCPtr->writePlotFile(*this);
+    }
   }
 };
 

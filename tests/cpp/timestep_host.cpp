@@ -167,7 +167,17 @@ static void run(Context& ctx, const Fixture& F, std::vector<DisjointBoxLayout*>&
       if (g_fail) return;
     }
     const long long launches0 = ctx.kernelLaunches();
-    TimeStepReport rep = amrObject.timeStepFAS(F.dt);
+    // every other step goes through AmrHydro::run (one step of amr.fixed_dt up to max_step) instead of a direct call
+    TimeStepReport rep;
+    if (s % 2 == 1) {
+      amrObject.m_fixed_dt = F.dt;
+      const int before = amrObject.m_cur_step;
+      amrObject.run(amrObject.m_time + 10.0 * F.dt, before + 1);
+      EXPECT(amrObject.m_cur_step == before + 1, "run() took %d steps instead of one", amrObject.m_cur_step - before);
+      rep = amrObject.m_lastReport;
+    } else {
+      rep = amrObject.timeStepFAS(F.dt);
+    }
     ctx.sync();
     std::printf("timestep_host: step %d (m_cur_step %d): %d Picard iterations, V-cycles per head solve", s, amrObject.m_cur_step, rep.picard_iterations);
     for (int c : rep.head_cycles) std::printf(" %d", c);
