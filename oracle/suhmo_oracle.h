@@ -9,8 +9,10 @@
  *  and cannot be built here (no gfortran, MPI, HDF5 or Chombo).  The in-tree
  * Fortran kernels restated below ARE pinned: tools/chf_translate.py executes the reference's .ChF
  * sources (translated in memory) on seeded inputs, tests/golden/chf_kernels.npz keeps the outputs and
- * tests/test_oracle_chf_golden.py holds this oracle to them bit for bit.  PARITY UNPINNED remains
- * true at the Chombo boundary (next paragraph).  This file restates, operation by operation and in
+ * tests/test_oracle_chf_golden.py holds this oracle to them bit for bit; the C++ cell loops of the
+ * Picard body (melt rate, right-hand sides, gap update, moulin quadrature: src/AmrHydro.cpp) are
+ * pinned the same way through tools/cxx_translate.py, tests/golden/cxx_kernels.npz and
+ * tests/test_oracle_cxx_golden.py.  PARITY UNPINNED remains true at the Chombo boundary (next paragraph).  This file restates, operation by operation and in
  * the Fortran evaluation order, the in-tree kernels
  *     src/VCAMRNonLinearPoissonOpF.ChF, src/AMRNonLinearPoissonOpF.ChF:607-741,
  *     src/AmrHydroF.ChF, util/GradientF.ChF, util/ExtrapBCF.ChF, util/DivergenceF.ChF
