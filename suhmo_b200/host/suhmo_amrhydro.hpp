@@ -320,7 +320,9 @@ class AmrHydro {
     m_amrDx.resize((size_t)new_finest_level + 1);
     for (int lev = 1; lev <= new_finest_level; lev++) {
       const Box dom{{m_domain0.lo[0] << lev, m_domain0.lo[1] << lev}, {((m_domain0.hi[0] + 1) << lev) - 1, ((m_domain0.hi[1] + 1) << lev) - 1}};
-      newOwned[lev].reset(new DisjointBoxLayout(m_ctx, new_grids[lev], std::vector<int>(), dom, m_periodic));   // LoadBalance: one rank
+      // LoadBalance(procIDs, new_grids[lev]) (:4301-4302); one rank owns everything without it
+      const std::vector<int> procIDs = m_ctx.nranks > 1 ? LoadBalance(new_grids[lev], m_ctx.nranks) : std::vector<int>();
+      newOwned[lev].reset(new DisjointBoxLayout(m_ctx, new_grids[lev], procIDs, dom, m_periodic));
       m_amrGrids[lev] = newOwned[lev].get();
       levelSetup(lev);
     }

@@ -26,7 +26,9 @@ struct Box { int lo[2], hi[2]; };
 class Context {
  public:
   sg_ctx* h = nullptr;
-  explicit Context(int device = 0, int rank = 0, int nranks = 1, const void* nccl_uid = nullptr) { SG_DO(sg_ctx_create(&h, device, rank, nranks, nccl_uid)); }
+  int rank = 0, nranks = 1;   // procID() / numProc()
+  explicit Context(int device = 0, int a_rank = 0, int a_nranks = 1, const void* nccl_uid = nullptr) : rank(a_rank), nranks(a_nranks)
+  { SG_DO(sg_ctx_create(&h, device, a_rank, a_nranks, nccl_uid)); }
   ~Context() { sg_ctx_destroy(h); }
   Context(const Context&) = delete;
   Context& operator=(const Context&) = delete;
