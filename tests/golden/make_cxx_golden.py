@@ -9,6 +9,7 @@ What stands between the loop bodies and the arrays is stated at each case (which
 calls before the loop do).
 """
 import os
+import re
 import sys
 from types import SimpleNamespace
 
@@ -138,6 +139,43 @@ def main():
     out.update(moulin_lo=np.array(lo, dtype=np.int32), moulin_dx=np.array(dx[1]), moulin_pos=np.array(P.m_moulin_position), moulin_sigma=np.array(P.m_sigma),
                moulin_flux=np.array(P.m_moulin_flux), moulin_runoff=np.array(P.m_runoff), moulin_time=np.array(time), moulin_nonorm=tmp,
                moulin_integral=np.array(integ), moulin_source=ms[0])
+
+    # ---- 6. VCAMRNonLinearPoissonOp::getFlux (src/VCAMRNonLinearPoissonOp.cpp:792-841), what reflux evaluates on both sides of a
+    # coarse-fine face: BoxIterator over the face box, data with one ghost cell, `scale` from the statement just above the loop
+    vc = open("/root/reference/src/VCAMRNonLinearPoissonOp.cpp").read()
+    gf = X.strip_comments(X.function_text(vc, "void VCAMRNonLinearPoissonOp::getFlux"))
+    loops_gf = X.box_loops(gf)
+    assert len(loops_gf) == 1
+    scale_expr = re.search(r"Real\s+scale\s*=\s*([^;]+);", gf).group(1)
+    cell = X.compile_cell(loops_gf[0], ["a_data", "a_flux", "bCoefDir"])
+    phi = ghosted(rng, 1200.0, 1500.0)
+    dxv = [37.5, 41.0]
+    out.update(flux_phi=phi[0], flux_dx=np.array(dxv), flux_beta=np.array(-1.0))
+    for d in (0, 1):
+        bco = -(1e-3 + 1e-3 * rng.rand(1, NY + (d == 1), NX + (d == 0)))
+        out[f"flux_b{d}"] = bco[0]
+        for ref in (1, 2):
+            scale = eval(scale_expr, {"m_beta": -1.0, "a_ref": ref, "m_dx_vect": dxv, "a_dir": d})
+            fl = np.zeros_like(bco)
+            X.run_box(cell, dict(a_data=X.Fab(phi, (-1, -1)), a_flux=fl, bCoefDir=bco), P, dict(a_dir=d, scale=scale), NY + (d == 1), NX + (d == 0))
+            out[f"flux_dir{d}_ref{ref}"] = fl[0]
+
+    # ---- 7. HydroIBC::setup_iceMask_EC (src/HydroIBC.cpp:138-184), the edge-centred ice mask WFlx_level multiplies bCoef with: a box on
+    # the low-x side of a larger domain, the cell mask with one ghost cell
+    ib = X.strip_comments(X.function_text(open("/root/reference/src/HydroIBC.cpp").read(), "HydroIBC::setup_iceMask_EC"))
+    loops_im = X.box_loops(ib)
+    assert len(loops_im) == 1
+    cell = X.compile_cell(loops_im[0], ["thisIM", "thisIMEC_dir"])
+    blo, dom = (0, 2), (0, 0, 23, 15)
+    imask = np.where(rng.rand(1, NY + 2, NX + 2) < 0.3, -1.0, 1.0)
+    out.update(imec_lo=np.array(blo, dtype=np.int32), imec_domain=np.array(dom, dtype=np.int32), imec_mask=imask[0])
+    for d in (0, 1):
+        ec = np.full((1, NY + (d == 1), NX + (d == 0)), 7.0)
+        face_box = SimpleNamespace(smallEnd=lambda k, _d=d: dom[k], bigEnd=lambda k, _d=d: dom[2 + k] + (1 if k == _d else 0))
+        X.run_box(cell, dict(thisIM=X.Fab(imask, (blo[0] - 1, blo[1] - 1)), thisIMEC_dir=ec), P, dict(dir=d, face_box=face_box),
+                  NY + (d == 1), NX + (d == 0), blo)
+        assert set(np.unique(ec)) == {-1.0, 0.0, 1.0} and (ec[0][:, 0] == 0).all() == (d == 0)
+        out[f"imec_dir{d}"] = ec[0]
 
     path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "cxx_kernels.npz")
     np.savez_compressed(path, **out)

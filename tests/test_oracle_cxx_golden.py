@@ -2,7 +2,8 @@
 BoxIterator loop bodies of src/AmrHydro.cpp through tools/cxx_translate.py -- see tests/golden/make_cxx_golden.py; the reference tree
 is not needed here).  Bit for bit.  This pins the part of the Picard body that the reference writes in C++ rather than Fortran:
 Calc_meltingRate (:2175-2252), the right-hand side of the head equation (:3044-3077), CalcRHS_gapHeightFAS (:2070-2171) in its four
-mask / implicit variants, and the explicit gap-height update (:3394-3408).  The CUDA library is held bit for bit to the same oracle
+mask / implicit variants, the explicit gap-height update (:3394-3408), the moulin quadrature (:1867-2069), getFlux
+(src/VCAMRNonLinearPoissonOp.cpp:792-841) and setup_iceMask_EC (src/HydroIBC.cpp:138-184).  The CUDA library is held bit for bit to the same oracle
 functions on every configuration by tests/test_gpu_picard.py and tests/test_gpu_amr_picard.py."""
 import ctypes as C
 import os
@@ -107,3 +108,33 @@ def test_moulin_recharge_one_level():
     ob.lib().orc_moulin_source(src.h, tmp.h, n, dp(integ), dp(flux), float(Z["moulin_runoff"]), float(Z["moulin_time"]))
     got = src.fab(0)[0][0].copy()
     assert np.array_equal(got, Z["moulin_source"]), np.abs(got - Z["moulin_source"]).max()
+
+
+@pytest.mark.parametrize("d", [0, 1])
+@pytest.mark.parametrize("ref", [1, 2])
+def test_get_flux(d, ref):
+    """VCAMRNonLinearPoissonOp::getFlux (src/VCAMRNonLinearPoissonOp.cpp:792-841): flux = -bCoef * ((phi_hi - phi_lo) * (beta * ref / dx))
+    on every face of the box, the evaluation order of the reference's statements"""
+    lay = layout()
+    dx = tuple(float(v) for v in Z["flux_dx"])
+    one = lambda ng=0, cent=ob.CELL: ob.Field(lay, 1, ng, cent)  # noqa: E731
+    bX, bY = one(0, ob.XFACE), one(0, ob.YFACE)
+    bX.set_global(Z["flux_b0"], (0, 0))
+    bY.set_global(Z["flux_b1"], (0, 0))
+    op = ob.Op(lay, dx, 0.0, float(Z["flux_beta"]), ob.make_bc((0, 0), (0, 0)), ob.make_params(), one(), bX, bY, one(1), one(1), one(1), one(1))
+    phi = ghosted(lay, Z["flux_phi"])
+    flux = one(0, ob.XFACE if d == 0 else ob.YFACE)
+    ob.lib().orc_op_get_flux(op.h, flux.h, phi.h, d, ref, 1.0)
+    same(flux.fab(0)[0][0].copy(), f"flux_dir{d}_ref{ref}")
+
+
+def test_icemask_ec():
+    """HydroIBC::setup_iceMask_EC (src/HydroIBC.cpp:138-184): +1 / -1 where both cells agree, 0 across an ice edge and on the domain faces"""
+    lo, dom = [int(v) for v in Z["imec_lo"]], tuple(int(v) for v in Z["imec_domain"])
+    lay = ob.Layout(np.array([[lo[0], lo[1], lo[0] + NX - 1, lo[1] + NY - 1]], dtype=np.int32), dom, (0, 0))
+    mask = ob.Field(lay, 1, 1)
+    mask.fab(0)[0][0][...] = Z["imec_mask"]
+    mx, my = ob.Field(lay, 1, 0, ob.XFACE), ob.Field(lay, 1, 0, ob.YFACE)
+    ob.lib().orc_icemask_ec(mask.h, mx.h, my.h)
+    same(mx.fab(0)[0][0].copy(), "imec_dir0")
+    same(my.fab(0)[0][0].copy(), "imec_dir1")
