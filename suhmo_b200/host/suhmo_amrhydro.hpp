@@ -22,6 +22,7 @@
 #include <string>
 
 #include "suhmo_gpu.hpp"
+#include "suhmo_inputs.hpp"
 
 namespace sg {
 
@@ -56,7 +57,44 @@ struct TagVar {
   int cap, min_level;
 };
 
-class AmrHydro {
+// The run controls AmrHydro::initialize reads from the input file (src/AmrHydro.cpp:864-1122): mesh generation, tagging, time stepping,
+// the Picard tolerance, the moulins.  Plain host data, separate from the device state so that it can be filled and checked without a GPU
+// (tests/cpp/inputs_dump.cpp); AmrHydro derives from it, so the members read as in the reference (amrObject.m_max_level, ...).
+struct AmrHydroControls {
+  // regrid controls (AmrHydro.* keys)
+  Box m_domain0{{0, 0}, {-1, -1}};
+  int m_periodic[2] = {0, 0};
+  int m_max_level = 0, m_block_factor = 8, m_nesting_radius = 1, m_max_box_size = 64, m_tags_grow = 1, m_tags_grow_dir[2] = {0, 0}, m_n_regrids = 0;
+  double m_fill_ratio = 0.85;
+  std::vector<TagVar> m_tag_vars;
+  bool m_regrid = false;
+  // time stepping controls of run() (amr.fixed_dt, cfl, initial_cfl, max_dt_grow_factor, regrid_interval, plot_interval, plot_time_interval)
+  double m_fixed_dt = 0.0, m_cfl = 0.25, m_initial_cfl = 0.25, m_max_dt_grow = 1.5, m_stable_dt = 0.0, m_plot_time_interval = 1.0e12;
+  int m_regrid_interval = 10000000, m_plot_interval = 10000000, m_restart_step = 0;
+  double m_eps_PicardIte = 1.0e-6;              // solver.eps_PicardIte
+  std::vector<Moulin> m_moulins;
+
+  // from a parsed input.hydro: what the ParmParse section of AmrHydro::initialize sets (src/AmrHydro.cpp:892-1122), the tagging
+  // variables in file order (tag_variables / tagging_values_min / tagging_values_max / tagging_caps / tagging_mins) and the moulins
+  void setParams(const SuhmoInputs& in) {
+    m_domain0 = Box{{in.domainLoIndex[0], in.domainLoIndex[1]}, {in.domainLoIndex[0] + in.num_cells[0] - 1, in.domainLoIndex[1] + in.num_cells[1] - 1}};
+    m_periodic[0] = in.is_periodic[0]; m_periodic[1] = in.is_periodic[1];
+    m_max_level = in.max_level; m_block_factor = in.block_factor; m_nesting_radius = in.nesting_radius; m_max_box_size = in.max_box_size;
+    m_tags_grow = in.tags_grow; m_tags_grow_dir[0] = in.tags_grow_dir[0]; m_tags_grow_dir[1] = in.tags_grow_dir[1];
+    m_fill_ratio = in.fill_ratio;
+    if (in.regrid_interval > 0) m_regrid_interval = in.regrid_interval;
+    m_fixed_dt = in.fixed_dt > 0 ? in.fixed_dt : 0.0;
+    m_eps_PicardIte = in.eps_PicardIte;
+    m_tag_vars.clear();
+    for (size_t k = 0; k < in.tag_variables.size(); k++)
+      m_tag_vars.push_back(TagVar{in.tag_variables[k], in.tagging_values_min[k], in.tagging_values_max[k], in.tagging_caps[k], in.tagging_mins[k]});
+    m_moulins.clear();
+    for (int k = 0; k < in.n_moulins; k++)
+      m_moulins.push_back(Moulin{in.moulin_position[2 * k], in.moulin_position[2 * k + 1], in.moulin_flux[k], in.moulin_sigma[k]});
+  }
+};
+
+class AmrHydro : public AmrHydroControls {
  public:
   typedef std::unique_ptr<LevelData> Ptr;
   struct FluxPtr {                  // LevelData<FluxBox>: one LevelData per face direction
@@ -69,16 +107,6 @@ class AmrHydro {
                                                 // until a regrid replaces levels >= 1 with layouts this object owns:
   std::vector<std::unique_ptr<DisjointBoxLayout>> m_ownedGrids;
   double m_coarsestDx[2];
-  // regrid controls (amr.* keys, src/AmrHydro.cpp:892-1122)
-  Box m_domain0{{0, 0}, {-1, -1}};
-  int m_periodic[2] = {0, 0};
-  int m_max_level = 0, m_block_factor = 8, m_nesting_radius = 1, m_max_box_size = 64, m_tags_grow = 1, m_tags_grow_dir[2] = {0, 0}, m_n_regrids = 0;
-  double m_fill_ratio = 0.85;
-  std::vector<TagVar> m_tag_vars;
-  bool m_regrid = false;
-  // time stepping controls of run() (amr.fixed_dt, cfl, initial_cfl, max_dt_grow_factor, regrid_interval, plot_interval, plot_time_interval)
-  double m_fixed_dt = 0.0, m_cfl = 0.25, m_initial_cfl = 0.25, m_max_dt_grow = 1.5, m_stable_dt = 0.0, m_plot_time_interval = 1.0e12;
-  int m_regrid_interval = 10000000, m_plot_interval = 10000000, m_restart_step = 0;
   HydroIBC* m_IBCPtr = nullptr;                 // setIBC: what regrid() re-initialises a redefined level with
   TimeStepReport m_lastReport;                  // of the most recent timeStepFAS
   std::vector<std::array<double, 2>> m_amrDx;
@@ -88,8 +116,6 @@ class AmrHydro {
   bool m_use_mask_gradients = false, m_use_ImplDiff = false;
   int m_cur_step = 0;
   double m_time = 0.0;
-  double m_eps_PicardIte = 1.0e-6;              // solver.eps_PicardIte
-  std::vector<Moulin> m_moulins;
 
   // persistent state, one entry per level (names of src/AmrHydro.H:466-497)
   std::vector<Ptr> m_head, m_gapheight, m_old_head, m_old_gapheight, m_gradhead, m_Pw, m_Re, m_meltRate, m_magVel, m_bedelevation,
@@ -112,6 +138,9 @@ class AmrHydro {
     for (size_t l = 0; l < grids.size(); l++) levelSetup((int)l);
     defineOperators();
   }
+  // the same from a parsed input.hydro: dx, suhmo.* / solver.* / bc.* blocks and the run controls (setParams)
+  AmrHydro(Context& ctx, const std::vector<DisjointBoxLayout*>& grids, const SuhmoInputs& in)
+      : AmrHydro(ctx, grids, std::array<double, 2>{in.dx(0), in.dx(1)}.data(), in.headParams(), in.bc, in.picardParams()) { setParams(in); }
   // solver and operators go before the factory and the fields they were defined on
   ~AmrHydro() { dropOperators(); }
 

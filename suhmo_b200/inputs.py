@@ -84,6 +84,19 @@ def read(path_or_text):
                    "tag_variables": g("AmrHydro.tag_variables", str, ntag) if ntag else [],
                    "tagging_values_min": g("AmrHydro.tagging_values_min", float, ntag) if ntag else [],
                    "tagging_values_max": g("AmrHydro.tagging_values_max", float, ntag) if ntag else []}
+    # the run controls of the driver class (sg::AmrHydroControls::setParams in suhmo_b200/host/suhmo_amrhydro.hpp; src/AmrHydro.cpp:892-1122)
+    nc, lo = g("AmrHydro.num_cells", int, 2), q("AmrHydro.domainLoIndex", [0, 0], int, 2)
+    ri, fdt = q("AmrHydro.regrid_interval", -1, int), out["mesh"]["fixed_dt"]
+    caps = g("AmrHydro.tagging_caps", int, ntag) if ntag else []
+    mins = g("AmrHydro.tagging_mins", int, ntag) if ntag else []
+    m = out["mesh"]
+    out["controls"] = {"domain0": [lo[0], lo[1], lo[0] + nc[0] - 1, lo[1] + nc[1] - 1], "periodic": g("AmrHydro.is_periodic", int, 2),
+                       "max_level": ml, "block_factor": m["block_factor"], "nesting_radius": m["nesting_radius"], "max_box_size": mbs,
+                       "tags_grow": m["tags_grow"], "tags_grow_dir": m["tags_grow_dir"], "fill_ratio": m["fill_ratio"],
+                       "regrid_interval": ri if ri > 0 else 10000000, "fixed_dt": fdt if fdt > 0 else 0.0,
+                       "eps_PicardIte": q("solver.eps_PicardIte", 1.0e-6),
+                       "tag_vars": [[m["tag_variables"][k], m["tagging_values_min"][k], m["tagging_values_max"][k], caps[k], mins[k]] for k in range(ntag)],
+                       "moulins": len(moulins)}
     out["slope"], out["H"], out["gap_init"] = g("suhmo.slope"), g("suhmo.IceHeight"), g("suhmo.GapInit")
     out["valley_gamma"] = q("valleypp.gamma", 0.05)
     return out

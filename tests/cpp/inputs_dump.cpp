@@ -2,7 +2,7 @@
 // object (compared with the Python twin suhmo_b200/inputs.py by tests/test_inputs.py).  Host only: no GPU, no library call.
 #include <cstdio>
 
-#include "../../suhmo_b200/host/suhmo_inputs.hpp"
+#include "../../suhmo_b200/host/suhmo_amrhydro.hpp"   // pulls in suhmo_inputs.hpp; only AmrHydroControls (host data) is used here
 
 int main(int argc, char** argv) {
   if (argc < 2) { std::fprintf(stderr, "usage: inputs_dump input.hydro [cur_step]\n"); return 2; }
@@ -42,6 +42,19 @@ int main(int argc, char** argv) {
   for (size_t k = 0; k < in.tagging_values_min.size(); k++) std::printf("%s%.17g", k ? ", " : "", in.tagging_values_min[k]);
   std::printf("], \"tagging_values_max\": [");
   for (size_t k = 0; k < in.tagging_values_max.size(); k++) std::printf("%s%.17g", k ? ", " : "", in.tagging_values_max[k]);
-  std::printf("]}}\n");
+  std::printf("]}, ");
+  // the run controls of the C++ driver class as AmrHydroControls::setParams fills them from the same file
+  sg::AmrHydroControls c;
+  c.setParams(in);
+  std::printf("\"controls\": {\"domain0\": [%d, %d, %d, %d], \"periodic\": [%d, %d], \"max_level\": %d, \"block_factor\": %d, \"nesting_radius\": %d, "
+              "\"max_box_size\": %d, \"tags_grow\": %d, \"tags_grow_dir\": [%d, %d], \"fill_ratio\": %.17g, \"regrid_interval\": %d, \"fixed_dt\": %.17g, "
+              "\"eps_PicardIte\": %.17g, \"tag_vars\": [",
+              c.m_domain0.lo[0], c.m_domain0.lo[1], c.m_domain0.hi[0], c.m_domain0.hi[1], c.m_periodic[0], c.m_periodic[1], c.m_max_level, c.m_block_factor,
+              c.m_nesting_radius, c.m_max_box_size, c.m_tags_grow, c.m_tags_grow_dir[0], c.m_tags_grow_dir[1], c.m_fill_ratio, c.m_regrid_interval,
+              c.m_fixed_dt, c.m_eps_PicardIte);
+  for (size_t k = 0; k < c.m_tag_vars.size(); k++)
+    std::printf("%s[\"%s\", %.17g, %.17g, %d, %d]", k ? ", " : "", c.m_tag_vars[k].var.c_str(), c.m_tag_vars[k].val_min, c.m_tag_vars[k].val_max,
+                c.m_tag_vars[k].cap, c.m_tag_vars[k].min_level);
+  std::printf("], \"moulins\": %zu}}\n", c.m_moulins.size());
   return 0;
 }

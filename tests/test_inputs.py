@@ -29,7 +29,7 @@ def cpp_read(exe, path, step):
 
 def agree(cpp, py, step):
     head, gap = inputs.solver_blocks(step)
-    for k in ("problem_type", "domain_size", "num_cells", "dx", "is_periodic", "bc", "params", "picard", "moulins", "mesh"):
+    for k in ("problem_type", "domain_size", "num_cells", "dx", "is_periodic", "bc", "params", "picard", "moulins", "mesh", "controls"):
         assert cpp[k] == py[k], (k, cpp[k], py[k])
     assert cpp["head_solver"] == head and cpp["gap_solver"] == gap
 
@@ -43,6 +43,9 @@ def test_sample_input(exe):
     assert py["picard"]["use_ImplDiff"] == 0            # the later definition wins
     assert py["mesh"]["ref_ratios"] == [2, 2] and py["mesh"]["max_base_grid_size"] == 16   # defaults to max_box_size
     assert len(py["moulins"]) == 2 and py["moulins"][1] == [40.5, 4.5, 12.0, 2.0]
+    # what sg::AmrHydroControls::setParams hands the C++ driver class (regrid / run controls, tagging variables in file order)
+    assert py["controls"]["tag_vars"] == [["meltingRate", 0.02, 1.0e8, 6, 0]] and py["controls"]["domain0"] == [0, 0, 31, 7]
+    assert py["controls"]["fixed_dt"] == 3600.0 and py["controls"]["regrid_interval"] == 10000000 and py["controls"]["eps_PicardIte"] == 1.0e-4
     cfg = inputs.to_config(py)
     c1 = syn.config("C1", 1)
     for k in ("ibc", "nx", "ny", "domain_size", "periodic", "bc_lo", "bc_hi", "max_box_size", "block_factor", "A", "omega", "nu", "H", "slope"):
