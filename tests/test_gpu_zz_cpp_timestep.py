@@ -1,4 +1,4 @@
-"""AmrHydro::timeStepFAS as C++ host code (suhmo_b200/host/suhmo_amrhydro.hpp) on the GPU against the CPU oracle's independent
+"""(Named to run last in the GPU suite: it compiles a host program.)  AmrHydro::timeStepFAS as C++ host code (suhmo_b200/host/suhmo_amrhydro.hpp) on the GPU against the CPU oracle's independent
 restatement (oracle/picard_amr.py): the oracle runs whole time steps here and writes inputs and outcomes to a fixture
 (tests/amr_timestep_fixture.py); the C++ program tests/cpp/timestep_host.cpp replays it on the device and asserts the same Picard
 iteration counts, V-cycle counts, convergence measures and BIT-identical head and gap height.  Without a GPU: the program compiles
