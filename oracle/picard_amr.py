@@ -3,7 +3,7 @@
 Written from src/AmrHydro.cpp:2255-3620 top to bottom, one statement of the reference per call into the oracle library, for any
 number of levels (one level included).  It deliberately shares no code with the product's orchestration (suhmo_b200/timestep.py):
 the parity tests run the two against each other field by field.  Only the explicit gap-height update is restated for more than
-one level (every reference input with solver.use_ImplDiff is single-level).
+one level (the implicit solve of SolveForGap_nl on an AMR hierarchy -- asked for by exec/AMR_multiMoulins/run_C_*lev -- is not restated).
 
 State: per level l a dict S[l] of oracle fields
   persistent   head B Pi zb mask MV BH BL mR Pw Re MS gradH(2 comps)             (1 ghost cell)

@@ -4,7 +4,8 @@ Host orchestration over the C ABI, as in the reference (the time and Picard loop
 ghost fills (PiecewiseLinearFillPatch, exchange, boundary conditions), centring changes, gradients with coarse-fine interpolation,
 Re, water flux, melt rate, RHS_h, aCoeff_bCoeff, the composite FAS head solve, average-down; then the explicit gap-height update.
 No field leaves the device between the head solves.  The single-level Picard step with the implicit gap solve lives in
-suhmo_b200/timestep.py; the implicit solve on more than one level is not built (no reference input uses it).
+suhmo_b200/timestep.py; the implicit solve on more than one level is not built, although reference inputs ask for it (exec/AMR_multiMoulins/run_C_*lev and
+exec/0_convergence_channelized/*_base* set solver.use_ImplDiff = true with max_level > 0): see DESIGN.md section 9.
 """
 import ctypes as C
 
