@@ -422,7 +422,7 @@ int sg_set_tuning(sg_ctx* ctx, int key, int value);
    BC = FixedNeumBCFill :404-436) and a linear, correction-form AMRMultiGrid with a RelaxSolver bottom (:617-628).  L(b) =
    alpha*a*b - beta*div(D grad b).  sg_gap_solver is that factory + solver pair.  One AMR level only, one patch per GPU;
    num_levels > 1 returns SG_ERR_UNSUPPORTED (the multi-level AMRMultiGrid is not built, although exec/AMR_multiMoulins/run_C_*lev and
-   exec/0_convergence_channelized/*_base* set use_ImplDiff with max_level > 0).  Stock Chombo is absent from the
+   the _base runs of exec/0_convergence_channelized set use_ImplDiff with max_level > 0).  Stock Chombo is absent from the
    SUHMO tree: the restatement is from recollection of public Chombo 3.2 (parity unpinned). */
 typedef struct sg_gap_solver sg_gap_solver;
 /* VCAMRPoissonOp2Factory::define(domain0, grids, refRatio, dx0, bc, alpha, aCoef, beta, bCoef) + AMRMultiGrid::define */

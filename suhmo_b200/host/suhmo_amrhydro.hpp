@@ -10,7 +10,7 @@
 //
 // The explicit gap-height update runs on any number of levels; the implicit one (solver.use_ImplDiff) on one level only: the stock
 // AMRMultiGrid of SolveForGap_nl is not restated for more than one AMR level and the C ABI answers SG_ERR_UNSUPPORTED there, although
-// reference inputs ask for it (exec/AMR_multiMoulins/run_C_*lev, exec/0_convergence_channelized/*_base*: use_ImplDiff with max_level > 0).
+// reference inputs ask for it (exec/AMR_multiMoulins/run_C_*lev, the _base runs of exec/0_convergence_channelized: use_ImplDiff with max_level > 0).
 //
 // Checked on the GPU by tests/cpp/timestep_host.cpp against the CPU oracle's independent restatement of the same functions
 // (oracle/picard_amr.py, oracle/br_regrid.py): Picard iteration counts, V-cycle counts, convergence measures, head and gap height bit
