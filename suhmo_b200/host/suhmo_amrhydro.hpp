@@ -74,6 +74,12 @@ struct AmrHydroControls {
   int m_regrid_interval = 10000000, m_plot_interval = 10000000, m_restart_step = 0;
   double m_eps_PicardIte = 1.0e-6;              // solver.eps_PicardIte
   std::vector<Moulin> m_moulins;
+  // solver.use_ImplDiff on MORE than one level: the reference runs the stock linear AMRMultiGrid there, which this library does not
+  // restate (SG_ERR_UNSUPPORTED).  With this switch the same linear system -- (a - dt DiffFactor div(D grad)) b = rhs, a = 1, zero
+  // Neumann sides -- goes through the FAS solver of the head equation with the nonlinear term switched off instead
+  // (SolveForGap_FAS below).  EXPERIMENTAL: checked on the CPU oracle only (tests/test_oracle_gap_hierarchy.py: identical to the linear
+  // solver on one level, residual to zero on three), not yet run on a GPU; off by default, the step then aborts with the library's message.
+  bool m_gapHierarchyViaFAS = false;
 
   // from a parsed input.hydro: what the ParmParse section of AmrHydro::initialize sets (src/AmrHydro.cpp:892-1122), the tagging
   // variables in file order (tag_variables / tagging_values_min / tagging_values_max / tagging_caps / tagging_mins) and the moulins
@@ -129,6 +135,9 @@ class AmrHydro : public AmrHydroControls {
   std::unique_ptr<VCAMRNonLinearPoissonOpFactory> m_opFactory;
   std::vector<std::unique_ptr<VCAMRNonLinearPoissonOp>> m_ops;
   std::unique_ptr<AMRFASMultiGrid> m_amrSolver;
+  std::unique_ptr<VCAMRNonLinearPoissonOpFactory> m_gapFactory;   // SolveForGap_FAS: alpha = 1, aCoef = 1, beta = dt DiffFactor, bCoef = Dcoef
+  std::unique_ptr<AMRFASMultiGrid> m_gapSolver;
+  double m_gapFactoryBeta = 0.0;
 
   AmrHydro(Context& ctx, const std::vector<DisjointBoxLayout*>& grids, const double coarsestDx[2], const sg_params& prm, const sg_bc& bc,
            const sg_picard_params& suhmoParm)
@@ -181,7 +190,7 @@ class AmrHydro : public AmrHydroControls {
                         raw(m_overburdenpress), raw(m_bedelevation), raw(m_iceMask));
     for (size_t l = 0; l < n; l++) m_ops.emplace_back(m_opFactory->AMRnewOp((int)l));
   }
-  void dropOperators() { m_amrSolver.reset(); m_ops.clear(); m_opFactory.reset(); }
+  void dropOperators() { m_gapSolver.reset(); m_gapFactory.reset(); m_amrSolver.reset(); m_ops.clear(); m_opFactory.reset(); }
 
   int finestLevel() const { return (int)m_amrGrids.size() - 1; }
   static std::vector<LevelData*> raw(std::vector<Ptr>& v) {
@@ -384,6 +393,45 @@ class AmrHydro : public AmrHydroControls {
     return new_finest_level;
   }
 
+  // The implicit gap-height equation on the whole hierarchy through the FAS solver with NL = 0 (see m_gapHierarchyViaFAS): the
+  // operator L(b) = a b - beta div(D grad b) of SolveForGap_nl (src/AmrHydro.cpp:594-662) with its solver constants (pre/post 2,
+  // bottom 4, eps 1e-7, hang 1e-6, m_imin 10 while m_cur_step < 50, m_iterMin 2) and FixedNeumBCFill's zero-gradient sides (:404-436).
+  // Not the reference's iteration sequence (correction-form AMRMultiGrid with a RelaxSolver bottom): the same discrete system, so
+  // agreement with the reference is to the solver tolerance, not bit for bit.  Returns the number of V-cycles.
+  int SolveForGap_FAS(double a_dt) {
+    const size_t n = m_amrGrids.size();
+    const double beta = a_dt * m_suhmoParm.DiffFactor;
+    if (!m_gapFactory || beta != m_gapFactoryBeta) {
+      m_gapSolver.reset();
+      std::vector<LevelData*> dx, dy;
+      for (size_t l = 0; l < n; l++) { dx.push_back(a_Dcoef[l].d[0].get()); dy.push_back(a_Dcoef[l].d[1].get()); }
+      sg_params lin = m_prm;
+      lin.use_NL = 0; lin.bcoeff_otf = 0;
+      const sg_bc neum = {{1, 1}, {1, 1}, {0.0, 0.0}, {0.0, 0.0}};
+      m_gapFactory.reset(new VCAMRNonLinearPoissonOpFactory);
+      m_gapFactory->define(m_ctx, m_amrGrids, std::vector<int>(n > 0 ? n - 1 : 0, 2), m_coarsestDx, neum, 1.0, raw(aCoef_GH), beta, dx, dy, lin,
+                           raw(m_gapheight), raw(m_overburdenpress), raw(m_bedelevation), raw(m_iceMask));
+      m_gapFactoryBeta = beta;
+    }
+    if (!m_gapSolver) {
+      m_gapSolver.reset(new AMRFASMultiGrid);
+      m_gapSolver->define(*m_gapFactory, (int)n);
+    } else {
+      m_gapSolver->refresh();
+    }
+    m_gapSolver->setSolverParameters(2, 2, 4, 1, 100, 1.0e-7, 1.0e-6, 1.0e-7);
+    m_gapSolver->m_imin = m_cur_step < 50 ? 10 : 5;
+    m_gapSolver->m_iterMin = 2;
+    m_gapSolver->params.fixed_cycles = 0;
+    std::vector<double> hist;
+    const int it = m_gapSolver->solve(raw(a_gh_curr), raw(RHS_b), finestLevel(), 0, nullptr, &hist);
+    if (it >= 100 || !(hist.back() <= hist.front())) {
+      std::fprintf(stderr, "suhmo_gpu: SolveForGap_FAS did not converge (%d V-cycles, residual %g -> %g)\n", it, hist.front(), hist.back());
+      std::abort();
+    }
+    return it;
+  }
+
   // ---- timeStepFAS, in the reference's four parts -----------------------------------------------------------------------------
   // I (src/AmrHydro.cpp:2356-2445): consistent head and gap height, old-time copies, edge-centred ice mask
   void beginStep() {
@@ -487,10 +535,14 @@ class AmrHydro : public AmrHydroControls {
     if (m_use_ImplDiff) {
       std::vector<LevelData*> dx, dy;
       for (size_t l = 0; l < m_amrGrids.size(); l++) { dx.push_back(a_Dcoef[l].d[0].get()); dy.push_back(a_Dcoef[l].d[1].get()); }
-      gapCycles = sg::SolveForGap_nl(m_ctx, m_amrGrids, raw(aCoef_GH), dx, dy, {}, m_amrDx[0].data(), raw(a_gh_curr), raw(RHS_b), dt,
-                                     m_suhmoParm.DiffFactor, m_cur_step);
+      if (finestLevel() > 0 && m_gapHierarchyViaFAS)
+        gapCycles = SolveForGap_FAS(dt);
+      else   // one level: the stock solver's restatement; more levels: the library's SG_ERR_UNSUPPORTED message and abort
+        gapCycles = sg::SolveForGap_nl(m_ctx, m_amrGrids, raw(aCoef_GH), dx, dy, {}, m_amrDx[0].data(), raw(a_gh_curr), raw(RHS_b), dt,
+                                       m_suhmoParm.DiffFactor, m_cur_step);
       for (int lev = 0; lev <= finestLevel(); lev++) {
         m_ops[lev]->assignLocal(*m_gapheight[lev], *a_gh_curr[lev]);
+        if (lev > 0) fillInterp(lev, m_gapheight);   // :3442-3451
         m_gapheight[lev]->exchange();
         CopyGhostCells(*m_gapheight[lev]);
       }
